@@ -1,0 +1,542 @@
+// batch.cu — pools, stream leases, Arrow C Data Interface import/export (see batch.h).
+#include <algorithm>
+#include <atomic>
+#include <map>
+
+#include "batch.h"
+
+namespace ark {
+
+// ---- error slot + launch accounting ---------------------------------------------------------------
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const std::string& last_error_ref() { return g_last_error; }
+
+static std::atomic<int64_t> g_launches{0};
+static std::atomic<int> g_timing{0};
+struct TimingEntry { double ms = 0; int64_t n = 0; };
+static std::mutex g_timing_mu;
+static std::map<std::string, TimingEntry> g_timing_map;
+
+void note_launch(const char*) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int64_t launch_count() { return g_launches.load(); }
+void timing_enable(int on) { g_timing.store(on); }
+void timing_reset() { std::lock_guard<std::mutex> l(g_timing_mu); g_timing_map.clear(); }
+bool timing_get(const char* name, double* ms, int64_t* n) {
+  std::lock_guard<std::mutex> l(g_timing_mu);
+  auto it = g_timing_map.find(name);
+  if (it == g_timing_map.end()) { *ms = 0; *n = 0; return false; }
+  *ms = it->second.ms; *n = it->second.n; return true;
+}
+
+KernelTimer::KernelTimer(const char* n, cudaStream_t s) : name(n), stream(s) {
+  note_launch(n);
+  if (g_timing.load(std::memory_order_relaxed)) {
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, stream);
+  }
+}
+KernelTimer::~KernelTimer() {
+  if (e0) {
+    cudaEventRecord(e1, stream);
+    cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    std::lock_guard<std::mutex> l(g_timing_mu);
+    auto& e = g_timing_map[name]; e.ms += ms; e.n += 1;
+  }
+}
+
+// ---- pools ------------------------------------------------------------------------------------------
+BlockPool::~BlockPool() {}  // process teardown: the driver reclaims; freeing here races CUDA shutdown
+
+void* BlockPool::alloc(size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  size_t want = (size_t)round_up((int64_t)bytes, kind_ == Device ? 512 : 4096);
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    auto it = std::lower_bound(free_.begin(), free_.end(), want, [](const Block& b, size_t w) { return b.size < w; });
+    if (it != free_.end() && it->size <= std::max(want + (want >> 2), want + (1u << 20))) {
+      Block b = *it; free_.erase(it); live_.push_back(b); return b.p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = kind_ == Device ? cudaMalloc(&p, want) : cudaHostAlloc(&p, want, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    trim();
+    e = kind_ == Device ? cudaMalloc(&p, want) : cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      fail(ARK_ERR_CUDA, std::string(kind_ == Device ? "device" : "pinned host") + " allocation of " +
+                             std::to_string(want) + " bytes failed: " + cudaGetErrorString(e));
+    }
+  }
+  std::lock_guard<std::mutex> l(mu_);
+  live_.push_back({p, want}); reserved_ += want;
+  return p;
+}
+
+void BlockPool::free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> l(mu_);
+  for (size_t i = 0; i < live_.size(); ++i) {
+    if (live_[i].p == p) {
+      Block b = live_[i];
+      live_[i] = live_.back(); live_.pop_back();
+      auto it = std::lower_bound(free_.begin(), free_.end(), b.size, [](const Block& x, size_t w) { return x.size < w; });
+      free_.insert(it, b);
+      return;
+    }
+  }
+}
+
+void BlockPool::trim() {
+  std::vector<Block> drop;
+  { std::lock_guard<std::mutex> l(mu_); drop.swap(free_); for (auto& b : drop) reserved_ -= b.size; }
+  for (auto& b : drop) { if (kind_ == Device) cudaFree(b.p); else cudaFreeHost(b.p); }
+}
+
+BlockPool& device_pool() { static BlockPool* p = new BlockPool(BlockPool::Device); return *p; }
+BlockPool& pinned_pool() { static BlockPool* p = new BlockPool(BlockPool::Pinned); return *p; }
+
+BufferPtr device_alloc(size_t bytes) {
+  void* p = device_pool().alloc(bytes);
+  return BufferPtr(p, [](void* q) { device_pool().free(q); });
+}
+BufferPtr pinned_alloc(size_t bytes) {
+  void* p = pinned_pool().alloc(bytes);
+  return BufferPtr(p, [](void* q) { pinned_pool().free(q); });
+}
+
+// ---- streams ------------------------------------------------------------------------------------------
+static std::mutex g_stream_mu;
+static std::vector<cudaStream_t> g_streams;
+StreamLease::StreamLease() {
+  {
+    std::lock_guard<std::mutex> l(g_stream_mu);
+    if (!g_streams.empty()) { s = g_streams.back(); g_streams.pop_back(); return; }
+  }
+  ARK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+}
+StreamLease::~StreamLease() {
+  std::lock_guard<std::mutex> l(g_stream_mu);
+  g_streams.push_back(s);
+}
+
+// ---- schema helpers -------------------------------------------------------------------------------------
+static DType dtype_from_format(const char* f) {
+  if (!f) return DType::Null;
+  if (!strcmp(f, "l")) return DType::Int64;
+  if (!strcmp(f, "g")) return DType::Float64;
+  if (!strcmp(f, "u")) return DType::Utf8;
+  if (!strcmp(f, "z")) return DType::Binary;
+  if (!strcmp(f, "b")) return DType::Bool;
+  return DType::Null;
+}
+
+std::vector<Field> schema_fields(const ArrowSchema* s) {
+  if (!s || !s->format || strcmp(s->format, "+s") != 0)
+    fail(ARK_ERR_PROCESS, "Registration failed: expected a struct (RecordBatch) schema");
+  std::vector<Field> out;
+  for (int64_t i = 0; i < s->n_children; ++i) {
+    const ArrowSchema* c = s->children[i];
+    Field f;
+    f.name = c->name ? c->name : "";
+    f.format = c->format ? c->format : "";
+    f.type = dtype_from_format(c->format);
+    f.nullable = (c->flags & ARROW_FLAG_NULLABLE) != 0;
+    out.push_back(f);
+  }
+  return out;
+}
+
+std::string schema_fingerprint(const std::vector<Field>& f) {
+  std::string s;
+  for (auto& x : f) { s += x.name; s += '\x1f'; s += x.format; s += x.nullable ? "?" : "!"; s += '\x1e'; }
+  return s;
+}
+
+static bool format_supported(const std::string& f) {
+  return f == "l" || f == "g" || f == "u" || f == "z" || f == "b";
+}
+
+// ---- import ---------------------------------------------------------------------------------------------
+static void h2d(void* dst, const void* src, size_t n, cudaStream_t s, int64_t* acc) {
+  if (n == 0) return;
+  ARK_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s));
+  if (acc) *acc += (int64_t)n;
+}
+
+Batch import_host(const ArrowArray* arr, const ArrowSchema* schema, const std::vector<bool>* needed,
+                  cudaStream_t stream, int64_t* h2d_bytes) {
+  std::vector<Field> fields = schema_fields(schema);
+  if (arr->n_children != (int64_t)fields.size())
+    fail(ARK_ERR_PROCESS, "Registration failed: array/schema child count mismatch");
+  if (arr->offset != 0) fail(ARK_ERR_UNSUPPORTED, "struct array with non-zero offset");
+  Batch b;
+  b.num_rows = arr->length;
+  for (size_t i = 0; i < fields.size(); ++i) {
+    Column c;
+    c.field = fields[i];
+    const ArrowArray* a = arr->children[i];
+    c.length = a->length;
+    bool want = (!needed || (*needed)[i]) && format_supported(fields[i].format);
+    if (!want) { c.present = false; b.cols.push_back(std::move(c)); continue; }
+    if (a->length != arr->length) fail(ARK_ERR_PROCESS, "Registration failed: column length mismatch");
+    int64_t off = a->offset, n = a->length;
+    c.null_count = a->null_count;
+    if (a->buffers[0] != nullptr && a->null_count != 0 && n > 0) {
+      int64_t byte0 = off >> 3, byte1 = (off + n + 7) >> 3;
+      BufferPtr v = device_alloc((size_t)(byte1 - byte0));
+      h2d(v.get(), (const uint8_t*)a->buffers[0] + byte0, (size_t)(byte1 - byte0), stream, h2d_bytes);
+      c.validity = (const uint8_t*)v.get();
+      c.validity_bit0 = (int32_t)(off & 7);
+      c.null_count = a->null_count;  // may be -1 (unknown): treated as "has nulls"
+      c.owners.push_back(v);
+    } else {
+      c.null_count = 0;
+    }
+    switch (c.field.type) {
+      case DType::Int64:
+      case DType::Float64: {
+        BufferPtr d = device_alloc((size_t)n * 8);
+        if (n) h2d(d.get(), (const uint8_t*)a->buffers[1] + off * 8, (size_t)n * 8, stream, h2d_bytes);
+        c.data = (const uint8_t*)d.get(); c.data_bytes = n * 8; c.owners.push_back(d);
+        break;
+      }
+      case DType::Bool: {
+        int64_t byte0 = off >> 3, byte1 = (off + n + 7) >> 3;
+        BufferPtr d = device_alloc((size_t)(byte1 - byte0));
+        if (n) h2d(d.get(), (const uint8_t*)a->buffers[1] + byte0, (size_t)(byte1 - byte0), stream, h2d_bytes);
+        c.data = (const uint8_t*)d.get(); c.data_bit0 = (int32_t)(off & 7); c.data_bytes = byte1 - byte0;
+        c.owners.push_back(d);
+        break;
+      }
+      case DType::Utf8:
+      case DType::Binary: {
+        BufferPtr o = device_alloc((size_t)(n + 1) * 4);
+        int32_t first = 0, last = 0;
+        if (a->buffers[1] != nullptr) {
+          const int32_t* ho = (const int32_t*)a->buffers[1] + off;
+          first = ho[0]; last = ho[n];
+          h2d(o.get(), ho, (size_t)(n + 1) * 4, stream, h2d_bytes);
+        } else {
+          ARK_CUDA(cudaMemsetAsync(o.get(), 0, (size_t)(n + 1) * 4, stream));
+        }
+        BufferPtr d = device_alloc((size_t)(last - first));
+        if (last > first) h2d(d.get(), (const uint8_t*)a->buffers[2] + first, (size_t)(last - first), stream, h2d_bytes);
+        c.offsets = (const int32_t*)o.get();
+        c.data = (const uint8_t*)d.get() - first;
+        c.data_bytes = last - first; c.first_offset = first;
+        c.owners.push_back(o); c.owners.push_back(d);
+        break;
+      }
+      default: break;
+    }
+    b.cols.push_back(std::move(c));
+  }
+  return b;
+}
+
+__global__ void gather_extents_kernel(const int32_t* const* offs, const int64_t* lens, int32_t* out, int n) {
+  int i = threadIdx.x;
+  if (i < n) { out[2 * i] = offs[i][0]; out[2 * i + 1] = offs[i][lens[i]]; }
+}
+
+Batch import_device(const ArrowDeviceArray* darr, const ArrowSchema* schema, const std::vector<bool>* needed,
+                    BufferPtr keep) {
+  if (darr->device_type != ARROW_DEVICE_CUDA && darr->device_type != ARROW_DEVICE_CUDA_HOST)
+    fail(ARK_ERR_PROCESS, "Registration failed: ArrowDeviceArray is not on a CUDA device");
+  const ArrowArray* arr = &darr->array;
+  if (darr->sync_event) ARK_CUDA(cudaEventSynchronize(*(cudaEvent_t*)darr->sync_event));
+  std::vector<Field> fields = schema_fields(schema);
+  if (arr->n_children != (int64_t)fields.size())
+    fail(ARK_ERR_PROCESS, "Registration failed: array/schema child count mismatch");
+  if (arr->offset != 0) fail(ARK_ERR_UNSUPPORTED, "struct array with non-zero offset");
+  Batch b;
+  b.num_rows = arr->length;
+  std::vector<int> varlen_idx;
+  for (size_t i = 0; i < fields.size(); ++i) {
+    Column c;
+    c.field = fields[i];
+    const ArrowArray* a = arr->children[i];
+    c.length = a->length;
+    bool want = (!needed || (*needed)[i]) && format_supported(fields[i].format);
+    if (!want) { c.present = false; b.cols.push_back(std::move(c)); continue; }
+    if (a->length != arr->length) fail(ARK_ERR_PROCESS, "Registration failed: column length mismatch");
+    int64_t off = a->offset, n = a->length;
+    if (keep) c.owners.push_back(keep);
+    if (a->buffers[0] != nullptr && a->null_count != 0) {
+      c.validity = (const uint8_t*)a->buffers[0] + (off >> 3);
+      c.validity_bit0 = (int32_t)(off & 7);
+      c.null_count = a->null_count;
+    } else c.null_count = 0;
+    switch (c.field.type) {
+      case DType::Int64: case DType::Float64:
+        c.data = (const uint8_t*)a->buffers[1] + off * 8; c.data_bytes = n * 8; break;
+      case DType::Bool:
+        c.data = (const uint8_t*)a->buffers[1] + (off >> 3); c.data_bit0 = (int32_t)(off & 7);
+        c.data_bytes = (n + 7) / 8 + 1; break;
+      case DType::Utf8: case DType::Binary:
+        c.offsets = (const int32_t*)a->buffers[1] + off;
+        c.data = (const uint8_t*)a->buffers[2];
+        c.data_bytes = -1;  // unknown until resolve_varlen_extents()
+        break;
+      default: break;
+    }
+    b.cols.push_back(std::move(c));
+  }
+  return b;
+}
+
+// Fetch offsets[0] / offsets[n] of device-resident var-len columns whose extent is still unknown.
+void resolve_varlen_extents(Batch& b, const std::vector<int>& col_idx, cudaStream_t stream) {
+  std::vector<int> todo;
+  for (int i : col_idx) {
+    Column& c = b.cols[i];
+    if (c.present && (c.field.type == DType::Utf8 || c.field.type == DType::Binary) && c.data_bytes < 0) {
+      if (c.length == 0 || c.offsets == nullptr) { c.data_bytes = 0; c.first_offset = 0; }
+      else todo.push_back(i);
+    }
+  }
+  if (todo.empty()) return;
+  int n = (int)todo.size();
+  if (n > 32) fail(ARK_ERR_UNSUPPORTED, "more than 32 var-len columns");
+  BufferPtr hp = pinned_alloc(1024);
+  BufferPtr dp = device_alloc(1024);
+  // layout (pinned & device): [0,256) pointers, [256,512) lens, [512,768) out
+  const int32_t** hptr = (const int32_t**)hp.get();
+  int64_t* hlen = (int64_t*)((char*)hp.get() + 256);
+  int32_t* hout = (int32_t*)((char*)hp.get() + 512);
+  for (int k = 0; k < n; ++k) { hptr[k] = b.cols[todo[k]].offsets; hlen[k] = b.cols[todo[k]].length; }
+  ARK_CUDA(cudaMemcpyAsync(dp.get(), hp.get(), 512, cudaMemcpyHostToDevice, stream));
+  {
+    KernelTimer t("gather_extents_kernel", stream);
+    gather_extents_kernel<<<1, 32, 0, stream>>>((const int32_t* const*)dp.get(), (const int64_t*)((char*)dp.get() + 256),
+                                               (int32_t*)((char*)dp.get() + 512), n);
+  }
+  ARK_CUDA(cudaMemcpyAsync(hout, (char*)dp.get() + 512, 256, cudaMemcpyDeviceToHost, stream));
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  for (int k = 0; k < n; ++k) {
+    Column& c = b.cols[todo[k]];
+    c.first_offset = hout[2 * k];
+    c.data_bytes = (int64_t)hout[2 * k + 1] - hout[2 * k];
+  }
+}
+
+// ---- export ---------------------------------------------------------------------------------------------
+namespace {
+
+struct SchemaPriv {
+  std::string format, name;
+  std::vector<ArrowSchema> child_storage;
+  std::vector<ArrowSchema*> child_ptrs;
+};
+void release_schema(ArrowSchema* s) {
+  if (!s || !s->release) return;
+  auto* p = (SchemaPriv*)s->private_data;
+  for (auto& c : p->child_storage) if (c.release) c.release(&c);
+  delete p;
+  s->release = nullptr;
+}
+void fill_schema(ArrowSchema* s, const char* fmt, const std::string& name, bool nullable) {
+  auto* p = new SchemaPriv();
+  p->format = fmt; p->name = name;
+  memset(s, 0, sizeof(*s));
+  s->format = p->format.c_str(); s->name = p->name.c_str(); s->metadata = nullptr;
+  s->flags = nullable ? ARROW_FLAG_NULLABLE : 0;
+  s->release = release_schema; s->private_data = p;
+}
+
+struct ArrayPriv {
+  std::vector<BufferPtr> owners;
+  std::vector<const void*> buffers;
+  std::vector<ArrowArray> child_storage;
+  std::vector<ArrowArray*> child_ptrs;
+};
+void release_array(ArrowArray* a) {
+  if (!a || !a->release) return;
+  auto* p = (ArrayPriv*)a->private_data;
+  for (auto& c : p->child_storage) if (c.release) c.release(&c);
+  delete p;
+  a->release = nullptr;
+}
+
+__global__ void rebase_offsets_kernel(const int32_t* in, int32_t* out, int64_t n1, int32_t first) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n1) out[i] = in[i] - first;
+}
+// copy `n` bits starting at bit `bit0` of `in` into a fresh bitmap starting at bit 0
+__global__ void realign_bits_kernel(const uint8_t* in, uint8_t* out, int64_t n, int32_t bit0) {
+  int64_t byte = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t nbytes = (n + 7) >> 3;
+  if (byte >= nbytes) return;
+  int64_t src_bit = byte * 8 + bit0;
+  uint32_t lo = in[src_bit >> 3];
+  uint32_t hi = (((src_bit & 7) != 0) && ((src_bit >> 3) + 1 <= ((bit0 + n - 1) >> 3))) ? in[(src_bit >> 3) + 1] : 0;
+  uint32_t v = ((lo | (hi << 8)) >> (src_bit & 7)) & 0xff;
+  int64_t rem = n - byte * 8;
+  if (rem < 8) v &= (1u << rem) - 1;
+  out[byte] = (uint8_t)v;
+}
+
+}  // namespace
+
+void export_schema(const Batch& b, ArrowSchema* out) {
+  fill_schema(out, "+s", "", false);
+  auto* p = (SchemaPriv*)out->private_data;
+  p->child_storage.resize(b.cols.size());
+  p->child_ptrs.resize(b.cols.size());
+  for (size_t i = 0; i < b.cols.size(); ++i) {
+    fill_schema(&p->child_storage[i], dtype_arrow_format(b.cols[i].field.type), b.cols[i].field.name, b.cols[i].field.nullable);
+    p->child_ptrs[i] = &p->child_storage[i];
+  }
+  out->n_children = (int64_t)b.cols.size();
+  out->children = p->child_ptrs.data();
+}
+
+void export_empty_schema(ArrowSchema* out) {
+  Batch b;
+  export_schema(b, out);
+}
+
+// Normalised device view of a column for export: offsets rebased to 0, bitmaps starting at bit 0.
+struct ExportCol {
+  const uint8_t* validity = nullptr; int64_t validity_bytes = 0;
+  const void* buf1 = nullptr; int64_t buf1_bytes = 0;
+  const void* buf2 = nullptr; int64_t buf2_bytes = 0;
+  int n_buffers = 2;
+  std::vector<BufferPtr> owners;
+};
+
+static ExportCol normalise_for_export(const Column& c, cudaStream_t stream) {
+  ExportCol e;
+  e.owners = c.owners;
+  int64_t n = c.length;
+  if (c.validity && c.null_count != 0 && n > 0) {
+    e.validity_bytes = (n + 7) / 8;
+    if (c.validity_bit0 != 0) {
+      BufferPtr v = device_alloc((size_t)e.validity_bytes);
+      KernelTimer t("realign_bits_kernel", stream);
+      realign_bits_kernel<<<(unsigned)ceil_div(e.validity_bytes, 256), 256, 0, stream>>>(c.validity, (uint8_t*)v.get(), n, c.validity_bit0);
+      e.validity = (const uint8_t*)v.get(); e.owners.push_back(v);
+    } else e.validity = c.validity;
+  }
+  switch (c.field.type) {
+    case DType::Int64: case DType::Float64:
+      e.buf1 = c.data; e.buf1_bytes = n * 8; e.n_buffers = 2; break;
+    case DType::Bool:
+      e.buf1_bytes = (n + 7) / 8;
+      if (c.data_bit0 != 0 && n > 0) {
+        BufferPtr v = device_alloc((size_t)e.buf1_bytes);
+        KernelTimer t("realign_bits_kernel", stream);
+        realign_bits_kernel<<<(unsigned)ceil_div(e.buf1_bytes, 256), 256, 0, stream>>>(c.data, (uint8_t*)v.get(), n, c.data_bit0);
+        e.buf1 = v.get(); e.owners.push_back(v);
+      } else e.buf1 = c.data;
+      e.n_buffers = 2; break;
+    case DType::Utf8: case DType::Binary: {
+      e.n_buffers = 3;
+      e.buf1_bytes = (n + 1) * 4;
+      if (c.data_bytes < 0) fail(ARK_ERR_PROCESS, "internal: var-len extent unresolved at export");
+      if (c.first_offset != 0 && c.offsets) {
+        BufferPtr o = device_alloc((size_t)e.buf1_bytes);
+        KernelTimer t("rebase_offsets_kernel", stream);
+        rebase_offsets_kernel<<<(unsigned)ceil_div(n + 1, 256), 256, 0, stream>>>(c.offsets, (int32_t*)o.get(), n + 1, (int32_t)c.first_offset);
+        e.buf1 = o.get(); e.owners.push_back(o);
+      } else if (c.offsets) e.buf1 = c.offsets;
+      else {
+        BufferPtr o = device_alloc(4);
+        ARK_CUDA(cudaMemsetAsync(o.get(), 0, 4, stream));
+        e.buf1 = o.get(); e.owners.push_back(o);
+      }
+      e.buf2 = c.data ? c.data + c.first_offset : nullptr; e.buf2_bytes = c.data_bytes;
+      break;
+    }
+    default: e.n_buffers = 0; break;
+  }
+  return e;
+}
+
+static void build_struct_array(const Batch& b, std::vector<ExportCol>& cols, bool to_host, cudaStream_t stream,
+                               ArrowArray* out, int64_t* d2h_bytes) {
+  auto* top = new ArrayPriv();
+  memset(out, 0, sizeof(*out));
+  out->length = b.num_rows; out->null_count = 0; out->offset = 0;
+  top->buffers.push_back(nullptr);
+  out->n_buffers = 1; out->buffers = top->buffers.data();
+  top->child_storage.resize(cols.size());
+  top->child_ptrs.resize(cols.size());
+  for (size_t i = 0; i < cols.size(); ++i) {
+    ExportCol& e = cols[i];
+    const Column& c = b.cols[i];
+    auto* cp = new ArrayPriv();
+    ArrowArray* ca = &top->child_storage[i];
+    memset(ca, 0, sizeof(*ca));
+    ca->length = c.length; ca->offset = 0;
+    ca->null_count = e.validity ? (c.null_count < 0 ? -1 : c.null_count) : 0;
+    auto place = [&](const void* dptr, int64_t bytes) -> const void* {
+      if (!to_host) return dptr;
+      if (!dptr && bytes == 0) {
+        BufferPtr h = pinned_alloc(64);
+        cp->owners.push_back(h);
+        return h.get();
+      }
+      BufferPtr h = pinned_alloc((size_t)std::max<int64_t>(bytes, 1));
+      if (bytes > 0) {
+        ARK_CUDA(cudaMemcpyAsync(h.get(), dptr, (size_t)bytes, cudaMemcpyDeviceToHost, stream));
+        if (d2h_bytes) *d2h_bytes += bytes;
+      }
+      cp->owners.push_back(h);
+      return h.get();
+    };
+    if (c.field.type == DType::Null) {
+      ca->n_buffers = 0; ca->null_count = c.length;
+    } else {
+      cp->buffers.push_back(e.validity ? place(e.validity, e.validity_bytes) : nullptr);
+      cp->buffers.push_back(place(e.buf1, e.buf1_bytes));
+      if (e.n_buffers == 3) cp->buffers.push_back(place(e.buf2, e.buf2_bytes));
+      ca->n_buffers = (int64_t)cp->buffers.size();
+    }
+    ca->buffers = cp->buffers.data();
+    if (!to_host) cp->owners = e.owners;  // device export keeps the HBM blocks alive
+    ca->release = release_array; ca->private_data = cp;
+    top->child_ptrs[i] = ca;
+  }
+  out->n_children = (int64_t)cols.size();
+  out->children = top->child_ptrs.data();
+  out->release = release_array; out->private_data = top;
+}
+
+void export_host(const Batch& b, cudaStream_t stream, ArrowArray* out, ArrowSchema* out_schema, int64_t* d2h_bytes) {
+  std::vector<ExportCol> cols;
+  for (auto& c : b.cols) cols.push_back(normalise_for_export(c, stream));
+  build_struct_array(b, cols, true, stream, out, d2h_bytes);
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  export_schema(b, out_schema);
+}
+
+void export_device(const Batch& b, ArrowDeviceArray* out, ArrowSchema* out_schema) {
+  StreamLease lease;
+  std::vector<ExportCol> cols;
+  for (auto& c : b.cols) cols.push_back(normalise_for_export(c, lease.s));
+  memset(out, 0, sizeof(*out));
+  build_struct_array(b, cols, false, lease.s, &out->array, nullptr);
+  ARK_CUDA(cudaStreamSynchronize(lease.s));
+  int dev = 0; cudaGetDevice(&dev);
+  out->device_id = dev; out->device_type = ARROW_DEVICE_CUDA; out->sync_event = nullptr;
+  export_schema(b, out_schema);
+}
+
+BufferPtr adopt_array(ArrowArray* arr) {
+  if (!arr || !arr->release) return BufferPtr();
+  auto* moved = new ArrowArray(*arr);
+  arr->release = nullptr;  // moved
+  return BufferPtr(moved, [](void* p) {
+    auto* a = (ArrowArray*)p;
+    if (a->release) a->release(a);
+    delete a;
+  });
+}
+
+}  // namespace ark

@@ -1,0 +1,124 @@
+// batch.h — HBM-resident record batch (the MessageBatch stand-in, crates/arkflow-core/src/lib.rs:236-240),
+// the device/pinned memory pools behind it, and the Arrow C Data Interface import/export.
+//
+// Layout in HBM (same as Arrow's columnar format, so a batch can be handed to the next processor
+// without reshaping): fixed-width columns = one contiguous values buffer; Utf8/Binary = int32
+// offsets[n+1] + contiguous bytes; Boolean = bit-packed; optional validity bitmap per column.
+#pragma once
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "sql.h"
+#include "vm.h"
+
+namespace ark {
+
+// ---- memory pools -------------------------------------------------------------------------------
+// Caching allocators.  Every C-ABI call ends with a synchronize of its stream, and Arrow's contract
+// is that a consumer releases an array only when it is done with it, so a freed block is idle and can
+// be handed to any stream without event tracking.
+class BlockPool {
+ public:
+  enum Kind { Device, Pinned };
+  explicit BlockPool(Kind k) : kind_(k) {}
+  ~BlockPool();
+  void* alloc(size_t bytes);
+  void free(void* p);
+  size_t bytes_reserved() const { return reserved_; }
+  void trim();
+
+ private:
+  struct Block { void* p; size_t size; };
+  Kind kind_;
+  std::mutex mu_;
+  std::vector<Block> free_;    // sorted by size
+  std::vector<Block> live_;
+  size_t reserved_ = 0;
+};
+
+BlockPool& device_pool();
+BlockPool& pinned_pool();
+
+using BufferPtr = std::shared_ptr<void>;  // owner of one allocation; get() = base pointer
+BufferPtr device_alloc(size_t bytes);
+BufferPtr pinned_alloc(size_t bytes);
+
+// ---- streams ------------------------------------------------------------------------------------
+// RAII lease of a non-blocking stream from a small pool (replaces the reference's
+// SessionContextPool::acquire/release, context_pool.rs:91-119, without its leak-on-error).
+struct StreamLease {
+  StreamLease();
+  ~StreamLease();
+  cudaStream_t s;
+  StreamLease(const StreamLease&) = delete;
+  StreamLease& operator=(const StreamLease&) = delete;
+};
+
+// ---- columns and batches ------------------------------------------------------------------------
+struct Field {
+  std::string name;
+  DType type = DType::Null;
+  bool nullable = true;
+  std::string format;  // original Arrow format string (kept for unsupported types)
+};
+
+struct Column {
+  Field field;
+  int64_t length = 0;
+  int64_t null_count = 0;
+  const uint8_t* validity = nullptr;  // device bitmap or nullptr
+  int32_t validity_bit0 = 0;
+  const int32_t* offsets = nullptr;   // element 0 (already shifted by the Arrow offset)
+  const uint8_t* data = nullptr;      // values of element 0 / byte base that offsets index into
+  int32_t data_bit0 = 0;              // Boolean
+  int64_t data_bytes = 0;             // var-len: bytes referenced (offsets[n]-offsets[0]); fixed: n*width
+  int64_t first_offset = 0;           // var-len: offsets[0] value (0 for batches we produced)
+  std::vector<BufferPtr> owners;      // keep-alive for everything referenced above
+  bool present = true;                // false ⇒ column was not imported (projection push-down)
+
+  ColView view() const {
+    ColView v;
+    v.data = data; v.offsets = offsets; v.validity = validity;
+    v.validity_bit0 = validity_bit0; v.data_bit0 = data_bit0;
+    return v;
+  }
+};
+
+struct Batch {
+  std::vector<Column> cols;
+  int64_t num_rows = 0;
+  std::string input_name;  // MessageBatch::input_name (lib.rs:239)
+  int find(const std::string& name) const {
+    for (size_t i = 0; i < cols.size(); ++i) if (cols[i].field.name == name) return (int)i;
+    return -1;
+  }
+};
+
+std::vector<Field> schema_fields(const ArrowSchema* s);  // struct schema → fields (no data needed)
+std::string schema_fingerprint(const std::vector<Field>& f);
+
+// Import a struct array.  `needed`: per top-level column, whether its buffers are required (others
+// get present=false and are not copied); nullptr ⇒ all.  Host import copies buffers to HBM on
+// `stream` (the source is read asynchronously when pinned; the caller synchronizes before
+// releasing `arr`).  Device import wraps the pointers without copying; `keep` (may be null) is
+// attached to every column as an owner.
+Batch import_host(const ArrowArray* arr, const ArrowSchema* schema, const std::vector<bool>* needed,
+                  cudaStream_t stream, int64_t* h2d_bytes = nullptr);
+Batch import_device(const ArrowDeviceArray* arr, const ArrowSchema* schema, const std::vector<bool>* needed,
+                    BufferPtr keep);
+
+// Export: builds a struct ArrowArray/ArrowSchema whose release callbacks drop the owners.
+// Host export copies HBM → pinned host on `stream` and synchronizes it.
+void export_schema(const Batch& b, ArrowSchema* out);
+void export_empty_schema(ArrowSchema* out);  // RecordBatch::new_empty(Schema::empty()), sql.rs:137-139
+void export_host(const Batch& b, cudaStream_t stream, ArrowArray* out, ArrowSchema* out_schema,
+                 int64_t* d2h_bytes = nullptr);
+void export_device(const Batch& b, ArrowDeviceArray* out, ArrowSchema* out_schema);
+
+// Moves an ArrowArray into shared ownership: the returned pointer releases it when dropped.
+BufferPtr adopt_array(ArrowArray* arr);
+
+}  // namespace ark

@@ -1,0 +1,130 @@
+// capi.cu — extern "C" entry points declared in include/arkflow_b200.h.
+#include <cstring>
+
+#include "engine.h"
+
+using namespace ark;
+
+struct ark_proc {
+  std::unique_ptr<Processor> impl;
+};
+
+namespace {
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    return ARK_OK;
+  } catch (const ArkError& e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    set_last_error("out of host memory");
+    return ARK_ERR_PROCESS;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return ARK_ERR_PROCESS;
+  }
+}
+
+SqlProcessor* as_sql(ark_proc_t* p) {
+  if (!p || !p->impl || strcmp(p->impl->type(), "sql") != 0) fail(ARK_ERR_PROCESS, "handle is not a sql processor");
+  return static_cast<SqlProcessor*>(p->impl.get());
+}
+
+std::vector<bool> needed_mask(const Plan& plan, size_t n_fields) {
+  std::vector<bool> m(n_fields, false);
+  if (plan.identity) { std::fill(m.begin(), m.end(), true); return m; }
+  for (int c : plan.used_cols) m[c] = true;
+  return m;
+}
+
+void set_none(ArrowArray* out, ArrowSchema* out_schema) {
+  memset(out, 0, sizeof(*out));
+  if (out_schema) memset(out_schema, 0, sizeof(*out_schema));
+}
+
+}  // namespace
+
+extern "C" {
+
+int ark_b200_init(int device) {
+  return guarded([&] {
+    if (device >= 0) ARK_CUDA(cudaSetDevice(device));
+    ARK_CUDA(cudaFree(0));
+    cudaDeviceProp prop;
+    int dev = 0;
+    ARK_CUDA(cudaGetDevice(&dev));
+    ARK_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) fail(ARK_ERR_CUDA, std::string("arkflow_b200 is built for sm_100a; found ") + prop.name);
+  });
+}
+
+int ark_b200_device_count(int* out_count) {
+  return guarded([&] { ARK_CUDA(cudaGetDeviceCount(out_count)); });
+}
+
+const char* ark_b200_version(void) { return "arkflow_b200 0.1.0 (sm_100a)"; }
+const char* ark_last_error(void) { return last_error_ref().c_str(); }
+
+int ark_sql_create(const char* config_json, ark_proc_t** out) {
+  return guarded([&] {
+    if (!out) fail(ARK_ERR_PROCESS, "null output handle");
+    *out = nullptr;
+    auto p = SqlProcessor::from_config(config_json);
+    auto* h = new ark_proc();
+    h->impl = std::move(p);
+    *out = h;
+  });
+}
+
+int ark_sql_process(ark_proc_t* p, ArrowArray* in, ArrowSchema* in_schema, ArrowArray* out, ArrowSchema* out_schema) {
+  BufferPtr in_owner = adopt_array(in);  // moved in: released on every path
+  return guarded([&] {
+    SqlProcessor* sp = as_sql(p);
+    const ArrowArray* arr = (const ArrowArray*)in_owner.get();
+    if (!arr) fail(ARK_ERR_PROCESS, "input array already released");
+    if (arr->length == 0) { set_none(out, out_schema); return; }  // ProcessResult::None, sql.rs:211-213
+    std::vector<Field> fields = schema_fields(in_schema);
+    auto plan = sp->plan_for(fields);
+    std::vector<bool> mask = needed_mask(*plan, fields.size());
+    StreamLease lease;
+    Batch b = import_host(arr, in_schema, &mask, lease.s);
+    Batch r = sp->execute(*plan, b, lease.s);
+    export_host(r, lease.s, out, out_schema);
+  });
+}
+
+int ark_sql_process_device(ark_proc_t* p, ArrowDeviceArray* in, ArrowSchema* in_schema, ArrowDeviceArray* out,
+                           ArrowSchema* out_schema) {
+  BufferPtr in_owner = adopt_array(&in->array);
+  return guarded([&] {
+    SqlProcessor* sp = as_sql(p);
+    if (!in_owner) fail(ARK_ERR_PROCESS, "input array already released");
+    ArrowDeviceArray view = *in;
+    view.array = *(const ArrowArray*)in_owner.get();
+    if (view.array.length == 0) { memset(out, 0, sizeof(*out)); if (out_schema) memset(out_schema, 0, sizeof(*out_schema)); return; }
+    std::vector<Field> fields = schema_fields(in_schema);
+    auto plan = sp->plan_for(fields);
+    std::vector<bool> mask = needed_mask(*plan, fields.size());
+    StreamLease lease;
+    Batch b = import_device(&view, in_schema, &mask, in_owner);
+    Batch r = sp->execute(*plan, b, lease.s);
+    ARK_CUDA(cudaStreamSynchronize(lease.s));
+    export_device(r, out, out_schema);
+  });
+}
+
+int ark_proc_close(ark_proc_t*) { return ARK_OK; }  // Processor::close is a no-op in the reference (sql.rs:222-224)
+
+void ark_proc_destroy(ark_proc_t* p) { delete p; }
+
+int64_t ark_kernel_launch_count(void) { return launch_count(); }
+void ark_kernel_timing_enable(int on) { timing_enable(on); }
+void ark_kernel_timing_reset(void) { timing_reset(); }
+int ark_kernel_timing_get(const char* name, double* total_ms, int64_t* launches) {
+  return timing_get(name, total_ms, launches) ? 0 : 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+// engine.cu — SqlProcessor (host side) and the filter/project executor.
+#include "engine.h"
+
+#include <algorithm>
+
+#include "json_mini.h"
+
+namespace ark {
+
+std::unique_ptr<SqlProcessor> SqlProcessor::from_config(const char* config_json) {
+  // reference: sql.rs:235-239 — the message really says "Batch processor" (copy-paste in the reference)
+  if (!config_json) fail(ARK_ERR_CONFIG, "Batch processor configuration is missing");
+  JsonValue cfg = parse_json(config_json);
+  if (cfg.kind == JsonValue::Null) fail(ARK_ERR_CONFIG, "Batch processor configuration is missing");
+  if (cfg.kind != JsonValue::Object) fail(ARK_ERR_SERIALIZATION, "invalid type: expected struct SqlProcessorConfig");
+  const JsonValue* q = cfg.get("query");
+  if (!q) fail(ARK_ERR_SERIALIZATION, "missing field `query`");
+  if (q->kind != JsonValue::String) fail(ARK_ERR_SERIALIZATION, "invalid type for `query`: expected a string");
+  auto p = std::make_unique<SqlProcessor>();
+  p->query_text = q->str;
+  if (const JsonValue* t = cfg.get("table_name")) {
+    if (t->kind == JsonValue::String) p->table_name = t->str;
+    else if (t->kind != JsonValue::Null) fail(ARK_ERR_SERIALIZATION, "invalid type for `table_name`: expected a string");
+  }
+  if (const JsonValue* tl = cfg.get("temporary_list")) {
+    if (tl->kind == JsonValue::Array && !tl->arr.empty()) {
+      // sql.rs:70-86: temporaries are looked up in Resource; this library has no Temporary registry,
+      // so a configured temporary is by construction "not found".
+      const JsonValue* nm = tl->arr[0].get("name");
+      fail(ARK_ERR_PROCESS, "Temporary " + (nm && nm->kind == JsonValue::String ? nm->str : std::string("?")) + " not found");
+    }
+  }
+  p->ast = parse_sql(p->query_text);  // throws "SQL query error: …" (sql.rs:92-98)
+  return p;
+}
+
+std::shared_ptr<const Plan> SqlProcessor::plan_for(const std::vector<Field>& fields) {
+  std::string key = schema_fingerprint(fields);
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    auto it = plans_.find(key);
+    if (it != plans_.end()) return it->second;
+  }
+  auto plan = std::make_shared<Plan>(bind_query(ast, table_name, fields));
+  std::lock_guard<std::mutex> l(mu_);
+  if (plans_.size() > 64) plans_.clear();
+  plans_[key] = plan;
+  return plan;
+}
+
+std::shared_ptr<const Plan> SqlProcessor::join_plan_for(const std::vector<std::string>& names,
+                                                        const std::vector<std::vector<Field>>& tables) {
+  std::string key = "J";
+  for (size_t i = 0; i < names.size(); ++i) { key += names[i]; key += '\x1d'; key += schema_fingerprint(tables[i]); key += '\x1c'; }
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    auto it = plans_.find(key);
+    if (it != plans_.end()) return it->second;
+  }
+  auto plan = std::make_shared<Plan>(bind_join(ast, names, tables));
+  std::lock_guard<std::mutex> l(mu_);
+  if (plans_.size() > 64) plans_.clear();
+  plans_[key] = plan;
+  return plan;
+}
+
+Batch SqlProcessor::execute(const Plan& plan, Batch& in, cudaStream_t stream) {
+  switch (plan.kind) {
+    case Plan::FilterProject: return run_filter_project(plan, in, stream);
+    case Plan::Aggregate: return run_aggregate(plan, in, stream);
+    default: fail(ARK_ERR_PROCESS, "internal: join plan executed through the single-table path");
+  }
+}
+
+// ---- filter / project ---------------------------------------------------------------------------------
+
+namespace {
+
+struct PendingOut {
+  int out_index;            // index into plan.outputs
+  BufferPtr data, offsets, valid_bytes;
+  bool is_bool = false;
+};
+
+const char* vm_error_text(int e) {
+  switch (e) {
+    case VMERR_DIV_ZERO: return "Arrow error: Divide by zero error";
+    case VMERR_OVERFLOW: return "Arrow error: Arithmetic overflow: Overflow happened on: i64::MIN / -1";
+    case VMERR_CAST: return "Arrow error: Cast error: Can't cast value to type Int64";
+    default: return "unknown evaluation error";
+  }
+}
+
+}  // namespace
+
+Batch run_filter_project(const Plan& plan, Batch& in, cudaStream_t stream) {
+  const int64_t n = in.num_rows;
+  Batch out;
+  out.input_name = in.input_name;
+  auto src_col = [&](int slot) -> Column& { return in.cols[plan.used_cols[slot]]; };
+
+  if (plan.identity) {  // SELECT * FROM flow: the batch itself (zero copy)
+    std::vector<int> varlen;
+    for (size_t i = 0; i < in.cols.size(); ++i) varlen.push_back((int)i);
+    resolve_varlen_extents(in, varlen, stream);
+    out.cols = in.cols;
+    out.num_rows = n;
+    return out;
+  }
+
+  {
+    std::vector<int> varlen;
+    for (auto& oc : plan.outputs)
+      if (oc.src.kind == ValueSource::PassThrough) varlen.push_back(plan.used_cols[oc.src.slot]);
+    resolve_varlen_extents(in, varlen, stream);
+  }
+
+  out.cols.resize(plan.outputs.size());
+  std::vector<int> todo;  // outputs that need the kernel
+  for (size_t i = 0; i < plan.outputs.size(); ++i) {
+    const OutputCol& oc = plan.outputs[i];
+    Column& c = out.cols[i];
+    c.field.name = oc.name; c.field.type = oc.src.type; c.field.nullable = oc.src.nullable;
+    if (!plan.has_pred && oc.src.kind == ValueSource::PassThrough) {
+      Column& s = src_col(oc.src.slot);  // no filter: the projected column is the input column
+      Field f = c.field;
+      c = s; c.field = f;
+    } else todo.push_back((int)i);
+  }
+  out.num_rows = n;
+
+  int64_t count = n;
+  if (!todo.empty() || plan.has_pred) {
+    const int n_tiles = (int)ceil_div(n, FP_TILE);
+    if (n_tiles <= 0) fail(ARK_ERR_PROCESS, "internal: empty batch reached the filter kernel");
+    std::vector<PendingOut> pend;
+    // scratch: [desc | ticket | totals | error] per launch; results gathered into one pinned block
+    const size_t desc_bytes = (size_t)n_tiles * FP_CHANNELS * 8;
+    const size_t scratch_bytes = round_up((int64_t)desc_bytes + 64 + FP_CHANNELS * 8, 256);
+    size_t pos = 0;
+    std::vector<BufferPtr> scratches;
+    std::vector<int> launch_n_out;
+    BufferPtr host_res = pinned_alloc(4096);
+    int launches = 0;
+    bool first = true;
+    while (first || pos < todo.size()) {
+      first = false;
+      FpParams P;
+      memset(&P, 0, sizeof P);
+      P.n_rows = n; P.n_tiles = n_tiles;
+      for (size_t s = 0; s < plan.used_cols.size(); ++s) P.cols[s] = src_col((int)s).view();
+      int pred_kind = !plan.has_pred ? 0 : (plan.simple.enabled ? 1 : 2);
+      if (pred_kind == 1) { P.sp_slot = plan.simple.slot; P.sp_cmp = plan.simple.cmp; P.sp_is_f64 = plan.simple.is_f64; P.sp_const = plan.simple.constant; }
+      if (pred_kind == 2) P.pred = plan.pred;
+      int n_progs = 0;
+      while (pos < todo.size() && P.n_out < FP_MAX_OUT) {
+        const int oi = todo[pos];
+        const OutputCol& oc = plan.outputs[oi];
+        const bool computed = oc.src.kind == ValueSource::Computed;
+        const bool varlen = !computed && (oc.src.type == DType::Utf8 || oc.src.type == DType::Binary);
+        if (computed && n_progs == FP_MAX_PROGS) break;
+        if (varlen && P.n_varlen == FP_MAX_VARLEN) break;
+        FpOutput& fo = P.outs[P.n_out];
+        PendingOut po; po.out_index = oi;
+        const Column* s = computed ? nullptr : &src_col(oc.src.slot);
+        bool want_valid = computed ? oc.src.nullable : (s->validity != nullptr);
+        if (want_valid) { po.valid_bytes = device_alloc((size_t)n); fo.out_valid = (uint8_t*)po.valid_bytes.get(); fo.write_validity = 1; }
+        if (computed) {
+          fo.prog = n_progs; P.progs[n_progs++] = oc.src.prog;
+          if (oc.src.type == DType::Bool) { fo.kind = FP_OUT_COMPUTED_BOOL; po.is_bool = true; po.data = device_alloc((size_t)n); }
+          else { fo.kind = FP_OUT_COMPUTED8; po.data = device_alloc((size_t)n * 8); }
+        } else if (varlen) {
+          fo.kind = FP_OUT_VARLEN; fo.slot = oc.src.slot; fo.varlen_idx = P.n_varlen;
+          P.varlen_slot[P.n_varlen++] = oc.src.slot;
+          po.offsets = device_alloc((size_t)(n + 1) * 4);
+          po.data = device_alloc((size_t)std::max<int64_t>(s->data_bytes, 0) + 16);
+          fo.out_offsets = (int32_t*)po.offsets.get();
+        } else if (oc.src.type == DType::Bool) {
+          fo.kind = FP_OUT_BOOL; fo.slot = oc.src.slot; po.is_bool = true; po.data = device_alloc((size_t)n);
+        } else if (oc.src.type == DType::Int64 || oc.src.type == DType::Float64) {
+          fo.kind = FP_OUT_FIXED8; fo.slot = oc.src.slot; po.data = device_alloc((size_t)n * 8);
+        } else {
+          fail(ARK_ERR_UNSUPPORTED, std::string("projection of a ") + dtype_name(oc.src.type) + " column");
+        }
+        fo.out_data = po.data.get();
+        pend.push_back(std::move(po));
+        ++P.n_out; ++pos;
+      }
+      BufferPtr scratch = device_alloc(scratch_bytes);
+      ARK_CUDA(cudaMemsetAsync(scratch.get(), 0, scratch_bytes, stream));
+      P.desc = (unsigned long long*)scratch.get();
+      P.ticket = (unsigned int*)((char*)scratch.get() + desc_bytes);
+      P.totals = (long long*)((char*)scratch.get() + desc_bytes + 16);
+      P.error = (int32_t*)((char*)scratch.get() + desc_bytes + 8);
+      launch_filter_project(P, pred_kind, stream);
+      ARK_CUDA(cudaGetLastError());
+      if (launches >= 32) fail(ARK_ERR_UNSUPPORTED, "too many output columns");
+      // totals[FP_CHANNELS] + error live contiguously from desc_bytes+8: copy 8 + 8 + 24 bytes
+      ARK_CUDA(cudaMemcpyAsync((char*)host_res.get() + launches * 64, (char*)scratch.get() + desc_bytes, 64,
+                               cudaMemcpyDeviceToHost, stream));
+      scratches.push_back(scratch);
+      launch_n_out.push_back(P.n_out);
+      ++launches;
+    }
+    ARK_CUDA(cudaStreamSynchronize(stream));
+    for (int l = 0; l < launches; ++l) {
+      const char* base = (const char*)host_res.get() + l * 64;
+      int32_t err = *(const int32_t*)(base + 8);
+      if (err) fail(ARK_ERR_PROCESS, std::string("Collection query results error: ") + vm_error_text(err));
+    }
+    count = *(const int64_t*)((const char*)host_res.get() + 16);
+    // finish the columns produced by the kernel
+    size_t pi = 0;
+    for (int l = 0; l < launches; ++l) {
+      const int64_t* totals = (const int64_t*)((const char*)host_res.get() + l * 64 + 16);
+      int vseen = 0;
+      const int n_out = launch_n_out[l];
+      for (int k = 0; k < n_out; ++k, ++pi) {
+        PendingOut& po = pend[pi];
+        const OutputCol& oc = plan.outputs[po.out_index];
+        Column& c = out.cols[po.out_index];
+        c.length = count; c.present = true;
+        const bool varlen = po.offsets != nullptr;
+        if (varlen) {
+          c.offsets = (const int32_t*)po.offsets.get(); c.data = (const uint8_t*)po.data.get();
+          c.data_bytes = totals[1 + vseen]; c.first_offset = 0; ++vseen;
+          c.owners = {po.offsets, po.data};
+        } else if (po.is_bool) {
+          BufferPtr bits = device_alloc((size_t)(count + 7) / 8 + 1);
+          launch_pack_bits((const uint8_t*)po.data.get(), count, (uint8_t*)bits.get(), nullptr, stream);
+          c.data = (const uint8_t*)bits.get(); c.data_bit0 = 0; c.data_bytes = (count + 7) / 8;
+          c.owners = {bits, po.data};
+        } else {
+          c.data = (const uint8_t*)po.data.get(); c.data_bytes = count * 8; c.owners = {po.data};
+        }
+        if (po.valid_bytes && count > 0) {
+          BufferPtr bits = device_alloc((size_t)(count + 7) / 8 + 1);
+          launch_pack_bits((const uint8_t*)po.valid_bytes.get(), count, (uint8_t*)bits.get(), nullptr, stream);
+          c.validity = (const uint8_t*)bits.get(); c.validity_bit0 = 0; c.null_count = -1;
+          c.owners.push_back(bits); c.owners.push_back(po.valid_bytes);
+        } else { c.validity = nullptr; c.null_count = 0; }
+        (void)oc;
+      }
+    }
+    // zero-copy passthrough columns of a predicate-less projection keep length n (= count)
+    out.num_rows = count;
+  }
+
+  if (plan.limit >= 0 && out.num_rows > plan.limit) {
+    // LIMIT k without ORDER BY on a single-partition scan: the first k surviving rows
+    out.num_rows = plan.limit;
+    for (auto& c : out.cols) {
+      c.length = plan.limit;
+      if (c.field.type == DType::Utf8 || c.field.type == DType::Binary) c.data_bytes = -1;
+    }
+    std::vector<int> all;
+    for (size_t i = 0; i < out.cols.size(); ++i) all.push_back((int)i);
+    resolve_varlen_extents(out, all, stream);
+  }
+  return out;
+}
+
+}  // namespace ark

@@ -1,0 +1,61 @@
+// engine.h — host-side processors: the C++ mirror of the reference's plugin objects for this path.
+//   SqlProcessor        ← crates/arkflow-plugin/src/processor/sql.rs:59-225
+//   JsonToArrow / ArrowToJson ← crates/arkflow-plugin/src/processor/json.rs:42-113
+#pragma once
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "batch.h"
+#include "filter_project.cuh"
+#include "plan.h"
+#include "sql.h"
+
+namespace ark {
+
+// declared in batch.cu
+const std::string& last_error_ref();
+int64_t launch_count();
+void timing_enable(int on);
+void timing_reset();
+bool timing_get(const char* name, double* ms, int64_t* n);
+void resolve_varlen_extents(Batch& b, const std::vector<int>& col_idx, cudaStream_t stream);
+
+// kernels' host launchers
+void launch_filter_project(const FpParams& P, int pred_kind, cudaStream_t stream);
+void launch_pack_bits(const uint8_t* bytes, int64_t n, uint8_t* bitmap, unsigned long long* zeros, cudaStream_t stream);
+
+struct Processor {
+  virtual ~Processor() {}
+  virtual const char* type() const = 0;
+};
+
+struct SqlProcessor : Processor {
+  const char* type() const override { return "sql"; }
+  std::string query_text;
+  std::string table_name = "flow";  // DEFAULT_TABLE_NAME, sql.rs:38
+  Query ast;
+
+  // config_json as documented at ark_sql_create
+  static std::unique_ptr<SqlProcessor> from_config(const char* config_json);
+
+  // plan cache: one bound plan per distinct input schema
+  std::shared_ptr<const Plan> plan_for(const std::vector<Field>& fields);
+  std::shared_ptr<const Plan> join_plan_for(const std::vector<std::string>& names,
+                                            const std::vector<std::vector<Field>>& tables);
+
+  // Runs the bound plan on an HBM-resident batch.  `in` must contain the plan's used columns.
+  Batch execute(const Plan& plan, Batch& in, cudaStream_t stream);
+
+ private:
+  std::mutex mu_;
+  std::map<std::string, std::shared_ptr<const Plan>> plans_;
+};
+
+Batch run_filter_project(const Plan& plan, Batch& in, cudaStream_t stream);
+Batch run_aggregate(const Plan& plan, Batch& in, cudaStream_t stream);
+Batch run_join(const Plan& plan, Batch& left, Batch& right, cudaStream_t stream);
+
+}  // namespace ark

@@ -1,0 +1,89 @@
+// plan.h — a Query bound to one concrete input schema: what DataFusion's
+// statement_to_plan + optimiser + physical planner produce per batch in the reference
+// (crates/arkflow-plugin/src/processor/sql.rs:188-204), produced here once per schema and cached.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "batch.h"
+#include "sql.h"
+#include "vm.h"
+
+namespace ark {
+
+// One value the row kernels can produce for a selected row.
+struct ValueSource {
+  enum Kind { PassThrough, Computed } kind = PassThrough;
+  int slot = -1;        // PassThrough: index into Plan::used_cols
+  VmProgram prog{};     // Computed: result type = type
+  DType type = DType::Null;
+  bool nullable = true;
+};
+
+struct OutputCol {
+  std::string name;
+  ValueSource src;
+};
+
+struct SimplePredicate {  // `col <cmp> literal` on an Int64/Float64 column: the templated fast path
+  bool enabled = false;
+  int slot = 0;
+  int cmp = 0;
+  bool is_f64 = false;
+  uint64_t constant = 0;  // raw bits of the literal (already coerced to the column's type)
+};
+
+enum class AggFunc { Sum, Count, CountStar, Avg, Min, Max };
+
+struct AggSpec {
+  AggFunc func = AggFunc::CountStar;
+  ValueSource arg;          // unused for CountStar
+  DType out_type = DType::Int64;
+  std::string name;         // DataFusion display name, e.g. sum(flow.value)
+};
+
+struct PostItem {  // one item of the SELECT list of an aggregate query
+  enum Kind { Key, Agg, Literal } kind = Key;
+  int index = 0;            // key index / agg index
+  DType lit_type = DType::Null;
+  uint64_t lit_bits = 0;
+  std::string lit_str;
+  std::string name;
+};
+
+struct Plan {
+  enum Kind { FilterProject, Aggregate, Join } kind = FilterProject;
+  std::vector<Field> input_fields;   // of table 0
+  std::vector<int> used_cols;        // slot → input column index (kernels see only these)
+  bool has_pred = false;
+  VmProgram pred{};
+  SimplePredicate simple;
+  // FilterProject
+  std::vector<OutputCol> outputs;
+  bool identity = false;             // SELECT * with no WHERE: output = input, no kernel
+  int64_t limit = -1;
+  // Aggregate
+  std::vector<ValueSource> keys;     // group keys (PassThrough only)
+  std::vector<std::string> key_names;
+  std::vector<AggSpec> aggs;
+  std::vector<PostItem> post;
+  // Join (two tables, inner equi-join)
+  std::string left_table, right_table;
+  std::vector<Field> right_fields;
+  int left_key = -1, right_key = -1;     // column indices in each table
+  struct JoinOut { int side; int col; std::string name; };
+  std::vector<JoinOut> join_out;
+};
+
+// Throws ARK_ERR_PROCESS ("Execution query error: …") for binding errors the reference would raise
+// at plan time (unknown column/table, type errors) and ARK_ERR_UNSUPPORTED for constructs outside
+// the GPU subset.
+Plan bind_query(const Query& q, const std::string& table_name, const std::vector<Field>& fields);
+Plan bind_join(const Query& q, const std::vector<std::string>& names,
+               const std::vector<std::vector<Field>>& tables);
+
+// DataFusion's `schema_name()` of an expression (result column naming).
+std::string expr_display_name(const Expr& e, const std::string& table);
+
+}  // namespace ark

@@ -1,0 +1,210 @@
+/*
+ * arkflow_b200.h — C ABI of libarkflow_b200.so (B200 / sm_100a)
+ *
+ * Drop-in boundary for ArkFlow's per-batch processor stage.  The reference has NO C ABI on this
+ * path: the boundary is two Rust traits resolved through a string-keyed registry
+ *   trait Processor { async fn process(&self, MessageBatchRef) -> Result<ProcessResult, Error>; close }
+ *       crates/arkflow-core/src/processor/mod.rs:32-79
+ *   trait Buffer    { write / read / flush / close }
+ *       crates/arkflow-core/src/buffer/mod.rs:26-47
+ * A ~150-line Rust shim implements those traits by calling the entry points
+ * below; data crosses as Arrow C Data Interface structs, the same mechanism the reference already
+ * uses toward Python (crates/arkflow-plugin/src/processor/python.rs:52,67).
+ *
+ * Conventions
+ *   - every function returns an ark_status; on non-zero, ark_last_error() (thread-local) holds
+ *     the message that the shim wraps into the reference's Error::{Config,Process,…} variant.
+ *   - `in` arrays are *moved* into the callee (Arrow C Data Interface semantics: the callee calls
+ *     in->release when it is done).  Callee-allocated `out` arrays are released by the caller.
+ *   - ProcessResult::None (reference: sql.rs:211-213, empty input batch) is signalled by
+ *     out->release == NULL with status ARK_OK.
+ *   - all entry points are thread-safe and re-entrant: `process` is called from `thread_num`
+ *     concurrent tokio workers in the reference (crates/arkflow-core/src/stream/mod.rs:117-126).
+ *   - host variants take host buffers (copies to/from HBM happen inside the call);
+ *     *_device variants take/return ArrowDeviceArray with device_type == ARROW_DEVICE_CUDA whose
+ *     buffer pointers are device pointers of the current CUDA device (batches stay resident in
+ *     HBM between processors).
+ */
+#ifndef ARKFLOW_B200_H
+#define ARKFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Arrow C Data Interface (https://arrow.apache.org/docs/format/CDataInterface.html) ---- */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+#define ARROW_FLAG_DICTIONARY_ORDERED 1
+#define ARROW_FLAG_NULLABLE 2
+#define ARROW_FLAG_MAP_KEYS_SORTED 4
+struct ArrowSchema {
+  const char* format;
+  const char* name;
+  const char* metadata;
+  int64_t flags;
+  int64_t n_children;
+  struct ArrowSchema** children;
+  struct ArrowSchema* dictionary;
+  void (*release)(struct ArrowSchema*);
+  void* private_data;
+};
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void** buffers;
+  struct ArrowArray** children;
+  struct ArrowArray* dictionary;
+  void (*release)(struct ArrowArray*);
+  void* private_data;
+};
+#endif
+
+#ifndef ARROW_C_DEVICE_DATA_INTERFACE
+#define ARROW_C_DEVICE_DATA_INTERFACE
+typedef int32_t ArrowDeviceType;
+#define ARROW_DEVICE_CPU 1
+#define ARROW_DEVICE_CUDA 2
+#define ARROW_DEVICE_CUDA_HOST 3
+struct ArrowDeviceArray {
+  struct ArrowArray array;
+  int64_t device_id;
+  ArrowDeviceType device_type;
+  void* sync_event; /* cudaEvent_t* or NULL (NULL: data is ready) */
+  int64_t reserved[3];
+};
+#endif
+
+/* ---- status codes → reference Error variants (crates/arkflow-core/src/lib.rs:66-110) ---- */
+typedef enum ark_status {
+  ARK_OK = 0,
+  ARK_ERR_CONFIG = 1,      /* Error::Config(msg)         e.g. sql.rs:235-239 missing configuration   */
+  ARK_ERR_PROCESS = 2,     /* Error::Process(msg)        e.g. sql.rs:92-98,120-147                   */
+  ARK_ERR_UNSUPPORTED = 3, /* SQL outside the GPU subset: the shim may fall back to DataFusion      */
+  ARK_ERR_SERIALIZATION = 4, /* Error::Serialization   (serde_json::from_value `?`, sql.rs:240)      */
+  ARK_ERR_CUDA = 5,        /* CUDA runtime failure (no reference analogue) → Error::Process          */
+  ARK_ERR_EOF = 6          /* Error::EOF (buffer closed and drained)                                 */
+} ark_status;
+
+typedef struct ark_proc ark_proc_t; /* a built Processor (sql / json_to_arrow / arrow_to_json)       */
+typedef struct ark_buf ark_buf_t;   /* a built Buffer (memory / session_window / tumbling_window)    */
+
+/* ---- library ---- */
+/* Bind the calling process to CUDA device `device` (-1: keep current) and warm the pools.
+ * Replaces nothing in the reference (it has no device); called once from the shim's init(). */
+int ark_b200_init(int device);
+int ark_b200_device_count(int* out_count);
+const char* ark_b200_version(void);
+const char* ark_last_error(void); /* thread-local, valid until the next call on this thread */
+
+/* ---- `sql` processor: replaces SqlProcessorBuilder::build / SqlProcessor::{new,process,close}
+ *      crates/arkflow-plugin/src/processor/sql.rs:227-243, 68-105, 208-225 ---- */
+/* config_json = the processor's flattened YAML as JSON: {"query": "...", "table_name": "flow"?}
+ * NULL config → ARK_ERR_CONFIG ("Batch processor configuration is missing", sql.rs:235-239);
+ * unparsable SQL → ARK_ERR_PROCESS ("SQL query error: …", sql.rs:92-98) at construction. */
+int ark_sql_create(const char* config_json, ark_proc_t** out);
+/* One RecordBatch (struct array + schema) in, one out.  Replaces SqlProcessor::process
+ * (sql.rs:209-220) + execute_query (sql.rs:108-149). */
+int ark_sql_process(ark_proc_t* p, struct ArrowArray* in, struct ArrowSchema* in_schema,
+                    struct ArrowArray* out, struct ArrowSchema* out_schema);
+int ark_sql_process_device(ark_proc_t* p, struct ArrowDeviceArray* in, struct ArrowSchema* in_schema,
+                           struct ArrowDeviceArray* out, struct ArrowSchema* out_schema);
+/* Multi-table form used by the window buffers' JoinOperation (buffer/join.rs:62-132): table i is
+ * registered under names[i] before the query runs. */
+int ark_sql_process_tables(ark_proc_t* p, int n_tables, const char* const* names,
+                           struct ArrowArray* ins, struct ArrowSchema* in_schemas,
+                           struct ArrowArray* out, struct ArrowSchema* out_schema);
+int ark_sql_process_tables_device(ark_proc_t* p, int n_tables, const char* const* names,
+                                  struct ArrowDeviceArray* ins, struct ArrowSchema* in_schemas,
+                                  struct ArrowDeviceArray* out, struct ArrowSchema* out_schema);
+
+/* ---- `json_to_arrow` / `arrow_to_json` processors: replace Json{ToArrow,…}ProcessorBuilder::build
+ *      and ::process, crates/arkflow-plugin/src/processor/json.rs:115-152, 48-61, 78-113 ---- */
+/* config_json: {"value_field": "__value__"?, "fields_to_include": ["a","b"]?}; NULL → ARK_ERR_CONFIG */
+int ark_json_to_arrow_create(const char* config_json, ark_proc_t** out);
+int ark_json_to_arrow_process(ark_proc_t* p, struct ArrowArray* in, struct ArrowSchema* in_schema,
+                              struct ArrowArray* out, struct ArrowSchema* out_schema);
+int ark_json_to_arrow_process_device(ark_proc_t* p, struct ArrowDeviceArray* in,
+                                     struct ArrowSchema* in_schema, struct ArrowDeviceArray* out,
+                                     struct ArrowSchema* out_schema);
+int ark_arrow_to_json_create(const char* config_json, ark_proc_t** out);
+int ark_arrow_to_json_process(ark_proc_t* p, struct ArrowArray* in, struct ArrowSchema* in_schema,
+                              struct ArrowArray* out, struct ArrowSchema* out_schema);
+
+/* Processor::close (sql.rs:222-224, json.rs:63-65) and drop. */
+int ark_proc_close(ark_proc_t* p);
+void ark_proc_destroy(ark_proc_t* p);
+
+/* ---- concat_batches: replaces arrow::compute::concat_batches at
+ *      buffer/memory.rs:130, buffer/window.rs:131,159, sql.rs:146, component/json.rs:54 ---- */
+int ark_concat_batches(int n, struct ArrowArray* ins, struct ArrowSchema* in_schemas,
+                       struct ArrowArray* out, struct ArrowSchema* out_schema);
+int ark_concat_batches_device(int n, struct ArrowDeviceArray* ins, struct ArrowSchema* in_schemas,
+                              struct ArrowDeviceArray* out, struct ArrowSchema* out_schema);
+
+/* ---- buffers: replace {Memory,SessionWindow,TumblingWindow}BufferBuilder::build and
+ *      Buffer::{write,read,flush,close}: buffer/memory.rs:142-237, session_window.rs:97-159,
+ *      tumbling_window.rs:90-145, window.rs:99-190 ---- */
+/* kind: "memory" | "session_window" | "tumbling_window"; config_json = the buffer's YAML as JSON
+ * ({"capacity":N,"timeout":"1s"} | {"gap":"1s","join":{...}?} | {"interval":"1s","join":{...}?});
+ * input_names_json: JSON array of the input names Resource.input_names held at build time
+ * (multiple_inputs.rs:133-142), or NULL. */
+int ark_buffer_create(const char* kind, const char* config_json, const char* input_names_json,
+                      ark_buf_t** out);
+/* input_name: MessageBatch::get_input_name() or NULL; ack_token: opaque id the shim maps back to
+ * its Arc<dyn Ack> (returned from read as a list). */
+int ark_buffer_write(ark_buf_t* b, struct ArrowArray* in, struct ArrowSchema* in_schema,
+                     const char* input_name, uint64_t ack_token);
+/* Blocks like Buffer::read.  status ARK_OK with out->release==NULL ⇒ Ok(None) (closed & empty).
+ * acks: caller-provided array of capacity acks_cap; *n_acks receives the number of tokens whose
+ * batches were merged into `out` (VecAck, window.rs:124-139 / ArrayAck, memory.rs:121-137). */
+int ark_buffer_read(ark_buf_t* b, struct ArrowArray* out, struct ArrowSchema* out_schema,
+                    uint64_t* acks, int64_t acks_cap, int64_t* n_acks);
+int ark_buffer_flush(ark_buf_t* b);
+int ark_buffer_close(ark_buf_t* b);
+void ark_buffer_destroy(ark_buf_t* b);
+
+/* ---- multi-GPU GROUP BY / JOIN building blocks (device-resident).  The
+ *      exchange between them is the caller's NCCL all-to-all; nothing like this exists in the
+ *      reference (DataFusion's RepartitionExec(Hash) is in-process). ---- */
+/* Partial aggregate of one local batch → (keys, partial states) batch, hash-partitioned into
+ * n_parts contiguous row ranges; part_rows[n_parts] receives the row count of each range. */
+int ark_sql_partial_aggregate_device(ark_proc_t* p, struct ArrowDeviceArray* in,
+                                     struct ArrowSchema* in_schema, int n_parts,
+                                     struct ArrowDeviceArray* out, struct ArrowSchema* out_schema,
+                                     int64_t* part_rows);
+/* Merge partial-state batches (as produced above, possibly from several ranks) into the final
+ * result of the query. */
+int ark_sql_final_aggregate_device(ark_proc_t* p, struct ArrowDeviceArray* in,
+                                   struct ArrowSchema* in_schema, struct ArrowDeviceArray* out,
+                                   struct ArrowSchema* out_schema);
+/* Hash-partition the rows of a batch on column key_column into n_parts contiguous ranges
+ * (RepartitionExec(Hash) stand-in for the join repartition). */
+int ark_hash_partition_device(struct ArrowDeviceArray* in, struct ArrowSchema* in_schema,
+                              const char* key_column, int n_parts, struct ArrowDeviceArray* out,
+                              struct ArrowSchema* out_schema, int64_t* part_rows);
+
+/* ---- synthetic input of schema S, generated in HBM.  Bench/test support. ---- */
+/* value_kind: 0 = Int64 uniform [0,20), 1 = Float64 20*u.  key_space K: sensor = "temp_%07d" % k.
+ * row0: global index of the first row (so shards/batches are slices of one logical table). */
+int ark_synth_batch_device(int64_t n_rows, int64_t row0, uint64_t seed, int value_kind,
+                           int64_t key_space, struct ArrowDeviceArray* out,
+                           struct ArrowSchema* out_schema);
+
+/* ---- counters (bench.py's gpu_launches claim) ---- */
+int64_t ark_kernel_launch_count(void); /* kernels of this library launched since load */
+/* Device time (ms, CUDA events on the launching stream) and launches accumulated for kernel
+ * `name` since the last reset; timing is off unless enabled. */
+void ark_kernel_timing_enable(int on);
+void ark_kernel_timing_reset(void);
+int ark_kernel_timing_get(const char* name, double* total_ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARKFLOW_B200_H */
