@@ -21,29 +21,55 @@ static std::map<std::string, TimingEntry> g_timing_map;
 void note_launch(const char*) { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int64_t launch_count() { return g_launches.load(); }
 void timing_enable(int on) { g_timing.store(on); }
-void timing_reset() { std::lock_guard<std::mutex> l(g_timing_mu); g_timing_map.clear(); }
+static void resolve_pending_locked();
+void timing_reset() { std::lock_guard<std::mutex> l(g_timing_mu); resolve_pending_locked(); g_timing_map.clear(); }
 bool timing_get(const char* name, double* ms, int64_t* n) {
   std::lock_guard<std::mutex> l(g_timing_mu);
+  resolve_pending_locked();
   auto it = g_timing_map.find(name);
   if (it == g_timing_map.end()) { *ms = 0; *n = 0; return false; }
   *ms = it->second.ms; *n = it->second.n; return true;
 }
 
+// Timed launches record an event pair and resolve it lazily (no synchronisation on the launch path):
+// ark_kernel_timing_get() is called after the caller has synchronised the device.
+struct PendingTiming { const char* name; cudaEvent_t e0, e1; };
+static std::vector<PendingTiming> g_pending;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t take_event() {
+  {
+    std::lock_guard<std::mutex> l(g_timing_mu);
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+static void resolve_pending_locked() {
+  for (auto& p : g_pending) {
+    float ms = 0;
+    if (cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+      auto& e = g_timing_map[p.name]; e.ms += ms; e.n += 1;
+    } else cudaGetLastError();
+    g_event_pool.push_back(p.e0); g_event_pool.push_back(p.e1);
+  }
+  g_pending.clear();
+}
+
 KernelTimer::KernelTimer(const char* n, cudaStream_t s) : name(n), stream(s) {
   note_launch(n);
   if (g_timing.load(std::memory_order_relaxed)) {
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    e0 = take_event(); e1 = take_event();
     cudaEventRecord(e0, stream);
   }
 }
 KernelTimer::~KernelTimer() {
   if (e0) {
     cudaEventRecord(e1, stream);
-    cudaEventSynchronize(e1);
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     std::lock_guard<std::mutex> l(g_timing_mu);
-    auto& e = g_timing_map[name]; e.ms += ms; e.n += 1;
+    g_pending.push_back({name, e0, e1});
   }
 }
 
