@@ -116,6 +116,45 @@ int ark_sql_process_device(ark_proc_t* p, ArrowDeviceArray* in, ArrowSchema* in_
   });
 }
 
+int ark_sql_partial_aggregate_device(ark_proc_t* p, ArrowDeviceArray* in, ArrowSchema* in_schema, int n_parts,
+                                     ArrowDeviceArray* out, ArrowSchema* out_schema, int64_t* part_rows) {
+  BufferPtr in_owner = adopt_array(&in->array);
+  return guarded([&] {
+    SqlProcessor* sp = as_sql(p);
+    if (!in_owner) fail(ARK_ERR_PROCESS, "input array already released");
+    if (n_parts < 1) fail(ARK_ERR_PROCESS, "n_parts must be >= 1");
+    ArrowDeviceArray view = *in;
+    view.array = *(const ArrowArray*)in_owner.get();
+    std::vector<Field> fields = schema_fields(in_schema);
+    auto plan = sp->plan_for(fields);
+    if (plan->kind != Plan::Aggregate) fail(ARK_ERR_PROCESS, "partial aggregate requested for a query without aggregation");
+    std::vector<bool> mask = needed_mask(*plan, fields.size());
+    StreamLease lease;
+    Batch b = import_device(&view, in_schema, &mask, in_owner);
+    std::vector<int64_t> rows;
+    Batch r = run_partial_aggregate(*plan, b, n_parts, rows, lease.s);
+    for (int i = 0; i < n_parts; ++i) part_rows[i] = rows[i];
+    export_device(r, out, out_schema);
+  });
+}
+
+int ark_sql_final_aggregate_device(ark_proc_t* p, ArrowDeviceArray* in, ArrowSchema* in_schema, ArrowDeviceArray* out,
+                                   ArrowSchema* out_schema) {
+  BufferPtr in_owner = adopt_array(&in->array);
+  return guarded([&] {
+    SqlProcessor* sp = as_sql(p);
+    if (!in_owner) fail(ARK_ERR_PROCESS, "input array already released");
+    ArrowDeviceArray view = *in;
+    view.array = *(const ArrowArray*)in_owner.get();
+    auto plan = sp->last_aggregate_plan();
+    if (!plan) fail(ARK_ERR_PROCESS, "final aggregate called before any partial aggregate bound the query");
+    StreamLease lease;
+    Batch b = import_device(&view, in_schema, nullptr, in_owner);
+    Batch r = run_final_aggregate(*plan, b, lease.s);
+    export_device(r, out, out_schema);
+  });
+}
+
 int ark_proc_close(ark_proc_t*) { return ARK_OK; }  // Processor::close is a no-op in the reference (sql.rs:222-224)
 
 void ark_proc_destroy(ark_proc_t* p) { delete p; }

@@ -39,13 +39,19 @@ std::shared_ptr<const Plan> SqlProcessor::plan_for(const std::vector<Field>& fie
   {
     std::lock_guard<std::mutex> l(mu_);
     auto it = plans_.find(key);
-    if (it != plans_.end()) return it->second;
+    if (it != plans_.end()) { if (it->second->kind == Plan::Aggregate) last_agg_ = it->second; return it->second; }
   }
   auto plan = std::make_shared<Plan>(bind_query(ast, table_name, fields));
   std::lock_guard<std::mutex> l(mu_);
   if (plans_.size() > 64) plans_.clear();
   plans_[key] = plan;
+  if (plan->kind == Plan::Aggregate) last_agg_ = plan;
   return plan;
+}
+
+std::shared_ptr<const Plan> SqlProcessor::last_aggregate_plan() {
+  std::lock_guard<std::mutex> l(mu_);
+  return last_agg_;
 }
 
 std::shared_ptr<const Plan> SqlProcessor::join_plan_for(const std::vector<std::string>& names,

@@ -43,6 +43,8 @@ struct SqlProcessor : Processor {
 
   // plan cache: one bound plan per distinct input schema
   std::shared_ptr<const Plan> plan_for(const std::vector<Field>& fields);
+  // the aggregate plan most recently bound by this processor (the final merge sees only partial states)
+  std::shared_ptr<const Plan> last_aggregate_plan();
   std::shared_ptr<const Plan> join_plan_for(const std::vector<std::string>& names,
                                             const std::vector<std::vector<Field>>& tables);
 
@@ -52,10 +54,14 @@ struct SqlProcessor : Processor {
  private:
   std::mutex mu_;
   std::map<std::string, std::shared_ptr<const Plan>> plans_;
+  std::shared_ptr<const Plan> last_agg_;
 };
 
 Batch run_filter_project(const Plan& plan, Batch& in, cudaStream_t stream);
 Batch run_aggregate(const Plan& plan, Batch& in, cudaStream_t stream);
 Batch run_join(const Plan& plan, Batch& left, Batch& right, cudaStream_t stream);
+Batch run_partial_aggregate(const Plan& plan, Batch& in, int n_parts, std::vector<int64_t>& part_rows, cudaStream_t stream);
+Batch run_final_aggregate(const Plan& plan, Batch& partial, cudaStream_t stream);
+Batch synth_batch(int64_t n, int64_t row0, uint64_t seed, int value_kind, int64_t key_space, cudaStream_t stream);
 
 }  // namespace ark

@@ -1,0 +1,730 @@
+// hash_agg.cu — GROUP BY hash-aggregate: WHERE + key hashing + accumulate in one pass over the
+// input, against an open-addressing table that stays L2-resident (126 MB L2 on B200).
+//
+// Stands in for DataFusion's AggregateExec(Partial) → RepartitionExec(Hash) → AggregateExec(Final)
+// (third-party; reached from crates/arkflow-plugin/src/processor/sql.rs:126-129).  The same kernel
+// runs the *final* merge of partial states on the multi-GPU path (sum of sums / counts, min of mins).
+//
+// Table: keys[capacity] of 16-byte Key16 claimed with a single 128-bit CAS (ATOMG.CAS.128), one
+// u64 accumulator array per aggregate updated with fire-and-forget RED atomics; a warp whose
+// lanes all hit the same group reduces with shuffles first (global aggregates, hot keys).
+// Algorithmic traffic = key + argument bytes read once (24 B/row for config 3).
+#include <cub/device/device_scan.cuh>
+
+#include "engine.h"
+#include "hash_agg.cuh"
+#include "vm.cuh"
+
+namespace ark {
+
+namespace {
+
+__device__ __forceinline__ Key16 cas128(Key16* addr, Key16 cmp, Key16 val) {
+  Key16 old;
+  asm volatile(
+      "{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\t"
+      "atom.relaxed.gpu.global.cas.b128 o, [%6], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
+      : "=l"(old.lo), "=l"(old.hi)
+      : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(addr)
+      : "memory");
+  return old;
+}
+__device__ __forceinline__ Key16 ld128(const Key16* addr) {  // single 128-bit access (LDG.E.128.STRONG.GPU)
+  Key16 v;
+  asm volatile("{\n\t.reg .b128 t;\n\tld.relaxed.gpu.global.b128 t, [%2];\n\tmov.b128 {%0, %1}, t;\n\t}"
+               : "=l"(v.lo), "=l"(v.hi) : "l"(addr) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ unsigned long long hash_key16(Key16 k) {
+  return mix64(k.lo * 0x9E3779B97F4A7C15ull + mix64(k.hi + 0x632BE59BD9B4E019ull));
+}
+__device__ inline unsigned long long hash_bytes(const uint8_t* p, int len) {
+  unsigned long long h = 0xCBF29CE484222325ull;
+  for (int i = 0; i < len; ++i) { h ^= p[i]; h *= 0x100000001B3ull; }
+  return mix64(h ^ (unsigned long long)len);
+}
+
+// Builds the table key of (column c, row): Key16 + 64-bit hash.
+__device__ inline void make_key(int kind, const ColView& c, int64_t row, Key16* key, unsigned long long* hash) {
+  Key16 k;
+  if (kind == KEY_NONE) { k.lo = 0; k.hi = (unsigned long long)KEYTAG_INT << 32; *key = k; *hash = 0; return; }
+  if (!col_valid(c, row)) { k.lo = 0; k.hi = (unsigned long long)KEYTAG_NULL << 32; *key = k; *hash = hash_key16(k); return; }
+  if (kind == KEY_INT64) {
+    k.lo = ((const unsigned long long*)c.data)[row]; k.hi = (unsigned long long)KEYTAG_INT << 32;
+  } else if (kind == KEY_BOOL) {
+    k.lo = bit_get((const uint8_t*)c.data, row + c.data_bit0); k.hi = (unsigned long long)KEYTAG_INT << 32;
+  } else {
+    const int32_t o0 = c.offsets[row], o1 = c.offsets[row + 1];
+    const int len = o1 - o0;
+    const uint8_t* p = (const uint8_t*)c.data + o0;
+    if (len <= 12) {
+      unsigned w[3] = {0, 0, 0};
+      if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) {
+        const unsigned* q = (const unsigned*)p;
+        for (int i = 0; i < 3; ++i) {
+          const int rem = len - 4 * i;
+          if (rem >= 4) w[i] = q[i];
+          else if (rem > 0) { for (int b = 0; b < rem; ++b) w[i] |= (unsigned)p[4 * i + b] << (8 * b); }
+        }
+      } else {
+        for (int b = 0; b < len; ++b) w[b >> 2] |= (unsigned)p[b] << (8 * (b & 3));
+      }
+      k.lo = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
+      k.hi = (unsigned long long)w[2] | ((unsigned long long)(unsigned)len << 32);
+    } else {
+      unsigned prefix = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
+      k.lo = (unsigned long long)row;
+      k.hi = (unsigned long long)prefix | ((unsigned long long)(KEYTAG_LONG | (unsigned)len) << 32);
+      *key = k; *hash = hash_bytes(p, len); return;
+    }
+  }
+  *key = k; *hash = hash_key16(k);
+}
+
+__device__ __forceinline__ bool key_is_long(Key16 k) {
+  const unsigned tag = (unsigned)(k.hi >> 32);
+  return (tag & KEYTAG_LONG) && tag < KEYTAG_NULL;
+}
+
+// equality of a probing key with a stored key (long keys: compare the bytes of both rows)
+__device__ inline bool key_equal(Key16 mine, Key16 stored, const ColView& c) {
+  if (!key_is_long(mine)) return mine.lo == stored.lo && mine.hi == stored.hi;
+  if (mine.hi != stored.hi) return false;
+  if (mine.lo == stored.lo) return true;
+  const int len = (int)((unsigned)(mine.hi >> 32) & 0x7FFFFFFFu);
+  const uint8_t* a = (const uint8_t*)c.data + c.offsets[(int64_t)mine.lo];
+  const uint8_t* b = (const uint8_t*)c.data + c.offsets[(int64_t)stored.lo];
+  for (int i = 0; i < len; ++i) if (a[i] != b[i]) return false;
+  return true;
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ long long warp_min_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+  return v;
+}
+__device__ __forceinline__ long long warp_max_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+  return v;
+}
+
+__global__ void agg_init_kernel(Key16* keys, unsigned long long capacity, int n_acc, AccParam a0, AccParam a1, AccParam a2,
+                                AccParam a3, AccParam a4, AccParam a5, AccParam a6, AccParam a7) {
+  const AccParam accs[AGG_MAX_ACC] = {a0, a1, a2, a3, a4, a5, a6, a7};
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    keys[i] = Key16{KEY_EMPTY, KEY_EMPTY};
+    for (int a = 0; a < n_acc; ++a) {
+      unsigned long long init = 0;
+      if (accs[a].kind == ACC_MIN_I64 || accs[a].kind == ACC_MIN_F64) init = 0x7FFFFFFFFFFFFFFFull;
+      if (accs[a].kind == ACC_MAX_I64 || accs[a].kind == ACC_MAX_F64) init = 0x8000000000000000ull;
+      accs[a].acc[i] = init;
+    }
+  }
+}
+
+constexpr int AGG_THREADS = 256;
+
+template <int PRED>
+__global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_constant__ AggParams P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = P.n_rows;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int32_t err = 0;
+  const ColView& kc = P.cols[P.key_kind == KEY_NONE ? 0 : P.key_slot];
+  if (P.key_kind == KEY_NONE && blockIdx.x == 0 && threadIdx.x == 0) {
+    // a global aggregate always yields one row, even when no row survives the filter
+    Key16 mine; unsigned long long h;
+    make_key(KEY_NONE, kc, 0, &mine, &h);
+    Key16 cur = cas128(P.keys + (h & P.mask), Key16{KEY_EMPTY, KEY_EMPTY}, mine);
+    if (cur.hi == KEY_EMPTY && cur.lo == KEY_EMPTY) atomicAdd(P.group_count, 1u);
+  }
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+    const int64_t row = base + threadIdx.x;
+    bool ok = row < n;
+    if (PRED == 1) {
+      if (ok) {
+        const ColView& c = P.cols[P.sp_slot];
+        const unsigned long long v = ((const unsigned long long*)c.data)[row];
+        if (P.sp_is_f64) ok = cmp_i64(P.sp_cmp, f64_total_key(v), f64_total_key(P.sp_const));
+        else ok = cmp_i64(P.sp_cmp, (int64_t)v, (int64_t)P.sp_const);
+        ok = ok && col_valid(c, row);
+      }
+    } else if (PRED == 2) {
+      if (ok) { VmVal v = vm_eval(P.pred, P.cols, row, &err); ok = v.valid && (v.bits & 1); }
+    }
+    unsigned long long slot = 0;
+    if (ok) {
+      Key16 mine; unsigned long long h;
+      make_key(P.key_kind, kc, row, &mine, &h);
+      slot = h & P.mask;
+      int probes = 0;
+      while (true) {
+        Key16 cur = ld128(P.keys + slot);
+        if (cur.hi == KEY_EMPTY) {
+          cur = cas128(P.keys + slot, Key16{KEY_EMPTY, KEY_EMPTY}, mine);
+          if (cur.hi == KEY_EMPTY && cur.lo == KEY_EMPTY) {  // claimed
+            const unsigned g = atomicAdd(P.group_count, 1u);
+            if (g >= P.max_groups) atomicExch(P.overflow, 1);
+            break;
+          }
+        }
+        if (key_equal(mine, cur, kc)) break;
+        slot = (slot + 1) & P.mask;
+        if (++probes > 4096) { atomicExch(P.overflow, 1); ok = false; break; }
+      }
+    }
+    // warp-uniform group ⇒ reduce with shuffles, one atomic per warp
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (m == 0) continue;
+    const int leader = __ffs(m) - 1;
+    const unsigned long long slot0 = __shfl_sync(0xffffffffu, slot, leader);
+    const bool uniform = __all_sync(0xffffffffu, !ok || slot == slot0) && __popc(m) > 1;
+    for (int a = 0; a < P.n_acc; ++a) {
+      const AccParam& A = P.accs[a];
+      unsigned long long bits = 0;
+      bool valid = ok;
+      if (ok && A.kind != ACC_COUNT_STAR) {
+        if (A.arg_prog >= 0) { VmVal v = vm_eval(P.progs[A.arg_prog], P.cols, row, &err); bits = v.bits; valid = v.valid; }
+        else { const ColView& c = P.cols[A.arg_slot]; valid = col_valid(c, row); bits = valid ? ((const unsigned long long*)c.data)[row] : 0; }
+      }
+      unsigned long long* dst = A.acc + (uniform ? slot0 : slot);
+      switch (A.kind) {
+        case ACC_COUNT_STAR:
+        case ACC_COUNT: {
+          if (uniform) { const int c = __popc(__ballot_sync(0xffffffffu, valid)); if (lane == leader && c) atomicAdd(dst, (unsigned long long)c); }
+          else if (valid) atomicAdd(dst, 1ull);
+          break;
+        }
+        case ACC_SUM_I64: {
+          if (uniform) { const long long s = warp_sum_ll(valid ? (long long)bits : 0); if (lane == leader) atomicAdd(dst, (unsigned long long)s); }
+          else if (valid) atomicAdd(dst, bits);
+          break;
+        }
+        case ACC_SUM_F64: {
+          double x = A.arg_is_f64 ? __longlong_as_double((long long)bits) : (double)(long long)bits;
+          if (uniform) { const double s = warp_sum_f64(valid ? x : 0.0); if (lane == leader) atomicAdd((double*)dst, s); }
+          else if (valid) atomicAdd((double*)dst, x);
+          break;
+        }
+        case ACC_MIN_I64: case ACC_MIN_F64: {
+          long long x = A.kind == ACC_MIN_F64 ? f64_total_key(bits) : (long long)bits;
+          if (uniform) { const long long s = warp_min_ll(valid ? x : 0x7FFFFFFFFFFFFFFFll); if (lane == leader) atomicMin((long long*)dst, s); }
+          else if (valid) atomicMin((long long*)dst, x);
+          break;
+        }
+        default: {
+          long long x = A.kind == ACC_MAX_F64 ? f64_total_key(bits) : (long long)bits;
+          if (uniform) { const long long s = warp_max_ll(valid ? x : (long long)0x8000000000000000ull); if (lane == leader) atomicMax((long long*)dst, s); }
+          else if (valid) atomicMax((long long*)dst, x);
+          break;
+        }
+      }
+    }
+  }
+  if (err) atomicExch(P.error, err);
+}
+
+// ---- table → dense group list, ordered by partition = hash(key) mod n_parts -----------------------
+__device__ __forceinline__ unsigned long long stored_key_hash(Key16 k, const ColView& kc) {
+  if (key_is_long(k)) {
+    const int len = (int)((unsigned)(k.hi >> 32) & 0x7FFFFFFFu);
+    return hash_bytes((const uint8_t*)kc.data + kc.offsets[(int64_t)k.lo], len);
+  }
+  return hash_key16(k);
+}
+__device__ __forceinline__ int partition_of(unsigned long long h, int n_parts) {
+  return (int)(((h >> 40) * (unsigned long long)n_parts) >> 24);  // top 24 bits → [0, n_parts)
+}
+
+__global__ void agg_count_parts_kernel(const Key16* keys, unsigned long long capacity, ColView kc, int key_kind, int n_parts,
+                                       unsigned int* part_counts) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    Key16 k = keys[i];
+    if (k.hi == KEY_EMPTY) continue;
+    const int p = n_parts > 1 ? partition_of(key_kind == KEY_NONE ? 0 : stored_key_hash(k, kc), n_parts) : 0;
+    atomicAdd(part_counts + p, 1u);
+  }
+}
+
+// part_cursor[p] starts at the exclusive prefix of part_counts; slots[] receives table slot ids
+__global__ void agg_compact_kernel(const Key16* keys, unsigned long long capacity, ColView kc, int key_kind, int n_parts,
+                                   unsigned int* part_cursor, unsigned int* slots) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    Key16 k = keys[i];
+    if (k.hi == KEY_EMPTY) continue;
+    const int p = n_parts > 1 ? partition_of(key_kind == KEY_NONE ? 0 : stored_key_hash(k, kc), n_parts) : 0;
+    slots[atomicAdd(part_cursor + p, 1u)] = (unsigned int)i;
+  }
+}
+
+__global__ void agg_key_lengths_kernel(const Key16* keys, const unsigned int* slots, unsigned int n_groups, int32_t* lens) {
+  unsigned int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  Key16 k = keys[slots[g]];
+  const unsigned tag = (unsigned)(k.hi >> 32);
+  lens[g] = tag == KEYTAG_NULL ? 0 : (int32_t)(tag & 0x7FFFFFFFu);
+}
+
+// materialise the key column of the dense group list
+__global__ void agg_emit_keys_kernel(const Key16* keys, const unsigned int* slots, unsigned int n_groups, ColView kc, int key_kind,
+                                     unsigned long long* out_fixed, uint8_t* out_bool_bytes, const int32_t* out_offsets,
+                                     uint8_t* out_bytes, uint8_t* out_valid_bytes) {
+  unsigned int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  Key16 k = keys[slots[g]];
+  const unsigned tag = (unsigned)(k.hi >> 32);
+  const bool is_null = tag == KEYTAG_NULL;
+  if (out_valid_bytes) out_valid_bytes[g] = !is_null;
+  if (key_kind == KEY_INT64) out_fixed[g] = is_null ? 0 : k.lo;
+  else if (key_kind == KEY_BOOL) out_bool_bytes[g] = is_null ? 0 : (uint8_t)(k.lo & 1);
+  else if (key_kind == KEY_BYTES && !is_null) {
+    uint8_t* d = out_bytes + out_offsets[g];
+    const int len = (int)(tag & 0x7FFFFFFFu);
+    if (tag & KEYTAG_LONG) {
+      const uint8_t* s = (const uint8_t*)kc.data + kc.offsets[(int64_t)k.lo];
+      for (int i = 0; i < len; ++i) d[i] = s[i];
+    } else {
+      for (int i = 0; i < len; ++i) d[i] = (uint8_t)((i < 8 ? (k.lo >> (8 * i)) : (k.hi >> (8 * (i - 8)))) & 0xff);
+    }
+  }
+}
+
+// dense accumulator columns: gather acc[slots[g]]
+__global__ void agg_gather_acc_kernel(const unsigned long long* acc, const unsigned int* slots, unsigned int n_groups,
+                                      unsigned long long* out) {
+  unsigned int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_groups) out[g] = acc[slots[g]];
+}
+
+enum FinalOp : int32_t { FIN_COPY = 0, FIN_AVG = 1, FIN_F64_KEY_BACK = 2, FIN_CONST = 3 };
+// out[g] = op(a[g], b[g]); valid[g] = (nn == null || nn[g] > 0)
+__global__ void agg_finalize_kernel(int op, const unsigned long long* a, const unsigned long long* cnt, unsigned long long constant,
+                                    unsigned int n_groups, unsigned long long* out, uint8_t* out_valid_bytes) {
+  unsigned int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const bool valid = cnt == nullptr || cnt[g] > 0;
+  unsigned long long r = 0;
+  if (op == FIN_CONST) r = constant;
+  else if (valid) {
+    if (op == FIN_COPY) r = a[g];
+    else if (op == FIN_AVG) r = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)a[g]) / (double)cnt[g]);
+    else { long long s = (long long)a[g]; r = (unsigned long long)(s ^ (long long)(((unsigned long long)(s >> 63)) >> 1)); }
+  }
+  out[g] = r;
+  if (out_valid_bytes) out_valid_bytes[g] = valid;
+}
+
+template <int PRED>
+void launch_agg(const AggParams& P, int grid, cudaStream_t stream) {
+  KernelTimer t("hash_agg_kernel", stream);
+  hash_agg_kernel<PRED><<<grid, AGG_THREADS, 0, stream>>>(P);
+}
+
+struct AccPlan {  // host-side description of one accumulator
+  AccKind kind;
+  int arg_slot = -1;
+  int arg_prog = -1;
+  bool arg_is_f64 = false;
+};
+
+}  // namespace
+
+// ---- executor ---------------------------------------------------------------------------------------
+// AggExec: the physical aggregate — key, accumulators, how SELECT items derive from them.
+struct AggExec {
+  int key_kind = KEY_NONE;
+  int key_slot = 0;
+  DType key_type = DType::Null;
+  std::vector<AccPlan> accs;
+  std::vector<VmProgram> progs;
+  int find_or_add(const AccPlan& a) {
+    for (size_t i = 0; i < accs.size(); ++i)
+      if (accs[i].kind == a.kind && accs[i].arg_slot == a.arg_slot && accs[i].arg_prog == a.arg_prog && accs[i].arg_is_f64 == a.arg_is_f64)
+        return (int)i;
+    if ((int)accs.size() >= AGG_MAX_ACC) fail(ARK_ERR_UNSUPPORTED, "too many aggregate accumulators in one query");
+    accs.push_back(a);
+    return (int)accs.size() - 1;
+  }
+};
+
+struct AggOutput {  // one aggregate of the SELECT list expressed over accumulators
+  int value_acc = -1;    // accumulator holding the value (sum / min / max / count)
+  int count_acc = -1;    // accumulator whose >0 decides validity (and divides for AVG); -1 ⇒ always valid
+  int final_op = FIN_COPY;
+  DType type = DType::Int64;
+  bool can_be_null = false;  // count_acc is a dedicated non-null counter (argument may be NULL)
+};
+
+struct DenseGroups {  // result of the hash pass: dense arrays of G groups, partition-ordered
+  unsigned int n_groups = 0;
+  std::vector<int64_t> part_rows;
+  BufferPtr keys, slots;                 // table + dense slot list
+  std::vector<BufferPtr> acc_tables;     // per accumulator, table-indexed
+  unsigned long long capacity = 0;
+};
+
+static std::atomic<unsigned long long> g_capacity_hint{1ull << 16};
+
+static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int n_parts, cudaStream_t stream) {
+  const int64_t n = in.num_rows;
+  unsigned long long capacity = std::max<unsigned long long>(g_capacity_hint.load(), 1ull << 12);
+  const unsigned long long cap_limit = 1ull << 31;
+  DenseGroups dg;
+  BufferPtr ctl = device_alloc(256);  // [group_count u32 | overflow i32 | error i32 | pad | part_counts u32[32] | part_cursor u32[32]]
+  BufferPtr hctl = pinned_alloc(256);
+  if (n_parts > 32) fail(ARK_ERR_UNSUPPORTED, "more than 32 partitions");
+  while (true) {
+    dg.keys = device_alloc((size_t)capacity * sizeof(Key16));
+    dg.acc_tables.clear();
+    AggParams P;
+    memset(&P, 0, sizeof P);
+    P.n_rows = n;
+    P.pred_kind = !plan.has_pred ? 0 : (plan.simple.enabled ? 1 : 2);
+    if (P.pred_kind == 1) { P.sp_slot = plan.simple.slot; P.sp_cmp = plan.simple.cmp; P.sp_is_f64 = plan.simple.is_f64; P.sp_const = plan.simple.constant; }
+    if (P.pred_kind == 2) P.pred = plan.pred;
+    P.key_kind = ex.key_kind; P.key_slot = ex.key_slot;
+    for (size_t s = 0; s < plan.used_cols.size(); ++s) P.cols[s] = in.cols[plan.used_cols[s]].view();
+    P.n_acc = (int)ex.accs.size();
+    for (size_t a = 0; a < ex.accs.size(); ++a) {
+      BufferPtr t = device_alloc((size_t)capacity * 8);
+      dg.acc_tables.push_back(t);
+      P.accs[a].kind = ex.accs[a].kind; P.accs[a].arg_slot = ex.accs[a].arg_slot; P.accs[a].arg_prog = ex.accs[a].arg_prog;
+      P.accs[a].arg_is_f64 = ex.accs[a].arg_is_f64; P.accs[a].acc = (unsigned long long*)t.get();
+    }
+    for (size_t i = 0; i < ex.progs.size(); ++i) P.progs[i] = ex.progs[i];
+    P.keys = (Key16*)dg.keys.get();
+    P.mask = capacity - 1;
+    P.group_count = (unsigned int*)ctl.get();
+    P.overflow = (int32_t*)((char*)ctl.get() + 4);
+    P.error = (int32_t*)((char*)ctl.get() + 8);
+    P.max_groups = (unsigned int)std::min<unsigned long long>(capacity / 2, 0x7FFFFFFFull);
+    ARK_CUDA(cudaMemsetAsync(ctl.get(), 0, 256, stream));
+    {
+      KernelTimer t("agg_init_kernel", stream);
+      const int grid = (int)std::min<unsigned long long>((capacity + 255) / 256, 148ull * 8);
+      agg_init_kernel<<<grid, 256, 0, stream>>>(P.keys, capacity, P.n_acc, P.accs[0], P.accs[1], P.accs[2], P.accs[3], P.accs[4],
+                                                P.accs[5], P.accs[6], P.accs[7]);
+    }
+    {
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, AGG_THREADS), 148 * 8));
+      if (P.pred_kind == 0) launch_agg<0>(P, grid, stream);
+      else if (P.pred_kind == 1) launch_agg<1>(P, grid, stream);
+      else launch_agg<2>(P, grid, stream);
+    }
+    ARK_CUDA(cudaGetLastError());
+    ARK_CUDA(cudaMemcpyAsync(hctl.get(), ctl.get(), 16, cudaMemcpyDeviceToHost, stream));
+    ARK_CUDA(cudaStreamSynchronize(stream));
+    const unsigned int groups = *(unsigned int*)hctl.get();
+    const int overflow = *(int32_t*)((char*)hctl.get() + 4);
+    const int err = *(int32_t*)((char*)hctl.get() + 8);
+    if (overflow) {
+      if (capacity >= cap_limit) fail(ARK_ERR_PROCESS, "Collection query results error: group-by hash table exceeded 2^31 slots");
+      capacity *= 4;
+      continue;
+    }
+    if (err) fail(ARK_ERR_PROCESS, std::string("Collection query results error: ") +
+                                       (err == VMERR_DIV_ZERO ? "Arrow error: Divide by zero error" : "Arrow error: arithmetic/cast error"));
+    dg.n_groups = groups;
+    dg.capacity = capacity;
+    // next batch: size for 4× the groups just seen (load ≤ 0.25), at least 2^12
+    unsigned long long want = 1ull << 12;
+    while (want < 4ull * groups) want <<= 1;
+    g_capacity_hint.store(want);
+    break;
+  }
+  // dense, partition-ordered slot list
+  const ColView kc = ex.key_kind == KEY_NONE ? ColView{} : in.cols[plan.used_cols[ex.key_slot]].view();
+  unsigned int* part_counts = (unsigned int*)((char*)ctl.get() + 16);
+  unsigned int* part_cursor = (unsigned int*)((char*)ctl.get() + 16 + 128);
+  dg.slots = device_alloc((size_t)std::max<unsigned int>(dg.n_groups, 1) * 4);
+  dg.part_rows.assign(n_parts, 0);
+  const int sgrid = (int)std::min<unsigned long long>((dg.capacity + 255) / 256, 148ull * 8);
+  if (n_parts > 1) {
+    {
+      KernelTimer t("agg_count_parts_kernel", stream);
+      agg_count_parts_kernel<<<sgrid, 256, 0, stream>>>((const Key16*)dg.keys.get(), dg.capacity, kc, ex.key_kind, n_parts, part_counts);
+    }
+    ARK_CUDA(cudaMemcpyAsync((char*)hctl.get() + 16, part_counts, 128, cudaMemcpyDeviceToHost, stream));
+    ARK_CUDA(cudaStreamSynchronize(stream));
+    unsigned int* hc = (unsigned int*)((char*)hctl.get() + 16);
+    unsigned int* hcur = (unsigned int*)((char*)hctl.get() + 16 + 128);
+    unsigned int run = 0;
+    for (int p = 0; p < n_parts; ++p) { dg.part_rows[p] = hc[p]; hcur[p] = run; run += hc[p]; }
+    ARK_CUDA(cudaMemcpyAsync(part_cursor, hcur, 128, cudaMemcpyHostToDevice, stream));
+  } else {
+    dg.part_rows[0] = dg.n_groups;
+  }
+  if (dg.n_groups > 0) {
+    KernelTimer t("agg_compact_kernel", stream);
+    agg_compact_kernel<<<sgrid, 256, 0, stream>>>((const Key16*)dg.keys.get(), dg.capacity, kc, ex.key_kind, n_parts, part_cursor,
+                                                  (unsigned int*)dg.slots.get());
+  }
+  ARK_CUDA(cudaGetLastError());
+  return dg;
+}
+
+// key column of the dense groups
+static Column emit_key_column(const AggExec& ex, const DenseGroups& dg, const Column& src, const std::string& name,
+                              bool nullable, cudaStream_t stream) {
+  const unsigned int G = dg.n_groups;
+  Column c;
+  c.field.name = name; c.field.type = ex.key_type; c.field.nullable = nullable; c.length = G;
+  const ColView kc = src.view();
+  const bool may_null = src.validity != nullptr;
+  BufferPtr valid_bytes = may_null ? device_alloc(std::max<size_t>(G, 1)) : BufferPtr();
+  const unsigned grid = (unsigned)ceil_div(std::max<unsigned int>(G, 1), 256);
+  const Key16* keys = (const Key16*)dg.keys.get();
+  const unsigned int* slots = (const unsigned int*)dg.slots.get();
+  if (ex.key_kind == KEY_BYTES) {
+    BufferPtr lens = device_alloc((size_t)(G + 1) * 4), offs = device_alloc((size_t)(G + 1) * 4);
+    ARK_CUDA(cudaMemsetAsync(lens.get(), 0, (size_t)(G + 1) * 4, stream));
+    if (G) {
+      KernelTimer t("agg_key_lengths_kernel", stream);
+      agg_key_lengths_kernel<<<grid, 256, 0, stream>>>(keys, slots, G, (int32_t*)lens.get());
+    }
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (int32_t*)lens.get(), (int32_t*)offs.get(), (int)(G + 1), stream);
+    BufferPtr tmp = device_alloc(tmp_bytes + 16);
+    note_launch("cub::DeviceScan::ExclusiveSum");
+    cub::DeviceScan::ExclusiveSum(tmp.get(), tmp_bytes, (int32_t*)lens.get(), (int32_t*)offs.get(), (int)(G + 1), stream);
+    BufferPtr h = pinned_alloc(64);
+    ARK_CUDA(cudaMemcpyAsync(h.get(), (int32_t*)offs.get() + G, 4, cudaMemcpyDeviceToHost, stream));
+    ARK_CUDA(cudaStreamSynchronize(stream));
+    const int32_t total = *(int32_t*)h.get();
+    BufferPtr bytes = device_alloc((size_t)total + 16);
+    if (G) {
+      KernelTimer t("agg_emit_keys_kernel", stream);
+      agg_emit_keys_kernel<<<grid, 256, 0, stream>>>(keys, slots, G, kc, ex.key_kind, nullptr, nullptr, (const int32_t*)offs.get(),
+                                                     (uint8_t*)bytes.get(), (uint8_t*)valid_bytes.get());
+    }
+    c.offsets = (const int32_t*)offs.get(); c.data = (const uint8_t*)bytes.get(); c.data_bytes = total; c.first_offset = 0;
+    c.owners = {offs, bytes};
+  } else if (ex.key_kind == KEY_INT64) {
+    BufferPtr vals = device_alloc((size_t)std::max<unsigned int>(G, 1) * 8);
+    if (G) {
+      KernelTimer t("agg_emit_keys_kernel", stream);
+      agg_emit_keys_kernel<<<grid, 256, 0, stream>>>(keys, slots, G, kc, ex.key_kind, (unsigned long long*)vals.get(), nullptr, nullptr,
+                                                     nullptr, (uint8_t*)valid_bytes.get());
+    }
+    c.data = (const uint8_t*)vals.get(); c.data_bytes = (int64_t)G * 8; c.owners = {vals};
+  } else {  // KEY_BOOL
+    BufferPtr bb = device_alloc(std::max<size_t>(G, 1)), bits = device_alloc((size_t)(G + 7) / 8 + 1);
+    if (G) {
+      KernelTimer t("agg_emit_keys_kernel", stream);
+      agg_emit_keys_kernel<<<grid, 256, 0, stream>>>(keys, slots, G, kc, ex.key_kind, nullptr, (uint8_t*)bb.get(), nullptr, nullptr,
+                                                     (uint8_t*)valid_bytes.get());
+    }
+    launch_pack_bits((const uint8_t*)bb.get(), G, (uint8_t*)bits.get(), nullptr, stream);
+    c.data = (const uint8_t*)bits.get(); c.data_bytes = (G + 7) / 8; c.owners = {bits, bb};
+  }
+  if (may_null && G) {
+    BufferPtr vbits = device_alloc((size_t)(G + 7) / 8 + 1);
+    launch_pack_bits((const uint8_t*)valid_bytes.get(), G, (uint8_t*)vbits.get(), nullptr, stream);
+    c.validity = (const uint8_t*)vbits.get(); c.null_count = -1;
+    c.owners.push_back(vbits); c.owners.push_back(valid_bytes);
+  }
+  return c;
+}
+
+static BufferPtr gather_acc(const DenseGroups& dg, int acc, cudaStream_t stream) {
+  const unsigned int G = dg.n_groups;
+  BufferPtr out = device_alloc((size_t)std::max<unsigned int>(G, 1) * 8);
+  if (G) {
+    KernelTimer t("agg_gather_acc_kernel", stream);
+    agg_gather_acc_kernel<<<(unsigned)ceil_div(G, 256), 256, 0, stream>>>((const unsigned long long*)dg.acc_tables[acc].get(),
+                                                                         (const unsigned int*)dg.slots.get(), G, (unsigned long long*)out.get());
+  }
+  return out;
+}
+
+static Column finalize_column(const std::string& name, DType type, int op, BufferPtr a, BufferPtr cnt, uint64_t constant, bool nullable,
+                              unsigned int G, cudaStream_t stream) {
+  Column c;
+  c.field.name = name; c.field.type = type; c.field.nullable = nullable; c.length = G;
+  BufferPtr out = device_alloc((size_t)std::max<unsigned int>(G, 1) * 8);
+  BufferPtr vb = (cnt && nullable) ? device_alloc(std::max<size_t>(G, 1)) : BufferPtr();
+  if (G) {
+    KernelTimer t("agg_finalize_kernel", stream);
+    agg_finalize_kernel<<<(unsigned)ceil_div(G, 256), 256, 0, stream>>>(op, (const unsigned long long*)a.get(), (const unsigned long long*)cnt.get(),
+                                                                       constant, G, (unsigned long long*)out.get(), (uint8_t*)vb.get());
+  }
+  c.data = (const uint8_t*)out.get(); c.data_bytes = (int64_t)G * 8; c.owners = {out};
+  if (vb && G) {
+    BufferPtr bits = device_alloc((size_t)(G + 7) / 8 + 1);
+    launch_pack_bits((const uint8_t*)vb.get(), G, (uint8_t*)bits.get(), nullptr, stream);
+    c.validity = (const uint8_t*)bits.get(); c.null_count = -1;
+    c.owners.push_back(bits); c.owners.push_back(vb);
+  }
+  return c;
+}
+
+// Builds the physical aggregate of a bound plan.  merge == false: over raw rows.  merge == true:
+// over partial-state rows (column layout produced by partial_state_batch below).
+static void build_exec(const Plan& plan, const Batch* in, AggExec& ex, std::vector<AggOutput>& outs) {
+  const bool schema_nullability = in == nullptr;
+  if (plan.keys.size() > 1) fail(ARK_ERR_UNSUPPORTED, "more than one GROUP BY key");
+  if (!plan.keys.empty()) {
+    const ValueSource& k = plan.keys[0];
+    ex.key_slot = k.slot; ex.key_type = k.type;
+    ex.key_kind = k.type == DType::Int64 ? KEY_INT64 : (k.type == DType::Bool ? KEY_BOOL : KEY_BYTES);
+  }
+  auto arg_of = [&](const ValueSource& v, AccPlan& a, bool* nullable) {
+    if (v.kind == ValueSource::PassThrough) {
+      a.arg_slot = v.slot;
+      // multi-GPU: every rank must build the same accumulator layout ⇒ decide from the schema, not the buffers
+      *nullable = schema_nullability ? plan.input_fields[plan.used_cols[v.slot]].nullable : in->cols[plan.used_cols[v.slot]].validity != nullptr;
+    } else {
+      if ((int)ex.progs.size() >= AGG_MAX_PROGS) fail(ARK_ERR_UNSUPPORTED, "too many computed aggregate arguments");
+      a.arg_prog = (int)ex.progs.size(); ex.progs.push_back(v.prog);
+      *nullable = v.nullable;
+    }
+    a.arg_is_f64 = v.type == DType::Float64;
+  };
+  const int star = ex.find_or_add(AccPlan{ACC_COUNT_STAR});
+  for (const AggSpec& s : plan.aggs) {
+    AggOutput o;
+    o.type = s.out_type;
+    if (s.func == AggFunc::CountStar) { o.value_acc = star; outs.push_back(o); continue; }
+    AccPlan a; bool nullable = false;
+    arg_of(s.arg, a, &nullable);
+    int nn = star;
+    if (nullable) { AccPlan c = a; c.kind = ACC_COUNT; c.arg_is_f64 = false; nn = ex.find_or_add(c); o.can_be_null = true; }
+    switch (s.func) {
+      case AggFunc::Count: o.value_acc = nn; break;
+      case AggFunc::Sum: a.kind = a.arg_is_f64 ? ACC_SUM_F64 : ACC_SUM_I64; o.value_acc = ex.find_or_add(a); o.count_acc = nn; break;
+      case AggFunc::Avg: {
+        const bool was_f64 = a.arg_is_f64;
+        a.kind = ACC_SUM_F64; a.arg_is_f64 = was_f64;
+        o.value_acc = ex.find_or_add(a); o.count_acc = nn; o.final_op = FIN_AVG; break;
+      }
+      case AggFunc::Min: a.kind = a.arg_is_f64 ? ACC_MIN_F64 : ACC_MIN_I64; o.value_acc = ex.find_or_add(a); o.count_acc = nn;
+        o.final_op = a.arg_is_f64 ? FIN_F64_KEY_BACK : FIN_COPY; break;
+      case AggFunc::Max: a.kind = a.arg_is_f64 ? ACC_MAX_F64 : ACC_MAX_I64; o.value_acc = ex.find_or_add(a); o.count_acc = nn;
+        o.final_op = a.arg_is_f64 ? FIN_F64_KEY_BACK : FIN_COPY; break;
+      default: break;
+    }
+    outs.push_back(o);
+  }
+}
+
+static Batch project_groups(const Plan& plan, const AggExec& ex, const std::vector<AggOutput>& outs, const DenseGroups& dg,
+                            const Column* key_src, cudaStream_t stream) {
+  const unsigned int G = dg.n_groups;
+  Batch out;
+  out.num_rows = G;
+  std::vector<BufferPtr> dense(ex.accs.size());
+  auto dense_acc = [&](int a) -> BufferPtr { if (!dense[a]) dense[a] = gather_acc(dg, a, stream); return dense[a]; };
+  for (const PostItem& pi : plan.post) {
+    if (pi.kind == PostItem::Key) {
+      out.cols.push_back(emit_key_column(ex, dg, *key_src, pi.name, key_src->field.nullable, stream));
+    } else if (pi.kind == PostItem::Agg) {
+      const AggOutput& o = outs[pi.index];
+      const AggSpec& s = plan.aggs[pi.index];
+      const bool is_count = s.func == AggFunc::Count || s.func == AggFunc::CountStar;
+      BufferPtr cnt = o.count_acc >= 0 ? dense_acc(o.count_acc) : BufferPtr();
+      // a group exists only if it has ≥ 1 row, so COUNT(*) > 0: validity is needed only when the
+      // argument itself can be NULL (dedicated ACC_COUNT accumulator)
+      const bool can_be_null = !is_count && o.count_acc >= 0 && o.can_be_null;
+      Column col = finalize_column(pi.name, o.type, o.final_op, dense_acc(o.value_acc), cnt, 0, can_be_null, G, stream);
+      col.field.nullable = !is_count;
+      out.cols.push_back(col);
+    } else {
+      if (pi.lit_type == DType::Utf8) fail(ARK_ERR_UNSUPPORTED, "string literal in an aggregate SELECT list");
+      if (pi.lit_type == DType::Bool) fail(ARK_ERR_UNSUPPORTED, "boolean literal in an aggregate SELECT list");
+      out.cols.push_back(finalize_column(pi.name, pi.lit_type, FIN_CONST, BufferPtr(), BufferPtr(), pi.lit_bits, false, G, stream));
+    }
+  }
+  return out;
+}
+
+Batch run_aggregate(const Plan& plan, Batch& in, cudaStream_t stream) {
+  AggExec ex;
+  std::vector<AggOutput> outs;
+  build_exec(plan, &in, ex, outs);
+  DenseGroups dg = hash_pass(plan, ex, in, 1, stream);
+  const Column* key_src = ex.key_kind == KEY_NONE ? nullptr : &in.cols[plan.used_cols[ex.key_slot]];
+  Batch out = project_groups(plan, ex, outs, dg, key_src, stream);
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  return out;
+}
+
+// ---- multi-GPU building blocks: partial states out, hash-partitioned; merge in ----
+// Partial-state batch layout: [key column (if any)] + one 8-byte column per accumulator, in the
+// accumulator order build_exec() derives from the plan alone (identical on every rank).
+Batch run_partial_aggregate(const Plan& plan, Batch& in, int n_parts, std::vector<int64_t>& part_rows, cudaStream_t stream) {
+  AggExec ex;
+  std::vector<AggOutput> outs;
+  build_exec(plan, nullptr, ex, outs);
+  DenseGroups dg = hash_pass(plan, ex, in, n_parts, stream);
+  part_rows = dg.part_rows;
+  Batch out;
+  out.num_rows = dg.n_groups;
+  if (ex.key_kind != KEY_NONE) {
+    const Column& src = in.cols[plan.used_cols[ex.key_slot]];
+    out.cols.push_back(emit_key_column(ex, dg, src, plan.key_names[0], src.field.nullable, stream));
+  }
+  for (size_t a = 0; a < ex.accs.size(); ++a) {
+    Column c;
+    c.field.name = "__acc" + std::to_string(a);
+    c.field.type = ex.accs[a].kind == ACC_SUM_F64 ? DType::Float64 : DType::Int64;
+    c.field.nullable = false; c.length = dg.n_groups;
+    BufferPtr d = gather_acc(dg, (int)a, stream);
+    c.data = (const uint8_t*)d.get(); c.data_bytes = (int64_t)dg.n_groups * 8; c.owners = {d};
+    out.cols.push_back(c);
+  }
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  return out;
+}
+
+Batch run_final_aggregate(const Plan& plan, Batch& partial, cudaStream_t stream) {
+  AggExec ex;
+  std::vector<AggOutput> outs;
+  build_exec(plan, nullptr, ex, outs);  // same accumulator layout as the partial side
+  const int key_cols = ex.key_kind == KEY_NONE ? 0 : 1;
+  if ((int)partial.cols.size() != key_cols + (int)ex.accs.size())
+    fail(ARK_ERR_PROCESS, "final aggregate: partial-state batch has " + std::to_string(partial.cols.size()) + " columns, expected " +
+                              std::to_string(key_cols + ex.accs.size()));
+  AggExec mx;  // merge: aggregate the state columns
+  mx.key_kind = ex.key_kind; mx.key_slot = 0; mx.key_type = ex.key_type;
+  for (size_t a = 0; a < ex.accs.size(); ++a) {
+    AccPlan m;
+    m.arg_slot = key_cols + (int)a;
+    switch (ex.accs[a].kind) {
+      case ACC_COUNT_STAR: case ACC_COUNT: case ACC_SUM_I64: m.kind = ACC_SUM_I64; break;
+      case ACC_SUM_F64: m.kind = ACC_SUM_F64; m.arg_is_f64 = true; break;
+      case ACC_MIN_I64: case ACC_MIN_F64: m.kind = ACC_MIN_I64; break;   // F64 states travel as totalOrder keys
+      default: m.kind = ACC_MAX_I64; break;
+    }
+    mx.accs.push_back(m);  // no dedup: positions must line up with `outs`
+  }
+  Plan mp;
+  mp.kind = Plan::Aggregate;
+  for (size_t i = 0; i < partial.cols.size(); ++i) mp.used_cols.push_back((int)i);
+  if ((int)mp.used_cols.size() > MAX_COLS) fail(ARK_ERR_UNSUPPORTED, "too many accumulator columns");
+  DenseGroups dg = hash_pass(mp, mx, partial, 1, stream);
+  Batch out = project_groups(plan, mx, outs, dg, key_cols ? &partial.cols[0] : nullptr, stream);
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  return out;
+}
+
+}  // namespace ark

@@ -1,0 +1,62 @@
+// hash_agg.cuh — parameter blocks of the GROUP BY hash-aggregate kernels.
+#pragma once
+#include "vm.h"
+
+namespace ark {
+
+// 16-byte group key word stored in the table.  Utf8/Binary keys up to 12 bytes live inline
+// ("German string": 12 bytes + u32 length); longer keys store a 4-byte prefix + the row index of
+// the first row that inserted them (their bytes are compared against that row of the input).
+struct __align__(16) Key16 {
+  unsigned long long lo, hi;
+};
+
+constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;  // lo == hi == KEY_EMPTY ⇒ empty slot
+constexpr unsigned KEYTAG_NULL = 0xFFFFFFFEu;                    // tag (top 32 bits of hi) of the NULL key
+constexpr unsigned KEYTAG_LONG = 0x80000000u;                    // | length for keys longer than 12 bytes
+constexpr unsigned KEYTAG_INT = 0x40000000u;                     // Int64 / Bool key: lo = value
+
+enum AccKind : int32_t {
+  ACC_COUNT_STAR = 0,
+  ACC_COUNT,     // non-null values of arg
+  ACC_SUM_I64,   // wrapping
+  ACC_SUM_F64,   // arg converted to f64 when arg_is_f64 == 0 (AVG over Int64)
+  ACC_MIN_I64, ACC_MAX_I64,
+  ACC_MIN_F64, ACC_MAX_F64,  // on the totalOrder key
+};
+
+enum KeyKind : int32_t { KEY_NONE = 0, KEY_INT64 = 1, KEY_BYTES = 2, KEY_BOOL = 3 };
+
+constexpr int AGG_MAX_ACC = 8;
+constexpr int AGG_MAX_PROGS = 2;
+
+struct AccParam {
+  int32_t kind;
+  int32_t arg_slot;    // column slot, or -1
+  int32_t arg_prog;    // program index, or -1
+  int32_t arg_is_f64;  // type of the argument value
+  unsigned long long* acc;  // [capacity]
+};
+
+struct AggParams {
+  int64_t n_rows;
+  int32_t pred_kind;   // 0 none, 1 simple, 2 VM
+  int32_t sp_slot, sp_cmp, sp_is_f64;
+  uint64_t sp_const;
+  int32_t key_kind;
+  int32_t key_slot;
+  int32_t n_acc;
+  int32_t pad;
+  ColView cols[MAX_COLS];
+  AccParam accs[AGG_MAX_ACC];
+  VmProgram pred;
+  VmProgram progs[AGG_MAX_PROGS];
+  Key16* keys;               // [capacity]
+  unsigned long long mask;   // capacity - 1
+  unsigned int* group_count; // number of occupied slots
+  unsigned int max_groups;   // load-factor limit; beyond it the kernel raises `overflow`
+  int32_t* overflow;
+  int32_t* error;
+};
+
+}  // namespace ark

@@ -1,7 +1,6 @@
 // stubs.cu — temporary: entry points / executors not implemented yet.
 #include "engine.h"
 namespace ark {
-Batch run_aggregate(const Plan&, Batch&, cudaStream_t) { fail(ARK_ERR_UNSUPPORTED, "aggregate not implemented yet"); }
 Batch run_join(const Plan&, Batch&, Batch&, cudaStream_t) { fail(ARK_ERR_UNSUPPORTED, "join not implemented yet"); }
 }
 
@@ -22,7 +21,5 @@ int ark_buffer_read(ark_buf_t*, ArrowArray*, ArrowSchema*, uint64_t*, int64_t, i
 int ark_buffer_flush(ark_buf_t*) ARK_STUB("ark_buffer_flush")
 int ark_buffer_close(ark_buf_t*) ARK_STUB("ark_buffer_close")
 void ark_buffer_destroy(ark_buf_t*) {}
-int ark_sql_partial_aggregate_device(ark_proc_t*, ArrowDeviceArray*, ArrowSchema*, int, ArrowDeviceArray*, ArrowSchema*, int64_t*) ARK_STUB("ark_sql_partial_aggregate_device")
-int ark_sql_final_aggregate_device(ark_proc_t*, ArrowDeviceArray*, ArrowSchema*, ArrowDeviceArray*, ArrowSchema*) ARK_STUB("ark_sql_final_aggregate_device")
 int ark_hash_partition_device(ArrowDeviceArray*, ArrowSchema*, const char*, int, ArrowDeviceArray*, ArrowSchema*, int64_t*) ARK_STUB("ark_hash_partition_device")
 }

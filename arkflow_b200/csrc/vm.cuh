@@ -55,7 +55,7 @@ __device__ inline int bytes_cmp(const uint8_t* a, int32_t la, const uint8_t* b, 
   return la < lb ? -1 : (la > lb ? 1 : 0);
 }
 
-__device__ __noinline__ VmVal vm_eval(const VmProgram& prog, const ColView* cols, int64_t row, int32_t* err) {
+static __device__ __noinline__ VmVal vm_eval(const VmProgram& prog, const ColView* cols, int64_t row, int32_t* err) {
   VmVal r[VM_MAX_REGS];
 #pragma unroll 1
   for (int pc = 0; pc < prog.n_instr; ++pc) {

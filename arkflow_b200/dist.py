@@ -1,0 +1,152 @@
+"""Multi-GPU execution of the sql processor: one process per GPU, torch.distributed for the plumbing.
+
+SURVEY.md §8(e):
+  * filter / project / json decode shard by rows — no collective (each rank processes its batches);
+  * GROUP BY: each rank partial-aggregates its rows (hash_agg kernel), the partial states are
+    hash-partitioned by key owner, ONE all-to-all(v) moves them (NCCL over NVLink; gloo on CPU for
+    the host-logic tests), the owner merges (same kernel in merge mode).  This mirrors DataFusion's
+    AggregateExec(Partial) → RepartitionExec(Hash) → AggregateExec(FinalPartitioned), which the
+    reference reaches in-process (crates/arkflow-plugin/src/processor/sql.rs:126-129);
+  * JOIN: both sides are hash-partitioned on the join key and exchanged the same way, then joined
+    locally (buffer/join.rs:111-118 runs the join on one node).
+
+The exchange code only touches torch tensors, so it is device-agnostic; the compute steps go through
+an `engine` object — `NativeEngine` (C ABI → CUDA kernels) in production.  Tests substitute a CPU
+engine to exercise this host logic under gloo with world_size 2.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from .arrow_ffi import DeviceBatch, DeviceColumn
+
+
+class NativeEngine:
+    """Compute steps on the local GPU through the C ABI."""
+
+    def __init__(self, query: str, table_name: str = "flow"):
+        from .processor import SqlProcessor
+
+        self.proc = SqlProcessor({"query": query, "table_name": table_name})
+
+    def partial_aggregate(self, batch: DeviceBatch, n_parts: int):
+        from .processor import _check
+
+        lib = L.lib()
+        dev, sch = batch.export()
+        out_dev, out_sch = L.ArrowDeviceArray(), L.ArrowSchema()
+        rows = (C.c_int64 * n_parts)()
+        try:
+            status = lib.ark_sql_partial_aggregate_device(self.proc._h, C.byref(dev), C.byref(sch), n_parts, C.byref(out_dev), C.byref(out_sch), rows)
+        finally:
+            from .arrow_ffi import release_array, release_schema
+
+            release_schema(sch)
+            release_array(dev.array)
+        _check(status)
+        return DeviceBatch.adopt(out_dev, out_sch), list(rows)
+
+    def final_aggregate(self, partial: DeviceBatch) -> DeviceBatch:
+        from .processor import _check
+
+        lib = L.lib()
+        dev, sch = partial.export()
+        out_dev, out_sch = L.ArrowDeviceArray(), L.ArrowSchema()
+        try:
+            status = lib.ark_sql_final_aggregate_device(self.proc._h, C.byref(dev), C.byref(sch), C.byref(out_dev), C.byref(out_sch))
+        finally:
+            from .arrow_ffi import release_array, release_schema
+
+            release_schema(sch)
+            release_array(dev.array)
+        _check(status)
+        return DeviceBatch.adopt(out_dev, out_sch)
+
+    def process(self, batch: DeviceBatch) -> Optional[DeviceBatch]:
+        return self.proc.process_device(batch)
+
+
+# ---------------------------------------------------------------------------------------------
+# all-to-all(v) of a partition-ordered batch
+# ---------------------------------------------------------------------------------------------
+def _all_to_all_rows(t: torch.Tensor, send_counts: list[int], recv_counts: list[int], group) -> torch.Tensor:
+    out = torch.empty(sum(recv_counts), dtype=t.dtype, device=t.device)
+    dist.all_to_all_single(out, t.contiguous(), output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
+    return out
+
+
+def _unpack_bits(bits: torch.Tensor, n: int) -> torch.Tensor:
+    idx = torch.arange(n, device=bits.device)
+    return ((bits[idx >> 3].to(torch.int32) >> (idx & 7).to(torch.int32)) & 1).to(torch.uint8)
+
+
+def _pack_bits(bytes_: torch.Tensor) -> torch.Tensor:
+    n = bytes_.numel()
+    pad = (-n) % 8
+    b = torch.cat([bytes_, torch.zeros(pad, dtype=torch.uint8, device=bytes_.device)]).view(-1, 8).to(torch.int32)
+    w = (b << torch.arange(8, device=bytes_.device, dtype=torch.int32)).sum(dim=1)
+    return w.to(torch.uint8)
+
+
+def exchange_partitions(batch: DeviceBatch, part_rows: list[int], group=None) -> DeviceBatch:
+    """Rows [sum(part_rows[:p]), sum(part_rows[:p+1])) of `batch` go to rank p; returns the rows this
+    rank received (in source-rank order).  One all-to-all(v) per buffer + one for the counts."""
+    world = dist.get_world_size(group)
+    assert len(part_rows) == world
+    device = batch.columns[0].data.device if batch.columns else torch.device("cpu")
+    send = torch.tensor(part_rows, dtype=torch.int64, device=device)
+    recv = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_to_all_single(recv, send, group=group)
+    send_counts, recv_counts = [int(x) for x in part_rows], [int(x) for x in recv.tolist()]
+    n_out = sum(recv_counts)
+    row_starts = [0]
+    for c in send_counts:
+        row_starts.append(row_starts[-1] + c)
+    cols = []
+    for c in batch.columns:
+        validity = None
+        if c.validity is not None and c.validity.numel():
+            vb = _all_to_all_rows(_unpack_bits(c.validity, c.length), send_counts, recv_counts, group)
+            validity = _pack_bits(vb)
+        if c.dtype in ("int64", "float64"):
+            data = _all_to_all_rows(c.data[: c.length], send_counts, recv_counts, group)
+            cols.append(DeviceColumn(c.name, c.dtype, n_out, data, None, validity, -1 if validity is not None else 0, c.nullable))
+        elif c.dtype == "bool":
+            data = _pack_bits(_all_to_all_rows(_unpack_bits(c.data, c.length), send_counts, recv_counts, group))
+            cols.append(DeviceColumn(c.name, c.dtype, n_out, data, None, validity, -1 if validity is not None else 0, c.nullable))
+        else:
+            offs = c.offsets[: c.length + 1].to(torch.int64)
+            lens = (offs[1:] - offs[:-1]).to(torch.int32)
+            rlens = _all_to_all_rows(lens, send_counts, recv_counts, group)
+            bounds = offs[torch.tensor(row_starts, device=device)]
+            bsend = (bounds[1:] - bounds[:-1]).to(torch.int64)
+            brecv = torch.empty(world, dtype=torch.int64, device=device)
+            dist.all_to_all_single(brecv, bsend, group=group)
+            first = int(offs[0].item()) if c.length else 0
+            payload = c.data[first: first + int(bsend.sum().item())]
+            rbytes = _all_to_all_rows(payload, [int(x) for x in bsend.tolist()], [int(x) for x in brecv.tolist()], group)
+            roffs = torch.zeros(n_out + 1, dtype=torch.int32, device=device)
+            if n_out:
+                roffs[1:] = torch.cumsum(rlens.to(torch.int64), 0).to(torch.int32)
+            cols.append(DeviceColumn(c.name, c.dtype, n_out, rbytes, roffs, validity, -1 if validity is not None else 0, c.nullable))
+    return DeviceBatch(cols, n_out)
+
+
+def distributed_group_by(engine, local_batch: DeviceBatch, group=None) -> DeviceBatch:
+    """GROUP BY over the union of every rank's `local_batch`; returns this rank's share of the groups
+    (group owners are disjoint, so the concatenation over ranks is the full result)."""
+    world = dist.get_world_size(group)
+    partial, part_rows = engine.partial_aggregate(local_batch, world)
+    keyless = not partial.columns or partial.columns[0].name.startswith("__acc")
+    received = exchange_partitions(partial, part_rows, group)
+    result = engine.final_aggregate(received)
+    if keyless and dist.get_rank(group) != 0:
+        # a global aggregate has one group, owned by rank 0; other ranks merged nothing
+        result = DeviceBatch([DeviceColumn(c.name, c.dtype, 0, c.data[:0], None if c.offsets is None else c.offsets[:1], None, 0, c.nullable)
+                              for c in result.columns], 0)
+    return result

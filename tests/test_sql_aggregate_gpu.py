@@ -1,0 +1,194 @@
+"""Parity of the CUDA GROUP BY hash-aggregate (through the C ABI) against the oracle.
+
+GROUP BY output order is unspecified in DataFusion, so results are compared as multisets keyed by the
+group key.  Integer SUM / COUNT / MIN / MAX are bit-exact; Float64 SUM / AVG are checked against the
+correctly-rounded sum with the tolerance of SURVEY.md §8(d):
+    |got − exact| ≤ 2·(n_g − 1)·2⁻⁵³ · Σ|x_i|      (any summation order satisfies it).
+"""
+import math
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from arkflow_b200.arrow_ffi import DeviceBatch
+from arkflow_b200.processor import ArkError, MessageBatch, SqlProcessor
+from oracle.sql_oracle import sql_process
+from oracle.synth import synth_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def run(rb, query, device=False):
+    p = SqlProcessor({"query": query})
+    if device:
+        out = p.process_device(DeviceBatch.from_arrow(rb))
+        return None if out is None else out.to_arrow()
+    r = p.process(MessageBatch.new_arrow(rb))
+    return None if r.is_none() else r.batches[0].record_batch
+
+
+def rows_as_dict(rb, key_cols):
+    cols = {n: rb.column(i).to_pylist() for i, n in enumerate(rb.schema.names)}
+    out = {}
+    for i in range(rb.num_rows):
+        k = tuple(cols[c][i] for c in key_cols)
+        assert k not in out, f"duplicate group {k}"
+        out[k] = {n: cols[n][i] for n in cols}
+    return out
+
+
+def check_agg(rb, query, key_cols, float_cols=(), abs_sums=None, counts=None):
+    want = sql_process(rb, query)
+    for device in (False, True):
+        got = run(rb, query, device=device)
+        assert got.schema.names == want.schema.names, (got.schema, want.schema)
+        assert [f.type for f in got.schema] == [f.type for f in want.schema], (got.schema, want.schema)
+        assert got.num_rows == want.num_rows, (query, got.num_rows, want.num_rows)
+        if not key_cols:  # global aggregate or key not projected: compare sorted rows
+            g = sorted(map(tuple, zip(*[c.to_pylist() for c in got.columns])), key=repr)
+            w = sorted(map(tuple, zip(*[c.to_pylist() for c in want.columns])), key=repr)
+            if not float_cols:
+                assert g == w
+            else:
+                assert len(g) == len(w)
+            continue
+        gd, wd = rows_as_dict(got, key_cols), rows_as_dict(want, key_cols)
+        assert gd.keys() == wd.keys()
+        for k in wd:
+            for n in want.schema.names:
+                gv, wv = gd[k][n], wd[k][n]
+                if n in float_cols and wv is not None and gv is not None:
+                    ng = counts[k] if counts else 1
+                    bound = 2 * max(ng - 1, 1) * 2.0 ** -53 * (abs_sums[k] if abs_sums else abs(wv)) + 1e-300
+                    if n.startswith("avg"):
+                        bound = bound / max(ng, 1) + abs(wv) * 2.0 ** -52
+                    assert abs(gv - wv) <= bound, (k, n, gv, wv, bound)
+                else:
+                    assert gv == wv, (k, n, gv, wv)
+    return want
+
+
+def test_config3_group_by_sensor_int(gpu):
+    rb = synth_batch(200_000, key_space=1000)
+    out = check_agg(rb, "SELECT sensor, SUM(value), COUNT(*) FROM flow GROUP BY sensor", ["sensor"])
+    assert out.num_rows == 1000
+    assert out.schema.names == ["sensor", "sum(flow.value)", "count(*)"]
+
+
+def test_config1a_generate_example_query(gpu):
+    # examples/generate_example.yaml:26 — key not projected, literal column
+    rb = pa.record_batch({"timestamp": pa.array([1625000000000], pa.int64()), "value": pa.array([10], pa.int64()),
+                          "sensor": pa.array(["temp_1"])})
+    out = check_agg(rb, "SELECT sum(value),avg(value) ,111 as x FROM flow  group by sensor", [])
+    assert out.to_pydict() == {"sum(flow.value)": [10], "avg(flow.value)": [10.0], "x": [111]}
+
+
+def test_drop_output_example_query(gpu):
+    # examples/drop_output_example.yaml:18
+    rb = synth_batch(50_000, key_space=13)
+    check_agg(rb, "SELECT count(*) FROM flow WHERE value >= 10 group by sensor", [])
+    check_agg(rb, "SELECT sensor, count(*) FROM flow WHERE value >= 10 group by sensor", ["sensor"])
+
+
+def test_stream_data_fixture(gpu):
+    import json, os
+    p = os.path.join(os.path.dirname(__file__), "golden", "stream_data.json")
+    rows = [json.loads(l) for l in open(p)]
+    rb = pa.record_batch({"timestamp": pa.array([r["timestamp"] for r in rows], pa.int64()),
+                          "value": pa.array([r["value"] for r in rows], pa.int64()),
+                          "sensor": pa.array([r["sensor"] for r in rows])})
+    out = check_agg(rb, "SELECT sensor, SUM(value), COUNT(*), AVG(value), MIN(value), MAX(value) FROM flow GROUP BY sensor", ["sensor"],
+                    float_cols=["avg(flow.value)"])
+    d = rows_as_dict(out, ["sensor"])
+    assert d[("temp_1",)]["sum(flow.value)"] == 223 and d[("temp_1",)]["count(*)"] == 11
+    assert d[("temp_2",)]["sum(flow.value)"] == 288 and d[("temp_2",)]["count(*)"] == 10
+
+
+@pytest.mark.parametrize("k", [1, 2, 37, 5000, 100_000])
+def test_cardinalities(gpu, k):
+    rb = synth_batch(300_000, key_space=k, seed=7 + k)
+    check_agg(rb, "SELECT sensor, SUM(value), COUNT(*), MIN(value), MAX(value) FROM flow GROUP BY sensor", ["sensor"])
+
+
+def test_float_sum_avg_tolerance(gpu):
+    rb = synth_batch(400_000, value_kind=1, key_space=500)
+    keys = rb.column("sensor").to_pylist()
+    vals = np.asarray(rb.column("value"))
+    abs_sums, counts = {}, {}
+    for kx, v in zip(keys, vals):
+        abs_sums[(kx,)] = abs_sums.get((kx,), 0.0) + abs(v)
+        counts[(kx,)] = counts.get((kx,), 0) + 1
+    check_agg(rb, "SELECT sensor, SUM(value), AVG(value), COUNT(value), MIN(value), MAX(value) FROM flow GROUP BY sensor", ["sensor"],
+              float_cols=["sum(flow.value)", "avg(flow.value)"], abs_sums=abs_sums, counts=counts)
+
+
+def test_int64_key_and_wrapping_sum(gpu):
+    rng = np.random.default_rng(5)
+    n = 100_000
+    big = rng.integers(-2**62, 2**62, n)
+    rb = pa.record_batch({"id": pa.array(rng.integers(-50, 50, n), pa.int64()), "v": pa.array(big, pa.int64())})
+    check_agg(rb, "SELECT id, SUM(v), COUNT(*), MIN(v), MAX(v) FROM flow GROUP BY id", ["id"])
+
+
+def test_global_aggregates(gpu):
+    rb = synth_batch(100_000, key_space=100)
+    check_agg(rb, "SELECT COUNT(*), SUM(value), MIN(value), MAX(value) FROM flow", [])
+    check_agg(rb, "SELECT COUNT(*) FROM flow WHERE value >= 10", [])
+    out = check_agg(rb, "SELECT COUNT(*), SUM(value) FROM flow WHERE value > 1000", [])
+    assert out.to_pydict() == {"count(*)": [0], "sum(flow.value)": [None]}
+
+
+def test_count_star_pins_reference_value(gpu):
+    # crates/arkflow-core/src/lib.rs:1811-1858: COUNT(*) over 5 rows is Int64 5
+    rb = pa.record_batch({"id": pa.array([1, 2, 3, 4, 5], pa.int64())})
+    out = run(rb, "SELECT COUNT(*) as cnt FROM flow")
+    assert out.schema.field(0).type == pa.int64() and out.column(0).to_pylist() == [5]
+
+
+def test_nulls_in_keys_and_values(gpu):
+    rng = np.random.default_rng(11)
+    n = 50_000
+    keys = [None if rng.random() < 0.1 else "k%d" % int(rng.integers(0, 40)) for _ in range(n)]
+    v = rng.integers(0, 100, n)
+    rb = pa.record_batch({"sensor": pa.array(keys), "value": pa.array(v, pa.int64(), mask=rng.random(n) < 0.3),
+                          "g": pa.array([None if rng.random() < 0.2 else int(x) % 7 for x in v], pa.int64()),
+                          "b": pa.array([None if rng.random() < 0.2 else bool(x & 1) for x in v], pa.bool_())})
+    check_agg(rb, "SELECT sensor, SUM(value), COUNT(value), COUNT(*), AVG(value), MIN(value), MAX(value) FROM flow GROUP BY sensor", ["sensor"],
+              float_cols=["avg(flow.value)"])
+    check_agg(rb, "SELECT g, COUNT(*), SUM(value) FROM flow GROUP BY g", ["g"])
+    check_agg(rb, "SELECT b, COUNT(*), SUM(value) FROM flow GROUP BY b", ["b"])
+    check_agg(rb, "SELECT sensor, SUM(value) FROM flow WHERE value IS NULL GROUP BY sensor", ["sensor"])
+
+
+def test_long_and_ragged_string_keys(gpu):
+    rng = np.random.default_rng(2)
+    base = ["", "a", "ab", "exactly12chr", "thirteen chrs", "x" * 40, "x" * 40 + "y", "prefix_same_" + "a" * 30, "prefix_same_" + "b" * 30]
+    base += ["key-%d-%s" % (i, "z" * int(rng.integers(0, 60))) for i in range(300)]
+    n = 60_000
+    keys = [base[int(i)] for i in rng.integers(0, len(base), n)]
+    rb = pa.record_batch({"sensor": pa.array(keys), "value": pa.array(rng.integers(0, 1000, n), pa.int64())})
+    check_agg(rb, "SELECT sensor, SUM(value), COUNT(*) FROM flow GROUP BY sensor", ["sensor"])
+    rbb = pa.record_batch({"sensor": pa.array([k.encode() for k in keys], pa.binary()), "value": rb.column("value")})
+    check_agg(rbb, "SELECT sensor, SUM(value), COUNT(*) FROM flow GROUP BY sensor", ["sensor"])
+
+
+def test_computed_aggregate_arguments(gpu):
+    rb = synth_batch(100_000, key_space=50)
+    check_agg(rb, "SELECT sensor, SUM(value * 2 + 1), AVG(value + 0.5), COUNT(*) FROM flow WHERE value >= 3 GROUP BY sensor", ["sensor"],
+              float_cols=["avg(flow.value + Float64(0.5))"])
+
+
+def test_table_growth_from_small_hint(gpu):
+    # first a tiny-cardinality batch (hint shrinks), then a high-cardinality one (forces the retry path)
+    check_agg(synth_batch(10_000, key_space=2), "SELECT sensor, COUNT(*) FROM flow GROUP BY sensor", ["sensor"])
+    check_agg(synth_batch(400_000, key_space=300_000, seed=9), "SELECT sensor, COUNT(*), SUM(value) FROM flow GROUP BY sensor", ["sensor"])
+
+
+def test_aggregate_planning_errors(gpu):
+    rb = synth_batch(10)
+    with pytest.raises(ArkError) as e:
+        run(rb, "SELECT timestamp, COUNT(*) FROM flow GROUP BY sensor")
+    assert e.value.kind == "Process"
+    with pytest.raises(ArkError):
+        run(rb, "SELECT SUM(sensor) FROM flow")
