@@ -644,7 +644,8 @@ static Batch project_groups(const Plan& plan, const AggExec& ex, const std::vect
       BufferPtr cnt = o.count_acc >= 0 ? dense_acc(o.count_acc) : BufferPtr();
       // a group exists only if it has ≥ 1 row, so COUNT(*) > 0: validity is needed only when the
       // argument itself can be NULL (dedicated ACC_COUNT accumulator)
-      const bool can_be_null = !is_count && o.count_acc >= 0 && o.can_be_null;
+      // … or when there is no key: the single group of a global aggregate may be empty (SUM → NULL)
+      const bool can_be_null = !is_count && o.count_acc >= 0 && (o.can_be_null || ex.key_kind == KEY_NONE);
       Column col = finalize_column(pi.name, o.type, o.final_op, dense_acc(o.value_acc), cnt, 0, can_be_null, G, stream);
       col.field.nullable = !is_count;
       out.cols.push_back(col);
