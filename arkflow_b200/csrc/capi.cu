@@ -155,6 +155,60 @@ int ark_sql_final_aggregate_device(ark_proc_t* p, ArrowDeviceArray* in, ArrowSch
   });
 }
 
+int ark_json_to_arrow_create(const char* config_json, ark_proc_t** out) {
+  return guarded([&] {
+    if (!out) fail(ARK_ERR_PROCESS, "null output handle");
+    *out = nullptr;
+    auto p = make_json_to_arrow(config_json);
+    auto* h = new ark_proc();
+    h->impl = std::move(p);
+    *out = h;
+  });
+}
+
+static Processor* as_json(ark_proc_t* p) {
+  if (!p || !p->impl || strcmp(p->impl->type(), "json_to_arrow") != 0) fail(ARK_ERR_PROCESS, "handle is not a json_to_arrow processor");
+  return p->impl.get();
+}
+
+static std::vector<bool> json_mask(const Processor& jp, const std::vector<Field>& fields) {
+  std::vector<bool> m(fields.size(), false);
+  for (size_t i = 0; i < fields.size(); ++i) if (fields[i].name == json_to_arrow_value_field(jp)) m[i] = true;
+  return m;
+}
+
+int ark_json_to_arrow_process(ark_proc_t* p, ArrowArray* in, ArrowSchema* in_schema, ArrowArray* out, ArrowSchema* out_schema) {
+  BufferPtr in_owner = adopt_array(in);
+  return guarded([&] {
+    Processor* jp = as_json(p);
+    const ArrowArray* arr = (const ArrowArray*)in_owner.get();
+    if (!arr) fail(ARK_ERR_PROCESS, "input array already released");
+    std::vector<Field> fields = schema_fields(in_schema);
+    std::vector<bool> mask = json_mask(*jp, fields);
+    StreamLease lease;
+    Batch b = import_host(arr, in_schema, &mask, lease.s);
+    Batch r = json_to_arrow_device(*jp, b, lease.s);
+    export_host(r, lease.s, out, out_schema);
+  });
+}
+
+int ark_json_to_arrow_process_device(ark_proc_t* p, ArrowDeviceArray* in, ArrowSchema* in_schema, ArrowDeviceArray* out,
+                                     ArrowSchema* out_schema) {
+  BufferPtr in_owner = adopt_array(&in->array);
+  return guarded([&] {
+    Processor* jp = as_json(p);
+    if (!in_owner) fail(ARK_ERR_PROCESS, "input array already released");
+    ArrowDeviceArray view = *in;
+    view.array = *(const ArrowArray*)in_owner.get();
+    std::vector<Field> fields = schema_fields(in_schema);
+    std::vector<bool> mask = json_mask(*jp, fields);
+    StreamLease lease;
+    Batch b = import_device(&view, in_schema, &mask, in_owner);
+    Batch r = json_to_arrow_device(*jp, b, lease.s);
+    export_device(r, out, out_schema);
+  });
+}
+
 int ark_proc_close(ark_proc_t*) { return ARK_OK; }  // Processor::close is a no-op in the reference (sql.rs:222-224)
 
 void ark_proc_destroy(ark_proc_t* p) { delete p; }

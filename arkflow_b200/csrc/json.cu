@@ -1,0 +1,649 @@
+// json.cu — `json_to_arrow`: NDJSON payloads (a Binary column) → typed Arrow columns, on the device.
+//
+// Stands in for JsonToArrowProcessor::process (crates/arkflow-plugin/src/processor/json.rs:48-61) and
+// component::json::try_to_arrow (crates/arkflow-plugin/src/component/json.rs:22-58), i.e. arrow-json
+// 55.2's infer_json_schema(.., Some(1)) + tape decoder (third-party, not under /root/reference):
+//   * the schema comes from the FIRST record only, fields in first-seen order, all nullable:
+//     integer that fits i64 → Int64, other number → Float64, bool → Boolean, string → Utf8, null → Null;
+//   * decoding is non-strict: unknown keys are skipped, missing keys → NULL;
+//   * Int64 column: a number with fraction/exponent (or beyond i64) is parsed as f64 and truncated;
+//     a quoted number is accepted for numeric columns; anything else is a decode error;
+//   * Utf8 column: only JSON strings (escapes decoded); Boolean column: only true/false.
+// The reference makes two full copies of the payload bytes around the decoder (json.rs:56,
+// component/json.rs:54); here the payload bytes are read in place, once per pass.
+//
+// One thread parses one payload (a payload may hold several whitespace-separated records).
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+
+#include "engine.h"
+#include "json_mini.h"
+
+namespace ark {
+
+namespace {
+
+constexpr int JS_MAX_FIELDS = 16;
+constexpr int JS_MAX_NAME = 48;
+
+enum JsonErr : int32_t { JE_NONE = 0, JE_SYNTAX = 1, JE_NOT_OBJECT = 2, JE_TYPE = 3, JE_NUMBER = 4 };
+
+struct JsonField {
+  int32_t dtype;     // DType as int
+  int32_t name_len;
+  char name[JS_MAX_NAME];
+  void* values;            // Int64/Float64: 8 B per row; Boolean: byte per row
+  uint8_t* valid_bytes;    // byte per row
+  int32_t* str_len;        // Utf8: decoded length per row (pass A), later the offsets array
+  long long* str_src;      // Utf8: absolute source position of the raw string body (after the quote)
+  int32_t* str_raw_len;    // Utf8: raw (escaped) byte length; negative ⇒ contains escapes
+};
+
+struct JsonParams {
+  const uint8_t* data;      // payload bytes base
+  const int32_t* offsets;   // payload i = data[offsets[i] .. offsets[i+1])
+  const uint8_t* validity;  // payload validity (NULL payloads are skipped: to_binary flattens them away)
+  int32_t validity_bit0;
+  int64_t n_payloads;
+  int32_t n_fields;
+  JsonField fields[JS_MAX_FIELDS];
+  const long long* row_start;  // pass A: first output row of payload i
+  int32_t* counts;             // count pass: records in payload i
+  int32_t* error;              // [0] = JsonErr, [1] = payload index (first error wins)
+};
+
+struct Cursor {
+  const uint8_t* p;
+  const uint8_t* end;
+};
+
+__device__ __forceinline__ void skip_ws(Cursor& c) {
+  while (c.p < c.end && (*c.p == ' ' || *c.p == '\n' || *c.p == '\r' || *c.p == '\t')) ++c.p;
+}
+
+// cursor on the opening quote; leaves it after the closing quote. Returns false on a malformed string.
+__device__ bool skip_string(Cursor& c, const uint8_t** body, int* raw_len, bool* has_escape) {
+  ++c.p;
+  const uint8_t* start = c.p;
+  bool esc = false;
+  while (c.p < c.end) {
+    const uint8_t ch = *c.p;
+    if (ch == '"') { *body = start; *raw_len = (int)(c.p - start); *has_escape = esc; ++c.p; return true; }
+    if (ch == '\\') { esc = true; c.p += 2; continue; }
+    if (ch < 0x20) return false;
+    ++c.p;
+  }
+  return false;
+}
+
+__device__ bool skip_value(Cursor& c, int depth);
+
+__device__ bool skip_number(Cursor& c, const uint8_t** start, int* len) {
+  *start = c.p;
+  if (c.p < c.end && *c.p == '-') ++c.p;
+  const uint8_t* d0 = c.p;
+  while (c.p < c.end && *c.p >= '0' && *c.p <= '9') ++c.p;
+  if (c.p == d0) return false;
+  if (c.p < c.end && *c.p == '.') { ++c.p; const uint8_t* f0 = c.p; while (c.p < c.end && *c.p >= '0' && *c.p <= '9') ++c.p; if (c.p == f0) return false; }
+  if (c.p < c.end && (*c.p == 'e' || *c.p == 'E')) {
+    ++c.p;
+    if (c.p < c.end && (*c.p == '+' || *c.p == '-')) ++c.p;
+    const uint8_t* e0 = c.p;
+    while (c.p < c.end && *c.p >= '0' && *c.p <= '9') ++c.p;
+    if (c.p == e0) return false;
+  }
+  *len = (int)(c.p - *start);
+  return true;
+}
+
+__device__ bool match_lit(Cursor& c, const char* lit, int n) {
+  if (c.end - c.p < n) return false;
+  for (int i = 0; i < n; ++i) if (c.p[i] != (uint8_t)lit[i]) return false;
+  c.p += n;
+  return true;
+}
+
+// iterative skip of any JSON value (nested containers tracked with a depth counter)
+__device__ bool skip_value(Cursor& c, int) {
+  skip_ws(c);
+  if (c.p >= c.end) return false;
+  int depth = 0;
+  do {
+    skip_ws(c);
+    if (c.p >= c.end) return false;
+    const uint8_t ch = *c.p;
+    if (ch == '{' || ch == '[') { ++depth; ++c.p; }
+    else if (ch == '}' || ch == ']') { --depth; ++c.p; }
+    else if (ch == '"') { const uint8_t* b; int l; bool e; if (!skip_string(c, &b, &l, &e)) return false; }
+    else if (ch == ',' || ch == ':') { ++c.p; }
+    else if (ch == 't') { if (!match_lit(c, "true", 4)) return false; }
+    else if (ch == 'f') { if (!match_lit(c, "false", 5)) return false; }
+    else if (ch == 'n') { if (!match_lit(c, "null", 4)) return false; }
+    else { const uint8_t* s; int l; if (!skip_number(c, &s, &l)) return false; }
+  } while (depth > 0);
+  return depth == 0;
+}
+
+__constant__ double kPow10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                                  1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+
+// decimal text → f64.  Exact (correctly rounded) on Clinger's fast path: ≤ 19 significant digits
+// with mantissa < 2^53 and |exp10| ≤ 22; otherwise scaled in double (≤ 1 ulp off).
+__device__ bool parse_f64(const uint8_t* s, int len, double* out) {
+  int i = 0;
+  bool neg = false;
+  if (i < len && s[i] == '-') { neg = true; ++i; }
+  else if (i < len && s[i] == '+') ++i;
+  unsigned long long mant = 0;
+  int digits = 0, exp10 = 0;
+  bool any = false;
+  for (; i < len && s[i] >= '0' && s[i] <= '9'; ++i) {
+    any = true;
+    if (digits < 19) { mant = mant * 10 + (s[i] - '0'); if (mant) ++digits; }
+    else ++exp10;
+  }
+  if (i < len && s[i] == '.') {
+    ++i;
+    for (; i < len && s[i] >= '0' && s[i] <= '9'; ++i) {
+      any = true;
+      if (digits < 19) { mant = mant * 10 + (s[i] - '0'); if (mant) ++digits; --exp10; }
+    }
+  }
+  if (!any) return false;
+  if (i < len && (s[i] == 'e' || s[i] == 'E')) {
+    ++i;
+    bool eneg = false;
+    if (i < len && (s[i] == '+' || s[i] == '-')) { eneg = s[i] == '-'; ++i; }
+    int e = 0; bool eany = false;
+    for (; i < len && s[i] >= '0' && s[i] <= '9'; ++i) { eany = true; if (e < 100000) e = e * 10 + (s[i] - '0'); }
+    if (!eany) return false;
+    exp10 += eneg ? -e : e;
+  }
+  if (i != len) return false;
+  double v;
+  if (mant == 0) v = 0.0;
+  else if (mant < (1ull << 53) && exp10 >= -22 && exp10 <= 22) {
+    v = (double)mant;
+    v = exp10 < 0 ? v / kPow10[-exp10] : v * kPow10[exp10];
+  } else {
+    v = (double)mant;
+    int e = exp10;
+    while (e > 0) { const int k = e > 22 ? 22 : e; v *= kPow10[k]; e -= k; }
+    while (e < 0) { const int k = -e > 22 ? 22 : -e; v /= kPow10[k]; e += k; }
+  }
+  *out = neg ? -v : v;
+  return true;
+}
+
+// JSON number text → i64 as arrow-json's ParseJsonNumber does: integer parse, else f64 then NumCast.
+__device__ bool parse_i64(const uint8_t* s, int len, long long* out) {
+  int i = 0;
+  bool neg = false;
+  if (i < len && s[i] == '-') { neg = true; ++i; }
+  else if (i < len && s[i] == '+') ++i;
+  unsigned long long v = 0;
+  bool ok = i < len, overflow = false;
+  for (; i < len; ++i) {
+    if (s[i] < '0' || s[i] > '9') { ok = false; break; }
+    const unsigned d = s[i] - '0';
+    if (v > (0xFFFFFFFFFFFFFFFFull - d) / 10) { overflow = true; break; }
+    v = v * 10 + d;
+  }
+  if (ok && !overflow) {
+    if (!neg && v <= 0x7FFFFFFFFFFFFFFFull) { *out = (long long)v; return true; }
+    if (neg && v <= 0x8000000000000000ull) { *out = (long long)(0 - v); return true; }
+  }
+  double d;
+  if (!parse_f64(s, len, &d)) return false;
+  if (!(d > -9223372036854777856.0 && d < 9223372036854775808.0)) return false;  // NumCast::from → None
+  *out = (long long)d;
+  return true;
+}
+
+// length of a JSON string body once escapes are decoded; -1 if malformed
+__device__ int decoded_len(const uint8_t* b, int raw) {
+  int n = 0;
+  for (int i = 0; i < raw;) {
+    if (b[i] != '\\') { ++n; ++i; continue; }
+    if (i + 1 >= raw) return -1;
+    const uint8_t e = b[i + 1];
+    if (e == 'u') {
+      if (i + 6 > raw) return -1;
+      unsigned cp = 0;
+      for (int k = 2; k < 6; ++k) {
+        const uint8_t h = b[i + k];
+        unsigned d = h >= '0' && h <= '9' ? h - '0' : h >= 'a' && h <= 'f' ? h - 'a' + 10 : h >= 'A' && h <= 'F' ? h - 'A' + 10 : 99;
+        if (d == 99) return -1;
+        cp = cp * 16 + d;
+      }
+      i += 6;
+      if (cp >= 0xD800 && cp < 0xDC00) {  // high surrogate: needs \uDC00..DFFF
+        if (i + 6 > raw || b[i] != '\\' || b[i + 1] != 'u') return -1;
+        i += 6;
+        n += 4;
+      } else n += cp < 0x80 ? 1 : cp < 0x800 ? 2 : 3;
+    } else {
+      if (e != '"' && e != '\\' && e != '/' && e != 'b' && e != 'f' && e != 'n' && e != 'r' && e != 't') return -1;
+      ++n; i += 2;
+    }
+  }
+  return n;
+}
+
+__device__ void decode_string(const uint8_t* b, int raw, uint8_t* out) {
+  for (int i = 0; i < raw;) {
+    if (b[i] != '\\') { *out++ = b[i++]; continue; }
+    const uint8_t e = b[i + 1];
+    if (e == 'u') {
+      auto hex4 = [&](int at) { unsigned cp = 0; for (int k = 0; k < 4; ++k) { const uint8_t h = b[at + k]; cp = cp * 16 + (h <= '9' ? h - '0' : (h | 0x20) - 'a' + 10); } return cp; };
+      unsigned cp = hex4(i + 2);
+      i += 6;
+      if (cp >= 0xD800 && cp < 0xDC00) { const unsigned lo = hex4(i + 2); i += 6; cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00); }
+      if (cp < 0x80) *out++ = (uint8_t)cp;
+      else if (cp < 0x800) { *out++ = 0xC0 | (cp >> 6); *out++ = 0x80 | (cp & 0x3F); }
+      else if (cp < 0x10000) { *out++ = 0xE0 | (cp >> 12); *out++ = 0x80 | ((cp >> 6) & 0x3F); *out++ = 0x80 | (cp & 0x3F); }
+      else { *out++ = 0xF0 | (cp >> 18); *out++ = 0x80 | ((cp >> 12) & 0x3F); *out++ = 0x80 | ((cp >> 6) & 0x3F); *out++ = 0x80 | (cp & 0x3F); }
+    } else {
+      uint8_t ch = e;
+      if (e == 'b') ch = '\b'; else if (e == 'f') ch = '\f'; else if (e == 'n') ch = '\n'; else if (e == 'r') ch = '\r'; else if (e == 't') ch = '\t';
+      *out++ = ch; i += 2;
+    }
+  }
+}
+
+__device__ void raise(const JsonParams& P, int code, int64_t payload) {
+  if (atomicCAS(P.error, 0, code) == 0) P.error[1] = (int32_t)payload;
+}
+
+// MODE 0: count records per payload.  MODE 1: parse into the columns.
+template <int MODE>
+__global__ void json_parse_kernel(const __grid_constant__ JsonParams P) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n_payloads) return;
+  if (P.validity && !((P.validity[(i + P.validity_bit0) >> 3] >> ((i + P.validity_bit0) & 7)) & 1)) {
+    if (MODE == 0) P.counts[i] = 0;
+    return;
+  }
+  Cursor c{P.data + P.offsets[i], P.data + P.offsets[i + 1]};
+  int records = 0;
+  long long row = MODE == 1 ? P.row_start[i] : 0;
+  while (true) {
+    skip_ws(c);
+    if (c.p >= c.end) break;
+    if (*c.p != '{') { raise(P, *c.p == '[' || *c.p == '"' || (*c.p >= '0' && *c.p <= '9') || *c.p == '-' || *c.p == 't' || *c.p == 'f' || *c.p == 'n' ? JE_NOT_OBJECT : JE_SYNTAX, i); return; }
+    if (MODE == 0) {
+      if (!skip_value(c, 0)) { raise(P, JE_SYNTAX, i); return; }
+      ++records;
+      continue;
+    }
+    // ---- MODE 1: one object → one row ----
+    ++c.p;
+    unsigned seen = 0;
+    skip_ws(c);
+    bool first = true;
+    while (true) {
+      skip_ws(c);
+      if (c.p >= c.end) { raise(P, JE_SYNTAX, i); return; }
+      if (*c.p == '}') { ++c.p; break; }
+      if (!first) { if (*c.p != ',') { raise(P, JE_SYNTAX, i); return; } ++c.p; skip_ws(c); }
+      first = false;
+      if (c.p >= c.end || *c.p != '"') { raise(P, JE_SYNTAX, i); return; }
+      const uint8_t* kb; int kl; bool kesc;
+      if (!skip_string(c, &kb, &kl, &kesc)) { raise(P, JE_SYNTAX, i); return; }
+      skip_ws(c);
+      if (c.p >= c.end || *c.p != ':') { raise(P, JE_SYNTAX, i); return; }
+      ++c.p;
+      skip_ws(c);
+      int f = -1;
+      if (!kesc) {
+        for (int k = 0; k < P.n_fields; ++k) {
+          if (P.fields[k].name_len != kl) continue;
+          bool eq = true;
+          for (int b = 0; b < kl; ++b) if ((uint8_t)P.fields[k].name[b] != kb[b]) { eq = false; break; }
+          if (eq) { f = k; break; }
+        }
+      }
+      if (f < 0) { if (!skip_value(c, 0)) { raise(P, JE_SYNTAX, i); return; } continue; }
+      const JsonField& F = P.fields[f];
+      if (c.p >= c.end) { raise(P, JE_SYNTAX, i); return; }
+      const uint8_t ch = *c.p;
+      if (ch == 'n') {  // null
+        if (!match_lit(c, "null", 4)) { raise(P, JE_SYNTAX, i); return; }
+        F.valid_bytes[row] = 0; seen |= 1u << f;
+        if (F.dtype == (int)DType::Utf8) { F.str_len[row] = 0; F.str_raw_len[row] = 0; }
+        continue;
+      }
+      switch ((DType)F.dtype) {
+        case DType::Int64: case DType::Float64: {
+          const uint8_t* ns; int nl;
+          if (ch == '"') { bool e; if (!skip_string(c, &ns, &nl, &e)) { raise(P, JE_SYNTAX, i); return; } }
+          else if (ch == '-' || (ch >= '0' && ch <= '9')) { if (!skip_number(c, &ns, &nl)) { raise(P, JE_SYNTAX, i); return; } }
+          else { raise(P, JE_TYPE, i); return; }
+          if ((DType)F.dtype == DType::Int64) {
+            long long v;
+            if (!parse_i64(ns, nl, &v)) { raise(P, JE_NUMBER, i); return; }
+            ((long long*)F.values)[row] = v;
+          } else {
+            double v;
+            if (!parse_f64(ns, nl, &v)) { raise(P, JE_NUMBER, i); return; }
+            ((double*)F.values)[row] = v;
+          }
+          break;
+        }
+        case DType::Bool: {
+          if (ch == 't') { if (!match_lit(c, "true", 4)) { raise(P, JE_SYNTAX, i); return; } ((uint8_t*)F.values)[row] = 1; }
+          else if (ch == 'f') { if (!match_lit(c, "false", 5)) { raise(P, JE_SYNTAX, i); return; } ((uint8_t*)F.values)[row] = 0; }
+          else { raise(P, JE_TYPE, i); return; }
+          break;
+        }
+        case DType::Utf8: {
+          if (ch != '"') { raise(P, JE_TYPE, i); return; }
+          const uint8_t* sb; int sl; bool esc;
+          if (!skip_string(c, &sb, &sl, &esc)) { raise(P, JE_SYNTAX, i); return; }
+          int dl = sl;
+          if (esc) { dl = decoded_len(sb, sl); if (dl < 0) { raise(P, JE_SYNTAX, i); return; } }
+          F.str_len[row] = dl; F.str_src[row] = (long long)(sb - P.data); F.str_raw_len[row] = esc ? -sl : sl;
+          break;
+        }
+        default:  // Null-typed column: any non-null value is a type error in arrow-json's NullArrayDecoder
+          raise(P, JE_TYPE, i); return;
+      }
+      F.valid_bytes[row] = 1; seen |= 1u << f;
+    }
+    for (int k = 0; k < P.n_fields; ++k) {
+      if (!((seen >> k) & 1)) {  // missing key → NULL
+        P.fields[k].valid_bytes[row] = 0;
+        if (P.fields[k].dtype == (int)DType::Utf8) { P.fields[k].str_len[row] = 0; P.fields[k].str_raw_len[row] = 0; }
+      }
+    }
+    ++row; ++records;
+  }
+  if (MODE == 0) P.counts[i] = records;
+}
+
+// string bytes of one Utf8 column: thread per row
+__global__ void json_strings_kernel(const uint8_t* data, const long long* src, const int32_t* raw_len, const int32_t* offsets,
+                                    int64_t n_rows, uint8_t* out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int raw = raw_len[r];
+  if (raw == 0) return;
+  uint8_t* d = out + offsets[r];
+  const uint8_t* s = data + src[r];
+  if (raw > 0) { for (int i = 0; i < raw; ++i) d[i] = s[i]; }
+  else decode_string(s, -raw, d);
+}
+
+__global__ void i32_to_i64_kernel(const int32_t* in, long long* out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+struct InferredField { std::string name; DType type; bool supported; std::string why; };
+
+// arrow-json infer_json_schema over the first record (host side; the record is a few dozen bytes)
+std::vector<InferredField> infer_schema(const std::string& first_record) {
+  JsonValue v;
+  try {
+    size_t used = 0;
+    // the first payload may hold several records: parse only the first value
+    std::string s = first_record;
+    // find the end of the first top-level value by bracket matching
+    int depth = 0; bool in_str = false; size_t end = std::string::npos;
+    for (size_t i = 0; i < s.size(); ++i) {
+      char ch = s[i];
+      if (in_str) { if (ch == '\\') ++i; else if (ch == '"') in_str = false; continue; }
+      if (ch == '"') in_str = true;
+      else if (ch == '{' || ch == '[') ++depth;
+      else if (ch == '}' || ch == ']') { if (--depth == 0) { end = i + 1; break; } }
+      else if (depth == 0 && !isspace((unsigned char)ch)) break;
+    }
+    (void)used;
+    if (end == std::string::npos) fail(ARK_ERR_PROCESS, "Schema inference error: Json error: Expected JSON record to be an object");
+    v = parse_json(s.substr(0, end));
+  } catch (const ArkError& e) {
+    if (e.code == ARK_ERR_SERIALIZATION) fail(ARK_ERR_PROCESS, std::string("Schema inference error: Json error: ") + e.what());
+    throw;
+  }
+  if (v.kind != JsonValue::Object)
+    fail(ARK_ERR_PROCESS, "Schema inference error: Json error: Expected JSON record to be an object, found " +
+                              std::string(v.kind == JsonValue::Array ? "Array" : "a scalar"));
+  std::vector<InferredField> out;
+  for (auto& kv : v.obj) {
+    bool dup = false;
+    for (auto& f : out) if (f.name == kv.first) dup = true;
+    if (dup) continue;
+    InferredField f;
+    f.name = kv.first; f.supported = true;
+    switch (kv.second.kind) {
+      case JsonValue::Null: f.type = DType::Null; break;
+      case JsonValue::Bool: f.type = DType::Bool; break;
+      case JsonValue::Number: f.type = kv.second.is_int ? DType::Int64 : DType::Float64; break;
+      case JsonValue::String: f.type = DType::Utf8; break;
+      case JsonValue::Array: f.type = DType::Null; f.supported = false; f.why = "List"; break;
+      case JsonValue::Object: f.type = DType::Null; f.supported = false; f.why = "Struct"; break;
+    }
+    out.push_back(f);
+  }
+  return out;
+}
+
+}  // namespace
+
+struct JsonToArrowProcessor : Processor {
+  const char* type() const override { return "json_to_arrow"; }
+  std::string value_field = "__value__";  // DEFAULT_BINARY_VALUE_FIELD, core/lib.rs:46
+  bool has_include = false;
+  std::vector<std::string> include;
+};
+
+std::unique_ptr<Processor> make_json_to_arrow(const char* config_json) {
+  // reference: json.rs:124-128 (missing configuration)
+  if (!config_json) fail(ARK_ERR_CONFIG, "JsonToArrow processor configuration is missing");
+  JsonValue cfg = parse_json(config_json);
+  if (cfg.kind == JsonValue::Null) fail(ARK_ERR_CONFIG, "JsonToArrow processor configuration is missing");
+  if (cfg.kind != JsonValue::Object) fail(ARK_ERR_SERIALIZATION, "invalid type: expected struct JsonProcessorConfig");
+  auto p = std::make_unique<JsonToArrowProcessor>();
+  if (const JsonValue* v = cfg.get("value_field")) {
+    if (v->kind == JsonValue::String) p->value_field = v->str;
+    else if (v->kind != JsonValue::Null) fail(ARK_ERR_SERIALIZATION, "invalid type for `value_field`: expected a string");
+  }
+  if (const JsonValue* v = cfg.get("fields_to_include")) {
+    if (v->kind == JsonValue::Array) {
+      p->has_include = true;
+      for (auto& e : v->arr) {
+        if (e.kind != JsonValue::String) fail(ARK_ERR_SERIALIZATION, "invalid type in `fields_to_include`: expected a string");
+        p->include.push_back(e.str);
+      }
+    } else if (v->kind != JsonValue::Null) fail(ARK_ERR_SERIALIZATION, "invalid type for `fields_to_include`: expected a sequence");
+  }
+  return p;
+}
+
+const std::string& json_to_arrow_value_field(const Processor& p) { return static_cast<const JsonToArrowProcessor&>(p).value_field; }
+
+// `in` holds the payload column (device-resident).  first_record: the bytes of the first payload.
+Batch json_to_arrow_device(const Processor& proc, Batch& in, cudaStream_t stream) {
+  const auto& jp = static_cast<const JsonToArrowProcessor&>(proc);
+  const int ci = in.find(jp.value_field);
+  if (ci < 0) fail(ARK_ERR_PROCESS, "not found column");                                  // core/lib.rs:357-359
+  Column& col = in.cols[ci];
+  if (col.field.format != "z" || !col.present) fail(ARK_ERR_PROCESS, "not support data type");  // core/lib.rs:363-367
+  std::vector<int> vl = {ci};
+  resolve_varlen_extents(in, vl, stream);
+  const int64_t n = col.length;
+  Batch out;
+  out.input_name = in.input_name;
+  if (n == 0 || col.data_bytes == 0) return out;  // empty input → RecordBatch::new_empty(inferred = empty schema)
+
+  // ---- schema from the first non-null, non-blank payload (host side) ----
+  BufferPtr hoff = pinned_alloc((size_t)(n + 1) * 4);
+  ARK_CUDA(cudaMemcpyAsync(hoff.get(), col.offsets, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, stream));
+  BufferPtr hval;
+  if (col.validity) {
+    const int64_t vb = (n + col.validity_bit0 + 7) / 8;
+    hval = pinned_alloc((size_t)vb);
+    ARK_CUDA(cudaMemcpyAsync(hval.get(), col.validity, (size_t)vb, cudaMemcpyDeviceToHost, stream));
+  }
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  const int32_t* ho = (const int32_t*)hoff.get();
+  std::string first;
+  for (int64_t i = 0; i < n && first.empty(); ++i) {
+    if (hval) { const int64_t b = i + col.validity_bit0; if (!((((const uint8_t*)hval.get())[b >> 3] >> (b & 7)) & 1)) continue; }
+    const int len = ho[i + 1] - ho[i];
+    if (len <= 0) continue;
+    std::string s((size_t)len, '\0');
+    ARK_CUDA(cudaMemcpyAsync(&s[0], col.data + ho[i], (size_t)len, cudaMemcpyDeviceToHost, stream));
+    ARK_CUDA(cudaStreamSynchronize(stream));
+    bool blank = true;
+    for (char ch : s) if (!isspace((unsigned char)ch)) blank = false;
+    if (!blank) first = s;
+  }
+  if (first.empty()) return out;
+  std::vector<InferredField> inferred = infer_schema(first);
+  std::vector<InferredField> fields;
+  if (jp.has_include) {
+    for (auto& f : inferred) if (std::find(jp.include.begin(), jp.include.end(), f.name) != jp.include.end()) fields.push_back(f);
+  } else fields = inferred;
+  for (auto& f : fields)
+    if (!f.supported) fail(ARK_ERR_UNSUPPORTED, "json_to_arrow: field '" + f.name + "' is a nested value (" + f.why + " column)");
+  if ((int)fields.size() > JS_MAX_FIELDS) fail(ARK_ERR_UNSUPPORTED, "json_to_arrow: more than 16 fields");
+  for (auto& f : fields) if ((int)f.name.size() > JS_MAX_NAME) fail(ARK_ERR_UNSUPPORTED, "json_to_arrow: field name longer than 48 bytes");
+
+  // ---- pass 0: records per payload ----
+  JsonParams P;
+  memset(&P, 0, sizeof P);
+  P.data = col.data; P.offsets = col.offsets; P.validity = col.validity; P.validity_bit0 = col.validity_bit0;
+  P.n_payloads = n; P.n_fields = (int)fields.size();
+  BufferPtr counts = device_alloc((size_t)(n + 1) * 4), counts64 = device_alloc((size_t)(n + 1) * 8), row_start = device_alloc((size_t)(n + 1) * 8);
+  BufferPtr err = device_alloc(16);
+  ARK_CUDA(cudaMemsetAsync(err.get(), 0, 16, stream));
+  ARK_CUDA(cudaMemsetAsync(counts.get(), 0, (size_t)(n + 1) * 4, stream));
+  P.counts = (int32_t*)counts.get(); P.error = (int32_t*)err.get();
+  const unsigned grid = (unsigned)ceil_div(n, 128);
+  {
+    KernelTimer t("json_count_kernel", stream);
+    json_parse_kernel<0><<<grid, 128, 0, stream>>>(P);
+  }
+  {
+    KernelTimer t("i32_to_i64_kernel", stream);
+    i32_to_i64_kernel<<<(unsigned)ceil_div(n + 1, 256), 256, 0, stream>>>((const int32_t*)counts.get(), (long long*)counts64.get(), n + 1);
+  }
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (long long*)counts64.get(), (long long*)row_start.get(), (int)(n + 1), stream);
+  BufferPtr tmp = device_alloc(tmp_bytes + 16);
+  note_launch("cub::DeviceScan::ExclusiveSum");
+  cub::DeviceScan::ExclusiveSum(tmp.get(), tmp_bytes, (long long*)counts64.get(), (long long*)row_start.get(), (int)(n + 1), stream);
+  BufferPtr h = pinned_alloc(64);
+  ARK_CUDA(cudaMemcpyAsync(h.get(), (long long*)row_start.get() + n, 8, cudaMemcpyDeviceToHost, stream));
+  ARK_CUDA(cudaMemcpyAsync((char*)h.get() + 16, err.get(), 8, cudaMemcpyDeviceToHost, stream));
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  auto check_err = [&]() {
+    const int32_t* e = (const int32_t*)((char*)h.get() + 16);
+    if (e[0] == JE_NONE) return;
+    const std::string where = " (payload " + std::to_string(e[1]) + ")";
+    switch (e[0]) {
+      case JE_NOT_OBJECT: fail(ARK_ERR_PROCESS, "Arrow JSON Reader Error: Json error: expected { got a non-object value" + where);
+      case JE_TYPE: fail(ARK_ERR_PROCESS, "Arrow JSON Reader Error: Json error: whilst decoding field: value does not match the inferred column type" + where);
+      case JE_NUMBER: fail(ARK_ERR_PROCESS, "Arrow JSON Reader Error: Json error: failed to parse number" + where);
+      default: fail(ARK_ERR_PROCESS, "Arrow JSON Reader Error: Json error: Encountered unexpected token / truncated record" + where);
+    }
+  };
+  check_err();
+  const int64_t rows = *(const long long*)h.get();
+  out.num_rows = rows;
+
+  // ---- pass 1: parse ----
+  struct FieldBufs { BufferPtr values, valid_bytes, str_len, str_src, str_raw; };
+  std::vector<FieldBufs> fb(fields.size());
+  for (size_t k = 0; k < fields.size(); ++k) {
+    JsonField& F = P.fields[k];
+    F.dtype = (int)fields[k].type; F.name_len = (int)fields[k].name.size();
+    memcpy(F.name, fields[k].name.data(), fields[k].name.size());
+    fb[k].valid_bytes = device_alloc((size_t)std::max<int64_t>(rows, 1));
+    F.valid_bytes = (uint8_t*)fb[k].valid_bytes.get();
+    if (fields[k].type == DType::Int64 || fields[k].type == DType::Float64) { fb[k].values = device_alloc((size_t)std::max<int64_t>(rows, 1) * 8); F.values = fb[k].values.get(); }
+    else if (fields[k].type == DType::Bool) { fb[k].values = device_alloc((size_t)std::max<int64_t>(rows, 1)); F.values = fb[k].values.get(); }
+    else if (fields[k].type == DType::Utf8) {
+      fb[k].str_len = device_alloc((size_t)(rows + 1) * 4); fb[k].str_src = device_alloc((size_t)std::max<int64_t>(rows, 1) * 8);
+      fb[k].str_raw = device_alloc((size_t)std::max<int64_t>(rows, 1) * 4);
+      ARK_CUDA(cudaMemsetAsync(fb[k].str_len.get(), 0, (size_t)(rows + 1) * 4, stream));
+      F.str_len = (int32_t*)fb[k].str_len.get(); F.str_src = (long long*)fb[k].str_src.get(); F.str_raw_len = (int32_t*)fb[k].str_raw.get();
+    }
+  }
+  P.row_start = (const long long*)row_start.get();
+  {
+    KernelTimer t("json_parse_kernel", stream);
+    json_parse_kernel<1><<<grid, 128, 0, stream>>>(P);
+  }
+  ARK_CUDA(cudaGetLastError());
+  // ---- strings: offsets = exclusive scan of the decoded lengths, then gather/decode the bytes ----
+  std::vector<BufferPtr> str_offsets(fields.size());
+  for (size_t k = 0; k < fields.size(); ++k) {
+    if (fields[k].type != DType::Utf8) continue;
+    str_offsets[k] = device_alloc((size_t)(rows + 1) * 4);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, (int32_t*)fb[k].str_len.get(), (int32_t*)str_offsets[k].get(), (int)(rows + 1), stream);
+    BufferPtr t2 = device_alloc(tb + 16);
+    note_launch("cub::DeviceScan::ExclusiveSum");
+    cub::DeviceScan::ExclusiveSum(t2.get(), tb, (int32_t*)fb[k].str_len.get(), (int32_t*)str_offsets[k].get(), (int)(rows + 1), stream);
+    ARK_CUDA(cudaMemcpyAsync((char*)h.get() + 32 + 0, (int32_t*)str_offsets[k].get() + rows, 4, cudaMemcpyDeviceToHost, stream));
+    ARK_CUDA(cudaMemcpyAsync((char*)h.get() + 16, err.get(), 8, cudaMemcpyDeviceToHost, stream));
+    ARK_CUDA(cudaStreamSynchronize(stream));
+    check_err();
+    const int32_t total = *(const int32_t*)((char*)h.get() + 32);
+    BufferPtr bytes = device_alloc((size_t)total + 16);
+    if (rows) {
+      KernelTimer t("json_strings_kernel", stream);
+      json_strings_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(col.data, (const long long*)fb[k].str_src.get(),
+                                                                            (const int32_t*)fb[k].str_raw.get(),
+                                                                            (const int32_t*)str_offsets[k].get(), rows, (uint8_t*)bytes.get());
+    }
+    Column c;
+    c.field.name = fields[k].name; c.field.type = DType::Utf8; c.field.nullable = true; c.length = rows;
+    c.offsets = (const int32_t*)str_offsets[k].get(); c.data = (const uint8_t*)bytes.get(); c.data_bytes = total; c.first_offset = 0;
+    c.owners = {str_offsets[k], bytes};
+    out.cols.push_back(std::move(c));
+  }
+  ARK_CUDA(cudaMemcpyAsync((char*)h.get() + 16, err.get(), 8, cudaMemcpyDeviceToHost, stream));
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  check_err();
+  // ---- assemble in schema order (string columns were built above; reorder) ----
+  std::vector<Column> ordered;
+  size_t next_str = 0;
+  std::vector<Column> strs = std::move(out.cols);
+  out.cols.clear();
+  for (size_t k = 0; k < fields.size(); ++k) {
+    Column c;
+    if (fields[k].type == DType::Utf8) c = strs[next_str++];
+    else {
+      c.field.name = fields[k].name; c.field.type = fields[k].type; c.field.nullable = true; c.length = rows;
+      if (fields[k].type == DType::Null) c.field.format = "n";
+      if (fields[k].type == DType::Int64 || fields[k].type == DType::Float64) {
+        c.data = (const uint8_t*)fb[k].values.get(); c.data_bytes = rows * 8; c.owners = {fb[k].values};
+      } else if (fields[k].type == DType::Bool) {
+        BufferPtr bits = device_alloc((size_t)(rows + 7) / 8 + 1);
+        launch_pack_bits((const uint8_t*)fb[k].values.get(), rows, (uint8_t*)bits.get(), nullptr, stream);
+        c.data = (const uint8_t*)bits.get(); c.data_bytes = (rows + 7) / 8; c.owners = {bits, fb[k].values};
+      }
+    }
+    if (fields[k].type != DType::Null && rows > 0) {
+      BufferPtr vbits = device_alloc((size_t)(rows + 7) / 8 + 1);
+      BufferPtr zeros = device_alloc(8);
+      ARK_CUDA(cudaMemsetAsync(zeros.get(), 0, 8, stream));
+      launch_pack_bits((const uint8_t*)fb[k].valid_bytes.get(), rows, (uint8_t*)vbits.get(), (unsigned long long*)zeros.get(), stream);
+      ARK_CUDA(cudaMemcpyAsync((char*)h.get() + 40, zeros.get(), 8, cudaMemcpyDeviceToHost, stream));
+      ARK_CUDA(cudaStreamSynchronize(stream));
+      const long long nulls = *(const long long*)((char*)h.get() + 40);
+      if (nulls > 0) { c.validity = (const uint8_t*)vbits.get(); c.null_count = nulls; c.owners.push_back(vbits); c.owners.push_back(fb[k].valid_bytes); }
+    }
+    ordered.push_back(std::move(c));
+  }
+  out.cols = std::move(ordered);
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  return out;
+}
+
+}  // namespace ark

@@ -2,6 +2,7 @@
 // component's `serde_json::Value` config back to a string; core/processor/mod.rs:83-90).
 #pragma once
 #include <cctype>
+#include <cerrno>
 #include <cstdlib>
 #include <map>
 #include <memory>
@@ -88,7 +89,11 @@ class JsonParser {
       std::string t = s_.substr(p_, q - p_);
       v.kind = JsonValue::Number;
       v.num = strtod(t.c_str(), nullptr);
-      if (t.find_first_of(".eE") == std::string::npos) { v.is_int = true; v.i64 = strtoll(t.c_str(), nullptr, 10); }
+      if (t.find_first_of(".eE") == std::string::npos) {
+        errno = 0;
+        v.i64 = strtoll(t.c_str(), nullptr, 10);
+        v.is_int = errno != ERANGE;  // beyond i64 (e.g. u64::MAX) is a Float64 for arrow-json's inference
+      }
       p_ = q;
     } else err(std::string("unexpected character '") + c + "'");
     return v;

@@ -8,13 +8,8 @@ Batch run_join(const Plan&, Batch&, Batch&, cudaStream_t) { fail(ARK_ERR_UNSUPPO
 extern "C" {
 int ark_sql_process_tables(ark_proc_t*, int, const char* const*, ArrowArray*, ArrowSchema*, ArrowArray*, ArrowSchema*) ARK_STUB("ark_sql_process_tables")
 int ark_sql_process_tables_device(ark_proc_t*, int, const char* const*, ArrowDeviceArray*, ArrowSchema*, ArrowDeviceArray*, ArrowSchema*) ARK_STUB("ark_sql_process_tables_device")
-int ark_json_to_arrow_create(const char*, ark_proc_t**) ARK_STUB("ark_json_to_arrow_create")
-int ark_json_to_arrow_process(ark_proc_t*, ArrowArray*, ArrowSchema*, ArrowArray*, ArrowSchema*) ARK_STUB("ark_json_to_arrow_process")
-int ark_json_to_arrow_process_device(ark_proc_t*, ArrowDeviceArray*, ArrowSchema*, ArrowDeviceArray*, ArrowSchema*) ARK_STUB("ark_json_to_arrow_process_device")
 int ark_arrow_to_json_create(const char*, ark_proc_t**) ARK_STUB("ark_arrow_to_json_create")
 int ark_arrow_to_json_process(ark_proc_t*, ArrowArray*, ArrowSchema*, ArrowArray*, ArrowSchema*) ARK_STUB("ark_arrow_to_json_process")
-int ark_concat_batches(int, ArrowArray*, ArrowSchema*, ArrowArray*, ArrowSchema*) ARK_STUB("ark_concat_batches")
-int ark_concat_batches_device(int, ArrowDeviceArray*, ArrowSchema*, ArrowDeviceArray*, ArrowSchema*) ARK_STUB("ark_concat_batches_device")
 int ark_buffer_create(const char*, const char*, const char*, ark_buf_t**) ARK_STUB("ark_buffer_create")
 int ark_buffer_write(ark_buf_t*, ArrowArray*, ArrowSchema*, const char*, uint64_t) ARK_STUB("ark_buffer_write")
 int ark_buffer_read(ark_buf_t*, ArrowArray*, ArrowSchema*, uint64_t*, int64_t, int64_t*) ARK_STUB("ark_buffer_read")

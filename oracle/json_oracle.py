@@ -1,0 +1,150 @@
+"""CPU oracle for `json_to_arrow` — TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+Restates JsonToArrowProcessor::process (crates/arkflow-plugin/src/processor/json.rs:48-61) and
+component::json::try_to_arrow (crates/arkflow-plugin/src/component/json.rs:22-58) on top of the
+published behaviour of arrow-json 55.2.0 (third-party; pinned in Cargo.lock, not vendored):
+  * to_binary(value_field) keeps the non-null payloads (core/lib.rs:355-371), joined with a newline;
+  * infer_json_schema(.., Some(1)): types from the FIRST record only, first-seen field order, every
+    field nullable; integer fitting i64 -> Int64, other numbers -> Float64, bool -> Boolean,
+    string -> Utf8, null -> Null (array/object -> List/Struct: outside this library's subset);
+  * decoding is non-strict: unknown keys ignored, missing keys -> NULL;
+  * numeric columns accept JSON numbers and quoted numbers; Int64 parses as integer, else as f64 and
+    truncates (error when out of range); Utf8 accepts only strings, Boolean only true/false;
+  * every top-level value must be an object.
+PARITY STATUS: unpinned by the reference beyond row counts / is_err (json.rs:170-266); the type
+inference table is from the arrow-json documentation.
+"""
+from __future__ import annotations
+
+import json
+import re
+from typing import Optional
+
+import pyarrow as pa
+
+from .sql_oracle import OracleError
+
+_NUM_RE = re.compile(rb"^[+-]?(\d+)(\.\d+)?([eE][+-]?\d+)?$|^[+-]?\.\d+([eE][+-]?\d+)?$")
+_INT_RE = re.compile(rb"^[+-]?\d+$")
+
+
+class _Num:
+    __slots__ = ("text",)
+
+    def __init__(self, text: str):
+        self.text = text
+
+
+def _bad_constant(s):
+    raise ValueError("invalid JSON constant " + s)
+
+
+def _decoder():
+    return json.JSONDecoder(parse_int=_Num, parse_float=_Num, parse_constant=_bad_constant,
+                            object_pairs_hook=lambda pairs: ("obj", pairs))
+
+
+def _iter_values(data: str):
+    dec = _decoder()
+    pos, n = 0, len(data)
+    while True:
+        while pos < n and data[pos] in " \t\r\n":
+            pos += 1
+        if pos >= n:
+            return
+        v, pos = dec.raw_decode(data, pos)
+        yield v
+
+
+def _infer_type(v) -> pa.DataType:
+    if v is None:
+        return pa.null()
+    if isinstance(v, bool):
+        return pa.bool_()
+    if isinstance(v, _Num):
+        if _INT_RE.match(v.text.encode()) and -(2 ** 63) <= int(v.text) <= 2 ** 63 - 1:
+            return pa.int64()
+        return pa.float64()
+    if isinstance(v, str):
+        return pa.utf8()
+    raise OracleError("Unsupported", "nested JSON value (List/Struct column)")
+
+
+def _to_i64(text: bytes) -> int:
+    if _INT_RE.match(text):
+        v = int(text)
+        if -(2 ** 63) <= v <= 2 ** 63 - 1:
+            return v
+    if not _NUM_RE.match(text):
+        raise OracleError("Process", "Arrow JSON Reader Error: Json error: failed to parse number")
+    f = float(text)
+    if not (-9223372036854777856.0 < f < 9223372036854775808.0):
+        raise OracleError("Process", "Arrow JSON Reader Error: Json error: failed to parse number")
+    return int(f)
+
+
+def _to_f64(text: bytes) -> float:
+    if not _NUM_RE.match(text):
+        raise OracleError("Process", "Arrow JSON Reader Error: Json error: failed to parse number")
+    return float(text)
+
+
+def json_to_arrow(rb: pa.RecordBatch, value_field: str = "__value__", fields_to_include: Optional[set] = None) -> pa.RecordBatch:
+    if value_field not in rb.schema.names:
+        raise OracleError("Process", "not found column")
+    col = rb.column(value_field)
+    if col.type != pa.binary():
+        raise OracleError("Process", "not support data type")
+    payloads = [v.as_py() for v in col if v.is_valid]
+    try:
+        data = b"\n".join(payloads).decode("utf-8")
+    except UnicodeDecodeError:
+        raise OracleError("Process", "Schema inference error: Json error: invalid UTF-8")
+    try:
+        values = list(_iter_values(data))
+    except (ValueError, json.JSONDecodeError) as e:
+        raise OracleError("Process", f"Arrow JSON Reader Error: Json error: {e}")
+    if not values:
+        return pa.RecordBatch.from_arrays([], schema=pa.schema([]))
+    first = values[0]
+    if not (isinstance(first, tuple) and first[0] == "obj"):
+        raise OracleError("Process", "Schema inference error: Json error: Expected JSON record to be an object")
+    fields, seen = [], set()
+    for k, v in first[1]:
+        if k in seen:
+            continue
+        seen.add(k)
+        if fields_to_include is not None and k not in fields_to_include:
+            continue
+        fields.append((k, _infer_type(v)))
+    cols = {k: [] for k, _ in fields}
+    for v in values:
+        if not (isinstance(v, tuple) and v[0] == "obj"):
+            raise OracleError("Process", "Arrow JSON Reader Error: Json error: expected { got a non-object value")
+        rec = {}
+        for k, x in v[1]:
+            rec[k] = x  # duplicate keys: the last one wins
+        for k, t in fields:
+            x = rec.get(k)
+            if x is None:
+                cols[k].append(None)
+            elif t == pa.int64() or t == pa.float64():
+                if isinstance(x, _Num):
+                    text = x.text.encode()
+                elif isinstance(x, str):
+                    text = x.encode()
+                else:
+                    raise OracleError("Process", "Arrow JSON Reader Error: Json error: expected a number")
+                cols[k].append(_to_i64(text) if t == pa.int64() else _to_f64(text))
+            elif t == pa.bool_():
+                if not isinstance(x, bool):
+                    raise OracleError("Process", "Arrow JSON Reader Error: Json error: expected a boolean")
+                cols[k].append(x)
+            elif t == pa.utf8():
+                if not isinstance(x, str):
+                    raise OracleError("Process", "Arrow JSON Reader Error: Json error: expected a string")
+                cols[k].append(x)
+            else:  # Null column: only nulls
+                raise OracleError("Process", "Arrow JSON Reader Error: Json error: expected null")
+    arrays = [pa.array(cols[k], type=t) for k, t in fields]
+    return pa.RecordBatch.from_arrays(arrays, schema=pa.schema([pa.field(k, t, True) for k, t in fields]))
