@@ -44,7 +44,7 @@ def release_array(arr: L.ArrowArray):
 # device
 # ---------------------------------------------------------------------------------------------
 
-_FMT = {"int64": b"l", "float64": b"g", "utf8": b"u", "binary": b"z", "bool": b"b"}
+_FMT = {"int64": b"l", "float64": b"g", "utf8": b"u", "binary": b"z", "bool": b"b", "null": b"n"}
 _FMT_INV = {v: k for k, v in _FMT.items()}
 
 
@@ -125,12 +125,15 @@ class DeviceBatch:
         child_schs = (L.ArrowSchema * n)()
         child_sptrs = (C.POINTER(L.ArrowSchema) * n)()
         for i, c in enumerate(self.columns):
-            bufs = [c.validity.data_ptr() if c.validity is not None else None,
+            if c.dtype == "null":
+                bufs = []
+            else:
+              bufs = [c.validity.data_ptr() if c.validity is not None else None,
                     (c.offsets if c.dtype in ("utf8", "binary") else c.data).data_ptr()
                     if (c.offsets if c.dtype in ("utf8", "binary") else c.data) is not None else None]
             if c.dtype in ("utf8", "binary"):
                 bufs.append(c.data.data_ptr() if c.data is not None and c.data.numel() else None)
-            barr = (C.c_void_p * len(bufs))(*bufs)
+            barr = (C.c_void_p * max(len(bufs), 1))(*bufs)
             a = child_arrs[i]
             a.length, a.null_count, a.offset = c.length, (c.null_count if c.validity is not None else 0), 0
             a.n_buffers, a.n_children = len(bufs), 0
@@ -182,6 +185,9 @@ class DeviceBatch:
                     return torch.empty(0, dtype=tdtype, device="cuda")
                 return torch.as_tensor(_CudaPtr(ptr, nbytes, typestr, itemsize, owner), device="cuda")
 
+            if dtype == "null":
+                cols.append(DeviceColumn(s.name.decode(), dtype, n, None, None, None, null_count=n, nullable=True))
+                continue
             validity = view(0, (n + 7) // 8, "|u1", 1, torch.uint8) if (a.n_buffers > 0 and a.buffers[0]) else None
             offsets = None
             if dtype in ("int64", "float64"):
@@ -203,6 +209,10 @@ class DeviceBatch:
             n = c.length
             vbuf = pa.py_buffer(c.validity.cpu().numpy().tobytes()) if c.validity is not None and c.validity.numel() else None
             nulls = c.null_count if vbuf is not None else 0
+            if c.dtype == "null":
+                arrays.append(pa.nulls(n))
+                fields.append(pa.field(c.name, pa.null(), nullable=True))
+                continue
             if c.dtype in ("int64", "float64"):
                 t = pa.int64() if c.dtype == "int64" else pa.float64()
                 arr = pa.Array.from_buffers(t, n, [vbuf, pa.py_buffer(c.data.cpu().numpy().tobytes())], null_count=nulls)

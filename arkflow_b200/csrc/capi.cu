@@ -155,6 +155,80 @@ int ark_sql_final_aggregate_device(ark_proc_t* p, ArrowDeviceArray* in, ArrowSch
   });
 }
 
+// Runs the processor's query over several named tables (JoinOperation, buffer/join.rs:92-118).
+static Batch run_tables(SqlProcessor* sp, std::vector<std::string>& names, std::vector<std::vector<Field>>& schemas,
+                        std::vector<Batch>& tables, cudaStream_t stream) {
+  auto plan = sp->join_plan_for(names, schemas);
+  if (plan->kind == Plan::Join) {
+    int li = -1, ri = -1;
+    for (size_t i = 0; i < names.size(); ++i) { if (names[i] == plan->left_table) li = (int)i; if (names[i] == plan->right_table) ri = (int)i; }
+    if (li < 0 || ri < 0) fail(ARK_ERR_PROCESS, "Failed to execute SQL query: table not found");
+    return run_join(*plan, tables[li], tables[ri], stream);
+  }
+  // a single-table query evaluated through the multi-table entry point
+  for (size_t i = 0; i < names.size(); ++i)
+    if (names[i] == sp->ast.from.name) return sp->execute(*plan, tables[i], stream);
+  fail(ARK_ERR_PROCESS, "Failed to execute SQL query: table '" + sp->ast.from.name + "' not found");
+}
+
+int ark_sql_process_tables(ark_proc_t* p, int n_tables, const char* const* names, ArrowArray* ins, ArrowSchema* in_schemas,
+                           ArrowArray* out, ArrowSchema* out_schema) {
+  std::vector<BufferPtr> owners;
+  for (int i = 0; i < n_tables; ++i) owners.push_back(adopt_array(&ins[i]));
+  return guarded([&] {
+    SqlProcessor* sp = as_sql(p);
+    StreamLease lease;
+    std::vector<std::string> nm;
+    std::vector<std::vector<Field>> schemas;
+    std::vector<Batch> tables;
+    for (int i = 0; i < n_tables; ++i) {
+      nm.push_back(names[i]);
+      schemas.push_back(schema_fields(&in_schemas[i]));
+      tables.push_back(import_host((const ArrowArray*)owners[i].get(), &in_schemas[i], nullptr, lease.s));
+    }
+    Batch r = run_tables(sp, nm, schemas, tables, lease.s);
+    export_host(r, lease.s, out, out_schema);
+  });
+}
+
+int ark_sql_process_tables_device(ark_proc_t* p, int n_tables, const char* const* names, ArrowDeviceArray* ins,
+                                  ArrowSchema* in_schemas, ArrowDeviceArray* out, ArrowSchema* out_schema) {
+  std::vector<BufferPtr> owners;
+  for (int i = 0; i < n_tables; ++i) owners.push_back(adopt_array(&ins[i].array));
+  return guarded([&] {
+    SqlProcessor* sp = as_sql(p);
+    StreamLease lease;
+    std::vector<std::string> nm;
+    std::vector<std::vector<Field>> schemas;
+    std::vector<Batch> tables;
+    for (int i = 0; i < n_tables; ++i) {
+      nm.push_back(names[i]);
+      schemas.push_back(schema_fields(&in_schemas[i]));
+      ArrowDeviceArray view = ins[i];
+      view.array = *(const ArrowArray*)owners[i].get();
+      tables.push_back(import_device(&view, &in_schemas[i], nullptr, owners[i]));
+    }
+    Batch r = run_tables(sp, nm, schemas, tables, lease.s);
+    export_device(r, out, out_schema);
+  });
+}
+
+int ark_hash_partition_device(ArrowDeviceArray* in, ArrowSchema* in_schema, const char* key_column, int n_parts,
+                              ArrowDeviceArray* out, ArrowSchema* out_schema, int64_t* part_rows) {
+  BufferPtr in_owner = adopt_array(&in->array);
+  return guarded([&] {
+    if (!in_owner) fail(ARK_ERR_PROCESS, "input array already released");
+    ArrowDeviceArray view = *in;
+    view.array = *(const ArrowArray*)in_owner.get();
+    StreamLease lease;
+    Batch b = import_device(&view, in_schema, nullptr, in_owner);
+    std::vector<int64_t> rows;
+    Batch r = hash_partition(b, key_column ? key_column : "", n_parts, rows, lease.s);
+    for (int i = 0; i < n_parts; ++i) part_rows[i] = rows[i];
+    export_device(r, out, out_schema);
+  });
+}
+
 int ark_json_to_arrow_create(const char* config_json, ark_proc_t** out) {
   return guarded([&] {
     if (!out) fail(ARK_ERR_PROCESS, "null output handle");

@@ -135,12 +135,12 @@ Batch concat_device(std::vector<Batch>& ins, cudaStream_t stream) {
                                   dtype_name(ins[b].cols[c].field.type) + " at column index " + std::to_string(c));
     }
   }
-  if (ins.size() == 1) return ins[0];
   for (auto& b : ins) {
     std::vector<int> all;
     for (size_t c = 0; c < ncol; ++c) all.push_back((int)c);
     resolve_varlen_extents(b, all, stream);
   }
+  if (ins.size() == 1) return ins[0];
   int64_t total_rows = 0;
   std::vector<int64_t> row0(ins.size());
   for (size_t b = 0; b < ins.size(); ++b) { row0[b] = total_rows; total_rows += ins[b].num_rows; }

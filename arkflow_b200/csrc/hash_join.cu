@@ -1,0 +1,322 @@
+// hash_join.cu — inner equi-join (build + probe + gather) and hash repartition, device-resident.
+//
+// Stands in for DataFusion's HashJoinExec and RepartitionExec(Hash) reached from
+// JoinOperation::join_operation (crates/arkflow-plugin/src/buffer/join.rs:111-118).
+//   build : every non-NULL key of the smaller side claims a table slot with one 128-bit CAS; rows
+//           with equal keys are chained through next[] (head exchange), so duplicates are handled;
+//   probe : two passes over the probe side — count matches per row, exclusive scan, fill
+//           (probe_row, build_row) pairs — then one gather per output column.
+// NULL keys never match.  `SELECT *` = left columns then right columns (SQL order), whichever side
+// was used to build.  Output row order is unspecified (as in DataFusion).
+#include <cub/device/device_scan.cuh>
+
+#include "engine.h"
+#include "hashkey.cuh"
+
+namespace ark {
+
+namespace {
+
+constexpr unsigned int NO_ROW = 0xFFFFFFFFu;
+
+__global__ void join_init_kernel(Key16* keys, unsigned int* head, unsigned long long capacity) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    keys[i] = Key16{KEY_EMPTY, KEY_EMPTY};
+    head[i] = NO_ROW;
+  }
+}
+
+__global__ void join_build_kernel(ColView kc, int key_kind, int64_t n, Key16* keys, unsigned int* head, unsigned int* next,
+                                  unsigned long long mask) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+    if (!col_valid(kc, row)) { next[row] = NO_ROW; continue; }  // NULL keys never match
+    Key16 mine; unsigned long long h;
+    make_key(key_kind, kc, row, &mine, &h);
+    unsigned long long slot = h & mask;
+    while (true) {
+      Key16 cur = ld128(keys + slot);
+      if (cur.hi == KEY_EMPTY) {
+        cur = cas128(keys + slot, Key16{KEY_EMPTY, KEY_EMPTY}, mine);
+        if (cur.hi == KEY_EMPTY && cur.lo == KEY_EMPTY) break;
+      }
+      if (key_equal(mine, cur, kc, kc)) break;
+      slot = (slot + 1) & mask;
+    }
+    next[row] = atomicExch(head + slot, (unsigned int)row);
+  }
+}
+
+// FILL == false: counts[row] = number of matches.  FILL == true: write the pairs at offsets[row].
+template <bool FILL>
+__global__ void join_probe_kernel(ColView pc, ColView bc, int key_kind, int64_t n, const Key16* keys, const unsigned int* head,
+                                  const unsigned int* next, unsigned long long mask, long long* counts, const long long* offsets,
+                                  unsigned int* out_probe, unsigned int* out_build) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+    long long c = 0;
+    if (col_valid(pc, row)) {
+      Key16 mine; unsigned long long h;
+      make_key(key_kind, pc, row, &mine, &h);
+      unsigned long long slot = h & mask;
+      while (true) {
+        const Key16 cur = keys[slot];  // the table is read-only during the probe
+        if (cur.hi == KEY_EMPTY) break;
+        if (key_equal(mine, cur, pc, bc)) {
+          long long o = FILL ? offsets[row] : 0;
+          for (unsigned int b = head[slot]; b != NO_ROW; b = next[b]) {
+            if (FILL) { out_probe[o] = (unsigned int)row; out_build[o] = b; ++o; }
+            ++c;
+          }
+          break;
+        }
+        slot = (slot + 1) & mask;
+      }
+    }
+    if (!FILL) counts[row] = c;
+  }
+}
+
+// ---- gathers -----------------------------------------------------------------------------------------
+__global__ void take_fixed8_kernel(const unsigned long long* src, const unsigned int* idx, long long n, unsigned long long* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+__global__ void take_bits_kernel(const uint8_t* bits, int bit0, const unsigned int* idx, long long n, uint8_t* out_bytes) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const long long p = (long long)idx[i] + bit0; out_bytes[i] = (bits[p >> 3] >> (p & 7)) & 1; }
+}
+__global__ void take_lengths_kernel(const int32_t* offsets, const unsigned int* idx, long long n, int32_t* lens) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const unsigned int r = idx[i]; lens[i] = offsets[r + 1] - offsets[r]; }
+}
+__global__ void take_bytes_kernel(const uint8_t* data, const int32_t* offsets, const unsigned int* idx, long long n,
+                                  const int32_t* out_offsets, uint8_t* out) {
+  // one warp per output row: lanes stride over the bytes
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const unsigned int r = idx[w];
+  const int32_t s0 = offsets[r], len = offsets[r + 1] - s0;
+  uint8_t* d = out + out_offsets[w];
+  for (int i = lane; i < len; i += 32) d[i] = data[s0 + i];
+}
+
+// ---- hash repartition ----------------------------------------------------------------------------------
+__global__ void partition_ids_kernel(ColView kc, int key_kind, int64_t n, int n_parts, uint8_t* part, unsigned int* part_counts) {
+  __shared__ unsigned int s_cnt[32];
+  if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+    Key16 k; unsigned long long h;
+    make_key(key_kind, kc, row, &k, &h);
+    const int p = partition_of(h, n_parts);
+    part[row] = (uint8_t)p;
+    atomicAdd(&s_cnt[p], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < n_parts && s_cnt[threadIdx.x]) atomicAdd(part_counts + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
+// stable within a block chunk is not required: DataFusion's repartition does not preserve order either
+__global__ void partition_scatter_kernel(const uint8_t* part, int64_t n, int n_parts, unsigned int* part_cursor, unsigned int* idx) {
+  __shared__ unsigned int s_cnt[32], s_base[32];
+  const int64_t chunk = (int64_t)blockDim.x * 8;
+  for (int64_t base = (int64_t)blockIdx.x * chunk; base < n; base += (int64_t)gridDim.x * chunk) {
+    if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned int local[8]; int p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t row = base + j * blockDim.x + threadIdx.x;
+      p[j] = row < n ? part[row] : -1;
+      if (p[j] >= 0) local[j] = atomicAdd(&s_cnt[p[j]], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < n_parts) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(part_cursor + threadIdx.x, s_cnt[threadIdx.x]) : 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t row = base + j * blockDim.x + threadIdx.x;
+      if (p[j] >= 0) idx[s_base[p[j]] + local[j]] = (unsigned int)row;
+    }
+    __syncthreads();
+  }
+}
+
+int key_kind_of(DType t) {
+  switch (t) {
+    case DType::Int64: return KEY_INT64;
+    case DType::Bool: return KEY_BOOL;
+    case DType::Utf8: case DType::Binary: return KEY_BYTES;
+    default: fail(ARK_ERR_UNSUPPORTED, std::string("hash key of type ") + dtype_name(t));
+  }
+}
+
+unsigned grid_for(int64_t n, int threads = 256) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, threads), 148 * 16)); }
+
+}  // namespace
+
+// out[i] = column[idx[i]] for i < n  (idx on the device)
+Column take_column(const Column& src, const unsigned int* idx, int64_t n, const std::string& name, cudaStream_t stream) {
+  Column c;
+  c.field = src.field; c.field.name = name; c.length = n;
+  const unsigned g = (unsigned)std::max<int64_t>(1, ceil_div(n, 256));
+  switch (src.field.type) {
+    case DType::Int64: case DType::Float64: {
+      BufferPtr d = device_alloc((size_t)std::max<int64_t>(n, 1) * 8);
+      if (n) { KernelTimer t("take_fixed8_kernel", stream); take_fixed8_kernel<<<g, 256, 0, stream>>>((const unsigned long long*)src.data, idx, n, (unsigned long long*)d.get()); }
+      c.data = (const uint8_t*)d.get(); c.data_bytes = n * 8; c.owners = {d};
+      break;
+    }
+    case DType::Bool: {
+      BufferPtr bytes = device_alloc((size_t)std::max<int64_t>(n, 1)), bits = device_alloc((size_t)(n + 7) / 8 + 1);
+      if (n) { KernelTimer t("take_bits_kernel", stream); take_bits_kernel<<<g, 256, 0, stream>>>(src.data, src.data_bit0, idx, n, (uint8_t*)bytes.get()); }
+      launch_pack_bits((const uint8_t*)bytes.get(), n, (uint8_t*)bits.get(), nullptr, stream);
+      c.data = (const uint8_t*)bits.get(); c.data_bit0 = 0; c.data_bytes = (n + 7) / 8; c.owners = {bits, bytes};
+      break;
+    }
+    case DType::Utf8: case DType::Binary: {
+      BufferPtr lens = device_alloc((size_t)(n + 1) * 4), offs = device_alloc((size_t)(n + 1) * 4);
+      ARK_CUDA(cudaMemsetAsync(lens.get(), 0, (size_t)(n + 1) * 4, stream));
+      if (n) { KernelTimer t("take_lengths_kernel", stream); take_lengths_kernel<<<g, 256, 0, stream>>>(src.offsets, idx, n, (int32_t*)lens.get()); }
+      size_t tb = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tb, (int32_t*)lens.get(), (int32_t*)offs.get(), (int)(n + 1), stream);
+      BufferPtr tmp = device_alloc(tb + 16);
+      note_launch("cub::DeviceScan::ExclusiveSum");
+      cub::DeviceScan::ExclusiveSum(tmp.get(), tb, (int32_t*)lens.get(), (int32_t*)offs.get(), (int)(n + 1), stream);
+      BufferPtr h = pinned_alloc(64);
+      ARK_CUDA(cudaMemcpyAsync(h.get(), (int32_t*)offs.get() + n, 4, cudaMemcpyDeviceToHost, stream));
+      ARK_CUDA(cudaStreamSynchronize(stream));
+      const int32_t total = *(int32_t*)h.get();
+      if (total < 0) fail(ARK_ERR_PROCESS, "Collection query results error: Arrow error: offset overflow, result column exceeds 2 GiB");
+      BufferPtr bytes = device_alloc((size_t)total + 16);
+      if (n) {
+        KernelTimer t("take_bytes_kernel", stream);
+        take_bytes_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, stream>>>(src.data, src.offsets, idx, n, (const int32_t*)offs.get(), (uint8_t*)bytes.get());
+      }
+      c.offsets = (const int32_t*)offs.get(); c.data = (const uint8_t*)bytes.get(); c.data_bytes = total; c.first_offset = 0;
+      c.owners = {offs, bytes};
+      break;
+    }
+    default:
+      if (src.field.format != "n") fail(ARK_ERR_UNSUPPORTED, "gather of a column with Arrow type '" + src.field.format + "'");
+      break;
+  }
+  if (src.validity && n > 0) {
+    BufferPtr vb = device_alloc((size_t)n), bits = device_alloc((size_t)(n + 7) / 8 + 1);
+    { KernelTimer t("take_bits_kernel", stream); take_bits_kernel<<<g, 256, 0, stream>>>(src.validity, src.validity_bit0, idx, n, (uint8_t*)vb.get()); }
+    launch_pack_bits((const uint8_t*)vb.get(), n, (uint8_t*)bits.get(), nullptr, stream);
+    c.validity = (const uint8_t*)bits.get(); c.validity_bit0 = 0; c.null_count = -1;
+    c.owners.push_back(bits); c.owners.push_back(vb);
+  } else { c.validity = nullptr; c.null_count = 0; }
+  return c;
+}
+
+Batch run_join(const Plan& plan, Batch& left, Batch& right, cudaStream_t stream) {
+  if (left.num_rows >= (1ll << 32) - 1 || right.num_rows >= (1ll << 32) - 1) fail(ARK_ERR_UNSUPPORTED, "join input with 2^32 or more rows");
+  Column& lk = left.cols[plan.left_key];
+  Column& rk = right.cols[plan.right_key];
+  const int key_kind = key_kind_of(lk.field.type);
+  // every projected var-len column needs its extent for the gathers
+  { std::vector<int> a, b; for (size_t i = 0; i < left.cols.size(); ++i) a.push_back((int)i); for (size_t i = 0; i < right.cols.size(); ++i) b.push_back((int)i);
+    resolve_varlen_extents(left, a, stream); resolve_varlen_extents(right, b, stream); }
+  const bool build_left = left.num_rows <= right.num_rows;
+  Batch& B = build_left ? left : right;
+  Batch& Pb = build_left ? right : left;
+  const ColView bc = (build_left ? lk : rk).view(), pc = (build_left ? rk : lk).view();
+  const int64_t nb = B.num_rows, np = Pb.num_rows;
+
+  unsigned long long capacity = 1ull << 10;
+  while (capacity < 2ull * (unsigned long long)std::max<int64_t>(nb, 1)) capacity <<= 1;
+  BufferPtr keys = device_alloc((size_t)capacity * sizeof(Key16)), head = device_alloc((size_t)capacity * 4);
+  BufferPtr next = device_alloc((size_t)std::max<int64_t>(nb, 1) * 4);
+  {
+    KernelTimer t("join_init_kernel", stream);
+    join_init_kernel<<<grid_for((int64_t)capacity), 256, 0, stream>>>((Key16*)keys.get(), (unsigned int*)head.get(), capacity);
+  }
+  if (nb) {
+    KernelTimer t("join_build_kernel", stream);
+    join_build_kernel<<<grid_for(nb), 256, 0, stream>>>(bc, key_kind, nb, (Key16*)keys.get(), (unsigned int*)head.get(), (unsigned int*)next.get(), capacity - 1);
+  }
+  BufferPtr counts = device_alloc((size_t)(np + 1) * 8), offsets = device_alloc((size_t)(np + 1) * 8);
+  ARK_CUDA(cudaMemsetAsync(counts.get(), 0, (size_t)(np + 1) * 8, stream));
+  if (np) {
+    KernelTimer t("join_probe_count_kernel", stream);
+    join_probe_kernel<false><<<grid_for(np), 256, 0, stream>>>(pc, bc, key_kind, np, (const Key16*)keys.get(), (const unsigned int*)head.get(),
+                                                               (const unsigned int*)next.get(), capacity - 1, (long long*)counts.get(), nullptr, nullptr, nullptr);
+  }
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, (long long*)counts.get(), (long long*)offsets.get(), (int)(np + 1), stream);
+  BufferPtr tmp = device_alloc(tb + 16);
+  note_launch("cub::DeviceScan::ExclusiveSum");
+  cub::DeviceScan::ExclusiveSum(tmp.get(), tb, (long long*)counts.get(), (long long*)offsets.get(), (int)(np + 1), stream);
+  BufferPtr h = pinned_alloc(64);
+  ARK_CUDA(cudaMemcpyAsync(h.get(), (long long*)offsets.get() + np, 8, cudaMemcpyDeviceToHost, stream));
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  const long long pairs = *(long long*)h.get();
+  if (pairs >= (1ll << 31)) fail(ARK_ERR_UNSUPPORTED, "join result with 2^31 or more rows in one batch");
+  BufferPtr probe_idx = device_alloc((size_t)std::max<long long>(pairs, 1) * 4), build_idx = device_alloc((size_t)std::max<long long>(pairs, 1) * 4);
+  if (np && pairs) {
+    KernelTimer t("join_probe_fill_kernel", stream);
+    join_probe_kernel<true><<<grid_for(np), 256, 0, stream>>>(pc, bc, key_kind, np, (const Key16*)keys.get(), (const unsigned int*)head.get(),
+                                                              (const unsigned int*)next.get(), capacity - 1, nullptr, (const long long*)offsets.get(),
+                                                              (unsigned int*)probe_idx.get(), (unsigned int*)build_idx.get());
+  }
+  ARK_CUDA(cudaGetLastError());
+  const unsigned int* lidx = (const unsigned int*)(build_left ? build_idx.get() : probe_idx.get());
+  const unsigned int* ridx = (const unsigned int*)(build_left ? probe_idx.get() : build_idx.get());
+  Batch out;
+  out.num_rows = pairs;
+  for (const auto& jo : plan.join_out) {
+    const Column& src = jo.side == 0 ? left.cols[jo.col] : right.cols[jo.col];
+    if (!src.present) fail(ARK_ERR_UNSUPPORTED, "join output column '" + jo.name + "' has Arrow type '" + src.field.format + "'");
+    out.cols.push_back(take_column(src, jo.side == 0 ? lidx : ridx, pairs, jo.name, stream));
+  }
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  return out;
+}
+
+// RepartitionExec(Hash([key], n_parts)): rows reordered into n_parts contiguous ranges by key owner
+Batch hash_partition(Batch& in, const std::string& key_column, int n_parts, std::vector<int64_t>& part_rows, cudaStream_t stream) {
+  if (n_parts < 1 || n_parts > 32) fail(ARK_ERR_PROCESS, "n_parts must be in [1, 32]");
+  const int ki = in.find(key_column);
+  if (ki < 0) fail(ARK_ERR_PROCESS, "Schema error: No field named " + key_column + ".");
+  const int64_t n = in.num_rows;
+  if (n >= (1ll << 32) - 1) fail(ARK_ERR_UNSUPPORTED, "partition input with 2^32 or more rows");
+  std::vector<int> all;
+  for (size_t i = 0; i < in.cols.size(); ++i) all.push_back((int)i);
+  resolve_varlen_extents(in, all, stream);
+  const int key_kind = key_kind_of(in.cols[ki].field.type);
+  BufferPtr part = device_alloc((size_t)std::max<int64_t>(n, 1)), idx = device_alloc((size_t)std::max<int64_t>(n, 1) * 4);
+  BufferPtr ctl = device_alloc(256), hctl = pinned_alloc(256);
+  ARK_CUDA(cudaMemsetAsync(ctl.get(), 0, 256, stream));
+  unsigned int* counts = (unsigned int*)ctl.get();
+  unsigned int* cursor = counts + 32;
+  if (n) {
+    KernelTimer t("partition_ids_kernel", stream);
+    partition_ids_kernel<<<grid_for(n), 256, 0, stream>>>(in.cols[ki].view(), key_kind, n, n_parts, (uint8_t*)part.get(), counts);
+  }
+  ARK_CUDA(cudaMemcpyAsync(hctl.get(), counts, 128, cudaMemcpyDeviceToHost, stream));
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  unsigned int* hc = (unsigned int*)hctl.get();
+  unsigned int* hcur = hc + 32;
+  unsigned int run = 0;
+  part_rows.assign(n_parts, 0);
+  for (int p = 0; p < n_parts; ++p) { part_rows[p] = hc[p]; hcur[p] = run; run += hc[p]; }
+  ARK_CUDA(cudaMemcpyAsync(cursor, hcur, 128, cudaMemcpyHostToDevice, stream));
+  if (n) {
+    KernelTimer t("partition_scatter_kernel", stream);
+    partition_scatter_kernel<<<grid_for(ceil_div(n, 8)), 256, 0, stream>>>((const uint8_t*)part.get(), n, n_parts, cursor, (unsigned int*)idx.get());
+  }
+  ARK_CUDA(cudaGetLastError());
+  Batch out;
+  out.num_rows = n; out.input_name = in.input_name;
+  for (auto& c : in.cols) {
+    if (!c.present) fail(ARK_ERR_UNSUPPORTED, "partition of a column with Arrow type '" + c.field.format + "'");
+    out.cols.push_back(take_column(c, (const unsigned int*)idx.get(), n, c.field.name, stream));
+  }
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  return out;
+}
+
+}  // namespace ark

@@ -1,0 +1,109 @@
+// hashkey.cuh — 16-byte table keys shared by the GROUP BY and JOIN kernels: construction from a
+// column row, hashing, equality, and the 128-bit CAS / load used to claim and read table slots.
+#pragma once
+#include "hash_agg.cuh"
+#include "vm.cuh"
+
+namespace ark {
+
+static __device__ __forceinline__ Key16 cas128(Key16* addr, Key16 cmp, Key16 val) {
+  Key16 old;
+  asm volatile(
+      "{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\t"
+      "atom.relaxed.gpu.global.cas.b128 o, [%6], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
+      : "=l"(old.lo), "=l"(old.hi)
+      : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(addr)
+      : "memory");
+  return old;
+}
+static __device__ __forceinline__ Key16 ld128(const Key16* addr) {  // single 128-bit access (LDG.E.128.STRONG.GPU)
+  Key16 v;
+  asm volatile("{\n\t.reg .b128 t;\n\tld.relaxed.gpu.global.b128 t, [%2];\n\tmov.b128 {%0, %1}, t;\n\t}"
+               : "=l"(v.lo), "=l"(v.hi) : "l"(addr) : "memory");
+  return v;
+}
+
+static __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static __device__ __forceinline__ unsigned long long hash_key16(Key16 k) {
+  return mix64(k.lo * 0x9E3779B97F4A7C15ull + mix64(k.hi + 0x632BE59BD9B4E019ull));
+}
+static __device__ inline unsigned long long hash_bytes(const uint8_t* p, int len) {
+  unsigned long long h = 0xCBF29CE484222325ull;
+  for (int i = 0; i < len; ++i) { h ^= p[i]; h *= 0x100000001B3ull; }
+  return mix64(h ^ (unsigned long long)len);
+}
+
+// Builds the table key of (column c, row): Key16 + 64-bit hash.
+static __device__ inline void make_key(int kind, const ColView& c, int64_t row, Key16* key, unsigned long long* hash) {
+  Key16 k;
+  if (kind == KEY_NONE) { k.lo = 0; k.hi = (unsigned long long)KEYTAG_INT << 32; *key = k; *hash = 0; return; }
+  if (!col_valid(c, row)) { k.lo = 0; k.hi = (unsigned long long)KEYTAG_NULL << 32; *key = k; *hash = hash_key16(k); return; }
+  if (kind == KEY_INT64) {
+    k.lo = ((const unsigned long long*)c.data)[row]; k.hi = (unsigned long long)KEYTAG_INT << 32;
+  } else if (kind == KEY_BOOL) {
+    k.lo = bit_get((const uint8_t*)c.data, row + c.data_bit0); k.hi = (unsigned long long)KEYTAG_INT << 32;
+  } else {
+    const int32_t o0 = c.offsets[row], o1 = c.offsets[row + 1];
+    const int len = o1 - o0;
+    const uint8_t* p = (const uint8_t*)c.data + o0;
+    if (len <= 12) {
+      unsigned w[3] = {0, 0, 0};
+      if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) {
+        const unsigned* q = (const unsigned*)p;
+        for (int i = 0; i < 3; ++i) {
+          const int rem = len - 4 * i;
+          if (rem >= 4) w[i] = q[i];
+          else if (rem > 0) { for (int b = 0; b < rem; ++b) w[i] |= (unsigned)p[4 * i + b] << (8 * b); }
+        }
+      } else {
+        for (int b = 0; b < len; ++b) w[b >> 2] |= (unsigned)p[b] << (8 * (b & 3));
+      }
+      k.lo = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
+      k.hi = (unsigned long long)w[2] | ((unsigned long long)(unsigned)len << 32);
+    } else {
+      unsigned prefix = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
+      k.lo = (unsigned long long)row;
+      k.hi = (unsigned long long)prefix | ((unsigned long long)(KEYTAG_LONG | (unsigned)len) << 32);
+      *key = k; *hash = hash_bytes(p, len); return;
+    }
+  }
+  *key = k; *hash = hash_key16(k);
+}
+
+static __device__ __forceinline__ bool key_is_long(Key16 k) {
+  const unsigned tag = (unsigned)(k.hi >> 32);
+  return (tag & KEYTAG_LONG) && tag < KEYTAG_NULL;
+}
+
+// equality of a probing key with a stored key (long keys: compare the bytes of both rows)
+// `mine` was built from column mc, `stored` from column sc (the same column for GROUP BY; probe vs
+// build column for a join)
+static __device__ inline bool key_equal(Key16 mine, Key16 stored, const ColView& mc, const ColView& sc) {
+  if (!key_is_long(mine)) return mine.lo == stored.lo && mine.hi == stored.hi;
+  if (mine.hi != stored.hi) return false;
+  if (mine.lo == stored.lo && mc.data == sc.data && mc.offsets == sc.offsets) return true;
+  const int len = (int)((unsigned)(mine.hi >> 32) & 0x7FFFFFFFu);
+  const uint8_t* a = (const uint8_t*)mc.data + mc.offsets[(int64_t)mine.lo];
+  const uint8_t* b = (const uint8_t*)sc.data + sc.offsets[(int64_t)stored.lo];
+  for (int i = 0; i < len; ++i) if (a[i] != b[i]) return false;
+  return true;
+}
+
+
+static __device__ __forceinline__ unsigned long long stored_key_hash(Key16 k, const ColView& kc) {
+  if (key_is_long(k)) {
+    const int len = (int)((unsigned)(k.hi >> 32) & 0x7FFFFFFFu);
+    return hash_bytes((const uint8_t*)kc.data + kc.offsets[(int64_t)k.lo], len);
+  }
+  return hash_key16(k);
+}
+// owner partition of a key hash: top 24 bits scaled to [0, n_parts) — identical on every rank
+static __device__ __forceinline__ int partition_of(unsigned long long h, int n_parts) {
+  return (int)(((h >> 40) * (unsigned long long)n_parts) >> 24);
+}
+
+}  // namespace ark

@@ -20,6 +20,7 @@
 
 #include "engine.h"
 #include "json_mini.h"
+#include "pow10_table.h"
 
 namespace ark {
 
@@ -167,11 +168,20 @@ __device__ bool parse_f64(const uint8_t* s, int len, double* out) {
   else if (mant < (1ull << 53) && exp10 >= -22 && exp10 <= 22) {
     v = (double)mant;
     v = exp10 < 0 ? v / kPow10[-exp10] : v * kPow10[exp10];
-  } else {
-    v = (double)mant;
-    int e = exp10;
-    while (e > 0) { const int k = e > 22 ? 22 : e; v *= kPow10[k]; e -= k; }
-    while (e < 0) { const int k = -e > 22 ? 22 : -e; v /= kPow10[k]; e += k; }
+  } else if (exp10 > ARK_POW10_MAX) v = __longlong_as_double(0x7FF0000000000000ll);  // overflow → inf
+  else if (exp10 < ARK_POW10_MIN) v = 0.0;
+  else {
+    // 64-bit mantissa × 64-bit truncated power of ten → 128-bit product, top 64 bits + sticky → f64
+    // (round-to-nearest-even by the integer→double conversion).  Within 1 ulp; exact unless the
+    // product lies within 2^-63 of a rounding boundary.
+    const int lz = __clzll((long long)mant);
+    const unsigned long long w = mant << lz;
+    const unsigned long long pm = kPow10Mant[exp10 - ARK_POW10_MIN];
+    unsigned long long hi = __umul64hi(w, pm), lo = w * pm;
+    int e2 = (int)kPow10Exp2[exp10 - ARK_POW10_MIN] - lz + 64;
+    if (!(hi >> 63)) { hi = (hi << 1) | (lo >> 63); lo <<= 1; e2 -= 1; }
+    if (lo) hi |= 1;
+    v = ldexp((double)hi, e2);
   }
   *out = neg ? -v : v;
   return true;

@@ -1,13 +1,10 @@
 // stubs.cu — temporary: entry points / executors not implemented yet.
 #include "engine.h"
 namespace ark {
-Batch run_join(const Plan&, Batch&, Batch&, cudaStream_t) { fail(ARK_ERR_UNSUPPORTED, "join not implemented yet"); }
 }
 
 #define ARK_STUB(name) { ark::set_last_error(name " is not implemented yet"); return ARK_ERR_UNSUPPORTED; }
 extern "C" {
-int ark_sql_process_tables(ark_proc_t*, int, const char* const*, ArrowArray*, ArrowSchema*, ArrowArray*, ArrowSchema*) ARK_STUB("ark_sql_process_tables")
-int ark_sql_process_tables_device(ark_proc_t*, int, const char* const*, ArrowDeviceArray*, ArrowSchema*, ArrowDeviceArray*, ArrowSchema*) ARK_STUB("ark_sql_process_tables_device")
 int ark_arrow_to_json_create(const char*, ark_proc_t**) ARK_STUB("ark_arrow_to_json_create")
 int ark_arrow_to_json_process(ark_proc_t*, ArrowArray*, ArrowSchema*, ArrowArray*, ArrowSchema*) ARK_STUB("ark_arrow_to_json_process")
 int ark_buffer_create(const char*, const char*, const char*, ark_buf_t**) ARK_STUB("ark_buffer_create")
@@ -16,5 +13,4 @@ int ark_buffer_read(ark_buf_t*, ArrowArray*, ArrowSchema*, uint64_t*, int64_t, i
 int ark_buffer_flush(ark_buf_t*) ARK_STUB("ark_buffer_flush")
 int ark_buffer_close(ark_buf_t*) ARK_STUB("ark_buffer_close")
 void ark_buffer_destroy(ark_buf_t*) {}
-int ark_hash_partition_device(ArrowDeviceArray*, ArrowSchema*, const char*, int, ArrowDeviceArray*, ArrowSchema*, int64_t*) ARK_STUB("ark_hash_partition_device")
 }

@@ -70,6 +70,25 @@ class NativeEngine:
     def process(self, batch: DeviceBatch) -> Optional[DeviceBatch]:
         return self.proc.process_device(batch)
 
+    def hash_partition(self, batch: DeviceBatch, key_column: str, n_parts: int):
+        from .arrow_ffi import release_array, release_schema
+        from .processor import _check
+
+        lib = L.lib()
+        dev, sch = batch.export()
+        out_dev, out_sch = L.ArrowDeviceArray(), L.ArrowSchema()
+        rows = (C.c_int64 * n_parts)()
+        try:
+            status = lib.ark_hash_partition_device(C.byref(dev), C.byref(sch), key_column.encode(), n_parts, C.byref(out_dev), C.byref(out_sch), rows)
+        finally:
+            release_schema(sch)
+            release_array(dev.array)
+        _check(status)
+        return DeviceBatch.adopt(out_dev, out_sch), list(rows)
+
+    def join(self, tables: dict) -> DeviceBatch:
+        return self.proc.process_tables_device(tables)
+
 
 # ---------------------------------------------------------------------------------------------
 # all-to-all(v) of a partition-ordered batch
@@ -150,3 +169,15 @@ def distributed_group_by(engine, local_batch: DeviceBatch, group=None) -> Device
         result = DeviceBatch([DeviceColumn(c.name, c.dtype, 0, c.data[:0], None if c.offsets is None else c.offsets[:1], None, 0, c.nullable)
                               for c in result.columns], 0)
     return result
+
+
+def distributed_join(engine, tables: dict, keys: dict, group=None) -> DeviceBatch:
+    """Inner equi-join over the union of every rank's tables.  `keys[name]` is the join column of table
+    `name`.  Both sides are hash-partitioned on the key and exchanged with one all-to-all(v) each
+    (SURVEY.md §8(e)); the local join then sees every row of its key range.  Output stays sharded."""
+    world = dist.get_world_size(group)
+    local = {}
+    for name, batch in tables.items():
+        parted, rows = engine.hash_partition(batch, keys[name], world)
+        local[name] = exchange_partitions(parted, rows, group)
+    return engine.join(local)

@@ -213,6 +213,29 @@ class SqlProcessor(_NativeProcessor):
         return F.import_record_batch(out_arr, out_sch)
 
 
+    def process_tables_device(self, tables: dict) -> Optional["F.DeviceBatch"]:
+        lib = L.lib()
+        n = len(tables)
+        names = (C.c_char_p * n)(*[k.encode() for k in tables])
+        devs = (L.ArrowDeviceArray * n)()
+        schs = (L.ArrowSchema * n)()
+        for i, b in enumerate(tables.values()):
+            d, s = b.export()
+            C.memmove(C.addressof(devs[i]), C.addressof(d), C.sizeof(L.ArrowDeviceArray))
+            C.memmove(C.addressof(schs[i]), C.addressof(s), C.sizeof(L.ArrowSchema))
+        out_dev, out_sch = L.ArrowDeviceArray(), L.ArrowSchema()
+        try:
+            status = lib.ark_sql_process_tables_device(self._h, n, names, devs, schs, C.byref(out_dev), C.byref(out_sch))
+        finally:
+            for i in range(n):
+                F.release_schema(schs[i])
+                F.release_array(devs[i].array)
+        _check(status)
+        if not out_dev.array.release:
+            return None
+        return F.DeviceBatch.adopt(out_dev, out_sch)
+
+
 class JsonToArrowProcessor(_NativeProcessor):
     """`type: json_to_arrow` — crates/arkflow-plugin/src/processor/json.rs:42-72."""
 
