@@ -56,3 +56,113 @@ def concat_batches_device(batches: list[F.DeviceBatch]) -> F.DeviceBatch:
             F.release_array(devs[i].array)
     _check(status)
     return F.DeviceBatch.adopt(out_dev, out_sch)
+
+
+class Ack:
+    """trait Ack (core/input/mod.rs:52-57)."""
+
+    def ack(self) -> None:  # pragma: no cover - interface
+        pass
+
+
+class NoopAck(Ack):
+    pass
+
+
+class VecAck(Ack):
+    """core/input/mod.rs:66-95 / ArrayAck memory.rs:227-237: acknowledges every contained ack."""
+
+    def __init__(self, acks):
+        self.acks = list(acks)
+
+    def ack(self) -> None:
+        for a in self.acks:
+            a.ack()
+
+
+class Buffer:
+    """trait Buffer (core/buffer/mod.rs:26-37) over the C ABI.  write(msg, ack) / read() / flush() / close()."""
+
+    KIND = ""
+
+    def __init__(self, config: Optional[dict], input_names: Optional[list] = None):
+        lib = L.lib()
+        handle = C.c_void_p()
+        cfg = None if config is None else json.dumps(config).encode()
+        names = None if input_names is None else json.dumps(list(input_names)).encode()
+        _check(lib.ark_buffer_create(self.KIND.encode(), cfg, names, C.byref(handle)))
+        self._h = handle
+        self._acks: dict[int, Ack] = {}
+        self._next = 1
+
+    def write(self, msg, ack: Optional[Ack] = None) -> None:
+        mb = msg if isinstance(msg, MessageBatch) else MessageBatch(msg)
+        token = self._next
+        self._next += 1
+        self._acks[token] = ack or NoopAck()
+        arr, sch = F.export_record_batch(mb.record_batch)
+        try:
+            status = L.lib().ark_buffer_write(self._h, C.byref(arr), C.byref(sch),
+                                              None if mb.input_name is None else mb.input_name.encode(), token)
+        finally:
+            F.release_schema(sch)
+            F.release_array(arr)
+        _check(status)
+
+    def read(self):
+        """Blocks like Buffer::read.  Returns None (closed and empty) or (MessageBatch, VecAck)."""
+        out_arr, out_sch = L.ArrowArray(), L.ArrowSchema()
+        cap = max(len(self._acks), 1) + 16
+        acks = (C.c_uint64 * cap)()
+        n = C.c_int64(0)
+        _check(L.lib().ark_buffer_read(self._h, C.byref(out_arr), C.byref(out_sch), acks, cap, C.byref(n)))
+        if not out_arr.release:
+            return None
+        rb = F.import_record_batch(out_arr, out_sch)
+        got = [self._acks.pop(int(acks[i])) for i in range(n.value)]
+        return MessageBatch(rb), VecAck(got)
+
+    def flush(self) -> None:
+        _check(L.lib().ark_buffer_flush(self._h))
+
+    def close(self) -> None:
+        _check(L.lib().ark_buffer_close(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                L.lib().ark_buffer_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class MemoryBuffer(Buffer):
+    """`type: memory` {capacity, timeout} — buffer/memory.rs:39-237."""
+
+    KIND = "memory"
+
+
+class SessionWindow(Buffer):
+    """`type: session_window` {gap, join?} — buffer/session_window.rs:39-159."""
+
+    KIND = "session_window"
+
+
+class TumblingWindow(Buffer):
+    """`type: tumbling_window` {interval, join?} — buffer/tumbling_window.rs:38-145."""
+
+    KIND = "tumbling_window"
+
+
+_BUFFERS = {"memory": MemoryBuffer, "session_window": SessionWindow, "tumbling_window": TumblingWindow}
+
+
+def build_buffer(config: dict, input_names: Optional[list] = None) -> Buffer:
+    """BufferConfig::build (core/buffer/mod.rs:50-73): {"type": ..., <flattened config>}."""
+    cfg = dict(config)
+    kind = cfg.pop("type", None)
+    cfg.pop("name", None)
+    if kind not in _BUFFERS:
+        raise ArkError(L.ARK_ERR_CONFIG, f"Unknown buffer type: {kind}")
+    return _BUFFERS[kind](cfg if cfg else None, input_names)

@@ -54,12 +54,12 @@ def test_join_int_key_duplicates_nulls_and_projection(gpu):
     rng = np.random.default_rng(4)
     n1, n2 = 3000, 2000
     a = pa.record_batch({"k": pa.array([None if rng.random() < 0.1 else int(x) for x in rng.integers(0, 300, n1)], pa.int64()),
-                         "av": pa.array(rng.random(n1), pa.float64()), "as": pa.array(["a%d" % i for i in range(n1)]),
+                         "av": pa.array(rng.random(n1), pa.float64()), "astr": pa.array(["a%d" % i for i in range(n1)]),
                          "ab": pa.array([bool(i & 1) for i in range(n1)], pa.bool_())})
     b = pa.record_batch({"k": pa.array([None if rng.random() < 0.1 else int(x) for x in rng.integers(100, 500, n2)], pa.int64()),
                          "bv": pa.array(rng.integers(0, 9, n2), pa.int64(), mask=rng.random(n2) < 0.2)})
     check_join({"a": a, "b": b}, "SELECT * FROM a JOIN b ON a.k = b.k")
-    check_join({"a": a, "b": b}, "SELECT a.as, b.bv, a.k AS key, ab FROM a INNER JOIN b ON b.k = a.k")
+    check_join({"a": a, "b": b}, "SELECT a.astr, b.bv, a.k AS key, ab FROM a INNER JOIN b ON b.k = a.k")
     check_join({"a": a, "b": b}, "SELECT x.*, y.bv FROM a AS x JOIN b y ON x.k = y.k")
 
 
