@@ -99,6 +99,79 @@ const char* vm_error_text(int e) {
 
 }  // namespace
 
+// ---- fast path: TMA-staged persistent kernel (filter_project_tma.cu) ------------------------------------
+size_t filter_project_tma_smem_bytes();
+int filter_project_tma_tile_rows();
+bool launch_filter_project_tma(int64_t n_rows, int n_fixed, const void* const* fixed_in, void* const* fixed_out, const int32_t* offsets_in,
+                               const uint8_t* data_in, int32_t* offsets_out, uint8_t* data_out, int cmp, int is_f64, uint64_t constant,
+                               unsigned long long* desc, unsigned int* ticket, long long* totals, cudaStream_t stream);
+
+// SELECT <≤2 fixed-width cols> [, <1 var-len col>] WHERE <fixed col> <cmp> <literal>, no NULLs in the used columns.
+static bool try_fast_filter(const Plan& plan, Batch& in, Batch& out, cudaStream_t stream) {
+  if (!plan.has_pred || !plan.simple.enabled || plan.outputs.empty()) return false;
+  auto src_col = [&](int slot) -> Column& { return in.cols[plan.used_cols[slot]]; };
+  for (size_t s = 0; s < plan.used_cols.size(); ++s) if (src_col((int)s).validity) return false;
+  int fixed_slots[2] = {plan.simple.slot, -1};
+  int n_fixed = 1, out_of_fixed[2] = {-1, -1}, varlen_out = -1;
+  for (size_t i = 0; i < plan.outputs.size(); ++i) {
+    const OutputCol& oc = plan.outputs[i];
+    if (oc.src.kind != ValueSource::PassThrough) return false;
+    const DType t = src_col(oc.src.slot).field.type;
+    if (t == DType::Int64 || t == DType::Float64) {
+      int c = -1;
+      for (int k = 0; k < n_fixed; ++k) if (fixed_slots[k] == oc.src.slot) c = k;
+      if (c < 0) { if (n_fixed == 2) return false; c = n_fixed; fixed_slots[n_fixed++] = oc.src.slot; }
+      if (out_of_fixed[c] >= 0) return false;  // the same column projected twice: general path
+      out_of_fixed[c] = (int)i;
+    } else if (t == DType::Utf8 || t == DType::Binary) {
+      if (varlen_out >= 0) return false;
+      varlen_out = (int)i;
+    } else return false;
+  }
+  const int64_t n = in.num_rows;
+  const int tile_rows = filter_project_tma_tile_rows();
+  const int n_tiles = (int)ceil_div(n, tile_rows);
+  const void* fin[2] = {nullptr, nullptr};
+  void* fout[2] = {nullptr, nullptr};
+  BufferPtr fbuf[2], obuf, dbuf;
+  for (int c = 0; c < n_fixed; ++c) {
+    fin[c] = src_col(fixed_slots[c]).data;
+    if (out_of_fixed[c] >= 0) { fbuf[c] = device_alloc((size_t)n * 8 + 16); fout[c] = fbuf[c].get(); }
+  }
+  const Column* vs = varlen_out >= 0 ? &src_col(plan.outputs[varlen_out].src.slot) : nullptr;
+  if (vs) { obuf = device_alloc((size_t)(n + 1) * 4 + 16); dbuf = device_alloc((size_t)std::max<int64_t>(vs->data_bytes, 0) + 32); }
+  const size_t desc_bytes = (size_t)n_tiles * FP_CHANNELS * 8;
+  const size_t scratch_bytes = round_up((int64_t)desc_bytes + 64 + FP_CHANNELS * 8, 256);
+  BufferPtr scratch = device_alloc(scratch_bytes);
+  ARK_CUDA(cudaMemsetAsync(scratch.get(), 0, scratch_bytes, stream));
+  long long* totals = (long long*)((char*)scratch.get() + desc_bytes + 16);
+  if (!launch_filter_project_tma(n, n_fixed, fin, fout, vs ? vs->offsets : nullptr, vs ? vs->data : nullptr, vs ? (int32_t*)obuf.get() : nullptr,
+                                 vs ? (uint8_t*)dbuf.get() : nullptr, plan.simple.cmp, plan.simple.is_f64, plan.simple.constant,
+                                 (unsigned long long*)scratch.get(), (unsigned int*)((char*)scratch.get() + desc_bytes), totals, stream))
+    return false;
+  ARK_CUDA(cudaGetLastError());
+  BufferPtr host_res = pinned_alloc(64);
+  ARK_CUDA(cudaMemcpyAsync(host_res.get(), totals, 16, cudaMemcpyDeviceToHost, stream));
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  const int64_t count = ((const int64_t*)host_res.get())[0], bytes = ((const int64_t*)host_res.get())[1];
+  out.cols.resize(plan.outputs.size());
+  out.num_rows = count;
+  for (size_t i = 0; i < plan.outputs.size(); ++i) {
+    const OutputCol& oc = plan.outputs[i];
+    Column& c = out.cols[i];
+    c.field.name = oc.name; c.field.type = oc.src.type; c.field.nullable = oc.src.nullable;
+    c.length = count; c.null_count = 0;
+    if ((int)i == varlen_out) {
+      c.offsets = (const int32_t*)obuf.get(); c.data = (const uint8_t*)dbuf.get(); c.data_bytes = bytes; c.first_offset = 0;
+      c.owners = {obuf, dbuf};
+    } else {
+      const int k = out_of_fixed[0] == (int)i ? 0 : 1;
+      c.data = (const uint8_t*)fbuf[k].get(); c.data_bytes = count * 8; c.owners = {fbuf[k]};
+    }
+  }
+  return true;
+}
+
 Batch run_filter_project(const Plan& plan, Batch& in, cudaStream_t stream) {
   const int64_t n = in.num_rows;
   Batch out;
@@ -119,6 +192,17 @@ Batch run_filter_project(const Plan& plan, Batch& in, cudaStream_t stream) {
     for (auto& oc : plan.outputs)
       if (oc.src.kind == ValueSource::PassThrough) varlen.push_back(plan.used_cols[oc.src.slot]);
     resolve_varlen_extents(in, varlen, stream);
+  }
+
+  if (try_fast_filter(plan, in, out, stream)) {
+    if (plan.limit >= 0 && out.num_rows > plan.limit) {
+      out.num_rows = plan.limit;
+      for (auto& c : out.cols) { c.length = plan.limit; if (c.field.type == DType::Utf8 || c.field.type == DType::Binary) c.data_bytes = -1; }
+      std::vector<int> all;
+      for (size_t i = 0; i < out.cols.size(); ++i) all.push_back((int)i);
+      resolve_varlen_extents(out, all, stream);
+    }
+    return out;
   }
 
   out.cols.resize(plan.outputs.size());
