@@ -99,44 +99,40 @@ const char* vm_error_text(int e) {
 
 }  // namespace
 
-// ---- fast path: TMA-staged persistent kernel (filter_project_tma.cu) ------------------------------------
-size_t filter_project_tma_smem_bytes();
+// ---- fast path: filter_project_tma.cu ------------------------------------------------------------------
 int filter_project_tma_tile_rows();
-bool launch_filter_project_tma(int64_t n_rows, int n_fixed, const void* const* fixed_in, void* const* fixed_out, const int32_t* offsets_in,
-                               const uint8_t* data_in, int32_t* offsets_out, uint8_t* data_out, int cmp, int is_f64, uint64_t constant,
-                               unsigned long long* desc, unsigned int* ticket, long long* totals, cudaStream_t stream);
+int filter_project_tma_max_fixed_out();
+bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_out, const void* const* fixed_in, void* const* fixed_out,
+                               const int32_t* offsets_in, const uint8_t* data_in, int64_t data_bytes, int32_t* offsets_out, uint8_t* data_out,
+                               int cmp, int is_f64, uint64_t constant, unsigned long long* desc, unsigned int* ticket, long long* totals,
+                               cudaStream_t stream);
 
-// SELECT <≤2 fixed-width cols> [, <1 var-len col>] WHERE <fixed col> <cmp> <literal>, no NULLs in the used columns.
+// SELECT <fixed-width cols…> [, <1 var-len col>] WHERE <fixed col> <cmp> <literal>, no NULLs in the used columns.
 static bool try_fast_filter(const Plan& plan, Batch& in, Batch& out, cudaStream_t stream) {
   if (!plan.has_pred || !plan.simple.enabled || plan.outputs.empty()) return false;
   auto src_col = [&](int slot) -> Column& { return in.cols[plan.used_cols[slot]]; };
   for (size_t s = 0; s < plan.used_cols.size(); ++s) if (src_col((int)s).validity) return false;
-  int fixed_slots[2] = {plan.simple.slot, -1};
-  int n_fixed = 1, out_of_fixed[2] = {-1, -1}, varlen_out = -1;
+  const int max_fixed = filter_project_tma_max_fixed_out();
+  std::vector<int> fixed_outs;
+  int varlen_out = -1;
   for (size_t i = 0; i < plan.outputs.size(); ++i) {
     const OutputCol& oc = plan.outputs[i];
     if (oc.src.kind != ValueSource::PassThrough) return false;
     const DType t = src_col(oc.src.slot).field.type;
-    if (t == DType::Int64 || t == DType::Float64) {
-      int c = -1;
-      for (int k = 0; k < n_fixed; ++k) if (fixed_slots[k] == oc.src.slot) c = k;
-      if (c < 0) { if (n_fixed == 2) return false; c = n_fixed; fixed_slots[n_fixed++] = oc.src.slot; }
-      if (out_of_fixed[c] >= 0) return false;  // the same column projected twice: general path
-      out_of_fixed[c] = (int)i;
-    } else if (t == DType::Utf8 || t == DType::Binary) {
-      if (varlen_out >= 0) return false;
-      varlen_out = (int)i;
-    } else return false;
+    if (t == DType::Int64 || t == DType::Float64) { if ((int)fixed_outs.size() == max_fixed) return false; fixed_outs.push_back((int)i); }
+    else if (t == DType::Utf8 || t == DType::Binary) { if (varlen_out >= 0) return false; varlen_out = (int)i; }
+    else return false;
   }
   const int64_t n = in.num_rows;
-  const int tile_rows = filter_project_tma_tile_rows();
-  const int n_tiles = (int)ceil_div(n, tile_rows);
-  const void* fin[2] = {nullptr, nullptr};
-  void* fout[2] = {nullptr, nullptr};
-  BufferPtr fbuf[2], obuf, dbuf;
-  for (int c = 0; c < n_fixed; ++c) {
-    fin[c] = src_col(fixed_slots[c]).data;
-    if (out_of_fixed[c] >= 0) { fbuf[c] = device_alloc((size_t)n * 8 + 16); fout[c] = fbuf[c].get(); }
+  const int n_tiles = (int)ceil_div(n, filter_project_tma_tile_rows());
+  const void* fin[8] = {nullptr};
+  void* fout[8] = {nullptr};
+  std::vector<BufferPtr> fbuf(fixed_outs.size());
+  BufferPtr obuf, dbuf;
+  for (size_t c = 0; c < fixed_outs.size(); ++c) {
+    fin[c] = src_col(plan.outputs[fixed_outs[c]].src.slot).data;
+    fbuf[c] = device_alloc((size_t)n * 8 + 16);
+    fout[c] = fbuf[c].get();
   }
   const Column* vs = varlen_out >= 0 ? &src_col(plan.outputs[varlen_out].src.slot) : nullptr;
   if (vs) { obuf = device_alloc((size_t)(n + 1) * 4 + 16); dbuf = device_alloc((size_t)std::max<int64_t>(vs->data_bytes, 0) + 32); }
@@ -145,7 +141,8 @@ static bool try_fast_filter(const Plan& plan, Batch& in, Batch& out, cudaStream_
   BufferPtr scratch = device_alloc(scratch_bytes);
   ARK_CUDA(cudaMemsetAsync(scratch.get(), 0, scratch_bytes, stream));
   long long* totals = (long long*)((char*)scratch.get() + desc_bytes + 16);
-  if (!launch_filter_project_tma(n, n_fixed, fin, fout, vs ? vs->offsets : nullptr, vs ? vs->data : nullptr, vs ? (int32_t*)obuf.get() : nullptr,
+  if (!launch_filter_project_tma(n, src_col(plan.simple.slot).data, (int)fixed_outs.size(), fin, fout, vs ? vs->offsets : nullptr,
+                                 vs ? vs->data : nullptr, vs ? vs->data_bytes : 0, vs ? (int32_t*)obuf.get() : nullptr,
                                  vs ? (uint8_t*)dbuf.get() : nullptr, plan.simple.cmp, plan.simple.is_f64, plan.simple.constant,
                                  (unsigned long long*)scratch.get(), (unsigned int*)((char*)scratch.get() + desc_bytes), totals, stream))
     return false;
@@ -165,7 +162,8 @@ static bool try_fast_filter(const Plan& plan, Batch& in, Batch& out, cudaStream_
       c.offsets = (const int32_t*)obuf.get(); c.data = (const uint8_t*)dbuf.get(); c.data_bytes = bytes; c.first_offset = 0;
       c.owners = {obuf, dbuf};
     } else {
-      const int k = out_of_fixed[0] == (int)i ? 0 : 1;
+      size_t k = 0;
+      while (fixed_outs[k] != (int)i) ++k;
       c.data = (const uint8_t*)fbuf[k].get(); c.data_bytes = count * 8; c.owners = {fbuf[k]};
     }
   }

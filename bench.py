@@ -244,7 +244,7 @@ def run_b200(args):
     clocks = sampler.stop()
     lib.ark_kernel_timing_enable(0)
     kms, kn = C.c_double(), C.c_int64()
-    lib.ark_kernel_timing_get(b"filter_project_kernel", C.byref(kms), C.byref(kn))
+    lib.ark_kernel_timing_get(b"filter_project_tma_kernel", C.byref(kms), C.byref(kn))
     dev_ms = max_over_ranks(dev_ms_local)
     rows_total = args.steps * ROWS_PER_BATCH * world
     value = rows_total / (dev_ms / 1e3)
@@ -328,7 +328,7 @@ def run_b200(args):
                        "query": QUERY, "rows_per_step": ROWS_PER_BATCH, "resident_batches": n_resident,
                        "schema": "timestamp:Int64,value:Int64,sensor:Utf8(12B)", "selectivity": kept / ROWS_PER_BATCH,
                        "l2": "inputs larger than L2 (537 MB per batch, distinct batch each step)", "parallelism": f"{world} rank(s), row shards, no collective"},
-            "roofline": {"bound": "hbm", "kernel": "filter_project_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "filter_project_tma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": kn.value},
             "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": d2h_per_step,
