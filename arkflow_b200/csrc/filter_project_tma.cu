@@ -29,9 +29,8 @@ namespace {
 
 constexpr int TT = 1024;                    // rows per tile
 constexpr int T_THREADS = 256;
-constexpr int T_CHUNKS = TT / T_THREADS;    // 4 rows per thread, interleaved by 256 (warp = 32 consecutive rows)
 constexpr int T_WARPS = T_THREADS / 32;
-constexpr int T_MAX_FIXED_OUT = 6;
+constexpr int T_MAX_FIXED_OUT = 2;
 
 struct TmaParams {
   int64_t n_rows;
@@ -39,8 +38,10 @@ struct TmaParams {
   int32_t n_fixed_out;
   int32_t has_varlen;
   int32_t str_cap;                          // bytes of shared memory per string buffer (multiple of 16)
-  int32_t sp_cmp, sp_is_f64;
-  uint64_t sp_const;
+  int32_t sp_is_f64, negate;                // predicate as a range test on the (totalOrder) key
+  long long range_lo;
+  unsigned long long range_span;            // keep ⇔ ((u64)(key - range_lo) <= range_span) != negate
+  uint32_t fixed_is_pred;                   // bit c ⇒ fixed output c is the predicate column (already in registers)
   const unsigned long long* pred_in;        // predicate column
   const unsigned long long* fixed_in[T_MAX_FIXED_OUT];
   unsigned long long* fixed_out[T_MAX_FIXED_OUT];
@@ -94,13 +95,11 @@ __device__ __forceinline__ long long warp_sum(long long v) {
   return v;
 }
 
-__device__ long long lookback(unsigned long long* desc, int tile, int ch, long long agg, int lane) {
+// Decoupled look-back, resolve half: the tile's aggregate has already been published (tagged AGG,
+// or PREFIX for tile 0).  Returns the exclusive prefix and upgrades the descriptor to PREFIX.
+__device__ long long lookback_resolve(unsigned long long* desc, int tile, int ch, long long agg, int lane) {
+  if (tile == 0) return 0;
   unsigned long long* mine = desc + (size_t)tile * FP_CHANNELS + ch;
-  if (tile == 0) {
-    if (lane == 0) st_volatile_u64(mine, DESC_PREFIX | (unsigned long long)agg);
-    return 0;
-  }
-  if (lane == 0) st_volatile_u64(mine, DESC_AGG | (unsigned long long)agg);
   long long running = 0;
   int look = tile - 1;
   while (true) {
@@ -131,6 +130,8 @@ __device__ __forceinline__ void smem_copy(uint8_t* dst, const uint8_t* src, int 
   if (((d0 | s0 | (unsigned)len) & 3) == 0) {  // everything word aligned (fixed-length keys such as "temp_0000123")
     const unsigned* s = reinterpret_cast<const unsigned*>(src);
     unsigned* d = reinterpret_cast<unsigned*>(dst);
+    if (len == 12) { const unsigned a = s[0], b = s[1], c = s[2]; d[0] = a; d[1] = b; d[2] = c; return; }
+#pragma unroll 4
     for (int i = 0; i < (len >> 2); ++i) d[i] = s[i];
     return;
   }
@@ -157,146 +158,185 @@ __device__ __forceinline__ void smem_copy(uint8_t* dst, const uint8_t* src, int 
   for (; i < len; ++i) dst[i] = src[i];  // tail
 }
 
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+  return v;
+}
+
+// Thread t owns rows 4t..4t+3 of the tile (blocked): two 16-byte loads per 8-byte column, one warp scan
+// per quantity, thread-local ranks.
+template <int NF, bool VARLEN>
 __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const __grid_constant__ TmaParams P) {
   extern __shared__ __align__(16) uint8_t smem[];   // [in_bytes: str_cap + 32][out_bytes: str_cap + 32]
   __shared__ __align__(8) unsigned long long s_bar;
-  __shared__ int s_tile, s_str_base, s_str_staged;
-  __shared__ int s_cnt[T_CHUNKS * T_WARPS];
-  __shared__ int s_bytes[T_CHUNKS * T_WARPS];
+  __shared__ int s_str_base, s_str_staged;
+  __shared__ int s_cnt[T_WARPS], s_bytes[T_WARPS];
   __shared__ long long s_excl[2];
-  __shared__ int s_total[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned lt_mask = (1u << lane) - 1;
+  const int tile = blockIdx.x;   // tiles are claimed in launch order (as CUB's single-pass scans assume)
+  const int64_t row0 = (int64_t)tile * TT;
+  const int rows = (int)((P.n_rows - row0) < TT ? (P.n_rows - row0) : TT);
   uint8_t* in_bytes = smem;
   uint8_t* out_bytes = smem + P.str_cap + 32;
 
-  if (tid == 0) {
-    const int tile = (int)atomicAdd(P.ticket, 1u);
-    s_tile = tile;
-    int staged = 0, base = 0;
-    if (P.has_varlen) {
-      mbar_init(&s_bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      const int64_t row0 = (int64_t)tile * TT;
-      const int rows = (int)((P.n_rows - row0) < TT ? (P.n_rows - row0) : TT);
-      const int32_t o0 = P.offsets_in[row0], o1 = P.offsets_in[row0 + rows];
-      const uintptr_t a0 = reinterpret_cast<uintptr_t>(P.data_in + o0), a1 = reinterpret_cast<uintptr_t>(P.data_in + o1);
-      const uintptr_t lo = a0 & ~(uintptr_t)15, hi = (a1 + 15) & ~(uintptr_t)15;
-      base = o0 - (int32_t)(a0 - lo);
-      if (o1 > o0 && hi - lo <= (uintptr_t)P.str_cap) {  // staged ⇒ selected bytes ≤ window ≤ str_cap
-        staged = 1;
-        mbar_expect_tx(&s_bar, (unsigned)(hi - lo));
-        tma_load_1d(in_bytes, reinterpret_cast<const void*>(lo), (unsigned)(hi - lo), &s_bar);
-      }
+  if (VARLEN && tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int32_t o0 = P.offsets_in[row0], o1 = P.offsets_in[row0 + rows];
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(P.data_in + o0), a1 = reinterpret_cast<uintptr_t>(P.data_in + o1);
+    const uintptr_t lo = a0 & ~(uintptr_t)15, hi = (a1 + 15) & ~(uintptr_t)15;
+    int staged = 0;
+    if (o1 > o0 && hi - lo <= (uintptr_t)P.str_cap) {  // staged ⇒ selected bytes ≤ window ≤ str_cap
+      staged = 1;
+      mbar_expect_tx(&s_bar, (unsigned)(hi - lo));
+      tma_load_1d(in_bytes, reinterpret_cast<const void*>(lo), (unsigned)(hi - lo), &s_bar);
     }
-    s_str_base = base; s_str_staged = staged;
+    s_str_base = o0 - (int32_t)(a0 - lo); s_str_staged = staged;
   }
-  __syncthreads();
-  const int tile = s_tile;
-  const int64_t row0 = (int64_t)tile * TT;
-  const int rows = (int)((P.n_rows - row0) < TT ? (P.n_rows - row0) : TT);
 
-  // ---- A: predicate on registers, per-warp counts, selected string lengths ----
-  const long long kc = P.sp_is_f64 ? f64_total_key(P.sp_const) : (long long)P.sp_const;
+  // ---- A: loads (registers), predicate, thread-local and warp-level prefix sums ----
+  const int lr0 = 4 * tid;
+  const bool full = lr0 + 4 <= rows;
+  unsigned long long pv[4] = {0, 0, 0, 0};
+  int off[5] = {0, 0, 0, 0, 0};
+  {
+    const unsigned long long* src = P.pred_in + row0 + lr0;
+    if (full && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(pv[0]), "=l"(pv[1]) : "l"(src));
+      asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(pv[2]), "=l"(pv[3]) : "l"(src + 2));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (lr0 + j < rows) pv[j] = src[j];
+    }
+    if (VARLEN) {
+      const int32_t* os = P.offsets_in + row0 + lr0;
+      if (full && (reinterpret_cast<uintptr_t>(os) & 15) == 0) {
+        int4 o4;
+        asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(o4.x), "=r"(o4.y), "=r"(o4.z), "=r"(o4.w) : "l"(os));
+        off[0] = o4.x; off[1] = o4.y; off[2] = o4.z; off[3] = o4.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (lr0 + j <= rows) off[j] = os[j];
+      }
+      off[4] = __shfl_down_sync(0xffffffffu, off[0], 1);
+      if ((lane == 31 || lr0 + 4 >= rows) && lr0 + 4 <= rows) off[4] = os[4];
+    }
+  }
   unsigned flags = 0;
-  unsigned bal[T_CHUNKS];
-  unsigned long long pv[T_CHUNKS];
-  int off0[T_CHUNKS], slen[T_CHUNKS], bp[T_CHUNKS];
+  int cnt = 0, sel_bytes = 0;
 #pragma unroll
-  for (int k = 0; k < T_CHUNKS; ++k) {
-    const int lr = k * T_THREADS + tid;
-    const bool in_range = lr < rows;
-    pv[k] = in_range ? ld_stream_u64(P.pred_in + row0 + lr) : 0;
-    if (P.has_varlen) off0[k] = in_range ? P.offsets_in[row0 + lr] : 0;
+  for (int j = 0; j < 4; ++j) {
+    const long long key = P.sp_is_f64 ? f64_total_key(pv[j]) : (long long)pv[j];
+    bool f = (unsigned long long)(key - P.range_lo) <= P.range_span;
+    f = (f != (bool)P.negate) && (lr0 + j < rows);
+    flags |= (unsigned)f << j;
+    cnt += f;
+    if (VARLEN && f) sel_bytes += off[j + 1] - off[j];
   }
-#pragma unroll
-  for (int k = 0; k < T_CHUNKS; ++k) {
-    const int lr = k * T_THREADS + tid;
-    const bool in_range = lr < rows;
-    const bool f = in_range && cmp_i64(P.sp_cmp, P.sp_is_f64 ? f64_total_key(pv[k]) : (long long)pv[k], kc);
-    bal[k] = __ballot_sync(0xffffffffu, f);
-    flags |= (unsigned)f << k;
-    if (lane == 0) s_cnt[k * T_WARPS + warp] = __popc(bal[k]);
-    if (P.has_varlen) {
-      int next = __shfl_down_sync(0xffffffffu, off0[k], 1);
-      if (lane == 31 && in_range) next = P.offsets_in[row0 + lr + 1];
-      if (in_range && lr + 1 == rows) next = P.offsets_in[row0 + rows];
-      slen[k] = in_range ? next - off0[k] : 0;
-      int incl = f ? slen[k] : 0;
-      const int own = incl;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-      bp[k] = incl - own;
-      if (lane == 31) s_bytes[k * T_WARPS + warp] = incl;
-    }
-  }
+  const int cnt_incl = warp_incl_scan(cnt, lane);
+  int bytes_incl = 0;
+  if (VARLEN) bytes_incl = warp_incl_scan(sel_bytes, lane);
+  if (lane == 31) { s_cnt[warp] = cnt_incl; if (VARLEN) s_bytes[warp] = bytes_incl; }
   __syncthreads();
-  // ---- B: tile scan + decoupled look-back (warp 0) ----
-  if (warp == 0) {
-    {
-      const int c = s_cnt[lane];
-      int incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-      s_cnt[lane] = incl - c;
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      const long long ex = lookback(P.desc, tile, 0, total, lane);
-      if (lane == 0) { s_excl[0] = ex; s_total[0] = total; if (tile == P.n_tiles - 1) P.totals[0] = ex + total; }
-    }
-    if (P.has_varlen) {
-      const int c = s_bytes[lane];
-      int incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-      s_bytes[lane] = incl - c;
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      const long long ex = lookback(P.desc, tile, 1, total, lane);
-      if (lane == 0) { s_excl[1] = ex; s_total[1] = total; if (tile == P.n_tiles - 1) P.totals[1] = ex + total; }
-    }
-  }
-  __syncthreads();
-  const int tile_cnt = s_total[0];
-  const long long base_cnt = s_excl[0];
-  const int tb = P.has_varlen ? s_total[1] : 0;
-  const long long bb = P.has_varlen ? s_excl[1] : 0;
-  const int shift = (int)(bb & 15);
-  const bool str_fast = P.has_varlen && s_str_staged;
-  if (str_fast) mbar_wait(&s_bar, 0);  // the TMA window has landed (issued before phase A)
 
-  // ---- C: warp-contiguous stores of fixed columns and offsets; strings compacted in shared memory ----
+  // ---- B: 8-entry tile scan (every warp, redundantly); warp 0 publishes the tile aggregate at once ----
+  int w_cnt_excl, w_bytes_excl = 0, tile_cnt, tb = 0;
+  {
+    const int c = lane < T_WARPS ? s_cnt[lane] : 0;
+    int incl = c;
 #pragma unroll
-  for (int k = 0; k < T_CHUNKS; ++k) {
-    if (!((flags >> k) & 1)) continue;
-    const int lr = k * T_THREADS + tid;
-    const long long pos = base_cnt + s_cnt[k * T_WARPS + warp] + __popc(bal[k] & lt_mask);
-    for (int c = 0; c < P.n_fixed_out; ++c) {
-      const unsigned long long* src = P.fixed_in[c];
-      P.fixed_out[c][pos] = src == P.pred_in ? pv[k] : ld_stream_u64(src + row0 + lr);
-    }
-    if (P.has_varlen) {
-      const int lbp = s_bytes[k * T_WARPS + warp] + bp[k];
-      P.offsets_out[pos] = (int32_t)(bb + lbp);
-      if (str_fast) smem_copy(out_bytes + shift + lbp, in_bytes + (off0[k] - s_str_base), slen[k]);
-      else {  // long strings: straight from global to global
-        const uint8_t* src = P.data_in + off0[k];
-        uint8_t* dst = P.data_out + bb + lbp;
-        for (int i = 0; i < slen[k]; ++i) dst[i] = src[i];
-      }
+    for (int o = 1; o < T_WARPS; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    w_cnt_excl = __shfl_sync(0xffffffffu, incl - c, warp);
+    tile_cnt = __shfl_sync(0xffffffffu, incl, T_WARPS - 1);
+    if (VARLEN) {
+      const int b = lane < T_WARPS ? s_bytes[lane] : 0;
+      int bi = b;
+#pragma unroll
+      for (int o = 1; o < T_WARPS; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, bi, o); if (lane >= o) bi += t; }
+      w_bytes_excl = __shfl_sync(0xffffffffu, bi - b, warp);
+      tb = __shfl_sync(0xffffffffu, bi, T_WARPS - 1);
     }
   }
-  if (P.has_varlen) {
+  if (warp == 0 && lane == 0) {
+    const unsigned long long tag = tile == 0 ? DESC_PREFIX : DESC_AGG;
+    st_volatile_u64(P.desc + (size_t)tile * FP_CHANNELS, tag | (unsigned long long)tile_cnt);
+    if (VARLEN) st_volatile_u64(P.desc + (size_t)tile * FP_CHANNELS + 1, tag | (unsigned long long)tb);
+  }
+  // ---- C: compact the strings in shared memory at tile-local positions (overlaps the look-back) ----
+  const int my_cnt_excl = w_cnt_excl + cnt_incl - cnt;
+  int lpos[4];
+  bool str_fast = false;
+  if (VARLEN) {
+    int run = w_bytes_excl + bytes_incl - sel_bytes;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { lpos[j] = run; if ((flags >> j) & 1) run += off[j + 1] - off[j]; }
+    str_fast = s_str_staged;
+    if (str_fast) {
+      mbar_wait(&s_bar, 0);  // TMA window landed (issued before phase A)
+      const int base = s_str_base;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((flags >> j) & 1) smem_copy(out_bytes + lpos[j], in_bytes + (off[j] - base), off[j + 1] - off[j]);
+    }
+  }
+  // ---- D: decoupled look-back (warp 0) ----
+  if (warp == 0) {
+    const long long ex0 = lookback_resolve(P.desc, tile, 0, tile_cnt, lane);
+    long long ex1 = 0;
+    if (VARLEN) ex1 = lookback_resolve(P.desc, tile, 1, tb, lane);
+    if (lane == 0) {
+      s_excl[0] = ex0; s_excl[1] = ex1;
+      if (tile == P.n_tiles - 1) { P.totals[0] = ex0 + tile_cnt; P.totals[1] = ex1 + tb; }
+    }
+  }
+  __syncthreads();
+  const long long base_cnt = s_excl[0];
+  const long long bb = VARLEN ? s_excl[1] : 0;
+
+  // ---- E: stores ----
+  {
+    long long pos = base_cnt + my_cnt_excl;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!((flags >> j) & 1)) continue;
+#pragma unroll
+      for (int c = 0; c < NF; ++c)
+        P.fixed_out[c][pos] = ((P.fixed_is_pred >> c) & 1) ? pv[j] : ld_stream_u64(P.fixed_in[c] + row0 + lr0 + j);
+      if (VARLEN) P.offsets_out[pos] = (int32_t)(bb + lpos[j]);
+      ++pos;
+    }
+  }
+  if (VARLEN) {
     if (tile == P.n_tiles - 1 && tid == 0) P.offsets_out[base_cnt + tile_cnt] = (int32_t)(bb + tb);
     if (str_fast) {
-      __syncthreads();
-      uint8_t* gbase = P.data_out + (bb - shift);
-      const int total = shift + tb;
-      for (int p = tid * 16; p < total; p += T_THREADS * 16) {
-        if (p >= shift && p + 16 <= total) *reinterpret_cast<uint4*>(gbase + p) = *reinterpret_cast<const uint4*>(out_bytes + p);
+      // destination-aligned 16-byte stores; the shared-memory source is misaligned by d = (-bb) mod 16
+      uint8_t* gdst = P.data_out + bb;
+      const int head = (int)((16 - (bb & 15)) & 15) < tb ? (int)((16 - (bb & 15)) & 15) : tb;
+      if (tid < head) gdst[tid] = out_bytes[tid];
+      const int body = (tb - head) >> 4;
+      const unsigned* sw = reinterpret_cast<const unsigned*>(out_bytes + (head & ~3));
+      const unsigned sh = (head & 3) * 8;
+      for (int g = tid; g < body; g += T_THREADS) {
+        const unsigned* w = sw + g * 4;
+        uint4 v;
+        if (sh == 0) { v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3]; }
         else {
-          const int q0 = p > shift ? p : shift, q1 = (p + 16 < total) ? p + 16 : total;
-          for (int q = q0; q < q1; ++q) gbase[q] = out_bytes[q];
+          const unsigned a = w[0], b = w[1], c = w[2], d = w[3], e = w[4];
+          v.x = __funnelshift_r(a, b, sh); v.y = __funnelshift_r(b, c, sh); v.z = __funnelshift_r(c, d, sh); v.w = __funnelshift_r(d, e, sh);
         }
+        *reinterpret_cast<uint4*>(gdst + head + g * 16) = v;
+      }
+      const int done = head + body * 16;
+      if (tid < tb - done) gdst[done + tid] = out_bytes[done + tid];
+    } else {  // long strings: straight from global to global
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!((flags >> j) & 1)) continue;
+        const uint8_t* src = P.data_in + off[j];
+        uint8_t* dst = P.data_out + bb + lpos[j];
+        for (int i = 0; i < off[j + 1] - off[j]; ++i) dst[i] = src[i];
       }
     }
   }
@@ -312,16 +352,36 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
                                const int32_t* offsets_in, const uint8_t* data_in, int64_t data_bytes, int32_t* offsets_out, uint8_t* data_out,
                                int cmp, int is_f64, uint64_t constant, unsigned long long* desc, unsigned int* ticket, long long* totals,
                                cudaStream_t stream) {
+  (void)ticket;
   if (reinterpret_cast<uintptr_t>(pred_in) & 7) return false;
   if (data_out && (reinterpret_cast<uintptr_t>(data_out) & 15)) return false;
+  if (n_fixed_out > 2) return false;
   TmaParams P;
   memset(&P, 0, sizeof P);
   P.n_rows = n_rows; P.n_tiles = (int)ceil_div(n_rows, TT); P.n_fixed_out = n_fixed_out; P.has_varlen = offsets_in != nullptr;
-  P.sp_cmp = cmp; P.sp_is_f64 = is_f64; P.sp_const = constant;
+  P.sp_is_f64 = is_f64;
+  {  // comparison against a constant → range membership on the totally ordered int64 key
+    long long c = (long long)constant;
+    if (is_f64) c = c ^ (long long)(((unsigned long long)(c >> 63)) >> 1);  // f64 totalOrder key
+    const long long MIN = INT64_MIN, MAX = INT64_MAX;
+    long long lo = MIN, hi = MAX; int neg = 0;
+    switch (cmp) {
+      case CMP_EQ: lo = hi = c; break;
+      case CMP_NE: lo = hi = c; neg = 1; break;
+      case CMP_LT: if (c == MIN) neg = 1; else hi = c - 1; break;   // empty set = NOT(everything)
+      case CMP_LE: hi = c; break;
+      case CMP_GT: if (c == MAX) neg = 1; else lo = c + 1; break;
+      default: lo = c; break;  // GE
+    }
+    P.range_lo = lo; P.range_span = (unsigned long long)hi - (unsigned long long)lo; P.negate = neg;
+  }
   P.pred_in = (const unsigned long long*)pred_in;
-  for (int c = 0; c < n_fixed_out; ++c) { P.fixed_in[c] = (const unsigned long long*)fixed_in[c]; P.fixed_out[c] = (unsigned long long*)fixed_out[c]; }
+  for (int c = 0; c < n_fixed_out; ++c) {
+    P.fixed_in[c] = (const unsigned long long*)fixed_in[c]; P.fixed_out[c] = (unsigned long long*)fixed_out[c];
+    if (fixed_in[c] == pred_in) P.fixed_is_pred |= 1u << c;
+  }
   P.offsets_in = offsets_in; P.data_in = data_in; P.offsets_out = offsets_out; P.data_out = data_out;
-  P.desc = desc; P.ticket = ticket; P.totals = totals;
+  P.desc = desc; P.ticket = nullptr; P.totals = totals;
   // string staging sized from the batch's average string length (+25 %), 2 KB granules, 4..24 KB
   int cap = 0;
   if (P.has_varlen) {
@@ -331,13 +391,22 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
   }
   P.str_cap = cap;
   const size_t smem = P.has_varlen ? 2 * (size_t)(cap + 32) : 0;
-  static int configured_smem = -1;
-  if ((int)smem > configured_smem) {
-    ARK_CUDA(cudaFuncSetAttribute(filter_project_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (24 * 1024 + 32)));
-    configured_smem = 2 * (24 * 1024 + 32);
+  const int max_smem = 2 * (24 * 1024 + 32);
+  static bool configured = false;
+  if (!configured) {
+    ARK_CUDA(cudaFuncSetAttribute(filter_project_tma_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ARK_CUDA(cudaFuncSetAttribute(filter_project_tma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ARK_CUDA(cudaFuncSetAttribute(filter_project_tma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    configured = true;
   }
   KernelTimer t("filter_project_tma_kernel", stream);
-  filter_project_tma_kernel<<<P.n_tiles, T_THREADS, smem, stream>>>(P);
+  const bool v = P.has_varlen;
+  if (n_fixed_out == 0 && v) filter_project_tma_kernel<0, true><<<P.n_tiles, T_THREADS, smem, stream>>>(P);
+  else if (n_fixed_out == 1 && v) filter_project_tma_kernel<1, true><<<P.n_tiles, T_THREADS, smem, stream>>>(P);
+  else if (n_fixed_out == 2 && v) filter_project_tma_kernel<2, true><<<P.n_tiles, T_THREADS, smem, stream>>>(P);
+  else if (n_fixed_out == 1) filter_project_tma_kernel<1, false><<<P.n_tiles, T_THREADS, 0, stream>>>(P);
+  else if (n_fixed_out == 2) filter_project_tma_kernel<2, false><<<P.n_tiles, T_THREADS, 0, stream>>>(P);
+  else return false;
   return true;
 }
 
