@@ -59,6 +59,41 @@ class DeviceColumn:
         self.null_count, self.nullable = null_count, nullable
 
 
+class _LazyBytes:
+    """The data buffer of a var-len column adopted from C: its size is offsets[n], which lives on the
+    device; reading it costs a synchronising copy, so it is deferred until somebody touches the bytes."""
+
+    def __init__(self, ptr, offsets, n, owner):
+        self._ptr, self._offsets, self._n, self._owner, self._t = ptr, offsets, n, owner, None
+
+    def tensor(self):
+        import torch
+
+        if self._t is None:
+            nbytes = int(self._offsets[-1].item()) if self._n > 0 else 0
+            if not self._ptr or nbytes <= 0:
+                self._t = torch.empty(0, dtype=torch.uint8, device="cuda")
+            else:
+                self._t = torch.as_tensor(_CudaPtr(self._ptr, nbytes, "|u1", 1, self._owner), device="cuda")
+        return self._t
+
+    def data_ptr(self):
+        return self._ptr or 0
+
+    def numel(self):
+        return self.tensor().numel()
+
+    def cpu(self):
+        return self.tensor().cpu()
+
+    def __getitem__(self, item):
+        return self.tensor()[item]
+
+    @property
+    def device(self):
+        return self._offsets.device
+
+
 class _CudaPtr:
     """Zero-copy view of foreign device memory for torch.as_tensor (via __cuda_array_interface__)."""
 
@@ -132,7 +167,7 @@ class DeviceBatch:
                     (c.offsets if c.dtype in ("utf8", "binary") else c.data).data_ptr()
                     if (c.offsets if c.dtype in ("utf8", "binary") else c.data) is not None else None]
             if c.dtype in ("utf8", "binary"):
-                bufs.append(c.data.data_ptr() if c.data is not None and c.data.numel() else None)
+                bufs.append((c.data.data_ptr() or None) if c.data is not None else None)
             barr = (C.c_void_p * max(len(bufs), 1))(*bufs)
             a = child_arrs[i]
             a.length, a.null_count, a.offset = c.length, (c.null_count if c.validity is not None else 0), 0
@@ -196,8 +231,8 @@ class DeviceBatch:
                 data = view(1, (n + 7) // 8, "|u1", 1, torch.uint8)
             else:
                 offsets = view(1, (n + 1) * 4, "<i4", 4, torch.int32)
-                nbytes = int(offsets[-1].item()) if n > 0 else 0
-                data = view(2, nbytes, "|u1", 1, torch.uint8)
+                ptr2 = a.buffers[2] if a.n_buffers > 2 else None
+                data = _LazyBytes(ptr2, offsets, n, owner)  # resolved on first use (needs one device read)
             cols.append(DeviceColumn(s.name.decode(), dtype, n, data, offsets, validity,
                                      null_count=a.null_count, nullable=bool(s.flags & 2)))
         return DeviceBatch(cols, dev.array.length, owner=owner)
