@@ -283,8 +283,9 @@ def run_b200(args):
             else:
                 to = torch.empty(c.length + 1, dtype=torch.int32, pin_memory=True)
                 to.copy_(c.offsets)
-                td = torch.empty(c.data.numel(), dtype=torch.uint8, pin_memory=True)
-                td.copy_(c.data)
+                dsrc = c.data.tensor() if hasattr(c.data, "tensor") else c.data
+                td = torch.empty(dsrc.numel(), dtype=torch.uint8, pin_memory=True)
+                td.copy_(dsrc)
                 keep += [to, td]
                 arrays.append(pa.Array.from_buffers(pa.utf8(), c.length, [None, pa.foreign_buffer(to.data_ptr(), (c.length + 1) * 4, base=to),
                                                                           pa.foreign_buffer(td.data_ptr(), td.numel(), base=td)]))
