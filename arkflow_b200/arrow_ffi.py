@@ -145,68 +145,101 @@ class DeviceBatch:
     """A RecordBatch resident in HBM (list of DeviceColumn)."""
 
     def __init__(self, columns: list[DeviceColumn], num_rows: int, owner=None):
-        self.columns, self.num_rows, self._owner = columns, int(num_rows), owner
+        self._columns, self.num_rows, self._owner = columns, int(num_rows), owner
 
     # --- Python → C (we own the memory; the release callback just drops our references) ---
     def export(self):
+        """(ArrowDeviceArray, ArrowSchema) for one C-ABI call.  The struct tree is built once per batch
+        and re-armed on every export (the callee's release only drops our keep-alive tokens)."""
         import torch
 
-        keep: list = [self]
-        n = len(self.columns)
-        dev = L.ArrowDeviceArray()
-        sch = L.ArrowSchema()
-        child_arrs = (L.ArrowArray * n)()
-        child_ptrs = (C.POINTER(L.ArrowArray) * n)()
-        child_schs = (L.ArrowSchema * n)()
-        child_sptrs = (C.POINTER(L.ArrowSchema) * n)()
-        for i, c in enumerate(self.columns):
-            if c.dtype == "null":
-                bufs = []
-            else:
-              bufs = [c.validity.data_ptr() if c.validity is not None else None,
-                    (c.offsets if c.dtype in ("utf8", "binary") else c.data).data_ptr()
-                    if (c.offsets if c.dtype in ("utf8", "binary") else c.data) is not None else None]
-            if c.dtype in ("utf8", "binary"):
-                bufs.append((c.data.data_ptr() or None) if c.data is not None else None)
-            barr = (C.c_void_p * max(len(bufs), 1))(*bufs)
-            a = child_arrs[i]
-            a.length, a.null_count, a.offset = c.length, (c.null_count if c.validity is not None else 0), 0
-            a.n_buffers, a.n_children = len(bufs), 0
-            a.buffers = C.cast(barr, C.POINTER(C.c_void_p))
-            a.release = C.cast(_REL_ARR, C.c_void_p)
-            a.private_data = _token((barr, c))
-            child_ptrs[i] = C.pointer(a)
-            s = child_schs[i]
-            nm = c.name.encode()
-            s.format, s.name, s.metadata = _FMT[c.dtype], nm, None
-            s.flags = 2 if c.nullable else 0
-            s.n_children = 0
-            s.release = C.cast(_REL_SCH, C.c_void_p)
-            s.private_data = _token((nm,))
-            child_sptrs[i] = C.pointer(s)
-        top_bufs = (C.c_void_p * 1)(None)
-        dev.array.length, dev.array.null_count, dev.array.offset = self.num_rows, 0, 0
-        dev.array.n_buffers, dev.array.n_children = 1, n
-        dev.array.buffers = C.cast(top_bufs, C.POINTER(C.c_void_p))
-        dev.array.children = C.cast(child_ptrs, C.POINTER(C.POINTER(L.ArrowArray)))
-        dev.array.release = C.cast(_REL_ARR, C.c_void_p)
-        dev.array.private_data = _token((top_bufs, child_arrs, child_ptrs, keep))
-        dev.device_id = torch.cuda.current_device()
-        dev.device_type = L.ARROW_DEVICE_CUDA
-        dev.sync_event = None
-        sch.format, sch.name, sch.metadata, sch.flags = b"+s", b"", None, 0
-        sch.n_children = n
-        sch.children = C.cast(child_sptrs, C.POINTER(C.POINTER(L.ArrowSchema)))
-        sch.release = C.cast(_REL_SCH, C.c_void_p)
-        sch.private_data = _token((child_schs, child_sptrs))
+        cache = getattr(self, "_export_cache", None)
+        if cache is None:
+            n = len(self.columns)
+            dev = L.ArrowDeviceArray()
+            sch = L.ArrowSchema()
+            child_arrs = (L.ArrowArray * max(n, 1))()
+            child_ptrs = (C.POINTER(L.ArrowArray) * max(n, 1))()
+            child_schs = (L.ArrowSchema * max(n, 1))()
+            child_sptrs = (C.POINTER(L.ArrowSchema) * max(n, 1))()
+            keep = [self]
+            for i, c in enumerate(self.columns):
+                if c.dtype == "null":
+                    bufs = []
+                else:
+                    first = c.offsets if c.dtype in ("utf8", "binary") else c.data
+                    bufs = [c.validity.data_ptr() if c.validity is not None else None,
+                            first.data_ptr() if first is not None else None]
+                    if c.dtype in ("utf8", "binary"):
+                        bufs.append((c.data.data_ptr() or None) if c.data is not None else None)
+                barr = (C.c_void_p * max(len(bufs), 1))(*bufs)
+                a = child_arrs[i]
+                a.length, a.null_count, a.offset = c.length, (c.null_count if c.validity is not None else 0), 0
+                a.n_buffers, a.n_children = len(bufs), 0
+                a.buffers = C.cast(barr, C.POINTER(C.c_void_p))
+                child_ptrs[i] = C.pointer(a)
+                s = child_schs[i]
+                nm = c.name.encode()
+                s.format, s.name, s.metadata = _FMT[c.dtype], nm, None
+                s.flags = 2 if c.nullable else 0
+                s.n_children = 0
+                child_sptrs[i] = C.pointer(s)
+                keep.append((barr, nm, c))
+            top_bufs = (C.c_void_p * 1)(None)
+            dev.array.length, dev.array.null_count, dev.array.offset = self.num_rows, 0, 0
+            dev.array.n_buffers, dev.array.n_children = 1, n
+            dev.array.buffers = C.cast(top_bufs, C.POINTER(C.c_void_p))
+            dev.array.children = C.cast(child_ptrs, C.POINTER(C.POINTER(L.ArrowArray)))
+            dev.device_id = torch.cuda.current_device()
+            dev.device_type = L.ARROW_DEVICE_CUDA
+            dev.sync_event = None
+            sch.format, sch.name, sch.metadata, sch.flags = b"+s", b"", None, 0
+            sch.n_children = n
+            sch.children = C.cast(child_sptrs, C.POINTER(C.POINTER(L.ArrowSchema)))
+            cache = (dev, sch, child_arrs, child_schs, (top_bufs, child_ptrs, child_sptrs, keep), n)
+            self._export_cache = cache
+        dev, sch, child_arrs, child_schs, keep, n = cache
+        if dev.array.release or sch.release:
+            # a previous export is still armed (concurrent use of one batch): build a private copy
+            clone = DeviceBatch(self.columns, self.num_rows, self._owner)
+            return clone.export()
+        rel_a, rel_s = C.cast(_REL_ARR, C.c_void_p), C.cast(_REL_SCH, C.c_void_p)
+        for i in range(n):
+            child_arrs[i].release = rel_a
+            child_arrs[i].private_data = None
+            child_schs[i].release = rel_s
+            child_schs[i].private_data = None
+        dev.array.release = rel_a
+        dev.array.private_data = _token(cache)
+        sch.release = rel_s
+        sch.private_data = _token(cache)
         return dev, sch
 
     # --- C → Python (the library owns the memory; we hold the struct and release it on close) ---
     @staticmethod
     def adopt(dev: L.ArrowDeviceArray, sch: L.ArrowSchema) -> "DeviceBatch":
+        """Wrap a callee-allocated result.  Columns (torch views of the device buffers) are built lazily."""
+        b = DeviceBatch.__new__(DeviceBatch)
+        b.num_rows = dev.array.length
+        b._owner = _CResult(dev, sch)
+        b._columns = None
+        return b
+
+    @property
+    def columns(self):
+        if self._columns is None:
+            self._columns = self._materialise()
+        return self._columns
+
+    @columns.setter
+    def columns(self, v):
+        self._columns = v
+
+    def _materialise(self):
         import torch
 
-        owner = _CResult(dev, sch)
+        owner = self._owner
+        dev, sch = owner.dev, owner.sch
         cols = []
         for i in range(dev.array.n_children):
             a = dev.array.children[i].contents
@@ -235,7 +268,7 @@ class DeviceBatch:
                 data = _LazyBytes(ptr2, offsets, n, owner)  # resolved on first use (needs one device read)
             cols.append(DeviceColumn(s.name.decode(), dtype, n, data, offsets, validity,
                                      null_count=a.null_count, nullable=bool(s.flags & 2)))
-        return DeviceBatch(cols, dev.array.length, owner=owner)
+        return cols
 
     def to_arrow(self) -> pa.RecordBatch:
         """Copy to host as a pyarrow RecordBatch (tests / debugging)."""

@@ -307,13 +307,37 @@ Batch import_device(const ArrowDeviceArray* darr, const ArrowSchema* schema, con
       case DType::Utf8: case DType::Binary:
         c.offsets = (const int32_t*)a->buffers[1] + off;
         c.data = (const uint8_t*)a->buffers[2];
-        c.data_bytes = -1;  // unknown until resolve_varlen_extents()
+        c.data_bytes = -1;  // unknown until resolve_varlen_extents(); most paths only need an upper bound
+        c.data_bound = a->buffers[2] ? std::min<int64_t>(device_alloc_remaining(a->buffers[2]), 2147483647ll) : 0;
         break;
       default: break;
     }
     b.cols.push_back(std::move(c));
   }
   return b;
+}
+
+int64_t device_alloc_remaining(const void* p) {
+  typedef int (*fn_t)(unsigned long long*, size_t*, unsigned long long);
+  static fn_t fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      f = nullptr;
+    }
+    return (fn_t)f;
+  }();
+  if (!fn || !p) return -1;
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, (unsigned long long)(uintptr_t)p) != 0) return -1;
+  return (int64_t)(base + size - (unsigned long long)(uintptr_t)p);
+}
+
+int64_t varlen_bytes_bound(const Column& c) {
+  if (c.data_bytes >= 0) return c.data_bytes;
+  return c.data_bound;
 }
 
 // Fetch offsets[0] / offsets[n] of device-resident var-len columns whose extent is still unknown.
@@ -352,6 +376,7 @@ void resolve_varlen_extents(Batch& b, const std::vector<int>& col_idx, cudaStrea
 }
 
 // ---- export ---------------------------------------------------------------------------------------------
+void resolve_varlen_extents(Batch& b, const std::vector<int>& col_idx, cudaStream_t stream);
 namespace {
 
 struct SchemaPriv {
@@ -436,7 +461,15 @@ struct ExportCol {
   std::vector<BufferPtr> owners;
 };
 
-static ExportCol normalise_for_export(const Column& c, cudaStream_t stream) {
+static ExportCol normalise_for_export(const Column& c_in, bool to_host, cudaStream_t stream) {
+  Column c = c_in;
+  if (to_host && c.present && (c.field.type == DType::Utf8 || c.field.type == DType::Binary) && c.data_bytes < 0) {
+    Batch tmp;  // the extent is needed to size the D2H copy
+    tmp.cols.push_back(c);
+    tmp.num_rows = c.length;
+    resolve_varlen_extents(tmp, {0}, stream);
+    c = tmp.cols[0];
+  }
   ExportCol e;
   e.owners = c.owners;
   int64_t n = c.length;
@@ -464,7 +497,12 @@ static ExportCol normalise_for_export(const Column& c, cudaStream_t stream) {
     case DType::Utf8: case DType::Binary: {
       e.n_buffers = 3;
       e.buf1_bytes = (n + 1) * 4;
-      if (c.data_bytes < 0) fail(ARK_ERR_PROCESS, "internal: var-len extent unresolved at export");
+      if (!to_host) {  // device export: Arrow does not require offsets[0] == 0; hand the buffers over as they are
+        if (c.offsets) e.buf1 = c.offsets;
+        else { BufferPtr o = device_alloc(4); ARK_CUDA(cudaMemsetAsync(o.get(), 0, 4, stream)); e.buf1 = o.get(); e.owners.push_back(o); }
+        e.buf2 = c.data; e.buf2_bytes = std::max<int64_t>(c.data_bytes, 0);
+        break;
+      }
       if (c.first_offset != 0 && c.offsets) {
         BufferPtr o = device_alloc((size_t)e.buf1_bytes);
         KernelTimer t("rebase_offsets_kernel", stream);
@@ -536,7 +574,7 @@ static void build_struct_array(const Batch& b, std::vector<ExportCol>& cols, boo
 
 void export_host(const Batch& b, cudaStream_t stream, ArrowArray* out, ArrowSchema* out_schema, int64_t* d2h_bytes) {
   std::vector<ExportCol> cols;
-  for (auto& c : b.cols) cols.push_back(normalise_for_export(c, stream));
+  for (auto& c : b.cols) cols.push_back(normalise_for_export(c, true, stream));
   build_struct_array(b, cols, true, stream, out, d2h_bytes);
   ARK_CUDA(cudaStreamSynchronize(stream));
   export_schema(b, out_schema);
@@ -545,7 +583,7 @@ void export_host(const Batch& b, cudaStream_t stream, ArrowArray* out, ArrowSche
 void export_device(const Batch& b, ArrowDeviceArray* out, ArrowSchema* out_schema) {
   StreamLease lease;
   std::vector<ExportCol> cols;
-  for (auto& c : b.cols) cols.push_back(normalise_for_export(c, lease.s));
+  for (auto& c : b.cols) cols.push_back(normalise_for_export(c, false, lease.s));
   memset(out, 0, sizeof(*out));
   build_struct_array(b, cols, false, lease.s, &out->array, nullptr);
   ARK_CUDA(cudaStreamSynchronize(lease.s));

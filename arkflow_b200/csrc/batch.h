@@ -76,6 +76,7 @@ struct Column {
   int32_t data_bit0 = 0;              // Boolean
   int64_t data_bytes = 0;             // var-len: bytes referenced (offsets[n]-offsets[0]); fixed: n*width
   int64_t first_offset = 0;           // var-len: offsets[0] value (0 for batches we produced)
+  int64_t data_bound = -1;            // var-len, extent unknown: upper bound on offsets[n] (end of the allocation), or -1
   std::vector<BufferPtr> owners;      // keep-alive for everything referenced above
   bool present = true;                // false ⇒ column was not imported (projection push-down)
 
@@ -120,5 +121,11 @@ void export_device(const Batch& b, ArrowDeviceArray* out, ArrowSchema* out_schem
 
 // Moves an ArrowArray into shared ownership: the returned pointer releases it when dropped.
 BufferPtr adopt_array(ArrowArray* arr);
+
+// Bytes from p to the end of the device allocation that contains it (driver cuMemGetAddressRange), or -1.
+int64_t device_alloc_remaining(const void* p);
+// Upper bound on the bytes a var-len column references: exact when known, else the allocation bound
+// (clamped to the 2 GiB an int32-offset column can address); -1 when neither is available.
+int64_t varlen_bytes_bound(const Column& c);
 
 }  // namespace ark

@@ -102,6 +102,7 @@ const char* vm_error_text(int e) {
 // ---- fast path: filter_project_tma.cu ------------------------------------------------------------------
 int filter_project_tma_tile_rows();
 int filter_project_tma_max_fixed_out();
+void filter_project_tma_note_avg_len(double avg);
 bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_out, const void* const* fixed_in, void* const* fixed_out,
                                const int32_t* offsets_in, const uint8_t* data_in, int64_t data_bytes, int32_t* offsets_out, uint8_t* data_out,
                                int cmp, int is_f64, uint64_t constant, unsigned long long* desc, unsigned int* ticket, long long* totals,
@@ -135,14 +136,14 @@ static bool try_fast_filter(const Plan& plan, Batch& in, Batch& out, cudaStream_
     fout[c] = fbuf[c].get();
   }
   const Column* vs = varlen_out >= 0 ? &src_col(plan.outputs[varlen_out].src.slot) : nullptr;
-  if (vs) { obuf = device_alloc((size_t)(n + 1) * 4 + 16); dbuf = device_alloc((size_t)std::max<int64_t>(vs->data_bytes, 0) + 32); }
+  if (vs) { obuf = device_alloc((size_t)(n + 1) * 4 + 16); dbuf = device_alloc((size_t)std::max<int64_t>(varlen_bytes_bound(*vs), 0) + 32); }
   const size_t desc_bytes = (size_t)n_tiles * FP_CHANNELS * 8;
   const size_t scratch_bytes = round_up((int64_t)desc_bytes + 64 + FP_CHANNELS * 8, 256);
   BufferPtr scratch = device_alloc(scratch_bytes);
   ARK_CUDA(cudaMemsetAsync(scratch.get(), 0, scratch_bytes, stream));
   long long* totals = (long long*)((char*)scratch.get() + desc_bytes + 16);
   if (!launch_filter_project_tma(n, src_col(plan.simple.slot).data, (int)fixed_outs.size(), fin, fout, vs ? vs->offsets : nullptr,
-                                 vs ? vs->data : nullptr, vs ? vs->data_bytes : 0, vs ? (int32_t*)obuf.get() : nullptr,
+                                 vs ? vs->data : nullptr, vs ? vs->data_bytes : 0 /* -1 = unknown */, vs ? (int32_t*)obuf.get() : nullptr,
                                  vs ? (uint8_t*)dbuf.get() : nullptr, plan.simple.cmp, plan.simple.is_f64, plan.simple.constant,
                                  (unsigned long long*)scratch.get(), (unsigned int*)((char*)scratch.get() + desc_bytes), totals, stream))
     return false;
@@ -151,6 +152,7 @@ static bool try_fast_filter(const Plan& plan, Batch& in, Batch& out, cudaStream_
   ARK_CUDA(cudaMemcpyAsync(host_res.get(), totals, 16, cudaMemcpyDeviceToHost, stream));
   ARK_CUDA(cudaStreamSynchronize(stream));
   const int64_t count = ((const int64_t*)host_res.get())[0], bytes = ((const int64_t*)host_res.get())[1];
+  if (vs && count > 0) filter_project_tma_note_avg_len((double)bytes / (double)count);
   out.cols.resize(plan.outputs.size());
   out.num_rows = count;
   for (size_t i = 0; i < plan.outputs.size(); ++i) {
@@ -177,19 +179,19 @@ Batch run_filter_project(const Plan& plan, Batch& in, cudaStream_t stream) {
   auto src_col = [&](int slot) -> Column& { return in.cols[plan.used_cols[slot]]; };
 
   if (plan.identity) {  // SELECT * FROM flow: the batch itself (zero copy)
-    std::vector<int> varlen;
-    for (size_t i = 0; i < in.cols.size(); ++i) varlen.push_back((int)i);
-    resolve_varlen_extents(in, varlen, stream);
     out.cols = in.cols;
     out.num_rows = n;
     return out;
   }
 
-  {
-    std::vector<int> varlen;
+  {  // outputs are allocated worst-case: an upper bound on each var-len source is enough
+    std::vector<int> unknown;
     for (auto& oc : plan.outputs)
-      if (oc.src.kind == ValueSource::PassThrough) varlen.push_back(plan.used_cols[oc.src.slot]);
-    resolve_varlen_extents(in, varlen, stream);
+      if (oc.src.kind == ValueSource::PassThrough) {
+        const Column& c = in.cols[plan.used_cols[oc.src.slot]];
+        if ((c.field.type == DType::Utf8 || c.field.type == DType::Binary) && varlen_bytes_bound(c) < 0) unknown.push_back(plan.used_cols[oc.src.slot]);
+      }
+    if (!unknown.empty()) resolve_varlen_extents(in, unknown, stream);
   }
 
   if (try_fast_filter(plan, in, out, stream)) {
@@ -261,7 +263,7 @@ Batch run_filter_project(const Plan& plan, Batch& in, cudaStream_t stream) {
           fo.kind = FP_OUT_VARLEN; fo.slot = oc.src.slot; fo.varlen_idx = P.n_varlen;
           P.varlen_slot[P.n_varlen++] = oc.src.slot;
           po.offsets = device_alloc((size_t)(n + 1) * 4);
-          po.data = device_alloc((size_t)std::max<int64_t>(s->data_bytes, 0) + 16);
+          po.data = device_alloc((size_t)std::max<int64_t>(varlen_bytes_bound(*s), 0) + 16);
           fo.out_offsets = (int32_t*)po.offsets.get();
         } else if (oc.src.type == DType::Bool) {
           fo.kind = FP_OUT_BOOL; fo.slot = oc.src.slot; po.is_bool = true; po.data = device_alloc((size_t)n);

@@ -19,6 +19,8 @@
 // only 2 tiles per SM were in flight and the look-back latency serialised each CTA.)
 // Bulk copies only touch 16-byte blocks that contain at least one valid byte of the source buffer,
 // so they never reach into an unmapped page.
+#include <atomic>
+
 #include "batch.h"
 #include "filter_project.cuh"
 #include "vm.cuh"
@@ -344,6 +346,8 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
 
 }  // namespace
 
+static std::atomic<double> g_avg_len_hint{12.8};
+void filter_project_tma_note_avg_len(double avg) { if (avg > 0) g_avg_len_hint.store(avg); }
 int filter_project_tma_tile_rows() { return TT; }
 int filter_project_tma_max_fixed_out() { return T_MAX_FIXED_OUT; }
 
@@ -385,7 +389,8 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
   // string staging sized from the batch's average string length (+25 %), 2 KB granules, 4..24 KB
   int cap = 0;
   if (P.has_varlen) {
-    const double avg = n_rows > 0 ? (double)data_bytes / (double)n_rows : 0.0;
+    // exact when the extent is known; otherwise the average selected-string length of the previous launch
+    double avg = n_rows > 0 && data_bytes >= 0 ? (double)data_bytes / (double)n_rows : g_avg_len_hint.load();
     cap = (int)round_up((int64_t)(avg * TT * 1.25) + 64, 2048);
     cap = std::max(4096, std::min(cap, 24 * 1024));
   }

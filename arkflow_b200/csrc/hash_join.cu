@@ -217,9 +217,6 @@ Batch run_join(const Plan& plan, Batch& left, Batch& right, cudaStream_t stream)
   Column& lk = left.cols[plan.left_key];
   Column& rk = right.cols[plan.right_key];
   const int key_kind = key_kind_of(lk.field.type);
-  // every projected var-len column needs its extent for the gathers
-  { std::vector<int> a, b; for (size_t i = 0; i < left.cols.size(); ++i) a.push_back((int)i); for (size_t i = 0; i < right.cols.size(); ++i) b.push_back((int)i);
-    resolve_varlen_extents(left, a, stream); resolve_varlen_extents(right, b, stream); }
   const bool build_left = left.num_rows <= right.num_rows;
   Batch& B = build_left ? left : right;
   Batch& Pb = build_left ? right : left;
@@ -283,9 +280,6 @@ Batch hash_partition(Batch& in, const std::string& key_column, int n_parts, std:
   if (ki < 0) fail(ARK_ERR_PROCESS, "Schema error: No field named " + key_column + ".");
   const int64_t n = in.num_rows;
   if (n >= (1ll << 32) - 1) fail(ARK_ERR_UNSUPPORTED, "partition input with 2^32 or more rows");
-  std::vector<int> all;
-  for (size_t i = 0; i < in.cols.size(); ++i) all.push_back((int)i);
-  resolve_varlen_extents(in, all, stream);
   const int key_kind = key_kind_of(in.cols[ki].field.type);
   BufferPtr part = device_alloc((size_t)std::max<int64_t>(n, 1)), idx = device_alloc((size_t)std::max<int64_t>(n, 1) * 4);
   BufferPtr ctl = device_alloc(256), hctl = pinned_alloc(256);
