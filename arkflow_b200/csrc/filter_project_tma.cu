@@ -97,33 +97,53 @@ __device__ __forceinline__ long long warp_sum(long long v) {
   return v;
 }
 
-// Decoupled look-back, resolve half: the tile's aggregate has already been published (tagged AGG,
-// or PREFIX for tile 0).  Returns the exclusive prefix and upgrades the descriptor to PREFIX.
-__device__ long long lookback_resolve(unsigned long long* desc, int tile, int ch, long long agg, int lane) {
-  if (tile == 0) return 0;
-  unsigned long long* mine = desc + (size_t)tile * FP_CHANNELS + ch;
-  long long running = 0;
-  int look = tile - 1;
-  while (true) {
-    const int idx = look - lane;
-    unsigned long long d = DESC_PREFIX;
-    if (idx >= 0) {
-      do { d = ld_volatile_u64(desc + (size_t)idx * FP_CHANNELS + ch); } while ((d >> 62) == 0);
+// Tile descriptor: [status:2 | rows:31 | bytes:31] in ONE 64-bit word, so both running sums travel (and
+// change status) atomically.  A batch on this path has < 2^31 rows and < 2^31 string bytes.
+__device__ __forceinline__ unsigned long long desc_pack(unsigned long long status, long long cnt, long long bytes) {
+  return status | ((unsigned long long)cnt << 31) | (unsigned long long)bytes;
+}
+constexpr unsigned long long DESC_FIELD = (1ull << 31) - 1;
+constexpr int LB_WINDOWS = 8;  // 8 × 32 predecessor tiles inspected per look-back round
+
+// Decoupled look-back, resolve half (warp 0).  The tile's aggregate is already published.  A wave of
+// ~900 CTAs starts together, so the nearest tile holding an inclusive prefix can be hundreds of tiles
+// back: each lane fetches LB_WINDOWS descriptors at once (independent loads, one L2 round trip) and
+// the windows are then folded nearest-first.  Returns the exclusive (rows, bytes) prefix.
+__device__ void lookback_resolve(unsigned long long* desc, int tile, long long agg_cnt, long long agg_bytes, int lane,
+                                 long long* ex_cnt, long long* ex_bytes) {
+  long long run_c = 0, run_b = 0;
+  if (tile > 0) {
+    int look = tile - 1;
+    bool done = false;
+    while (!done) {
+      unsigned long long d[LB_WINDOWS];
+#pragma unroll
+      for (int w = 0; w < LB_WINDOWS; ++w) {
+        const int idx = look - w * 32 - lane;
+        d[w] = idx >= 0 ? ld_volatile_u64(desc + idx) : DESC_PREFIX;  // virtual tile -1: inclusive prefix 0
+      }
+#pragma unroll
+      for (int w = 0; w < LB_WINDOWS; ++w) {
+        if (done) break;
+        const int idx = look - w * 32 - lane;
+        while (__any_sync(0xffffffffu, (d[w] >> 62) == 0)) {  // a predecessor has not published yet
+          if ((d[w] >> 62) == 0) d[w] = ld_volatile_u64(desc + idx);
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, (d[w] >> 62) == 2);
+        long long c = (long long)((d[w] >> 31) & DESC_FIELD), b = (long long)(d[w] & DESC_FIELD);
+        if (pm) {
+          const int first = __ffs(pm) - 1;
+          if (lane > first) { c = 0; b = 0; }
+          done = true;
+        }
+        run_c += warp_sum(c);
+        run_b += warp_sum(b);
+      }
+      look -= LB_WINDOWS * 32;
     }
-    __syncwarp();
-    const unsigned pm = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-    long long val = (long long)(d & DESC_MASK);
-    if (pm) {
-      const int first = __ffs(pm) - 1;
-      if (lane > first) val = 0;
-      running += warp_sum(val);
-      break;
-    }
-    running += warp_sum(val);
-    look -= 32;
+    if (lane == 0) st_volatile_u64(desc + tile, desc_pack(DESC_PREFIX, run_c + agg_cnt, run_b + agg_bytes));
   }
-  if (lane == 0) st_volatile_u64(mine, DESC_PREFIX | (unsigned long long)(running + agg));
-  return running;
+  *ex_cnt = run_c; *ex_bytes = run_b;
 }
 
 // copy len bytes inside shared memory, word-granular on the destination
@@ -261,11 +281,7 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
       tb = __shfl_sync(0xffffffffu, bi, T_WARPS - 1);
     }
   }
-  if (warp == 0 && lane == 0) {
-    const unsigned long long tag = tile == 0 ? DESC_PREFIX : DESC_AGG;
-    st_volatile_u64(P.desc + (size_t)tile * FP_CHANNELS, tag | (unsigned long long)tile_cnt);
-    if (VARLEN) st_volatile_u64(P.desc + (size_t)tile * FP_CHANNELS + 1, tag | (unsigned long long)tb);
-  }
+  if (warp == 0 && lane == 0) st_volatile_u64(P.desc + tile, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
   // ---- C: compact the strings in shared memory at tile-local positions (overlaps the look-back) ----
   const int my_cnt_excl = w_cnt_excl + cnt_incl - cnt;
   int lpos[4];
@@ -285,9 +301,8 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
   }
   // ---- D: decoupled look-back (warp 0) ----
   if (warp == 0) {
-    const long long ex0 = lookback_resolve(P.desc, tile, 0, tile_cnt, lane);
-    long long ex1 = 0;
-    if (VARLEN) ex1 = lookback_resolve(P.desc, tile, 1, tb, lane);
+    long long ex0, ex1;
+    lookback_resolve(P.desc, tile, tile_cnt, tb, lane, &ex0, &ex1);
     if (lane == 0) {
       s_excl[0] = ex0; s_excl[1] = ex1;
       if (tile == P.n_tiles - 1) { P.totals[0] = ex0 + tile_cnt; P.totals[1] = ex1 + tb; }
@@ -358,6 +373,7 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
                                cudaStream_t stream) {
   (void)ticket;
   if (reinterpret_cast<uintptr_t>(pred_in) & 7) return false;
+  if (n_rows >= (1ll << 31) - 1) return false;  // 31-bit descriptor fields
   if (data_out && (reinterpret_cast<uintptr_t>(data_out) & 15)) return false;
   if (n_fixed_out > 2) return false;
   TmaParams P;
