@@ -103,7 +103,7 @@ __device__ __forceinline__ unsigned long long desc_pack(unsigned long long statu
   return status | ((unsigned long long)cnt << 31) | (unsigned long long)bytes;
 }
 constexpr unsigned long long DESC_FIELD = (1ull << 31) - 1;
-constexpr int LB_WINDOWS = 8;  // 8 × 32 predecessor tiles inspected per look-back round
+constexpr int LB_WINDOWS = 4;  // 4 × 32 predecessor tiles inspected per look-back round
 
 // Decoupled look-back, resolve half (warp 0).  The tile's aggregate is already published.  A wave of
 // ~900 CTAs starts together, so the nearest tile holding an inclusive prefix can be hundreds of tiles
@@ -124,20 +124,22 @@ __device__ void lookback_resolve(unsigned long long* desc, int tile, long long a
       }
 #pragma unroll
       for (int w = 0; w < LB_WINDOWS; ++w) {
-        if (done) break;
-        const int idx = look - w * 32 - lane;
-        while (__any_sync(0xffffffffu, (d[w] >> 62) == 0)) {  // a predecessor has not published yet
-          if ((d[w] >> 62) == 0) d[w] = ld_volatile_u64(desc + idx);
+        if (!done) {  // warp-uniform
+          const int idx = look - w * 32 - lane;
+          unsigned long long dw = d[w];
+          while (__any_sync(0xffffffffu, (dw >> 62) == 0)) {  // a predecessor has not published yet
+            if ((dw >> 62) == 0) dw = ld_volatile_u64(desc + idx);
+          }
+          const unsigned pm = __ballot_sync(0xffffffffu, (dw >> 62) == 2);
+          long long c = (long long)((dw >> 31) & DESC_FIELD), b = (long long)(dw & DESC_FIELD);
+          if (pm) {
+            const int first = __ffs(pm) - 1;
+            if (lane > first) { c = 0; b = 0; }
+            done = true;
+          }
+          run_c += warp_sum(c);
+          run_b += warp_sum(b);
         }
-        const unsigned pm = __ballot_sync(0xffffffffu, (d[w] >> 62) == 2);
-        long long c = (long long)((d[w] >> 31) & DESC_FIELD), b = (long long)(d[w] & DESC_FIELD);
-        if (pm) {
-          const int first = __ffs(pm) - 1;
-          if (lane > first) { c = 0; b = 0; }
-          done = true;
-        }
-        run_c += warp_sum(c);
-        run_b += warp_sum(b);
       }
       look -= LB_WINDOWS * 32;
     }
@@ -282,8 +284,17 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
     }
   }
   if (warp == 0 && lane == 0) st_volatile_u64(P.desc + tile, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
-  // ---- C: compact the strings in shared memory at tile-local positions (overlaps the look-back) ----
+  // ---- C: decoupled look-back on warp 0, while warps 1-7 already compact their strings ----
   const int my_cnt_excl = w_cnt_excl + cnt_incl - cnt;
+  if (warp == 0) {
+    long long ex0, ex1;
+    lookback_resolve(P.desc, tile, tile_cnt, tb, lane, &ex0, &ex1);
+    if (lane == 0) {
+      s_excl[0] = ex0; s_excl[1] = ex1;
+      if (tile == P.n_tiles - 1) { P.totals[0] = ex0 + tile_cnt; P.totals[1] = ex1 + tb; }
+    }
+  }
+  // ---- D: compact the strings in shared memory at tile-local positions ----
   int lpos[4];
   bool str_fast = false;
   if (VARLEN) {
@@ -297,15 +308,6 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if ((flags >> j) & 1) smem_copy(out_bytes + lpos[j], in_bytes + (off[j] - base), off[j + 1] - off[j]);
-    }
-  }
-  // ---- D: decoupled look-back (warp 0) ----
-  if (warp == 0) {
-    long long ex0, ex1;
-    lookback_resolve(P.desc, tile, tile_cnt, tb, lane, &ex0, &ex1);
-    if (lane == 0) {
-      s_excl[0] = ex0; s_excl[1] = ex1;
-      if (tile == P.n_tiles - 1) { P.totals[0] = ex0 + tile_cnt; P.totals[1] = ex1 + tb; }
     }
   }
   __syncthreads();
