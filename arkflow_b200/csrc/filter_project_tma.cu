@@ -103,12 +103,13 @@ __device__ __forceinline__ unsigned long long desc_pack(unsigned long long statu
   return status | ((unsigned long long)cnt << 31) | (unsigned long long)bytes;
 }
 constexpr unsigned long long DESC_FIELD = (1ull << 31) - 1;
-constexpr int LB_WINDOWS = 4;  // 4 × 32 predecessor tiles inspected per look-back round
+constexpr int LB_WINDOWS = 2;  // 2 × 32 predecessor tiles fetched per look-back round
 
-// Decoupled look-back, resolve half (warp 0).  The tile's aggregate is already published.  A wave of
-// ~900 CTAs starts together, so the nearest tile holding an inclusive prefix can be hundreds of tiles
-// back: each lane fetches LB_WINDOWS descriptors at once (independent loads, one L2 round trip) and
-// the windows are then folded nearest-first.  Returns the exclusive (rows, bytes) prefix.
+// Decoupled look-back, resolve half (warp 0).  The tile's aggregate is already published.
+// The sustainable tile rate of a single-pass scan is (tiles inspected per round) / (round latency):
+// at ~85 tiles/µs a 32-wide round with shuffle reductions (~0.4 µs) is exactly the limit, so the
+// round is kept short — one volatile load per window, REDUX (`__reduce_add_sync`) instead of shuffle
+// trees, the prefix tile's sums fetched with one shuffle — and two windows are in flight per round.
 __device__ void lookback_resolve(unsigned long long* desc, int tile, long long agg_cnt, long long agg_bytes, int lane,
                                  long long* ex_cnt, long long* ex_bytes) {
   long long run_c = 0, run_b = 0;
@@ -116,29 +117,29 @@ __device__ void lookback_resolve(unsigned long long* desc, int tile, long long a
     int look = tile - 1;
     bool done = false;
     while (!done) {
-      unsigned long long d[LB_WINDOWS];
-#pragma unroll
-      for (int w = 0; w < LB_WINDOWS; ++w) {
-        const int idx = look - w * 32 - lane;
-        d[w] = idx >= 0 ? ld_volatile_u64(desc + idx) : DESC_PREFIX;  // virtual tile -1: inclusive prefix 0
-      }
+      const int idx0 = look - lane, idx1 = look - 32 - lane;
+      unsigned long long d0 = idx0 >= 0 ? ld_volatile_u64(desc + idx0) : DESC_PREFIX;  // virtual tile -1: prefix 0
+      unsigned long long d1 = idx1 >= 0 ? ld_volatile_u64(desc + idx1) : DESC_PREFIX;
 #pragma unroll
       for (int w = 0; w < LB_WINDOWS; ++w) {
         if (!done) {  // warp-uniform
-          const int idx = look - w * 32 - lane;
-          unsigned long long dw = d[w];
+          const int idx = w == 0 ? idx0 : idx1;
+          unsigned long long dw = w == 0 ? d0 : d1;
           while (__any_sync(0xffffffffu, (dw >> 62) == 0)) {  // a predecessor has not published yet
             if ((dw >> 62) == 0) dw = ld_volatile_u64(desc + idx);
           }
           const unsigned pm = __ballot_sync(0xffffffffu, (dw >> 62) == 2);
-          long long c = (long long)((dw >> 31) & DESC_FIELD), b = (long long)(dw & DESC_FIELD);
+          const int first = pm ? __ffs(pm) - 1 : 32;
+          // aggregates of the tiles nearer than the first prefix tile (small numbers: REDUX on u32)
+          const bool is_agg = lane < first;
+          run_c += __reduce_add_sync(0xffffffffu, is_agg ? (unsigned)((dw >> 31) & DESC_FIELD) : 0u);
+          run_b += __reduce_add_sync(0xffffffffu, is_agg ? (unsigned)(dw & DESC_FIELD) : 0u);
           if (pm) {
-            const int first = __ffs(pm) - 1;
-            if (lane > first) { c = 0; b = 0; }
+            const unsigned long long dp = __shfl_sync(0xffffffffu, dw, first);
+            run_c += (long long)((dp >> 31) & DESC_FIELD);
+            run_b += (long long)(dp & DESC_FIELD);
             done = true;
           }
-          run_c += warp_sum(c);
-          run_b += warp_sum(b);
         }
       }
       look -= LB_WINDOWS * 32;
@@ -284,17 +285,8 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
     }
   }
   if (warp == 0 && lane == 0) st_volatile_u64(P.desc + tile, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
-  // ---- C: decoupled look-back on warp 0, while warps 1-7 already compact their strings ----
+  // ---- C: compact the strings in shared memory at tile-local positions ----
   const int my_cnt_excl = w_cnt_excl + cnt_incl - cnt;
-  if (warp == 0) {
-    long long ex0, ex1;
-    lookback_resolve(P.desc, tile, tile_cnt, tb, lane, &ex0, &ex1);
-    if (lane == 0) {
-      s_excl[0] = ex0; s_excl[1] = ex1;
-      if (tile == P.n_tiles - 1) { P.totals[0] = ex0 + tile_cnt; P.totals[1] = ex1 + tb; }
-    }
-  }
-  // ---- D: compact the strings in shared memory at tile-local positions ----
   int lpos[4];
   bool str_fast = false;
   if (VARLEN) {
@@ -308,6 +300,15 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if ((flags >> j) & 1) smem_copy(out_bytes + lpos[j], in_bytes + (off[j] - base), off[j + 1] - off[j]);
+    }
+  }
+  // ---- D: decoupled look-back (warp 0) ----
+  if (warp == 0) {
+    long long ex0, ex1;
+    lookback_resolve(P.desc, tile, tile_cnt, tb, lane, &ex0, &ex1);
+    if (lane == 0) {
+      s_excl[0] = ex0; s_excl[1] = ex1;
+      if (tile == P.n_tiles - 1) { P.totals[0] = ex0 + tile_cnt; P.totals[1] = ex1 + tb; }
     }
   }
   __syncthreads();
