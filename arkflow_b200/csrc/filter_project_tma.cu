@@ -40,6 +40,7 @@ struct TmaParams {
   int32_t n_fixed_out;
   int32_t has_varlen;
   int32_t str_cap;                          // bytes of shared memory per string buffer (multiple of 16)
+  int32_t scout;                            // CTA t also pre-aggregates tile t + scout (0 = off)
   int32_t sp_is_f64, negate;                // predicate as a range test on the (totalOrder) key
   long long range_lo;
   unsigned long long range_span;            // keep ⇔ ((u64)(key - range_lo) <= range_span) != negate
@@ -189,14 +190,64 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   return v;
 }
 
+// Loads rows 4t..4t+3 of a tile: predicate values and (VARLEN) the 5 bounding offsets.
+template <bool VARLEN>
+__device__ __forceinline__ void load_rows(const TmaParams& P, int64_t row0, int rows, int lr0, int lane, unsigned long long pv[4], int off[5]) {
+  const bool full = lr0 + 4 <= rows;
+  const unsigned long long* src = P.pred_in + row0 + lr0;
+  if (full && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(pv[0]), "=l"(pv[1]) : "l"(src));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(pv[2]), "=l"(pv[3]) : "l"(src + 2));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pv[j] = (lr0 + j < rows) ? src[j] : 0;
+  }
+  if (VARLEN) {
+    const int32_t* os = P.offsets_in + row0 + lr0;
+    if (full && (reinterpret_cast<uintptr_t>(os) & 15) == 0) {
+      asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(off[0]), "=r"(off[1]), "=r"(off[2]), "=r"(off[3]) : "l"(os));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) off[j] = (lr0 + j <= rows) ? os[j] : 0;
+    }
+    off[4] = __shfl_down_sync(0xffffffffu, off[0], 1);
+    if ((lane == 31 || lr0 + 4 >= rows) && lr0 + 4 <= rows) off[4] = os[4];
+  }
+}
+
+template <bool VARLEN>
+__device__ __forceinline__ unsigned eval_rows(const TmaParams& P, int rows, int lr0, const unsigned long long pv[4], const int off[5],
+                                              int* cnt, int* sel_bytes) {
+  unsigned flags = 0;
+  int c = 0, sb = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long key = P.sp_is_f64 ? f64_total_key(pv[j]) : (long long)pv[j];
+    bool f = (unsigned long long)(key - P.range_lo) <= P.range_span;
+    f = (f != (bool)P.negate) && (lr0 + j < rows);
+    flags |= (unsigned)f << j;
+    c += f;
+    if (VARLEN && f) sb += off[j + 1] - off[j];
+  }
+  *cnt = c; *sel_bytes = sb;
+  return flags;
+}
+
 // Thread t owns rows 4t..4t+3 of the tile (blocked): two 16-byte loads per 8-byte column, one warp scan
 // per quantity, thread-local ranks.
+//
+// Look-back off the critical path: CTA t also "scouts" tile t + P.scout — it reads that tile's
+// predicate column and offsets (12 B/row, which stay in the 126 MB L2 for the owner) and publishes
+// its aggregate.  When a CTA starts, the aggregates of ALL its predecessors (and its own) were
+// published one CTA lifetime ago, so warp 0 resolves the tile's prefix immediately, while the
+// tile's own loads and the TMA copy are still in flight, instead of after them behind the slowest
+// of its in-flight predecessors.  The first P.scout tiles have no scout and use the classic order.
 template <int NF, bool VARLEN>
 __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const __grid_constant__ TmaParams P) {
   extern __shared__ __align__(16) uint8_t smem[];   // [in_bytes: str_cap + 32][out_bytes: str_cap + 32]
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_str_base, s_str_staged;
-  __shared__ int s_cnt[T_WARPS], s_bytes[T_WARPS];
+  __shared__ int s_cnt[T_WARPS], s_bytes[T_WARPS], s_scout_cnt[T_WARPS], s_scout_bytes[T_WARPS];
   __shared__ long long s_excl[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -205,6 +256,9 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
   const int rows = (int)((P.n_rows - row0) < TT ? (P.n_rows - row0) : TT);
   uint8_t* in_bytes = smem;
   uint8_t* out_bytes = smem + P.str_cap + 32;
+  const bool scouted = P.scout > 0 && tile >= P.scout;           // my aggregate was published by CTA tile - scout
+  const int stile = P.scout > 0 ? tile + P.scout : P.n_tiles;    // the tile I scout
+  const bool do_scout = stile < P.n_tiles;
 
   if (VARLEN && tid == 0) {
     mbar_init(&s_bar, 1);
@@ -221,52 +275,44 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
     s_str_base = o0 - (int32_t)(a0 - lo); s_str_staged = staged;
   }
 
-  // ---- A: loads (registers), predicate, thread-local and warp-level prefix sums ----
+  // ---- A: loads in flight: own tile, then the scouted tile ----
   const int lr0 = 4 * tid;
-  const bool full = lr0 + 4 <= rows;
-  unsigned long long pv[4] = {0, 0, 0, 0};
+  unsigned long long pv[4];
   int off[5] = {0, 0, 0, 0, 0};
-  {
-    const unsigned long long* src = P.pred_in + row0 + lr0;
-    if (full && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-      asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(pv[0]), "=l"(pv[1]) : "l"(src));
-      asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(pv[2]), "=l"(pv[3]) : "l"(src + 2));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (lr0 + j < rows) pv[j] = src[j];
-    }
-    if (VARLEN) {
-      const int32_t* os = P.offsets_in + row0 + lr0;
-      if (full && (reinterpret_cast<uintptr_t>(os) & 15) == 0) {
-        int4 o4;
-        asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(o4.x), "=r"(o4.y), "=r"(o4.z), "=r"(o4.w) : "l"(os));
-        off[0] = o4.x; off[1] = o4.y; off[2] = o4.z; off[3] = o4.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (lr0 + j <= rows) off[j] = os[j];
-      }
-      off[4] = __shfl_down_sync(0xffffffffu, off[0], 1);
-      if ((lane == 31 || lr0 + 4 >= rows) && lr0 + 4 <= rows) off[4] = os[4];
-    }
+  load_rows<VARLEN>(P, row0, rows, lr0, lane, pv, off);
+  unsigned long long spv[4] = {0, 0, 0, 0};
+  int soff[5] = {0, 0, 0, 0, 0};
+  const int64_t srow0 = (int64_t)stile * TT;
+  const int srows = do_scout ? (int)((P.n_rows - srow0) < TT ? (P.n_rows - srow0) : TT) : 0;
+  if (do_scout) load_rows<VARLEN>(P, srow0, srows, lr0, lane, spv, soff);
+
+  // ---- B: scouted tiles resolve their prefix NOW (all predecessor aggregates are long published) ----
+  if (scouted && warp == 0) {
+    unsigned long long mine = 0;
+    if (lane == 0) { do { mine = ld_volatile_u64(P.desc + tile); } while ((mine >> 62) == 0); }
+    mine = __shfl_sync(0xffffffffu, mine, 0);
+    long long ex0, ex1;
+    lookback_resolve(P.desc, tile, (long long)((mine >> 31) & DESC_FIELD), (long long)(mine & DESC_FIELD), lane, &ex0, &ex1);
+    if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
   }
-  unsigned flags = 0;
-  int cnt = 0, sel_bytes = 0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const long long key = P.sp_is_f64 ? f64_total_key(pv[j]) : (long long)pv[j];
-    bool f = (unsigned long long)(key - P.range_lo) <= P.range_span;
-    f = (f != (bool)P.negate) && (lr0 + j < rows);
-    flags |= (unsigned)f << j;
-    cnt += f;
-    if (VARLEN && f) sel_bytes += off[j + 1] - off[j];
-  }
+
+  // ---- C: predicate, thread-local and warp-level prefix sums (own tile); warp sums (scouted tile) ----
+  int cnt, sel_bytes;
+  const unsigned flags = eval_rows<VARLEN>(P, rows, lr0, pv, off, &cnt, &sel_bytes);
   const int cnt_incl = warp_incl_scan(cnt, lane);
   int bytes_incl = 0;
   if (VARLEN) bytes_incl = warp_incl_scan(sel_bytes, lane);
   if (lane == 31) { s_cnt[warp] = cnt_incl; if (VARLEN) s_bytes[warp] = bytes_incl; }
+  if (do_scout) {
+    int sc, sb;
+    eval_rows<VARLEN>(P, srows, lr0, spv, soff, &sc, &sb);
+    const unsigned wc = __reduce_add_sync(0xffffffffu, (unsigned)sc);
+    const unsigned wb = VARLEN ? __reduce_add_sync(0xffffffffu, (unsigned)sb) : 0u;
+    if (lane == 0) { s_scout_cnt[warp] = (int)wc; s_scout_bytes[warp] = (int)wb; }
+  }
   __syncthreads();
 
-  // ---- B: 8-entry tile scan (every warp, redundantly); warp 0 publishes the tile aggregate at once ----
+  // ---- D: 8-entry tile scan (every warp, redundantly); publish aggregates ----
   int w_cnt_excl, w_bytes_excl = 0, tile_cnt, tb = 0;
   {
     const int c = lane < T_WARPS ? s_cnt[lane] : 0;
@@ -284,8 +330,14 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
       tb = __shfl_sync(0xffffffffu, bi, T_WARPS - 1);
     }
   }
-  if (warp == 0 && lane == 0) st_volatile_u64(P.desc + tile, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
-  // ---- C: compact the strings in shared memory at tile-local positions ----
+  if (warp == 1 && do_scout) {  // aggregate of the scouted tile (tile 0 is never scouted: scout >= 1)
+    const unsigned c = __reduce_add_sync(0xffffffffu, lane < T_WARPS ? (unsigned)s_scout_cnt[lane] : 0u);
+    const unsigned b = __reduce_add_sync(0xffffffffu, lane < T_WARPS ? (unsigned)s_scout_bytes[lane] : 0u);
+    if (lane == 0) st_volatile_u64(P.desc + stile, desc_pack(DESC_AGG, c, b));
+  }
+  if (!scouted && warp == 0 && lane == 0) st_volatile_u64(P.desc + tile, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
+
+  // ---- E: compact the strings in shared memory at tile-local positions ----
   const int my_cnt_excl = w_cnt_excl + cnt_incl - cnt;
   int lpos[4];
   bool str_fast = false;
@@ -302,20 +354,18 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
         if ((flags >> j) & 1) smem_copy(out_bytes + lpos[j], in_bytes + (off[j] - base), off[j + 1] - off[j]);
     }
   }
-  // ---- D: decoupled look-back (warp 0) ----
-  if (warp == 0) {
+  // ---- F: classic decoupled look-back for the unscouted head of the batch (warp 0) ----
+  if (!scouted && warp == 0) {
     long long ex0, ex1;
     lookback_resolve(P.desc, tile, tile_cnt, tb, lane, &ex0, &ex1);
-    if (lane == 0) {
-      s_excl[0] = ex0; s_excl[1] = ex1;
-      if (tile == P.n_tiles - 1) { P.totals[0] = ex0 + tile_cnt; P.totals[1] = ex1 + tb; }
-    }
+    if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
   }
   __syncthreads();
   const long long base_cnt = s_excl[0];
   const long long bb = VARLEN ? s_excl[1] : 0;
+  if (tile == P.n_tiles - 1 && tid == 0) { P.totals[0] = base_cnt + tile_cnt; P.totals[1] = bb + tb; }
 
-  // ---- E: stores ----
+  // ---- G: stores ----
   {
     long long pos = base_cnt + my_cnt_excl;
 #pragma unroll
@@ -365,6 +415,7 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
 }  // namespace
 
 static std::atomic<double> g_avg_len_hint{12.8};
+static int g_scout_distance = [] { const char* e = getenv("ARK_FP_SCOUT"); return e ? atoi(e) : 1536; }();
 void filter_project_tma_note_avg_len(double avg) { if (avg > 0) g_avg_len_hint.store(avg); }
 int filter_project_tma_tile_rows() { return TT; }
 int filter_project_tma_max_fixed_out() { return T_MAX_FIXED_OUT; }
@@ -414,6 +465,7 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
     cap = std::max(4096, std::min(cap, 24 * 1024));
   }
   P.str_cap = cap;
+  P.scout = g_scout_distance;
   const size_t smem = P.has_varlen ? 2 * (size_t)(cap + 32) : 0;
   const int max_smem = 2 * (24 * 1024 + 32);
   static bool configured = false;
