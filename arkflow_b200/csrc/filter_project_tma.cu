@@ -29,9 +29,6 @@ namespace ark {
 
 namespace {
 
-constexpr int TT = 1024;                    // rows per tile
-constexpr int T_THREADS = 256;
-constexpr int T_WARPS = T_THREADS / 32;
 constexpr int T_MAX_FIXED_OUT = 2;
 
 struct TmaParams {
@@ -41,6 +38,7 @@ struct TmaParams {
   int32_t has_varlen;
   int32_t str_cap;                          // bytes of shared memory per string buffer (multiple of 16)
   int32_t scout;                            // CTA t also pre-aggregates tile t + scout (0 = off)
+  int32_t desc_stride;                      // u64 words between consecutive tile descriptors
   int32_t sp_is_f64, negate;                // predicate as a range test on the (totalOrder) key
   long long range_lo;
   unsigned long long range_span;            // keep ⇔ ((u64)(key - range_lo) <= range_span) != negate
@@ -111,7 +109,7 @@ constexpr int LB_WINDOWS = 2;  // 2 × 32 predecessor tiles fetched per look-bac
 // at ~85 tiles/µs a 32-wide round with shuffle reductions (~0.4 µs) is exactly the limit, so the
 // round is kept short — one volatile load per window, REDUX (`__reduce_add_sync`) instead of shuffle
 // trees, the prefix tile's sums fetched with one shuffle — and two windows are in flight per round.
-__device__ void lookback_resolve(unsigned long long* desc, int tile, long long agg_cnt, long long agg_bytes, int lane,
+__device__ void lookback_resolve(unsigned long long* desc, int stride, int tile, long long agg_cnt, long long agg_bytes, int lane,
                                  long long* ex_cnt, long long* ex_bytes) {
   long long run_c = 0, run_b = 0;
   if (tile > 0) {
@@ -119,15 +117,15 @@ __device__ void lookback_resolve(unsigned long long* desc, int tile, long long a
     bool done = false;
     while (!done) {
       const int idx0 = look - lane, idx1 = look - 32 - lane;
-      unsigned long long d0 = idx0 >= 0 ? ld_volatile_u64(desc + idx0) : DESC_PREFIX;  // virtual tile -1: prefix 0
-      unsigned long long d1 = idx1 >= 0 ? ld_volatile_u64(desc + idx1) : DESC_PREFIX;
+      unsigned long long d0 = idx0 >= 0 ? ld_volatile_u64(desc + (size_t)idx0 * stride) : DESC_PREFIX;  // virtual tile -1: prefix 0
+      unsigned long long d1 = idx1 >= 0 ? ld_volatile_u64(desc + (size_t)idx1 * stride) : DESC_PREFIX;
 #pragma unroll
       for (int w = 0; w < LB_WINDOWS; ++w) {
         if (!done) {  // warp-uniform
           const int idx = w == 0 ? idx0 : idx1;
           unsigned long long dw = w == 0 ? d0 : d1;
           while (__any_sync(0xffffffffu, (dw >> 62) == 0)) {  // a predecessor has not published yet
-            if ((dw >> 62) == 0) dw = ld_volatile_u64(desc + idx);
+            if ((dw >> 62) == 0) dw = ld_volatile_u64(desc + (size_t)idx * stride);
           }
           const unsigned pm = __ballot_sync(0xffffffffu, (dw >> 62) == 2);
           const int first = pm ? __ffs(pm) - 1 : 32;
@@ -145,7 +143,7 @@ __device__ void lookback_resolve(unsigned long long* desc, int tile, long long a
       }
       look -= LB_WINDOWS * 32;
     }
-    if (lane == 0) st_volatile_u64(desc + tile, desc_pack(DESC_PREFIX, run_c + agg_cnt, run_b + agg_bytes));
+    if (lane == 0) st_volatile_u64(desc + (size_t)tile * stride, desc_pack(DESC_PREFIX, run_c + agg_cnt, run_b + agg_bytes));
   }
   *ex_cnt = run_c; *ex_bytes = run_b;
 }
@@ -242,8 +240,11 @@ __device__ __forceinline__ unsigned eval_rows(const TmaParams& P, int rows, int 
 // published one CTA lifetime ago, so warp 0 resolves the tile's prefix immediately, while the
 // tile's own loads and the TMA copy are still in flight, instead of after them behind the slowest
 // of its in-flight predecessors.  The first P.scout tiles have no scout and use the classic order.
-template <int NF, bool VARLEN>
-__global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const __grid_constant__ TmaParams P) {
+template <int NF, bool VARLEN, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 6 : 3) filter_project_tma_kernel(const __grid_constant__ TmaParams P) {
+  constexpr int TT = THREADS * 4;          // rows per tile
+  constexpr int T_WARPS = THREADS / 32;
+  constexpr int T_THREADS = THREADS;
   extern __shared__ __align__(16) uint8_t smem[];   // [in_bytes: str_cap + 32][out_bytes: str_cap + 32]
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_str_base, s_str_staged;
@@ -289,10 +290,10 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
   // ---- B: scouted tiles resolve their prefix NOW (all predecessor aggregates are long published) ----
   if (scouted && warp == 0) {
     unsigned long long mine = 0;
-    if (lane == 0) { do { mine = ld_volatile_u64(P.desc + tile); } while ((mine >> 62) == 0); }
+    if (lane == 0) { do { mine = ld_volatile_u64(P.desc + (size_t)tile * P.desc_stride); } while ((mine >> 62) == 0); }
     mine = __shfl_sync(0xffffffffu, mine, 0);
     long long ex0, ex1;
-    lookback_resolve(P.desc, tile, (long long)((mine >> 31) & DESC_FIELD), (long long)(mine & DESC_FIELD), lane, &ex0, &ex1);
+    lookback_resolve(P.desc, P.desc_stride, tile, (long long)((mine >> 31) & DESC_FIELD), (long long)(mine & DESC_FIELD), lane, &ex0, &ex1);
     if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
   }
 
@@ -333,9 +334,9 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
   if (warp == 1 && do_scout) {  // aggregate of the scouted tile (tile 0 is never scouted: scout >= 1)
     const unsigned c = __reduce_add_sync(0xffffffffu, lane < T_WARPS ? (unsigned)s_scout_cnt[lane] : 0u);
     const unsigned b = __reduce_add_sync(0xffffffffu, lane < T_WARPS ? (unsigned)s_scout_bytes[lane] : 0u);
-    if (lane == 0) st_volatile_u64(P.desc + stile, desc_pack(DESC_AGG, c, b));
+    if (lane == 0) st_volatile_u64(P.desc + (size_t)stile * P.desc_stride, desc_pack(DESC_AGG, c, b));
   }
-  if (!scouted && warp == 0 && lane == 0) st_volatile_u64(P.desc + tile, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
+  if (!scouted && warp == 0 && lane == 0) st_volatile_u64(P.desc + (size_t)tile * P.desc_stride, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
 
   // ---- E: compact the strings in shared memory at tile-local positions ----
   const int my_cnt_excl = w_cnt_excl + cnt_incl - cnt;
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
   // ---- F: classic decoupled look-back for the unscouted head of the batch (warp 0) ----
   if (!scouted && warp == 0) {
     long long ex0, ex1;
-    lookback_resolve(P.desc, tile, tile_cnt, tb, lane, &ex0, &ex1);
+    lookback_resolve(P.desc, P.desc_stride, tile, tile_cnt, tb, lane, &ex0, &ex1);
     if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
   }
   __syncthreads();
@@ -417,7 +418,10 @@ __global__ void __launch_bounds__(T_THREADS, 6) filter_project_tma_kernel(const 
 static std::atomic<double> g_avg_len_hint{12.8};
 static int g_scout_distance = [] { const char* e = getenv("ARK_FP_SCOUT"); return e ? atoi(e) : 1536; }();
 void filter_project_tma_note_avg_len(double avg) { if (avg > 0) g_avg_len_hint.store(avg); }
-int filter_project_tma_tile_rows() { return TT; }
+static int g_fp_threads = [] { const char* e = getenv("ARK_FP_THREADS"); return e && atoi(e) == 512 ? 512 : 256; }();
+static int g_desc_stride = [] { const char* e = getenv("ARK_FP_DESC_STRIDE"); int v = e ? atoi(e) : 1; return v >= 1 && v <= 16 ? v : 1; }();
+int filter_project_tma_tile_rows() { return g_fp_threads * 4; }
+int filter_project_tma_desc_stride() { return g_desc_stride; }
 int filter_project_tma_max_fixed_out() { return T_MAX_FIXED_OUT; }
 
 // Returns false when the inputs do not meet the alignment rules of this path (caller falls back).
@@ -432,6 +436,7 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
   if (n_fixed_out > 2) return false;
   TmaParams P;
   memset(&P, 0, sizeof P);
+  const int TT = g_fp_threads * 4;
   P.n_rows = n_rows; P.n_tiles = (int)ceil_div(n_rows, TT); P.n_fixed_out = n_fixed_out; P.has_varlen = offsets_in != nullptr;
   P.sp_is_f64 = is_f64;
   {  // comparison against a constant → range membership on the totally ordered int64 key
@@ -462,27 +467,42 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
     // exact when the extent is known; otherwise the average selected-string length of the previous launch
     double avg = n_rows > 0 && data_bytes >= 0 ? (double)data_bytes / (double)n_rows : g_avg_len_hint.load();
     cap = (int)round_up((int64_t)(avg * TT * 1.25) + 64, 2048);
-    cap = std::max(4096, std::min(cap, 24 * 1024));
+    cap = std::max(4096, std::min(cap, (TT / 1024) * 24 * 1024));
   }
   P.str_cap = cap;
   P.scout = g_scout_distance;
+  P.desc_stride = g_desc_stride;
   const size_t smem = P.has_varlen ? 2 * (size_t)(cap + 32) : 0;
-  const int max_smem = 2 * (24 * 1024 + 32);
+  const int max_smem = 2 * (48 * 1024 + 32);
   static bool configured = false;
   if (!configured) {
-    ARK_CUDA(cudaFuncSetAttribute(filter_project_tma_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    ARK_CUDA(cudaFuncSetAttribute(filter_project_tma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    ARK_CUDA(cudaFuncSetAttribute(filter_project_tma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ARK_CUDA(cudaFuncSetAttribute(filter_project_tma_kernel<0, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ARK_CUDA(cudaFuncSetAttribute(filter_project_tma_kernel<1, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ARK_CUDA(cudaFuncSetAttribute(filter_project_tma_kernel<2, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ARK_CUDA(cudaFuncSetAttribute(filter_project_tma_kernel<0, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ARK_CUDA(cudaFuncSetAttribute(filter_project_tma_kernel<1, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    ARK_CUDA(cudaFuncSetAttribute(filter_project_tma_kernel<2, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
   KernelTimer t("filter_project_tma_kernel", stream);
   const bool v = P.has_varlen;
-  if (n_fixed_out == 0 && v) filter_project_tma_kernel<0, true><<<P.n_tiles, T_THREADS, smem, stream>>>(P);
-  else if (n_fixed_out == 1 && v) filter_project_tma_kernel<1, true><<<P.n_tiles, T_THREADS, smem, stream>>>(P);
-  else if (n_fixed_out == 2 && v) filter_project_tma_kernel<2, true><<<P.n_tiles, T_THREADS, smem, stream>>>(P);
-  else if (n_fixed_out == 1) filter_project_tma_kernel<1, false><<<P.n_tiles, T_THREADS, 0, stream>>>(P);
-  else if (n_fixed_out == 2) filter_project_tma_kernel<2, false><<<P.n_tiles, T_THREADS, 0, stream>>>(P);
-  else return false;
+#define ARK_TMA_LAUNCH(NF, V, TH) filter_project_tma_kernel<NF, V, TH><<<P.n_tiles, TH, (V) ? smem : 0, stream>>>(P)
+  if (g_fp_threads == 256) {
+    if (n_fixed_out == 0 && v) ARK_TMA_LAUNCH(0, true, 256);
+    else if (n_fixed_out == 1 && v) ARK_TMA_LAUNCH(1, true, 256);
+    else if (n_fixed_out == 2 && v) ARK_TMA_LAUNCH(2, true, 256);
+    else if (n_fixed_out == 1) ARK_TMA_LAUNCH(1, false, 256);
+    else if (n_fixed_out == 2) ARK_TMA_LAUNCH(2, false, 256);
+    else return false;
+  } else {
+    if (n_fixed_out == 0 && v) ARK_TMA_LAUNCH(0, true, 512);
+    else if (n_fixed_out == 1 && v) ARK_TMA_LAUNCH(1, true, 512);
+    else if (n_fixed_out == 2 && v) ARK_TMA_LAUNCH(2, true, 512);
+    else if (n_fixed_out == 1) ARK_TMA_LAUNCH(1, false, 512);
+    else if (n_fixed_out == 2) ARK_TMA_LAUNCH(2, false, 512);
+    else return false;
+  }
+#undef ARK_TMA_LAUNCH
   return true;
 }
 
