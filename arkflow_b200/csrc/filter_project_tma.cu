@@ -416,10 +416,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 6 : 3) filter_projec
 }  // namespace
 
 static std::atomic<double> g_avg_len_hint{12.8};
-static int g_scout_distance = [] { const char* e = getenv("ARK_FP_SCOUT"); return e ? atoi(e) : 1536; }();
+static int g_scout_distance = [] { const char* e = getenv("ARK_FP_SCOUT"); return e ? atoi(e) : 0; }();
 void filter_project_tma_note_avg_len(double avg) { if (avg > 0) g_avg_len_hint.store(avg); }
 static int g_fp_threads = [] { const char* e = getenv("ARK_FP_THREADS"); return e && atoi(e) == 512 ? 512 : 256; }();
-static int g_desc_stride = [] { const char* e = getenv("ARK_FP_DESC_STRIDE"); int v = e ? atoi(e) : 1; return v >= 1 && v <= 16 ? v : 1; }();
+static int g_desc_stride = [] { const char* e = getenv("ARK_FP_DESC_STRIDE"); int v = e ? atoi(e) : 4; return v >= 1 && v <= 16 ? v : 4; }();  // one descriptor per 32-byte sector
 int filter_project_tma_tile_rows() { return g_fp_threads * 4; }
 int filter_project_tma_desc_stride() { return g_desc_stride; }
 int filter_project_tma_max_fixed_out() { return T_MAX_FIXED_OUT; }
