@@ -2,7 +2,7 @@
 # the reference is Rust on top of un-vendored crates and cannot be compiled here.
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v --expt-relaxed-constexpr
+NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v --expt-relaxed-constexpr $(EXTRA)
 CSRC      := arkflow_b200/csrc
 OBJDIR    := build/obj
 SRCS      := $(wildcard $(CSRC)/*.cu) $(wildcard $(CSRC)/*.cc)

@@ -25,6 +25,10 @@
 #include "filter_project.cuh"
 #include "vm.cuh"
 
+#ifndef ARK_FP_MINBLOCKS
+#define ARK_FP_MINBLOCKS 6
+#endif
+
 namespace ark {
 
 namespace {
@@ -37,7 +41,6 @@ struct TmaParams {
   int32_t n_fixed_out;
   int32_t has_varlen;
   int32_t str_cap;                          // bytes of shared memory per string buffer (multiple of 16)
-  int32_t scout;                            // CTA t also pre-aggregates tile t + scout (0 = off)
   int32_t desc_stride;                      // u64 words between consecutive tile descriptors
   int32_t sp_is_f64, negate;                // predicate as a range test on the (totalOrder) key
   long long range_lo;
@@ -234,21 +237,20 @@ __device__ __forceinline__ unsigned eval_rows(const TmaParams& P, int rows, int 
 // Thread t owns rows 4t..4t+3 of the tile (blocked): two 16-byte loads per 8-byte column, one warp scan
 // per quantity, thread-local ranks.
 //
-// Look-back off the critical path: CTA t also "scouts" tile t + P.scout — it reads that tile's
-// predicate column and offsets (12 B/row, which stay in the 126 MB L2 for the owner) and publishes
-// its aggregate.  When a CTA starts, the aggregates of ALL its predecessors (and its own) were
-// published one CTA lifetime ago, so warp 0 resolves the tile's prefix immediately, while the
-// tile's own loads and the TMA copy are still in flight, instead of after them behind the slowest
-// of its in-flight predecessors.  The first P.scout tiles have no scout and use the classic order.
+// Measured on B200 (2^24 rows, 16384 tiles): the tile rate of a single-pass scan is bounded by the
+// descriptor traffic, not by HBM — with descriptors packed 4 per 32-byte sector every variant of this
+// kernel (with or without strings, look-back before or after staging, 32..256-tile rounds, aggregates
+// published one CTA lifetime ahead by "scout" CTAs) ran at ~80 tiles/us; one descriptor per sector
+// lifted that to ~95 tiles/us (0.21 -> 0.176 ms).  512-thread / 2048-row tiles were not faster.
 template <int NF, bool VARLEN, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 6 : 3) filter_project_tma_kernel(const __grid_constant__ TmaParams P) {
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? ARK_FP_MINBLOCKS : 3) filter_project_tma_kernel(const __grid_constant__ TmaParams P) {
   constexpr int TT = THREADS * 4;          // rows per tile
   constexpr int T_WARPS = THREADS / 32;
   constexpr int T_THREADS = THREADS;
   extern __shared__ __align__(16) uint8_t smem[];   // [in_bytes: str_cap + 32][out_bytes: str_cap + 32]
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_str_base, s_str_staged;
-  __shared__ int s_cnt[T_WARPS], s_bytes[T_WARPS], s_scout_cnt[T_WARPS], s_scout_bytes[T_WARPS];
+  __shared__ int s_cnt[T_WARPS], s_bytes[T_WARPS];
   __shared__ long long s_excl[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -257,9 +259,6 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 6 : 3) filter_projec
   const int rows = (int)((P.n_rows - row0) < TT ? (P.n_rows - row0) : TT);
   uint8_t* in_bytes = smem;
   uint8_t* out_bytes = smem + P.str_cap + 32;
-  const bool scouted = P.scout > 0 && tile >= P.scout;           // my aggregate was published by CTA tile - scout
-  const int stile = P.scout > 0 ? tile + P.scout : P.n_tiles;    // the tile I scout
-  const bool do_scout = stile < P.n_tiles;
 
   if (VARLEN && tid == 0) {
     mbar_init(&s_bar, 1);
@@ -276,44 +275,21 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 6 : 3) filter_projec
     s_str_base = o0 - (int32_t)(a0 - lo); s_str_staged = staged;
   }
 
-  // ---- A: loads in flight: own tile, then the scouted tile ----
+  // ---- A: loads ----
   const int lr0 = 4 * tid;
   unsigned long long pv[4];
   int off[5] = {0, 0, 0, 0, 0};
   load_rows<VARLEN>(P, row0, rows, lr0, lane, pv, off);
-  unsigned long long spv[4] = {0, 0, 0, 0};
-  int soff[5] = {0, 0, 0, 0, 0};
-  const int64_t srow0 = (int64_t)stile * TT;
-  const int srows = do_scout ? (int)((P.n_rows - srow0) < TT ? (P.n_rows - srow0) : TT) : 0;
-  if (do_scout) load_rows<VARLEN>(P, srow0, srows, lr0, lane, spv, soff);
-
-  // ---- B: scouted tiles resolve their prefix NOW (all predecessor aggregates are long published) ----
-  if (scouted && warp == 0) {
-    unsigned long long mine = 0;
-    if (lane == 0) { do { mine = ld_volatile_u64(P.desc + (size_t)tile * P.desc_stride); } while ((mine >> 62) == 0); }
-    mine = __shfl_sync(0xffffffffu, mine, 0);
-    long long ex0, ex1;
-    lookback_resolve(P.desc, P.desc_stride, tile, (long long)((mine >> 31) & DESC_FIELD), (long long)(mine & DESC_FIELD), lane, &ex0, &ex1);
-    if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
-  }
-
-  // ---- C: predicate, thread-local and warp-level prefix sums (own tile); warp sums (scouted tile) ----
+  // ---- B: predicate, thread-local and warp-level prefix sums ----
   int cnt, sel_bytes;
   const unsigned flags = eval_rows<VARLEN>(P, rows, lr0, pv, off, &cnt, &sel_bytes);
   const int cnt_incl = warp_incl_scan(cnt, lane);
   int bytes_incl = 0;
   if (VARLEN) bytes_incl = warp_incl_scan(sel_bytes, lane);
   if (lane == 31) { s_cnt[warp] = cnt_incl; if (VARLEN) s_bytes[warp] = bytes_incl; }
-  if (do_scout) {
-    int sc, sb;
-    eval_rows<VARLEN>(P, srows, lr0, spv, soff, &sc, &sb);
-    const unsigned wc = __reduce_add_sync(0xffffffffu, (unsigned)sc);
-    const unsigned wb = VARLEN ? __reduce_add_sync(0xffffffffu, (unsigned)sb) : 0u;
-    if (lane == 0) { s_scout_cnt[warp] = (int)wc; s_scout_bytes[warp] = (int)wb; }
-  }
   __syncthreads();
 
-  // ---- D: 8-entry tile scan (every warp, redundantly); publish aggregates ----
+  // ---- D: tile scan over the per-warp totals (every warp, redundantly); publish the tile aggregate at once ----
   int w_cnt_excl, w_bytes_excl = 0, tile_cnt, tb = 0;
   {
     const int c = lane < T_WARPS ? s_cnt[lane] : 0;
@@ -331,12 +307,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 6 : 3) filter_projec
       tb = __shfl_sync(0xffffffffu, bi, T_WARPS - 1);
     }
   }
-  if (warp == 1 && do_scout) {  // aggregate of the scouted tile (tile 0 is never scouted: scout >= 1)
-    const unsigned c = __reduce_add_sync(0xffffffffu, lane < T_WARPS ? (unsigned)s_scout_cnt[lane] : 0u);
-    const unsigned b = __reduce_add_sync(0xffffffffu, lane < T_WARPS ? (unsigned)s_scout_bytes[lane] : 0u);
-    if (lane == 0) st_volatile_u64(P.desc + (size_t)stile * P.desc_stride, desc_pack(DESC_AGG, c, b));
-  }
-  if (!scouted && warp == 0 && lane == 0) st_volatile_u64(P.desc + (size_t)tile * P.desc_stride, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
+  if (warp == 0 && lane == 0) st_volatile_u64(P.desc + (size_t)tile * P.desc_stride, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
 
   // ---- E: compact the strings in shared memory at tile-local positions ----
   const int my_cnt_excl = w_cnt_excl + cnt_incl - cnt;
@@ -355,8 +326,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 6 : 3) filter_projec
         if ((flags >> j) & 1) smem_copy(out_bytes + lpos[j], in_bytes + (off[j] - base), off[j + 1] - off[j]);
     }
   }
-  // ---- F: classic decoupled look-back for the unscouted head of the batch (warp 0) ----
-  if (!scouted && warp == 0) {
+  // ---- F: decoupled look-back (warp 0) ----
+  if (warp == 0) {
     long long ex0, ex1;
     lookback_resolve(P.desc, P.desc_stride, tile, tile_cnt, tb, lane, &ex0, &ex1);
     if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
@@ -416,7 +387,6 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 6 : 3) filter_projec
 }  // namespace
 
 static std::atomic<double> g_avg_len_hint{12.8};
-static int g_scout_distance = [] { const char* e = getenv("ARK_FP_SCOUT"); return e ? atoi(e) : 0; }();
 void filter_project_tma_note_avg_len(double avg) { if (avg > 0) g_avg_len_hint.store(avg); }
 static int g_fp_threads = [] { const char* e = getenv("ARK_FP_THREADS"); return e && atoi(e) == 512 ? 512 : 256; }();
 static int g_desc_stride = [] { const char* e = getenv("ARK_FP_DESC_STRIDE"); int v = e ? atoi(e) : 4; return v >= 1 && v <= 16 ? v : 4; }();  // one descriptor per 32-byte sector
@@ -466,11 +436,11 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
   if (P.has_varlen) {
     // exact when the extent is known; otherwise the average selected-string length of the previous launch
     double avg = n_rows > 0 && data_bytes >= 0 ? (double)data_bytes / (double)n_rows : g_avg_len_hint.load();
-    cap = (int)round_up((int64_t)(avg * TT * 1.25) + 64, 2048);
+    static const double slack = [] { const char* e = getenv("ARK_FP_CAP_SLACK"); return e ? atof(e) : 1.0625; }();
+    cap = (int)round_up((int64_t)(avg * TT * slack) + 64, 1024);
     cap = std::max(4096, std::min(cap, (TT / 1024) * 24 * 1024));
   }
   P.str_cap = cap;
-  P.scout = g_scout_distance;
   P.desc_stride = g_desc_stride;
   const size_t smem = P.has_varlen ? 2 * (size_t)(cap + 32) : 0;
   const int max_smem = 2 * (48 * 1024 + 32);
