@@ -5,8 +5,8 @@
 // (third-party; reached from crates/arkflow-plugin/src/processor/sql.rs:126-129).  The same kernel
 // runs the *final* merge of partial states on the multi-GPU path (sum of sums / counts, min of mins).
 //
-// Table: keys[capacity] of 16-byte Key16 claimed with a single 128-bit CAS (ATOMG.CAS.128), one
-// u64 accumulator array per aggregate updated with fire-and-forget RED atomics; a warp whose
+// Table: slots of {Key16, accumulators…} (32 B for ≤ 2 accumulators: ONE L2 sector per group); the key
+// is claimed with a single 128-bit CAS (ATOMG.CAS.128), accumulators take fire-and-forget RED atomics; a warp whose
 // lanes all hit the same group reduces with shuffles first (global aggregates, hot keys).
 // Algorithmic traffic = key + argument bytes read once (24 B/row for config 3).
 #include <cub/device/device_scan.cuh>
@@ -41,17 +41,25 @@ __device__ __forceinline__ long long warp_max_ll(long long v) {
   return v;
 }
 
-__global__ void agg_init_kernel(Key16* keys, unsigned long long capacity, int n_acc, AccParam a0, AccParam a1, AccParam a2,
+__device__ __forceinline__ Key16* slot_key(uint8_t* table, unsigned long long slot, int stride) {
+  return reinterpret_cast<Key16*>(table + slot * (unsigned long long)stride);
+}
+__device__ __forceinline__ const Key16* slot_key(const uint8_t* table, unsigned long long slot, int stride) {
+  return reinterpret_cast<const Key16*>(table + slot * (unsigned long long)stride);
+}
+
+__global__ void agg_init_kernel(uint8_t* table, unsigned long long capacity, int stride, int n_acc, AccParam a0, AccParam a1, AccParam a2,
                                 AccParam a3, AccParam a4, AccParam a5, AccParam a6, AccParam a7) {
   const AccParam accs[AGG_MAX_ACC] = {a0, a1, a2, a3, a4, a5, a6, a7};
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
        i += (unsigned long long)gridDim.x * blockDim.x) {
-    keys[i] = Key16{KEY_EMPTY, KEY_EMPTY};
+    uint8_t* s = table + i * (unsigned long long)stride;
+    *reinterpret_cast<Key16*>(s) = Key16{KEY_EMPTY, KEY_EMPTY};
     for (int a = 0; a < n_acc; ++a) {
       unsigned long long init = 0;
       if (accs[a].kind == ACC_MIN_I64 || accs[a].kind == ACC_MIN_F64) init = 0x7FFFFFFFFFFFFFFFull;
       if (accs[a].kind == ACC_MAX_I64 || accs[a].kind == ACC_MAX_F64) init = 0x8000000000000000ull;
-      accs[a].acc[i] = init;
+      *reinterpret_cast<unsigned long long*>(s + accs[a].acc_offset) = init;
     }
   }
 }
@@ -69,7 +77,7 @@ __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_cons
     // a global aggregate always yields one row, even when no row survives the filter
     Key16 mine; unsigned long long h;
     make_key(KEY_NONE, kc, 0, &mine, &h);
-    Key16 cur = cas128(P.keys + (h & P.mask), Key16{KEY_EMPTY, KEY_EMPTY}, mine);
+    Key16 cur = cas128(slot_key(P.table, h & P.mask, P.slot_stride), Key16{KEY_EMPTY, KEY_EMPTY}, mine);
     if (cur.hi == KEY_EMPTY && cur.lo == KEY_EMPTY) atomicAdd(P.group_count, 1u);
   }
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
@@ -93,9 +101,9 @@ __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_cons
       slot = h & P.mask;
       int probes = 0;
       while (true) {
-        Key16 cur = ld128(P.keys + slot);
+        Key16 cur = ld128(slot_key(P.table, slot, P.slot_stride));
         if (cur.hi == KEY_EMPTY) {
-          cur = cas128(P.keys + slot, Key16{KEY_EMPTY, KEY_EMPTY}, mine);
+          cur = cas128(slot_key(P.table, slot, P.slot_stride), Key16{KEY_EMPTY, KEY_EMPTY}, mine);
           if (cur.hi == KEY_EMPTY && cur.lo == KEY_EMPTY) {  // claimed
             const unsigned g = atomicAdd(P.group_count, 1u);
             if (g >= P.max_groups) atomicExch(P.overflow, 1);
@@ -119,9 +127,9 @@ __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_cons
       bool valid = ok;
       if (ok && A.kind != ACC_COUNT_STAR) {
         if (A.arg_prog >= 0) { VmVal v = vm_eval(P.progs[A.arg_prog], P.cols, row, &err); bits = v.bits; valid = v.valid; }
-        else { const ColView& c = P.cols[A.arg_slot]; valid = col_valid(c, row); bits = valid ? ((const unsigned long long*)c.data)[row] : 0; }
+        else { const ColView& c = P.cols[A.arg_slot]; valid = col_valid(c, row); bits = valid ? __ldcs((const unsigned long long*)c.data + row) : 0; }
       }
-      unsigned long long* dst = A.acc + (uniform ? slot0 : slot);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.table + (uniform ? slot0 : slot) * (unsigned long long)P.slot_stride + A.acc_offset);
       switch (A.kind) {
         case ACC_COUNT_STAR:
         case ACC_COUNT: {
@@ -159,11 +167,11 @@ __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_cons
 }
 
 // ---- table → dense group list, ordered by partition = hash(key) mod n_parts -----------------------
-__global__ void agg_count_parts_kernel(const Key16* keys, unsigned long long capacity, ColView kc, int key_kind, int n_parts,
+__global__ void agg_count_parts_kernel(const uint8_t* table, int stride, unsigned long long capacity, ColView kc, int key_kind, int n_parts,
                                        unsigned int* part_counts) {
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
        i += (unsigned long long)gridDim.x * blockDim.x) {
-    Key16 k = keys[i];
+    Key16 k = *slot_key(table, i, stride);
     if (k.hi == KEY_EMPTY) continue;
     const int p = n_parts > 1 ? partition_of(key_kind == KEY_NONE ? 0 : stored_key_hash(k, kc), n_parts) : 0;
     atomicAdd(part_counts + p, 1u);
@@ -171,32 +179,32 @@ __global__ void agg_count_parts_kernel(const Key16* keys, unsigned long long cap
 }
 
 // part_cursor[p] starts at the exclusive prefix of part_counts; slots[] receives table slot ids
-__global__ void agg_compact_kernel(const Key16* keys, unsigned long long capacity, ColView kc, int key_kind, int n_parts,
+__global__ void agg_compact_kernel(const uint8_t* table, int stride, unsigned long long capacity, ColView kc, int key_kind, int n_parts,
                                    unsigned int* part_cursor, unsigned int* slots) {
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
        i += (unsigned long long)gridDim.x * blockDim.x) {
-    Key16 k = keys[i];
+    Key16 k = *slot_key(table, i, stride);
     if (k.hi == KEY_EMPTY) continue;
     const int p = n_parts > 1 ? partition_of(key_kind == KEY_NONE ? 0 : stored_key_hash(k, kc), n_parts) : 0;
     slots[atomicAdd(part_cursor + p, 1u)] = (unsigned int)i;
   }
 }
 
-__global__ void agg_key_lengths_kernel(const Key16* keys, const unsigned int* slots, unsigned int n_groups, int32_t* lens) {
+__global__ void agg_key_lengths_kernel(const uint8_t* table, int stride, const unsigned int* slots, unsigned int n_groups, int32_t* lens) {
   unsigned int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_groups) return;
-  Key16 k = keys[slots[g]];
+  Key16 k = *slot_key(table, slots[g], stride);
   const unsigned tag = (unsigned)(k.hi >> 32);
   lens[g] = tag == KEYTAG_NULL ? 0 : (int32_t)(tag & 0x7FFFFFFFu);
 }
 
 // materialise the key column of the dense group list
-__global__ void agg_emit_keys_kernel(const Key16* keys, const unsigned int* slots, unsigned int n_groups, ColView kc, int key_kind,
+__global__ void agg_emit_keys_kernel(const uint8_t* table, int stride, const unsigned int* slots, unsigned int n_groups, ColView kc, int key_kind,
                                      unsigned long long* out_fixed, uint8_t* out_bool_bytes, const int32_t* out_offsets,
                                      uint8_t* out_bytes, uint8_t* out_valid_bytes) {
   unsigned int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_groups) return;
-  Key16 k = keys[slots[g]];
+  Key16 k = *slot_key(table, slots[g], stride);
   const unsigned tag = (unsigned)(k.hi >> 32);
   const bool is_null = tag == KEYTAG_NULL;
   if (out_valid_bytes) out_valid_bytes[g] = !is_null;
@@ -215,10 +223,10 @@ __global__ void agg_emit_keys_kernel(const Key16* keys, const unsigned int* slot
 }
 
 // dense accumulator columns: gather acc[slots[g]]
-__global__ void agg_gather_acc_kernel(const unsigned long long* acc, const unsigned int* slots, unsigned int n_groups,
+__global__ void agg_gather_acc_kernel(const uint8_t* table, int stride, int acc_offset, const unsigned int* slots, unsigned int n_groups,
                                       unsigned long long* out) {
   unsigned int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < n_groups) out[g] = acc[slots[g]];
+  if (g < n_groups) out[g] = *reinterpret_cast<const unsigned long long*>(table + (unsigned long long)slots[g] * stride + acc_offset);
 }
 
 enum FinalOp : int32_t { FIN_COPY = 0, FIN_AVG = 1, FIN_F64_KEY_BACK = 2, FIN_CONST = 3 };
@@ -283,8 +291,9 @@ struct AggOutput {  // one aggregate of the SELECT list expressed over accumulat
 struct DenseGroups {  // result of the hash pass: dense arrays of G groups, partition-ordered
   unsigned int n_groups = 0;
   std::vector<int64_t> part_rows;
-  BufferPtr keys, slots;                 // table + dense slot list
-  std::vector<BufferPtr> acc_tables;     // per accumulator, table-indexed
+  BufferPtr table, slots;                // table + dense slot list
+  int stride = 32;
+  std::vector<int> acc_offsets;
   unsigned long long capacity = 0;
 };
 
@@ -299,8 +308,10 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
   BufferPtr hctl = pinned_alloc(256);
   if (n_parts > 32) fail(ARK_ERR_UNSUPPORTED, "more than 32 partitions");
   while (true) {
-    dg.keys = device_alloc((size_t)capacity * sizeof(Key16));
-    dg.acc_tables.clear();
+    const int stride = 32 * (int)ceil_div(16 + 8 * (int64_t)ex.accs.size(), 32);
+    dg.stride = stride;
+    dg.table = device_alloc((size_t)capacity * stride);
+    dg.acc_offsets.clear();
     AggParams P;
     memset(&P, 0, sizeof P);
     P.n_rows = n;
@@ -311,23 +322,23 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     for (size_t s = 0; s < plan.used_cols.size(); ++s) P.cols[s] = in.cols[plan.used_cols[s]].view();
     P.n_acc = (int)ex.accs.size();
     for (size_t a = 0; a < ex.accs.size(); ++a) {
-      BufferPtr t = device_alloc((size_t)capacity * 8);
-      dg.acc_tables.push_back(t);
+      dg.acc_offsets.push_back(16 + 8 * (int)a);
       P.accs[a].kind = ex.accs[a].kind; P.accs[a].arg_slot = ex.accs[a].arg_slot; P.accs[a].arg_prog = ex.accs[a].arg_prog;
-      P.accs[a].arg_is_f64 = ex.accs[a].arg_is_f64; P.accs[a].acc = (unsigned long long*)t.get();
+      P.accs[a].arg_is_f64 = ex.accs[a].arg_is_f64; P.accs[a].acc_offset = 16 + 8 * (int)a;
     }
     for (size_t i = 0; i < ex.progs.size(); ++i) P.progs[i] = ex.progs[i];
-    P.keys = (Key16*)dg.keys.get();
+    P.table = (uint8_t*)dg.table.get();
+    P.slot_stride = stride;
     P.mask = capacity - 1;
     P.group_count = (unsigned int*)ctl.get();
     P.overflow = (int32_t*)((char*)ctl.get() + 4);
     P.error = (int32_t*)((char*)ctl.get() + 8);
-    P.max_groups = (unsigned int)std::min<unsigned long long>(capacity / 2, 0x7FFFFFFFull);
+    P.max_groups = (unsigned int)std::min<unsigned long long>(capacity - capacity / 4, 0x7FFFFFFFull);  // retry above load 0.75
     ARK_CUDA(cudaMemsetAsync(ctl.get(), 0, 256, stream));
     {
       KernelTimer t("agg_init_kernel", stream);
       const int grid = (int)std::min<unsigned long long>((capacity + 255) / 256, 148ull * 8);
-      agg_init_kernel<<<grid, 256, 0, stream>>>(P.keys, capacity, P.n_acc, P.accs[0], P.accs[1], P.accs[2], P.accs[3], P.accs[4],
+      agg_init_kernel<<<grid, 256, 0, stream>>>(P.table, capacity, stride, P.n_acc, P.accs[0], P.accs[1], P.accs[2], P.accs[3], P.accs[4],
                                                 P.accs[5], P.accs[6], P.accs[7]);
     }
     {
@@ -351,9 +362,10 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
                                        (err == VMERR_DIV_ZERO ? "Arrow error: Divide by zero error" : "Arrow error: arithmetic/cast error"));
     dg.n_groups = groups;
     dg.capacity = capacity;
-    // next batch: size for 4× the groups just seen (load ≤ 0.25), at least 2^12
+    // next batch: the smallest power of two ≥ 2× the groups just seen (load ≤ 0.5), at least 2^12, so that
+    // the table of config 3 (10^6 keys × 32-byte slots = 64 MB) stays inside the 126 MB L2
     unsigned long long want = 1ull << 12;
-    while (want < 4ull * groups) want <<= 1;
+    while (want < 2ull * groups) want <<= 1;
     g_capacity_hint.store(want);
     break;
   }
@@ -367,7 +379,7 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
   if (n_parts > 1) {
     {
       KernelTimer t("agg_count_parts_kernel", stream);
-      agg_count_parts_kernel<<<sgrid, 256, 0, stream>>>((const Key16*)dg.keys.get(), dg.capacity, kc, ex.key_kind, n_parts, part_counts);
+      agg_count_parts_kernel<<<sgrid, 256, 0, stream>>>((const uint8_t*)dg.table.get(), dg.stride, dg.capacity, kc, ex.key_kind, n_parts, part_counts);
     }
     ARK_CUDA(cudaMemcpyAsync((char*)hctl.get() + 16, part_counts, 128, cudaMemcpyDeviceToHost, stream));
     ARK_CUDA(cudaStreamSynchronize(stream));
@@ -381,7 +393,7 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
   }
   if (dg.n_groups > 0) {
     KernelTimer t("agg_compact_kernel", stream);
-    agg_compact_kernel<<<sgrid, 256, 0, stream>>>((const Key16*)dg.keys.get(), dg.capacity, kc, ex.key_kind, n_parts, part_cursor,
+    agg_compact_kernel<<<sgrid, 256, 0, stream>>>((const uint8_t*)dg.table.get(), dg.stride, dg.capacity, kc, ex.key_kind, n_parts, part_cursor,
                                                   (unsigned int*)dg.slots.get());
   }
   ARK_CUDA(cudaGetLastError());
@@ -398,14 +410,15 @@ static Column emit_key_column(const AggExec& ex, const DenseGroups& dg, const Co
   const bool may_null = src.validity != nullptr;
   BufferPtr valid_bytes = may_null ? device_alloc(std::max<size_t>(G, 1)) : BufferPtr();
   const unsigned grid = (unsigned)ceil_div(std::max<unsigned int>(G, 1), 256);
-  const Key16* keys = (const Key16*)dg.keys.get();
+  const uint8_t* keys = (const uint8_t*)dg.table.get();
+  const int kstride = dg.stride;
   const unsigned int* slots = (const unsigned int*)dg.slots.get();
   if (ex.key_kind == KEY_BYTES) {
     BufferPtr lens = device_alloc((size_t)(G + 1) * 4), offs = device_alloc((size_t)(G + 1) * 4);
     ARK_CUDA(cudaMemsetAsync(lens.get(), 0, (size_t)(G + 1) * 4, stream));
     if (G) {
       KernelTimer t("agg_key_lengths_kernel", stream);
-      agg_key_lengths_kernel<<<grid, 256, 0, stream>>>(keys, slots, G, (int32_t*)lens.get());
+      agg_key_lengths_kernel<<<grid, 256, 0, stream>>>(keys, kstride, slots, G, (int32_t*)lens.get());
     }
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (int32_t*)lens.get(), (int32_t*)offs.get(), (int)(G + 1), stream);
@@ -419,7 +432,7 @@ static Column emit_key_column(const AggExec& ex, const DenseGroups& dg, const Co
     BufferPtr bytes = device_alloc((size_t)total + 16);
     if (G) {
       KernelTimer t("agg_emit_keys_kernel", stream);
-      agg_emit_keys_kernel<<<grid, 256, 0, stream>>>(keys, slots, G, kc, ex.key_kind, nullptr, nullptr, (const int32_t*)offs.get(),
+      agg_emit_keys_kernel<<<grid, 256, 0, stream>>>(keys, kstride, slots, G, kc, ex.key_kind, nullptr, nullptr, (const int32_t*)offs.get(),
                                                      (uint8_t*)bytes.get(), (uint8_t*)valid_bytes.get());
     }
     c.offsets = (const int32_t*)offs.get(); c.data = (const uint8_t*)bytes.get(); c.data_bytes = total; c.first_offset = 0;
@@ -428,7 +441,7 @@ static Column emit_key_column(const AggExec& ex, const DenseGroups& dg, const Co
     BufferPtr vals = device_alloc((size_t)std::max<unsigned int>(G, 1) * 8);
     if (G) {
       KernelTimer t("agg_emit_keys_kernel", stream);
-      agg_emit_keys_kernel<<<grid, 256, 0, stream>>>(keys, slots, G, kc, ex.key_kind, (unsigned long long*)vals.get(), nullptr, nullptr,
+      agg_emit_keys_kernel<<<grid, 256, 0, stream>>>(keys, kstride, slots, G, kc, ex.key_kind, (unsigned long long*)vals.get(), nullptr, nullptr,
                                                      nullptr, (uint8_t*)valid_bytes.get());
     }
     c.data = (const uint8_t*)vals.get(); c.data_bytes = (int64_t)G * 8; c.owners = {vals};
@@ -436,7 +449,7 @@ static Column emit_key_column(const AggExec& ex, const DenseGroups& dg, const Co
     BufferPtr bb = device_alloc(std::max<size_t>(G, 1)), bits = device_alloc((size_t)(G + 7) / 8 + 1);
     if (G) {
       KernelTimer t("agg_emit_keys_kernel", stream);
-      agg_emit_keys_kernel<<<grid, 256, 0, stream>>>(keys, slots, G, kc, ex.key_kind, nullptr, (uint8_t*)bb.get(), nullptr, nullptr,
+      agg_emit_keys_kernel<<<grid, 256, 0, stream>>>(keys, kstride, slots, G, kc, ex.key_kind, nullptr, (uint8_t*)bb.get(), nullptr, nullptr,
                                                      (uint8_t*)valid_bytes.get());
     }
     launch_pack_bits((const uint8_t*)bb.get(), G, (uint8_t*)bits.get(), nullptr, stream);
@@ -456,7 +469,7 @@ static BufferPtr gather_acc(const DenseGroups& dg, int acc, cudaStream_t stream)
   BufferPtr out = device_alloc((size_t)std::max<unsigned int>(G, 1) * 8);
   if (G) {
     KernelTimer t("agg_gather_acc_kernel", stream);
-    agg_gather_acc_kernel<<<(unsigned)ceil_div(G, 256), 256, 0, stream>>>((const unsigned long long*)dg.acc_tables[acc].get(),
+    agg_gather_acc_kernel<<<(unsigned)ceil_div(G, 256), 256, 0, stream>>>((const uint8_t*)dg.table.get(), dg.stride, dg.acc_offsets[acc],
                                                                          (const unsigned int*)dg.slots.get(), G, (unsigned long long*)out.get());
   }
   return out;

@@ -35,7 +35,8 @@ struct AccParam {
   int32_t arg_slot;    // column slot, or -1
   int32_t arg_prog;    // program index, or -1
   int32_t arg_is_f64;  // type of the argument value
-  unsigned long long* acc;  // [capacity]
+  int32_t acc_offset;  // byte offset of this accumulator inside a table slot
+  int32_t pad;
 };
 
 struct AggParams {
@@ -51,8 +52,10 @@ struct AggParams {
   AccParam accs[AGG_MAX_ACC];
   VmProgram pred;
   VmProgram progs[AGG_MAX_PROGS];
-  Key16* keys;               // [capacity]
+  uint8_t* table;            // [capacity] slots of slot_stride bytes: Key16 at +0, u64 accumulators at +16, +24, …
   unsigned long long mask;   // capacity - 1
+  int32_t slot_stride;       // 32 * ceil((16 + 8 n_acc) / 32): a slot never straddles a 32-byte sector boundary unevenly
+  int32_t pad2;
   unsigned int* group_count; // number of occupied slots
   unsigned int max_groups;   // load-factor limit; beyond it the kernel raises `overflow`
   int32_t* overflow;

@@ -43,11 +43,11 @@ static __device__ inline void make_key(int kind, const ColView& c, int64_t row, 
   if (kind == KEY_NONE) { k.lo = 0; k.hi = (unsigned long long)KEYTAG_INT << 32; *key = k; *hash = 0; return; }
   if (!col_valid(c, row)) { k.lo = 0; k.hi = (unsigned long long)KEYTAG_NULL << 32; *key = k; *hash = hash_key16(k); return; }
   if (kind == KEY_INT64) {
-    k.lo = ((const unsigned long long*)c.data)[row]; k.hi = (unsigned long long)KEYTAG_INT << 32;
+    k.lo = __ldcs((const unsigned long long*)c.data + row); k.hi = (unsigned long long)KEYTAG_INT << 32;  // streaming: keep L2 for the table
   } else if (kind == KEY_BOOL) {
     k.lo = bit_get((const uint8_t*)c.data, row + c.data_bit0); k.hi = (unsigned long long)KEYTAG_INT << 32;
   } else {
-    const int32_t o0 = c.offsets[row], o1 = c.offsets[row + 1];
+    const int32_t o0 = __ldcs(c.offsets + row), o1 = __ldcs(c.offsets + row + 1);
     const int len = o1 - o0;
     const uint8_t* p = (const uint8_t*)c.data + o0;
     if (len <= 12) {
@@ -56,7 +56,7 @@ static __device__ inline void make_key(int kind, const ColView& c, int64_t row, 
         const unsigned* q = (const unsigned*)p;
         for (int i = 0; i < 3; ++i) {
           const int rem = len - 4 * i;
-          if (rem >= 4) w[i] = q[i];
+          if (rem >= 4) w[i] = __ldcs(q + i);
           else if (rem > 0) { for (int b = 0; b < rem; ++b) w[i] |= (unsigned)p[4 * i + b] << (8 * b); }
         }
       } else {
