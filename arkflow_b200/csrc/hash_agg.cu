@@ -297,11 +297,13 @@ struct DenseGroups {  // result of the hash pass: dense arrays of G groups, part
   unsigned long long capacity = 0;
 };
 
+bool launch_hash_agg_tile(const AggParams& P, unsigned long long capacity, int64_t key_bytes, cudaStream_t stream);
+
 static std::atomic<unsigned long long> g_capacity_hint{1ull << 16};
 
 static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int n_parts, cudaStream_t stream) {
   const int64_t n = in.num_rows;
-  unsigned long long capacity = std::max<unsigned long long>(g_capacity_hint.load(), 1ull << 12);
+  unsigned long long capacity = std::max<unsigned long long>(g_capacity_hint.load(), 1ull << 10);
   const unsigned long long cap_limit = 1ull << 31;
   DenseGroups dg;
   BufferPtr ctl = device_alloc(256);  // [group_count u32 | overflow i32 | error i32 | pad | part_counts u32[32] | part_cursor u32[32]]
@@ -341,7 +343,10 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
       agg_init_kernel<<<grid, 256, 0, stream>>>(P.table, capacity, stride, P.n_acc, P.accs[0], P.accs[1], P.accs[2], P.accs[3], P.accs[4],
                                                 P.accs[5], P.accs[6], P.accs[7]);
     }
-    {
+    const int64_t key_bytes = ex.key_kind == KEY_BYTES ? in.cols[plan.used_cols[ex.key_slot]].data_bytes : 0;
+    if (n > 0 && launch_hash_agg_tile(P, capacity, key_bytes, stream)) {
+      // tiled kernel (TMA-staged keys, 4 rows per thread, privatised accumulators for small tables)
+    } else {
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, AGG_THREADS), 148 * 8));
       if (P.pred_kind == 0) launch_agg<0>(P, grid, stream);
       else if (P.pred_kind == 1) launch_agg<1>(P, grid, stream);
@@ -364,7 +369,7 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     dg.capacity = capacity;
     // next batch: the smallest power of two ≥ 2× the groups just seen (load ≤ 0.5), at least 2^12, so that
     // the table of config 3 (10^6 keys × 32-byte slots = 64 MB) stays inside the 126 MB L2
-    unsigned long long want = 1ull << 12;
+    unsigned long long want = 1ull << 10;
     while (want < 2ull * groups) want <<= 1;
     g_capacity_hint.store(want);
     break;

@@ -33,7 +33,7 @@ lib.ark_kernel_timing_enable(1)
 for i in range(reps):
     proc.process_device(bs[i % 3]).close()
 torch.cuda.synchronize()
-for name in (b"hash_agg_kernel", b"filter_project_tma_kernel", b"filter_project_kernel", b"agg_init_kernel", b"agg_compact_kernel"):
+for name in (b"hash_agg_kernel", b"hash_agg_tile_kernel", b"filter_project_tma_kernel", b"filter_project_kernel", b"agg_init_kernel", b"agg_compact_kernel"):
     ms, n = C.c_double(), C.c_int64()
     lib.ark_kernel_timing_get(name, C.byref(ms), C.byref(n))
     if n.value:
