@@ -173,6 +173,23 @@ static bool try_fast_filter(const Plan& plan, Batch& in, Batch& out, cudaStream_
   return true;
 }
 
+// CAST(Binary AS Utf8) columns: arrow-cast (safe = false) fails the query on invalid UTF-8.
+static void validate_utf8_outputs(const Plan& plan, Batch& out, cudaStream_t stream) {
+  bool any = false;
+  for (auto& oc : plan.outputs) any = any || oc.src.validate_utf8;
+  if (!any || out.num_rows == 0) return;
+  BufferPtr flag = device_alloc(16), h = pinned_alloc(16);
+  ARK_CUDA(cudaMemsetAsync(flag.get(), 0, 16, stream));
+  for (size_t i = 0; i < plan.outputs.size(); ++i) {
+    if (!plan.outputs[i].src.validate_utf8) continue;
+    const Column& c = out.cols[i];
+    launch_utf8_validate(c.offsets, c.data, c.validity, c.validity_bit0, c.length, (int*)flag.get(), stream);
+  }
+  ARK_CUDA(cudaMemcpyAsync(h.get(), flag.get(), 4, cudaMemcpyDeviceToHost, stream));
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  if (*(int*)h.get()) fail(ARK_ERR_PROCESS, "Collection query results error: Arrow error: Cast error: Cannot cast binary to string: invalid utf-8 sequence");
+}
+
 Batch run_filter_project(const Plan& plan, Batch& in, cudaStream_t stream) {
   const int64_t n = in.num_rows;
   Batch out;
@@ -196,6 +213,7 @@ Batch run_filter_project(const Plan& plan, Batch& in, cudaStream_t stream) {
   }
 
   if (try_fast_filter(plan, in, out, stream)) {
+    validate_utf8_outputs(plan, out, stream);
     if (plan.limit >= 0 && out.num_rows > plan.limit) {
       out.num_rows = plan.limit;
       for (auto& c : out.cols) { c.length = plan.limit; if (c.field.type == DType::Utf8 || c.field.type == DType::Binary) c.data_bytes = -1; }
@@ -337,6 +355,7 @@ Batch run_filter_project(const Plan& plan, Batch& in, cudaStream_t stream) {
     out.num_rows = count;
   }
 
+  validate_utf8_outputs(plan, out, stream);
   if (plan.limit >= 0 && out.num_rows > plan.limit) {
     // LIMIT k without ORDER BY on a single-partition scan: the first k surviving rows
     out.num_rows = plan.limit;

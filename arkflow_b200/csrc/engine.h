@@ -25,6 +25,7 @@ void resolve_varlen_extents(Batch& b, const std::vector<int>& col_idx, cudaStrea
 
 // kernels' host launchers
 void launch_filter_project(const FpParams& P, int pred_kind, cudaStream_t stream);
+void launch_utf8_validate(const int32_t* offsets, const uint8_t* data, const uint8_t* validity, int vbit0, int64_t n, int* bad, cudaStream_t stream);
 void launch_pack_bits(const uint8_t* bytes, int64_t n, uint8_t* bitmap, unsigned long long* zeros, cudaStream_t stream);
 
 struct Processor {

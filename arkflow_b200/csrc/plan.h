@@ -19,6 +19,7 @@ struct ValueSource {
   VmProgram prog{};     // Computed: result type = type
   DType type = DType::Null;
   bool nullable = true;
+  bool validate_utf8 = false;  // CAST(Binary AS Utf8): arrow-cast rejects invalid UTF-8 (safe = false)
 };
 
 struct OutputCol {

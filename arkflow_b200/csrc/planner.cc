@@ -275,8 +275,8 @@ struct Binder {
         return v;
       }
       if (from == DType::Binary && e.cast_to == DType::Utf8) {
-        // TODO(utf8): arrow-cast validates UTF-8 here; payloads produced by arrow_to_json are valid by construction
         v.kind = ValueSource::PassThrough; v.slot = slot_of(col); v.type = DType::Utf8; v.nullable = (*fields)[col].nullable;
+        v.validate_utf8 = true;  // checked on the surviving rows by utf8_validate_kernel
         return v;
       }
     }

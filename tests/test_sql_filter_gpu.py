@@ -230,3 +230,19 @@ def test_missing_config(gpu):
     with pytest.raises(ArkError) as e:
         SqlProcessor(None)
     assert e.value.kind == "Config"
+
+
+def test_cast_binary_to_string_validates_utf8(gpu):
+    # examples/generate_example.yaml:30 — second sql of the shipped pipeline
+    rb = pa.record_batch({"__value__": pa.array([b'{"sum(flow.value)":10}', "héllo 漢".encode(), b""], pa.binary()),
+                          "x": pa.array([1, 2, 3], pa.int64())})
+    out = check(rb, "SELECT *,cast( __value__  as string) as y FROM flow ")
+    assert out.schema.names == ["__value__", "x", "y"] and out.schema.field("y").type == pa.utf8()
+    bad = pa.record_batch({"__value__": pa.array([b"ok", b"\xff\xfe", b"\xed\xa0\x80", b"\xc0\xaf", b"\xe2\x82"], pa.binary()),
+                           "i": pa.array(range(5), pa.int64())})
+    for q in ("SELECT cast(__value__ as string) AS y FROM flow", "SELECT cast(__value__ as string) AS y FROM flow WHERE i >= 2"):
+        with pytest.raises(ArkError) as e:
+            run(bad, q)
+        assert e.value.kind == "Process" and "utf-8" in e.value.message.lower()
+    # rows removed by the filter are not validated (FilterExec runs before the projection)
+    check(bad, "SELECT cast(__value__ as string) AS y FROM flow WHERE i < 1")
