@@ -283,6 +283,30 @@ int ark_json_to_arrow_process_device(ark_proc_t* p, ArrowDeviceArray* in, ArrowS
   });
 }
 
+int ark_arrow_to_json_create(const char* config_json, ark_proc_t** out) {
+  return guarded([&] {
+    if (!out) fail(ARK_ERR_PROCESS, "null output handle");
+    *out = nullptr;
+    auto p = make_arrow_to_json(config_json);
+    auto* h = new ark_proc();
+    h->impl = std::move(p);
+    *out = h;
+  });
+}
+
+int ark_arrow_to_json_process(ark_proc_t* p, ArrowArray* in, ArrowSchema* in_schema, ArrowArray* out, ArrowSchema* out_schema) {
+  BufferPtr in_owner = adopt_array(in);
+  return guarded([&] {
+    if (!p || !p->impl || strcmp(p->impl->type(), "arrow_to_json") != 0) fail(ARK_ERR_PROCESS, "handle is not an arrow_to_json processor");
+    const ArrowArray* arr = (const ArrowArray*)in_owner.get();
+    if (!arr) fail(ARK_ERR_PROCESS, "input array already released");
+    StreamLease lease;
+    Batch b = import_host(arr, in_schema, nullptr, lease.s);
+    Batch r = arrow_to_json_device(*p->impl, b, lease.s);
+    export_host(r, lease.s, out, out_schema);
+  });
+}
+
 int ark_proc_close(ark_proc_t*) { return ARK_OK; }  // Processor::close is a no-op in the reference (sql.rs:222-224)
 
 void ark_proc_destroy(ark_proc_t* p) { delete p; }

@@ -68,6 +68,8 @@ const std::string& json_to_arrow_value_field(const Processor& p);
 Batch json_to_arrow_device(const Processor& proc, Batch& in, cudaStream_t stream);
 Batch hash_partition(Batch& in, const std::string& key_column, int n_parts, std::vector<int64_t>& part_rows, cudaStream_t stream);
 Column take_column(const Column& src, const unsigned int* idx, int64_t n, const std::string& name, cudaStream_t stream);
+std::unique_ptr<Processor> make_arrow_to_json(const char* config_json);
+Batch arrow_to_json_device(const Processor& proc, Batch& in, cudaStream_t stream);
 Batch concat_device(std::vector<Batch>& ins, cudaStream_t stream);
 Batch synth_batch(int64_t n, int64_t row0, uint64_t seed, int value_kind, int64_t key_space, cudaStream_t stream);
 

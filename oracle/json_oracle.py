@@ -148,3 +148,75 @@ def json_to_arrow(rb: pa.RecordBatch, value_field: str = "__value__", fields_to_
                 raise OracleError("Process", "Arrow JSON Reader Error: Json error: expected null")
     arrays = [pa.array(cols[k], type=t) for k, t in fields]
     return pa.RecordBatch.from_arrays(arrays, schema=pa.schema([pa.field(k, t, True) for k, t in fields]))
+
+
+# ------------------------------------------------------------------------------------------------
+# arrow_to_json  (crates/arkflow-plugin/src/processor/json.rs:78-113 + core/lib.rs:280-302)
+# ------------------------------------------------------------------------------------------------
+def _lexical_f64(x: float) -> str:
+    """lexical-core's default float text (arrow-json 55.2 writes finite f64 through lexical_core::write):
+    shortest round-trip digits (= Python repr digits); positional with at least ".0" while the
+    scientific exponent is in [-5, 9], d.ddde±x otherwise."""
+    import math
+
+    if math.isnan(x) or math.isinf(x):
+        return "null"
+    if x == 0:
+        return "-0.0" if math.copysign(1.0, x) < 0 else "0.0"
+    r = repr(abs(x))
+    mant, _, ex = r.partition("e")
+    ip, _, fp = mant.partition(".")
+    digits = (ip + fp).lstrip("0")
+    e10 = (int(ex) if ex else 0) - len(fp)
+    stripped = digits.rstrip("0")
+    e10 += len(digits) - len(stripped)
+    ds = stripped
+    sci = e10 + len(ds) - 1
+    if -5 <= sci <= 9:
+        if e10 >= 0:
+            s = ds + "0" * e10 + ".0"
+        elif -e10 < len(ds):
+            s = ds[: len(ds) + e10] + "." + ds[len(ds) + e10:]
+        else:
+            s = "0." + "0" * (-e10 - len(ds)) + ds
+    else:
+        s = ds[0] + "." + (ds[1:] if len(ds) > 1 else "0") + "e" + str(sci)
+    return ("-" if x < 0 else "") + s
+
+
+def arrow_to_json_lines(rb: pa.RecordBatch, fields_to_include: Optional[set] = None) -> list[bytes]:
+    """LineDelimitedWriter with default options: schema order, NULL fields omitted, no whitespace."""
+    names = [n for n in rb.schema.names if fields_to_include is None or n in fields_to_include]
+    cols = [(n, rb.column(rb.schema.names.index(n))) for n in names]
+    lines = []
+    for i in range(rb.num_rows):
+        parts = []
+        for n, c in cols:
+            v = c[i]
+            if not v.is_valid or c.type == pa.null():
+                continue
+            key = json.dumps(n, ensure_ascii=False)
+            if c.type == pa.int64():
+                val = str(v.as_py())
+            elif c.type == pa.float64():
+                val = _lexical_f64(v.as_py())
+            elif c.type == pa.bool_():
+                val = "true" if v.as_py() else "false"
+            elif c.type == pa.utf8():
+                val = json.dumps(v.as_py(), ensure_ascii=False)
+            elif c.type == pa.binary():
+                val = '"' + v.as_py().hex() + '"'
+            else:
+                raise OracleError("Unsupported", f"arrow_to_json of {c.type}")
+            parts.append(f"{key}:{val}")
+        lines.append(("{" + ",".join(parts) + "}").encode("utf-8"))
+    return lines
+
+
+def arrow_to_json(rb: pa.RecordBatch, fields_to_include: Optional[set] = None) -> pa.RecordBatch:
+    """ArrowToJsonProcessor::process: the original columns + a non-null Binary `__value__` column."""
+    lines = arrow_to_json_lines(rb, fields_to_include)
+    if len(lines) != rb.num_rows:
+        raise OracleError("Process", "Creating an Arrow record batch failed")
+    fields = list(rb.schema) + [pa.field("__value__", pa.binary(), nullable=False)]
+    return pa.RecordBatch.from_arrays(list(rb.columns) + [pa.array(lines, pa.binary())], schema=pa.schema(fields))
