@@ -292,7 +292,8 @@ Batch arrow_to_json_device(const Processor& proc, Batch& in, cudaStream_t stream
   memset(&P, 0, sizeof P);
   P.n_rows = n;
   for (auto& c : in.cols) {
-    if (!c.present) fail(ARK_ERR_UNSUPPORTED, "arrow_to_json: column '" + c.field.name + "' has Arrow type '" + c.field.format + "'");
+    if (!c.present && c.field.format != "n") fail(ARK_ERR_UNSUPPORTED, "arrow_to_json: column '" + c.field.name + "' has Arrow type '" + c.field.format + "'");
+    if (c.field.format == "n") continue;  // Null-typed column: never emitted
     if (ap.has_include && std::find(ap.include.begin(), ap.include.end(), c.field.name) == ap.include.end()) continue;  // filter_columns, lib.rs:304-328
     if (P.n_cols == AJ_MAX_COLS) fail(ARK_ERR_UNSUPPORTED, "arrow_to_json: more than 16 columns");
     const std::string key = json_escape_key(c.field.name);
