@@ -73,10 +73,24 @@ KernelTimer::~KernelTimer() {
   }
 }
 
+// ---- device binding ---------------------------------------------------------------------------------
+// One process drives one GPU (ark_b200_init).  CUDA's "current device" is per host thread and defaults
+// to 0, so worker threads that never called cudaSetDevice (tokio blocking threads, Python thread pools)
+// are re-bound to the library's device on entry.
+static std::atomic<int> g_device{-1};
+void bind_device(int device) { g_device.store(device); }
+void ensure_device() {
+  const int want = g_device.load(std::memory_order_relaxed);
+  if (want < 0) return;
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur != want) cudaSetDevice(want);
+}
+
 // ---- pools ------------------------------------------------------------------------------------------
 BlockPool::~BlockPool() {}  // process teardown: the driver reclaims; freeing here races CUDA shutdown
 
 void* BlockPool::alloc(size_t bytes) {
+  ensure_device();
   if (bytes == 0) bytes = 1;
   size_t want = (size_t)round_up((int64_t)bytes, kind_ == Device ? 512 : 4096);
   {
@@ -139,6 +153,7 @@ BufferPtr pinned_alloc(size_t bytes) {
 static std::mutex g_stream_mu;
 static std::vector<cudaStream_t> g_streams;
 StreamLease::StreamLease() {
+  ensure_device();
   {
     std::lock_guard<std::mutex> l(g_stream_mu);
     if (!g_streams.empty()) { s = g_streams.back(); g_streams.pop_back(); return; }

@@ -58,6 +58,7 @@ int ark_b200_init(int device) {
     ARK_CUDA(cudaGetDevice(&dev));
     ARK_CUDA(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10) fail(ARK_ERR_CUDA, std::string("arkflow_b200 is built for sm_100a; found ") + prop.name);
+    bind_device(dev);
   });
 }
 

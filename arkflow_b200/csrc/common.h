@@ -42,6 +42,9 @@ struct KernelTimer {  // RAII: records CUDA events around one launch when timing
   cudaEvent_t e0 = nullptr, e1 = nullptr;
 };
 
+void bind_device(int device);   // remembered by ark_b200_init
+void ensure_device();           // re-binds the calling host thread to that device
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_cons
       const int leader = __ffs(m) - 1;
       const unsigned long long slot0 = __shfl_sync(0xffffffffu, slot[r], leader);
       const bool uniform = __all_sync(0xffffffffu, !ok[r] || slot[r] == slot0) && __popc(m) > 1;
-      for (int a = 0; a < P.n_acc; ++a) {
+      for (int a = 0; a < P.n_acc - P.pad; ++a) {
         const AccParam& A = P.accs[a];
         unsigned long long bits = 0;
         bool valid = ok[r];
@@ -394,6 +394,7 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     for (size_t i = 0; i < ex.progs.size(); ++i) P.progs[i] = ex.progs[i];
     P.table = (uint8_t*)dg.table.get();
     P.slot_stride = stride;
+    { const char* e = getenv("ARK_AGG_DEBUG_SKIP_ACC"); P.pad = e ? atoi(e) : 0; }  // experiment only: skip the last k accumulators
     P.mask = capacity - 1;
     P.group_count = (unsigned int*)ctl.get();
     P.overflow = (int32_t*)((char*)ctl.get() + 4);
