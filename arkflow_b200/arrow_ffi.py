@@ -153,6 +153,9 @@ class DeviceBatch:
         and re-armed on every export (the callee's release only drops our keep-alive tokens)."""
         import torch
 
+        # the library runs on its own streams: whatever torch / NCCL queued on the current stream to
+        # produce these tensors must have completed before the pointers are handed over
+        torch.cuda.current_stream().synchronize()
         cache = getattr(self, "_export_cache", None)
         if cache is None:
             n = len(self.columns)
