@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_cons
       const int leader = __ffs(m) - 1;
       const unsigned long long slot0 = __shfl_sync(0xffffffffu, slot[r], leader);
       const bool uniform = __all_sync(0xffffffffu, !ok[r] || slot[r] == slot0) && __popc(m) > 1;
-      for (int a = 0; a < P.n_acc - P.pad; ++a) {
+      for (int a = 0; a < P.n_acc; ++a) {
         const AccParam& A = P.accs[a];
         unsigned long long bits = 0;
         bool valid = ok[r];
@@ -272,7 +272,7 @@ __global__ void agg_finalize_kernel(int op, const unsigned long long* a, const u
 
 template <int PRED>
 void launch_agg(const AggParams& P, int64_t n, cudaStream_t stream) {
-  static const int rows_per_thread = [] { const char* e = getenv("ARK_AGG_R"); int v = e ? atoi(e) : 4; return v == 1 || v == 2 || v == 4 ? v : 4; }();
+  static const int rows_per_thread = [] { const char* e = getenv("ARK_AGG_R"); int v = e ? atoi(e) : 1; return v == 1 || v == 2 || v == 4 ? v : 1; }();  // measured at 10^6 groups: R=1 0.97 ms, R=2 1.03, R=4 1.20
   KernelTimer t("hash_agg_kernel", stream);
   const int R = PRED == 2 ? 1 : rows_per_thread;  // the VM path keeps its register file small
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, (int64_t)AGG_THREADS * R), 148 * 8));
@@ -326,6 +326,8 @@ struct DenseGroups {  // result of the hash pass: dense arrays of G groups, part
 };
 
 bool launch_hash_agg_tile(const AggParams& P, unsigned long long capacity, int64_t key_bytes, cudaStream_t stream);
+bool launch_hash_agg_radix(const AggParams& P, unsigned long long capacity, int32_t* skew_dev, std::vector<BufferPtr>* keep, cudaStream_t stream);
+void hash_agg_radix_note_skew();
 
 // RAII: cudaAccessPolicyWindow (persisting) over [ptr, ptr+bytes) on `stream`, cleared on destruction.
 struct L2Window {
@@ -369,8 +371,9 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
   unsigned long long capacity = std::max<unsigned long long>(g_capacity_hint.load(), 1ull << 10);
   const unsigned long long cap_limit = 1ull << 31;
   DenseGroups dg;
-  BufferPtr ctl = device_alloc(256);  // [group_count u32 | overflow i32 | error i32 | pad | part_counts u32[32] | part_cursor u32[32]]
-  BufferPtr hctl = pinned_alloc(256);
+  BufferPtr ctl = device_alloc(512);  // [group_count u32 | overflow i32 | error i32 | skew i32 | part_counts u32[32] | part_cursor u32[32]]
+  BufferPtr hctl = pinned_alloc(512);
+  bool allow_radix = true;
   if (n_parts > 32) fail(ARK_ERR_UNSUPPORTED, "more than 32 partitions");
   while (true) {
     const int stride = 32 * (int)ceil_div(16 + 8 * (int64_t)ex.accs.size(), 32);
@@ -394,14 +397,16 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     for (size_t i = 0; i < ex.progs.size(); ++i) P.progs[i] = ex.progs[i];
     P.table = (uint8_t*)dg.table.get();
     P.slot_stride = stride;
-    { const char* e = getenv("ARK_AGG_DEBUG_SKIP_ACC"); P.pad = e ? atoi(e) : 0; }  // experiment only: skip the last k accumulators
     P.mask = capacity - 1;
     P.group_count = (unsigned int*)ctl.get();
     P.overflow = (int32_t*)((char*)ctl.get() + 4);
     P.error = (int32_t*)((char*)ctl.get() + 8);
     P.max_groups = (unsigned int)std::min<unsigned long long>(capacity - capacity / 4, 0x7FFFFFFFull);  // retry above load 0.75
-    ARK_CUDA(cudaMemsetAsync(ctl.get(), 0, 256, stream));
-    {
+    ARK_CUDA(cudaMemsetAsync(ctl.get(), 0, 512, stream));
+    // large tables: partition rows by table region, build each region in shared memory (hash_agg_radix.cu)
+    std::vector<BufferPtr> radix_keep;
+    const bool radix = allow_radix && n > 0 && launch_hash_agg_radix(P, capacity, (int32_t*)((char*)ctl.get() + 12), &radix_keep, stream);
+    if (!radix) {
       KernelTimer t("agg_init_kernel", stream);
       const int grid = (int)std::min<unsigned long long>((capacity + 255) / 256, 148ull * 8);
       agg_init_kernel<<<grid, 256, 0, stream>>>(P.table, capacity, stride, P.n_acc, P.accs[0], P.accs[1], P.accs[2], P.accs[3], P.accs[4],
@@ -415,7 +420,8 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     // serialise on L2 atomics: K = 2 → 12.3 ms vs 1.6 ms).  Large tables: measured 0.95 ms (row kernel) vs
     // 1.22 ms (tiled) at 10^6 keys — the row kernel keeps more independent probes in flight.
     static const bool tile_all = getenv("ARK_AGG_TILE") && atoi(getenv("ARK_AGG_TILE")) == 1;
-    if (n > 0 && (capacity <= 2048 || tile_all) && launch_hash_agg_tile(P, capacity, key_bytes, stream)) {
+    if (radix) {
+    } else if (n > 0 && (capacity <= 2048 || tile_all) && launch_hash_agg_tile(P, capacity, key_bytes, stream)) {
     } else {
       if (P.pred_kind == 0) launch_agg<0>(P, n, stream);
       else if (P.pred_kind == 1) launch_agg<1>(P, n, stream);
@@ -427,7 +433,12 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     const unsigned int groups = *(unsigned int*)hctl.get();
     const int overflow = *(int32_t*)((char*)hctl.get() + 4);
     const int err = *(int32_t*)((char*)hctl.get() + 8);
-    if (overflow) {
+    if (*(int32_t*)((char*)hctl.get() + 12)) {  // skewed keys overflowed a bucket's record array: same capacity, row kernel
+      hash_agg_radix_note_skew();
+      allow_radix = false;
+      continue;
+    }
+    if (overflow || groups > P.max_groups) {
       if (capacity >= cap_limit) fail(ARK_ERR_PROCESS, "Collection query results error: group-by hash table exceeded 2^31 slots");
       capacity *= 4;
       continue;

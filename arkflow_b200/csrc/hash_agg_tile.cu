@@ -15,6 +15,7 @@
 // Table layout, key format and CAS protocol are those of hash_agg.cu.
 #include <atomic>
 
+#include "agg_acc.cuh"
 #include "engine.h"
 #include "hash_agg.cuh"
 #include "hashkey.cuh"
@@ -69,35 +70,6 @@ __device__ __forceinline__ void make_key_smem(const uint8_t* p, int len, int64_t
     k.lo = (unsigned long long)row;
     k.hi = (unsigned long long)prefix | ((unsigned long long)(KEYTAG_LONG | (unsigned)len) << 32);
     *key = k; *hash = hash_bytes(p, len);
-  }
-}
-
-__device__ __forceinline__ unsigned long long acc_identity(int kind) {
-  if (kind == ACC_MIN_I64 || kind == ACC_MIN_F64) return 0x7FFFFFFFFFFFFFFFull;
-  if (kind == ACC_MAX_I64 || kind == ACC_MAX_F64) return 0x8000000000000000ull;
-  return 0;
-}
-
-// dst may be a global or a shared address (generic atomics)
-__device__ __forceinline__ void accumulate(int kind, int arg_is_f64, unsigned long long* dst, unsigned long long bits) {
-  switch (kind) {
-    case ACC_COUNT_STAR: case ACC_COUNT: atomicAdd(dst, 1ull); break;
-    case ACC_SUM_I64: atomicAdd(dst, bits); break;
-    case ACC_SUM_F64: atomicAdd(reinterpret_cast<double*>(dst), arg_is_f64 ? __longlong_as_double((long long)bits) : (double)(long long)bits); break;
-    case ACC_MIN_I64: atomicMin(reinterpret_cast<long long*>(dst), (long long)bits); break;
-    case ACC_MIN_F64: atomicMin(reinterpret_cast<long long*>(dst), f64_total_key(bits)); break;
-    case ACC_MAX_I64: atomicMax(reinterpret_cast<long long*>(dst), (long long)bits); break;
-    default: atomicMax(reinterpret_cast<long long*>(dst), f64_total_key(bits)); break;
-  }
-}
-
-// merge a privatised (shared-memory) accumulator into the table
-__device__ __forceinline__ void merge_acc(int kind, unsigned long long* dst, unsigned long long v) {
-  switch (kind) {
-    case ACC_COUNT_STAR: case ACC_COUNT: case ACC_SUM_I64: atomicAdd(dst, v); break;
-    case ACC_SUM_F64: atomicAdd(reinterpret_cast<double*>(dst), __longlong_as_double((long long)v)); break;
-    case ACC_MIN_I64: case ACC_MIN_F64: atomicMin(reinterpret_cast<long long*>(dst), (long long)v); break;
-    default: atomicMax(reinterpret_cast<long long*>(dst), (long long)v); break;
   }
 }
 
