@@ -1,16 +1,17 @@
-// hash_agg_radix.cu — GROUP BY for large tables: radix-partition the rows by table region, then build
-// each region of the open-addressing table in shared memory.
+// hash_agg_radix.cu — GROUP BY for tables that outgrow the L2: radix-partition the rows by table region,
+// then build each region of the open-addressing table in shared memory.
 //
-// hash_agg_kernel (hash_agg.cu) sends every row to a random 32-byte slot of a table that no longer fits
-// close to the SMs (10^6 groups = 64 MB): ncu shows neither DRAM (13 %), L2 (28 %) nor issue slots
-// (19 %) busy — the pass is bound by the latency of ~3 dependent random accesses per row (0.97 ms for
-// 2^24 rows, 0.65 ms of it without the accumulator atomics).  Here random access never leaves the SM:
+// hash_agg_kernel (hash_agg.cu) sends every row to a random 32-byte slot.  While the table sits in the
+// 126 MB L2 that is the fastest path measured (10^6 groups, 64 MB: 0.97 ms per 2^24 rows); beyond it
+// every probe and every accumulator update is a random DRAM sector access (4·10^6 groups: 2.75 ms,
+// 8·10^6: 3.0 ms).  Here random access never leaves the SM:
 //
-//   K1  agg_radix_partition_kernel: one CTA per 2048-row tile.  Predicate, key, hash exactly as
-//       hash_agg_kernel; the home slot's top bits name a *bucket* = one contiguous region of S table
-//       slots.  The tile is counting-sorted by bucket in shared memory and each bucket's run is
-//       appended to that bucket's record array {Key16, value0, value1} (SoA, one atomicAdd per
-//       non-empty bucket per tile reserves the range): sequential reads, run-coalesced writes.
+//   K1  agg_radix_partition_kernel: one CTA per 2048-row tile.  Predicate and key as in hash_agg_kernel;
+//       the top bits of a 32-bit key hash name a *bucket* = one contiguous region of S table slots.
+//       The tile is counting-sorted by bucket in shared memory and each bucket's run is appended to
+//       that bucket's record array {Key16, value0, value1} (SoA; one atomicAdd per non-empty bucket
+//       per tile reserves the range): sequential reads, run-coalesced writes.  (Scattering the
+//       records straight from registers instead of sorting them first was measured 40 % slower.)
 //   K2  agg_radix_bucket_kernel: one CTA per bucket.  The region's S slots live in shared memory
 //       (keys + accumulators, SoA); the bucket's records stream in coalesced, probe/claim/accumulate
 //       with shared-memory atomics, and the finished region is written to the global table in the
@@ -18,9 +19,11 @@
 //       emission, partition ordering for the multi-GPU exchange) is shared.
 //
 // Traffic: input once (24 B/row for config 3) + records written and read once (24 B/row each) + the
-// table written once.  Covered shape = that of the tiled kernel (no VM programs), non-nullable
-// argument columns, ≤ 2 distinct argument columns.  A skewed key distribution overflows a bucket's
-// record array; the launcher then reports failure and the caller falls back to hash_agg_kernel.
+// table written once.  Measured per 2^24 rows (K1 + K2): 1.10 ms at 10^6 groups, 1.41 ms at 4·10^6,
+// 1.59 ms at 8·10^6 — so the launcher takes this path from 2^22 slots (a 128 MB table) upwards.
+// Covered shape = that of the tiled kernel (no VM programs), non-nullable argument columns, ≤ 2
+// distinct argument columns.  A skewed key distribution overflows a bucket's record array; the
+// kernels raise `skew`, and the caller reruns the batch through hash_agg_kernel.
 #include <atomic>
 
 #include "agg_acc.cuh"
@@ -214,6 +217,9 @@ __global__ void __launch_bounds__(1024) agg_radix_bucket_kernel(const __grid_con
   const unsigned long long* r1 = R.nv >= 2 ? R.rec_v1 + (size_t)b * R.cap : nullptr;
   unsigned int claimed = 0;
   bool full = false;
+  const int n_acc = P.n_acc;
+  const int kind0 = P.accs[0].kind, f0 = P.accs[0].arg_is_f64, vi0 = R.acc_v[0];
+  const int kind1 = P.accs[1].kind, f1 = P.accs[1].arg_is_f64, vi1 = R.acc_v[1];
   for (unsigned int i0 = tid; i0 < cnt; i0 += nthreads * RB_U) {
     Key16 key[RB_U];
     unsigned long long v0[RB_U], v1[RB_U];
@@ -238,12 +244,21 @@ __global__ void __launch_bounds__(1024) agg_radix_bucket_kernel(const __grid_con
       slot[u] = region_find_or_claim(K, S, h32 & (unsigned int)(S - 1), key[u], kc, &claimed);
       if (slot[u] < 0) full = true;
     }
-    for (int a = 0; a < P.n_acc; ++a) {
-      const int kind = P.accs[a].kind, is_f64 = P.accs[a].arg_is_f64, vi = R.acc_v[a];
-      unsigned long long* acc = ACC + a * S;
+    if (n_acc <= 2) {
 #pragma unroll
-      for (int u = 0; u < RB_U; ++u)
-        if (slot[u] >= 0) accumulate(kind, is_f64, acc + slot[u], vi == 0 ? v0[u] : v1[u]);
+      for (int u = 0; u < RB_U; ++u) {
+        if (slot[u] < 0) continue;
+        accumulate(kind0, f0, ACC + slot[u], vi0 == 0 ? v0[u] : v1[u]);
+        if (n_acc == 2) accumulate(kind1, f1, ACC + S + slot[u], vi1 == 0 ? v0[u] : v1[u]);
+      }
+    } else {
+      for (int a = 0; a < n_acc; ++a) {
+        const int kind = P.accs[a].kind, is_f64 = P.accs[a].arg_is_f64, vi = R.acc_v[a];
+        unsigned long long* acc = ACC + a * S;
+#pragma unroll
+        for (int u = 0; u < RB_U; ++u)
+          if (slot[u] >= 0) accumulate(kind, is_f64, acc + slot[u], vi == 0 ? v0[u] : v1[u]);
+      }
     }
   }
   if (claimed) atomicAdd(&s_groups, claimed);
@@ -273,13 +288,14 @@ std::atomic<int> g_skew_backoff{0};
 // (the kernels raise it in device memory at `skew_dev`).  When the flag is set the table is garbage and
 // the caller reruns with hash_agg_kernel.
 bool launch_hash_agg_radix(const AggParams& P, unsigned long long capacity, int32_t* skew_dev, std::vector<BufferPtr>* keep, cudaStream_t stream) {
-  static const int mode = [] { const char* e = getenv("ARK_AGG_RADIX"); return e ? atoi(e) : 1; }();  // 0 = never
+  const char* mode_env = getenv("ARK_AGG_RADIX");  // read per call (tests flip it): 0 = never, 2 = already from 2^16 rows / slots
+  const int mode = mode_env ? atoi(mode_env) : 1;
   static const int log2_slots_env = [] { const char* e = getenv("ARK_AGG_RADIX_S"); return e ? atoi(e) : 12; }();
   if (!mode) return false;
   const int64_t n = P.n_rows;
   if (P.pred_kind == 2 || (P.key_kind != KEY_INT64 && P.key_kind != KEY_BYTES)) return false;
-  if (n < (1 << 20) || n >= (1ll << 31) || capacity < (1ull << 16)) return false;
-  if (g_skew_backoff.load() > 0) { g_skew_backoff.fetch_sub(1); return false; }
+  if (n < (mode == 2 ? 1 << 16 : 1 << 20) || n >= (1ll << 31) || capacity < (mode == 2 ? 1ull << 16 : 1ull << 22)) return false;
+  if (mode != 2 && g_skew_backoff.load() > 0) { g_skew_backoff.fetch_sub(1); return false; }
   RadixParams R;
   memset(&R, 0, sizeof R);
   for (int a = 0; a < P.n_acc; ++a) {
@@ -297,7 +313,7 @@ bool launch_hash_agg_radix(const AggParams& P, unsigned long long capacity, int3
   log2_slots = std::min(12, std::max(9, log2_slots));
   while (log2_slots > 9 && ((size_t)(16 + 8 * P.n_acc) << log2_slots) > 160 * 1024) --log2_slots;
   const unsigned long long n_buckets = capacity >> log2_slots;
-  if (n_buckets < 16 || n_buckets > 2048) return false;
+  if (n_buckets < 16 || n_buckets > 4096) return false;
   int log2_buckets = 0;
   while ((1ull << log2_buckets) < n_buckets) ++log2_buckets;
   const unsigned long long cap = (unsigned long long)((double)n / (double)n_buckets * 1.25) + 1024;

@@ -9,6 +9,7 @@ import math
 
 import numpy as np
 import pyarrow as pa
+import pyarrow.compute  # noqa: F401
 import pytest
 
 from arkflow_b200.arrow_ffi import DeviceBatch
@@ -192,3 +193,87 @@ def test_aggregate_planning_errors(gpu):
     assert e.value.kind == "Process"
     with pytest.raises(ArkError):
         run(rb, "SELECT SUM(sensor) FROM flow")
+
+
+# ---- partitioned (radix) path: csrc/hash_agg_radix.cu ------------------------------------------------
+def _launches(lib, name):
+    import ctypes as C
+    ms, n = C.c_double(), C.c_int64()
+    lib.ark_kernel_timing_get(name.encode(), C.byref(ms), C.byref(n))
+    return n.value
+
+
+def check_agg_sorted(rb, query, key, float_cols=()):
+    """check_agg for many groups: both results sorted by the key column, columns compared as arrays."""
+    want = sql_process(rb, query)
+    for device in (False, True):
+        got = run(rb, query, device=device)
+        assert got.schema.names == want.schema.names
+        assert [f.type for f in got.schema] == [f.type for f in want.schema]
+        assert got.num_rows == want.num_rows
+        g = pa.Table.from_batches([got]).sort_by(key)
+        w = pa.Table.from_batches([want]).sort_by(key)
+        for name in want.schema.names:
+            a, b = g.column(name).combine_chunks(), w.column(name).combine_chunks()
+            if name in float_cols:
+                x, y = a.to_numpy(zero_copy_only=False), b.to_numpy(zero_copy_only=False)
+                assert np.allclose(x, y, rtol=1e-12, atol=0.0), name  # ≤ a few hundred addends per group here
+            else:
+                assert a.equals(b), name
+    return want
+
+
+@pytest.fixture
+def radix_mode(gpu, monkeypatch):
+    monkeypatch.setenv("ARK_AGG_RADIX", "2")  # take the partitioned path already from 2^16 rows / slots
+    gpu.ark_kernel_timing_reset()
+    gpu.ark_kernel_timing_enable(1)
+    yield gpu
+    gpu.ark_kernel_timing_enable(0)
+
+
+def test_radix_path_string_keys(radix_mode):
+    rb = synth_batch(400_000, key_space=150_000, seed=21)
+    q = "SELECT sensor, SUM(value), COUNT(*) FROM flow GROUP BY sensor"
+    check_agg_sorted(rb, q, "sensor")  # first call may still be growing the capacity hint
+    radix_mode.ark_kernel_timing_reset()
+    check_agg_sorted(rb, q, "sensor")
+    assert _launches(radix_mode, "agg_radix_bucket_kernel") >= 2 and _launches(radix_mode, "hash_agg_kernel") == 0
+    check_agg_sorted(rb, "SELECT sensor, SUM(value), COUNT(*), MIN(value), MAX(value), AVG(value) FROM flow WHERE value >= 4 GROUP BY sensor",
+                     "sensor", float_cols=["avg(flow.value)"])
+
+
+def test_radix_path_float_values_and_int_keys(radix_mode):
+    rb = synth_batch(300_000, value_kind=1, key_space=120_000, seed=22)
+    check_agg_sorted(rb, "SELECT sensor, SUM(value), AVG(value), COUNT(*) FROM flow GROUP BY sensor", "sensor",
+                     float_cols=["sum(flow.value)", "avg(flow.value)"])
+    rng = np.random.default_rng(23)
+    n = 300_000
+    rb2 = pa.record_batch({"id": pa.array(rng.integers(-2**40, 2**40, n) // 2**23, pa.int64()), "v": pa.array(rng.integers(-2**62, 2**62, n), pa.int64())})
+    check_agg_sorted(rb2, "SELECT id, SUM(v), COUNT(*), MIN(v), MAX(v) FROM flow GROUP BY id", "id")
+    assert _launches(radix_mode, "agg_radix_bucket_kernel") >= 2
+
+
+def test_radix_path_long_keys_and_null_keys(radix_mode):
+    rng = np.random.default_rng(24)
+    n = 200_000
+    ids = rng.integers(0, 90_000, n)
+    keys = [None if i % 997 == 0 else (f"k{i}" if i % 3 else f"a-rather-long-sensor-name-{i:09d}") for i in ids.tolist()]
+    rb = pa.record_batch({"sensor": pa.array(keys, pa.utf8()), "value": pa.array(rng.integers(0, 1000, n), pa.int64())})
+    want = check_agg_sorted(rb, "SELECT sensor, SUM(value), COUNT(*) FROM flow GROUP BY sensor", "sensor")
+    assert want.column("sensor").null_count == 1
+    assert _launches(radix_mode, "agg_radix_bucket_kernel") >= 1
+
+
+def test_radix_path_skewed_keys_fall_back(radix_mode):
+    # half of the rows carry one key: that bucket's record array overflows, the batch is redone by hash_agg_kernel
+    rb = synth_batch(400_000, key_space=150_000, seed=25)
+    hot = pa.array(["hot_sensor_0"] * 400_000)
+    idx = np.arange(400_000)
+    sensor = pa.compute.if_else(pa.array(idx % 2 == 0), hot, rb.column("sensor"))
+    rb = pa.record_batch({"timestamp": rb.column("timestamp"), "value": rb.column("value"), "sensor": sensor})
+    q = "SELECT sensor, SUM(value), COUNT(*) FROM flow GROUP BY sensor"
+    check_agg_sorted(rb, q, "sensor")
+    radix_mode.ark_kernel_timing_reset()
+    check_agg_sorted(rb, q, "sensor")
+    assert _launches(radix_mode, "agg_radix_partition_kernel") >= 1 and _launches(radix_mode, "hash_agg_kernel") >= 1
