@@ -281,7 +281,7 @@ Batch import_host(const ArrowArray* arr, const ArrowSchema* schema, const std::v
 }
 
 __global__ void gather_extents_kernel(const int32_t* const* offs, const int64_t* lens, int32_t* out, int n) {
-  int i = threadIdx.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { out[2 * i] = offs[i][0]; out[2 * i + 1] = offs[i][lens[i]]; }
 }
 
@@ -356,38 +356,43 @@ int64_t varlen_bytes_bound(const Column& c) {
 }
 
 // Fetch offsets[0] / offsets[n] of device-resident var-len columns whose extent is still unknown.
-void resolve_varlen_extents(Batch& b, const std::vector<int>& col_idx, cudaStream_t stream) {
-  std::vector<int> todo;
-  for (int i : col_idx) {
-    Column& c = b.cols[i];
-    if (c.present && (c.field.type == DType::Utf8 || c.field.type == DType::Binary) && c.data_bytes < 0) {
-      if (c.length == 0 || c.offsets == nullptr) { c.data_bytes = 0; c.first_offset = 0; }
-      else todo.push_back(i);
+// Reads offsets[0] and offsets[length] of every var-len column whose byte extent is still unknown — all
+// of them (across batches) with ONE kernel, one D2H copy and one stream synchronize.
+void resolve_varlen_extents_many(std::vector<Column*>& cols, cudaStream_t stream) {
+  std::vector<Column*> todo;
+  for (Column* c : cols) {
+    if (c->present && (c->field.type == DType::Utf8 || c->field.type == DType::Binary) && c->data_bytes < 0) {
+      if (c->length == 0 || c->offsets == nullptr) { c->data_bytes = 0; c->first_offset = 0; }
+      else todo.push_back(c);
     }
   }
   if (todo.empty()) return;
-  int n = (int)todo.size();
-  if (n > 32) fail(ARK_ERR_UNSUPPORTED, "more than 32 var-len columns");
-  BufferPtr hp = pinned_alloc(1024);
-  BufferPtr dp = device_alloc(1024);
-  // layout (pinned & device): [0,256) pointers, [256,512) lens, [512,768) out
+  const size_t n = todo.size();
+  // layout (pinned & device): [pointers n×8][lens n×8][out n×8]
+  BufferPtr hp = pinned_alloc(n * 24 + 64);
+  BufferPtr dp = device_alloc(n * 24 + 64);
   const int32_t** hptr = (const int32_t**)hp.get();
-  int64_t* hlen = (int64_t*)((char*)hp.get() + 256);
-  int32_t* hout = (int32_t*)((char*)hp.get() + 512);
-  for (int k = 0; k < n; ++k) { hptr[k] = b.cols[todo[k]].offsets; hlen[k] = b.cols[todo[k]].length; }
-  ARK_CUDA(cudaMemcpyAsync(dp.get(), hp.get(), 512, cudaMemcpyHostToDevice, stream));
+  int64_t* hlen = (int64_t*)((char*)hp.get() + n * 8);
+  int32_t* hout = (int32_t*)((char*)hp.get() + n * 16);
+  for (size_t k = 0; k < n; ++k) { hptr[k] = todo[k]->offsets; hlen[k] = todo[k]->length; }
+  ARK_CUDA(cudaMemcpyAsync(dp.get(), hp.get(), n * 16, cudaMemcpyHostToDevice, stream));
   {
     KernelTimer t("gather_extents_kernel", stream);
-    gather_extents_kernel<<<1, 32, 0, stream>>>((const int32_t* const*)dp.get(), (const int64_t*)((char*)dp.get() + 256),
-                                               (int32_t*)((char*)dp.get() + 512), n);
+    gather_extents_kernel<<<(unsigned)ceil_div((int64_t)n, 32), 32, 0, stream>>>((const int32_t* const*)dp.get(), (const int64_t*)((char*)dp.get() + n * 8),
+                                                                            (int32_t*)((char*)dp.get() + n * 16), (int)n);
   }
-  ARK_CUDA(cudaMemcpyAsync(hout, (char*)dp.get() + 512, 256, cudaMemcpyDeviceToHost, stream));
+  ARK_CUDA(cudaMemcpyAsync(hout, (char*)dp.get() + n * 16, n * 8, cudaMemcpyDeviceToHost, stream));
   ARK_CUDA(cudaStreamSynchronize(stream));
-  for (int k = 0; k < n; ++k) {
-    Column& c = b.cols[todo[k]];
-    c.first_offset = hout[2 * k];
-    c.data_bytes = (int64_t)hout[2 * k + 1] - hout[2 * k];
+  for (size_t k = 0; k < n; ++k) {
+    todo[k]->first_offset = hout[2 * k];
+    todo[k]->data_bytes = (int64_t)hout[2 * k + 1] - hout[2 * k];
   }
+}
+
+void resolve_varlen_extents(Batch& b, const std::vector<int>& col_idx, cudaStream_t stream) {
+  std::vector<Column*> cols;
+  for (int i : col_idx) cols.push_back(&b.cols[i]);
+  resolve_varlen_extents_many(cols, stream);
 }
 
 // ---- export ---------------------------------------------------------------------------------------------

@@ -135,10 +135,10 @@ Batch concat_device(std::vector<Batch>& ins, cudaStream_t stream) {
                                   dtype_name(ins[b].cols[c].field.type) + " at column index " + std::to_string(c));
     }
   }
-  for (auto& b : ins) {
-    std::vector<int> all;
-    for (size_t c = 0; c < ncol; ++c) all.push_back((int)c);
-    resolve_varlen_extents(b, all, stream);
+  {
+    std::vector<Column*> all;  // one round trip for the extents of every batch
+    for (auto& b : ins) for (auto& c : b.cols) all.push_back(&c);
+    resolve_varlen_extents_many(all, stream);
   }
   if (ins.size() == 1) return ins[0];
   int64_t total_rows = 0;

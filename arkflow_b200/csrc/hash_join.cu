@@ -89,16 +89,78 @@ __global__ void take_lengths_kernel(const int32_t* offsets, const unsigned int* 
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { const unsigned int r = idx[i]; lens[i] = offsets[r + 1] - offsets[r]; }
 }
-__global__ void take_bytes_kernel(const uint8_t* data, const int32_t* offsets, const unsigned int* idx, long long n,
-                                  const int32_t* out_offsets, uint8_t* out) {
-  // one warp per output row: lanes stride over the bytes
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= n) return;
-  const unsigned int r = idx[w];
-  const int32_t s0 = offsets[r], len = offsets[r + 1] - s0;
-  uint8_t* d = out + out_offsets[w];
-  for (int i = lane; i < len; i += 32) d[i] = data[s0 + i];
+// global → shared copy of one string, word-granular on the (shared) destination: aligned source words are
+// funnel-shifted into place, so a 12-byte key costs 3–4 loads and 3 stores instead of 12 + 12.
+__device__ __forceinline__ void gather_string(uint8_t* dst, const uint8_t* src, int len) {
+  const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
+  int i = 0;
+  for (; i < len && ((d0 + i) & 3); ++i) dst[i] = src[i];  // head: up to 3 bytes
+  const int words = (len - i) >> 2;
+  if (words > 0) {
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(src + i);
+    const unsigned sh = (unsigned)(sa & 3) * 8;
+    const unsigned* sw = reinterpret_cast<const unsigned*>(sa & ~(uintptr_t)3);  // aligned word holding src[i]
+    unsigned* d = reinterpret_cast<unsigned*>(dst + i);
+    if (sh == 0) {
+      for (int w = 0; w < words; ++w) d[w] = sw[w];
+    } else {
+      unsigned lo = sw[0];
+      for (int w = 0; w < words; ++w) {  // sw[w + 1] holds source byte i + 4w + 3 < len: never past the string's last word
+        const unsigned hi = sw[w + 1];
+        d[w] = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+      }
+    }
+    i += words * 4;
+  }
+  for (; i < len; ++i) dst[i] = src[i];  // tail
+}
+
+constexpr int TAKE_TILE = 1024;
+constexpr int TAKE_STAGE = 40 * 1024;  // bytes of output staged per tile; longer tiles take the per-row path
+
+// Gathers the bytes of TAKE_TILE output rows into shared memory (their output range is contiguous), then
+// writes the range with destination-aligned 16-byte stores.  Replaces the warp-per-row kernel on the join's
+// gather of string columns (2^24 rows of 12 bytes: 2.97 ms → see profiles/).
+__global__ void __launch_bounds__(256) take_bytes_tile_kernel(const uint8_t* data, const int32_t* offsets, const unsigned int* idx, long long n,
+                                                               const int32_t* out_offsets, uint8_t* out) {
+  __shared__ __align__(16) uint8_t stage[TAKE_STAGE + 16];
+  const long long row0 = (long long)blockIdx.x * TAKE_TILE;
+  const int rows = (int)((n - row0) < TAKE_TILE ? (n - row0) : TAKE_TILE);
+  const int tid = threadIdx.x;
+  const int32_t bb = out_offsets[row0];
+  const int tb = out_offsets[row0 + rows] - bb;
+  if (tb > TAKE_STAGE) {  // long strings: straight per-row copies, a warp per row
+    const int lane = tid & 31;
+    for (int i = tid >> 5; i < rows; i += 8) {
+      const unsigned int r = idx[row0 + i];
+      const int32_t s0 = offsets[r], len = offsets[r + 1] - s0;
+      uint8_t* d = out + out_offsets[row0 + i];
+      for (int b = lane; b < len; b += 32) d[b] = data[s0 + b];
+    }
+    return;
+  }
+  // staging starts at the destination's misalignment so that shared and global addresses agree mod 16
+  const int mis = (int)(reinterpret_cast<uintptr_t>(out + bb) & 15);
+#pragma unroll
+  for (int k = 0; k < TAKE_TILE / 256; ++k) {
+    const int i = k * 256 + tid;
+    if (i < rows) {
+      const unsigned int r = idx[row0 + i];
+      const int32_t s0 = offsets[r], len = offsets[r + 1] - s0;
+      gather_string(stage + mis + (out_offsets[row0 + i] - bb), data + s0, len);
+    }
+  }
+  __syncthreads();
+  uint8_t* gdst = out + bb;
+  const int head = min((16 - mis) & 15, tb);
+  if (tid < head) gdst[tid] = stage[mis + tid];
+  const int body = (tb - head) >> 4;
+  const uint4* sv = reinterpret_cast<const uint4*>(stage + mis + head);  // 16-byte aligned: mis + head ≡ 0 (mod 16) when body > 0
+  uint4* gv = reinterpret_cast<uint4*>(gdst + head);
+  for (int g = tid; g < body; g += 256) gv[g] = sv[g];
+  const int tail0 = head + body * 16;
+  if (tid < tb - tail0) gdst[tail0 + tid] = stage[mis + tail0 + tid];
 }
 
 // ---- hash repartition ----------------------------------------------------------------------------------
@@ -191,8 +253,8 @@ Column take_column(const Column& src, const unsigned int* idx, int64_t n, const 
       if (total < 0) fail(ARK_ERR_PROCESS, "Collection query results error: Arrow error: offset overflow, result column exceeds 2 GiB");
       BufferPtr bytes = device_alloc((size_t)total + 16);
       if (n) {
-        KernelTimer t("take_bytes_kernel", stream);
-        take_bytes_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, stream>>>(src.data, src.offsets, idx, n, (const int32_t*)offs.get(), (uint8_t*)bytes.get());
+        KernelTimer t("take_bytes_tile_kernel", stream);
+        take_bytes_tile_kernel<<<(unsigned)ceil_div(n, TAKE_TILE), 256, 0, stream>>>(src.data, src.offsets, idx, n, (const int32_t*)offs.get(), (uint8_t*)bytes.get());
       }
       c.offsets = (const int32_t*)offs.get(); c.data = (const uint8_t*)bytes.get(); c.data_bytes = total; c.first_offset = 0;
       c.owners = {offs, bytes};

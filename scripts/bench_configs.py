@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--keys", type=int, default=1_000_000)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default="")
+    ap.add_argument("--only", default="", help="comma-separated legs: groupby,join,concat,json (default: all)")
     args = ap.parse_args()
 
     import numpy as np
@@ -57,11 +58,13 @@ def main():
         lib.ark_kernel_timing_reset()
         lib.ark_kernel_timing_enable(1)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.reps):
+        per_call = []
+        for _ in range(args.reps):  # every entry point synchronises its stream before returning
+            t0 = time.perf_counter()
             fn()
+            per_call.append(time.perf_counter() - t0)
         torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) / args.reps
+        wall = sorted(per_call)[len(per_call) // 2]  # median: a one-off host hiccup (GC, allocator growth) is not the path's cost
         lib.ark_kernel_timing_enable(0)
         kern = {}
         for k in kernel_names:
@@ -72,9 +75,10 @@ def main():
 
     results = {"peak_gbs": peak, "rows": args.rows, "keys": args.keys}
     n = args.rows
+    legs = set(args.only.split(",")) if args.only else {"groupby", "join", "concat", "json"}
 
     # ---- config 3: GROUP BY ----
-    for kind, label in ((0, "int64"), (1, "float64")):
+    for kind, label in ((0, "int64"), (1, "float64")) if "groupby" in legs else ():
         batches = [synth(n, row0=i * n, kind=kind) for i in range(3)]
         proc = SqlProcessor({"query": "SELECT sensor, SUM(value), COUNT(*) FROM flow GROUP BY sensor"})
         state = {"i": 0}
@@ -94,58 +98,61 @@ def main():
         del batches
 
     # ---- config 4: join (probe n rows, build K unique keys) ----
-    K = min(args.keys, 1_000_000)
-    probe = synth(n, keys=K)
-    bkeys = pa.array(["temp_%07d" % i for i in np.random.default_rng(0).permutation(K)])
-    build = F.DeviceBatch.from_arrow(pa.record_batch({"sensor": bkeys, "w": pa.array(np.arange(K), pa.int64())}))
-    jp = SqlProcessor({"query": "SELECT * FROM p JOIN b ON p.sensor = b.sensor"})
+    if "join" in legs:
+        K = min(args.keys, 1_000_000)
+        probe = synth(n, keys=K)
+        bkeys = pa.array(["temp_%07d" % i for i in np.random.default_rng(0).permutation(K)])
+        build = F.DeviceBatch.from_arrow(pa.record_batch({"sensor": bkeys, "w": pa.array(np.arange(K), pa.int64())}))
+        jp = SqlProcessor({"query": "SELECT * FROM p JOIN b ON p.sensor = b.sensor"})
 
-    def jstep():
-        out = jp.process_tables_device({"p": probe, "b": build})
-        out.close()
+        def jstep():
+            out = jp.process_tables_device({"p": probe, "b": build})
+            out.close()
 
-    wall, kern = timed(jstep, ["join_build_kernel", "join_probe_count_kernel", "join_probe_fill_kernel", "take_fixed8_kernel", "take_bytes_kernel", "take_lengths_kernel"])
-    alg = n * 32 + K * 24 + n * (32 + 24)
-    results["config4_join"] = {"probe_rows_per_s_call": n / wall, "ms_per_call": wall * 1e3, "algorithmic_bytes": alg,
-                               "achieved_gbs_call": alg / wall / 1e9, "frac_call": alg / wall / 1e9 / peak, "kernels": kern}
-    del probe, build
+        wall, kern = timed(jstep, ["join_build_kernel", "join_probe_count_kernel", "join_probe_fill_kernel", "take_fixed8_kernel", "take_bytes_tile_kernel", "take_lengths_kernel"])
+        alg = n * 32 + K * 24 + n * (32 + 24)
+        results["config4_join"] = {"probe_rows_per_s_call": n / wall, "ms_per_call": wall * 1e3, "algorithmic_bytes": alg,
+                                   "achieved_gbs_call": alg / wall / 1e9, "frac_call": alg / wall / 1e9 / peak, "kernels": kern}
+        del probe, build
 
     # ---- config 5: concat of 16 batches of n/16 rows ----
-    parts = [synth(n // 16, row0=i * (n // 16)) for i in range(16)]
+    if "concat" in legs:
+        parts = [synth(n // 16, row0=i * (n // 16)) for i in range(16)]
 
-    def cstep():
-        out = concat_batches_device(parts)
-        out.close()
+        def cstep():
+            out = concat_batches_device(parts)
+            out.close()
 
-    wall, kern = timed(cstep, ["concat_copy_kernel", "concat_offsets_kernel"])
-    alg = 2 * n * 32
-    k = kern["concat_copy_kernel"]["avg_ms"]
-    results["config5_concat"] = {"rows_per_s_call": n / wall, "ms_per_call": wall * 1e3, "kernel_ms": k,
-                                 "roofline": {"bound": "hbm", "achieved": (2 * n * 28) / (k / 1e3) / 1e9 if k else None, "peak": peak,
-                                              "frac": ((2 * n * 28) / (k / 1e3) / 1e9 / peak) if k else None,
-                                              "note": "concat_copy_kernel moves the 28 B/row of values + string bytes; offsets (4 B/row) go through concat_offsets_kernel"},
-                                 "kernels": kern}
-    del parts
+        wall, kern = timed(cstep, ["concat_copy_kernel", "concat_offsets_kernel"])
+        alg = 2 * n * 32
+        k = kern["concat_copy_kernel"]["avg_ms"]
+        results["config5_concat"] = {"rows_per_s_call": n / wall, "ms_per_call": wall * 1e3, "kernel_ms": k,
+                                     "roofline": {"bound": "hbm", "achieved": (2 * n * 28) / (k / 1e3) / 1e9 if k else None, "peak": peak,
+                                                  "frac": ((2 * n * 28) / (k / 1e3) / 1e9 / peak) if k else None,
+                                                  "note": "concat_copy_kernel moves the 28 B/row of values + string bytes; offsets (4 B/row) go through concat_offsets_kernel"},
+                                     "kernels": kern}
+        del parts
 
     # ---- json_to_arrow ----
-    m = min(n, 1 << 22)
-    msg = b'{ "timestamp": 1625000000000, "value": 10, "sensor": "temp_1" }'
-    data = torch.from_numpy(np.frombuffer(msg * m, dtype=np.uint8).copy()).cuda()
-    offs = torch.arange(0, (m + 1) * len(msg), len(msg), dtype=torch.int32, device="cuda")
-    payload = F.DeviceBatch([F.DeviceColumn("__value__", "binary", m, data, offs, None, 0, False)], m)
-    jproc = JsonToArrowProcessor({})
+    if "json" in legs:
+        m = min(n, 1 << 22)
+        msg = b'{ "timestamp": 1625000000000, "value": 10, "sensor": "temp_1" }'
+        data = torch.from_numpy(np.frombuffer(msg * m, dtype=np.uint8).copy()).cuda()
+        offs = torch.arange(0, (m + 1) * len(msg), len(msg), dtype=torch.int32, device="cuda")
+        payload = F.DeviceBatch([F.DeviceColumn("__value__", "binary", m, data, offs, None, 0, False)], m)
+        jproc = JsonToArrowProcessor({})
 
-    def pstep():
-        out = jproc.process_device(payload)
-        out.close()
+        def pstep():
+            out = jproc.process_device(payload)
+            out.close()
 
-    wall, kern = timed(pstep, ["json_count_kernel", "json_parse_kernel", "json_strings_kernel"])
-    alg = m * (len(msg) + 4) + m * 26
-    k = kern["json_parse_kernel"]["avg_ms"]
-    results["json_to_arrow"] = {"msgs_per_s_call": m / wall, "ms_per_call": wall * 1e3, "kernel_ms": k,
-                                "roofline": {"bound": "hbm", "achieved": alg / (k / 1e3) / 1e9 if k else None, "peak": peak,
-                                             "frac": (alg / (k / 1e3) / 1e9 / peak) if k else None, "algorithmic_bytes_per_launch": alg},
-                                "kernels": kern}
+        wall, kern = timed(pstep, ["json_count_kernel", "json_parse_kernel", "json_strings_kernel"])
+        alg = m * (len(msg) + 4) + m * 26
+        k = kern["json_parse_kernel"]["avg_ms"]
+        results["json_to_arrow"] = {"msgs_per_s_call": m / wall, "ms_per_call": wall * 1e3, "kernel_ms": k,
+                                    "roofline": {"bound": "hbm", "achieved": alg / (k / 1e3) / 1e9 if k else None, "peak": peak,
+                                                 "frac": (alg / (k / 1e3) / 1e9 / peak) if k else None, "algorithmic_bytes_per_launch": alg},
+                                    "kernels": kern}
     print(json.dumps(results, indent=1))
     if args.out:
         with open(os.path.join(ROOT, args.out), "w") as f:
