@@ -93,6 +93,11 @@ def _declare(lib):
         "ark_buffer_flush": (C.c_int, [vp]),
         "ark_buffer_close": (C.c_int, [vp]),
         "ark_buffer_destroy": (None, [vp]),
+        "ark_batch_create": (C.c_int, [C.c_char_p, P(vp)]),
+        "ark_batch_process": (C.c_int, [vp, P(ArrowArray), P(ArrowSchema), P(ArrowArray), P(ArrowSchema)]),
+        "ark_batch_flush": (C.c_int, [vp, P(ArrowArray), P(ArrowSchema)]),
+        "ark_batch_close": (C.c_int, [vp]),
+        "ark_batch_destroy": (None, [vp]),
         "ark_sql_partial_aggregate_device": (C.c_int, [vp, P(ArrowDeviceArray), P(ArrowSchema), C.c_int, P(ArrowDeviceArray), P(ArrowSchema), P(C.c_int64)]),
         "ark_sql_final_aggregate_device": (C.c_int, [vp, P(ArrowDeviceArray), P(ArrowSchema), P(ArrowDeviceArray), P(ArrowSchema)]),
         "ark_hash_partition_device": (C.c_int, [P(ArrowDeviceArray), P(ArrowSchema), C.c_char_p, C.c_int, P(ArrowDeviceArray), P(ArrowSchema), P(C.c_int64)]),

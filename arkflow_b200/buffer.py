@@ -155,7 +155,28 @@ class TumblingWindow(Buffer):
     KIND = "tumbling_window"
 
 
-_BUFFERS = {"memory": MemoryBuffer, "session_window": SessionWindow, "tumbling_window": TumblingWindow}
+class SlidingWindow(Buffer):
+    """`type: sliding_window` {window_size, interval, slide_size} — buffer/sliding_window.rs:37-238.
+    A window is the first `window_size` queued BATCHES in arrival order; `slide_size` of them are then
+    dropped, so consecutive windows overlap (and a batch's ack can be returned more than once)."""
+
+    KIND = "sliding_window"
+
+    def read(self):
+        out_arr, out_sch = L.ArrowArray(), L.ArrowSchema()
+        cap = max(len(self._acks), 1) + 16
+        acks = (C.c_uint64 * cap)()
+        n = C.c_int64(0)
+        _check(L.lib().ark_buffer_read(self._h, C.byref(out_arr), C.byref(out_sch), acks, cap, C.byref(n)))
+        if not out_arr.release:
+            return None
+        rb = F.import_record_batch(out_arr, out_sch)
+        got = [self._acks[int(acks[i])] for i in range(n.value)]  # kept: the batch may be part of the next window too
+        return MessageBatch(rb), VecAck(got)
+
+
+_BUFFERS = {"memory": MemoryBuffer, "session_window": SessionWindow, "tumbling_window": TumblingWindow,
+            "sliding_window": SlidingWindow}
 
 
 def build_buffer(config: dict, input_names: Optional[list] = None) -> Buffer:

@@ -1,15 +1,21 @@
-// buffers.cu — the buffer stage: memory / session_window / tumbling_window (+ JoinOperation), with the
-// queued batches resident in HBM and concat / json-decode / join running as kernels.
+// buffers.cu — the buffer stage: memory / session_window / tumbling_window / sliding_window
+// (+ JoinOperation) and the count/timeout `batch` processor, with the queued batches resident in HBM and
+// concat / json-decode / join running as kernels.
 //
 //   MemoryBuffer   ← crates/arkflow-plugin/src/buffer/memory.rs:39-237   (drain OLDEST first: push_front / pop_back)
 //   BaseWindow     ← crates/arkflow-plugin/src/buffer/window.rs:28-217   (per-input queues, drain NEWEST first: push_front / pop_front)
 //   SessionWindow  ← crates/arkflow-plugin/src/buffer/session_window.rs:97-159
 //   TumblingWindow ← crates/arkflow-plugin/src/buffer/tumbling_window.rs:90-145
 //   JoinOperation  ← crates/arkflow-plugin/src/buffer/join.rs:62-146
+//   SlidingWindow  ← crates/arkflow-plugin/src/buffer/sliding_window.rs:52-238 (FIFO of batches; a window = the
+//                    first window_size BATCHES in arrival order, then slide_size of them are dropped)
+//   BatchProcessor ← crates/arkflow-plugin/src/processor/batch.rs:37-124
 // tokio's Notify + timer task become a condition variable + a timer thread; the wake-up rules are the
 // reference's (capacity reached, timer tick, flush/close).  Deliberate differences:
 // row totals are kept incrementally instead of recounted on every write; a reader that is already
-// waiting when the window is flushed drains what is left instead of waiting for a tick that never comes.
+// waiting when the window is flushed drains what is left instead of waiting for a tick that never comes;
+// a sliding-window reader blocked on a flushed/closed buffer gets None instead of hanging (the
+// reference's timer task exits on close, so nothing would ever wake that reader again).
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
@@ -106,7 +112,7 @@ std::unique_ptr<JoinOp> make_join(const JsonValue& j, const char* input_names_js
 }  // namespace
 
 struct ark_buf {
-  enum Kind { Memory, Session, Tumbling } kind;
+  enum Kind { Memory, Session, Tumbling, Sliding } kind;
   std::mutex mu;
   std::condition_variable cv;
   bool closed = false;
@@ -116,6 +122,8 @@ struct ark_buf {
   uint32_t capacity = 0;
   std::deque<Queued> queue;  // front = newest
   int64_t queued_rows = 0;
+  // sliding window: `queue` is FIFO here (push_back / front = oldest), sliding_window.rs:170-174
+  uint32_t window_size = 0, slide_size = 0;
   // windows
   std::vector<std::string> input_order;
   std::vector<std::deque<Queued>> input_queues;  // per input, front = newest
@@ -220,6 +228,7 @@ int ark_buffer_create(const char* kind, const char* config_json, const char* inp
     const char* missing = k == "memory" ? "Memory buffer configuration is missing"          // memory.rs:256-258
                           : k == "session_window" ? "Session window configuration is missing"  // session_window.rs:178-180
                           : k == "tumbling_window" ? "Tumbling window configuration is missing"  // tumbling_window.rs:164-166
+                          : k == "sliding_window" ? "Sliding window configuration is missing"    // sliding_window.rs:248-252
                           : nullptr;
     if (!missing) fail(ARK_ERR_CONFIG, "Unknown buffer type: " + k);
     if (!config_json) fail(ARK_ERR_CONFIG, missing);
@@ -235,6 +244,21 @@ int ark_buffer_create(const char* kind, const char* config_json, const char* inp
         fail(ARK_ERR_SERIALIZATION, "invalid value for `capacity`: expected u32");
       b->capacity = (uint32_t)cap->i64;
       b->period = duration_field(cfg, "timeout", "MemoryBufferConfig");
+    } else if (k == "sliding_window") {
+      b->kind = ark_buf::Sliding;
+      auto u32_field = [&](const char* key) -> uint32_t {
+        const JsonValue* v = cfg.get(key);
+        if (!v) fail(ARK_ERR_SERIALIZATION, std::string("missing field `") + key + "` (SlidingWindowConfig)");
+        if (v->kind != JsonValue::Number || !v->is_int || v->i64 < 0 || v->i64 > 0xFFFFFFFFll)
+          fail(ARK_ERR_SERIALIZATION, std::string("invalid value for `") + key + "`: expected u32");
+        return (uint32_t)v->i64;
+      };
+      b->window_size = u32_field("window_size");
+      b->period = duration_field(cfg, "interval", "SlidingWindowConfig");
+      b->slide_size = u32_field("slide_size");
+      if (b->window_size == 0) fail(ARK_ERR_CONFIG, "Sliding window window_size must be greater than 0");            // sliding_window.rs:256-260
+      if (b->slide_size == 0) fail(ARK_ERR_CONFIG, "Sliding window slide_size must be greater than 0");              // sliding_window.rs:261-265
+      if (b->window_size < b->slide_size) fail(ARK_ERR_CONFIG, "Sliding window window_size must be greater than slide_size");  // :266-270
     } else {
       b->kind = k == "session_window" ? ark_buf::Session : ark_buf::Tumbling;
       b->period = duration_field(cfg, k == "session_window" ? "gap" : "interval", k == "session_window" ? "SessionWindowConfig" : "TumblingWindowConfig");
@@ -261,6 +285,9 @@ int ark_buffer_write(ark_buf_t* b, ArrowArray* in, ArrowSchema* in_schema, const
       b->queued_rows += batch.num_rows;
       b->queue.push_front({std::move(batch), ack_token});            // memory.rs:155
       if (b->queued_rows >= (int64_t)b->capacity) b->cv.notify_all();  // memory.rs:164-167
+    } else if (b->kind == ark_buf::Sliding) {
+      b->queue.push_back({std::move(batch), ack_token});               // sliding_window.rs:170-174
+      if (b->queue.size() >= b->window_size) b->cv.notify_all();       // (the reference waits for the next timer tick)
     } else {
       size_t idx = 0;
       for (; idx < b->input_order.size(); ++idx) if (b->input_order[idx] == batch.input_name) break;
@@ -293,6 +320,23 @@ int ark_buffer_read(ark_buf_t* b, ArrowArray* out, ArrowSchema* out_schema, uint
           b->queue.pop_back();
         }
         b->queued_rows = 0;
+      }
+      Batch r = concat_device(bs, lease.s);
+      export_host(r, lease.s, out, out_schema);
+    } else if (b->kind == ark_buf::Sliding) {
+      std::vector<Batch> bs;
+      {
+        std::unique_lock<std::mutex> l(b->mu);
+        if (b->closed) return;                                 // sliding_window.rs:183-185
+        while (b->queue.size() < b->window_size) {            // sliding_window.rs:187-201
+          if (b->closed) return;
+          b->cv.wait(l);
+        }
+        for (uint32_t i = 0; i < b->window_size; ++i) {       // the first window_size batches, oldest first (:112-131)
+          bs.push_back(b->queue[i].batch);                     // shared buffers: the batches stay queued for the next window
+          got_acks.push_back(b->queue[i].ack);                 // VecAck of every batch in the window (:140)
+        }
+        for (uint32_t i = 0; i < b->slide_size && !b->queue.empty(); ++i) b->queue.pop_front();  // :144-148
       }
       Batch r = concat_device(bs, lease.s);
       export_host(r, lease.s, out, out_schema);
@@ -342,5 +386,85 @@ int ark_buffer_close(ark_buf_t* b) {
 }
 
 void ark_buffer_destroy(ark_buf_t* b) { delete b; }
+
+// ---- `batch` processor (processor/batch.rs) -----------------------------------------------------------
+struct ark_batcher {
+  std::mutex mu;
+  uint64_t count = 0, timeout_ms = 0;
+  std::vector<Batch> held;                 // device-resident
+  Clock::time_point last_flush = Clock::now();  // batch.rs:49 (creation), :90-92 (each flush)
+};
+
+int ark_batch_create(const char* config_json, ark_batcher_t** out) {
+  return guarded([&] {
+    if (!out) fail(ARK_ERR_PROCESS, "null output handle");
+    *out = nullptr;
+    if (!config_json) fail(ARK_ERR_CONFIG, "Batch processor configuration is missing");  // batch.rs:135-139
+    JsonValue cfg = parse_json(config_json);
+    if (cfg.kind == JsonValue::Null) fail(ARK_ERR_CONFIG, "Batch processor configuration is missing");
+    if (cfg.kind != JsonValue::Object) fail(ARK_ERR_SERIALIZATION, "invalid type: expected a batch processor configuration object");
+    auto u64_field = [&](const char* key) -> uint64_t {
+      const JsonValue* v = cfg.get(key);
+      if (!v) fail(ARK_ERR_SERIALIZATION, std::string("missing field `") + key + "` (BatchProcessorConfig)");
+      if (v->kind != JsonValue::Number || !v->is_int || v->i64 < 0) fail(ARK_ERR_SERIALIZATION, std::string("invalid value for `") + key + "`: expected an unsigned integer");
+      return (uint64_t)v->i64;
+    };
+    auto b = std::make_unique<ark_batcher>();
+    b->count = u64_field("count");
+    b->timeout_ms = u64_field("timeout_ms");
+    *out = b.release();
+  });
+}
+
+static void batcher_flush_locked(ark_batcher* b, ArrowArray* out, ArrowSchema* out_schema) {
+  if (b->held.empty()) return;  // Ok(vec![]) → ProcessResult::None (batch.rs:77-79, 107-108)
+  StreamLease lease;
+  Batch r = concat_device(b->held, lease.s);
+  export_host(r, lease.s, out, out_schema);
+  b->held.clear();
+  b->last_flush = Clock::now();
+}
+
+int ark_batch_process(ark_batcher_t* b, ArrowArray* in, ArrowSchema* in_schema, ArrowArray* out, ArrowSchema* out_schema) {
+  BufferPtr in_owner = adopt_array(in);
+  return guarded([&] {
+    if (!b) fail(ARK_ERR_PROCESS, "null batch processor");
+    memset(out, 0, sizeof(*out));
+    if (out_schema) memset(out_schema, 0, sizeof(*out_schema));
+    const ArrowArray* arr = (const ArrowArray*)in_owner.get();
+    if (!arr) fail(ARK_ERR_PROCESS, "input array already released");
+    Batch batch;
+    {
+      StreamLease lease;
+      batch = import_host(arr, in_schema, nullptr, lease.s);
+      ARK_CUDA(cudaStreamSynchronize(lease.s));
+    }
+    std::lock_guard<std::mutex> l(b->mu);
+    b->held.push_back(std::move(batch));  // batch.rs:98-102
+    const bool by_count = b->held.size() >= b->count;  // batch.rs:56-58
+    const bool by_time = (uint64_t)std::chrono::duration_cast<std::chrono::milliseconds>(Clock::now() - b->last_flush).count() >= b->timeout_ms;  // :60-65
+    if (by_count || by_time) batcher_flush_locked(b, out, out_schema);
+  });
+}
+
+int ark_batch_flush(ark_batcher_t* b, ArrowArray* out, ArrowSchema* out_schema) {
+  return guarded([&] {
+    if (!b) fail(ARK_ERR_PROCESS, "null batch processor");
+    memset(out, 0, sizeof(*out));
+    if (out_schema) memset(out_schema, 0, sizeof(*out_schema));
+    std::lock_guard<std::mutex> l(b->mu);
+    batcher_flush_locked(b, out, out_schema);
+  });
+}
+
+int ark_batch_close(ark_batcher_t* b) {  // batch.rs:118-123
+  return guarded([&] {
+    if (!b) fail(ARK_ERR_PROCESS, "null batch processor");
+    std::lock_guard<std::mutex> l(b->mu);
+    b->held.clear();
+  });
+}
+
+void ark_batch_destroy(ark_batcher_t* b) { delete b; }
 
 }  // extern "C"

@@ -107,6 +107,9 @@ class ProcessResult:
     def is_none(self):
         return self.kind == "None"
 
+    def is_empty(self):  # ProcessResult::is_empty, core/lib.rs
+        return len(self.batches) == 0
+
     def into_vec(self):
         return list(self.batches)
 
@@ -259,6 +262,53 @@ class ArrowToJsonProcessor(_NativeProcessor):
         super().__init__(config)
 
 
+class BatchProcessor(Processor):
+    """`type: batch` {count, timeout_ms} — processor/batch.rs:37-124.  Holds the incoming batches in HBM and
+    returns their concatenation once `count` of them are held or `timeout_ms` has passed since the last flush."""
+
+    def __init__(self, config: Optional[dict]):
+        handle = C.c_void_p()
+        cfg = None if config is None else json.dumps(config).encode()
+        _check(L.lib().ark_batch_create(cfg, C.byref(handle)))
+        self._h = handle
+        self.config = config
+
+    def _result(self, out_arr, out_sch, input_name=None) -> ProcessResult:
+        if not out_arr.release:
+            return ProcessResult.none()
+        return ProcessResult.single(MessageBatch(F.import_record_batch(out_arr, out_sch), input_name))
+
+    def process(self, msg_batch) -> ProcessResult:
+        mb = msg_batch if isinstance(msg_batch, MessageBatch) else MessageBatch(msg_batch)
+        arr, sch = F.export_record_batch(mb.record_batch)
+        out_arr, out_sch = L.ArrowArray(), L.ArrowSchema()
+        try:
+            status = L.lib().ark_batch_process(self._h, C.byref(arr), C.byref(sch), C.byref(out_arr), C.byref(out_sch))
+        finally:
+            F.release_schema(sch)
+            F.release_array(arr)
+        _check(status)
+        return self._result(out_arr, out_sch)
+
+    def flush(self) -> ProcessResult:
+        """BatchProcessor::flush (batch.rs:72-92): Vec<MessageBatchRef> of zero or one batch."""
+        out_arr, out_sch = L.ArrowArray(), L.ArrowSchema()
+        _check(L.lib().ark_batch_flush(self._h, C.byref(out_arr), C.byref(out_sch)))
+        return self._result(out_arr, out_sch)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _check(L.lib().ark_batch_close(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                L.lib().ark_batch_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
 # ---- registry (core/processor/mod.rs:107-129) --------------------------------------------------------
 _PROCESSOR_BUILDERS: dict[str, Callable[[Optional[str], Optional[dict]], Processor]] = {}
 
@@ -282,7 +332,8 @@ def build_processor(config: dict) -> Processor:
 
 def init() -> None:
     """plugin::processor::init for the hot-path processors (processor/mod.rs:28-35)."""
-    for t, cls in (("sql", SqlProcessor), ("json_to_arrow", JsonToArrowProcessor), ("arrow_to_json", ArrowToJsonProcessor)):
+    for t, cls in (("sql", SqlProcessor), ("json_to_arrow", JsonToArrowProcessor), ("arrow_to_json", ArrowToJsonProcessor),
+                   ("batch", BatchProcessor)):
         if t not in _PROCESSOR_BUILDERS:
             register_processor_builder(t, lambda name, cfg, _c=cls: _c(cfg))
 

@@ -92,7 +92,8 @@ typedef enum ark_status {
 } ark_status;
 
 typedef struct ark_proc ark_proc_t; /* a built Processor (sql / json_to_arrow / arrow_to_json)       */
-typedef struct ark_buf ark_buf_t;   /* a built Buffer (memory / session_window / tumbling_window)    */
+typedef struct ark_buf ark_buf_t;   /* a built Buffer (memory / session_window / tumbling_window / sliding_window) */
+typedef struct ark_batcher ark_batcher_t; /* a built `batch` processor                                  */
 
 /* ---- library ---- */
 /* Bind the calling process to CUDA device `device` (-1: keep current) and warm the pools.
@@ -150,8 +151,10 @@ int ark_concat_batches_device(int n, struct ArrowDeviceArray* ins, struct ArrowS
 /* ---- buffers: replace {Memory,SessionWindow,TumblingWindow}BufferBuilder::build and
  *      Buffer::{write,read,flush,close}: buffer/memory.rs:142-237, session_window.rs:97-159,
  *      tumbling_window.rs:90-145, window.rs:99-190 ---- */
-/* kind: "memory" | "session_window" | "tumbling_window"; config_json = the buffer's YAML as JSON
- * ({"capacity":N,"timeout":"1s"} | {"gap":"1s","join":{...}?} | {"interval":"1s","join":{...}?});
+/* kind: "memory" | "session_window" | "tumbling_window" | "sliding_window" (buffer/sliding_window.rs:
+ * 52-238, builder checks :255-270); config_json = the buffer's YAML as JSON
+ * ({"capacity":N,"timeout":"1s"} | {"gap":"1s","join":{...}?} | {"interval":"1s","join":{...}?} |
+ *  {"window_size":N,"interval":"1s","slide_size":M});
  * input_names_json: JSON array of the input names Resource.input_names held at build time
  * (multiple_inputs.rs:133-142), or NULL. */
 int ark_buffer_create(const char* kind, const char* config_json, const char* input_names_json,
@@ -168,6 +171,19 @@ int ark_buffer_read(ark_buf_t* b, struct ArrowArray* out, struct ArrowSchema* ou
 int ark_buffer_flush(ark_buf_t* b);
 int ark_buffer_close(ark_buf_t* b);
 void ark_buffer_destroy(ark_buf_t* b);
+
+/* ---- `batch` processor: replaces BatchProcessorBuilder::build and BatchProcessor::{process,flush,close},
+ *      crates/arkflow-plugin/src/processor/batch.rs:126-143, 95-124, 72-92 ---- */
+/* config_json: {"count": N, "timeout_ms": T}; NULL → ARK_ERR_CONFIG ("Batch processor configuration is
+ * missing", batch.rs:135-139).  process() keeps the batch in HBM; when `count` batches are held or
+ * `timeout_ms` has passed since the last flush it returns their concatenation (ProcessResult::Single),
+ * otherwise out->release stays NULL (ProcessResult::None). */
+int ark_batch_create(const char* config_json, ark_batcher_t** out);
+int ark_batch_process(ark_batcher_t* b, struct ArrowArray* in, struct ArrowSchema* in_schema,
+                      struct ArrowArray* out, struct ArrowSchema* out_schema);
+int ark_batch_flush(ark_batcher_t* b, struct ArrowArray* out, struct ArrowSchema* out_schema);
+int ark_batch_close(ark_batcher_t* b);
+void ark_batch_destroy(ark_batcher_t* b);
 
 /* ---- multi-GPU GROUP BY / JOIN building blocks (device-resident).  The
  *      exchange between them is the caller's NCCL all-to-all; nothing like this exists in the

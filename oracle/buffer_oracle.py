@@ -47,3 +47,28 @@ def window_drain(writes: list[tuple[Optional[str], pa.RecordBatch]], join: Optio
     if not all(n in tables for n in input_names):
         return pa.RecordBatch.from_arrays([], schema=pa.schema([]))
     return sql_join(tables, join["query"])
+
+
+def sliding_windows(writes: list[pa.RecordBatch], window_size: int, slide_size: int) -> list[pa.RecordBatch]:
+    """SlidingWindow::process_slide repeated until fewer than window_size batches remain
+    (buffer/sliding_window.rs:104-158): a window is the first window_size queued batches concatenated in
+    arrival order; then slide_size batches leave the front of the queue.  PARITY: the reference asserts
+    only that a window is produced (sliding_window.rs:396-418) — contents unpinned."""
+    q = list(writes)
+    out = []
+    while len(q) >= window_size:
+        out.append(concat(q[:window_size]))
+        del q[:slide_size]
+    return out
+
+
+def batch_processor(writes: list[pa.RecordBatch], count: int) -> list[pa.RecordBatch]:
+    """BatchProcessor::process by count only (processor/batch.rs:95-116): every `count`-th message returns
+    the concatenation of the held ones.  batch.rs:170-186 pins `batch.len() == 2` for count = 2."""
+    out, held = [], []
+    for rb in writes:
+        held.append(rb)
+        if len(held) >= count:
+            out.append(concat(held))
+            held = []
+    return out

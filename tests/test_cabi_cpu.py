@@ -88,3 +88,29 @@ def test_split_batch_matches_reference_rules():
     parts = split_batch(rb, 64)           # 64 * 8192 >= 100000 → 8192-row chunks
     assert [p.num_rows for p in parts][:2] == [8192, 8192] and sum(p.num_rows for p in parts) == 100_000
     assert len(split_batch(rb, 0)) == 1 or sum(p.num_rows for p in split_batch(rb, 0)) == 100_000
+
+
+def test_sliding_window_and_batch_builders_validate_config(lib):
+    # buffer/sliding_window.rs:248-270, 318-394 and processor/batch.rs:135-139 — all decided before any CUDA call
+    from arkflow_b200.buffer import SlidingWindow, build_buffer
+    from arkflow_b200.processor import BatchProcessor
+
+    for cfg, text in (({"window_size": 0, "interval": "1s", "slide_size": 5}, "window_size must be greater than 0"),
+                      ({"window_size": 10, "interval": "1s", "slide_size": 0}, "slide_size must be greater than 0"),
+                      ({"window_size": 5, "interval": "1s", "slide_size": 10}, "window_size must be greater than slide_size")):
+        with pytest.raises(ArkError) as e:
+            build_buffer({"type": "sliding_window", **cfg})
+        assert e.value.kind == "Config" and text in e.value.message
+    with pytest.raises(ArkError) as e:
+        SlidingWindow(None)
+    assert e.value.kind == "Config"
+    with pytest.raises(ArkError) as e:
+        SlidingWindow({"window_size": 3, "interval": "soon", "slide_size": 1})
+    assert e.value.kind == "Serialization"
+    with pytest.raises(ArkError) as e:
+        BatchProcessor(None)
+    assert e.value.kind == "Config" and e.value.message == "Batch processor configuration is missing"
+    with pytest.raises(ArkError) as e:
+        BatchProcessor({"count": 2})
+    assert e.value.kind == "Serialization"
+    BatchProcessor({"count": 2, "timeout_ms": 10}).close()
