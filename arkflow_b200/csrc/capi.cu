@@ -1,6 +1,9 @@
 // capi.cu — extern "C" entry points declared in include/arkflow_b200.h.
 #include <cstring>
 
+#include <map>
+#include <mutex>
+
 #include "engine.h"
 
 using namespace ark;
@@ -305,6 +308,120 @@ int ark_arrow_to_json_process(ark_proc_t* p, ArrowArray* in, ArrowSchema* in_sch
     Batch b = import_host(arr, in_schema, nullptr, lease.s);
     Batch r = arrow_to_json_device(*p->impl, b, lease.s);
     export_host(r, lease.s, out, out_schema);
+  });
+}
+
+// ---- expr::evaluate_expr (plugin/expr/mod.rs:92-122) ---------------------------------------------------
+namespace {
+
+bool references_column(const Expr& e) {
+  if (e.kind == Expr::Column || e.kind == Expr::Star) return true;
+  for (auto& a : e.args) if (references_column(*a)) return true;
+  return false;
+}
+
+struct CachedExpr { std::shared_ptr<SqlProcessor> proc; bool scalar; };
+
+// EXPR_CACHE (expr/mod.rs:27-28): expression text → bound processor (plans are cached per schema inside it)
+CachedExpr expr_processor(const char* text) {
+  static std::mutex mu;
+  static std::map<std::string, CachedExpr> cache;
+  {
+    std::lock_guard<std::mutex> l(mu);
+    auto it = cache.find(text);
+    if (it != cache.end()) return it->second;
+  }
+  ExprPtr e = parse_sql_expr(text);
+  CachedExpr ce;
+  ce.scalar = !references_column(*e);
+  if (e->kind == Expr::Literal && e->lit_type == DType::Utf8) {  // a bare string: the one-argument concat of it
+    auto f = std::make_unique<Expr>();
+    f->kind = Expr::Func; f->name = "concat"; f->args.push_back(std::move(e));
+    e = std::move(f);
+  }
+  auto p = std::make_shared<SqlProcessor>();
+  p->query_text = text;
+  p->ast.from.name = p->table_name;
+  SelectItem it;
+  it.expr = std::move(e);
+  it.alias = "value";
+  p->ast.select.push_back(std::move(it));
+  ce.proc = p;
+  std::lock_guard<std::mutex> l(mu);
+  if (cache.size() > 256) cache.clear();
+  cache[text] = ce;
+  return ce;
+}
+
+Batch evaluate_expr_on(const CachedExpr& ce, Batch& in, const std::vector<Field>& fields, cudaStream_t stream) {
+  auto plan = ce.proc->plan_for(ce.scalar ? std::vector<Field>{} : fields);
+  if (plan->kind != Plan::FilterProject)
+    fail(ARK_ERR_PROCESS, "Error during planning: aggregate functions are not valid in a scalar expression");
+  if (ce.scalar) {
+    Batch one;
+    one.num_rows = 1;
+    return ce.proc->execute(*plan, one, stream);
+  }
+  if (in.num_rows == 0) {  // an empty array of the expression's type
+    Batch out;
+    Column c;
+    c.field.name = "value"; c.field.nullable = true; c.length = 0;
+    c.field.type = (!plan->final_items.empty() && plan->final_items[0].is_concat) ? DType::Utf8 : plan->outputs[0].src.type;
+    BufferPtr z = device_alloc(16);
+    ARK_CUDA(cudaMemsetAsync(z.get(), 0, 16, stream));
+    c.data = (const uint8_t*)z.get(); c.data_bytes = 0;
+    if (c.field.type == DType::Utf8 || c.field.type == DType::Binary) { c.offsets = (const int32_t*)z.get(); c.first_offset = 0; }
+    c.owners = {z};
+    out.cols.push_back(c);
+    return out;
+  }
+  return ce.proc->execute(*plan, in, stream);
+}
+
+}  // namespace
+
+int ark_expr_evaluate(const char* expr, ArrowArray* in, ArrowSchema* in_schema, ArrowArray* out, ArrowSchema* out_schema, int* is_scalar) {
+  BufferPtr in_owner = adopt_array(in);
+  return guarded([&] {
+    if (!expr || !out) fail(ARK_ERR_PROCESS, "null argument");
+    const ArrowArray* arr = (const ArrowArray*)in_owner.get();
+    if (!arr) fail(ARK_ERR_PROCESS, "input array already released");
+    CachedExpr ce = expr_processor(expr);
+    if (is_scalar) *is_scalar = ce.scalar ? 1 : 0;
+    std::vector<Field> fields = schema_fields(in_schema);
+    auto plan = ce.proc->plan_for(ce.scalar ? std::vector<Field>{} : fields);
+    StreamLease lease;
+    Batch b;
+    if (!ce.scalar) {
+      std::vector<bool> mask = needed_mask(*plan, fields.size());
+      b = import_host(arr, in_schema, &mask, lease.s);
+    }
+    Batch r = evaluate_expr_on(ce, b, fields, lease.s);
+    export_host(r, lease.s, out, out_schema);
+  });
+}
+
+int ark_expr_evaluate_device(const char* expr, ArrowDeviceArray* in, ArrowSchema* in_schema, ArrowDeviceArray* out, ArrowSchema* out_schema,
+                             int* is_scalar) {
+  BufferPtr in_owner = adopt_array(&in->array);
+  return guarded([&] {
+    if (!expr || !out) fail(ARK_ERR_PROCESS, "null argument");
+    if (!in_owner) fail(ARK_ERR_PROCESS, "input array already released");
+    ArrowDeviceArray view = *in;
+    view.array = *(const ArrowArray*)in_owner.get();
+    CachedExpr ce = expr_processor(expr);
+    if (is_scalar) *is_scalar = ce.scalar ? 1 : 0;
+    std::vector<Field> fields = schema_fields(in_schema);
+    auto plan = ce.proc->plan_for(ce.scalar ? std::vector<Field>{} : fields);
+    StreamLease lease;
+    Batch b;
+    if (!ce.scalar) {
+      std::vector<bool> mask = needed_mask(*plan, fields.size());
+      b = import_device(&view, in_schema, &mask, in_owner);
+    }
+    Batch r = evaluate_expr_on(ce, b, fields, lease.s);
+    ARK_CUDA(cudaStreamSynchronize(lease.s));
+    export_device(r, out, out_schema);
   });
 }
 

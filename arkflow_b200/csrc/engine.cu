@@ -22,10 +22,12 @@ std::unique_ptr<SqlProcessor> SqlProcessor::from_config(const char* config_json)
     if (t->kind == JsonValue::String) p->table_name = t->str;
     else if (t->kind != JsonValue::Null) fail(ARK_ERR_SERIALIZATION, "invalid type for `table_name`: expected a string");
   }
+  bool resolved = false;  // the shim owns Resource.temporary: it checks the names (sql.rs:70-86) and says so
+  if (const JsonValue* r = cfg.get("temporaries_resolved")) resolved = r->kind == JsonValue::Bool && r->b;
   if (const JsonValue* tl = cfg.get("temporary_list")) {
-    if (tl->kind == JsonValue::Array && !tl->arr.empty()) {
-      // sql.rs:70-86: temporaries are looked up in Resource; this library has no Temporary registry,
-      // so a configured temporary is by construction "not found".
+    if (tl->kind == JsonValue::Array && !tl->arr.empty() && !resolved) {
+      // sql.rs:70-86: temporaries are looked up in Resource; without the shim's confirmation a configured
+      // temporary is by construction "not found".
       const JsonValue* nm = tl->arr[0].get("name");
       fail(ARK_ERR_PROCESS, "Temporary " + (nm && nm->kind == JsonValue::String ? nm->str : std::string("?")) + " not found");
     }
@@ -72,7 +74,10 @@ std::shared_ptr<const Plan> SqlProcessor::join_plan_for(const std::vector<std::s
 
 Batch SqlProcessor::execute(const Plan& plan, Batch& in, cudaStream_t stream) {
   switch (plan.kind) {
-    case Plan::FilterProject: return run_filter_project(plan, in, stream);
+    case Plan::FilterProject: {
+      Batch r = run_filter_project(plan, in, stream);
+      return plan.concats.empty() ? r : apply_concats(plan, r, stream);
+    }
     case Plan::Aggregate: return run_aggregate(plan, in, stream);
     default: fail(ARK_ERR_PROCESS, "internal: join plan executed through the single-table path");
   }

@@ -53,6 +53,23 @@ struct PostItem {  // one item of the SELECT list of an aggregate query
   std::string name;
 };
 
+// concat(a, b, …) of Utf8 columns and string literals (datafusion-functions' ConcatFunc: NULL arguments
+// count as empty strings, the result is never NULL).  Evaluated after the row kernels, on the surviving
+// rows: its column arguments ride along as hidden PassThrough outputs.
+struct ConcatPart {
+  bool is_literal = false;
+  std::string literal;
+  int out_index = -1;   // index into Plan::outputs (visible or hidden)
+};
+struct ConcatItem {
+  std::string name;
+  std::vector<ConcatPart> parts;
+};
+struct FinalItem {      // one column of the result, in SELECT order
+  bool is_concat = false;
+  int index = 0;        // Plan::outputs index, or Plan::concats index
+};
+
 struct Plan {
   enum Kind { FilterProject, Aggregate, Join } kind = FilterProject;
   std::vector<Field> input_fields;   // of table 0
@@ -64,6 +81,8 @@ struct Plan {
   std::vector<OutputCol> outputs;
   bool identity = false;             // SELECT * with no WHERE: output = input, no kernel
   int64_t limit = -1;
+  std::vector<ConcatItem> concats;   // empty ⇒ the result is `outputs` as is
+  std::vector<FinalItem> final_items;
   // Aggregate
   std::vector<ValueSource> keys;     // group keys (PassThrough only)
   std::vector<std::string> key_names;

@@ -377,6 +377,7 @@ Plan bind_query(const Query& q, const std::string& table_name, const std::vector
   if (!has_agg) {
     plan.kind = Plan::FilterProject;
     bool all_star = true;
+    std::vector<std::pair<int, const SelectItem*>> concat_items;
     for (auto& it : q.select) {
       if (it.is_star) {
         if (!it.star_qualifier.empty() && it.star_qualifier != b.table)
@@ -388,6 +389,12 @@ Plan bind_query(const Query& q, const std::string& table_name, const std::vector
           oc.src.kind = ValueSource::PassThrough; oc.src.slot = b.slot_of((int)c); oc.src.type = f.type; oc.src.nullable = f.nullable;
           plan.outputs.push_back(oc);
         }
+      } else if (it.expr->kind == Expr::Func && it.expr->name == "concat") {
+        all_star = false;
+        concat_items.push_back({(int)plan.outputs.size(), &it});  // bound after the visible outputs
+        OutputCol placeholder;
+        placeholder.name = "\x01concat";
+        plan.outputs.push_back(placeholder);
       } else {
         all_star = false;
         OutputCol oc;
@@ -395,6 +402,45 @@ Plan bind_query(const Query& q, const std::string& table_name, const std::vector
         oc.name = !it.alias.empty() ? it.alias : (it.expr->kind == Expr::Column ? it.expr->name : display(*it.expr, b.table));
         plan.outputs.push_back(oc);
       }
+    }
+    if (!concat_items.empty()) {
+      // visible outputs keep their order; placeholders are dropped and the concat sources appended (hidden)
+      std::vector<OutputCol> visible;
+      std::vector<int> new_index(plan.outputs.size(), -1);
+      for (size_t i = 0; i < plan.outputs.size(); ++i)
+        if (plan.outputs[i].name != "\x01concat") { new_index[i] = (int)visible.size(); visible.push_back(plan.outputs[i]); }
+      size_t next_concat = 0;
+      for (size_t i = 0; i < plan.outputs.size(); ++i) {
+        FinalItem fi;
+        if (new_index[i] >= 0) { fi.index = new_index[i]; }
+        else {
+          const SelectItem& it = *concat_items[next_concat++].second;
+          const Expr& e = *it.expr;
+          if (e.distinct || e.star_arg || e.args.empty()) plan_error("Error during planning: concat expects at least one argument");
+          ConcatItem ci;
+          ci.name = !it.alias.empty() ? it.alias : display(e, b.table);
+          for (auto& a : e.args) {
+            ConcatPart part;
+            if (a->kind == Expr::Literal && a->lit_type == DType::Utf8) { part.is_literal = true; part.literal = a->str; }
+            else if (a->kind == Expr::Literal && a->lit_type == DType::Null) { part.is_literal = true; }
+            else if (a->kind == Expr::Column) {
+              ValueSource v = b.value_source(*a);
+              if (v.type != DType::Utf8) unsupported(std::string("concat() over a ") + dtype_name(v.type) + " argument");
+              OutputCol hidden;
+              hidden.name = "\x01src" + std::to_string(visible.size());
+              hidden.src = v;
+              part.out_index = (int)visible.size();
+              visible.push_back(hidden);
+            } else unsupported("concat() over a computed argument");
+            ci.parts.push_back(part);
+          }
+          fi.is_concat = true; fi.index = (int)plan.concats.size();
+          plan.concats.push_back(std::move(ci));
+        }
+        plan.final_items.push_back(fi);
+      }
+      plan.outputs = std::move(visible);
+      all_star = false;
     }
     plan.identity = all_star && q.select.size() == 1 && !plan.has_pred && plan.limit < 0;
     return plan;

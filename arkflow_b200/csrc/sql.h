@@ -75,5 +75,7 @@ struct Query {
 // Throws ArkError(ARK_ERR_PROCESS, "SQL query error: …") on a syntax error (reference: sql.rs:92-98)
 // and ArkError(ARK_ERR_UNSUPPORTED, …) for valid SQL outside the subset (ORDER BY, subqueries, …).
 Query parse_sql(const std::string& sql);
+// One scalar expression (DataFusion's parse_sql_expr); the same error classes as parse_sql.
+ExprPtr parse_sql_expr(const std::string& text);
 
 }  // namespace ark

@@ -451,6 +451,16 @@ struct Parser {
 
 }  // namespace
 
+// SessionContext::parse_sql_expr (plugin/expr/mod.rs:111): one scalar expression, nothing after it.
+ExprPtr parse_sql_expr(const std::string& text) {
+  Parser ps;
+  ps.toks = tokenize(text);
+  if (ps.toks.size() == 1) syntax("Expected an expression, found: EOF");
+  ExprPtr e = ps.parse_expr();
+  if (ps.cur().t != Tok::End) syntax("Expected end of expression, found: " + ps.describe());
+  return e;
+}
+
 Query parse_sql(const std::string& sql) {
   Parser ps;
   ps.toks = tokenize(sql);

@@ -1,0 +1,123 @@
+// string_funcs.cu — string-valued scalar functions of the `sql` processor and of expr::evaluate_expr.
+//
+// concat(a, b, …): datafusion-functions 47 `ConcatFunc` (third-party; reached from
+// crates/arkflow-plugin/src/expr/mod.rs:92-122 — the reference's own test is `concat(name, ' is here')`,
+// expr/mod.rs:148-166 — and from any SELECT list, processor/sql.rs:188-204).  NULL arguments count as
+// empty strings and the result is never NULL.  Runs after the row kernels on the surviving rows:
+// lengths → exclusive scan → one thread per row writes its parts.
+#include <cub/device/device_scan.cuh>
+
+#include "engine.h"
+
+namespace ark {
+
+namespace {
+
+constexpr int CONCAT_MAX_PARTS = 8;
+
+struct ConcatPartView {
+  const uint8_t* data;      // column bytes base, or the literal's bytes
+  const int32_t* offsets;   // nullptr ⇒ literal
+  const uint8_t* validity;
+  int32_t validity_bit0;
+  int32_t lit_len;
+};
+
+struct ConcatParams {
+  int32_t n_parts;
+  int64_t n_rows;
+  ConcatPartView parts[CONCAT_MAX_PARTS];
+};
+
+__device__ __forceinline__ int part_len(const ConcatPartView& p, int64_t r, const uint8_t** src) {
+  if (!p.offsets) { *src = p.data; return p.lit_len; }
+  if (p.validity) { const int64_t b = r + p.validity_bit0; if (!((p.validity[b >> 3] >> (b & 7)) & 1)) return 0; }
+  const int32_t o0 = p.offsets[r];
+  *src = p.data + o0;
+  return p.offsets[r + 1] - o0;
+}
+
+__global__ void concat_lengths_kernel(const __grid_constant__ ConcatParams P, int32_t* lens) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P.n_rows) return;
+  int total = 0;
+  const uint8_t* src;
+  for (int k = 0; k < P.n_parts; ++k) total += part_len(P.parts[k], r, &src);
+  lens[r] = total;
+}
+
+__global__ void concat_write_kernel(const __grid_constant__ ConcatParams P, const int32_t* out_offsets, uint8_t* out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P.n_rows) return;
+  uint8_t* d = out + out_offsets[r];
+  for (int k = 0; k < P.n_parts; ++k) {
+    const uint8_t* src = nullptr;
+    const int len = part_len(P.parts[k], r, &src);
+    for (int i = 0; i < len; ++i) d[i] = src[i];
+    d += len;
+  }
+}
+
+}  // namespace
+
+// Builds the result of a FilterProject plan that holds concat() items: `r` carries plan.outputs (visible
+// columns first, hidden concat sources after them).
+Batch apply_concats(const Plan& plan, Batch& r, cudaStream_t stream) {
+  const int64_t n = r.num_rows;
+  std::vector<Column> made(plan.concats.size());
+  for (size_t ci = 0; ci < plan.concats.size(); ++ci) {
+    const ConcatItem& item = plan.concats[ci];
+    if ((int)item.parts.size() > CONCAT_MAX_PARTS) fail(ARK_ERR_UNSUPPORTED, "concat() with more than 8 arguments");
+    ConcatParams P;
+    memset(&P, 0, sizeof P);
+    P.n_parts = (int)item.parts.size();
+    P.n_rows = n;
+    size_t lit_bytes = 0;
+    for (auto& part : item.parts) if (part.is_literal) lit_bytes += part.literal.size();
+    BufferPtr lit_host = pinned_alloc(lit_bytes + 16), lit_dev = device_alloc(lit_bytes + 16);
+    size_t pos = 0;
+    for (size_t k = 0; k < item.parts.size(); ++k) {
+      const ConcatPart& part = item.parts[k];
+      ConcatPartView& v = P.parts[k];
+      if (part.is_literal) {
+        memcpy((char*)lit_host.get() + pos, part.literal.data(), part.literal.size());
+        v.data = (const uint8_t*)lit_dev.get() + pos; v.offsets = nullptr; v.lit_len = (int32_t)part.literal.size();
+        pos += part.literal.size();
+      } else {
+        const Column& c = r.cols[part.out_index];
+        v.data = c.data; v.offsets = c.offsets; v.validity = c.validity; v.validity_bit0 = (int32_t)c.validity_bit0;
+      }
+    }
+    if (lit_bytes) ARK_CUDA(cudaMemcpyAsync(lit_dev.get(), lit_host.get(), lit_bytes, cudaMemcpyHostToDevice, stream));
+    BufferPtr lens = device_alloc((size_t)(n + 1) * 4), offs = device_alloc((size_t)(n + 1) * 4);
+    ARK_CUDA(cudaMemsetAsync((int32_t*)lens.get() + n, 0, 4, stream));
+    const unsigned grid = (unsigned)std::max<int64_t>(1, ceil_div(n, 256));
+    if (n) { KernelTimer t("concat_lengths_kernel", stream); concat_lengths_kernel<<<grid, 256, 0, stream>>>(P, (int32_t*)lens.get()); }
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, (int32_t*)lens.get(), (int32_t*)offs.get(), (int)(n + 1), stream);
+    BufferPtr tmp = device_alloc(tb + 16);
+    note_launch("cub::DeviceScan::ExclusiveSum");
+    cub::DeviceScan::ExclusiveSum(tmp.get(), tb, (int32_t*)lens.get(), (int32_t*)offs.get(), (int)(n + 1), stream);
+    BufferPtr h = pinned_alloc(64);
+    ARK_CUDA(cudaMemcpyAsync(h.get(), (int32_t*)offs.get() + n, 4, cudaMemcpyDeviceToHost, stream));
+    ARK_CUDA(cudaStreamSynchronize(stream));
+    const int32_t total = *(const int32_t*)h.get();
+    if (total < 0) fail(ARK_ERR_PROCESS, "Collection query results error: Arrow error: offset overflow, concat() result exceeds 2 GiB");
+    BufferPtr bytes = device_alloc((size_t)total + 16);
+    if (n) { KernelTimer t("concat_write_kernel", stream); concat_write_kernel<<<grid, 256, 0, stream>>>(P, (const int32_t*)offs.get(), (uint8_t*)bytes.get()); }
+    ARK_CUDA(cudaGetLastError());
+    ARK_CUDA(cudaStreamSynchronize(stream));  // the literal staging blocks go back to the pool
+    Column& c = made[ci];
+    c.field.name = item.name; c.field.type = DType::Utf8; c.field.nullable = true; c.length = n;
+    c.offsets = (const int32_t*)offs.get(); c.data = (const uint8_t*)bytes.get(); c.data_bytes = total; c.first_offset = 0;
+    c.validity = nullptr; c.null_count = 0;
+    c.owners = {offs, bytes};
+  }
+  Batch out;
+  out.num_rows = n;
+  out.input_name = r.input_name;
+  for (auto& fi : plan.final_items) out.cols.push_back(fi.is_concat ? made[fi.index] : r.cols[fi.index]);
+  return out;
+}
+
+}  // namespace ark

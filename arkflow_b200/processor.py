@@ -194,6 +194,48 @@ class SqlProcessor(_NativeProcessor):
 
     _create, _process, _process_device = "ark_sql_create", "ark_sql_process", "ark_sql_process_device"
 
+    def __init__(self, config: Optional[dict], resource=None):
+        # SqlProcessor::new (sql.rs:68-105): every configured temporary must exist in Resource
+        self._temporaries = []
+        if config and config.get("temporary_list"):
+            from .expr import Expr
+
+            known = getattr(resource, "temporary", None) or {}
+            for t in config["temporary_list"]:
+                for field in ("name", "table_name", "key"):
+                    if field not in t:
+                        raise ArkError(L.ARK_ERR_SERIALIZATION, f"missing field `{field}` (TemporaryConfig)")
+                if t["name"] not in known:
+                    raise ArkError(L.ARK_ERR_PROCESS, f"Temporary {t['name']} not found")
+                self._temporaries.append((known[t["name"]], t["table_name"], Expr.from_config(t["key"])))
+            config = dict(config, temporaries_resolved=True)
+        super().__init__(config)
+
+    def process(self, msg_batch) -> ProcessResult:
+        if not self._temporaries or isinstance(msg_batch, F.DeviceBatch):
+            return super().process(msg_batch)
+        # execute_query with get_temporary_message_batch (sql.rs:108-186): evaluate each key on the batch,
+        # ask the Temporary for its rows, register them next to the batch, run the query
+        from .expr import ColumnarValue, evaluate_expr
+
+        mb = msg_batch if isinstance(msg_batch, MessageBatch) else MessageBatch(msg_batch)
+        if mb.num_rows == 0:
+            return ProcessResult.none()  # sql.rs:211-213
+        tables = {(self.config or {}).get("table_name") or "flow": mb.record_batch}
+        for temporary, table_name, key in self._temporaries:
+            if key.kind == "Value":
+                cv = ColumnarValue.scalar_utf8(key.payload)
+            else:
+                try:
+                    cv = evaluate_expr(key.payload, mb.record_batch)
+                except ArkError as e:
+                    raise ArkError(L.ARK_ERR_PROCESS, f"Evaluate expression failed: {e.message}")
+            data = temporary.get([cv])
+            if data is not None:
+                tables[table_name] = data.record_batch if isinstance(data, MessageBatch) else data
+        out = self.process_tables(tables)
+        return ProcessResult.none() if out is None else ProcessResult.single(MessageBatch(out, mb.input_name))
+
     def process_tables(self, tables: dict[str, pa.RecordBatch]) -> Optional[pa.RecordBatch]:
         """JoinOperation's `ctx.sql(query)` over several registered tables (buffer/join.rs:92-118)."""
         lib = L.lib()

@@ -105,7 +105,11 @@ const char* ark_last_error(void); /* thread-local, valid until the next call on 
 
 /* ---- `sql` processor: replaces SqlProcessorBuilder::build / SqlProcessor::{new,process,close}
  *      crates/arkflow-plugin/src/processor/sql.rs:227-243, 68-105, 208-225 ---- */
-/* config_json = the processor's flattened YAML as JSON: {"query": "...", "table_name": "flow"?}
+/* config_json = the processor's flattened YAML as JSON: {"query": "...", "table_name": "flow"?,
+ * "temporary_list": [{"name","table_name","key"}]?, "temporaries_resolved": true?} — the shim owns
+ * Resource.temporary: it checks each name (sql.rs:70-86: "Temporary X not found"), sets
+ * temporaries_resolved, evaluates the keys with ark_expr_evaluate and registers what Temporary::get
+ * returns through ark_sql_process_tables.
  * NULL config → ARK_ERR_CONFIG ("Batch processor configuration is missing", sql.rs:235-239);
  * unparsable SQL → ARK_ERR_PROCESS ("SQL query error: …", sql.rs:92-98) at construction. */
 int ark_sql_create(const char* config_json, ark_proc_t** out);
@@ -136,6 +140,17 @@ int ark_json_to_arrow_process_device(ark_proc_t* p, struct ArrowDeviceArray* in,
 int ark_arrow_to_json_create(const char* config_json, ark_proc_t** out);
 int ark_arrow_to_json_process(ark_proc_t* p, struct ArrowArray* in, struct ArrowSchema* in_schema,
                               struct ArrowArray* out, struct ArrowSchema* out_schema);
+
+/* ---- expr::evaluate_expr: replaces crates/arkflow-plugin/src/expr/mod.rs:92-122 (the key expression
+ *      of a `temporary_list` entry, processor/sql.rs:151-186) ---- */
+/* Parses `expr` as ONE SQL scalar expression against the batch schema and evaluates it on the device.
+ * The result is a one-column batch: as many rows as the input (ColumnarValue::Array), or ONE row with
+ * *is_scalar = 1 when the expression references no column (ColumnarValue::Scalar).  Parsed expressions
+ * are cached by text (EXPR_CACHE, expr/mod.rs:27-28).  Errors → ARK_ERR_PROCESS / ARK_ERR_UNSUPPORTED. */
+int ark_expr_evaluate(const char* expr, struct ArrowArray* in, struct ArrowSchema* in_schema,
+                      struct ArrowArray* out, struct ArrowSchema* out_schema, int* is_scalar);
+int ark_expr_evaluate_device(const char* expr, struct ArrowDeviceArray* in, struct ArrowSchema* in_schema,
+                             struct ArrowDeviceArray* out, struct ArrowSchema* out_schema, int* is_scalar);
 
 /* Processor::close (sql.rs:222-224, json.rs:63-65) and drop. */
 int ark_proc_close(ark_proc_t* p);

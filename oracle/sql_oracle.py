@@ -397,6 +397,17 @@ class _Parser:
         self.err("an expression")
 
 
+def parse_expr(text: str) -> E:
+    """SessionContext::parse_sql_expr: one scalar expression and nothing after it (expr/mod.rs:111)."""
+    ps = _Parser(text)
+    if len(ps.t) == 1:
+        raise OracleError("Process", "SQL query error: Expected an expression, found: EOF")
+    e = ps.expr()
+    if ps.p != len(ps.t) - 1:
+        ps.err("end of expression")
+    return e
+
+
 def parse(sql: str) -> Query:
     toks = _tokenize(sql)
     if len(toks) == 1:
@@ -542,10 +553,20 @@ class _Ctx:
             self.type_of(e.args[0])
             return "Boolean"
         if e.kind == "func":
+            if e.name == "concat" and e.args:
+                for a in e.args:  # the library's subset: Utf8 columns and string / NULL literals
+                    if a.kind == "col":
+                        if self.type_of(a) != "Utf8":
+                            raise OracleError("Unsupported", f"concat() over a {self.type_of(a)} argument")
+                    elif not (a.kind == "lit" and a.vtype in ("Utf8", "Null")):
+                        raise OracleError("Unsupported", "concat() over a computed argument")
+                return "Utf8"
             raise OracleError("Unsupported", f"scalar function {e.name}()")
         raise AssertionError
 
     def nullable_of(self, e: E) -> bool:
+        if e.kind == "func" and e.name == "concat":
+            return True  # ScalarUDFImpl::is_nullable default; the values themselves are never NULL
         if e.kind == "col":
             return self.rb.schema.field(self.resolve(e)).nullable
         if e.kind == "lit":
@@ -654,7 +675,20 @@ class _Ctx:
             r = a.valid if e.negated else ~a.valid
             return Vec("Boolean", r.copy(), np.ones(n, dtype=bool))
         if e.kind == "func":
-            raise OracleError("Unsupported", f"scalar function {e.name}()")
+            self.type_of(e)
+            # datafusion-functions ConcatFunc: NULL arguments count as empty strings, the result is never NULL
+            import pyarrow.compute as pc
+
+            parts = []
+            for a in e.args:
+                v = self.eval(a, sel)
+                if v.dtype == "Null":
+                    parts.append(pa.array([""] * n, type=pa.utf8()))
+                else:
+                    arr = v.values if isinstance(v.values, (pa.Array, pa.ChunkedArray)) else pa.array(v.values)
+                    parts.append(pc.if_else(pa.array(v.valid), arr, pa.scalar("", pa.utf8())))
+            out = pc.binary_join_element_wise(*parts, pa.scalar("", pa.utf8())) if n else pa.array([], type=pa.utf8())
+            return Vec("Utf8", out, np.ones(n, dtype=bool))
         raise AssertionError
 
 
@@ -967,3 +1001,28 @@ def sql_join(tables: dict[str, pa.RecordBatch], query: str) -> pa.RecordBatch:
         else:
             raise OracleError("Unsupported", "computed join projection")
     return pa.RecordBatch.from_arrays(cols, schema=pa.schema(fields))
+
+
+# ------------------------------------------------------------------------------------------------
+# expr::evaluate_expr  (crates/arkflow-plugin/src/expr/mod.rs:92-122)
+# ------------------------------------------------------------------------------------------------
+def _references_column(e: E) -> bool:
+    return e.kind == "col" or any(_references_column(a) for a in e.args)
+
+
+def evaluate_expr(text: str, rb: pa.RecordBatch) -> tuple[bool, pa.Array]:
+    """→ (is_scalar, values).  ColumnarValue::Scalar when the expression references no column (a literal
+    evaluates to a scalar, and datum::apply keeps scalar ∘ scalar a scalar), else an array of rb.num_rows.
+    PARITY: pinned by expr/mod.rs:133-212 — `0.9` → Scalar Float64(0.9); concat(name, ' is here') → the three
+    joined strings; `invalid sql` and `1 + name` → errors."""
+    e = parse_expr(text)
+    if _has_agg(e):
+        raise OracleError("Process", "Error during planning: aggregate functions are not valid in a scalar expression")
+    scalar = not _references_column(e)
+    base = pa.RecordBatch.from_arrays([pa.array([0], pa.int64())], names=["\x01dummy"]) if scalar else rb
+    ctx = _Ctx("flow", base)
+    ctx.type_of(e)
+    v = ctx.eval(e)
+    if v.dtype == "Null":
+        raise OracleError("Unsupported", "NULL-typed projection")
+    return scalar, _vec_to_arrow(v)

@@ -114,3 +114,10 @@ def test_sliding_window_and_batch_builders_validate_config(lib):
         BatchProcessor({"count": 2})
     assert e.value.kind == "Serialization"
     BatchProcessor({"count": 2, "timeout_ms": 10}).close()
+
+
+def test_temporary_list_needs_the_shims_confirmation(lib):
+    # sql.rs:70-86: a configured temporary that Resource does not hold is a construction error
+    with pytest.raises(ArkError) as e:
+        SqlProcessor({"query": "SELECT * FROM flow", "temporary_list": [{"name": "redis_temporary", "table_name": "redis_table", "key": {"type": "value", "value": "test"}}]})
+    assert e.value.kind == "Process" and e.value.message == "Temporary redis_temporary not found"
