@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "engine.h"
+#include "stage_store.cuh"
 #include "json_mini.h"
 #include "ryu_tables.h"
 
@@ -239,9 +240,26 @@ __global__ void arrow_to_json_measure_kernel(const __grid_constant__ AjParams P,
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < P.n_rows) lens[r] = emit_row(P, r, nullptr);
 }
-__global__ void arrow_to_json_write_kernel(const __grid_constant__ AjParams P, const int32_t* offsets, uint8_t* out) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < P.n_rows) emit_row(P, r, out + offsets[r]);
+// The lines of one CTA's rows are contiguous in the output: each thread formats its row into a shared-memory
+// image of that range, which then leaves with 16-byte stores (byte-wise stores at a ~65-byte stride straight
+// to global memory cost 1.59 ms per 4·10^6 rows; the formatting itself 0.10 ms).
+constexpr int AJ_THREADS = 128;
+__global__ void __launch_bounds__(AJ_THREADS) arrow_to_json_write_kernel(const __grid_constant__ AjParams P, const int32_t* offsets, uint8_t* out,
+                                                                          int stage_bytes) {
+  extern __shared__ __align__(16) uint8_t aj_stage[];
+  const int64_t r0 = (int64_t)blockIdx.x * AJ_THREADS;
+  const int rows = (int)((P.n_rows - r0) < AJ_THREADS ? (P.n_rows - r0) : AJ_THREADS);
+  const int64_t r = r0 + threadIdx.x;
+  const int32_t bb = offsets[r0];
+  const int tb = offsets[r0 + rows] - bb;
+  if (tb + 16 > stage_bytes) {  // long rows: format straight into global memory
+    if (r < P.n_rows) emit_row(P, r, out + offsets[r]);
+    return;
+  }
+  const int mis = stage_misalignment(out + bb);
+  if (r < P.n_rows) emit_row(P, r, aj_stage + mis + (offsets[r] - bb));
+  __syncthreads();
+  stage_store(out + bb, aj_stage, mis, tb, threadIdx.x, AJ_THREADS);
 }
 
 std::string json_escape_key(const std::string& name) {
@@ -325,7 +343,9 @@ Batch arrow_to_json_device(const Processor& proc, Batch& in, cudaStream_t stream
   BufferPtr bytes = device_alloc((size_t)total + 16);
   if (n) {
     KernelTimer t("arrow_to_json_write_kernel", stream);
-    arrow_to_json_write_kernel<<<grid, 128, 0, stream>>>(P, (const int32_t*)offs.get(), (uint8_t*)bytes.get());
+    // staging window: the average CTA's bytes + 50 %; CTAs whose rows are longer take the direct path
+    const int stage = (int)std::min<int64_t>(44 * 1024, round_up((int64_t)((double)total / (double)n * AJ_THREADS * 1.5) + 256, 1024));
+    arrow_to_json_write_kernel<<<grid, AJ_THREADS, stage, stream>>>(P, (const int32_t*)offs.get(), (uint8_t*)bytes.get(), stage);
   }
   ARK_CUDA(cudaGetLastError());
   Batch out;

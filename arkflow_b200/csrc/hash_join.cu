@@ -12,6 +12,7 @@
 
 #include "engine.h"
 #include "hashkey.cuh"
+#include "stage_store.cuh"
 
 namespace ark {
 
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256) take_bytes_tile_kernel(const uint8_t* dat
     return;
   }
   // staging starts at the destination's misalignment so that shared and global addresses agree mod 16
-  const int mis = (int)(reinterpret_cast<uintptr_t>(out + bb) & 15);
+  const int mis = stage_misalignment(out + bb);
 #pragma unroll
   for (int k = 0; k < TAKE_TILE / 256; ++k) {
     const int i = k * 256 + tid;
@@ -152,15 +153,7 @@ __global__ void __launch_bounds__(256) take_bytes_tile_kernel(const uint8_t* dat
     }
   }
   __syncthreads();
-  uint8_t* gdst = out + bb;
-  const int head = min((16 - mis) & 15, tb);
-  if (tid < head) gdst[tid] = stage[mis + tid];
-  const int body = (tb - head) >> 4;
-  const uint4* sv = reinterpret_cast<const uint4*>(stage + mis + head);  // 16-byte aligned: mis + head ≡ 0 (mod 16) when body > 0
-  uint4* gv = reinterpret_cast<uint4*>(gdst + head);
-  for (int g = tid; g < body; g += 256) gv[g] = sv[g];
-  const int tail0 = head + body * 16;
-  if (tid < tb - tail0) gdst[tail0 + tid] = stage[mis + tail0 + tid];
+  stage_store(out + bb, stage, mis, tb, tid, 256);
 }
 
 // ---- hash repartition ----------------------------------------------------------------------------------

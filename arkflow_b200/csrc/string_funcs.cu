@@ -8,6 +8,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "engine.h"
+#include "stage_store.cuh"
 
 namespace ark {
 
@@ -46,16 +47,33 @@ __global__ void concat_lengths_kernel(const __grid_constant__ ConcatParams P, in
   lens[r] = total;
 }
 
-__global__ void concat_write_kernel(const __grid_constant__ ConcatParams P, const int32_t* out_offsets, uint8_t* out) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= P.n_rows) return;
-  uint8_t* d = out + out_offsets[r];
+__device__ __forceinline__ void concat_row(const ConcatParams& P, int64_t r, uint8_t* d) {
   for (int k = 0; k < P.n_parts; ++k) {
     const uint8_t* src = nullptr;
     const int len = part_len(P.parts[k], r, &src);
     for (int i = 0; i < len; ++i) d[i] = src[i];
     d += len;
   }
+}
+
+// The rows of a CTA are contiguous in the output: build them in shared memory, store them 16 bytes at a time.
+constexpr int CONCAT_THREADS = 256;
+__global__ void __launch_bounds__(CONCAT_THREADS) concat_write_kernel(const __grid_constant__ ConcatParams P, const int32_t* out_offsets, uint8_t* out,
+                                                                       int stage_bytes) {
+  extern __shared__ __align__(16) uint8_t cc_stage[];
+  const int64_t r0 = (int64_t)blockIdx.x * CONCAT_THREADS;
+  const int rows = (int)((P.n_rows - r0) < CONCAT_THREADS ? (P.n_rows - r0) : CONCAT_THREADS);
+  const int64_t r = r0 + threadIdx.x;
+  const int32_t bb = out_offsets[r0];
+  const int tb = out_offsets[r0 + rows] - bb;
+  if (tb + 16 > stage_bytes) {
+    if (r < P.n_rows) concat_row(P, r, out + out_offsets[r]);
+    return;
+  }
+  const int mis = stage_misalignment(out + bb);
+  if (r < P.n_rows) concat_row(P, r, cc_stage + mis + (out_offsets[r] - bb));
+  __syncthreads();
+  stage_store(out + bb, cc_stage, mis, tb, threadIdx.x, CONCAT_THREADS);
 }
 
 }  // namespace
@@ -104,7 +122,11 @@ Batch apply_concats(const Plan& plan, Batch& r, cudaStream_t stream) {
     const int32_t total = *(const int32_t*)h.get();
     if (total < 0) fail(ARK_ERR_PROCESS, "Collection query results error: Arrow error: offset overflow, concat() result exceeds 2 GiB");
     BufferPtr bytes = device_alloc((size_t)total + 16);
-    if (n) { KernelTimer t("concat_write_kernel", stream); concat_write_kernel<<<grid, 256, 0, stream>>>(P, (const int32_t*)offs.get(), (uint8_t*)bytes.get()); }
+    if (n) {
+      const int stage = (int)std::min<int64_t>(44 * 1024, round_up((int64_t)((double)total / (double)n * CONCAT_THREADS * 1.5) + 256, 1024));
+      KernelTimer t("concat_write_kernel", stream);
+      concat_write_kernel<<<grid, CONCAT_THREADS, stage, stream>>>(P, (const int32_t*)offs.get(), (uint8_t*)bytes.get(), stage);
+    }
     ARK_CUDA(cudaGetLastError());
     ARK_CUDA(cudaStreamSynchronize(stream));  // the literal staging blocks go back to the pool
     Column& c = made[ci];

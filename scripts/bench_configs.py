@@ -75,7 +75,7 @@ def main():
 
     results = {"peak_gbs": peak, "rows": args.rows, "keys": args.keys}
     n = args.rows
-    legs = set(args.only.split(",")) if args.only else {"groupby", "join", "concat", "json"}
+    legs = set(args.only.split(",")) if args.only else {"groupby", "join", "concat", "json", "tojson"}
 
     # ---- config 3: GROUP BY ----
     for kind, label in ((0, "int64"), (1, "float64")) if "groupby" in legs else ():
@@ -150,6 +150,27 @@ def main():
         alg = m * (len(msg) + 4) + m * 26
         k = kern["json_parse_kernel"]["avg_ms"]
         results["json_to_arrow"] = {"msgs_per_s_call": m / wall, "ms_per_call": wall * 1e3, "kernel_ms": k,
+                                    "roofline": {"bound": "hbm", "achieved": alg / (k / 1e3) / 1e9 if k else None, "peak": peak,
+                                                 "frac": (alg / (k / 1e3) / 1e9 / peak) if k else None, "algorithmic_bytes_per_launch": alg},
+                                    "kernels": kern}
+    if "tojson" in legs:
+        # ---- arrow_to_json of schema S (host entry point only: the processor appends a Binary column) ----
+        from arkflow_b200.processor import ArrowToJsonProcessor, MessageBatch
+        from oracle.synth import synth_batch
+
+        m = min(n, 1 << 22)
+        rb = synth_batch(m, key_space=args.keys)
+        aproc = ArrowToJsonProcessor({})
+        mb = MessageBatch.new_arrow(rb)
+
+        def astep():
+            aproc.process(mb)
+
+        wall, kern = timed(astep, ["arrow_to_json_measure_kernel", "arrow_to_json_write_kernel"])
+        out_bytes = int(aproc.process(mb).batches[0].record_batch.column("__value__").nbytes)
+        alg = m * 32 + out_bytes
+        k = kern["arrow_to_json_measure_kernel"]["avg_ms"] + kern["arrow_to_json_write_kernel"]["avg_ms"]
+        results["arrow_to_json"] = {"rows_per_s_call_host_to_host": m / wall, "ms_per_call": wall * 1e3, "kernel_ms": k,
                                     "roofline": {"bound": "hbm", "achieved": alg / (k / 1e3) / 1e9 if k else None, "peak": peak,
                                                  "frac": (alg / (k / 1e3) / 1e9 / peak) if k else None, "algorithmic_bytes_per_launch": alg},
                                     "kernels": kern}
