@@ -48,13 +48,12 @@ __global__ void join_build_kernel(ColView kc, int key_kind, int64_t n, Key16* ke
   }
 }
 
-// FILL == false: counts[row] = number of matches.  FILL == true: write the pairs at offsets[row].
-template <bool FILL>
-__global__ void join_probe_kernel(ColView pc, ColView bc, int key_kind, int64_t n, const Key16* keys, const unsigned int* head,
-                                  const unsigned int* next, unsigned long long mask, long long* counts, const long long* offsets,
-                                  unsigned int* out_probe, unsigned int* out_build) {
+// Probe pass: counts[row] = number of matches, match_slot[row] = table slot of the probe key (NO_ROW if none).
+__global__ void join_probe_count_kernel(ColView pc, ColView bc, int key_kind, int64_t n, const Key16* keys, const unsigned int* head,
+                                        const unsigned int* next, unsigned long long mask, long long* counts, unsigned int* match_slot) {
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
     long long c = 0;
+    unsigned int found = NO_ROW;
     if (col_valid(pc, row)) {
       Key16 mine; unsigned long long h;
       make_key(key_kind, pc, row, &mine, &h);
@@ -63,17 +62,27 @@ __global__ void join_probe_kernel(ColView pc, ColView bc, int key_kind, int64_t 
         const Key16 cur = keys[slot];  // the table is read-only during the probe
         if (cur.hi == KEY_EMPTY) break;
         if (key_equal(mine, cur, pc, bc)) {
-          long long o = FILL ? offsets[row] : 0;
-          for (unsigned int b = head[slot]; b != NO_ROW; b = next[b]) {
-            if (FILL) { out_probe[o] = (unsigned int)row; out_build[o] = b; ++o; }
-            ++c;
-          }
+          found = (unsigned int)slot;
+          for (unsigned int b = head[slot]; b != NO_ROW; b = next[b]) ++c;
           break;
         }
         slot = (slot + 1) & mask;
       }
     }
-    if (!FILL) counts[row] = c;
+    counts[row] = c;
+    match_slot[row] = found;
+  }
+}
+
+// Fill pass: the (probe row, build row) pairs at offsets[row]; the slot comes from the count pass (no second
+// hash + probe: 4 sequential bytes per row instead of a random table access).
+__global__ void join_probe_fill_kernel(int64_t n, const unsigned int* head, const unsigned int* next, const unsigned int* match_slot,
+                                       const long long* offsets, unsigned int* out_probe, unsigned int* out_build) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned int slot = match_slot[row];
+    if (slot == NO_ROW) continue;
+    long long o = offsets[row];
+    for (unsigned int b = head[slot]; b != NO_ROW; b = next[b]) { out_probe[o] = (unsigned int)row; out_build[o] = b; ++o; }
   }
 }
 
@@ -290,12 +299,13 @@ Batch run_join(const Plan& plan, Batch& left, Batch& right, cudaStream_t stream)
     KernelTimer t("join_build_kernel", stream);
     join_build_kernel<<<grid_for(nb), 256, 0, stream>>>(bc, key_kind, nb, (Key16*)keys.get(), (unsigned int*)head.get(), (unsigned int*)next.get(), capacity - 1);
   }
-  BufferPtr counts = device_alloc((size_t)(np + 1) * 8), offsets = device_alloc((size_t)(np + 1) * 8);
-  ARK_CUDA(cudaMemsetAsync(counts.get(), 0, (size_t)(np + 1) * 8, stream));
+  if (capacity >= (1ull << 32)) fail(ARK_ERR_UNSUPPORTED, "join build side with 2^31 or more distinct keys");
+  BufferPtr counts = device_alloc((size_t)(np + 1) * 8), offsets = device_alloc((size_t)(np + 1) * 8), match_slot = device_alloc((size_t)std::max<int64_t>(np, 1) * 4);
+  ARK_CUDA(cudaMemsetAsync((long long*)counts.get() + np, 0, 8, stream));
   if (np) {
     KernelTimer t("join_probe_count_kernel", stream);
-    join_probe_kernel<false><<<grid_for(np), 256, 0, stream>>>(pc, bc, key_kind, np, (const Key16*)keys.get(), (const unsigned int*)head.get(),
-                                                               (const unsigned int*)next.get(), capacity - 1, (long long*)counts.get(), nullptr, nullptr, nullptr);
+    join_probe_count_kernel<<<grid_for(np), 256, 0, stream>>>(pc, bc, key_kind, np, (const Key16*)keys.get(), (const unsigned int*)head.get(),
+                                                              (const unsigned int*)next.get(), capacity - 1, (long long*)counts.get(), (unsigned int*)match_slot.get());
   }
   size_t tb = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tb, (long long*)counts.get(), (long long*)offsets.get(), (int)(np + 1), stream);
@@ -310,9 +320,8 @@ Batch run_join(const Plan& plan, Batch& left, Batch& right, cudaStream_t stream)
   BufferPtr probe_idx = device_alloc((size_t)std::max<long long>(pairs, 1) * 4), build_idx = device_alloc((size_t)std::max<long long>(pairs, 1) * 4);
   if (np && pairs) {
     KernelTimer t("join_probe_fill_kernel", stream);
-    join_probe_kernel<true><<<grid_for(np), 256, 0, stream>>>(pc, bc, key_kind, np, (const Key16*)keys.get(), (const unsigned int*)head.get(),
-                                                              (const unsigned int*)next.get(), capacity - 1, nullptr, (const long long*)offsets.get(),
-                                                              (unsigned int*)probe_idx.get(), (unsigned int*)build_idx.get());
+    join_probe_fill_kernel<<<grid_for(np), 256, 0, stream>>>(np, (const unsigned int*)head.get(), (const unsigned int*)next.get(), (const unsigned int*)match_slot.get(),
+                                                             (const long long*)offsets.get(), (unsigned int*)probe_idx.get(), (unsigned int*)build_idx.get());
   }
   ARK_CUDA(cudaGetLastError());
   const unsigned int* lidx = (const unsigned int*)(build_left ? build_idx.get() : probe_idx.get());

@@ -43,3 +43,36 @@ def test_oracle_wrapping_and_division():
     assert out.column(2).to_pylist() == [(2**62) % 3, -((2**62) % 3), 1, -1]
     with pytest.raises(OracleError):
         sql_process(rb, "SELECT v / 0 FROM flow")
+
+
+# ---- pins the reference's tests hold for the §8(f) rows (CPU: the oracle alone) ---------------------------
+def test_oracle_expr_pins():
+    # crates/arkflow-plugin/src/expr/mod.rs:131-146, 148-166, 191-211
+    import pyarrow as pa
+    from oracle.sql_oracle import evaluate_expr
+
+    ints = pa.record_batch({"a": pa.array([4, 230, 21], pa.int32())})
+    scalar, v = evaluate_expr(" 0.9", ints)
+    assert scalar and v.type == pa.float64() and v.to_pylist() == [0.9]
+    names = pa.record_batch({"name": pa.array(["Alice", "Bob", "Charlie"])})
+    scalar, v = evaluate_expr("concat(name, ' is here')", names)
+    assert not scalar and v.to_pylist() == ["Alice is here", "Bob is here", "Charlie is here"]
+    for bad in ("invalid sql", "1 + name"):
+        with pytest.raises(OracleError):
+            evaluate_expr(bad, names)
+
+
+def test_oracle_batch_and_sliding_window_pins():
+    # processor/batch.rs:153-186 (count 2 → one batch of 2 rows); buffer/sliding_window.rs:396-418 (3 writes,
+    # window 3 → a window); sliding_window.rs:420-444 (2 writes < window 3 → nothing)
+    import pyarrow as pa
+    from oracle.buffer_oracle import batch_processor, sliding_windows
+
+    msgs = [pa.record_batch({"__value__": pa.array([f"test{i}".encode()], pa.binary())}) for i in (1, 2)]
+    out = batch_processor(msgs, 2)
+    assert len(out) == 1 and out[0].num_rows == 2
+    assert batch_processor(msgs[:1], 2) == []
+    three = [pa.record_batch({"__value__": pa.array([f"msg{i}".encode()], pa.binary())}) for i in range(3)]
+    w = sliding_windows(three, 3, 2)
+    assert len(w) == 1 and w[0].column(0).to_pylist() == [b"msg0", b"msg1", b"msg2"]
+    assert sliding_windows(three[:2], 3, 1) == []
