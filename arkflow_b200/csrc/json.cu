@@ -65,8 +65,11 @@ struct Cursor {
   const uint8_t* end;
 };
 
+__device__ __forceinline__ bool is_ws(unsigned ch) {  // ' ' \t \n \r: one range test + one bit test
+  return ch <= 0x20u && ((0x100002600ull >> ch) & 1ull);
+}
 __device__ __forceinline__ void skip_ws(Cursor& c) {
-  while (c.p < c.end && (*c.p == ' ' || *c.p == '\n' || *c.p == '\r' || *c.p == '\t')) ++c.p;
+  while (c.p < c.end && is_ws(*c.p)) ++c.p;
 }
 
 // cursor on the opening quote; leaves it after the closing quote. Returns false on a malformed string.
@@ -76,6 +79,7 @@ __device__ bool skip_string(Cursor& c, const uint8_t** body, int* raw_len, bool*
   bool esc = false;
   while (c.p < c.end) {
     const uint8_t ch = *c.p;
+    if (ch > '\\') { ++c.p; continue; }  // lower-case letters, '_', '{', UTF-8 continuation bytes: the common case first
     if (ch == '"') { *body = start; *raw_len = (int)(c.p - start); *has_escape = esc; ++c.p; return true; }
     if (ch == '\\') { esc = true; c.p += 2; continue; }
     if (ch < 0x20) return false;
@@ -86,14 +90,26 @@ __device__ bool skip_string(Cursor& c, const uint8_t** body, int* raw_len, bool*
 
 __device__ bool skip_value(Cursor& c, int depth);
 
-__device__ bool skip_number(Cursor& c, const uint8_t** start, int* len) {
+// Scans one JSON number.  When `fast` is given it also receives the value of a plain integer literal that fits
+// i64 (no fraction, no exponent) — the digits are then read once instead of scanned and parsed again.
+struct FastInt { bool ok; long long value; };
+__device__ bool skip_number(Cursor& c, const uint8_t** start, int* len, FastInt* fast = nullptr) {
   *start = c.p;
-  if (c.p < c.end && *c.p == '-') ++c.p;
+  bool neg = false;
+  if (c.p < c.end && *c.p == '-') { neg = true; ++c.p; }
   const uint8_t* d0 = c.p;
-  while (c.p < c.end && *c.p >= '0' && *c.p <= '9') ++c.p;
+  unsigned long long acc = 0;
+  bool plain = true;
+  while (c.p < c.end && *c.p >= '0' && *c.p <= '9') {
+    const unsigned d = *c.p - '0';
+    if (acc > 922337203685477580ull) plain = false;  // acc * 10 + d could pass 2^63: leave it to parse_i64
+    acc = acc * 10 + d;
+    ++c.p;
+  }
   if (c.p == d0) return false;
-  if (c.p < c.end && *c.p == '.') { ++c.p; const uint8_t* f0 = c.p; while (c.p < c.end && *c.p >= '0' && *c.p <= '9') ++c.p; if (c.p == f0) return false; }
+  if (c.p < c.end && *c.p == '.') { plain = false; ++c.p; const uint8_t* f0 = c.p; while (c.p < c.end && *c.p >= '0' && *c.p <= '9') ++c.p; if (c.p == f0) return false; }
   if (c.p < c.end && (*c.p == 'e' || *c.p == 'E')) {
+    plain = false;
     ++c.p;
     if (c.p < c.end && (*c.p == '+' || *c.p == '-')) ++c.p;
     const uint8_t* e0 = c.p;
@@ -101,6 +117,10 @@ __device__ bool skip_number(Cursor& c, const uint8_t** start, int* len) {
     if (c.p == e0) return false;
   }
   *len = (int)(c.p - *start);
+  if (fast) {
+    fast->ok = plain && acc <= 0x7FFFFFFFFFFFFFFFull;
+    fast->value = neg ? -(long long)acc : (long long)acc;
+  }
   return true;
 }
 
@@ -203,7 +223,8 @@ __device__ bool parse_i64(const uint8_t* s, int len, long long* out) {
   for (; i < len; ++i) {
     if (s[i] < '0' || s[i] > '9') { ok = false; break; }
     const unsigned d = s[i] - '0';
-    if (v > (0xFFFFFFFFFFFFFFFFull - d) / 10) { overflow = true; break; }
+    // v * 10 + d > u64::MAX  ⇔  v > 1844674407370955161 or (v == 1844674407370955161 and d > 5)
+    if (v > 1844674407370955161ull || (v == 1844674407370955161ull && d > 5)) { overflow = true; break; }
     v = v * 10 + d;
   }
   if (ok && !overflow) {
@@ -339,6 +360,7 @@ __global__ void __launch_bounds__(JS_THREADS) json_parse_kernel(const __grid_con
     // ---- MODE 1: one object → one row ----
     ++c.p;
     unsigned seen = 0;
+    int next_field = 0;
     skip_ws(c);
     bool first = true;
     while (true) {
@@ -356,12 +378,14 @@ __global__ void __launch_bounds__(JS_THREADS) json_parse_kernel(const __grid_con
       skip_ws(c);
       int f = -1;
       if (!kesc) {
-        for (int k = 0; k < P.n_fields; ++k) {
+        // records usually list their keys in the order of the first record: try that position first
+        for (int t = 0, k = next_field; t < P.n_fields; ++t, k = (k + 1 == P.n_fields ? 0 : k + 1)) {
           if (P.fields[k].name_len != kl) continue;
           bool eq = true;
           for (int b = 0; b < kl; ++b) if ((uint8_t)P.fields[k].name[b] != kb[b]) { eq = false; break; }
           if (eq) { f = k; break; }
         }
+        if (f >= 0) next_field = f + 1 == P.n_fields ? 0 : f + 1;
       }
       if (f < 0) { if (!skip_value(c, 0)) { raise(P, JE_SYNTAX, i); return; } continue; }
       const JsonField& F = P.fields[f];
@@ -376,12 +400,13 @@ __global__ void __launch_bounds__(JS_THREADS) json_parse_kernel(const __grid_con
       switch ((DType)F.dtype) {
         case DType::Int64: case DType::Float64: {
           const uint8_t* ns; int nl;
+          FastInt fi{false, 0};
           if (ch == '"') { bool e; if (!skip_string(c, &ns, &nl, &e)) { raise(P, JE_SYNTAX, i); return; } }
-          else if (ch == '-' || (ch >= '0' && ch <= '9')) { if (!skip_number(c, &ns, &nl)) { raise(P, JE_SYNTAX, i); return; } }
+          else if (ch == '-' || (ch >= '0' && ch <= '9')) { if (!skip_number(c, &ns, &nl, &fi)) { raise(P, JE_SYNTAX, i); return; } }
           else { raise(P, JE_TYPE, i); return; }
           if ((DType)F.dtype == DType::Int64) {
-            long long v;
-            if (!parse_i64(ns, nl, &v)) { raise(P, JE_NUMBER, i); return; }
+            long long v = fi.value;
+            if (!fi.ok && !parse_i64(ns, nl, &v)) { raise(P, JE_NUMBER, i); return; }
             ((long long*)F.values)[row] = v;
           } else {
             double v;
