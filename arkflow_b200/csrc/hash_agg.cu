@@ -329,41 +329,6 @@ bool launch_hash_agg_tile(const AggParams& P, unsigned long long capacity, int64
 bool launch_hash_agg_radix(const AggParams& P, unsigned long long capacity, int32_t* skew_dev, std::vector<BufferPtr>* keep, cudaStream_t stream);
 void hash_agg_radix_note_skew();
 
-// RAII: cudaAccessPolicyWindow (persisting) over [ptr, ptr+bytes) on `stream`, cleared on destruction.
-struct L2Window {
-  cudaStream_t stream;
-  bool active = false;
-  L2Window(cudaStream_t s, void* ptr, size_t bytes) : stream(s) {
-    static const char* off = getenv("ARK_NO_L2_WINDOW");
-    if (off) return;
-    static size_t max_persist = [] {
-      int dev = 0; cudaGetDevice(&dev);
-      cudaDeviceProp prop; cudaGetDeviceProperties(&prop, dev);
-      size_t m = (size_t)prop.persistingL2CacheMaxSize;
-      if (m) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, m);
-      size_t w = (size_t)prop.accessPolicyMaxWindowSize;
-      return std::min(m, w);
-    }();
-    if (!max_persist || bytes < (1u << 20)) return;  // small tables live in L2 anyway
-    cudaStreamAttrValue v;
-    memset(&v, 0, sizeof v);
-    v.accessPolicyWindow.base_ptr = ptr;
-    v.accessPolicyWindow.num_bytes = std::min(bytes, max_persist);
-    v.accessPolicyWindow.hitRatio = bytes <= max_persist ? 1.0f : (float)max_persist / (float)bytes;
-    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess) active = true;
-    else cudaGetLastError();
-  }
-  ~L2Window() {
-    if (!active) return;
-    cudaStreamAttrValue v;
-    memset(&v, 0, sizeof v);
-    v.accessPolicyWindow.num_bytes = 0;
-    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v);
-  }
-};
-
 static std::atomic<unsigned long long> g_capacity_hint{1ull << 16};
 
 static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int n_parts, cudaStream_t stream) {
@@ -412,9 +377,9 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
       agg_init_kernel<<<grid, 256, 0, stream>>>(P.table, capacity, stride, P.n_acc, P.accs[0], P.accs[1], P.accs[2], P.accs[3], P.accs[4],
                                                 P.accs[5], P.accs[6], P.accs[7]);
     }
-    // keep the table resident in L2 while 400 MB of input stream through it: persisting access window
-    // on the table for this stream (input loads carry evict-first hints)
-    L2Window l2win(stream, dg.table.get(), (size_t)capacity * stride);
+    // (A persisting L2 access-policy window on the table was tried: no gain for this kernel — 0.974 vs 0.984 ms —
+    // and the set-aside it needs, cudaLimitPersistingL2CacheSize, stays carved out of the L2 for every later
+    // kernel of the process: a following concat ran at 0.35 ms instead of 0.16 ms.  Removed.)
     const int64_t key_bytes = ex.key_kind == KEY_BYTES ? in.cols[plan.used_cols[ex.key_slot]].data_bytes : 0;
     // small tables (≤ 2048 slots): tiled kernel with shared-memory privatised accumulators (hot keys would
     // serialise on L2 atomics: K = 2 → 12.3 ms vs 1.6 ms).  Large tables: measured 0.95 ms (row kernel) vs
