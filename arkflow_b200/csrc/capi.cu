@@ -326,6 +326,24 @@ int ark_arrow_to_json_process(ark_proc_t* p, ArrowArray* in, ArrowSchema* in_sch
   });
 }
 
+int ark_arrow_to_json_process_device(ark_proc_t* p, ArrowDeviceArray* in, ArrowSchema* in_schema, ArrowDeviceArray* out,
+                                     ArrowSchema* out_schema) {
+  BufferPtr in_owner = adopt_array(&in->array);
+  return guarded([&] {
+    if (!p || !p->impl || strcmp(p->impl->type(), "arrow_to_json") != 0) fail(ARK_ERR_PROCESS, "handle is not an arrow_to_json processor");
+    if (!in_owner) fail(ARK_ERR_PROCESS, "input array already released");
+    ArrowDeviceArray view = *in;
+    view.array = *(const ArrowArray*)in_owner.get();
+    StreamLease lease;
+    Batch b = import_device(&view, in_schema, nullptr, in_owner);
+    std::vector<Column*> all;
+    for (auto& c : b.cols) all.push_back(&c);
+    resolve_varlen_extents_many(all, lease.s);
+    Batch r = arrow_to_json_device(*p->impl, b, lease.s);
+    export_device(r, out, out_schema);
+  });
+}
+
 // ---- expr::evaluate_expr (plugin/expr/mod.rs:92-122) ---------------------------------------------------
 namespace {
 

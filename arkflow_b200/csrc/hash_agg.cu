@@ -67,8 +67,7 @@ __global__ void agg_init_kernel(uint8_t* table, unsigned long long capacity, int
 constexpr int AGG_THREADS = 256;
 
 // R rows per thread per iteration, processed phase by phase (predicate → key → slot fetch → claim →
-// accumulate) so that the R dependent load chains of a thread overlap: ncu showed the 1-row-at-a-time
-// version latency-bound (long-scoreboard stalls 43 per issue, issue slots 19 % busy, DRAM 13 %).
+// accumulate) so that the R dependent load chains of a thread overlap (R = 1 is what is launched, see launch_agg).
 template <int PRED, int R>
 __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_constant__ AggParams P) {
   const int lane = threadIdx.x & 31;
@@ -272,13 +271,13 @@ __global__ void agg_finalize_kernel(int op, const unsigned long long* a, const u
 
 template <int PRED>
 void launch_agg(const AggParams& P, int64_t n, cudaStream_t stream) {
-  static const int rows_per_thread = [] { const char* e = getenv("ARK_AGG_R"); int v = e ? atoi(e) : 1; return v == 1 || v == 2 || v == 4 ? v : 1; }();  // measured at 10^6 groups: R=1 0.97 ms, R=2 1.03, R=4 1.20
+  // One row per thread per iteration.  The kernel keeps its R-rows-per-thread form (all slot loads of a thread
+  // issued before any is resolved), but more rows in flight per thread measured slower at 10^6 groups —
+  // R = 1 0.97 ms, R = 2 1.03 ms, R = 4 1.20 ms — the pass is bound by the rate of random DRAM sector
+  // accesses, not by latency hiding.
   KernelTimer t("hash_agg_kernel", stream);
-  const int R = PRED == 2 ? 1 : rows_per_thread;  // the VM path keeps its register file small
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, (int64_t)AGG_THREADS * R), 148 * 8));
-  if (R == 4) hash_agg_kernel<PRED, 4><<<grid, AGG_THREADS, 0, stream>>>(P);
-  else if (R == 2) hash_agg_kernel<PRED, 2><<<grid, AGG_THREADS, 0, stream>>>(P);
-  else hash_agg_kernel<PRED, 1><<<grid, AGG_THREADS, 0, stream>>>(P);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, (int64_t)AGG_THREADS), 148 * 8));
+  hash_agg_kernel<PRED, 1><<<grid, AGG_THREADS, 0, stream>>>(P);
 }
 
 struct AccPlan {  // host-side description of one accumulator

@@ -296,7 +296,7 @@ class JsonToArrowProcessor(_NativeProcessor):
 class ArrowToJsonProcessor(_NativeProcessor):
     """`type: arrow_to_json` — crates/arkflow-plugin/src/processor/json.rs:74-113."""
 
-    _create, _process, _process_device = "ark_arrow_to_json_create", "ark_arrow_to_json_process", ""
+    _create, _process, _process_device = "ark_arrow_to_json_create", "ark_arrow_to_json_process", "ark_arrow_to_json_process_device"
 
     def __init__(self, config: Optional[dict]):
         if config is not None and isinstance(config.get("fields_to_include"), (set, frozenset)):

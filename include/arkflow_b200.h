@@ -140,6 +140,9 @@ int ark_json_to_arrow_process_device(ark_proc_t* p, struct ArrowDeviceArray* in,
 int ark_arrow_to_json_create(const char* config_json, ark_proc_t** out);
 int ark_arrow_to_json_process(ark_proc_t* p, struct ArrowArray* in, struct ArrowSchema* in_schema,
                               struct ArrowArray* out, struct ArrowSchema* out_schema);
+int ark_arrow_to_json_process_device(ark_proc_t* p, struct ArrowDeviceArray* in,
+                                     struct ArrowSchema* in_schema, struct ArrowDeviceArray* out,
+                                     struct ArrowSchema* out_schema);
 
 /* ---- expr::evaluate_expr: replaces crates/arkflow-plugin/src/expr/mod.rs:92-122 (the key expression
  *      of a `temporary_list` entry, processor/sql.rs:151-186) ---- */

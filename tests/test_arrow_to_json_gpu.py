@@ -9,6 +9,7 @@ import pytest
 
 from arkflow_b200.processor import ArkError, ArrowToJsonProcessor, JsonToArrowProcessor, MessageBatch, Pipeline, SqlProcessor
 from oracle.json_oracle import arrow_to_json, arrow_to_json_lines, json_to_arrow
+from oracle.sql_oracle import sql_process as sql_oracle_process
 
 pytestmark = pytest.mark.gpu
 
@@ -106,3 +107,22 @@ def test_large_batch(gpu):
 
     rb = synth_batch(100_000, value_kind=1, key_space=1000)
     check(rb)
+
+
+def test_device_resident_chain_json_sql_json(gpu):
+    # json_to_arrow → sql → arrow_to_json without leaving HBM; the batch crosses PCIe once each way
+    from arkflow_b200.arrow_ffi import DeviceBatch
+
+    payloads = [json.dumps({"timestamp": 1625000000000 + i, "value": i % 20, "sensor": f"temp_{i % 7}"}).encode() for i in range(5000)]
+    host = MessageBatch.new_binary(payloads)
+    dev = DeviceBatch.from_arrow(host.record_batch)
+    q = "SELECT sensor, value FROM flow WHERE value >= 10"
+    stages = [JsonToArrowProcessor({}), SqlProcessor({"query": q}), ArrowToJsonProcessor({})]
+    cur = dev
+    for st in stages:
+        cur = st.process_device(cur)
+    got = cur.to_arrow()
+    want = arrow_to_json(sql_oracle_process(json_to_arrow(host.record_batch), q))
+    assert got.schema.names == want.schema.names == ["sensor", "value", "__value__"]
+    assert got.column("__value__").to_pylist() == want.column("__value__").to_pylist()
+    assert got.num_rows == 2500
