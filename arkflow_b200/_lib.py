@@ -104,6 +104,8 @@ def _declare(lib):
         "ark_sql_partial_aggregate_device": (C.c_int, [vp, P(ArrowDeviceArray), P(ArrowSchema), C.c_int, P(ArrowDeviceArray), P(ArrowSchema), P(C.c_int64)]),
         "ark_sql_final_aggregate_device": (C.c_int, [vp, P(ArrowDeviceArray), P(ArrowSchema), P(ArrowDeviceArray), P(ArrowSchema)]),
         "ark_hash_partition_device": (C.c_int, [P(ArrowDeviceArray), P(ArrowSchema), C.c_char_p, C.c_int, P(ArrowDeviceArray), P(ArrowSchema), P(C.c_int64)]),
+        "ark_ipc_export_device": (C.c_int, [P(ArrowDeviceArray), P(ArrowSchema), P(C.c_uint8), C.c_int64, P(C.c_int64)]),
+        "ark_ipc_concat_slices_device": (C.c_int, [C.c_int, P(P(C.c_uint8)), P(C.c_int64), P(C.c_int64), P(C.c_int64), P(ArrowDeviceArray), P(ArrowSchema)]),
         "ark_synth_batch_device": (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, C.c_int, C.c_int64, P(ArrowDeviceArray), P(ArrowSchema)]),
         "ark_kernel_launch_count": (C.c_int64, []),
         "ark_kernel_timing_enable": (None, [C.c_int]),

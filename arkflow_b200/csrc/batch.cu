@@ -350,6 +350,17 @@ int64_t device_alloc_remaining(const void* p) {
   return (int64_t)(base + size - (unsigned long long)(uintptr_t)p);
 }
 
+// base address and size of the CUDA allocation that contains p
+bool device_alloc_range(const void* p, unsigned long long* base, size_t* size) {
+  const int64_t rest = device_alloc_remaining(p);
+  if (rest < 0) return false;
+  typedef int (*fn_t)(unsigned long long*, size_t*, unsigned long long);
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult st;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) { cudaGetLastError(); return false; }
+  return ((fn_t)f)(base, size, (unsigned long long)(uintptr_t)p) == 0;
+}
+
 int64_t varlen_bytes_bound(const Column& c) {
   if (c.data_bytes >= 0) return c.data_bytes;
   return c.data_bound;

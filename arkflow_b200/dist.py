@@ -3,8 +3,10 @@
 SURVEY.md §8(e):
   * filter / project / json decode shard by rows — no collective (each rank processes its batches);
   * GROUP BY: each rank partial-aggregates its rows (hash_agg kernel), the partial states are
-    hash-partitioned by key owner, ONE all-to-all(v) moves them (NCCL over NVLink; gloo on CPU for
-    the host-logic tests), the owner merges (same kernel in merge mode).  This mirrors DataFusion's
+    hash-partitioned by key owner and exchanged — over peer memory on GPUs (exchange_partitions_p2p: every
+    rank pulls its slices of its peers' batches with ONE segmented-copy kernel over NVLink), or with one
+    all-to-all(v) per buffer (NCCL; gloo on CPU for the host-logic tests) — and the owner merges (same
+    kernel in merge mode).  This mirrors DataFusion's
     AggregateExec(Partial) → RepartitionExec(Hash) → AggregateExec(FinalPartitioned), which the
     reference reaches in-process (crates/arkflow-plugin/src/processor/sql.rs:126-129);
   * JOIN: both sides are hash-partitioned on the join key and exchanged the same way, then joined
@@ -156,13 +158,70 @@ def exchange_partitions(batch: DeviceBatch, part_rows: list[int], group=None) ->
     return DeviceBatch(cols, n_out)
 
 
-def distributed_group_by(engine, local_batch: DeviceBatch, group=None) -> DeviceBatch:
+def _ipc_export(batch: DeviceBatch) -> Optional[bytes]:
+    """CUDA-IPC descriptor of a device batch, or None when its memory cannot be exported."""
+    from .arrow_ffi import release_array, release_schema
+
+    lib = L.lib()
+    cap = 96 + 400 * max(len(batch.columns), 1)
+    blob = (C.c_uint8 * cap)()
+    size = C.c_int64(0)
+    dev, sch = batch.export()
+    try:
+        status = lib.ark_ipc_export_device(C.byref(dev), C.byref(sch), blob, cap, C.byref(size))
+    finally:
+        release_schema(sch)
+        release_array(dev.array)
+    return bytes(blob[: size.value]) if status == 0 else None
+
+
+def exchange_partitions_p2p(batch: DeviceBatch, part_rows: list[int], group=None) -> Optional[DeviceBatch]:
+    """The same exchange as exchange_partitions, over peer memory (csrc/ipc_exchange.cu): every rank publishes
+    its partition-ordered batch as CUDA IPC handles and PULLS its slice of every peer's batch with one
+    segmented-copy launch — NVLink transfer, concatenation and offset rebasing in the same kernel.
+    Returns None (on every rank alike) when some rank's memory cannot be exported; callers then use NCCL."""
+    from .processor import _check
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    blob = _ipc_export(batch)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (blob, [int(x) for x in part_rows]), group=group)
+    if any(g[0] is None for g in gathered):
+        return None
+    blobs = [g[0] for g in gathered]
+    row0 = (C.c_int64 * world)(*[sum(g[1][:rank]) for g in gathered])
+    nrows = (C.c_int64 * world)(*[g[1][rank] for g in gathered])
+    keep = [(C.c_uint8 * len(b)).from_buffer_copy(b) for b in blobs]
+    ptrs = (C.POINTER(C.c_uint8) * world)(*[C.cast(k, C.POINTER(C.c_uint8)) for k in keep])
+    sizes = (C.c_int64 * world)(*[len(b) for b in blobs])
+    out_dev, out_sch = L.ArrowDeviceArray(), L.ArrowSchema()
+    status = L.lib().ark_ipc_concat_slices_device(world, ptrs, sizes, row0, nrows, C.byref(out_dev), C.byref(out_sch))
+    dist.barrier(group)  # every reader is done with this rank's buffers before they are released
+    _check(status)
+    return DeviceBatch.adopt(out_dev, out_sch)
+
+
+def _exchange(batch: DeviceBatch, part_rows: list[int], group, p2p: Optional[bool]) -> DeviceBatch:
+    """p2p: True / False force the path; None = peer memory when the backend is NCCL (GPU ranks), else the
+    torch all-to-all (gloo on CPU)."""
+    import os
+
+    if p2p is None:
+        p2p = dist.get_backend(group) == "nccl" and os.environ.get("ARK_DIST_EXCHANGE", "p2p") != "nccl"
+    if p2p:
+        out = exchange_partitions_p2p(batch, part_rows, group)
+        if out is not None:
+            return out
+    return exchange_partitions(batch, part_rows, group)
+
+
+def distributed_group_by(engine, local_batch: DeviceBatch, group=None, p2p: Optional[bool] = None) -> DeviceBatch:
     """GROUP BY over the union of every rank's `local_batch`; returns this rank's share of the groups
     (group owners are disjoint, so the concatenation over ranks is the full result)."""
     world = dist.get_world_size(group)
     partial, part_rows = engine.partial_aggregate(local_batch, world)
     keyless = not partial.columns or partial.columns[0].name.startswith("__acc")
-    received = exchange_partitions(partial, part_rows, group)
+    received = _exchange(partial, part_rows, group, p2p)
     result = engine.final_aggregate(received)
     if keyless and dist.get_rank(group) != 0:
         # a global aggregate has one group, owned by rank 0; other ranks merged nothing
@@ -171,7 +230,7 @@ def distributed_group_by(engine, local_batch: DeviceBatch, group=None) -> Device
     return result
 
 
-def distributed_join(engine, tables: dict, keys: dict, group=None) -> DeviceBatch:
+def distributed_join(engine, tables: dict, keys: dict, group=None, p2p: Optional[bool] = None) -> DeviceBatch:
     """Inner equi-join over the union of every rank's tables.  `keys[name]` is the join column of table
     `name`.  Both sides are hash-partitioned on the key and exchanged with one all-to-all(v) each
     (SURVEY.md §8(e)); the local join then sees every row of its key range.  Output stays sharded."""
@@ -179,5 +238,5 @@ def distributed_join(engine, tables: dict, keys: dict, group=None) -> DeviceBatc
     local = {}
     for name, batch in tables.items():
         parted, rows = engine.hash_partition(batch, keys[name], world)
-        local[name] = exchange_partitions(parted, rows, group)
+        local[name] = _exchange(parted, rows, group, p2p)
     return engine.join(local)

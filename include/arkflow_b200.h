@@ -204,7 +204,7 @@ int ark_batch_close(ark_batcher_t* b);
 void ark_batch_destroy(ark_batcher_t* b);
 
 /* ---- multi-GPU GROUP BY / JOIN building blocks (device-resident).  The
- *      exchange between them is the caller's NCCL all-to-all; nothing like this exists in the
+ *      exchange between them is the caller's NCCL all-to-all or the peer-memory pull below; nothing like this exists in the
  *      reference (DataFusion's RepartitionExec(Hash) is in-process). ---- */
 /* Partial aggregate of one local batch → (keys, partial states) batch, hash-partitioned into
  * n_parts contiguous row ranges; part_rows[n_parts] receives the row count of each range. */
@@ -222,6 +222,19 @@ int ark_sql_final_aggregate_device(ark_proc_t* p, struct ArrowDeviceArray* in,
 int ark_hash_partition_device(struct ArrowDeviceArray* in, struct ArrowSchema* in_schema,
                               const char* key_column, int n_parts, struct ArrowDeviceArray* out,
                               struct ArrowSchema* out_schema, int64_t* part_rows);
+
+/* ---- the same exchange over peer memory instead of NCCL (csrc/ipc_exchange.cu; one node, one process per
+ *      GPU).  ark_ipc_export_device describes a device batch as CUDA IPC handles (blob: header + one record
+ *      per column; query the size with blob_cap = 0, status ARK_ERR_PROCESS and *blob_size set); the caller
+ *      all-gathers the blobs and the partition row counts, and every rank pulls its slices of all sources
+ *      with ark_ipc_concat_slices_device: ONE segmented-copy launch reads the peers' buffers over NVLink and
+ *      lays the rows out as one local batch (sources in order).  The exporter keeps its batch alive until
+ *      every reader is done (a barrier in the caller). ---- */
+int ark_ipc_export_device(struct ArrowDeviceArray* in, struct ArrowSchema* in_schema, uint8_t* blob,
+                          int64_t blob_cap, int64_t* blob_size);
+int ark_ipc_concat_slices_device(int n_src, const uint8_t* const* blobs, const int64_t* blob_sizes,
+                                 const int64_t* row0, const int64_t* n_rows,
+                                 struct ArrowDeviceArray* out, struct ArrowSchema* out_schema);
 
 /* ---- synthetic input of schema S, generated in HBM.  Bench/test support. ---- */
 /* value_kind: 0 = Int64 uniform [0,20), 1 = Float64 20*u.  key_space K: sensor = "temp_%07d" % k.

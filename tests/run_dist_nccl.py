@@ -1,4 +1,5 @@
-"""torchrun entry: GROUP BY over N GPUs with the NCCL all-to-all, checked against the oracle on rank 0."""
+"""torchrun entry: GROUP BY and JOIN over N GPUs, exchanged over peer memory (CUDA IPC pull) and with the
+NCCL all-to-all, both checked against the oracle on rank 0; plus a timing of the two exchanges."""
 import os
 import sys
 
@@ -26,7 +27,22 @@ def main():
     query = "SELECT sensor, SUM(value), COUNT(*) FROM flow GROUP BY sensor"
     eng = NativeEngine(query)
     local_rb = synth_batch(n, row0=rank * n, seed=42, key_space=10_007)
-    out = distributed_group_by(eng, DeviceBatch.from_arrow(local_rb)).to_arrow()
+    import arkflow_b200.dist as D
+
+    taken = {"p2p": 0}
+    real_p2p = D.exchange_partitions_p2p
+
+    def counting_p2p(*a, **k):
+        r = real_p2p(*a, **k)
+        taken["p2p"] += r is not None
+        return r
+
+    D.exchange_partitions_p2p = counting_p2p
+    out_nccl = distributed_group_by(eng, DeviceBatch.from_arrow(local_rb), p2p=False).to_arrow()
+    out = distributed_group_by(eng, DeviceBatch.from_arrow(local_rb), p2p=True).to_arrow()
+    assert taken["p2p"] == 1, "the peer-memory exchange was not taken"
+    key = lambda b: sorted(map(repr, zip(*[c.to_pylist() for c in b.columns])))
+    assert key(out) == key(out_nccl), "peer-memory and NCCL exchanges disagree"
     rows = out.to_pylist()
     gathered = [None] * world
     dist.all_gather_object(gathered, rows)
@@ -51,7 +67,10 @@ def main():
     probe = synth_batch(50_000, row0=rank * 50_000, seed=7, key_space=K)
     lo, hi = rank * K // world, (rank + 1) * K // world
     build = pa.record_batch({"sensor": pa.array(["temp_%07d" % i for i in range(lo, hi)]), "w": pa.array(range(lo, hi), pa.int64())})
-    jout = distributed_join(jeng, {"p": DeviceBatch.from_arrow(probe), "b": DeviceBatch.from_arrow(build)}, {"p": "sensor", "b": "sensor"}).to_arrow()
+    jout_nccl = distributed_join(jeng, {"p": DeviceBatch.from_arrow(probe), "b": DeviceBatch.from_arrow(build)}, {"p": "sensor", "b": "sensor"}, p2p=False).to_arrow()
+    jout = distributed_join(jeng, {"p": DeviceBatch.from_arrow(probe), "b": DeviceBatch.from_arrow(build)}, {"p": "sensor", "b": "sensor"}, p2p=True).to_arrow()
+    assert taken["p2p"] == 3, "the peer-memory exchange was not taken for the join"
+    assert key(jout) == key(jout_nccl), "peer-memory and NCCL join exchanges disagree"
     jrows = list(map(repr, zip(*[c.to_pylist() for c in jout.columns])))
     jg = [None] * world
     dist.all_gather_object(jg, jrows)
@@ -62,6 +81,28 @@ def main():
         assert sorted(sum(jg, [])) == want_rows, "distributed JOIN differs from the oracle"
         print(f"JOIN_OK world={world} rows={len(want_rows)} per-rank={[len(x) for x in jg]}")
         print("DIST_OK")
+
+    # ---- exchange timing: 2^24 rows of schema S per rank (generated in HBM), hash-partitioned on sensor ----
+    import ctypes as C
+    import time
+
+    n_big = 1 << 24
+    dev_arr, dev_sch = L.ArrowDeviceArray(), L.ArrowSchema()
+    _check(L.lib().ark_synth_batch_device(n_big, rank * n_big, 3, 0, 1_000_000, C.byref(dev_arr), C.byref(dev_sch)))
+    big = DeviceBatch.adopt(dev_arr, dev_sch)
+    parted, prow = jeng.hash_partition(big, "sensor", world)
+    res = {}
+    for name, fn in (("nccl", D.exchange_partitions), ("p2p", real_p2p)):
+        for it in range(4):
+            dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+            r = fn(parted, prow)
+            torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
+            if it:
+                res.setdefault(name, []).append(dt)
+            del r
+    if rank == 0:
+        nbytes = n_big * 32
+        print("EXCHANGE " + " ".join(f"{k}={min(v) * 1e3:.2f}ms({nbytes * (world - 1) / world / min(v) / 1e9:.0f}GB/s-out-per-rank)" for k, v in res.items()))
     dist.destroy_process_group()
 
 

@@ -84,3 +84,41 @@ def test_group_by_two_gpus_nccl(gpu, tmp_path):
                         "--master-port", "29631", script], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DIST_OK" in r.stdout
+
+
+def test_ipc_descriptor_pull_of_partition_slices(gpu):
+    """csrc/ipc_exchange.cu on one GPU: each simulated rank exports its hash-partitioned batch as an IPC
+    descriptor; owner p pulls rows [start_p, start_p + count_p) of every source with
+    ark_ipc_concat_slices_device (same-process sources resolve to the exporter's own pointers, the slicing /
+    concatenation / offset rebasing is the code path peers take).  Compared with slicing on the host."""
+    import ctypes as C
+
+    from arkflow_b200 import _lib as L
+    from arkflow_b200.dist import _ipc_export
+    from arkflow_b200.processor import _check
+
+    ranks = 3
+    eng = NativeEngine("SELECT * FROM p JOIN b ON p.sensor = b.sensor")
+    parted, rows, hosts = [], [], []
+    for r in range(ranks):
+        rb = synth_batch(20_000 + 1000 * r, row0=r * 50_000, seed=11, key_space=977)
+        nulls = pa.array([None if i % 97 == 0 else v for i, v in enumerate(rb.column("value").to_pylist())], pa.int64())
+        rb = pa.record_batch({"timestamp": rb.column("timestamp"), "value": nulls, "sensor": rb.column("sensor"),
+                              "flag": pa.array([i % 3 == 0 for i in range(rb.num_rows)])})
+        pb, pr = eng.hash_partition(DeviceBatch.from_arrow(rb), "sensor", ranks)
+        parted.append(pb); rows.append(pr); hosts.append(pb.to_arrow())
+    blobs = [_ipc_export(pb) for pb in parted]
+    assert all(b is not None for b in blobs)
+    for owner in range(ranks):
+        row0 = (C.c_int64 * ranks)(*[sum(rows[s][:owner]) for s in range(ranks)])
+        nrows = (C.c_int64 * ranks)(*[rows[s][owner] for s in range(ranks)])
+        keep = [(C.c_uint8 * len(b)).from_buffer_copy(b) for b in blobs]
+        ptrs = (C.POINTER(C.c_uint8) * ranks)(*[C.cast(k, C.POINTER(C.c_uint8)) for k in keep])
+        sizes = (C.c_int64 * ranks)(*[len(b) for b in blobs])
+        out_dev, out_sch = L.ArrowDeviceArray(), L.ArrowSchema()
+        _check(L.lib().ark_ipc_concat_slices_device(ranks, ptrs, sizes, row0, nrows, C.byref(out_dev), C.byref(out_sch)))
+        got = DeviceBatch.adopt(out_dev, out_sch).to_arrow()
+        want = pa.Table.from_batches([hosts[s].slice(row0[s], nrows[s]) for s in range(ranks)]).combine_chunks().to_batches()[0]
+        assert got.schema.names == want.schema.names
+        for name in want.schema.names:
+            assert got.column(name).equals(want.column(name)), (owner, name)
