@@ -158,6 +158,9 @@ def exchange_partitions(batch: DeviceBatch, part_rows: list[int], group=None) ->
     return DeviceBatch(cols, n_out)
 
 
+_IPC_SLOT_BYTES = 8192  # descriptor bytes per rank in the exchange's all-gather (24 + 400 per column)
+
+
 def _ipc_export(batch: DeviceBatch) -> Optional[bytes]:
     """CUDA-IPC descriptor of a device batch, or None when its memory cannot be exported."""
     from .arrow_ffi import release_array, release_schema
@@ -184,8 +187,25 @@ def exchange_partitions_p2p(batch: DeviceBatch, part_rows: list[int], group=None
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     blob = _ipc_export(batch)
-    gathered = [None] * world
-    dist.all_gather_object(gathered, (blob, [int(x) for x in part_rows]), group=group)
+    # ONE fixed-size all-gather carries every rank's descriptor and partition row counts:
+    # [ok:int64 | blob_len:int64 | part_rows: world × int64 | blob bytes, zero-padded]
+    slot = 16 + 8 * world + _IPC_SLOT_BYTES
+    if blob is not None and len(blob) > _IPC_SLOT_BYTES:
+        blob = None
+    head = [0 if blob is None else 1, 0 if blob is None else len(blob)] + [int(x) for x in part_rows]
+    mine = torch.zeros(slot, dtype=torch.uint8)
+    mine[: 16 + 8 * world] = torch.tensor(head, dtype=torch.int64).view(torch.uint8)
+    if blob is not None:
+        mine[16 + 8 * world: 16 + 8 * world + len(blob)] = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+    device = torch.device("cuda", torch.cuda.current_device())
+    everyone = torch.empty(slot * world, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(everyone, mine.to(device), group=group)
+    everyone = everyone.cpu()
+    gathered = []
+    for s_ in range(world):
+        rec = everyone[s_ * slot: (s_ + 1) * slot]
+        h = rec[: 16 + 8 * world].view(torch.int64).tolist()
+        gathered.append((bytes(rec[16 + 8 * world: 16 + 8 * world + h[1]].numpy()) if h[0] else None, h[2:]))
     if any(g[0] is None for g in gathered):
         return None
     blobs = [g[0] for g in gathered]
