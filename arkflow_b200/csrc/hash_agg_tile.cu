@@ -77,7 +77,7 @@ template <int PRED>
 __global__ void __launch_bounds__(HT_THREADS, 4) hash_agg_tile_kernel(const __grid_constant__ AggParams P, const int str_cap, const int priv_slots) {
   extern __shared__ __align__(16) uint8_t smem[];  // [key bytes window: str_cap + 32][privatised accumulators]
   __shared__ __align__(8) unsigned long long s_bar;
-  __shared__ int s_str_base, s_str_staged;
+  __shared__ int s_str_base, s_str_staged, s_stop;
   const int tid = threadIdx.x, lane = tid & 31;
   uint8_t* in_bytes = smem;
   unsigned long long* priv = reinterpret_cast<unsigned long long*>(smem + (str_cap ? str_cap + 32 : 0));
@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(HT_THREADS, 4) hash_agg_tile_kernel(const __gr
   for (int tile = blockIdx.x, it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
     const int64_t row0 = (int64_t)tile * HT_TILE;
     const int rows = (int)((n - row0) < HT_TILE ? (n - row0) : HT_TILE);
-    if (bytes_key && tid == 0) {
+    if (tid == 0) s_stop = *reinterpret_cast<volatile int32_t*>(P.overflow);  // table too small: the host retries with 4× the slots
+    if (bytes_key && tid == 0 && !s_stop) {
       const int32_t o0 = koff[row0], o1 = koff[row0 + rows];
       const uintptr_t a0 = reinterpret_cast<uintptr_t>((const uint8_t*)kc.data + o0), a1 = reinterpret_cast<uintptr_t>((const uint8_t*)kc.data + o1);
       const uintptr_t lo = a0 & ~(uintptr_t)15, hi = (a1 + 15) & ~(uintptr_t)15;
@@ -142,7 +143,8 @@ __global__ void __launch_bounds__(HT_THREADS, 4) hash_agg_tile_kernel(const __gr
         for (int j = 0; j < 4; ++j) pv[j] = (lr0 + j < rows) ? src[j] : 0;
       }
     }
-    __syncthreads();  // s_str_staged / s_str_base visible; (it > 0) previous tile's readers are done
+    __syncthreads();  // s_str_staged / s_str_base / s_stop visible; (it > 0) previous tile's readers are done
+    if (s_stop) break;  // CTA-uniform; no bulk copy was issued for this tile
     unsigned ok = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
