@@ -127,20 +127,20 @@ __device__ __forceinline__ void gather_string(uint8_t* dst, const uint8_t* src, 
 }
 
 constexpr int TAKE_TILE = 1024;
-constexpr int TAKE_STAGE = 40 * 1024;  // bytes of output staged per tile; longer tiles take the per-row path
+constexpr int TAKE_STAGE_MAX = 44 * 1024;  // most bytes of output staged per tile; longer tiles take the per-row path
 
 // Gathers the bytes of TAKE_TILE output rows into shared memory (their output range is contiguous), then
 // writes the range with destination-aligned 16-byte stores.  Replaces the warp-per-row kernel on the join's
 // gather of string columns (2^24 rows of 12 bytes: 2.97 ms → see profiles/).
 __global__ void __launch_bounds__(256) take_bytes_tile_kernel(const uint8_t* data, const int32_t* offsets, const unsigned int* idx, long long n,
-                                                               const int32_t* out_offsets, uint8_t* out) {
-  __shared__ __align__(16) uint8_t stage[TAKE_STAGE + 16];
+                                                               const int32_t* out_offsets, uint8_t* out, int stage_bytes) {
+  extern __shared__ __align__(16) uint8_t stage[];  // stage_bytes: sized to the column's average row (more CTAs per SM for short strings)
   const long long row0 = (long long)blockIdx.x * TAKE_TILE;
   const int rows = (int)((n - row0) < TAKE_TILE ? (n - row0) : TAKE_TILE);
   const int tid = threadIdx.x;
   const int32_t bb = out_offsets[row0];
   const int tb = out_offsets[row0 + rows] - bb;
-  if (tb > TAKE_STAGE) {  // long strings: straight per-row copies, a warp per row
+  if (tb + 16 > stage_bytes) {  // long strings: straight per-row copies, a warp per row
     const int lane = tid & 31;
     for (int i = tid >> 5; i < rows; i += 8) {
       const unsigned int r = idx[row0 + i];
@@ -152,15 +152,24 @@ __global__ void __launch_bounds__(256) take_bytes_tile_kernel(const uint8_t* dat
   }
   // staging starts at the destination's misalignment so that shared and global addresses agree mod 16
   const int mis = stage_misalignment(out + bb);
+  // all index / offset loads of a thread's 4 rows are issued before any string is copied (three dependent
+  // levels — index → offsets → bytes — would otherwise serialise per row)
+  constexpr int RPT = TAKE_TILE / 256;
+  int32_t s0[RPT], len[RPT], dst[RPT];
 #pragma unroll
-  for (int k = 0; k < TAKE_TILE / 256; ++k) {
+  for (int k = 0; k < RPT; ++k) {
     const int i = k * 256 + tid;
+    s0[k] = 0; len[k] = 0; dst[k] = 0;
     if (i < rows) {
       const unsigned int r = idx[row0 + i];
-      const int32_t s0 = offsets[r], len = offsets[r + 1] - s0;
-      gather_string(stage + mis + (out_offsets[row0 + i] - bb), data + s0, len);
+      s0[k] = offsets[r];
+      len[k] = offsets[r + 1] - s0[k];
+      dst[k] = out_offsets[row0 + i] - bb;
     }
   }
+#pragma unroll
+  for (int k = 0; k < RPT; ++k)
+    if (len[k] > 0) gather_string(stage + mis + dst[k], data + s0[k], len[k]);
   __syncthreads();
   stage_store(out + bb, stage, mis, tb, tid, 256);
 }
@@ -256,7 +265,8 @@ Column take_column(const Column& src, const unsigned int* idx, int64_t n, const 
       BufferPtr bytes = device_alloc((size_t)total + 16);
       if (n) {
         KernelTimer t("take_bytes_tile_kernel", stream);
-        take_bytes_tile_kernel<<<(unsigned)ceil_div(n, TAKE_TILE), 256, 0, stream>>>(src.data, src.offsets, idx, n, (const int32_t*)offs.get(), (uint8_t*)bytes.get());
+        const int stage = (int)std::min<int64_t>(TAKE_STAGE_MAX, round_up((int64_t)((double)total / (double)n * TAKE_TILE * 1.5) + 256, 1024));
+        take_bytes_tile_kernel<<<(unsigned)ceil_div(n, TAKE_TILE), 256, stage, stream>>>(src.data, src.offsets, idx, n, (const int32_t*)offs.get(), (uint8_t*)bytes.get(), stage);
       }
       c.offsets = (const int32_t*)offs.get(); c.data = (const uint8_t*)bytes.get(); c.data_bytes = total; c.first_offset = 0;
       c.owners = {offs, bytes};
