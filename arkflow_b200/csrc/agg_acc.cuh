@@ -34,4 +34,26 @@ static __device__ __forceinline__ void merge_acc(int kind, unsigned long long* d
   }
 }
 
+static __device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+static __device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+static __device__ __forceinline__ long long warp_min_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+  return v;
+}
+static __device__ __forceinline__ long long warp_max_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+  return v;
+}
+
+
 }  // namespace ark

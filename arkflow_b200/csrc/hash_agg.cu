@@ -11,6 +11,7 @@
 // Algorithmic traffic = key + argument bytes read once (24 B/row for config 3).
 #include <cub/device/device_scan.cuh>
 
+#include "agg_acc.cuh"
 #include "engine.h"
 #include "hash_agg.cuh"
 #include "hashkey.cuh"
@@ -19,27 +20,6 @@
 namespace ark {
 
 namespace {
-
-__device__ __forceinline__ long long warp_sum_ll(long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ double warp_sum_f64(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ long long warp_min_ll(long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
-  return v;
-}
-__device__ __forceinline__ long long warp_max_ll(long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
-  return v;
-}
 
 __device__ __forceinline__ Key16* slot_key(uint8_t* table, unsigned long long slot, int stride) {
   return reinterpret_cast<Key16*>(table + slot * (unsigned long long)stride);
@@ -327,11 +307,12 @@ struct DenseGroups {  // result of the hash pass: dense arrays of G groups, part
   unsigned long long capacity = 0;
 };
 
-bool launch_hash_agg_tile(const AggParams& P, unsigned long long capacity, int64_t key_bytes, cudaStream_t stream);
+bool launch_hash_agg_tile(const AggParams& P, unsigned long long capacity, unsigned int groups_hint, int64_t key_bytes, cudaStream_t stream);
 bool launch_hash_agg_radix(const AggParams& P, unsigned long long capacity, int32_t* skew_dev, std::vector<BufferPtr>* keep, cudaStream_t stream);
 void hash_agg_radix_note_skew();
 
 static std::atomic<unsigned long long> g_capacity_hint{1ull << 16};
+static std::atomic<unsigned int> g_groups_hint{0};  // groups of the previous batch (0 = none yet)
 
 static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int n_parts, cudaStream_t stream) {
   const int64_t n = in.num_rows;
@@ -386,9 +367,9 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     // small tables (≤ 2048 slots): tiled kernel with shared-memory privatised accumulators (hot keys would
     // serialise on L2 atomics: K = 2 → 12.3 ms vs 1.6 ms).  Large tables: measured 0.95 ms (row kernel) vs
     // 1.22 ms (tiled) at 10^6 keys — the row kernel keeps more independent probes in flight.
-    static const bool tile_all = getenv("ARK_AGG_TILE") && atoi(getenv("ARK_AGG_TILE")) == 1;
+    static const unsigned long long tile_max = [] { const char* e = getenv("ARK_AGG_TILE_MAX"); return e ? (unsigned long long)atoll(e) : 1024ull; }();  // 2048 slots (≈ 1000 groups): 1.65 ms here vs 1.34 ms in hash_agg_kernel
     if (radix) {
-    } else if (n > 0 && (capacity <= 2048 || tile_all) && launch_hash_agg_tile(P, capacity, key_bytes, stream)) {
+    } else if (n > 0 && capacity <= tile_max && launch_hash_agg_tile(P, capacity, g_groups_hint.load(), key_bytes, stream)) {
     } else {
       if (P.pred_kind == 0) launch_agg<0>(P, n, stream);
       else if (P.pred_kind == 1) launch_agg<1>(P, n, stream);
@@ -408,6 +389,7 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     if (overflow || groups > P.max_groups) {
       if (capacity >= cap_limit) fail(ARK_ERR_PROCESS, "Collection query results error: group-by hash table exceeded 2^31 slots");
       capacity *= 4;
+      g_groups_hint.store(0);  // the previous batch's group count undersized the shared-memory table: size it by capacity
       continue;
     }
     if (err) fail(ARK_ERR_PROCESS, std::string("Collection query results error: ") +
@@ -419,6 +401,7 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     unsigned long long want = 1ull << 10;
     while (want < 2ull * groups) want <<= 1;
     g_capacity_hint.store(want);
+    g_groups_hint.store(groups);
     break;
   }
   // dense, partition-ordered slot list

@@ -30,6 +30,7 @@
 #include "engine.h"
 #include "hash_agg.cuh"
 #include "hashkey.cuh"
+#include "smem_table.cuh"
 
 namespace ark {
 
@@ -38,7 +39,6 @@ namespace {
 constexpr int RP_THREADS = 512;
 constexpr int RP_ROWS = 4;
 constexpr int RP_TILE = RP_THREADS * RP_ROWS;
-constexpr unsigned long long KEY_PENDING = 0xFFFFFFFFFFFFFFFEull;  // tag 0xFFFFFFFF is never a key tag
 
 struct RadixParams {
   Key16* rec_keys;             // [n_buckets * cap]
@@ -157,39 +157,6 @@ __global__ void __launch_bounds__(RP_THREADS, 2) agg_radix_partition_kernel(cons
     R.rec_keys[g] = s_keys[i];
     if (R.nv >= 1) R.rec_v0[g] = s_v0[i];
     if (R.nv >= 2) R.rec_v1[g] = s_v1[i];
-  }
-}
-
-__device__ __forceinline__ unsigned long long lds_volatile(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
-__device__ __forceinline__ void sts_volatile(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
-
-// Finds or claims the slot of `mine` in the shared-memory region (linear probing, wraps inside the region).
-// Claim protocol without a 128-bit shared-memory CAS: hi EMPTY → PENDING (64-bit CAS), lo stored, then
-// hi published; readers re-read while they see PENDING.  The owner never waits on anybody, so the loop
-// terminates under any warp scheduling.  Returns -1 when the region is full.
-__device__ __forceinline__ int region_find_or_claim(Key16* K, int S, unsigned int home, Key16 mine, const ColView& kc, unsigned int* claimed) {
-  unsigned int s = home;
-  int probes = 0;
-  while (true) {
-    unsigned long long hi = lds_volatile(&K[s].hi);
-    if (hi == mine.hi) {  // the common case first: the group exists
-      const Key16 stored{lds_volatile(&K[s].lo), hi};
-      if (key_equal(mine, stored, kc, kc)) return (int)s;
-    } else if (hi == KEY_EMPTY) {
-      const unsigned long long old = atomicCAS(&K[s].hi, KEY_EMPTY, KEY_PENDING);
-      if (old == KEY_EMPTY) {
-        sts_volatile(&K[s].lo, mine.lo);
-        __threadfence_block();
-        sts_volatile(&K[s].hi, mine.hi);
-        ++*claimed;
-        return (int)s;
-      }
-      continue;  // somebody else claimed it: look again
-    } else if (hi == KEY_PENDING) {
-      continue;
-    }
-    s = (s + 1) & (unsigned int)(S - 1);
-    if (++probes >= S) return -1;
   }
 }
 

@@ -1,24 +1,26 @@
-// hash_agg_tile.cu — tiled GROUP BY kernel: the common shape (optional `col <cmp> literal` filter,
-// column-valued aggregate arguments) restructured for memory-level parallelism.
+// hash_agg_tile.cu — GROUP BY for low-cardinality keys (table ≤ 2048 slots): the whole hash table of a CTA —
+// keys and accumulators — lives in shared memory, and the global table is touched once per CTA and group.
 //
-// hash_agg_kernel (hash_agg.cu) walks one row per thread through a chain of dependent loads
-// (offsets → key bytes → table slot → atomics); ncu shows it latency-bound (issue slots 20 % busy,
-// long-scoreboard stalls 39 per issue).  Here a CTA takes 1024-row tiles and each thread owns 4
-// consecutive rows:
+// This is the shape of every shipped example (sensor ∈ {temp_1, temp_2, …}).  hash_agg_kernel sends each row to
+// the global table (a 128-bit load + two L2 atomics per row: 0.58 ms per 2^24 rows at 10^4 keys, and hot keys
+// serialise on the L2 atomic unit: K = 2 → 12.3 ms).  Here a persistent CTA takes 1024-row tiles, each thread
+// owns 4 consecutive rows:
 //   * the tile's key bytes arrive through ONE 1-D TMA bulk copy (cp.async.bulk → mbarrier) of the
-//     16-byte-aligned window around [offsets[t0], offsets[t1]), so keys are built from shared memory;
-//   * offsets / predicate / argument values are 16-byte vector loads issued up front;
-//   * the 4 table slots of a thread are fetched with 4 independent 128-bit loads before any is resolved;
-//   * low-cardinality tables (≤ 2048 slots) accumulate in a per-CTA shared-memory copy of the
-//     accumulators (shared-memory atomics) that is flushed once per CTA — hot keys no longer
-//     serialise on L2 atomics (K = 2: 12.3 ms → see profiles/).
-// Table layout, key format and CAS protocol are those of hash_agg.cu.
+//     16-byte-aligned window around [offsets[t0], offsets[t1]); offsets / predicate / argument values are
+//     16-byte vector loads issued up front;
+//   * keys are found or claimed in the CTA's shared-memory table (smem_table.cuh) and accumulated there;
+//   * tables of ≤ 64 slots (and global aggregates) first reduce each distinct slot of a warp with shuffles, so a
+//     hot key costs one shared-memory atomic per warp instead of 32 serialised ones;
+//   * at the end each CTA merges its ≤ S groups into the global table (128-bit CAS + global atomics), which
+//     keeps the layout every downstream step expects.
+// A batch with more distinct keys than slots raises `overflow`; the host retries with 4× the slots.
 #include <atomic>
 
 #include "agg_acc.cuh"
 #include "engine.h"
 #include "hash_agg.cuh"
 #include "hashkey.cuh"
+#include "smem_table.cuh"
 
 namespace ark {
 
@@ -46,8 +48,8 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 
-// Key16 + hash of a byte string that sits in shared memory (same encoding as make_key)
-__device__ __forceinline__ void make_key_smem(const uint8_t* p, int len, int64_t row, Key16* key, unsigned long long* hash) {
+// Key16 + 32-bit table hash of a byte string that sits in shared memory (same key encoding as make_key)
+__device__ __forceinline__ void make_key_smem(const uint8_t* p, int len, int64_t row, Key16* key, unsigned int* hash) {
   Key16 k;
   if (len <= 12) {
     unsigned w[3] = {0, 0, 0};
@@ -64,26 +66,82 @@ __device__ __forceinline__ void make_key_smem(const uint8_t* p, int len, int64_t
     }
     k.lo = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
     k.hi = (unsigned long long)w[2] | ((unsigned long long)(unsigned)len << 32);
-    *key = k; *hash = hash_key16(k);
+    *key = k; *hash = hash32_key16(k);
   } else {
     const unsigned prefix = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
     k.lo = (unsigned long long)row;
     k.hi = (unsigned long long)prefix | ((unsigned long long)(KEYTAG_LONG | (unsigned)len) << 32);
-    *key = k; *hash = hash_bytes(p, len);
+    *key = k;
+    const unsigned long long h = hash_bytes(p, len);
+    *hash = (unsigned)(h >> 32) ^ (unsigned)h;
+  }
+}
+
+// Tables of ≤ 64 slots.  For every distinct slot among the warp's 128 rows: each lane first combines its own rows
+// of that slot, one shuffle reduction per slot follows, lane 0 applies the result to the WARP'S OWN copy of the
+// accumulator with a plain read-modify-write (no atomics, no contention between warps).
+// CLS: 0 count, 1 sum i64, 2 sum f64, 3 min i64, 4 min f64 (totalOrder key), 5 max i64, 6 max f64.
+template <int CLS>
+__device__ __forceinline__ void tiny_accumulate(unsigned long long* acc, const int (&slot)[4], unsigned ok, unsigned valid,
+                                                const unsigned long long (&av)[4], int arg_is_f64, int lane) {
+  unsigned act0 = __ballot_sync(0xffffffffu, ok & 1), act1 = __ballot_sync(0xffffffffu, (ok >> 1) & 1),
+           act2 = __ballot_sync(0xffffffffu, (ok >> 2) & 1), act3 = __ballot_sync(0xffffffffu, (ok >> 3) & 1);
+  while (act0 | act1 | act2 | act3) {
+    const unsigned am = act0 ? act0 : act1 ? act1 : act2 ? act2 : act3;
+    const int pick = act0 ? slot[0] : act1 ? slot[1] : act2 ? slot[2] : slot[3];
+    const int s = __shfl_sync(0xffffffffu, pick, __ffs(am) - 1);
+    long long li = CLS == 3 || CLS == 4 ? 0x7FFFFFFFFFFFFFFFll : (CLS == 5 || CLS == 6 ? (long long)0x8000000000000000ull : 0);
+    double lf = 0.0;
+    int lcnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool in = ((ok >> j) & 1) && slot[j] == s;
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      if (j == 0) act0 &= ~m; else if (j == 1) act1 &= ~m; else if (j == 2) act2 &= ~m; else act3 &= ~m;
+      if (in && ((valid >> j) & 1)) {
+        ++lcnt;
+        if (CLS == 1) li += (long long)av[j];
+        if (CLS == 2) lf += arg_is_f64 ? __longlong_as_double((long long)av[j]) : (double)(long long)av[j];
+        if (CLS == 3 || CLS == 5) { const long long x = (long long)av[j]; li = CLS == 3 ? (x < li ? x : li) : (x > li ? x : li); }
+        if (CLS == 4 || CLS == 6) { const long long x = f64_total_key(av[j]); li = CLS == 4 ? (x < li ? x : li) : (x > li ? x : li); }
+      }
+    }
+    unsigned long long* dst = acc + s;
+    if (CLS == 0) { const int c = __reduce_add_sync(0xffffffffu, lcnt); if (lane == 0) *dst += (unsigned long long)c; }
+    else if (CLS == 1) { const long long v = warp_sum_ll(li); if (lane == 0) *dst += (unsigned long long)v; }
+    else if (CLS == 2) {
+      const double v = warp_sum_f64(lf);
+      const bool any = __any_sync(0xffffffffu, lcnt > 0);
+      if (lane == 0 && any) *reinterpret_cast<double*>(dst) += v;
+    } else if (CLS == 3 || CLS == 4) { const long long v = warp_min_ll(li); if (lane == 0 && v < *reinterpret_cast<long long*>(dst)) *reinterpret_cast<long long*>(dst) = v; }
+    else { const long long v = warp_max_ll(li); if (lane == 0 && v > *reinterpret_cast<long long*>(dst)) *reinterpret_cast<long long*>(dst) = v; }
+  }
+}
+
+// fold warp copy `src` into copy 0 (same slot, same accumulator)
+__device__ __forceinline__ void fold_acc(int kind, unsigned long long* dst, unsigned long long v) {
+  switch (kind) {
+    case ACC_COUNT_STAR: case ACC_COUNT: case ACC_SUM_I64: *dst += v; break;
+    case ACC_SUM_F64: *reinterpret_cast<double*>(dst) += __longlong_as_double((long long)v); break;
+    case ACC_MIN_I64: case ACC_MIN_F64: if ((long long)v < *reinterpret_cast<long long*>(dst)) *reinterpret_cast<long long*>(dst) = (long long)v; break;
+    default: if ((long long)v > *reinterpret_cast<long long*>(dst)) *reinterpret_cast<long long*>(dst) = (long long)v; break;
   }
 }
 
 template <int PRED>
-__global__ void __launch_bounds__(HT_THREADS, 4) hash_agg_tile_kernel(const __grid_constant__ AggParams P, const int str_cap, const int priv_slots) {
-  extern __shared__ __align__(16) uint8_t smem[];  // [key bytes window: str_cap + 32][privatised accumulators]
+__global__ void __launch_bounds__(HT_THREADS, 3) hash_agg_tile_kernel(const __grid_constant__ AggParams P, const int str_cap, const int log2_slots) {
+  extern __shared__ __align__(16) uint8_t smem[];  // [key bytes window: str_cap + 32][Key16 K[S]][u64 ACC[copies][n_acc][S]], copies = 8 warps when S ≤ 64
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_str_base, s_str_staged, s_stop;
   const int tid = threadIdx.x, lane = tid & 31;
+  const int S = 1 << log2_slots;
   uint8_t* in_bytes = smem;
-  unsigned long long* priv = reinterpret_cast<unsigned long long*>(smem + (str_cap ? str_cap + 32 : 0));
+  Key16* K = reinterpret_cast<Key16*>(smem + (str_cap ? str_cap + 32 : 0));
+  unsigned long long* ACC = reinterpret_cast<unsigned long long*>(K + S);
   const int64_t n = P.n_rows;
   const int n_tiles = (int)((n + HT_TILE - 1) / HT_TILE);
   const bool bytes_key = P.key_kind == KEY_BYTES;
+  const bool tiny = S <= 64;  // hot keys: reduce inside the warp before touching shared memory
   const ColView& kc = P.cols[P.key_kind == KEY_NONE ? 0 : P.key_slot];
   const int32_t* koff = kc.offsets;
 
@@ -97,9 +155,13 @@ __global__ void __launch_bounds__(HT_THREADS, 4) hash_agg_tile_kernel(const __gr
       if (cur.hi == KEY_EMPTY && cur.lo == KEY_EMPTY) atomicAdd(P.group_count, 1u);
     }
   }
-  for (int i = tid; i < priv_slots * P.n_acc; i += HT_THREADS) priv[i] = acc_identity(P.accs[i % P.n_acc].kind);
+  const int copies = tiny ? HT_THREADS / 32 : 1;
+  for (int s = tid; s < S; s += HT_THREADS) K[s] = Key16{KEY_EMPTY, KEY_EMPTY};
+  for (int i = tid; i < copies * P.n_acc * S; i += HT_THREADS) ACC[i] = acc_identity(P.accs[(i / S) % P.n_acc].kind);
   __syncthreads();
 
+  unsigned int claimed = 0;
+  bool full = false;
   const long long pred_c = P.sp_is_f64 ? f64_total_key(P.sp_const) : (long long)P.sp_const;
   for (int tile = blockIdx.x, it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
     const int64_t row0 = (int64_t)tile * HT_TILE;
@@ -119,12 +181,12 @@ __global__ void __launch_bounds__(HT_THREADS, 4) hash_agg_tile_kernel(const __gr
     }
     // ---- loads in flight: offsets, predicate column ----
     const int lr0 = 4 * tid;
-    const bool full = lr0 + 4 <= rows;
+    const bool full_rows = lr0 + 4 <= rows;
     int off[5] = {0, 0, 0, 0, 0};
     unsigned long long pv[4] = {0, 0, 0, 0};
     if (bytes_key) {
       const int32_t* os = koff + row0 + lr0;
-      if (full && (reinterpret_cast<uintptr_t>(os) & 15) == 0) {
+      if (full_rows && (reinterpret_cast<uintptr_t>(os) & 15) == 0) {
         asm volatile("ld.global.cs.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(off[0]), "=r"(off[1]), "=r"(off[2]), "=r"(off[3]) : "l"(os));
       } else {
 #pragma unroll
@@ -135,7 +197,7 @@ __global__ void __launch_bounds__(HT_THREADS, 4) hash_agg_tile_kernel(const __gr
     }
     if (PRED == 1) {
       const unsigned long long* src = (const unsigned long long*)P.cols[P.sp_slot].data + row0 + lr0;
-      if (full && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      if (full_rows && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
         asm volatile("ld.global.cs.v2.u64 {%0, %1}, [%2];" : "=l"(pv[0]), "=l"(pv[1]) : "l"(src));
         asm volatile("ld.global.cs.v2.u64 {%0, %1}, [%2];" : "=l"(pv[2]), "=l"(pv[3]) : "l"(src + 2));
       } else {
@@ -157,43 +219,25 @@ __global__ void __launch_bounds__(HT_THREADS, 4) hash_agg_tile_kernel(const __gr
     }
     const bool staged = bytes_key && s_str_staged;
     if (staged) mbar_wait(&s_bar, it & 1);
-    // ---- keys + hashes, then all 4 table slots fetched before any is resolved ----
-    Key16 mine[4];
-    unsigned long long slot[4];
-    Key16 cur[4];
+    // ---- keys → slots of the shared-memory table ----
+    int slot[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      slot[j] = 0;
+      slot[j] = -1;
       if (!((ok >> j) & 1)) continue;
       const int64_t row = row0 + lr0 + j;
-      unsigned long long h;
-      if (bytes_key && staged && col_valid(kc, row)) make_key_smem(in_bytes + (off[j] - s_str_base), off[j + 1] - off[j], row, &mine[j], &h);
-      else make_key(P.key_kind, kc, row, &mine[j], &h);
-      slot[j] = h & P.mask;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if ((ok >> j) & 1) cur[j] = ld128(reinterpret_cast<const Key16*>(P.table + slot[j] * (unsigned long long)P.slot_stride));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (!((ok >> j) & 1)) continue;
-      Key16 c = cur[j];
-      int probes = 0;
-      while (true) {
-        Key16* sk = reinterpret_cast<Key16*>(P.table + slot[j] * (unsigned long long)P.slot_stride);
-        if (c.hi == KEY_EMPTY) {
-          c = cas128(sk, Key16{KEY_EMPTY, KEY_EMPTY}, mine[j]);
-          if (c.hi == KEY_EMPTY && c.lo == KEY_EMPTY) {
-            const unsigned g = atomicAdd(P.group_count, 1u);
-            if (g >= P.max_groups) atomicExch(P.overflow, 1);
-            break;
-          }
-        }
-        if (key_equal(mine[j], c, kc, kc)) break;
-        slot[j] = (slot[j] + 1) & P.mask;
-        if (++probes > 4096) { atomicExch(P.overflow, 1); ok &= ~(1u << j); break; }
-        c = ld128(reinterpret_cast<const Key16*>(P.table + slot[j] * (unsigned long long)P.slot_stride));
+      Key16 mine;
+      unsigned int h32;
+      if (bytes_key && staged && col_valid(kc, row)) {
+        make_key_smem(in_bytes + (off[j] - s_str_base), off[j + 1] - off[j], row, &mine, &h32);
+      } else {
+        int llen = 0;
+        const uint8_t* lp = make_key_raw(P.key_kind, kc, row, &mine, &llen);
+        if (lp) { const unsigned long long h = hash_bytes(lp, llen); h32 = (unsigned)(h >> 32) ^ (unsigned)h; }
+        else h32 = hash32_key16(mine);
       }
+      slot[j] = region_find_or_claim(K, S, h32 & (unsigned)(S - 1), mine, kc, &claimed);
+      if (slot[j] < 0) { full = true; ok &= ~(1u << j); }
     }
     // ---- accumulate ----
     for (int a = 0; a < P.n_acc; ++a) {
@@ -203,7 +247,7 @@ __global__ void __launch_bounds__(HT_THREADS, 4) hash_agg_tile_kernel(const __gr
       if (A.kind != ACC_COUNT_STAR) {
         const ColView& c = P.cols[A.arg_slot];
         const unsigned long long* src = (const unsigned long long*)c.data + row0 + lr0;
-        if (full && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        if (full_rows && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
           asm volatile("ld.global.cs.v2.u64 {%0, %1}, [%2];" : "=l"(av[0]), "=l"(av[1]) : "l"(src));
           asm volatile("ld.global.cs.v2.u64 {%0, %1}, [%2];" : "=l"(av[2]), "=l"(av[3]) : "l"(src + 2));
         } else {
@@ -215,23 +259,60 @@ __global__ void __launch_bounds__(HT_THREADS, 4) hash_agg_tile_kernel(const __gr
           for (int j = 0; j < 4; ++j) if (((valid >> j) & 1) && !col_valid(c, row0 + lr0 + j)) valid &= ~(1u << j);
         }
       }
+      unsigned long long* acc = ACC + ((tiny ? (tid >> 5) * P.n_acc : 0) + a) * S;
+      if (tiny) {
+        const int is_f64 = A.arg_is_f64;
+        switch (A.kind) {
+          case ACC_COUNT_STAR: case ACC_COUNT: tiny_accumulate<0>(acc, slot, ok, valid, av, is_f64, lane); break;
+          case ACC_SUM_I64: tiny_accumulate<1>(acc, slot, ok, valid, av, is_f64, lane); break;
+          case ACC_SUM_F64: tiny_accumulate<2>(acc, slot, ok, valid, av, is_f64, lane); break;
+          case ACC_MIN_I64: tiny_accumulate<3>(acc, slot, ok, valid, av, is_f64, lane); break;
+          case ACC_MIN_F64: tiny_accumulate<4>(acc, slot, ok, valid, av, is_f64, lane); break;
+          case ACC_MAX_I64: tiny_accumulate<5>(acc, slot, ok, valid, av, is_f64, lane); break;
+          default: tiny_accumulate<6>(acc, slot, ok, valid, av, is_f64, lane); break;
+        }
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (!((valid >> j) & 1)) continue;
-        unsigned long long* dst = priv_slots ? priv + slot[j] * P.n_acc + a
-                                             : reinterpret_cast<unsigned long long*>(P.table + slot[j] * (unsigned long long)P.slot_stride + A.acc_offset);
-        accumulate(A.kind, A.arg_is_f64, dst, av[j]);
+        for (int j = 0; j < 4; ++j)
+          if ((valid >> j) & 1) accumulate(A.kind, A.arg_is_f64, acc + slot[j], av[j]);
       }
     }
     __syncthreads();  // everyone is done with in_bytes before the next tile's bulk copy overwrites it
   }
-  // ---- flush the privatised accumulators ----
-  if (priv_slots) {
-    for (int i = tid; i < priv_slots * P.n_acc; i += HT_THREADS) {
-      const int a = i % P.n_acc, s = i / P.n_acc;
-      const unsigned long long v = priv[i];
+  if (full) atomicExch(P.overflow, 1);
+  __syncthreads();
+  if (tiny) {  // fold the warps' copies into copy 0
+    for (int i = tid; i < P.n_acc * S; i += HT_THREADS)
+      for (int w = 1; w < copies; ++w) fold_acc(P.accs[i / S].kind, ACC + i, ACC[w * P.n_acc * S + i]);
+    __syncthreads();
+  }
+  // ---- merge this CTA's groups into the global table ----
+  for (int s = tid; s < S; s += HT_THREADS) {
+    const Key16 mine = K[s];
+    if (mine.hi == KEY_EMPTY) continue;
+    unsigned long long g = (P.key_kind == KEY_NONE ? 0ull : stored_key_hash(mine, kc)) & P.mask;
+    int probes = 0;
+    bool placed = false;
+    while (true) {
+      Key16* sk = reinterpret_cast<Key16*>(P.table + g * (unsigned long long)P.slot_stride);
+      Key16 c = ld128(sk);
+      if (c.hi == KEY_EMPTY) {
+        c = cas128(sk, Key16{KEY_EMPTY, KEY_EMPTY}, mine);
+        if (c.hi == KEY_EMPTY && c.lo == KEY_EMPTY) {
+          const unsigned cnt = atomicAdd(P.group_count, 1u);
+          if (cnt >= P.max_groups) atomicExch(P.overflow, 1);
+          placed = true; break;
+        }
+      }
+      if (key_equal(mine, c, kc, kc)) { placed = true; break; }
+      g = (g + 1) & P.mask;
+      if (++probes > 4096) { atomicExch(P.overflow, 1); break; }
+    }
+    if (!placed) continue;
+    for (int a = 0; a < P.n_acc; ++a) {
+      const unsigned long long v = ACC[a * S + s];
       if (v != acc_identity(P.accs[a].kind))
-        merge_acc(P.accs[a].kind, reinterpret_cast<unsigned long long*>(P.table + (unsigned long long)s * P.slot_stride + P.accs[a].acc_offset), v);
+        merge_acc(P.accs[a].kind, reinterpret_cast<unsigned long long*>(P.table + g * (unsigned long long)P.slot_stride + P.accs[a].acc_offset), v);
     }
   }
 }
@@ -239,7 +320,7 @@ __global__ void __launch_bounds__(HT_THREADS, 4) hash_agg_tile_kernel(const __gr
 }  // namespace
 
 // Returns false when the plan/batch shape is not covered (caller uses hash_agg_kernel).
-bool launch_hash_agg_tile(const AggParams& P, unsigned long long capacity, int64_t key_bytes, cudaStream_t stream) {
+bool launch_hash_agg_tile(const AggParams& P, unsigned long long capacity, unsigned int groups_hint, int64_t key_bytes, cudaStream_t stream) {
   if (P.pred_kind == 2) return false;
   for (int a = 0; a < P.n_acc; ++a) if (P.accs[a].arg_prog >= 0) return false;
   const int64_t n = P.n_rows;
@@ -251,20 +332,26 @@ bool launch_hash_agg_tile(const AggParams& P, unsigned long long capacity, int64
     cap = (int)round_up((int64_t)(avg * HT_TILE * 1.0625) + 64, 1024);
     cap = std::max(4096, std::min(cap, 48 * 1024));
   }
-  int priv_slots = 0;
-  if (capacity <= 2048 && P.n_acc <= 6) priv_slots = (int)capacity;
-  const size_t smem = (cap ? cap + 32 : 0) + (size_t)priv_slots * P.n_acc * 8;
+  if (capacity > 2048 || (capacity & (capacity - 1)) || P.n_acc > 6) return false;
+  // shared-memory table: 4× the groups last seen (short probe chains keep the lanes of a warp together), between 16
+  // slots (tiny tables reduce inside the warp first) and the global capacity
+  int log2_slots = 4;
+  const unsigned long long want = groups_hint ? 4ull * groups_hint : capacity;
+  while ((1ull << log2_slots) < want && (1ull << log2_slots) < capacity) ++log2_slots;
+  const size_t copies = log2_slots <= 6 ? HT_THREADS / 32 : 1;
+  const size_t smem = (cap ? cap + 32 : 0) + ((size_t)(16 + 8 * P.n_acc * copies) << log2_slots);
   static bool configured = false;
   if (!configured) {
-    ARK_CUDA(cudaFuncSetAttribute(hash_agg_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    ARK_CUDA(cudaFuncSetAttribute(hash_agg_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    ARK_CUDA(cudaFuncSetAttribute(hash_agg_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ARK_CUDA(cudaFuncSetAttribute(hash_agg_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
   const int n_tiles = (int)ceil_div(n, HT_TILE);
-  const int grid = std::max(1, std::min(n_tiles, 148 * 4));
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / std::max<size_t>(smem, 1)));
+  const int grid = std::max(1, std::min(n_tiles, 148 * per_sm));
   KernelTimer t("hash_agg_tile_kernel", stream);
-  if (P.pred_kind == 0) hash_agg_tile_kernel<0><<<grid, HT_THREADS, smem, stream>>>(P, cap, priv_slots);
-  else hash_agg_tile_kernel<1><<<grid, HT_THREADS, smem, stream>>>(P, cap, priv_slots);
+  if (P.pred_kind == 0) hash_agg_tile_kernel<0><<<grid, HT_THREADS, smem, stream>>>(P, cap, log2_slots);
+  else hash_agg_tile_kernel<1><<<grid, HT_THREADS, smem, stream>>>(P, cap, log2_slots);
   return true;
 }
 
