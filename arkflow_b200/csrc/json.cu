@@ -471,7 +471,6 @@ struct InferredField { std::string name; DType type; bool supported; std::string
 std::vector<InferredField> infer_schema(const std::string& first_record) {
   JsonValue v;
   try {
-    size_t used = 0;
     // the first payload may hold several records: parse only the first value
     std::string s = first_record;
     // find the end of the first top-level value by bracket matching
@@ -484,7 +483,6 @@ std::vector<InferredField> infer_schema(const std::string& first_record) {
       else if (ch == '}' || ch == ']') { if (--depth == 0) { end = i + 1; break; } }
       else if (depth == 0 && !isspace((unsigned char)ch)) break;
     }
-    (void)used;
     if (end == std::string::npos) fail(ARK_ERR_PROCESS, "Schema inference error: Json error: Expected JSON record to be an object");
     v = parse_json(s.substr(0, end));
   } catch (const ArkError& e) {
