@@ -62,12 +62,17 @@ __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_cons
     Key16 cur = cas128(slot_key(P.table, h & P.mask, P.slot_stride), Key16{KEY_EMPTY, KEY_EMPTY}, mine);
     if (cur.hi == KEY_EMPTY && cur.lo == KEY_EMPTY) atomicAdd(P.group_count, 1u);
   }
+  __shared__ volatile int32_t s_stop;
+  if (threadIdx.x == 0) s_stop = 0;
+  __syncthreads();
+  unsigned int claimed = 0;
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x * R; base < n; base += stride) {
-    // the table is too small (first batch of a high-cardinality stream): stop, the host retries with 4× the slots —
-    // without this every remaining row walks a full table (measured 63 ms for one 2^24-row launch).  The flag is
-    // loaded here and looked at only at the END of the iteration, so its latency hides behind the row's own loads
-    // (testing it up front cost 0.97 → 1.30 ms per launch).
-    const int32_t stop_flag = *reinterpret_cast<volatile int32_t*>(P.overflow);
+    // A table that is too small (first batch of a high-cardinality stream): once some row has raised `overflow` the
+    // launch is void (the host retries with 4× the slots), so stop instead of walking a full table with every
+    // remaining row (63 ms for one 2^24-row launch).  ONE thread per CTA polls the flag — every thread polling the
+    // same L2 line cost 0.33 ms per launch — and the other warps pick it up from shared memory an iteration later.
+    if (threadIdx.x == 0) s_stop = *reinterpret_cast<volatile int32_t*>(P.overflow);
+    if (__any_sync(0xffffffffu, s_stop != 0)) break;  // warp-uniform: the full-mask shuffles below need every lane
     int64_t row[R];
     bool ok[R];
     Key16 mine[R];
@@ -106,16 +111,16 @@ __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_cons
       int probes = 0;
       while (true) {
         if (c.hi == KEY_EMPTY) {
+          // A table that is too small (first batch of a high-cardinality stream) must not fill up: past the load
+          // limit no new key is inserted, so probe chains stay short and the launch ends quickly with `overflow`
+          // set (the host retries with 4× the slots).  Without this the remaining rows walk a full table —
+          // 63 ms for one 2^24-row launch.  Only rows that found an EMPTY slot pay for the counter read.
           c = cas128(slot_key(P.table, slot[r], P.slot_stride), Key16{KEY_EMPTY, KEY_EMPTY}, mine[r]);
-          if (c.hi == KEY_EMPTY && c.lo == KEY_EMPTY) {  // claimed
-            const unsigned g = atomicAdd(P.group_count, 1u);
-            if (g >= P.max_groups) atomicExch(P.overflow, 1);
-            break;
-          }
+          if (c.hi == KEY_EMPTY && c.lo == KEY_EMPTY) { ++claimed; break; }  // counted per thread, added once per warp at the end
         }
         if (key_equal(mine[r], c, kc, kc)) break;
         slot[r] = (slot[r] + 1) & P.mask;
-        if (++probes > 4096) { atomicExch(P.overflow, 1); ok[r] = false; break; }
+        if (++probes > 128) { atomicExch(P.overflow, 1); ok[r] = false; break; }  // the table is too loaded for this batch
         c = ld128(slot_key(P.table, slot[r], P.slot_stride));
       }
     }
@@ -169,8 +174,9 @@ __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_cons
         }
       }
     }
-    if (__any_sync(0xffffffffu, stop_flag != 0)) break;  // warp-uniform: the full-mask shuffles above need every lane
   }
+  claimed = (unsigned int)__reduce_add_sync(0xffffffffu, claimed);
+  if (lane == 0 && claimed) atomicAdd(P.group_count, claimed);
   if (err) atomicExch(P.error, err);
 }
 
