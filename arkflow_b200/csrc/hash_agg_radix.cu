@@ -1,10 +1,5 @@
-// hash_agg_radix.cu — GROUP BY for tables that outgrow the L2: radix-partition the rows by table region,
-// then build each region of the open-addressing table in shared memory.
-//
-// hash_agg_kernel (hash_agg.cu) sends every row to a random 32-byte slot.  While the table sits in the
-// 126 MB L2 that is the fastest path measured (10^6 groups, 64 MB: 0.97 ms per 2^24 rows); beyond it
-// every probe and every accumulator update is a random DRAM sector access (4·10^6 groups: 2.75 ms,
-// 8·10^6: 3.0 ms).  Here random access never leaves the SM:
+// hash_agg_radix.cu — GROUP BY by radix partitioning: an ALTERNATIVE to hash_agg_kernel that is kept, tested and
+// measured, but is NOT taken by default (ARK_AGG_RADIX=1 enables it from 2^22 table slots, =2 from 2^16).
 //
 //   K1  agg_radix_partition_kernel: one CTA per 2048-row tile.  Predicate and key as in hash_agg_kernel;
 //       the top bits of a 32-bit key hash name a *bucket* = one contiguous region of S table slots.
@@ -13,14 +8,16 @@
 //       per tile reserves the range): sequential reads, run-coalesced writes.  (Scattering the
 //       records straight from registers instead of sorting them first was measured 40 % slower.)
 //   K2  agg_radix_bucket_kernel: one CTA per bucket.  The region's S slots live in shared memory
-//       (keys + accumulators, SoA); the bucket's records stream in coalesced, probe/claim/accumulate
-//       with shared-memory atomics, and the finished region is written to the global table in the
+//       (smem_table.cuh); the bucket's records stream in coalesced, probe/claim/accumulate with
+//       shared-memory atomics, and the finished region is written to the global table in the
 //       layout hash_agg_kernel produces — so everything downstream (compaction, key/aggregate
 //       emission, partition ordering for the multi-GPU exchange) is shared.
 //
-// Traffic: input once (24 B/row for config 3) + records written and read once (24 B/row each) + the
-// table written once.  Measured per 2^24 rows (K1 + K2): 1.10 ms at 10^6 groups, 1.41 ms at 4·10^6,
-// 1.59 ms at 8·10^6 — so the launcher takes this path from 2^22 slots (a 128 MB table) upwards.
+// History of the measurement (per 2^24 rows, K1 + K2 vs hash_agg_kernel): while hash_agg_kernel still did one
+// returning atomicAdd on a single counter per inserted group, it lost badly on large tables and this path won —
+// 4·10^6 groups 1.41 vs 2.75 ms, 8·10^6 1.59 vs 3.00 ms.  With that hot atomic gone the direct kernel takes
+// 0.63 / 0.81 / 1.20 ms at 10^6 / 4·10^6 / 8·10^6 groups against 1.10 / 1.16 / 1.45 ms here: moving every record
+// through HBM twice costs more than the random table accesses it avoids, even with a 512 MB table.
 // Covered shape = that of the tiled kernel (no VM programs), non-nullable argument columns, ≤ 2
 // distinct argument columns.  A skewed key distribution overflows a bucket's record array; the
 // kernels raise `skew`, and the caller reruns the batch through hash_agg_kernel.
@@ -255,8 +252,8 @@ std::atomic<int> g_skew_backoff{0};
 // (the kernels raise it in device memory at `skew_dev`).  When the flag is set the table is garbage and
 // the caller reruns with hash_agg_kernel.
 bool launch_hash_agg_radix(const AggParams& P, unsigned long long capacity, int32_t* skew_dev, std::vector<BufferPtr>* keep, cudaStream_t stream) {
-  const char* mode_env = getenv("ARK_AGG_RADIX");  // read per call (tests flip it): 0 = never, 2 = already from 2^16 rows / slots
-  const int mode = mode_env ? atoi(mode_env) : 1;
+  const char* mode_env = getenv("ARK_AGG_RADIX");  // read per call (tests flip it): 0 = never (default), 1 = from 2^22 slots, 2 = from 2^16 rows / slots
+  const int mode = mode_env ? atoi(mode_env) : 0;
   static const int log2_slots_env = [] { const char* e = getenv("ARK_AGG_RADIX_S"); return e ? atoi(e) : 12; }();
   if (!mode) return false;
   const int64_t n = P.n_rows;
