@@ -16,6 +16,7 @@
 // A batch with more distinct keys than slots raises `overflow`; the host retries with 4× the slots.
 #include <atomic>
 
+#include "tma.cuh"
 #include "agg_acc.cuh"
 #include "engine.h"
 #include "hash_agg.cuh"
@@ -29,24 +30,6 @@ namespace {
 constexpr int HT_THREADS = 256;
 constexpr int HT_TILE = HT_THREADS * 4;
 
-__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra.uni WAIT_DONE;\n\tbra.uni WAIT_LOOP;\n\tWAIT_DONE:\n\t}"
-      ::"r"(smem_addr(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
 
 // Key16 + 32-bit table hash of a byte string that sits in shared memory (same key encoding as make_key)
 __device__ __forceinline__ void make_key_smem(const uint8_t* p, int len, int64_t row, Key16* key, unsigned int* hash) {
@@ -147,7 +130,7 @@ __global__ void __launch_bounds__(HT_THREADS, 3) hash_agg_tile_kernel(const __gr
 
   if (tid == 0) {
     mbar_init(&s_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
     if (P.key_kind == KEY_NONE && blockIdx.x == 0) {  // a global aggregate always yields one row
       Key16 mine; unsigned long long h;
       make_key(KEY_NONE, kc, 0, &mine, &h);

@@ -20,6 +20,15 @@ namespace {
 
 constexpr unsigned int NO_ROW = 0xFFFFFFFFu;
 
+// table hash of the join: 32 bits are plenty for ≤ 2^31 slots and cost a quarter of hash_key16
+__device__ __forceinline__ unsigned long long join_key(int key_kind, const ColView& c, int64_t row, Key16* key) {
+  int llen = 0;
+  const uint8_t* lp = make_key_raw(key_kind, c, row, key, &llen);
+  if (lp) return hash_bytes(lp, llen);
+  const unsigned h = hash32_key16(*key);
+  return ((unsigned long long)h << 32) | (h * 0x9E3779B1u);  // spread over 64 bits: masks wider than 32 bits stay usable
+}
+
 __global__ void join_init_kernel(Key16* keys, unsigned int* head, unsigned long long capacity) {
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
        i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -32,8 +41,8 @@ __global__ void join_build_kernel(ColView kc, int key_kind, int64_t n, Key16* ke
                                   unsigned long long mask) {
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
     if (!col_valid(kc, row)) { next[row] = NO_ROW; continue; }  // NULL keys never match
-    Key16 mine; unsigned long long h;
-    make_key(key_kind, kc, row, &mine, &h);
+    Key16 mine;
+    const unsigned long long h = join_key(key_kind, kc, row, &mine);
     unsigned long long slot = h & mask;
     while (true) {
       Key16 cur = ld128(keys + slot);
@@ -55,8 +64,8 @@ __global__ void join_probe_count_kernel(ColView pc, ColView bc, int key_kind, in
     long long c = 0;
     unsigned int found = NO_ROW;
     if (col_valid(pc, row)) {
-      Key16 mine; unsigned long long h;
-      make_key(key_kind, pc, row, &mine, &h);
+      Key16 mine;
+      const unsigned long long h = join_key(key_kind, pc, row, &mine);
       unsigned long long slot = h & mask;
       while (true) {
         const Key16 cur = keys[slot];  // the table is read-only during the probe

@@ -19,6 +19,7 @@
 #include <cmath>
 
 #include "engine.h"
+#include "tma.cuh"
 #include "json_mini.h"
 #include "pow10_table.h"
 
@@ -58,7 +59,6 @@ struct JsonParams {
 
 constexpr int JS_THREADS = 128;
 
-__device__ __forceinline__ unsigned js_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 struct Cursor {
   const uint8_t* p;
@@ -317,11 +317,10 @@ __global__ void __launch_bounds__(JS_THREADS) json_parse_kernel(const __grid_con
       const uintptr_t a0 = reinterpret_cast<uintptr_t>(P.data + o0), a1 = reinterpret_cast<uintptr_t>(P.data + o1);
       const uintptr_t lo = a0 & ~(uintptr_t)15, hi = (a1 + 15) & ~(uintptr_t)15;
       if (o1 > o0 && hi - lo <= (uintptr_t)P.stage_bytes) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(js_smem_addr(&s_bar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(js_smem_addr(&s_bar)), "r"((unsigned)(hi - lo)) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(js_smem_addr(js_stage)), "l"(reinterpret_cast<const void*>(lo)), "r"((unsigned)(hi - lo)), "r"(js_smem_addr(&s_bar)) : "memory");
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&s_bar, (unsigned)(hi - lo));
+        tma_load_1d(js_stage, reinterpret_cast<const void*>(lo), (unsigned)(hi - lo), &s_bar);
         s_stage_off = (long long)o0 - (long long)(a0 - lo);
         s_staged = 1;
       }
@@ -330,12 +329,7 @@ __global__ void __launch_bounds__(JS_THREADS) json_parse_kernel(const __grid_con
   __syncthreads();
   const bool staged = s_staged != 0;
   const long long stage_off = staged ? s_stage_off : 0;
-  if (staged) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tJS_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
-        "@p bra.uni JS_DONE;\n\tbra.uni JS_WAIT;\n\tJS_DONE:\n\t}" ::"r"(js_smem_addr(&s_bar)) : "memory");
-  }
+  if (staged) mbar_wait(&s_bar, 0);
   if (i >= P.n_payloads) return;
   if (P.validity && !((P.validity[(i + P.validity_bit0) >> 3] >> ((i + P.validity_bit0) & 7)) & 1)) {
     if (MODE == 0) P.counts[i] = 0;
