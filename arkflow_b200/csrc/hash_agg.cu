@@ -373,9 +373,8 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     // and the set-aside it needs, cudaLimitPersistingL2CacheSize, stays carved out of the L2 for every later
     // kernel of the process: a following concat ran at 0.35 ms instead of 0.16 ms.  Removed.)
     const int64_t key_bytes = ex.key_kind == KEY_BYTES ? in.cols[plan.used_cols[ex.key_slot]].data_bytes : 0;
-    // small tables (≤ 2048 slots): tiled kernel with shared-memory privatised accumulators (hot keys would
-    // serialise on L2 atomics: K = 2 → 12.3 ms vs 1.6 ms).  Large tables: measured 0.95 ms (row kernel) vs
-    // 1.22 ms (tiled) at 10^6 keys — the row kernel keeps more independent probes in flight.
+    // low cardinality (table ≤ 1024 slots): per-CTA hash table in shared memory (hash_agg_tile.cu) — hot keys would
+    // serialise on L2 atomics here (K = 2: 12.9 ms vs 0.24 ms).  Everything larger: this file's row kernel.
     static const unsigned long long tile_max = [] { const char* e = getenv("ARK_AGG_TILE_MAX"); return e ? (unsigned long long)atoll(e) : 1024ull; }();  // 2048 slots (≈ 1000 groups): 1.65 ms here vs 1.34 ms in hash_agg_kernel
     if (radix) {
     } else if (n > 0 && capacity <= tile_max && launch_hash_agg_tile(P, capacity, g_groups_hint.load(), key_bytes, stream)) {
