@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_cons
         }
         if (key_equal(mine[r], c, kc, kc)) break;
         slot[r] = (slot[r] + 1) & P.mask;
-        if (++probes > 128) { atomicExch(P.overflow, 1); ok[r] = false; break; }  // the table is too loaded for this batch
+        if (++probes > 512) { atomicExch(P.overflow, 1); ok[r] = false; break; }  // the table is too loaded for this batch (longest run expected at load 0.5: ~75 slots, at 0.75: ~400)
         c = ld128(slot_key(P.table, slot[r], P.slot_stride));
       }
     }
