@@ -147,15 +147,16 @@ static bool try_fast_filter(const Plan& plan, Batch& in, Batch& out, cudaStream_
   const size_t scratch_bytes = round_up((int64_t)desc_bytes + 64 + FP_CHANNELS * 8, 256);
   BufferPtr scratch = device_alloc(scratch_bytes);
   ARK_CUDA(cudaMemsetAsync(scratch.get(), 0, scratch_bytes, stream));
-  long long* totals = (long long*)((char*)scratch.get() + desc_bytes + 16);
+  // the kernel's last tile stores the two totals straight into pinned host memory (device-accessible under unified
+  // addressing): one stream synchronize, no separate device→host copy on the critical path of every call
+  BufferPtr host_res = pinned_alloc(64);
+  long long* totals = (long long*)host_res.get();
   if (!launch_filter_project_tma(n, src_col(plan.simple.slot).data, (int)fixed_outs.size(), fin, fout, vs ? vs->offsets : nullptr,
                                  vs ? vs->data : nullptr, vs ? vs->data_bytes : 0 /* -1 = unknown */, vs ? (int32_t*)obuf.get() : nullptr,
                                  vs ? (uint8_t*)dbuf.get() : nullptr, plan.simple.cmp, plan.simple.is_f64, plan.simple.constant,
                                  (unsigned long long*)scratch.get(), (unsigned int*)((char*)scratch.get() + desc_bytes), totals, stream))
     return false;
   ARK_CUDA(cudaGetLastError());
-  BufferPtr host_res = pinned_alloc(64);
-  ARK_CUDA(cudaMemcpyAsync(host_res.get(), totals, 16, cudaMemcpyDeviceToHost, stream));
   ARK_CUDA(cudaStreamSynchronize(stream));
   const int64_t count = ((const int64_t*)host_res.get())[0], bytes = ((const int64_t*)host_res.get())[1];
   if (vs && count > 0) filter_project_tma_note_avg_len((double)bytes / (double)count);
