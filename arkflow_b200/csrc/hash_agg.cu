@@ -46,6 +46,17 @@ __global__ void agg_init_kernel(uint8_t* table, unsigned long long capacity, int
 
 constexpr int AGG_THREADS = 256;
 
+// home-slot hash of this kernel's table: the 32-bit key hash spread over 64 bits (a quarter of hash_key16's
+// instructions; the 64-bit hash stays what partitions groups across GPUs, see partition_of)
+__device__ __forceinline__ unsigned long long table_hash(int key_kind, const ColView& c, int64_t row, Key16* key) {
+  int llen = 0;
+  const uint8_t* lp = make_key_raw(key_kind, c, row, key, &llen);
+  if (key_kind == KEY_NONE) return 0;
+  if (lp) return hash_bytes(lp, llen);
+  const unsigned h = hash32_key16(*key);
+  return ((unsigned long long)h << 32) | (h * 0x9E3779B1u);
+}
+
 // R rows per thread per iteration, processed phase by phase (predicate → key → slot fetch → claim →
 // accumulate) so that the R dependent load chains of a thread overlap (R = 1 is what is launched, see launch_agg).
 template <int PRED, int R>
@@ -99,7 +110,7 @@ __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_cons
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       slot[r] = 0;
-      if (ok[r]) { unsigned long long h; make_key(P.key_kind, kc, row[r], &mine[r], &h); slot[r] = h & P.mask; }
+      if (ok[r]) slot[r] = table_hash(P.key_kind, kc, row[r], &mine[r]) & P.mask;
     }
     // ---- all slots fetched before any is resolved ----
 #pragma unroll
