@@ -117,8 +117,21 @@ void* BlockPool::alloc(size_t bytes) {
   return p;
 }
 
+// A block released while the calling thread is inside a C-ABI call (it holds a StreamLease) may still be read or
+// written by work that call has queued on its stream — cub temporaries, staging blocks and the like go out of scope
+// right after the launch.  Handing such a block to ANOTHER thread's call would corrupt both, so it is parked here
+// and returns to the pool when the thread's outermost lease ends, after the stream synchronize in ~StreamLease.
+// (Blocks released outside a call — an Arrow consumer dropping a result — belong to calls that completed.)
+static thread_local int tl_lease_depth = 0;
+static thread_local std::vector<std::pair<BlockPool*, void*>> tl_parked;
+
 void BlockPool::free(void* p) {
   if (!p) return;
+  if (tl_lease_depth > 0) { tl_parked.push_back({this, p}); return; }
+  free_now(p);
+}
+
+void BlockPool::free_now(void* p) {
   std::lock_guard<std::mutex> l(mu_);
   for (size_t i = 0; i < live_.size(); ++i) {
     if (live_[i].p == p) {
@@ -156,13 +169,22 @@ StreamLease::StreamLease() {
   ensure_device();
   {
     std::lock_guard<std::mutex> l(g_stream_mu);
-    if (!g_streams.empty()) { s = g_streams.back(); g_streams.pop_back(); return; }
+    if (!g_streams.empty()) { s = g_streams.back(); g_streams.pop_back(); ++tl_lease_depth; return; }
   }
   ARK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  ++tl_lease_depth;
 }
 StreamLease::~StreamLease() {
-  std::lock_guard<std::mutex> l(g_stream_mu);
-  g_streams.push_back(s);
+  cudaStreamSynchronize(s);  // whatever this call queued is done: its temporaries may now serve any other call
+  {
+    std::lock_guard<std::mutex> l(g_stream_mu);
+    g_streams.push_back(s);
+  }
+  if (--tl_lease_depth == 0 && !tl_parked.empty()) {
+    std::vector<std::pair<BlockPool*, void*>> v;
+    v.swap(tl_parked);
+    for (auto& e : v) e.first->free_now(e.second);
+  }
 }
 
 // ---- schema helpers -------------------------------------------------------------------------------------

@@ -17,16 +17,17 @@
 namespace ark {
 
 // ---- memory pools -------------------------------------------------------------------------------
-// Caching allocators.  Every C-ABI call ends with a synchronize of its stream, and Arrow's contract
-// is that a consumer releases an array only when it is done with it, so a freed block is idle and can
-// be handed to any stream without event tracking.
+// Caching allocators.  A block freed inside a call is parked until that call's stream has been synchronised
+// (~StreamLease); Arrow's contract is that a consumer releases an array only when it is done with it.  So a
+// block in the free list is idle and can be handed to any stream without event tracking.
 class BlockPool {
  public:
   enum Kind { Device, Pinned };
   explicit BlockPool(Kind k) : kind_(k) {}
   ~BlockPool();
   void* alloc(size_t bytes);
-  void free(void* p);
+  void free(void* p);      // parks the block while the calling thread is inside a call (see batch.cu)
+  void free_now(void* p);
   size_t bytes_reserved() const { return reserved_; }
   void trim();
 
