@@ -8,6 +8,7 @@ torch is only the owner of device memory here.
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 from typing import Optional
 
 import pyarrow as pa
@@ -131,12 +132,11 @@ def _keepalive_release_schema(ptr):
 
 _REL_ARR = L.RELEASE_ARRAY(_keepalive_release_array)
 _REL_SCH = L.RELEASE_SCHEMA(_keepalive_release_schema)
-_next_token = [1]
+_next_token = itertools.count(1)  # next() on a count is atomic under the GIL: worker threads never share a token
 
 
 def _token(obj) -> int:
-    t = _next_token[0]
-    _next_token[0] += 1
+    t = next(_next_token)
     _live_exports[t] = obj
     return t
 

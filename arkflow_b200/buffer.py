@@ -9,6 +9,7 @@ All compute (concatenation, join) goes through the C ABI; there is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import json
 from typing import Optional
 
@@ -93,12 +94,11 @@ class Buffer:
         _check(lib.ark_buffer_create(self.KIND.encode(), cfg, names, C.byref(handle)))
         self._h = handle
         self._acks: dict[int, Ack] = {}
-        self._next = 1
+        self._next = itertools.count(1)  # write() may be called from several input threads
 
     def write(self, msg, ack: Optional[Ack] = None) -> None:
         mb = msg if isinstance(msg, MessageBatch) else MessageBatch(msg)
-        token = self._next
-        self._next += 1
+        token = next(self._next)
         self._acks[token] = ack or NoopAck()
         arr, sch = F.export_record_batch(mb.record_batch)
         try:
