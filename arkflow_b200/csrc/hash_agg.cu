@@ -331,12 +331,11 @@ bool launch_hash_agg_tile(const AggParams& P, unsigned long long capacity, unsig
 bool launch_hash_agg_radix(const AggParams& P, unsigned long long capacity, int32_t* skew_dev, std::vector<BufferPtr>* keep, cudaStream_t stream);
 void hash_agg_radix_note_skew();
 
-static std::atomic<unsigned long long> g_capacity_hint{1ull << 16};
-static std::atomic<unsigned int> g_groups_hint{0};  // groups of the previous batch (0 = none yet)
 
 static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int n_parts, cudaStream_t stream) {
   const int64_t n = in.num_rows;
-  unsigned long long capacity = std::max<unsigned long long>(g_capacity_hint.load(), 1ull << 10);
+  AggHints& hints = *plan.hints;  // per plan: the table size this query needed last time
+  unsigned long long capacity = std::max<unsigned long long>(hints.capacity.load(), 1ull << 10);
   const unsigned long long cap_limit = 1ull << 31;
   DenseGroups dg;
   BufferPtr ctl = device_alloc(512);  // [group_count u32 | overflow i32 | error i32 | skew i32 | part_counts u32[32] | part_cursor u32[32]]
@@ -388,7 +387,7 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     // serialise on L2 atomics here (K = 2: 12.9 ms vs 0.24 ms).  Everything larger: this file's row kernel.
     static const unsigned long long tile_max = [] { const char* e = getenv("ARK_AGG_TILE_MAX"); return e ? (unsigned long long)atoll(e) : 1024ull; }();  // 2048 slots (≈ 1000 groups): 1.65 ms here vs 1.34 ms in hash_agg_kernel
     if (radix) {
-    } else if (n > 0 && capacity <= tile_max && launch_hash_agg_tile(P, capacity, g_groups_hint.load(), key_bytes, stream)) {
+    } else if (n > 0 && capacity <= tile_max && launch_hash_agg_tile(P, capacity, hints.groups.load(), key_bytes, stream)) {
     } else {
       if (P.pred_kind == 0) launch_agg<0>(P, n, stream);
       else if (P.pred_kind == 1) launch_agg<1>(P, n, stream);
@@ -408,7 +407,7 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     if (overflow || groups > P.max_groups) {
       if (capacity >= cap_limit) fail(ARK_ERR_PROCESS, "Collection query results error: group-by hash table exceeded 2^31 slots");
       capacity *= 4;
-      g_groups_hint.store(0);  // the previous batch's group count undersized the shared-memory table: size it by capacity
+      hints.groups.store(0);  // the previous batch's group count undersized the shared-memory table: size it by capacity
       continue;
     }
     if (err) fail(ARK_ERR_PROCESS, std::string("Collection query results error: ") +
@@ -419,8 +418,8 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     // the table of config 3 (10^6 keys × 32-byte slots = 64 MB) stays inside the 126 MB L2
     unsigned long long want = 1ull << 10;
     while (want < 2ull * groups) want <<= 1;
-    g_capacity_hint.store(want);
-    g_groups_hint.store(groups);
+    hints.capacity.store(want);
+    hints.groups.store(groups);
     break;
   }
   // dense, partition-ordered slot list

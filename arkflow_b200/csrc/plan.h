@@ -2,7 +2,9 @@
 // statement_to_plan + optimiser + physical planner produce per batch in the reference
 // (crates/arkflow-plugin/src/processor/sql.rs:188-204), produced here once per schema and cached.
 #pragma once
+#include <atomic>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -70,6 +72,13 @@ struct FinalItem {      // one column of the result, in SELECT order
   int index = 0;        // Plan::outputs index, or Plan::concats index
 };
 
+// What the previous batch taught an aggregate plan about its table: sized per plan (two queries of different
+// cardinality running side by side must not resize each other's tables).  Shared by the copies of a Plan.
+struct AggHints {
+  std::atomic<unsigned long long> capacity{1ull << 16};  // table slots to start with
+  std::atomic<unsigned int> groups{0};                   // groups of the previous batch (0 = none yet)
+};
+
 struct Plan {
   enum Kind { FilterProject, Aggregate, Join } kind = FilterProject;
   std::vector<Field> input_fields;   // of table 0
@@ -88,6 +97,7 @@ struct Plan {
   std::vector<std::string> key_names;
   std::vector<AggSpec> aggs;
   std::vector<PostItem> post;
+  std::shared_ptr<AggHints> hints = std::make_shared<AggHints>();
   // Join (two tables, inner equi-join)
   std::string left_table, right_table;
   std::vector<Field> right_fields;
