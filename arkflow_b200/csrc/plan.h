@@ -62,10 +62,12 @@ struct ConcatPart {
   bool is_literal = false;
   std::string literal;
   int out_index = -1;   // index into Plan::outputs (visible or hidden)
+  DType col_type = DType::Utf8;  // Utf8 bytes, or an Int64 / Boolean column rendered as arrow-cast does ("-12", "true")
 };
 struct ConcatItem {
   std::string name;
   std::vector<ConcatPart> parts;
+  bool is_cast = false;  // CAST(col AS STRING): one part, NULL in ⇒ NULL out (concat() itself never yields NULL)
 };
 struct FinalItem {      // one column of the result, in SELECT order
   bool is_concat = false;

@@ -389,7 +389,9 @@ Plan bind_query(const Query& q, const std::string& table_name, const std::vector
           oc.src.kind = ValueSource::PassThrough; oc.src.slot = b.slot_of((int)c); oc.src.type = f.type; oc.src.nullable = f.nullable;
           plan.outputs.push_back(oc);
         }
-      } else if (it.expr->kind == Expr::Func && it.expr->name == "concat") {
+      } else if ((it.expr->kind == Expr::Func && it.expr->name == "concat") ||
+                 (it.expr->kind == Expr::Cast && it.expr->cast_to == DType::Utf8 && it.expr->args[0]->kind == Expr::Column &&
+                  (b.type_of(*it.expr->args[0]) == DType::Int64 || b.type_of(*it.expr->args[0]) == DType::Bool))) {
         all_star = false;
         concat_items.push_back({(int)plan.outputs.size(), &it});  // bound after the visible outputs
         OutputCol placeholder;
@@ -418,6 +420,7 @@ Plan bind_query(const Query& q, const std::string& table_name, const std::vector
           const Expr& e = *it.expr;
           if (e.distinct || e.star_arg || e.args.empty()) plan_error("Error during planning: concat expects at least one argument");
           ConcatItem ci;
+          ci.is_cast = e.kind == Expr::Cast;  // CAST(<Int64 | Boolean column> AS STRING)
           ci.name = !it.alias.empty() ? it.alias : display(e, b.table);
           for (auto& a : e.args) {
             ConcatPart part;
@@ -425,7 +428,9 @@ Plan bind_query(const Query& q, const std::string& table_name, const std::vector
             else if (a->kind == Expr::Literal && a->lit_type == DType::Null) { part.is_literal = true; }
             else if (a->kind == Expr::Column) {
               ValueSource v = b.value_source(*a);
-              if (v.type != DType::Utf8) unsupported(std::string("concat() over a ") + dtype_name(v.type) + " argument");
+              if (v.type != DType::Utf8 && v.type != DType::Int64 && v.type != DType::Bool)
+                unsupported(std::string("concat() over a ") + dtype_name(v.type) + " argument");
+              part.col_type = v.type;
               OutputCol hidden;
               hidden.name = "\x01src" + std::to_string(visible.size());
               hidden.src = v;

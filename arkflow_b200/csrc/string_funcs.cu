@@ -16,12 +16,16 @@ namespace {
 
 constexpr int CONCAT_MAX_PARTS = 8;
 
+enum : int32_t { PART_LITERAL = 0, PART_UTF8 = 1, PART_INT64 = 2, PART_BOOL = 3 };
+
 struct ConcatPartView {
-  const uint8_t* data;      // column bytes base, or the literal's bytes
-  const int32_t* offsets;   // nullptr ⇒ literal
+  const uint8_t* data;      // column bytes base / values / bit-packed booleans, or the literal's bytes
+  const int32_t* offsets;   // Utf8 columns only
   const uint8_t* validity;
   int32_t validity_bit0;
   int32_t lit_len;
+  int32_t kind;
+  int32_t data_bit0;
 };
 
 struct ConcatParams {
@@ -30,9 +34,32 @@ struct ConcatParams {
   ConcatPartView parts[CONCAT_MAX_PARTS];
 };
 
-__device__ __forceinline__ int part_len(const ConcatPartView& p, int64_t r, const uint8_t** src) {
-  if (!p.offsets) { *src = p.data; return p.lit_len; }
+// decimal text of an i64, as arrow-cast / lexical write it; returns the length (≤ 20)
+__device__ __forceinline__ int format_i64(long long v, uint8_t* out) {
+  unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+  uint8_t rev[20];
+  int n = 0;
+  do { rev[n++] = (uint8_t)('0' + u % 10); u /= 10; } while (u);
+  int k = 0;
+  if (v < 0) out[k++] = '-';
+  while (n) out[k++] = rev[--n];
+  return k;
+}
+
+// bytes of part p for row r: *src points at them (literal / column bytes) or they are rendered into scratch
+__device__ __forceinline__ int part_len(const ConcatPartView& p, int64_t r, const uint8_t** src, uint8_t* scratch) {
+  if (p.kind == PART_LITERAL) { *src = p.data; return p.lit_len; }
   if (p.validity) { const int64_t b = r + p.validity_bit0; if (!((p.validity[b >> 3] >> (b & 7)) & 1)) return 0; }
+  if (p.kind == PART_INT64) { *src = scratch; return format_i64(reinterpret_cast<const long long*>(p.data)[r], scratch); }
+  if (p.kind == PART_BOOL) {
+    const int64_t b = r + p.data_bit0;
+    const bool t = (p.data[b >> 3] >> (b & 7)) & 1;
+    const char* w = t ? "true" : "false";
+    const int n = t ? 4 : 5;
+    for (int i = 0; i < n; ++i) scratch[i] = (uint8_t)w[i];
+    *src = scratch;
+    return n;
+  }
   const int32_t o0 = p.offsets[r];
   *src = p.data + o0;
   return p.offsets[r + 1] - o0;
@@ -43,14 +70,16 @@ __global__ void concat_lengths_kernel(const __grid_constant__ ConcatParams P, in
   if (r >= P.n_rows) return;
   int total = 0;
   const uint8_t* src;
-  for (int k = 0; k < P.n_parts; ++k) total += part_len(P.parts[k], r, &src);
+  uint8_t scratch[24];
+  for (int k = 0; k < P.n_parts; ++k) total += part_len(P.parts[k], r, &src, scratch);
   lens[r] = total;
 }
 
 __device__ __forceinline__ void concat_row(const ConcatParams& P, int64_t r, uint8_t* d) {
+  uint8_t scratch[24];
   for (int k = 0; k < P.n_parts; ++k) {
     const uint8_t* src = nullptr;
-    const int len = part_len(P.parts[k], r, &src);
+    const int len = part_len(P.parts[k], r, &src, scratch);
     for (int i = 0; i < len; ++i) d[i] = src[i];
     d += len;
   }
@@ -100,10 +129,13 @@ Batch apply_concats(const Plan& plan, Batch& r, cudaStream_t stream) {
       if (part.is_literal) {
         memcpy((char*)lit_host.get() + pos, part.literal.data(), part.literal.size());
         v.data = (const uint8_t*)lit_dev.get() + pos; v.offsets = nullptr; v.lit_len = (int32_t)part.literal.size();
+        v.kind = PART_LITERAL;
         pos += part.literal.size();
       } else {
         const Column& c = r.cols[part.out_index];
         v.data = c.data; v.offsets = c.offsets; v.validity = c.validity; v.validity_bit0 = (int32_t)c.validity_bit0;
+        v.data_bit0 = (int32_t)c.data_bit0;
+        v.kind = part.col_type == DType::Int64 ? PART_INT64 : part.col_type == DType::Bool ? PART_BOOL : PART_UTF8;
       }
     }
     if (lit_bytes) ARK_CUDA(cudaMemcpyAsync(lit_dev.get(), lit_host.get(), lit_bytes, cudaMemcpyHostToDevice, stream));
@@ -134,6 +166,14 @@ Batch apply_concats(const Plan& plan, Batch& r, cudaStream_t stream) {
     c.offsets = (const int32_t*)offs.get(); c.data = (const uint8_t*)bytes.get(); c.data_bytes = total; c.first_offset = 0;
     c.validity = nullptr; c.null_count = 0;
     c.owners = {offs, bytes};
+    if (item.is_cast && !item.parts.empty() && !item.parts[0].is_literal) {  // CAST: NULL in ⇒ NULL out — the source's bitmap is the result's
+      const Column& src = r.cols[item.parts[0].out_index];
+      c.field.nullable = src.field.nullable;
+      if (src.validity) {
+        c.validity = src.validity; c.validity_bit0 = src.validity_bit0; c.null_count = src.null_count;
+        for (auto& o : src.owners) c.owners.push_back(o);
+      }
+    }
   }
   Batch out;
   out.num_rows = n;

@@ -556,7 +556,7 @@ class _Ctx:
             if e.name == "concat" and e.args:
                 for a in e.args:  # the library's subset: Utf8 columns and string / NULL literals
                     if a.kind == "col":
-                        if self.type_of(a) != "Utf8":
+                        if self.type_of(a) not in ("Utf8", "Int64", "Boolean"):
                             raise OracleError("Unsupported", f"concat() over a {self.type_of(a)} argument")
                     elif not (a.kind == "lit" and a.vtype in ("Utf8", "Null")):
                         raise OracleError("Unsupported", "concat() over a computed argument")
@@ -682,6 +682,8 @@ class _Ctx:
             parts = []
             for a in e.args:
                 v = self.eval(a, sel)
+                if v.dtype in ("Int64", "Boolean"):
+                    v = _cast(v, "Utf8")  # concat() coerces its arguments to strings
                 if v.dtype == "Null":
                     parts.append(pa.array([""] * n, type=pa.utf8()))
                 else:
@@ -722,6 +724,10 @@ def _cast(a: Vec, to: str) -> Vec:
         return Vec("Utf8", a.values.cast(pa.utf8()), a.valid)
     if a.dtype == "Utf8" and to == "Binary":
         return Vec("Binary", a.values.cast(pa.binary()), a.valid)
+    if a.dtype == "Int64" and to == "Utf8":  # arrow-cast: lexical decimal text
+        return Vec("Utf8", pa.array([str(int(v)) if ok else None for v, ok in zip(a.values.tolist(), a.valid.tolist())], pa.utf8()), a.valid)
+    if a.dtype == "Boolean" and to == "Utf8":  # arrow-cast: "true" / "false"
+        return Vec("Utf8", pa.array([("true" if v else "false") if ok else None for v, ok in zip(a.values.tolist(), a.valid.tolist())], pa.utf8()), a.valid)
     raise OracleError("Unsupported", f"CAST {a.dtype} → {to}")
 
 

@@ -91,8 +91,8 @@ def test_concat_in_select_list(gpu):
         got = SqlProcessor({"query": q}).process(MessageBatch.new_arrow(rb)).batches[0].record_batch
         assert got.schema.names == want.schema.names
         assert got.equals(want), q
-    with pytest.raises(ArkError) as e:
-        SqlProcessor({"query": "SELECT concat(value, 'x') FROM flow"}).process(MessageBatch.new_arrow(rb))
+    with pytest.raises(ArkError) as e:  # Float64 arguments are not rendered on the device (Int64 / Boolean / Utf8 are)
+        SqlProcessor({"query": "SELECT concat(value, 'x') FROM flow"}).process(MessageBatch.new_arrow(synth_batch(100, value_kind=1)))
     assert e.value.kind == "Unsupported"
 
 
@@ -147,3 +147,26 @@ def test_temporary_list_value_key_and_missing_temporary(gpu):
                            Resource(temporary={"kv": store}))
         bad.process(MessageBatch.new_arrow(rb))
     assert e.value.message.startswith("Evaluate expression failed: ")
+
+
+def test_cast_to_string_and_numeric_concat_arguments(gpu):
+    # examples/mqtt_example.yaml: SELECT * ,cast(value as string) as tx FROM flow WHERE value > 10
+    rb = synth_batch(30_000, key_space=40)
+    q = "SELECT * ,cast(value as string) as tx FROM flow WHERE value > 10"
+    want = sql_oracle.sql_process(rb, q)
+    got = SqlProcessor({"query": q}).process(MessageBatch.new_arrow(rb)).batches[0].record_batch
+    assert got.schema.names == want.schema.names == ["timestamp", "value", "sensor", "tx"]
+    assert got.equals(want)
+    mixed = pa.record_batch({"value": pa.array([5, None, -12, 30, -(2**63), 2**63 - 1], pa.int64()),
+                             "flag": pa.array([True, False, None, True, False, None]),
+                             "s": pa.array(["a", "b", None, "d", "", "ünï"])})
+    for q in ("SELECT cast(value as string) AS tx, CAST(flag AS STRING) AS f, value FROM flow",
+              "SELECT concat(s, '#', value, '/', flag) AS c FROM flow",
+              "SELECT concat(value, value) FROM flow WHERE value IS NOT NULL"):
+        want = sql_oracle.sql_process(mixed, q)
+        got = SqlProcessor({"query": q}).process(MessageBatch.new_arrow(mixed)).batches[0].record_batch
+        assert got.schema.names == want.schema.names
+        for name in want.schema.names:
+            assert got.column(name).to_pylist() == want.column(name).to_pylist(), (q, name)
+    cv = evaluate_expr("cast(value as string)", mixed)
+    assert cv.array.to_pylist() == ["5", None, "-12", "30", str(-(2**63)), str(2**63 - 1)]
