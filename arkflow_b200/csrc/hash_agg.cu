@@ -276,8 +276,8 @@ template <int PRED>
 void launch_agg(const AggParams& P, int64_t n, cudaStream_t stream) {
   // One row per thread per iteration.  The kernel keeps its R-rows-per-thread form (all slot loads of a thread
   // issued before any is resolved), but more rows in flight per thread measured slower at 10^6 groups —
-  // R = 1 0.97 ms, R = 2 1.03 ms, R = 4 1.20 ms — the pass is bound by the rate of random DRAM sector
-  // accesses, not by latency hiding.
+  // R = 1 0.62 ms, R = 2 0.65 ms, R = 4 1.05 ms (and 0.97 / 1.03 / 1.20 ms while the kernel still had the hot
+  // group_count atomic).
   KernelTimer t("hash_agg_kernel", stream);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, (int64_t)AGG_THREADS), 148 * 8));
   hash_agg_kernel<PRED, 1><<<grid, AGG_THREADS, 0, stream>>>(P);
