@@ -121,3 +121,21 @@ def test_temporary_list_needs_the_shims_confirmation(lib):
     with pytest.raises(ArkError) as e:
         SqlProcessor({"query": "SELECT * FROM flow", "temporary_list": [{"name": "redis_temporary", "table_name": "redis_table", "key": {"type": "value", "value": "test"}}]})
     assert e.value.kind == "Process" and e.value.message == "Temporary redis_temporary not found"
+
+
+def test_expr_config_and_evaluate_result_host_logic():
+    # expr/mod.rs:30-49, 178-189: the serde-tagged Expr enum and EvaluateResult::get (no device involved)
+    from arkflow_b200.expr import EvaluateResult, Expr
+
+    e = Expr.from_config({"type": "expr", "expr": "concat(name, '!')"})
+    assert e.kind == "Expr" and e.payload == "concat(name, '!')"
+    v = Expr.from_config({"type": "value", "value": "test"})
+    assert v.kind == "Value" and v.evaluate_expr(None).get(7) == "test"
+    for bad in ({}, {"type": "expr"}, {"type": "nope", "value": 1}, "x"):
+        with pytest.raises(ArkError) as err:
+            Expr.from_config(bad)
+        assert err.value.kind == "Serialization"
+    s = EvaluateResult("Scalar", "test")
+    assert s.get(0) == "test" and s.get(1) == "test"
+    vec = EvaluateResult("Vec", ["a", "b"])
+    assert vec.get(0) == "a" and vec.get(1) == "b" and vec.get(2) is None
