@@ -24,6 +24,7 @@ bool timing_get(const char* name, double* ms, int64_t* n);
 void resolve_varlen_extents(Batch& b, const std::vector<int>& col_idx, cudaStream_t stream);
 void resolve_varlen_extents_many(std::vector<Column*>& cols, cudaStream_t stream);
 Batch apply_concats(const Plan& plan, Batch& r, cudaStream_t stream);  // string_funcs.cu
+Column format_int64_column(const Column& src, const std::string& name, cudaStream_t stream);  // string_funcs.cu
 
 // kernels' host launchers
 void launch_filter_project(const FpParams& P, int pred_kind, cudaStream_t stream);

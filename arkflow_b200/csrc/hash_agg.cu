@@ -619,6 +619,7 @@ static Batch project_groups(const Plan& plan, const AggExec& ex, const std::vect
       const bool can_be_null = !is_count && o.count_acc >= 0 && (o.can_be_null || ex.key_kind == KEY_NONE);
       Column col = finalize_column(pi.name, o.type, o.final_op, dense_acc(o.value_acc), cnt, 0, can_be_null, G, stream);
       col.field.nullable = !is_count;
+      if (pi.cast_utf8) col = format_int64_column(col, pi.name, stream);  // CAST(<Int64 aggregate> AS STRING)
       out.cols.push_back(col);
     } else {
       if (pi.lit_type == DType::Utf8) fail(ARK_ERR_UNSUPPORTED, "string literal in an aggregate SELECT list");

@@ -53,6 +53,7 @@ struct PostItem {  // one item of the SELECT list of an aggregate query
   uint64_t lit_bits = 0;
   std::string lit_str;
   std::string name;
+  bool cast_utf8 = false;   // Agg: CAST(<Int64 aggregate> AS STRING), e.g. cast(count(sensor) as string)
 };
 
 // concat(a, b, …) of Utf8 columns and string literals (datafusion-functions' ConcatFunc: NULL arguments

@@ -373,6 +373,9 @@ Plan bind_query(const Query& q, const std::string& table_name, const std::vector
     plan_error("Error during planning: Aggregate functions are not allowed in the WHERE clause");
 
   bind_where(q, b, plan);
+  // ORDER BY is accepted only where it cannot change the result: a global aggregate yields exactly one row
+  // (examples/protobuf_example.yaml orders such a query by one of its aliases)
+  if (!q.order_by.empty() && (!has_agg || !q.group_by.empty())) unsupported("ORDER BY");
 
   if (!has_agg) {
     plan.kind = Plan::FilterProject;
@@ -467,8 +470,13 @@ Plan bind_query(const Query& q, const std::string& table_name, const std::vector
   if (plan.keys.size() > 2) unsupported("more than two GROUP BY keys");
   for (auto& it : q.select) {
     if (it.is_star) plan_error("Error during planning: SELECT * is not valid with GROUP BY / aggregates");
-    const Expr& e = *it.expr;
+    const Expr* ep = it.expr.get();
     PostItem pi;
+    if (ep->kind == Expr::Cast && ep->cast_to == DType::Utf8 && ep->args[0]->kind == Expr::Func && is_aggregate_name(ep->args[0]->name)) {
+      pi.cast_utf8 = true;  // CAST(<aggregate> AS STRING): the aggregate, rendered as decimal text afterwards
+      ep = ep->args[0].get();
+    }
+    const Expr& e = *ep;
     if (e.kind == Expr::Func && is_aggregate_name(e.name)) {
       if (e.distinct) unsupported("aggregate DISTINCT");
       AggSpec a;
@@ -499,6 +507,7 @@ Plan bind_query(const Query& q, const std::string& table_name, const std::vector
       ExprPtr named = e.clone();
       named->name = fn;
       a.name = display(*named, b.table);
+      if (pi.cast_utf8 && a.out_type != DType::Int64) unsupported(std::string("CAST(") + dtype_name(a.out_type) + " aggregate AS STRING)");
       pi.kind = PostItem::Agg; pi.index = (int)plan.aggs.size();
       pi.name = it.alias.empty() ? a.name : it.alias;
       plan.aggs.push_back(a);

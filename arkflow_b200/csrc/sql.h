@@ -69,6 +69,7 @@ struct Query {
   std::vector<JoinClause> joins;
   ExprPtr where;
   std::vector<ExprPtr> group_by;
+  std::vector<ExprPtr> order_by;  // accepted only where it cannot change the result (one-row global aggregates)
   int64_t limit = -1;
 };
 

@@ -139,6 +139,12 @@ std::vector<Token> tokenize(const std::string& s) {
   return out;
 }
 
+bool has_aggregate_call(const Expr& e) {
+  if (e.kind == Expr::Func && (e.name == "sum" || e.name == "count" || e.name == "avg" || e.name == "mean" || e.name == "min" || e.name == "max")) return true;
+  for (auto& a : e.args) if (has_aggregate_call(*a)) return true;
+  return false;
+}
+
 struct Parser {
   std::vector<Token> toks;
   size_t p = 0;
@@ -234,7 +240,14 @@ struct Parser {
       do { q.group_by.push_back(parse_expr()); } while (accept(Tok::Comma));
     }
     if (is_kw("HAVING")) unsupported("HAVING");
-    if (is_kw("ORDER")) unsupported("ORDER BY");
+    if (accept_kw("ORDER")) {
+      expect_kw("BY");
+      do {
+        q.order_by.push_back(parse_expr());
+        if (!accept_kw("ASC")) accept_kw("DESC");
+        if (accept_kw("NULLS")) { if (!accept_kw("FIRST")) expect_kw("LAST"); }
+      } while (accept(Tok::Comma));
+    }
     if (is_kw("UNION") || is_kw("EXCEPT") || is_kw("INTERSECT")) unsupported(cur().upper);
     if (accept_kw("LIMIT")) {
       if (cur().t != Tok::Number) syntax("Expected a number after LIMIT, found: " + describe());
@@ -242,6 +255,12 @@ struct Parser {
       ++p;
     }
     if (is_kw("OFFSET")) unsupported("OFFSET");
+    if (!q.order_by.empty()) {
+      // ORDER BY survives only where it cannot change the result: an aggregate query without GROUP BY has one row
+      bool agg = false;
+      for (auto& it : q.select) if (!it.is_star && has_aggregate_call(*it.expr)) agg = true;
+      if (!agg || !q.group_by.empty()) unsupported("ORDER BY");
+    }
     return q;
   }
 

@@ -107,6 +107,50 @@ __global__ void __launch_bounds__(CONCAT_THREADS) concat_write_kernel(const __gr
 
 }  // namespace
 
+// lengths → scan → bytes for one string column described by P; returns the offsets / bytes of the n_rows strings
+static void render_strings(const ConcatParams& P, int64_t n, cudaStream_t stream, BufferPtr* out_offs, BufferPtr* out_bytes, int32_t* out_total) {
+  BufferPtr lens = device_alloc((size_t)(n + 1) * 4), offs = device_alloc((size_t)(n + 1) * 4);
+  ARK_CUDA(cudaMemsetAsync((int32_t*)lens.get() + n, 0, 4, stream));
+  const unsigned grid = (unsigned)std::max<int64_t>(1, ceil_div(n, 256));
+  if (n) { KernelTimer t("concat_lengths_kernel", stream); concat_lengths_kernel<<<grid, 256, 0, stream>>>(P, (int32_t*)lens.get()); }
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, (int32_t*)lens.get(), (int32_t*)offs.get(), (int)(n + 1), stream);
+  BufferPtr tmp = device_alloc(tb + 16);
+  note_launch("cub::DeviceScan::ExclusiveSum");
+  cub::DeviceScan::ExclusiveSum(tmp.get(), tb, (int32_t*)lens.get(), (int32_t*)offs.get(), (int)(n + 1), stream);
+  BufferPtr h = pinned_alloc(64);
+  ARK_CUDA(cudaMemcpyAsync(h.get(), (int32_t*)offs.get() + n, 4, cudaMemcpyDeviceToHost, stream));
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  const int32_t total = *(const int32_t*)h.get();
+  if (total < 0) fail(ARK_ERR_PROCESS, "Collection query results error: Arrow error: offset overflow, string result exceeds 2 GiB");
+  BufferPtr bytes = device_alloc((size_t)total + 16);
+  if (n) {
+    const int stage = (int)std::min<int64_t>(44 * 1024, round_up((int64_t)((double)total / (double)n * CONCAT_THREADS * 1.5) + 256, 1024));
+    KernelTimer t("concat_write_kernel", stream);
+    concat_write_kernel<<<grid, CONCAT_THREADS, stage, stream>>>(P, (const int32_t*)offs.get(), (uint8_t*)bytes.get(), stage);
+  }
+  ARK_CUDA(cudaGetLastError());
+  *out_offs = offs; *out_bytes = bytes; *out_total = total;
+}
+
+// CAST(<Int64 column> AS STRING) of an already materialised column (aggregate results): decimal text, NULL stays NULL
+Column format_int64_column(const Column& src, const std::string& name, cudaStream_t stream) {
+  ConcatParams P;
+  memset(&P, 0, sizeof P);
+  P.n_parts = 1; P.n_rows = src.length;
+  P.parts[0].data = src.data; P.parts[0].validity = src.validity; P.parts[0].validity_bit0 = (int32_t)src.validity_bit0; P.parts[0].kind = PART_INT64;
+  BufferPtr offs, bytes;
+  int32_t total = 0;
+  render_strings(P, src.length, stream, &offs, &bytes, &total);
+  Column c;
+  c.field.name = name; c.field.type = DType::Utf8; c.field.nullable = src.field.nullable; c.length = src.length;
+  c.offsets = (const int32_t*)offs.get(); c.data = (const uint8_t*)bytes.get(); c.data_bytes = total; c.first_offset = 0;
+  c.validity = src.validity; c.validity_bit0 = src.validity_bit0; c.null_count = src.null_count;
+  c.owners = {offs, bytes};
+  for (auto& o : src.owners) c.owners.push_back(o);
+  return c;
+}
+
 // Builds the result of a FilterProject plan that holds concat() items: `r` carries plan.outputs (visible
 // columns first, hidden concat sources after them).
 Batch apply_concats(const Plan& plan, Batch& r, cudaStream_t stream) {
@@ -139,27 +183,9 @@ Batch apply_concats(const Plan& plan, Batch& r, cudaStream_t stream) {
       }
     }
     if (lit_bytes) ARK_CUDA(cudaMemcpyAsync(lit_dev.get(), lit_host.get(), lit_bytes, cudaMemcpyHostToDevice, stream));
-    BufferPtr lens = device_alloc((size_t)(n + 1) * 4), offs = device_alloc((size_t)(n + 1) * 4);
-    ARK_CUDA(cudaMemsetAsync((int32_t*)lens.get() + n, 0, 4, stream));
-    const unsigned grid = (unsigned)std::max<int64_t>(1, ceil_div(n, 256));
-    if (n) { KernelTimer t("concat_lengths_kernel", stream); concat_lengths_kernel<<<grid, 256, 0, stream>>>(P, (int32_t*)lens.get()); }
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, (int32_t*)lens.get(), (int32_t*)offs.get(), (int)(n + 1), stream);
-    BufferPtr tmp = device_alloc(tb + 16);
-    note_launch("cub::DeviceScan::ExclusiveSum");
-    cub::DeviceScan::ExclusiveSum(tmp.get(), tb, (int32_t*)lens.get(), (int32_t*)offs.get(), (int)(n + 1), stream);
-    BufferPtr h = pinned_alloc(64);
-    ARK_CUDA(cudaMemcpyAsync(h.get(), (int32_t*)offs.get() + n, 4, cudaMemcpyDeviceToHost, stream));
-    ARK_CUDA(cudaStreamSynchronize(stream));
-    const int32_t total = *(const int32_t*)h.get();
-    if (total < 0) fail(ARK_ERR_PROCESS, "Collection query results error: Arrow error: offset overflow, concat() result exceeds 2 GiB");
-    BufferPtr bytes = device_alloc((size_t)total + 16);
-    if (n) {
-      const int stage = (int)std::min<int64_t>(44 * 1024, round_up((int64_t)((double)total / (double)n * CONCAT_THREADS * 1.5) + 256, 1024));
-      KernelTimer t("concat_write_kernel", stream);
-      concat_write_kernel<<<grid, CONCAT_THREADS, stage, stream>>>(P, (const int32_t*)offs.get(), (uint8_t*)bytes.get(), stage);
-    }
-    ARK_CUDA(cudaGetLastError());
+    BufferPtr offs, bytes;
+    int32_t total = 0;
+    render_strings(P, n, stream, &offs, &bytes, &total);
     ARK_CUDA(cudaStreamSynchronize(stream));  // the literal staging blocks go back to the pool
     Column& c = made[ci];
     c.field.name = item.name; c.field.type = DType::Utf8; c.field.nullable = true; c.length = n;

@@ -203,7 +203,21 @@ class _Parser:
             group_by.append(self.expr())
             while self.accept_op(","):
                 group_by.append(self.expr())
-        for w in ("HAVING", "ORDER", "UNION", "OFFSET"):
+        if self.kw("HAVING"):
+            raise OracleError("Unsupported", "HAVING")
+        order_by = []
+        if self.accept_kw("ORDER"):
+            if not self.accept_kw("BY"):
+                self.err("BY")
+            while True:
+                order_by.append(self.expr())
+                if not self.accept_kw("ASC"):
+                    self.accept_kw("DESC")
+                if self.accept_kw("NULLS") and not (self.accept_kw("FIRST") or self.accept_kw("LAST")):
+                    self.err("FIRST or LAST")
+                if not self.accept_op(","):
+                    break
+        for w in ("UNION", "OFFSET"):
             if self.kw(w):
                 raise OracleError("Unsupported", w)
         limit = -1
@@ -216,6 +230,9 @@ class _Parser:
             pass
         if self.cur().kind != "end":
             self.err("end of statement")
+        if order_by and (group_by or not any((not it.star) and _has_agg(it.expr) for it in sel)):
+            # ORDER BY survives only where it cannot change the result: an aggregate query without GROUP BY has one row
+            raise OracleError("Unsupported", "ORDER BY")
         return Query(sel, table, alias, joins, where, group_by, limit)
 
     def table_ref(self):
@@ -851,6 +868,19 @@ def sql_process(rb: pa.RecordBatch, query: str, table_name: str = "flow") -> Opt
         if it.star:
             raise OracleError("Process", "Execution query error: Error during planning: SELECT * with GROUP BY")
         e = it.expr
+        cast_str = e.kind == "cast" and e.to == "Utf8" and e.args[0].kind == "func" and e.args[0].name in _AGG
+        if cast_str:
+            e = e.args[0]
+
+        def _finish():
+            if cast_str:  # CAST(<Int64 aggregate> AS STRING): arrow-cast's decimal text, NULL stays NULL
+                if cols[-1].type != pa.int64():
+                    raise OracleError("Unsupported", f"CAST({cols[-1].type} aggregate AS STRING)")
+                import pyarrow.compute as pc
+
+                cols[-1] = pc.cast(cols[-1], pa.utf8())
+                fields[-1] = pa.field(fields[-1].name, pa.utf8(), fields[-1].nullable)
+
         if e.kind == "func" and e.name in _AGG:
             fn = "avg" if e.name == "mean" else e.name
             name = it.alias or display(E("func", name=fn, args=e.args, star=e.star), vis)
@@ -859,6 +889,7 @@ def sql_process(rb: pa.RecordBatch, query: str, table_name: str = "flow") -> Opt
                 cnt = np.bincount(inv, minlength=k).astype(np.int64)
                 cols.append(pa.array(cnt, type=pa.int64()))
                 fields.append(pa.field(name, pa.int64(), False))
+                _finish()
                 continue
             if len(e.args) != 1 or e.star:
                 raise OracleError("Process", f"Execution query error: Error during planning: {fn} expects one argument")
@@ -869,6 +900,7 @@ def sql_process(rb: pa.RecordBatch, query: str, table_name: str = "flow") -> Opt
                 cnt = np.bincount(inv[v.valid], minlength=k).astype(np.int64)
                 cols.append(pa.array(cnt, type=pa.int64()))
                 fields.append(pa.field(name, pa.int64(), False))
+                _finish()
                 continue
             if v.dtype not in ("Int64", "Float64"):
                 if fn in ("min", "max"):
@@ -925,6 +957,7 @@ def sql_process(rb: pa.RecordBatch, query: str, table_name: str = "flow") -> Opt
             fields.append(pa.field(it.alias or display(e, vis), t, False))
         else:
             raise OracleError("Unsupported", "expression in aggregate SELECT list")
+        _finish()
     return pa.RecordBatch.from_arrays(cols, schema=pa.schema(fields))
 
 

@@ -277,3 +277,26 @@ def test_radix_path_skewed_keys_fall_back(radix_mode):
     radix_mode.ark_kernel_timing_reset()
     check_agg_sorted(rb, q, "sensor")
     assert _launches(radix_mode, "agg_radix_partition_kernel") >= 1 and _launches(radix_mode, "hash_agg_kernel") >= 1
+
+
+def test_protobuf_example_query_cast_of_aggregate_and_order_by(gpu):
+    # examples/protobuf_example.yaml: a global aggregate with CAST(count(..) AS STRING) and an ORDER BY over its one row
+    rb = synth_batch(50_000, key_space=11)
+    q = ("SELECT count(timestamp) as timestamp, sum(value) as value, cast(count(sensor) as string) as  sensor "
+         "FROM flow WHERE value >= 10 order by sensor")
+    want = sql_process(rb, q)
+    for device in (False, True):
+        got = run(rb, q, device=device)
+        assert got.schema.names == want.schema.names == ["timestamp", "value", "sensor"]
+        assert [f.type for f in got.schema] == [pa.int64(), pa.int64(), pa.utf8()]
+        assert got.to_pydict() == want.to_pydict()
+    check_agg(rb, "SELECT sensor, cast(count(*) as string) AS c, cast(sum(value) as string), cast(min(value) as string) AS lo FROM flow GROUP BY sensor", ["sensor"])
+    nulls = pa.record_batch({"k": pa.array(["a", "a", "b"]), "v": pa.array([None, None, 4], pa.int64())})
+    out = check_agg(nulls, "SELECT k, cast(sum(v) as string) AS s, cast(count(v) as string) AS c FROM flow GROUP BY k", ["k"])
+    assert sorted(zip(out.column("k").to_pylist(), out.column("s").to_pylist(), out.column("c").to_pylist())) == [("a", None, "0"), ("b", "4", "1")]
+    with pytest.raises(ArkError) as e:
+        SqlProcessor({"query": "SELECT sensor, count(*) FROM flow GROUP BY sensor ORDER BY sensor"})
+    assert e.value.kind == "Unsupported"
+    with pytest.raises(ArkError) as e:
+        run(rb, "SELECT cast(avg(value) as string) FROM flow")
+    assert e.value.kind == "Unsupported"
