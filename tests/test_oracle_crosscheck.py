@@ -72,3 +72,25 @@ def test_inner_join_matches_acero():
     want = pa.Table.from_batches([left]).join(pa.Table.from_batches([right]), keys="k", join_type="inner").select(["k", "v", "z"])
     key = lambda tbl: sorted(map(repr, zip(*[tbl.column(i).to_pylist() for i in range(3)])))
     assert key(got) == key(want)  # NULL keys never match, on either side
+
+
+def test_json_decode_matches_arrow_json_reader():
+    # uniform scalar records: arrow-json (first-record inference) and Arrow C++'s reader must decode the same values
+    import io
+    import json
+
+    import pyarrow.json as pj
+
+    from arkflow_b200.processor import MessageBatch
+    from oracle.json_oracle import json_to_arrow
+
+    rng = np.random.default_rng(5)
+    NOTE = 'caf\u00e9 "q" \\ \n'  # non-ASCII, a quote, a backslash, a newline: all escaped by json.dumps
+    recs = [{"timestamp": int(1625000000000 + i), "value": int(rng.integers(-10**12, 10**12)), "x": float(rng.normal() * 10.0 ** int(rng.integers(-8, 9))),
+             "flag": bool(i % 3 == 0), "sensor": f"temp_{int(rng.integers(0, 50))}", "note": NOTE if i % 7 == 0 else "plain"} for i in range(500)]
+    payloads = [json.dumps(r).encode() for r in recs]
+    got = json_to_arrow(MessageBatch.new_binary(payloads).record_batch)
+    want = pj.read_json(io.BytesIO(b"\n".join(payloads)))
+    assert got.schema.names == want.schema.names
+    for name in want.schema.names:
+        assert got.column(name).to_pylist() == want[name].to_pylist(), name
