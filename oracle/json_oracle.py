@@ -24,6 +24,11 @@ import pyarrow as pa
 
 from .sql_oracle import OracleError
 
+# Nested values (List / Struct columns).  The library does not decode them yet, so the default
+# mirrors it and reports Unsupported; NESTED = True is the restatement of arrow-json's behaviour the next round's
+# kernels will be checked against (tests/test_oracle_golden.py pins it to processor/json.rs:170-207).
+NESTED = False
+
 _NUM_RE = re.compile(rb"^[+-]?(\d+)(\.\d+)?([eE][+-]?\d+)?$|^[+-]?\.\d+([eE][+-]?\d+)?$")
 _INT_RE = re.compile(rb"^[+-]?\d+$")
 
@@ -67,6 +72,28 @@ def _infer_type(v) -> pa.DataType:
         return pa.float64()
     if isinstance(v, str):
         return pa.utf8()
+    if NESTED and isinstance(v, list):
+        # arrow-json infer_json_schema: the element type is the coercion of the elements' types
+        # (Int64 + Float64 → Float64, anything + Null → that thing, an empty array → List<Null>)
+        t = pa.null()
+        for x in v:
+            xt = _infer_type(x)
+            if t == pa.null():
+                t = xt
+            elif xt == pa.null() or xt == t:
+                pass
+            elif {t, xt} == {pa.int64(), pa.float64()}:
+                t = pa.float64()
+            else:
+                raise OracleError("Unsupported", "JSON array of mixed types")
+        return pa.list_(pa.field("item", t, True))
+    if NESTED and isinstance(v, tuple) and v[0] == "obj":
+        fields, seen = [], set()
+        for k, x in v[1]:
+            if k not in seen:
+                seen.add(k)
+                fields.append(pa.field(k, _infer_type(x), True))
+        return pa.struct(fields)
     raise OracleError("Unsupported", "nested JSON value (List/Struct column)")
 
 
@@ -117,6 +144,38 @@ def json_to_arrow(rb: pa.RecordBatch, value_field: str = "__value__", fields_to_
         if fields_to_include is not None and k not in fields_to_include:
             continue
         fields.append((k, _infer_type(v)))
+    def convert(x, t):
+        if x is None:
+            return None
+        if t == pa.int64() or t == pa.float64():
+            if isinstance(x, _Num):
+                text = x.text.encode()
+            elif isinstance(x, str):
+                text = x.encode()
+            else:
+                raise OracleError("Process", "Arrow JSON Reader Error: Json error: expected a number")
+            return _to_i64(text) if t == pa.int64() else _to_f64(text)
+        if t == pa.bool_():
+            if not isinstance(x, bool):
+                raise OracleError("Process", "Arrow JSON Reader Error: Json error: expected a boolean")
+            return x
+        if t == pa.utf8():
+            if not isinstance(x, str):
+                raise OracleError("Process", "Arrow JSON Reader Error: Json error: expected a string")
+            return x
+        if pa.types.is_list(t):
+            if not isinstance(x, list):
+                raise OracleError("Process", "Arrow JSON Reader Error: Json error: expected an array")
+            return [convert(e, t.value_type) for e in x]
+        if pa.types.is_struct(t):
+            if not (isinstance(x, tuple) and x[0] == "obj"):
+                raise OracleError("Process", "Arrow JSON Reader Error: Json error: expected an object")
+            rec = {}
+            for k, e in x[1]:
+                rec[k] = e
+            return {f.name: convert(rec.get(f.name), f.type) for f in t}
+        raise OracleError("Process", "Arrow JSON Reader Error: Json error: expected null")
+
     cols = {k: [] for k, _ in fields}
     for v in values:
         if not (isinstance(v, tuple) and v[0] == "obj"):
@@ -128,6 +187,8 @@ def json_to_arrow(rb: pa.RecordBatch, value_field: str = "__value__", fields_to_
             x = rec.get(k)
             if x is None:
                 cols[k].append(None)
+            elif pa.types.is_list(t) or pa.types.is_struct(t):
+                cols[k].append(convert(x, t))
             elif t == pa.int64() or t == pa.float64():
                 if isinstance(x, _Num):
                     text = x.text.encode()

@@ -76,3 +76,28 @@ def test_oracle_batch_and_sliding_window_pins():
     w = sliding_windows(three, 3, 2)
     assert len(w) == 1 and w[0].column(0).to_pylist() == [b"msg0", b"msg1", b"msg2"]
     assert sliding_windows(three[:2], 3, 1) == []
+
+
+def test_oracle_nested_json_pin(monkeypatch):
+    # processor/json.rs:170-207 (test_json_to_arrow_basic_types): the record also holds an array and an object field and
+    # decodes to ONE row.  The library does not decode nested values yet; the oracle's NESTED
+    # mode is the restatement the next kernels will be checked against, pinned here to the reference's assertion.
+    import json
+
+    import pyarrow as pa
+
+    import oracle.json_oracle as J
+    from arkflow_b200.processor import MessageBatch
+
+    rec = {"null_field": None, "bool_field": True, "int_field": 42, "uint_field": 18446744073709551615, "float_field": 3.14,
+           "string_field": "hello", "array_field": [1, 2, 3], "object_field": {"key": "value"}}
+    mb = MessageBatch.new_binary([json.dumps(rec).encode()]).record_batch
+    with pytest.raises(OracleError) as e:
+        J.json_to_arrow(mb)
+    assert e.value.kind == "Unsupported"  # what the library reports today
+    monkeypatch.setattr(J, "NESTED", True)
+    out = J.json_to_arrow(mb)
+    assert out.num_rows == 1  # the reference's assertion
+    assert out.schema.field("array_field").type == pa.list_(pa.field("item", pa.int64(), True))
+    assert out.schema.field("object_field").type == pa.struct([pa.field("key", pa.utf8(), True)])
+    assert out.column("array_field").to_pylist() == [[1, 2, 3]] and out.column("object_field").to_pylist() == [{"key": "value"}]
