@@ -57,6 +57,7 @@ struct TmaParams {
   unsigned long long* desc;
   unsigned int* ticket;
   long long* totals;
+  int32_t debug;                            // measurement knob (ARK_FP_DEBUG): bit 0 = skip the look-back (results are garbage)
 };
 
 constexpr unsigned long long DESC_AGG = 1ull << 62;
@@ -361,6 +362,229 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? ARK_FP_MINBLOCKS : 3
   }
 }
 
+// ================================================================================================
+// filter_project_pipe_kernel — the same tile algorithm as a PERSISTENT, software-pipelined kernel.
+//
+// filter_project_tma_kernel above runs one tile per CTA: loads → predicate → look-back → stores, so a CTA's
+// loads are in flight for only ~a quarter of its life (ncu r1f: 28 % of warp time parked at the look-back
+// barrier, 21 % waiting for the tile's loads, DRAM 48 % busy) and forward progress relied on CTAs being
+// dispatched in blockIdx order.  Here a CTA stays resident and claims tiles from a TICKET (a tile is only
+// ever owned by a running CTA, so the look-back cannot wait on a CTA that was never scheduled), and the loads
+// of the NEXT tile — predicate column and offsets into registers, the string window by TMA into the other
+// half of a two-stage ring — are issued before the current tile is evaluated.  A tile's aggregate is
+// therefore published a few hundred cycles after its iteration starts (its data is already on chip), which
+// is what keeps the look-back of its successors short.
+// Producer duties (ticket two tiles ahead, the tile's two bounding offsets one tile ahead, then the bulk
+// copy) belong to one thread of the LAST warp, so that warp 0 keeps only the look-back.
+// ================================================================================================
+
+template <bool VARLEN>
+__device__ __forceinline__ void load_rows_raw(const TmaParams& P, int64_t row0, int rows, int lr0, int lane, unsigned long long pv[4], int off[4],
+                                              int* offx) {
+  const bool full = lr0 + 4 <= rows;
+  const unsigned long long* src = P.pred_in + row0 + lr0;
+  if (full && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(pv[0]), "=l"(pv[1]) : "l"(src));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(pv[2]), "=l"(pv[3]) : "l"(src + 2));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pv[j] = (lr0 + j < rows) ? src[j] : 0;
+  }
+  if (VARLEN) {
+    const int32_t* os = P.offsets_in + row0 + lr0;
+    if (full && (reinterpret_cast<uintptr_t>(os) & 15) == 0) {
+      asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(off[0]), "=r"(off[1]), "=r"(off[2]), "=r"(off[3]) : "l"(os));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) off[j] = (lr0 + j <= rows) ? os[j] : 0;
+    }
+    *offx = ((lane == 31 || lr0 + 4 >= rows) && lr0 + 4 <= rows) ? os[4] : 0;
+  }
+}
+
+template <int NF, bool VARLEN, int MINB>
+__global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __grid_constant__ TmaParams P) {
+  constexpr int T_THREADS = 256, TT = T_THREADS * 4, T_WARPS = T_THREADS / 32;
+  constexpr int PRODUCER = T_THREADS - 32;  // lane 0 of the last warp
+  extern __shared__ __align__(16) uint8_t smem[];   // [in_bytes stage 0][in_bytes stage 1][out_bytes], each str_cap + 32
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  __shared__ int s_tile[4];
+  __shared__ int s_str_base[2], s_str_staged[2];
+  __shared__ int s_cnt[T_WARPS], s_bytes[T_WARPS];
+  __shared__ long long s_excl[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int stage_bytes = P.str_cap + 32;
+  uint8_t* const out_bytes = smem + 2 * stage_bytes;
+  const int n_tiles = P.n_tiles;
+  const int lr0 = 4 * tid;
+  auto tile_rows = [&](int t) { const int64_t r = P.n_rows - (int64_t)t * TT; return (int)(r < TT ? r : TT); };
+  // producer: arm stage `st` for tile t whose bounding offsets are o0, o1
+  auto issue_window = [&](int st, int32_t o0, int32_t o1) {
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(P.data_in + o0), a1 = reinterpret_cast<uintptr_t>(P.data_in + o1);
+    const uintptr_t lo = a0 & ~(uintptr_t)15, hi = (a1 + 15) & ~(uintptr_t)15;
+    int staged = 0;
+    if (o1 > o0 && hi - lo <= (uintptr_t)P.str_cap) {  // staged ⇒ selected bytes ≤ window ≤ str_cap
+      staged = 1;
+      mbar_expect_tx(&s_bar[st], (unsigned)(hi - lo));
+      tma_load_1d(smem + st * stage_bytes, reinterpret_cast<const void*>(lo), (unsigned)(hi - lo), &s_bar[st]);
+    }
+    s_str_base[st] = o0 - (int32_t)(a0 - lo); s_str_staged[st] = staged;
+  };
+
+  // ---- prologue: tickets for the first three tiles of this CTA (same thread, same address ⇒ increasing) ----
+  unsigned tk_next = 0;
+  int32_t bo0 = 0, bo1 = 0;  // bounding offsets of the NEXT tile (consumed when its bulk copy is issued)
+  if (tid == PRODUCER) {
+    if (VARLEN) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+    const unsigned t0 = atomicAdd(P.ticket, 1u);
+    const unsigned t1 = atomicAdd(P.ticket, 1u);
+    tk_next = atomicAdd(P.ticket, 1u);
+    s_tile[0] = (int)min(t0, (unsigned)n_tiles); s_tile[1] = (int)min(t1, (unsigned)n_tiles);
+    if (VARLEN) {
+      if ((int)t0 < n_tiles) { const int64_t r0 = (int64_t)t0 * TT; issue_window(0, P.offsets_in[r0], P.offsets_in[r0 + tile_rows((int)t0)]); }
+      if ((int)t1 < n_tiles) { const int64_t r1 = (int64_t)t1 * TT; bo0 = P.offsets_in[r1]; bo1 = P.offsets_in[r1 + tile_rows((int)t1)]; }
+    }
+  }
+  __syncthreads();
+  int tile = s_tile[0];
+  unsigned long long pvn[4] = {0, 0, 0, 0};
+  int offn[4] = {0, 0, 0, 0}, offxn = 0;
+  if (tile < n_tiles) load_rows_raw<VARLEN>(P, (int64_t)tile * TT, tile_rows(tile), lr0, lane, pvn, offn, &offxn);
+  unsigned ph = 0;  // bit s: parity to wait for on stage s (flips only when a bulk copy was issued for it)
+
+  for (int it = 0; tile < n_tiles; ++it) {
+    const int st = it & 1;
+    const int64_t row0 = (int64_t)tile * TT;
+    const int rows = tile_rows(tile);
+    uint8_t* const in_bytes = smem + st * stage_bytes;
+    // this tile's registers (loaded one iteration ago)
+    unsigned long long pv[4] = {pvn[0], pvn[1], pvn[2], pvn[3]};
+    int off[5] = {offn[0], offn[1], offn[2], offn[3], 0};
+    const int offx = offxn;
+    // ---- A: everything the NEXT tile needs is put in flight now ----
+    const int next = s_tile[(it + 1) & 3];
+    if (tid == PRODUCER) {
+      if (VARLEN && next < n_tiles) issue_window(st ^ 1, bo0, bo1);
+      const int next2 = (int)min(tk_next, (unsigned)n_tiles);
+      s_tile[(it + 2) & 3] = next2;
+      if (VARLEN && next2 < n_tiles) { const int64_t r2 = (int64_t)next2 * TT; bo0 = P.offsets_in[r2]; bo1 = P.offsets_in[r2 + tile_rows(next2)]; }
+      if (next2 < n_tiles) tk_next = atomicAdd(P.ticket, 1u);
+    }
+    if (next < n_tiles) load_rows_raw<VARLEN>(P, (int64_t)next * TT, tile_rows(next), lr0, lane, pvn, offn, &offxn);
+    // ---- B: predicate, thread-local and warp-level prefix sums ----
+    if (VARLEN) {
+      off[4] = __shfl_down_sync(0xffffffffu, off[0], 1);
+      if ((lane == 31 || lr0 + 4 >= rows) && lr0 + 4 <= rows) off[4] = offx;
+    }
+    int cnt, sel_bytes;
+    const unsigned flags = eval_rows<VARLEN>(P, rows, lr0, pv, off, &cnt, &sel_bytes);
+    const int cnt_incl = warp_incl_scan(cnt, lane);
+    int bytes_incl = 0;
+    if (VARLEN) bytes_incl = warp_incl_scan(sel_bytes, lane);
+    if (lane == 31) { s_cnt[warp] = cnt_incl; if (VARLEN) s_bytes[warp] = bytes_incl; }
+    __syncthreads();   // (1)
+
+    // ---- D: tile scan over the per-warp totals (every warp, redundantly); publish the tile aggregate at once ----
+    int w_cnt_excl, w_bytes_excl = 0, tile_cnt, tb = 0;
+    {
+      const int c = lane < T_WARPS ? s_cnt[lane] : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < T_WARPS; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      w_cnt_excl = __shfl_sync(0xffffffffu, incl - c, warp);
+      tile_cnt = __shfl_sync(0xffffffffu, incl, T_WARPS - 1);
+      if (VARLEN) {
+        const int b = lane < T_WARPS ? s_bytes[lane] : 0;
+        int bi = b;
+#pragma unroll
+        for (int o = 1; o < T_WARPS; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, bi, o); if (lane >= o) bi += t; }
+        w_bytes_excl = __shfl_sync(0xffffffffu, bi - b, warp);
+        tb = __shfl_sync(0xffffffffu, bi, T_WARPS - 1);
+      }
+    }
+    if (warp == 0 && lane == 0) st_volatile_u64(P.desc + (size_t)tile * P.desc_stride, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
+    // ---- F: decoupled look-back (warp 0) runs while the other warps compact the strings ----
+    if (warp == 0) {
+      long long ex0, ex1;
+      if (P.debug & 1) { ex0 = (long long)tile * (TT / 2); ex1 = ex0 * 12; }
+      else lookback_resolve(P.desc, P.desc_stride, tile, tile_cnt, tb, lane, &ex0, &ex1);
+      if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
+    }
+    // ---- E: compact the strings in shared memory at tile-local positions ----
+    const int my_cnt_excl = w_cnt_excl + cnt_incl - cnt;
+    int lpos[4];
+    bool str_fast = false;
+    if (VARLEN) {
+      int run = w_bytes_excl + bytes_incl - sel_bytes;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { lpos[j] = run; if ((flags >> j) & 1) run += off[j + 1] - off[j]; }
+      str_fast = s_str_staged[st];
+      if (str_fast) {
+        mbar_wait(&s_bar[st], (ph >> st) & 1);  // this tile's window (issued one iteration ago)
+        ph ^= 1u << st;
+        const int base = s_str_base[st];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if ((flags >> j) & 1) smem_copy(out_bytes + lpos[j], in_bytes + (off[j] - base), off[j + 1] - off[j]);
+      }
+    }
+    __syncthreads();   // (2)
+    const long long base_cnt = s_excl[0];
+    const long long bb = VARLEN ? s_excl[1] : 0;
+    if (tile == n_tiles - 1 && tid == 0) { P.totals[0] = base_cnt + tile_cnt; P.totals[1] = bb + tb; }
+
+    // ---- G: stores ----
+    {
+      long long pos = base_cnt + my_cnt_excl;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!((flags >> j) & 1)) continue;
+#pragma unroll
+        for (int c = 0; c < NF; ++c)
+          P.fixed_out[c][pos] = ((P.fixed_is_pred >> c) & 1) ? pv[j] : ld_stream_u64(P.fixed_in[c] + row0 + lr0 + j);
+        if (VARLEN) P.offsets_out[pos] = (int32_t)(bb + lpos[j]);
+        ++pos;
+      }
+    }
+    if (VARLEN) {
+      if (tile == n_tiles - 1 && tid == 0) P.offsets_out[base_cnt + tile_cnt] = (int32_t)(bb + tb);
+      if (str_fast) {
+        // destination-aligned 16-byte stores; the shared-memory source is misaligned by d = (-bb) mod 16
+        uint8_t* gdst = P.data_out + bb;
+        const int head = (int)((16 - (bb & 15)) & 15) < tb ? (int)((16 - (bb & 15)) & 15) : tb;
+        if (tid < head) gdst[tid] = out_bytes[tid];
+        const int body = (tb - head) >> 4;
+        const unsigned* sw = reinterpret_cast<const unsigned*>(out_bytes + (head & ~3));
+        const unsigned sh = (head & 3) * 8;
+        for (int g = tid; g < body; g += T_THREADS) {
+          const unsigned* w = sw + g * 4;
+          uint4 v;
+          if (sh == 0) { v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3]; }
+          else {
+            const unsigned a = w[0], b = w[1], c = w[2], d = w[3], e = w[4];
+            v.x = __funnelshift_r(a, b, sh); v.y = __funnelshift_r(b, c, sh); v.z = __funnelshift_r(c, d, sh); v.w = __funnelshift_r(d, e, sh);
+          }
+          *reinterpret_cast<uint4*>(gdst + head + g * 16) = v;
+        }
+        const int done = head + body * 16;
+        if (tid < tb - done) gdst[done + tid] = out_bytes[done + tid];
+      } else {  // long strings: straight from global to global
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!((flags >> j) & 1)) continue;
+          const uint8_t* src = P.data_in + off[j];
+          uint8_t* dst = P.data_out + bb + lpos[j];
+          for (int i = 0; i < off[j + 1] - off[j]; ++i) dst[i] = src[i];
+        }
+      }
+    }
+    tile = next;
+    // out_bytes / s_cnt / s_excl are next written after barrier (1) resp. (2) of the following iteration — every
+    // thread has finished this iteration's reads before it arrives there.
+  }
+}
+
 }  // namespace
 
 static std::atomic<double> g_avg_len_hint{12.8};
@@ -376,7 +600,6 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
                                const int32_t* offsets_in, const uint8_t* data_in, int64_t data_bytes, int32_t* offsets_out, uint8_t* data_out,
                                int cmp, int is_f64, uint64_t constant, unsigned long long* desc, unsigned int* ticket, long long* totals,
                                cudaStream_t stream) {
-  (void)ticket;
   if (reinterpret_cast<uintptr_t>(pred_in) & 7) return false;
   if (n_rows >= (1ll << 31) - 1) return false;  // 31-bit descriptor fields
   if (data_out && (reinterpret_cast<uintptr_t>(data_out) & 15)) return false;
@@ -407,7 +630,9 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
     if (fixed_in[c] == pred_in) P.fixed_is_pred |= 1u << c;
   }
   P.offsets_in = offsets_in; P.data_in = data_in; P.offsets_out = offsets_out; P.data_out = data_out;
-  P.desc = desc; P.ticket = nullptr; P.totals = totals;
+  P.desc = desc; P.ticket = ticket; P.totals = totals;
+  static const int debug = [] { const char* e = getenv("ARK_FP_DEBUG"); return e ? atoi(e) : 0; }();
+  P.debug = debug;
   // string staging sized from the batch's average string length (+25 %), 2 KB granules, 4..24 KB
   int cap = 0;
   if (P.has_varlen) {
@@ -419,6 +644,46 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
   }
   P.str_cap = cap;
   P.desc_stride = g_desc_stride;
+  const bool v = P.has_varlen;
+  // implementation: 0 = persistent pipelined kernel (default), 1 = one tile per CTA (the r1 kernel, kept for A/B runs)
+  static const int impl = [] { const char* e = getenv("ARK_FP_IMPL"); return e ? atoi(e) : 0; }();
+  if (impl == 0 && g_fp_threads == 256 && ticket != nullptr) {
+    const size_t smem = v ? 3 * (size_t)(cap + 32) : 0;
+    static int occ[2][3] = {{0, 0, 0}, {0, 0, 0}};   // CTAs per SM by (varlen, n_fixed) at the largest staging size seen
+    static size_t occ_smem[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    static bool configured = false;
+    const int max_smem = 3 * (48 * 1024 + 32);
+    // CTAs per SM the kernel is compiled for: 5 (48 registers, a few spilled words) or 4 (64 registers)
+    static const int minb = [] { const char* e = getenv("ARK_FP_MINB"); return e && atoi(e) == 4 ? 4 : 5; }();
+#define ARK_PIPE_FN(NF, V) (minb == 4 ? (const void*)filter_project_pipe_kernel<NF, V, 4> : (const void*)filter_project_pipe_kernel<NF, V, 5>)
+    if (!configured) {
+      for (const void* f : {ARK_PIPE_FN(0, true), ARK_PIPE_FN(1, true), ARK_PIPE_FN(2, true)})
+        ARK_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      configured = true;
+    }
+    const void* fn = nullptr;
+    if (n_fixed_out == 0 && v) fn = ARK_PIPE_FN(0, true);
+    else if (n_fixed_out == 1 && v) fn = ARK_PIPE_FN(1, true);
+    else if (n_fixed_out == 2 && v) fn = ARK_PIPE_FN(2, true);
+    else if (n_fixed_out == 1) fn = ARK_PIPE_FN(1, false);
+    else if (n_fixed_out == 2) fn = ARK_PIPE_FN(2, false);
+    else return false;
+#undef ARK_PIPE_FN
+    int& o = occ[v ? 1 : 0][n_fixed_out];
+    if (o == 0 || occ_smem[v ? 1 : 0][n_fixed_out] != smem) {
+      ARK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, 256, smem));
+      occ_smem[v ? 1 : 0][n_fixed_out] = smem;
+      if (o < 1) o = 1;
+    }
+    static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+    static const int cap_per_sm = [] { const char* e = getenv("ARK_FP_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    const int per_sm = cap_per_sm > 0 ? std::min(cap_per_sm, o) : o;
+    const int grid = std::max(1, std::min(P.n_tiles, sms * per_sm));
+    KernelTimer t("filter_project_tma_kernel", stream);
+    void* args[] = {(void*)&P};
+    ARK_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(256), args, smem, stream));
+    return true;
+  }
   const size_t smem = P.has_varlen ? 2 * (size_t)(cap + 32) : 0;
   const int max_smem = 2 * (48 * 1024 + 32);
   static bool configured = false;
@@ -432,7 +697,6 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
     configured = true;
   }
   KernelTimer t("filter_project_tma_kernel", stream);
-  const bool v = P.has_varlen;
 #define ARK_TMA_LAUNCH(NF, V, TH) filter_project_tma_kernel<NF, V, TH><<<P.n_tiles, TH, (V) ? smem : 0, stream>>>(P)
   if (g_fp_threads == 256) {
     if (n_fixed_out == 0 && v) ARK_TMA_LAUNCH(0, true, 256);

@@ -328,6 +328,7 @@ struct DenseGroups {  // result of the hash pass: dense arrays of G groups, part
 };
 
 bool launch_hash_agg_tile(const AggParams& P, unsigned long long capacity, unsigned int groups_hint, int64_t key_bytes, cudaStream_t stream);
+bool launch_hash_agg_stream(const AggParams& P, unsigned long long capacity, int64_t key_bytes, cudaStream_t stream);
 bool launch_hash_agg_radix(const AggParams& P, unsigned long long capacity, int32_t* skew_dev, std::vector<BufferPtr>* keep, cudaStream_t stream);
 void hash_agg_radix_note_skew();
 
@@ -382,12 +383,24 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     // (A persisting L2 access-policy window on the table was tried: no gain for this kernel — 0.974 vs 0.984 ms —
     // and the set-aside it needs, cudaLimitPersistingL2CacheSize, stays carved out of the L2 for every later
     // kernel of the process: a following concat ran at 0.35 ms instead of 0.16 ms.  Removed.)
-    const int64_t key_bytes = ex.key_kind == KEY_BYTES ? in.cols[plan.used_cols[ex.key_slot]].data_bytes : 0;
+    int64_t key_bytes = ex.key_kind == KEY_BYTES ? in.cols[plan.used_cols[ex.key_slot]].data_bytes : 0;
+    if (ex.key_kind == KEY_BYTES) {
+      // staging of the key bytes is sized from the column's average key length: the batch's own when its extent is
+      // known, else what this plan saw last (a wrong guess only sends tiles down the unstaged path)
+      if (key_bytes >= 0 && n > 0) hints.avg_key_len.store((double)key_bytes / (double)n);
+      else if (hints.avg_key_len.load() >= 0) key_bytes = (int64_t)(hints.avg_key_len.load() * (double)n);
+      else {
+        resolve_varlen_extents(in, {plan.used_cols[ex.key_slot]}, stream);
+        key_bytes = in.cols[plan.used_cols[ex.key_slot]].data_bytes;
+        if (n > 0) hints.avg_key_len.store((double)key_bytes / (double)n);
+      }
+    }
     // low cardinality (table ≤ 1024 slots): per-CTA hash table in shared memory (hash_agg_tile.cu) — hot keys would
     // serialise on L2 atomics here (K = 2: 12.9 ms vs 0.24 ms).  Everything larger: this file's row kernel.
     static const unsigned long long tile_max = [] { const char* e = getenv("ARK_AGG_TILE_MAX"); return e ? (unsigned long long)atoll(e) : 1024ull; }();  // 2048 slots (≈ 1000 groups): 1.65 ms here vs 1.34 ms in hash_agg_kernel
     if (radix) {
     } else if (n > 0 && capacity <= tile_max && launch_hash_agg_tile(P, capacity, hints.groups.load(), key_bytes, stream)) {
+    } else if (n > 0 && launch_hash_agg_stream(P, capacity, key_bytes, stream)) {
     } else {
       if (P.pred_kind == 0) launch_agg<0>(P, n, stream);
       else if (P.pred_kind == 1) launch_agg<1>(P, n, stream);

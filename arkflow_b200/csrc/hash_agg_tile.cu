@@ -31,35 +31,6 @@ constexpr int HT_THREADS = 256;
 constexpr int HT_TILE = HT_THREADS * 4;
 
 
-// Key16 + 32-bit table hash of a byte string that sits in shared memory (same key encoding as make_key)
-__device__ __forceinline__ void make_key_smem(const uint8_t* p, int len, int64_t row, Key16* key, unsigned int* hash) {
-  Key16 k;
-  if (len <= 12) {
-    unsigned w[3] = {0, 0, 0};
-    if ((smem_addr(p) & 3) == 0) {
-      const unsigned* q = reinterpret_cast<const unsigned*>(p);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int rem = len - 4 * i;
-        if (rem >= 4) w[i] = q[i];
-        else if (rem > 0) { for (int b = 0; b < rem; ++b) w[i] |= (unsigned)p[4 * i + b] << (8 * b); }
-      }
-    } else {
-      for (int b = 0; b < len; ++b) w[b >> 2] |= (unsigned)p[b] << (8 * (b & 3));
-    }
-    k.lo = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
-    k.hi = (unsigned long long)w[2] | ((unsigned long long)(unsigned)len << 32);
-    *key = k; *hash = hash32_key16(k);
-  } else {
-    const unsigned prefix = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
-    k.lo = (unsigned long long)row;
-    k.hi = (unsigned long long)prefix | ((unsigned long long)(KEYTAG_LONG | (unsigned)len) << 32);
-    *key = k;
-    const unsigned long long h = hash_bytes(p, len);
-    *hash = (unsigned)(h >> 32) ^ (unsigned)h;
-  }
-}
-
 // Tables of ≤ 64 slots.  For every distinct slot among the warp's 128 rows: each lane first combines its own rows
 // of that slot, one shuffle reduction per slot follows, lane 0 applies the result to the WARP'S OWN copy of the
 // accumulator with a plain read-modify-write (no atomics, no contention between warps).
@@ -145,8 +116,9 @@ __global__ void __launch_bounds__(HT_THREADS, 3) hash_agg_tile_kernel(const __gr
 
   unsigned int claimed = 0;
   bool full = false;
+  unsigned phase = 0;  // mbarrier phases completed so far: advances only for tiles whose bulk copy was issued (CTA-uniform)
   const long long pred_c = P.sp_is_f64 ? f64_total_key(P.sp_const) : (long long)P.sp_const;
-  for (int tile = blockIdx.x, it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = (int64_t)tile * HT_TILE;
     const int rows = (int)((n - row0) < HT_TILE ? (n - row0) : HT_TILE);
     if (tid == 0) s_stop = *reinterpret_cast<volatile int32_t*>(P.overflow);  // table too small: the host retries with 4× the slots
@@ -201,7 +173,7 @@ __global__ void __launch_bounds__(HT_THREADS, 3) hash_agg_tile_kernel(const __gr
       ok |= (unsigned)f << j;
     }
     const bool staged = bytes_key && s_str_staged;
-    if (staged) mbar_wait(&s_bar, it & 1);
+    if (staged) { mbar_wait(&s_bar, phase & 1); ++phase; }
     // ---- keys → slots of the shared-memory table ----
     int slot[4];
 #pragma unroll
@@ -309,9 +281,8 @@ bool launch_hash_agg_tile(const AggParams& P, unsigned long long capacity, unsig
   const int64_t n = P.n_rows;
   int cap = 0;
   if (P.key_kind == KEY_BYTES) {
-    static std::atomic<double> avg_hint{12.8};
-    const double avg = (n > 0 && key_bytes >= 0) ? (double)key_bytes / (double)n : avg_hint.load();
-    if (n > 0 && key_bytes >= 0) avg_hint.store(avg);
+    // hash_pass passes the key column's extent (the batch's own, or the plan's last-seen average × rows)
+    const double avg = (n > 0 && key_bytes >= 0) ? (double)key_bytes / (double)n : 12.8;
     cap = (int)round_up((int64_t)(avg * HT_TILE * 1.0625) + 64, 1024);
     cap = std::max(4096, std::min(cap, 48 * 1024));
   }

@@ -2,6 +2,7 @@
 // column row, hashing, equality, and the 128-bit CAS / load used to claim and read table slots.
 #pragma once
 #include "hash_agg.cuh"
+#include "tma.cuh"
 #include "vm.cuh"
 
 namespace ark {
@@ -133,5 +134,35 @@ static __device__ __forceinline__ unsigned stored_key_hash32(Key16 k, const ColV
 static __device__ __forceinline__ int partition_of(unsigned long long h, int n_parts) {
   return (int)(((h >> 40) * (unsigned long long)n_parts) >> 24);
 }
+
+// Key16 + 32-bit table hash of a byte string that sits in shared memory (same key encoding as make_key)
+static __device__ __forceinline__ void make_key_smem(const uint8_t* p, int len, int64_t row, Key16* key, unsigned int* hash) {
+  Key16 k;
+  if (len <= 12) {
+    unsigned w[3] = {0, 0, 0};
+    if ((smem_addr(p) & 3) == 0) {
+      const unsigned* q = reinterpret_cast<const unsigned*>(p);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int rem = len - 4 * i;
+        if (rem >= 4) w[i] = q[i];
+        else if (rem > 0) { for (int b = 0; b < rem; ++b) w[i] |= (unsigned)p[4 * i + b] << (8 * b); }
+      }
+    } else {
+      for (int b = 0; b < len; ++b) w[b >> 2] |= (unsigned)p[b] << (8 * (b & 3));
+    }
+    k.lo = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
+    k.hi = (unsigned long long)w[2] | ((unsigned long long)(unsigned)len << 32);
+    *key = k; *hash = hash32_key16(k);
+  } else {
+    const unsigned prefix = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
+    k.lo = (unsigned long long)row;
+    k.hi = (unsigned long long)prefix | ((unsigned long long)(KEYTAG_LONG | (unsigned)len) << 32);
+    *key = k;
+    const unsigned long long h = hash_bytes(p, len);
+    *hash = (unsigned)(h >> 32) ^ (unsigned)h;
+  }
+}
+
 
 }  // namespace ark

@@ -80,6 +80,7 @@ struct FinalItem {      // one column of the result, in SELECT order
 struct AggHints {
   std::atomic<unsigned long long> capacity{1ull << 16};  // table slots to start with
   std::atomic<unsigned int> groups{0};                   // groups of the previous batch (0 = none yet)
+  std::atomic<double> avg_key_len{-1.0};                 // bytes per var-len key of the previous batch (sizes the key staging)
 };
 
 struct Plan {
