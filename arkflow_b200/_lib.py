@@ -106,6 +106,14 @@ def _declare(lib):
         "ark_hash_partition_device": (C.c_int, [P(ArrowDeviceArray), P(ArrowSchema), C.c_char_p, C.c_int, P(ArrowDeviceArray), P(ArrowSchema), P(C.c_int64)]),
         "ark_ipc_export_device": (C.c_int, [P(ArrowDeviceArray), P(ArrowSchema), P(C.c_uint8), C.c_int64, P(C.c_int64)]),
         "ark_ipc_concat_slices_device": (C.c_int, [C.c_int, P(P(C.c_uint8)), P(C.c_int64), P(C.c_int64), P(C.c_int64), P(ArrowDeviceArray), P(ArrowSchema)]),
+        "ark_dist_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, P(vp)]),
+        "ark_dist_handle_bytes": (C.c_int64, []),
+        "ark_dist_export": (C.c_int, [vp, P(C.c_uint8), C.c_int64, P(C.c_int64)]),
+        "ark_dist_connect": (C.c_int, [vp, P(C.c_uint8), C.c_int64]),
+        "ark_dist_destroy": (None, [vp]),
+        "ark_sql_group_by_exchange_device": (C.c_int, [vp, vp, P(ArrowDeviceArray), P(ArrowSchema), P(ArrowDeviceArray), P(ArrowSchema)]),
+        "ark_sql_group_by_push_device": (C.c_int, [vp, vp, P(ArrowDeviceArray), P(ArrowSchema)]),
+        "ark_sql_group_by_merge_device": (C.c_int, [vp, vp, P(ArrowDeviceArray), P(ArrowSchema)]),
         "ark_synth_batch_device": (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, C.c_int, C.c_int64, P(ArrowDeviceArray), P(ArrowSchema)]),
         "ark_kernel_launch_count": (C.c_int64, []),
         "ark_kernel_timing_enable": (None, [C.c_int]),

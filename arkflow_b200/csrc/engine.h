@@ -66,6 +66,9 @@ Batch run_aggregate(const Plan& plan, Batch& in, cudaStream_t stream);
 Batch run_join(const Plan& plan, Batch& left, Batch& right, cudaStream_t stream);
 Batch run_partial_aggregate(const Plan& plan, Batch& in, int n_parts, std::vector<int64_t>& part_rows, cudaStream_t stream);
 Batch run_final_aggregate(const Plan& plan, Batch& partial, cudaStream_t stream);
+struct DistCtx;  // group_exchange.h
+void run_group_by_push(const Plan& plan, Batch& in, DistCtx& d, cudaStream_t stream);
+bool run_group_by_merge(const Plan& plan, DistCtx& d, Batch& out, cudaStream_t stream);
 std::unique_ptr<Processor> make_json_to_arrow(const char* config_json);
 const std::string& json_to_arrow_value_field(const Processor& p);
 Batch json_to_arrow_device(const Processor& proc, Batch& in, cudaStream_t stream);

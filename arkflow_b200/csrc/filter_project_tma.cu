@@ -363,42 +363,48 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? ARK_FP_MINBLOCKS : 3
 }
 
 // ================================================================================================
-// filter_project_pipe_kernel — the same tile algorithm as a PERSISTENT, software-pipelined kernel.
+// filter_project_pipe_kernel — the same tile algorithm as a PERSISTENT, software-pipelined kernel with
+// warp-striped rows.
 //
-// filter_project_tma_kernel above runs one tile per CTA: loads → predicate → look-back → stores, so a CTA's
-// loads are in flight for only ~a quarter of its life (ncu r1f: 28 % of warp time parked at the look-back
-// barrier, 21 % waiting for the tile's loads, DRAM 48 % busy) and forward progress relied on CTAs being
-// dispatched in blockIdx order.  Here a CTA stays resident and claims tiles from a TICKET (a tile is only
-// ever owned by a running CTA, so the look-back cannot wait on a CTA that was never scheduled), and the loads
-// of the NEXT tile — predicate column and offsets into registers, the string window by TMA into the other
-// half of a two-stage ring — are issued before the current tile is evaluated.  A tile's aggregate is
-// therefore published a few hundred cycles after its iteration starts (its data is already on chip), which
-// is what keeps the look-back of its successors short.
-// Producer duties (ticket two tiles ahead, the tile's two bounding offsets one tile ahead, then the bulk
-// copy) belong to one thread of the LAST warp, so that warp 0 keeps only the look-back.
+// What ncu showed about filter_project_tma_kernel above (profiles/r1f_filter_project_tma_ncu.json and the
+// per-line view of the same capture): the LSU data pipe was the busiest unit (64 % of peak) and half of its
+// shared-memory wavefronts were bank conflicts; L1 handed the crossbar 501 MB of stores for 161 MB of output;
+// 28 % of warp time sat at the look-back barrier and 21 % waited for the tile's own loads.  A thread there owns
+// four CONSECUTIVE rows (two 16-byte loads per column), so the lanes of a warp touch strings 48 bytes apart in
+// shared memory (4-way conflicts) and every store instruction sprays 32 partial sectors.  Here:
+//   * rows are WARP-STRIPED: lane l of warp w owns rows 128 w + 32 j + l, j = 0..3.  For a given j the lanes
+//     read consecutive 12-byte strings (conflict-free) and the surviving lanes write CONSECUTIVE output slots
+//     (whole sectors); ranks come from ballots + popc instead of shuffle scans, and a warp whose 128 strings all
+//     have the same length (ids, codes: the benchmark's "temp_%07d") derives byte positions from the ranks;
+//   * the kernel is persistent and tiles come from a TICKET, so a tile is only ever owned by a running CTA and the
+//     look-back cannot wait on a CTA that was never scheduled (the r1 kernel relied on blockIdx dispatch order);
+//   * the loads of the NEXT tile — predicate column and offsets into registers, the string window by TMA into
+//     the other half of a two-stage ring — are issued before the current tile is evaluated; a tile's aggregate
+//     is published a few hundred cycles after its iteration starts, which keeps its successors' look-back short.
+// Producer duties (ticket two tiles ahead, the tile's two bounding offsets one tile ahead, then the bulk copy)
+// belong to one thread of the LAST warp, so that warp 0 keeps only the look-back.  The three tickets a CTA holds
+// at start-up are claimed one dependent-load latency apart: a CTA must not own ADJACENT tiles, because it
+// publishes them one iteration apart and every later tile's look-back would wait for that.
 // ================================================================================================
-
 template <bool VARLEN>
-__device__ __forceinline__ void load_rows_raw(const TmaParams& P, int64_t row0, int rows, int lr0, int lane, unsigned long long pv[4], int off[4],
-                                              int* offx) {
-  const bool full = lr0 + 4 <= rows;
-  const unsigned long long* src = P.pred_in + row0 + lr0;
-  if (full && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(pv[0]), "=l"(pv[1]) : "l"(src));
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(pv[2]), "=l"(pv[3]) : "l"(src + 2));
-  } else {
+__device__ __forceinline__ void load_rows_striped(const TmaParams& P, int64_t row0, int rows, int wrow0, int lane, unsigned long long pv[4], int off[4],
+                                                  int* offx) {
+  const unsigned long long* src = P.pred_in + row0 + wrow0 + lane;
+  const int32_t* os = P.offsets_in + row0 + wrow0 + lane;
+  const bool full = wrow0 + 128 <= rows;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) pv[j] = (lr0 + j < rows) ? src[j] : 0;
-  }
-  if (VARLEN) {
-    const int32_t* os = P.offsets_in + row0 + lr0;
-    if (full && (reinterpret_cast<uintptr_t>(os) & 15) == 0) {
-      asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(off[0]), "=r"(off[1]), "=r"(off[2]), "=r"(off[3]) : "l"(os));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) off[j] = (lr0 + j <= rows) ? os[j] : 0;
+  for (int j = 0; j < 4; ++j) {
+    const int r = wrow0 + 32 * j + lane;
+    if (full || r < rows) asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(pv[j]) : "l"(src + 32 * j));
+    else pv[j] = 0;
+    if (VARLEN) {
+      if (full || r <= rows) asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(off[j]) : "l"(os + 32 * j));
+      else off[j] = 0;
     }
-    *offx = ((lane == 31 || lr0 + 4 >= rows) && lr0 + 4 <= rows) ? os[4] : 0;
+  }
+  if (VARLEN) {  // offsets[first row of the next warp]: the end of lane 31's last string
+    *offx = 0;
+    if (lane == 31 && wrow0 + 128 <= rows) asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(*offx) : "l"(os + 97));
   }
 }
 
@@ -414,12 +420,13 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
   __shared__ long long s_excl[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wrow0 = warp * 128;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const int stage_bytes = P.str_cap + 32;
   uint8_t* const out_bytes = smem + 2 * stage_bytes;
   const int n_tiles = P.n_tiles;
-  const int lr0 = 4 * tid;
   auto tile_rows = [&](int t) { const int64_t r = P.n_rows - (int64_t)t * TT; return (int)(r < TT ? r : TT); };
-  // producer: arm stage `st` for tile t whose bounding offsets are o0, o1
+  // producer: arm stage `st` for the tile whose bounding offsets are o0, o1
   auto issue_window = [&](int st, int32_t o0, int32_t o1) {
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(P.data_in + o0), a1 = reinterpret_cast<uintptr_t>(P.data_in + o1);
     const uintptr_t lo = a0 & ~(uintptr_t)15, hi = (a1 + 15) & ~(uintptr_t)15;
@@ -432,25 +439,34 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
     s_str_base[st] = o0 - (int32_t)(a0 - lo); s_str_staged[st] = staged;
   };
 
-  // ---- prologue: tickets for the first three tiles of this CTA (same thread, same address ⇒ increasing) ----
+  // ---- prologue: the CTA's first three tickets, each claimed only after the previous one's dependent loads ----
   unsigned tk_next = 0;
   int32_t bo0 = 0, bo1 = 0;  // bounding offsets of the NEXT tile (consumed when its bulk copy is issued)
   if (tid == PRODUCER) {
     if (VARLEN) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
     const unsigned t0 = atomicAdd(P.ticket, 1u);
-    const unsigned t1 = atomicAdd(P.ticket, 1u);
-    tk_next = atomicAdd(P.ticket, 1u);
-    s_tile[0] = (int)min(t0, (unsigned)n_tiles); s_tile[1] = (int)min(t1, (unsigned)n_tiles);
-    if (VARLEN) {
-      if ((int)t0 < n_tiles) { const int64_t r0 = (int64_t)t0 * TT; issue_window(0, P.offsets_in[r0], P.offsets_in[r0 + tile_rows((int)t0)]); }
-      if ((int)t1 < n_tiles) { const int64_t r1 = (int64_t)t1 * TT; bo0 = P.offsets_in[r1]; bo1 = P.offsets_in[r1 + tile_rows((int)t1)]; }
+    s_tile[0] = (int)min(t0, (unsigned)n_tiles);
+    unsigned dep = 0;  // makes the next claim wait for this tile's loads (separates the claims in time)
+    if ((int)t0 < n_tiles) {
+      const int64_t r0 = (int64_t)t0 * TT;
+      if (VARLEN) { const int32_t o0 = P.offsets_in[r0], o1 = P.offsets_in[r0 + tile_rows((int)t0)]; issue_window(0, o0, o1); dep = (unsigned)(o0 ^ o1) & 0x80000000u; }
+      else dep = (unsigned)(ld_volatile_u64(P.pred_in + r0) >> 63) & 0u;
     }
+    const unsigned t1 = atomicAdd(P.ticket, 1u + dep);
+    s_tile[1] = (int)min(t1, (unsigned)n_tiles);
+    dep = 0;
+    if ((int)t1 < n_tiles) {
+      const int64_t r1 = (int64_t)t1 * TT;
+      if (VARLEN) { bo0 = P.offsets_in[r1]; bo1 = P.offsets_in[r1 + tile_rows((int)t1)]; dep = (unsigned)(bo0 ^ bo1) & 0x80000000u; }
+      else dep = (unsigned)(ld_volatile_u64(P.pred_in + r1) >> 63) & 0u;
+    }
+    tk_next = atomicAdd(P.ticket, 1u + dep);
   }
   __syncthreads();
   int tile = s_tile[0];
   unsigned long long pvn[4] = {0, 0, 0, 0};
   int offn[4] = {0, 0, 0, 0}, offxn = 0;
-  if (tile < n_tiles) load_rows_raw<VARLEN>(P, (int64_t)tile * TT, tile_rows(tile), lr0, lane, pvn, offn, &offxn);
+  if (tile < n_tiles) load_rows_striped<VARLEN>(P, (int64_t)tile * TT, tile_rows(tile), wrow0, lane, pvn, offn, &offxn);
   unsigned ph = 0;  // bit s: parity to wait for on stage s (flips only when a bulk copy was issued for it)
 
   for (int it = 0; tile < n_tiles; ++it) {
@@ -460,7 +476,7 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
     uint8_t* const in_bytes = smem + st * stage_bytes;
     // this tile's registers (loaded one iteration ago)
     unsigned long long pv[4] = {pvn[0], pvn[1], pvn[2], pvn[3]};
-    int off[5] = {offn[0], offn[1], offn[2], offn[3], 0};
+    int off[4] = {offn[0], offn[1], offn[2], offn[3]};
     const int offx = offxn;
     // ---- A: everything the NEXT tile needs is put in flight now ----
     const int next = s_tile[(it + 1) & 3];
@@ -471,18 +487,67 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
       if (VARLEN && next2 < n_tiles) { const int64_t r2 = (int64_t)next2 * TT; bo0 = P.offsets_in[r2]; bo1 = P.offsets_in[r2 + tile_rows(next2)]; }
       if (next2 < n_tiles) tk_next = atomicAdd(P.ticket, 1u);
     }
-    if (next < n_tiles) load_rows_raw<VARLEN>(P, (int64_t)next * TT, tile_rows(next), lr0, lane, pvn, offn, &offxn);
-    // ---- B: predicate, thread-local and warp-level prefix sums ----
-    if (VARLEN) {
-      off[4] = __shfl_down_sync(0xffffffffu, off[0], 1);
-      if ((lane == 31 || lr0 + 4 >= rows) && lr0 + 4 <= rows) off[4] = offx;
+    if (next < n_tiles) load_rows_striped<VARLEN>(P, (int64_t)next * TT, tile_rows(next), wrow0, lane, pvn, offn, &offxn);
+    // ---- B: predicate; ranks from ballots; byte positions ----
+    unsigned flags = 0;
+    int len[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long key = P.sp_is_f64 ? f64_total_key(pv[j]) : (long long)pv[j];
+      bool f = (unsigned long long)(key - P.range_lo) <= P.range_span;
+      f = (f != (bool)P.negate) && (wrow0 + 32 * j + lane < rows);
+      flags |= (unsigned)f << j;
     }
-    int cnt, sel_bytes;
-    const unsigned flags = eval_rows<VARLEN>(P, rows, lr0, pv, off, &cnt, &sel_bytes);
-    const int cnt_incl = warp_incl_scan(cnt, lane);
-    int bytes_incl = 0;
-    if (VARLEN) bytes_incl = warp_incl_scan(sel_bytes, lane);
-    if (lane == 31) { s_cnt[warp] = cnt_incl; if (VARLEN) s_bytes[warp] = bytes_incl; }
+    if (VARLEN) {
+      // end of row (j, lane) = start of row (j, lane + 1); lane 31: row (j + 1, 0), or the next warp's first row
+      const int rows_w = rows - wrow0;  // rows of this warp's slice that exist (may be ≤ 0 or < 128 in the last tile)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int e = __shfl_down_sync(0xffffffffu, off[j], 1);
+        const int nxt = j < 3 ? __shfl_sync(0xffffffffu, off[j < 3 ? j + 1 : 3], 0) : offx;
+        if (lane == 31) e = nxt;
+        len[j] = (32 * j + lane < rows_w) ? e - off[j] : 0;
+      }
+    }
+    int wpos[4];  // rank of row (j, lane) among the warp's selected rows
+    int warp_cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned m = __ballot_sync(0xffffffffu, (flags >> j) & 1);
+      wpos[j] = warp_cnt + __popc(m & lt_mask);
+      warp_cnt += __popc(m);
+    }
+    int bpos[4] = {0, 0, 0, 0};  // byte position of row (j, lane) among the warp's selected bytes
+    int warp_bytes = 0;
+    if (VARLEN) {
+      const int len0 = __shfl_sync(0xffffffffu, len[0], 0);
+      const bool same = (len[0] == len0 || wrow0 + lane >= rows) && (len[1] == len0 || wrow0 + 32 + lane >= rows) &&
+                        (len[2] == len0 || wrow0 + 64 + lane >= rows) && (len[3] == len0 || wrow0 + 96 + lane >= rows);
+      if (__all_sync(0xffffffffu, same)) {  // fixed-width strings: positions follow from the ranks
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bpos[j] = wpos[j] * len0;
+        warp_bytes = warp_cnt * len0;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int sl = ((flags >> j) & 1) ? len[j] : 0;
+          const int incl = warp_incl_scan(sl, lane);
+          bpos[j] = warp_bytes + incl - sl;
+          warp_bytes += __shfl_sync(0xffffffffu, incl, 31);
+        }
+      }
+    }
+    if (lane == 0) { s_cnt[warp] = warp_cnt; if (VARLEN) s_bytes[warp] = warp_bytes; }
+    // other projected fixed-width columns: requested now, stored after the look-back
+    unsigned long long fx[NF > 0 ? NF : 1][4];
+#pragma unroll
+    for (int c = 0; c < NF; ++c) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        fx[c][j] = pv[j];
+        if (!((P.fixed_is_pred >> c) & 1) && ((flags >> j) & 1)) fx[c][j] = ld_stream_u64(P.fixed_in[c] + row0 + wrow0 + 32 * j + lane);
+      }
+    }
     __syncthreads();   // (1)
 
     // ---- D: tile scan over the per-warp totals (every warp, redundantly); publish the tile aggregate at once ----
@@ -512,13 +577,8 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
       if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
     }
     // ---- E: compact the strings in shared memory at tile-local positions ----
-    const int my_cnt_excl = w_cnt_excl + cnt_incl - cnt;
-    int lpos[4];
     bool str_fast = false;
     if (VARLEN) {
-      int run = w_bytes_excl + bytes_incl - sel_bytes;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { lpos[j] = run; if ((flags >> j) & 1) run += off[j + 1] - off[j]; }
       str_fast = s_str_staged[st];
       if (str_fast) {
         mbar_wait(&s_bar[st], (ph >> st) & 1);  // this tile's window (issued one iteration ago)
@@ -526,7 +586,7 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
         const int base = s_str_base[st];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if ((flags >> j) & 1) smem_copy(out_bytes + lpos[j], in_bytes + (off[j] - base), off[j + 1] - off[j]);
+          if ((flags >> j) & 1) smem_copy(out_bytes + w_bytes_excl + bpos[j], in_bytes + (off[j] - base), len[j]);
       }
     }
     __syncthreads();   // (2)
@@ -534,18 +594,14 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
     const long long bb = VARLEN ? s_excl[1] : 0;
     if (tile == n_tiles - 1 && tid == 0) { P.totals[0] = base_cnt + tile_cnt; P.totals[1] = bb + tb; }
 
-    // ---- G: stores ----
-    {
-      long long pos = base_cnt + my_cnt_excl;
+    // ---- G: stores — for each j the surviving lanes of a warp write consecutive slots ----
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (!((flags >> j) & 1)) continue;
+    for (int j = 0; j < 4; ++j) {
+      if (!((flags >> j) & 1)) continue;
+      const long long pos = base_cnt + w_cnt_excl + wpos[j];
 #pragma unroll
-        for (int c = 0; c < NF; ++c)
-          P.fixed_out[c][pos] = ((P.fixed_is_pred >> c) & 1) ? pv[j] : ld_stream_u64(P.fixed_in[c] + row0 + lr0 + j);
-        if (VARLEN) P.offsets_out[pos] = (int32_t)(bb + lpos[j]);
-        ++pos;
-      }
+      for (int c = 0; c < NF; ++c) P.fixed_out[c][pos] = fx[c][j];
+      if (VARLEN) P.offsets_out[pos] = (int32_t)(bb + w_bytes_excl + bpos[j]);
     }
     if (VARLEN) {
       if (tile == n_tiles - 1 && tid == 0) P.offsets_out[base_cnt + tile_cnt] = (int32_t)(bb + tb);
@@ -574,8 +630,8 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
         for (int j = 0; j < 4; ++j) {
           if (!((flags >> j) & 1)) continue;
           const uint8_t* src = P.data_in + off[j];
-          uint8_t* dst = P.data_out + bb + lpos[j];
-          for (int i = 0; i < off[j + 1] - off[j]; ++i) dst[i] = src[i];
+          uint8_t* dst = P.data_out + bb + w_bytes_excl + bpos[j];
+          for (int i = 0; i < len[j]; ++i) dst[i] = src[i];
         }
       }
     }
@@ -653,9 +709,9 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
     static size_t occ_smem[2][3] = {{0, 0, 0}, {0, 0, 0}};
     static bool configured = false;
     const int max_smem = 3 * (48 * 1024 + 32);
-    // CTAs per SM the kernel is compiled for: 5 (48 registers, a few spilled words) or 4 (64 registers)
-    static const int minb = [] { const char* e = getenv("ARK_FP_MINB"); return e && atoi(e) == 4 ? 4 : 5; }();
-#define ARK_PIPE_FN(NF, V) (minb == 4 ? (const void*)filter_project_pipe_kernel<NF, V, 4> : (const void*)filter_project_pipe_kernel<NF, V, 5>)
+    // CTAs per SM the kernel is compiled for: 4 (64 registers, the default) or 5 (48 registers, a few spilled words)
+    static const int minb = [] { const char* e = getenv("ARK_FP_MINB"); const int v = e ? atoi(e) : 4; return v == 3 || v == 5 ? v : 4; }();
+#define ARK_PIPE_FN(NF, V) (minb == 4 ? (const void*)filter_project_pipe_kernel<NF, V, 4> : minb == 3 ? (const void*)filter_project_pipe_kernel<NF, V, 3> : (const void*)filter_project_pipe_kernel<NF, V, 5>)
     if (!configured) {
       for (const void* f : {ARK_PIPE_FN(0, true), ARK_PIPE_FN(1, true), ARK_PIPE_FN(2, true)})
         ARK_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));

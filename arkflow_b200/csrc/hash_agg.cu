@@ -5,14 +5,15 @@
 // (third-party; reached from crates/arkflow-plugin/src/processor/sql.rs:126-129).  The same kernel
 // runs the *final* merge of partial states on the multi-GPU path (sum of sums / counts, min of mins).
 //
-// Table: slots of {Key16, accumulators…} (32 B for ≤ 2 accumulators: ONE L2 sector per group); the key
-// is claimed with a single 128-bit CAS (ATOMG.CAS.128), accumulators take fire-and-forget RED atomics; a warp whose
-// lanes all hit the same group reduces with shuffles first (global aggregates, hot keys).
+// Table: buckets of four slots — four Key16 keys (two sectors) followed by one sector per accumulator (hash_agg.cuh);
+// a probe reads a whole bucket, a key is claimed with a single 128-bit CAS (ATOMG.CAS.128), accumulators take
+// fire-and-forget RED atomics; a warp whose lanes all hit the same group reduces with shuffles first.
 // Algorithmic traffic = key + argument bytes read once (24 B/row for config 3).
 #include <cub/device/device_scan.cuh>
 
 #include "agg_acc.cuh"
 #include "engine.h"
+#include "group_exchange.h"
 #include "hash_agg.cuh"
 #include "hashkey.cuh"
 #include "vm.cuh"
@@ -21,25 +22,17 @@ namespace ark {
 
 namespace {
 
-__device__ __forceinline__ Key16* slot_key(uint8_t* table, unsigned long long slot, int stride) {
-  return reinterpret_cast<Key16*>(table + slot * (unsigned long long)stride);
-}
-__device__ __forceinline__ const Key16* slot_key(const uint8_t* table, unsigned long long slot, int stride) {
-  return reinterpret_cast<const Key16*>(table + slot * (unsigned long long)stride);
-}
-
-__global__ void agg_init_kernel(uint8_t* table, unsigned long long capacity, int stride, int n_acc, AccParam a0, AccParam a1, AccParam a2,
+__global__ void agg_init_kernel(uint8_t* table, unsigned long long capacity, int bstride, int n_acc, AccParam a0, AccParam a1, AccParam a2,
                                 AccParam a3, AccParam a4, AccParam a5, AccParam a6, AccParam a7) {
   const AccParam accs[AGG_MAX_ACC] = {a0, a1, a2, a3, a4, a5, a6, a7};
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
        i += (unsigned long long)gridDim.x * blockDim.x) {
-    uint8_t* s = table + i * (unsigned long long)stride;
-    *reinterpret_cast<Key16*>(s) = Key16{KEY_EMPTY, KEY_EMPTY};
+    *tbl_key(table, i, bstride) = Key16{KEY_EMPTY, KEY_EMPTY};
     for (int a = 0; a < n_acc; ++a) {
       unsigned long long init = 0;
       if (accs[a].kind == ACC_MIN_I64 || accs[a].kind == ACC_MIN_F64) init = 0x7FFFFFFFFFFFFFFFull;
       if (accs[a].kind == ACC_MAX_I64 || accs[a].kind == ACC_MAX_F64) init = 0x8000000000000000ull;
-      *reinterpret_cast<unsigned long long*>(s + accs[a].acc_offset) = init;
+      *tbl_acc(table, i, a, bstride) = init;
     }
   }
 }
@@ -57,131 +50,100 @@ __device__ __forceinline__ unsigned long long table_hash(int key_kind, const Col
   return ((unsigned long long)h << 32) | (h * 0x9E3779B1u);
 }
 
-// R rows per thread per iteration, processed phase by phase (predicate → key → slot fetch → claim →
-// accumulate) so that the R dependent load chains of a thread overlap (R = 1 is what is launched, see launch_agg).
-template <int PRED, int R>
+// The general row kernel: one row per thread per iteration, any predicate (simple or VM program), any key kind,
+// computed aggregate arguments.  High-cardinality plain-column queries take hash_agg_stream.cu instead.
+template <int PRED>
 __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_constant__ AggParams P) {
   const int lane = threadIdx.x & 31;
   const int64_t n = P.n_rows;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x * R;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int bstride = P.bucket_stride;
+  const unsigned long long bmask = P.mask >> 2;
   int32_t err = 0;
   const ColView& kc = P.cols[P.key_kind == KEY_NONE ? 0 : P.key_slot];
   if (P.key_kind == KEY_NONE && blockIdx.x == 0 && threadIdx.x == 0) {
     // a global aggregate always yields one row, even when no row survives the filter
     Key16 mine; unsigned long long h;
     make_key(KEY_NONE, kc, 0, &mine, &h);
-    Key16 cur = cas128(slot_key(P.table, h & P.mask, P.slot_stride), Key16{KEY_EMPTY, KEY_EMPTY}, mine);
-    if (cur.hi == KEY_EMPTY && cur.lo == KEY_EMPTY) atomicAdd(P.group_count, 1u);
+    unsigned int c = 0;
+    table_find_or_claim(P.table, bmask, bstride, h, mine, kc, kc, &c);
+    if (c) atomicAdd(P.group_count, c);
   }
   __shared__ volatile int32_t s_stop;
   if (threadIdx.x == 0) s_stop = 0;
   __syncthreads();
   unsigned int claimed = 0;
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * R; base < n; base += stride) {
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
     // A table that is too small (first batch of a high-cardinality stream): once some row has raised `overflow` the
     // launch is void (the host retries with 4× the slots), so stop instead of walking a full table with every
-    // remaining row (63 ms for one 2^24-row launch).  ONE thread per CTA polls the flag — every thread polling the
-    // same L2 line cost 0.33 ms per launch — and the other warps pick it up from shared memory an iteration later.
+    // remaining row.  ONE thread per CTA polls the flag — every thread polling the same L2 line cost 0.33 ms per
+    // launch — and the other warps pick it up from shared memory an iteration later.
     if (threadIdx.x == 0) s_stop = *reinterpret_cast<volatile int32_t*>(P.overflow);
     if (__any_sync(0xffffffffu, s_stop != 0)) break;  // warp-uniform: the full-mask shuffles below need every lane
-    int64_t row[R];
-    bool ok[R];
-    Key16 mine[R];
-    unsigned long long slot[R];
-    Key16 cur[R];
-    // ---- predicate ----
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      row[r] = base + (int64_t)r * blockDim.x + threadIdx.x;
-      ok[r] = row[r] < n;
-      if (PRED == 1) {
-        if (ok[r]) {
-          const ColView& c = P.cols[P.sp_slot];
-          const unsigned long long v = __ldcs((const unsigned long long*)c.data + row[r]);
-          if (P.sp_is_f64) ok[r] = cmp_i64(P.sp_cmp, f64_total_key(v), f64_total_key(P.sp_const));
-          else ok[r] = cmp_i64(P.sp_cmp, (int64_t)v, (int64_t)P.sp_const);
-          ok[r] = ok[r] && col_valid(c, row[r]);
-        }
-      } else if (PRED == 2) {
-        if (ok[r]) { VmVal v = vm_eval(P.pred, P.cols, row[r], &err); ok[r] = v.valid && (v.bits & 1); }
+    const int64_t row = base + threadIdx.x;
+    bool ok = row < n;
+    if (PRED == 1) {
+      if (ok) {
+        const ColView& c = P.cols[P.sp_slot];
+        const unsigned long long v = __ldcs((const unsigned long long*)c.data + row);
+        if (P.sp_is_f64) ok = cmp_i64(P.sp_cmp, f64_total_key(v), f64_total_key(P.sp_const));
+        else ok = cmp_i64(P.sp_cmp, (int64_t)v, (int64_t)P.sp_const);
+        ok = ok && col_valid(c, row);
       }
+    } else if (PRED == 2) {
+      if (ok) { VmVal v = vm_eval(P.pred, P.cols, row, &err); ok = v.valid && (v.bits & 1); }
     }
-    // ---- keys + hashes ----
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      slot[r] = 0;
-      if (ok[r]) slot[r] = table_hash(P.key_kind, kc, row[r], &mine[r]) & P.mask;
-    }
-    // ---- all slots fetched before any is resolved ----
-#pragma unroll
-    for (int r = 0; r < R; ++r) if (ok[r]) cur[r] = ld128(slot_key(P.table, slot[r], P.slot_stride));
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (!ok[r]) continue;
-      Key16 c = cur[r];
-      int probes = 0;
-      while (true) {
-        if (c.hi == KEY_EMPTY) {
-          // A table that is too small (first batch of a high-cardinality stream) must not fill up: past the load
-          // limit no new key is inserted, so probe chains stay short and the launch ends quickly with `overflow`
-          // set (the host retries with 4× the slots).  Without this the remaining rows walk a full table —
-          // 63 ms for one 2^24-row launch.  Only rows that found an EMPTY slot pay for the counter read.
-          c = cas128(slot_key(P.table, slot[r], P.slot_stride), Key16{KEY_EMPTY, KEY_EMPTY}, mine[r]);
-          if (c.hi == KEY_EMPTY && c.lo == KEY_EMPTY) { ++claimed; break; }  // counted per thread, added once per warp at the end
-        }
-        if (key_equal(mine[r], c, kc, kc)) break;
-        slot[r] = (slot[r] + 1) & P.mask;
-        if (++probes > 512) { atomicExch(P.overflow, 1); ok[r] = false; break; }  // the table is too loaded for this batch (longest run expected at load 0.5: ~75 slots, at 0.75: ~400)
-        c = ld128(slot_key(P.table, slot[r], P.slot_stride));
-      }
+    unsigned long long slot = 0;
+    if (ok) {
+      Key16 mine;
+      const unsigned long long h = table_hash(P.key_kind, kc, row, &mine);
+      slot = table_find_or_claim(P.table, bmask, bstride, h, mine, kc, kc, &claimed);
+      if (slot == ~0ull) { atomicExch(P.overflow, 1); ok = false; }  // the table is too loaded for this batch
     }
     // ---- accumulate; a warp whose lanes all hit one group reduces with shuffles first ----
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const unsigned m = __ballot_sync(0xffffffffu, ok[r]);
-      if (m == 0) continue;
-      const int leader = __ffs(m) - 1;
-      const unsigned long long slot0 = __shfl_sync(0xffffffffu, slot[r], leader);
-      const bool uniform = __all_sync(0xffffffffu, !ok[r] || slot[r] == slot0) && __popc(m) > 1;
-      for (int a = 0; a < P.n_acc; ++a) {
-        const AccParam& A = P.accs[a];
-        unsigned long long bits = 0;
-        bool valid = ok[r];
-        if (ok[r] && A.kind != ACC_COUNT_STAR) {
-          if (A.arg_prog >= 0) { VmVal v = vm_eval(P.progs[A.arg_prog], P.cols, row[r], &err); bits = v.bits; valid = v.valid; }
-          else { const ColView& c = P.cols[A.arg_slot]; valid = col_valid(c, row[r]); bits = valid ? __ldcs((const unsigned long long*)c.data + row[r]) : 0; }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (m == 0) continue;
+    const int leader = __ffs(m) - 1;
+    const unsigned long long slot0 = __shfl_sync(0xffffffffu, slot, leader);
+    const bool uniform = __all_sync(0xffffffffu, !ok || slot == slot0) && __popc(m) > 1;
+    for (int a = 0; a < P.n_acc; ++a) {
+      const AccParam& A = P.accs[a];
+      unsigned long long bits = 0;
+      bool valid = ok;
+      if (ok && A.kind != ACC_COUNT_STAR) {
+        if (A.arg_prog >= 0) { VmVal v = vm_eval(P.progs[A.arg_prog], P.cols, row, &err); bits = v.bits; valid = v.valid; }
+        else { const ColView& c = P.cols[A.arg_slot]; valid = col_valid(c, row); bits = valid ? __ldcs((const unsigned long long*)c.data + row) : 0; }
+      }
+      unsigned long long* dst = tbl_acc(P.table, uniform ? slot0 : slot, a, bstride);
+      switch (A.kind) {
+        case ACC_COUNT_STAR:
+        case ACC_COUNT: {
+          if (uniform) { const int c = __popc(__ballot_sync(0xffffffffu, valid)); if (lane == leader && c) atomicAdd(dst, (unsigned long long)c); }
+          else if (valid) atomicAdd(dst, 1ull);
+          break;
         }
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.table + (uniform ? slot0 : slot[r]) * (unsigned long long)P.slot_stride + A.acc_offset);
-        switch (A.kind) {
-          case ACC_COUNT_STAR:
-          case ACC_COUNT: {
-            if (uniform) { const int c = __popc(__ballot_sync(0xffffffffu, valid)); if (lane == leader && c) atomicAdd(dst, (unsigned long long)c); }
-            else if (valid) atomicAdd(dst, 1ull);
-            break;
-          }
-          case ACC_SUM_I64: {
-            if (uniform) { const long long s = warp_sum_ll(valid ? (long long)bits : 0); if (lane == leader) atomicAdd(dst, (unsigned long long)s); }
-            else if (valid) atomicAdd(dst, bits);
-            break;
-          }
-          case ACC_SUM_F64: {
-            double x = A.arg_is_f64 ? __longlong_as_double((long long)bits) : (double)(long long)bits;
-            if (uniform) { const double s = warp_sum_f64(valid ? x : 0.0); if (lane == leader) atomicAdd((double*)dst, s); }
-            else if (valid) atomicAdd((double*)dst, x);
-            break;
-          }
-          case ACC_MIN_I64: case ACC_MIN_F64: {
-            long long x = A.kind == ACC_MIN_F64 ? f64_total_key(bits) : (long long)bits;
-            if (uniform) { const long long s = warp_min_ll(valid ? x : 0x7FFFFFFFFFFFFFFFll); if (lane == leader) atomicMin((long long*)dst, s); }
-            else if (valid) atomicMin((long long*)dst, x);
-            break;
-          }
-          default: {
-            long long x = A.kind == ACC_MAX_F64 ? f64_total_key(bits) : (long long)bits;
-            if (uniform) { const long long s = warp_max_ll(valid ? x : (long long)0x8000000000000000ull); if (lane == leader) atomicMax((long long*)dst, s); }
-            else if (valid) atomicMax((long long*)dst, x);
-            break;
-          }
+        case ACC_SUM_I64: {
+          if (uniform) { const long long sm = warp_sum_ll(valid ? (long long)bits : 0); if (lane == leader) atomicAdd(dst, (unsigned long long)sm); }
+          else if (valid) atomicAdd(dst, bits);
+          break;
+        }
+        case ACC_SUM_F64: {
+          double x = A.arg_is_f64 ? __longlong_as_double((long long)bits) : (double)(long long)bits;
+          if (uniform) { const double sm = warp_sum_f64(valid ? x : 0.0); if (lane == leader) atomicAdd((double*)dst, sm); }
+          else if (valid) atomicAdd((double*)dst, x);
+          break;
+        }
+        case ACC_MIN_I64: case ACC_MIN_F64: {
+          long long x = A.kind == ACC_MIN_F64 ? f64_total_key(bits) : (long long)bits;
+          if (uniform) { const long long sm = warp_min_ll(valid ? x : 0x7FFFFFFFFFFFFFFFll); if (lane == leader) atomicMin((long long*)dst, sm); }
+          else if (valid) atomicMin((long long*)dst, x);
+          break;
+        }
+        default: {
+          long long x = A.kind == ACC_MAX_F64 ? f64_total_key(bits) : (long long)bits;
+          if (uniform) { const long long sm = warp_max_ll(valid ? x : (long long)0x8000000000000000ull); if (lane == leader) atomicMax((long long*)dst, sm); }
+          else if (valid) atomicMax((long long*)dst, x);
+          break;
         }
       }
     }
@@ -196,7 +158,7 @@ __global__ void agg_count_parts_kernel(const uint8_t* table, int stride, unsigne
                                        unsigned int* part_counts) {
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
        i += (unsigned long long)gridDim.x * blockDim.x) {
-    Key16 k = *slot_key(table, i, stride);
+    Key16 k = *tbl_key(table, i, stride);
     if (k.hi == KEY_EMPTY) continue;
     const int p = n_parts > 1 ? partition_of(key_kind == KEY_NONE ? 0 : stored_key_hash(k, kc), n_parts) : 0;
     atomicAdd(part_counts + p, 1u);
@@ -208,7 +170,7 @@ __global__ void agg_compact_kernel(const uint8_t* table, int stride, unsigned lo
                                    unsigned int* part_cursor, unsigned int* slots) {
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
        i += (unsigned long long)gridDim.x * blockDim.x) {
-    Key16 k = *slot_key(table, i, stride);
+    Key16 k = *tbl_key(table, i, stride);
     if (k.hi == KEY_EMPTY) continue;
     const int p = n_parts > 1 ? partition_of(key_kind == KEY_NONE ? 0 : stored_key_hash(k, kc), n_parts) : 0;
     slots[atomicAdd(part_cursor + p, 1u)] = (unsigned int)i;
@@ -218,7 +180,7 @@ __global__ void agg_compact_kernel(const uint8_t* table, int stride, unsigned lo
 __global__ void agg_key_lengths_kernel(const uint8_t* table, int stride, const unsigned int* slots, unsigned int n_groups, int32_t* lens) {
   unsigned int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_groups) return;
-  Key16 k = *slot_key(table, slots[g], stride);
+  Key16 k = *tbl_key(table, slots[g], stride);
   const unsigned tag = (unsigned)(k.hi >> 32);
   lens[g] = tag == KEYTAG_NULL ? 0 : (int32_t)(tag & 0x7FFFFFFFu);
 }
@@ -229,7 +191,7 @@ __global__ void agg_emit_keys_kernel(const uint8_t* table, int stride, const uns
                                      uint8_t* out_bytes, uint8_t* out_valid_bytes) {
   unsigned int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_groups) return;
-  Key16 k = *slot_key(table, slots[g], stride);
+  Key16 k = *tbl_key(table, slots[g], stride);
   const unsigned tag = (unsigned)(k.hi >> 32);
   const bool is_null = tag == KEYTAG_NULL;
   if (out_valid_bytes) out_valid_bytes[g] = !is_null;
@@ -248,10 +210,10 @@ __global__ void agg_emit_keys_kernel(const uint8_t* table, int stride, const uns
 }
 
 // dense accumulator columns: gather acc[slots[g]]
-__global__ void agg_gather_acc_kernel(const uint8_t* table, int stride, int acc_offset, const unsigned int* slots, unsigned int n_groups,
+__global__ void agg_gather_acc_kernel(const uint8_t* table, int stride, int acc, const unsigned int* slots, unsigned int n_groups,
                                       unsigned long long* out) {
   unsigned int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < n_groups) out[g] = *reinterpret_cast<const unsigned long long*>(table + (unsigned long long)slots[g] * stride + acc_offset);
+  if (g < n_groups) out[g] = *tbl_acc(table, slots[g], acc, stride);
 }
 
 enum FinalOp : int32_t { FIN_COPY = 0, FIN_AVG = 1, FIN_F64_KEY_BACK = 2, FIN_CONST = 3 };
@@ -274,13 +236,9 @@ __global__ void agg_finalize_kernel(int op, const unsigned long long* a, const u
 
 template <int PRED>
 void launch_agg(const AggParams& P, int64_t n, cudaStream_t stream) {
-  // One row per thread per iteration.  The kernel keeps its R-rows-per-thread form (all slot loads of a thread
-  // issued before any is resolved), but more rows in flight per thread measured slower at 10^6 groups —
-  // R = 1 0.62 ms, R = 2 0.65 ms, R = 4 1.05 ms (and 0.97 / 1.03 / 1.20 ms while the kernel still had the hot
-  // group_count atomic).
   KernelTimer t("hash_agg_kernel", stream);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, (int64_t)AGG_THREADS), 148 * 8));
-  hash_agg_kernel<PRED, 1><<<grid, AGG_THREADS, 0, stream>>>(P);
+  hash_agg_kernel<PRED><<<grid, AGG_THREADS, 0, stream>>>(P);
 }
 
 struct AccPlan {  // host-side description of one accumulator
@@ -322,8 +280,7 @@ struct DenseGroups {  // result of the hash pass: dense arrays of G groups, part
   unsigned int n_groups = 0;
   std::vector<int64_t> part_rows;
   BufferPtr table, slots;                // table + dense slot list
-  int stride = 32;
-  std::vector<int> acc_offsets;
+  int stride = 128;   // bucket stride (hash_agg.cuh: table layout)
   unsigned long long capacity = 0;
 };
 
@@ -333,7 +290,11 @@ bool launch_hash_agg_radix(const AggParams& P, unsigned long long capacity, int3
 void hash_agg_radix_note_skew();
 
 
-static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int n_parts, cudaStream_t stream) {
+// dense, partition-ordered slot list of a built table (n_parts = 1: plain compaction)
+static void compact_groups(DenseGroups& dg, const ColView& kc, int key_kind, int n_parts, BufferPtr ctl, BufferPtr hctl, cudaStream_t stream);
+
+// compact == false: stop once the table is built (the device-side exchange pushes the slots themselves)
+static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int n_parts, cudaStream_t stream, bool compact = true) {
   const int64_t n = in.num_rows;
   AggHints& hints = *plan.hints;  // per plan: the table size this query needed last time
   unsigned long long capacity = std::max<unsigned long long>(hints.capacity.load(), 1ull << 10);
@@ -344,10 +305,9 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
   bool allow_radix = true;
   if (n_parts > 32) fail(ARK_ERR_UNSUPPORTED, "more than 32 partitions");
   while (true) {
-    const int stride = 32 * (int)ceil_div(16 + 8 * (int64_t)ex.accs.size(), 32);
+    const int stride = table_bucket_stride((int)ex.accs.size());
     dg.stride = stride;
-    dg.table = device_alloc((size_t)capacity * stride);
-    dg.acc_offsets.clear();
+    dg.table = device_alloc((size_t)table_bytes(capacity, (int)ex.accs.size()));
     AggParams P;
     memset(&P, 0, sizeof P);
     P.n_rows = n;
@@ -358,13 +318,12 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     for (size_t s = 0; s < plan.used_cols.size(); ++s) P.cols[s] = in.cols[plan.used_cols[s]].view();
     P.n_acc = (int)ex.accs.size();
     for (size_t a = 0; a < ex.accs.size(); ++a) {
-      dg.acc_offsets.push_back(16 + 8 * (int)a);
       P.accs[a].kind = ex.accs[a].kind; P.accs[a].arg_slot = ex.accs[a].arg_slot; P.accs[a].arg_prog = ex.accs[a].arg_prog;
-      P.accs[a].arg_is_f64 = ex.accs[a].arg_is_f64; P.accs[a].acc_offset = 16 + 8 * (int)a;
+      P.accs[a].arg_is_f64 = ex.accs[a].arg_is_f64; P.accs[a].acc_index = (int)a;
     }
     for (size_t i = 0; i < ex.progs.size(); ++i) P.progs[i] = ex.progs[i];
     P.table = (uint8_t*)dg.table.get();
-    P.slot_stride = stride;
+    P.bucket_stride = stride;
     P.mask = capacity - 1;
     P.group_count = (unsigned int*)ctl.get();
     P.overflow = (int32_t*)((char*)ctl.get() + 4);
@@ -435,17 +394,23 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     hints.groups.store(groups);
     break;
   }
-  // dense, partition-ordered slot list
+  if (!compact) return dg;
   const ColView kc = ex.key_kind == KEY_NONE ? ColView{} : in.cols[plan.used_cols[ex.key_slot]].view();
+  compact_groups(dg, kc, ex.key_kind, n_parts, ctl, hctl, stream);
+  return dg;
+}
+
+static void compact_groups(DenseGroups& dg, const ColView& kc, int key_kind, int n_parts, BufferPtr ctl, BufferPtr hctl, cudaStream_t stream) {
   unsigned int* part_counts = (unsigned int*)((char*)ctl.get() + 16);
   unsigned int* part_cursor = (unsigned int*)((char*)ctl.get() + 16 + 128);
+  ARK_CUDA(cudaMemsetAsync(part_counts, 0, 256, stream));
   dg.slots = device_alloc((size_t)std::max<unsigned int>(dg.n_groups, 1) * 4);
   dg.part_rows.assign(n_parts, 0);
   const int sgrid = (int)std::min<unsigned long long>((dg.capacity + 255) / 256, 148ull * 8);
   if (n_parts > 1) {
     {
       KernelTimer t("agg_count_parts_kernel", stream);
-      agg_count_parts_kernel<<<sgrid, 256, 0, stream>>>((const uint8_t*)dg.table.get(), dg.stride, dg.capacity, kc, ex.key_kind, n_parts, part_counts);
+      agg_count_parts_kernel<<<sgrid, 256, 0, stream>>>((const uint8_t*)dg.table.get(), dg.stride, dg.capacity, kc, key_kind, n_parts, part_counts);
     }
     ARK_CUDA(cudaMemcpyAsync((char*)hctl.get() + 16, part_counts, 128, cudaMemcpyDeviceToHost, stream));
     ARK_CUDA(cudaStreamSynchronize(stream));
@@ -459,21 +424,19 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
   }
   if (dg.n_groups > 0) {
     KernelTimer t("agg_compact_kernel", stream);
-    agg_compact_kernel<<<sgrid, 256, 0, stream>>>((const uint8_t*)dg.table.get(), dg.stride, dg.capacity, kc, ex.key_kind, n_parts, part_cursor,
+    agg_compact_kernel<<<sgrid, 256, 0, stream>>>((const uint8_t*)dg.table.get(), dg.stride, dg.capacity, kc, key_kind, n_parts, part_cursor,
                                                   (unsigned int*)dg.slots.get());
   }
   ARK_CUDA(cudaGetLastError());
-  return dg;
 }
 
 // key column of the dense groups
-static Column emit_key_column(const AggExec& ex, const DenseGroups& dg, const Column& src, const std::string& name,
+// kc: the column long keys (> 12 bytes) point into; may_null: emit a validity bitmap
+static Column emit_key_column(const AggExec& ex, const DenseGroups& dg, const ColView& kc, bool may_null, const std::string& name,
                               bool nullable, cudaStream_t stream) {
   const unsigned int G = dg.n_groups;
   Column c;
   c.field.name = name; c.field.type = ex.key_type; c.field.nullable = nullable; c.length = G;
-  const ColView kc = src.view();
-  const bool may_null = src.validity != nullptr;
   BufferPtr valid_bytes = may_null ? device_alloc(std::max<size_t>(G, 1)) : BufferPtr();
   const unsigned grid = (unsigned)ceil_div(std::max<unsigned int>(G, 1), 256);
   const uint8_t* keys = (const uint8_t*)dg.table.get();
@@ -530,12 +493,17 @@ static Column emit_key_column(const AggExec& ex, const DenseGroups& dg, const Co
   return c;
 }
 
+static Column emit_key_column(const AggExec& ex, const DenseGroups& dg, const Column& src, const std::string& name,
+                              bool nullable, cudaStream_t stream) {
+  return emit_key_column(ex, dg, src.view(), src.validity != nullptr, name, nullable, stream);
+}
+
 static BufferPtr gather_acc(const DenseGroups& dg, int acc, cudaStream_t stream) {
   const unsigned int G = dg.n_groups;
   BufferPtr out = device_alloc((size_t)std::max<unsigned int>(G, 1) * 8);
   if (G) {
     KernelTimer t("agg_gather_acc_kernel", stream);
-    agg_gather_acc_kernel<<<(unsigned)ceil_div(G, 256), 256, 0, stream>>>((const uint8_t*)dg.table.get(), dg.stride, dg.acc_offsets[acc],
+    agg_gather_acc_kernel<<<(unsigned)ceil_div(G, 256), 256, 0, stream>>>((const uint8_t*)dg.table.get(), dg.stride, acc,
                                                                          (const unsigned int*)dg.slots.get(), G, (unsigned long long*)out.get());
   }
   return out;
@@ -705,12 +673,131 @@ Batch run_final_aggregate(const Plan& plan, Batch& partial, cudaStream_t stream)
   }
   Plan mp;
   mp.kind = Plan::Aggregate;
+  mp.hints = plan.final_hints;  // the merge table's size carries over from batch to batch like the partial side's
   for (size_t i = 0; i < partial.cols.size(); ++i) mp.used_cols.push_back((int)i);
   if ((int)mp.used_cols.size() > MAX_COLS) fail(ARK_ERR_UNSUPPORTED, "too many accumulator columns");
   DenseGroups dg = hash_pass(mp, mx, partial, 1, stream);
   Batch out = project_groups(plan, mx, outs, dg, key_cols ? &partial.cols[0] : nullptr, stream);
   ARK_CUDA(cudaStreamSynchronize(stream));
   return out;
+}
+
+// ---- device-side exchange (group_exchange.cu): partial table → push over NVLink → merge → result --------------
+// Push phase: build this rank's partial table and push its slots into the owners' receive regions.
+void run_group_by_push(const Plan& plan, Batch& in, DistCtx& d, cudaStream_t stream) {
+  AggExec ex;
+  std::vector<AggOutput> outs;
+  build_exec(plan, nullptr, ex, outs);  // accumulator layout from the schema alone: identical on every rank
+  DenseGroups dg = hash_pass(plan, ex, in, 1, stream, /*compact=*/false);
+  launch_exchange_push((const uint8_t*)dg.table.get(), dg.capacity, (int)ex.accs.size(), ex.key_kind, d.peers, d.world, d.rank, d.step, d.region_bytes, stream);
+  ARK_CUDA(cudaGetLastError());
+  ARK_CUDA(cudaStreamSynchronize(stream));  // the table is released when dg goes out of scope
+}
+
+// Merge phase: wait for every source's records, merge them into the final table, acknowledge, project the result.
+// Returns false (on every rank alike) when some source held keys that cannot travel inline; the step is still
+// acknowledged, so the caller can fall back to the descriptor exchange for this batch.
+bool run_group_by_merge(const Plan& plan, DistCtx& d, Batch& out, cudaStream_t stream) {
+  AggExec ex;
+  std::vector<AggOutput> outs;
+  build_exec(plan, nullptr, ex, outs);
+  AggExec mx;  // same accumulators, merged instead of fed (sum of sums and counts, min of mins, …)
+  mx.key_kind = ex.key_kind; mx.key_slot = 0; mx.key_type = ex.key_type;
+  int32_t kinds[AGG_MAX_ACC] = {0};
+  for (size_t a = 0; a < ex.accs.size(); ++a) {
+    AccPlan m;
+    switch (ex.accs[a].kind) {
+      case ACC_COUNT_STAR: case ACC_COUNT: case ACC_SUM_I64: m.kind = ACC_SUM_I64; break;
+      case ACC_SUM_F64: m.kind = ACC_SUM_F64; m.arg_is_f64 = true; break;
+      case ACC_MIN_I64: case ACC_MIN_F64: m.kind = ACC_MIN_I64; break;
+      default: m.kind = ACC_MAX_I64; break;
+    }
+    mx.accs.push_back(m);
+    kinds[a] = m.kind;
+  }
+  AggHints& hints = *plan.final_hints;
+  unsigned long long capacity = std::max<unsigned long long>(hints.capacity.load(), 1ull << 10);
+  DenseGroups dg;
+  dg.stride = table_bucket_stride((int)ex.accs.size());
+  BufferPtr ctl = device_alloc(512), hctl = pinned_alloc(512);
+  bool poisoned = false;
+  while (true) {
+    dg.table = device_alloc((size_t)table_bytes(capacity, (int)ex.accs.size()));
+    ARK_CUDA(cudaMemsetAsync(ctl.get(), 0, 512, stream));
+    {
+      AccParam ap[AGG_MAX_ACC];
+      memset(ap, 0, sizeof ap);
+      for (size_t a = 0; a < mx.accs.size(); ++a) { ap[a].kind = mx.accs[a].kind; ap[a].acc_index = (int)a; }
+      KernelTimer t("agg_init_kernel", stream);
+      const int grid = (int)std::min<unsigned long long>((capacity + 255) / 256, 148ull * 8);
+      agg_init_kernel<<<grid, 256, 0, stream>>>((uint8_t*)dg.table.get(), capacity, dg.stride, (int)mx.accs.size(), ap[0], ap[1], ap[2], ap[3], ap[4],
+                                                ap[5], ap[6], ap[7]);
+    }
+    // ctl: [group_count u32 | overflow i32 | status i32 | pad | total u64 @ 272]
+    launch_exchange_merge((uint8_t*)dg.table.get(), capacity, (int)mx.accs.size(), kinds, d.comm, d.world, d.rank, d.step, d.region_bytes,
+                          (unsigned int*)ctl.get(), (int32_t*)((char*)ctl.get() + 4), (int32_t*)((char*)ctl.get() + 8),
+                          (unsigned long long*)((char*)ctl.get() + 272), stream);
+    ARK_CUDA(cudaGetLastError());
+    ARK_CUDA(cudaMemcpyAsync(hctl.get(), ctl.get(), 16, cudaMemcpyDeviceToHost, stream));
+    ARK_CUDA(cudaMemcpyAsync((char*)hctl.get() + 16, (char*)ctl.get() + 272, 8, cudaMemcpyDeviceToHost, stream));
+    ARK_CUDA(cudaStreamSynchronize(stream));
+    const unsigned int groups = *(unsigned int*)hctl.get();
+    const int overflow = *(int32_t*)((char*)hctl.get() + 4);
+    const int status = *(int32_t*)((char*)hctl.get() + 8);
+    const unsigned long long total = *(unsigned long long*)((char*)hctl.get() + 16);
+    if (status & 2) {
+      launch_exchange_ack(d.peers, d.world, d.rank, d.step, stream);
+      ARK_CUDA(cudaStreamSynchronize(stream));
+      fail(ARK_ERR_PROCESS, "Collection query results error: a rank's partial states exceed the exchange region (ark_dist_create region_bytes)");
+    }
+    if (status & 1) { poisoned = true; break; }
+    const unsigned long long max_groups = capacity - capacity / 4;
+    if (overflow || groups > max_groups) {  // the records stay in the receive region until the ack: merge again into a larger table
+      if (capacity >= (1ull << 31)) fail(ARK_ERR_PROCESS, "Collection query results error: group-by hash table exceeded 2^31 slots");
+      capacity = std::max(capacity * 4, (unsigned long long)1 << 10);
+      while (capacity < 2 * total) capacity <<= 1;
+      continue;
+    }
+    dg.n_groups = groups;
+    dg.capacity = capacity;
+    unsigned long long want = 1ull << 10;
+    while (want < 2ull * groups) want <<= 1;
+    hints.capacity.store(want);
+    hints.groups.store(groups);
+    break;
+  }
+  launch_exchange_ack(d.peers, d.world, d.rank, d.step, stream);
+  ARK_CUDA(cudaGetLastError());
+  if (poisoned) { ARK_CUDA(cudaStreamSynchronize(stream)); return false; }
+  compact_groups(dg, ColView{}, mx.key_kind, 1, ctl, hctl, stream);
+  // project: key column straight from the inline keys, aggregates from the merged accumulators
+  const unsigned int G = dg.n_groups;
+  out = Batch();
+  out.num_rows = G;
+  std::vector<BufferPtr> dense(mx.accs.size());
+  auto dense_acc = [&](int a) -> BufferPtr { if (!dense[a]) dense[a] = gather_acc(dg, a, stream); return dense[a]; };
+  for (const PostItem& pi : plan.post) {
+    if (pi.kind == PostItem::Key) {
+      const Field& kf = plan.input_fields[plan.used_cols[plan.keys[0].slot]];
+      out.cols.push_back(emit_key_column(mx, dg, ColView{}, kf.nullable, pi.name, kf.nullable, stream));
+    } else if (pi.kind == PostItem::Agg) {
+      const AggOutput& o = outs[pi.index];
+      const AggSpec& sp = plan.aggs[pi.index];
+      const bool is_count = sp.func == AggFunc::Count || sp.func == AggFunc::CountStar;
+      BufferPtr cnt = o.count_acc >= 0 ? dense_acc(o.count_acc) : BufferPtr();
+      const bool can_be_null = !is_count && o.count_acc >= 0 && (o.can_be_null || mx.key_kind == KEY_NONE);
+      Column col = finalize_column(pi.name, o.type, o.final_op, dense_acc(o.value_acc), cnt, 0, can_be_null, G, stream);
+      col.field.nullable = !is_count;
+      if (pi.cast_utf8) col = format_int64_column(col, pi.name, stream);
+      out.cols.push_back(col);
+    } else {
+      if (pi.lit_type == DType::Utf8) fail(ARK_ERR_UNSUPPORTED, "string literal in an aggregate SELECT list");
+      if (pi.lit_type == DType::Bool) fail(ARK_ERR_UNSUPPORTED, "boolean literal in an aggregate SELECT list");
+      out.cols.push_back(finalize_column(pi.name, pi.lit_type, FIN_CONST, BufferPtr(), BufferPtr(), pi.lit_bits, false, G, stream));
+    }
+  }
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  return true;
 }
 
 }  // namespace ark

@@ -230,11 +230,10 @@ __global__ void __launch_bounds__(1024) agg_radix_bucket_kernel(const __grid_con
   __syncthreads();
 
   // ---- region → global table (the layout hash_agg_kernel builds); empty slots carry the EMPTY key ----
-  uint8_t* region = P.table + ((unsigned long long)b << R.log2_slots) * (unsigned long long)P.slot_stride;
+  const unsigned long long region0 = (unsigned long long)b << R.log2_slots;  // first slot of this bucket's region
   for (int s = tid; s < S; s += nthreads) {
-    uint8_t* slot = region + (size_t)s * P.slot_stride;
-    *reinterpret_cast<Key16*>(slot) = K[s];
-    for (int a = 0; a < P.n_acc; ++a) *reinterpret_cast<unsigned long long*>(slot + P.accs[a].acc_offset) = ACC[a * S + s];
+    *tbl_key(P.table, region0 + s, P.bucket_stride) = K[s];
+    for (int a = 0; a < P.n_acc; ++a) *tbl_acc(P.table, region0 + s, a, P.bucket_stride) = ACC[a * S + s];
   }
   if (tid == 0) {
     const unsigned int g = s_groups;

@@ -8,9 +8,9 @@
 //   * a CTA stays resident and takes 256·R-row tiles; the loads of the NEXT tile (offsets / Int64 keys / predicate
 //     column into registers, the tile's key bytes by one 1-D TMA bulk copy into the other half of a two-stage ring)
 //     are issued before the current tile is touched, so the only latency on a row's critical path is the table's;
-//   * every thread owns R consecutive rows and probes them in LOCKSTEP: all R slot loads are issued, then each trip
-//     of the loop inspects every unresolved row and issues its next probe — R independent L2 chains per thread
-//     instead of one (the R > 1 form of hash_agg_kernel resolved its rows serially, which is why it was slower);
+//   * every thread owns R consecutive rows: the home BUCKETS of all R rows (four keys each, hash_agg.cuh) are requested
+//     before any is inspected — R independent L2 requests per thread — and a row that is not settled by its home
+//     bucket (4 % of the rows at load 0.48) continues with table_find_or_claim;
 //   * aggregate arguments are fetched with 16-byte loads while the probes are in flight.
 // Table layout, key encoding, claim protocol (128-bit CAS), accumulators (fire-and-forget REDs) and the overflow /
 // group-count protocol are exactly hash_agg_kernel's, so everything downstream (compaction, emit, multi-GPU
@@ -30,19 +30,21 @@ namespace {
 constexpr int HS_THREADS = 256;
 constexpr int HS_PRE = 2;  // aggregate arguments prefetched into registers per tile (further ones are loaded in place)
 
-__device__ __forceinline__ Key16* hs_slot(uint8_t* table, unsigned slot, int stride) {
-  return reinterpret_cast<Key16*>(table + (unsigned long long)slot * (unsigned long long)stride);
-}
 
 template <int R>
 __device__ __forceinline__ void ld_vec_u64(const unsigned long long* src, bool fast, int lr0, int rows, unsigned long long (&v)[R]) {
-  if (fast) {
-#pragma unroll
-    for (int j = 0; j < R; j += 2)
-      asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v[j]), "=l"(v[j + 1]) : "l"(src + j));
+  if constexpr (R == 1) {
+    v[0] = 0;
+    if (lr0 < rows) asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v[0]) : "l"(src));
   } else {
+    if (fast) {
 #pragma unroll
-    for (int j = 0; j < R; ++j) v[j] = (lr0 + j < rows) ? src[j] : 0;
+      for (int j = 0; j < R; j += 2)
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v[j]), "=l"(v[j + 1]) : "l"(src + j));
+    } else {
+#pragma unroll
+      for (int j = 0; j < R; ++j) v[j] = (lr0 + j < rows) ? src[j] : 0;
+    }
   }
 }
 
@@ -50,7 +52,8 @@ template <int R>
 __device__ __forceinline__ void ld_vec_off(const int32_t* os, bool fast, int lr0, int rows, int lane, int (&off)[R], int* offx) {
   if (fast) {
     if constexpr (R == 4) asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(off[0]), "=r"(off[1]), "=r"(off[2]), "=r"(off[3]) : "l"(os));
-    else asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(off[0]), "=r"(off[1]) : "l"(os));
+    else if constexpr (R == 2) asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(off[0]), "=r"(off[1]) : "l"(os));
+    else asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(off[0]) : "l"(os));
   } else {
 #pragma unroll
     for (int j = 0; j < R; ++j) off[j] = (lr0 + j <= rows) ? os[j] : 0;
@@ -58,7 +61,8 @@ __device__ __forceinline__ void ld_vec_off(const int32_t* os, bool fast, int lr0
   *offx = ((lane == 31 || lr0 + R >= rows) && lr0 + R <= rows) ? os[R] : 0;
 }
 
-template <int KEYK, int PRED, int R>
+// SIG 1: the accumulators are exactly {COUNT(*), SUM(<non-null Int64 column>)} (config 3): two REDs, no dispatch.
+template <int KEYK, int PRED, int R, int SIG>
 __global__ void __launch_bounds__(HS_THREADS) hash_agg_stream_kernel(const __grid_constant__ AggParams P, const int str_cap) {
   constexpr int TR = HS_THREADS * R;
   constexpr int PRODUCER = HS_THREADS - 32;
@@ -71,8 +75,8 @@ __global__ void __launch_bounds__(HS_THREADS) hash_agg_stream_kernel(const __gri
   const int lr0 = R * tid;
   const int stage_bytes = str_cap + 32;
   const ColView& kc = P.cols[P.key_slot];
-  const unsigned mask = (unsigned)P.mask;
-  const int stride = P.slot_stride;
+  const unsigned long long bmask = P.mask >> 2;
+  const int bstride = P.bucket_stride;
   auto tile_rows = [&](int t) { const int64_t r = n - (int64_t)t * TR; return (int)(r < TR ? r : TR); };
   auto issue_window = [&](int st, int32_t o0, int32_t o1) {
     const uintptr_t a0 = reinterpret_cast<uintptr_t>((const uint8_t*)kc.data + o0), a1 = reinterpret_cast<uintptr_t>((const uint8_t*)kc.data + o1);
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(HS_THREADS) hash_agg_stream_kernel(const __gri
     }
     // ---- keys ----
     Key16 mine[R];
-    unsigned slot[R];
+    unsigned home[R];
     if (KEYK == KEY_BYTES) {
       off[R] = __shfl_down_sync(0xffffffffu, off[0], 1);
       if ((lane == 31 || lr0 + R >= rows) && lr0 + R <= rows) off[R] = offx;
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(HS_THREADS) hash_agg_stream_kernel(const __gri
       const uint8_t* in_bytes = smem + st * stage_bytes;
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-        slot[j] = 0;
+        home[j] = 0;
         if (!((ok >> j) & 1)) continue;
         const int64_t row = row0 + lr0 + j;
         unsigned h32;
@@ -200,16 +204,16 @@ __global__ void __launch_bounds__(HS_THREADS) hash_agg_stream_kernel(const __gri
           if (lp) { const unsigned long long h = hash_bytes(lp, llen); h32 = (unsigned)(h >> 32) ^ (unsigned)h; }
           else h32 = hash32_key16(mine[j]);
         }
-        slot[j] = (h32 * 0x9E3779B1u) & mask;
+        home[j] = (unsigned)((h32 * 0x9E3779B1u) & bmask);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-        slot[j] = 0;
+        home[j] = 0;
         if (!((ok >> j) & 1)) continue;
         if (col_valid(kc, row0 + lr0 + j)) { mine[j].lo = kv[j]; mine[j].hi = (unsigned long long)KEYTAG_INT << 32; }
         else { mine[j].lo = 0; mine[j].hi = (unsigned long long)KEYTAG_NULL << 32; }
-        slot[j] = (hash32_key16(mine[j]) * 0x9E3779B1u) & mask;
+        home[j] = (unsigned)((hash32_key16(mine[j]) * 0x9E3779B1u) & bmask);
       }
     }
     // this stage's key bytes are in registers: the producer may refill it in the iteration after next.  The barrier
@@ -219,42 +223,60 @@ __global__ void __launch_bounds__(HS_THREADS) hash_agg_stream_kernel(const __gri
       if (KEYK == KEY_BYTES && next < n_tiles && s_str_staged[st ^ 1]) mbar_wait(&s_bar[st ^ 1], (ph >> (st ^ 1)) & 1);
       break;
     }
-    // ---- probes in lockstep ----
-    Key16 cur[R];
+    // ---- home buckets of all R rows requested at once ----
+    Key16 kb[R][TBL_B];
 #pragma unroll
-    for (int j = 0; j < R; ++j) if ((ok >> j) & 1) cur[j] = ld128(hs_slot(P.table, slot[j], stride));
-    unsigned pending = ok;
-    int trips = 0;
-    while (pending) {
+    for (int j = 0; j < R; ++j) {
+      if (!((ok >> j) & 1)) continue;
+      const Key16* b = reinterpret_cast<const Key16*>(P.table + (unsigned long long)home[j] * (unsigned long long)bstride);
 #pragma unroll
-      for (int j = 0; j < R; ++j) {
-        if (!((pending >> j) & 1)) continue;
-        Key16 c = cur[j];
-        bool done = false;
+      for (int i = 0; i < TBL_B; ++i) kb[j][i] = ld128(b + i);
+    }
+    unsigned long long slot[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      slot[j] = ~0ull;
+      if (!((ok >> j) & 1)) continue;
+      Key16* b = reinterpret_cast<Key16*>(P.table + (unsigned long long)home[j] * (unsigned long long)bstride);
+      bool done = false;
+#pragma unroll
+      for (int i = 0; i < TBL_B; ++i) {
+        if (done) continue;
+        Key16 c = kb[j][i];
         if (c.hi == KEY_EMPTY) {
-          c = cas128(hs_slot(P.table, slot[j], stride), Key16{KEY_EMPTY, KEY_EMPTY}, mine[j]);
-          if (c.hi == KEY_EMPTY && c.lo == KEY_EMPTY) { ++claimed; done = true; }
+          c = cas128(b + i, Key16{KEY_EMPTY, KEY_EMPTY}, mine[j]);
+          if (c.hi == KEY_EMPTY && c.lo == KEY_EMPTY) { ++claimed; done = true; slot[j] = (unsigned long long)home[j] * TBL_B + i; continue; }
         }
-        if (!done && key_equal(mine[j], c, kc, kc)) done = true;
-        if (done) pending &= ~(1u << j);
-        else { slot[j] = (slot[j] + 1) & mask; cur[j] = ld128(hs_slot(P.table, slot[j], stride)); }
+        if (key_equal(mine[j], c, kc, kc)) { done = true; slot[j] = (unsigned long long)home[j] * TBL_B + i; }
       }
-      if (++trips > 512 && pending) { err_overflow = 1; ok &= ~pending; pending = 0; }  // table too loaded for this batch
+      if (!done) {  // the home bucket is full of other keys: walk on
+        slot[j] = table_find_or_claim(P.table, bmask, bstride, (unsigned long long)home[j] + 1, mine[j], kc, kc, &claimed);
+        if (slot[j] == ~0ull) { err_overflow = 1; ok &= ~(1u << j); }  // table too loaded for this batch
+      }
     }
     // ---- accumulate (fire-and-forget REDs) ----
-    for (int a = 0; a < P.n_acc; ++a) {
-      const AccParam& A = P.accs[a];
+    if (SIG == 1) {
 #pragma unroll
       for (int j = 0; j < R; ++j) {
         if (!((ok >> j) & 1)) continue;
-        unsigned long long bits = 0;
-        bool valid = true;
-        if (A.kind != ACC_COUNT_STAR) {
-          const ColView& c = P.cols[A.arg_slot];
-          valid = col_valid(c, row0 + lr0 + j);
-          bits = a == pre_acc[0] ? av[0][j] : (a == pre_acc[1] ? av[1][j] : __ldcs((const unsigned long long*)c.data + row0 + lr0 + j));
+        atomicAdd(tbl_acc(P.table, slot[j], 0, bstride), 1ull);
+        atomicAdd(tbl_acc(P.table, slot[j], 1, bstride), av[0][j]);
+      }
+    } else {
+      for (int a = 0; a < P.n_acc; ++a) {
+        const AccParam& A = P.accs[a];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          if (!((ok >> j) & 1)) continue;
+          unsigned long long bits = 0;
+          bool valid = true;
+          if (A.kind != ACC_COUNT_STAR) {
+            const ColView& c = P.cols[A.arg_slot];
+            valid = col_valid(c, row0 + lr0 + j);
+            bits = a == pre_acc[0] ? av[0][j] : (a == pre_acc[1] ? av[1][j] : __ldcs((const unsigned long long*)c.data + row0 + lr0 + j));
+          }
+          if (valid) accumulate(A.kind, A.arg_is_f64, tbl_acc(P.table, slot[j], a, bstride), bits);
         }
-        if (valid) accumulate(A.kind, A.arg_is_f64, reinterpret_cast<unsigned long long*>(P.table + (unsigned long long)slot[j] * stride + A.acc_offset), bits);
       }
     }
   }
@@ -273,7 +295,7 @@ bool launch_hash_agg_stream(const AggParams& P, unsigned long long capacity, int
   if (capacity > (1ull << 31) || P.n_rows <= 0) return false;
   for (int a = 0; a < P.n_acc; ++a) if (P.accs[a].arg_prog >= 0) return false;
   if (P.pred_kind == 1 && (reinterpret_cast<uintptr_t>(P.cols[P.sp_slot].data) & 7)) return false;
-  static const int rows_per_thread = [] { const char* e = getenv("ARK_AGG_STREAM_R"); return e && atoi(e) == 2 ? 2 : 4; }();
+  static const int rows_per_thread = [] { const char* e = getenv("ARK_AGG_STREAM_R"); const int v = e ? atoi(e) : 2; return v == 1 || v == 4 ? v : 2; }();
   const int R = rows_per_thread;
   const int TR = HS_THREADS * R;
   int cap = 0;
@@ -284,11 +306,15 @@ bool launch_hash_agg_stream(const AggParams& P, unsigned long long capacity, int
     cap = std::max(2048, std::min(cap, 48 * 1024));
   }
   const size_t smem = cap ? 2 * (size_t)(cap + 32) : 0;
+  // {COUNT(*), SUM(non-null Int64 column)}: the specialised accumulate
+  const bool sig1 = P.n_acc == 2 && P.accs[0].kind == ACC_COUNT_STAR && P.accs[1].kind == ACC_SUM_I64 && P.cols[P.accs[1].arg_slot].validity == nullptr;
   const void* fn = nullptr;
-#define ARK_HS_FN(K, PR) (R == 2 ? (const void*)hash_agg_stream_kernel<K, PR, 2> : (const void*)hash_agg_stream_kernel<K, PR, 4>)
+#define ARK_HS_R(K, PR, S) (R == 1 ? (const void*)hash_agg_stream_kernel<K, PR, 1, S> : R == 4 ? (const void*)hash_agg_stream_kernel<K, PR, 4, S> : (const void*)hash_agg_stream_kernel<K, PR, 2, S>)
+#define ARK_HS_FN(K, PR) (sig1 ? ARK_HS_R(K, PR, 1) : ARK_HS_R(K, PR, 0))
   if (P.key_kind == KEY_BYTES) fn = P.pred_kind ? ARK_HS_FN(KEY_BYTES, 1) : ARK_HS_FN(KEY_BYTES, 0);
   else fn = P.pred_kind ? ARK_HS_FN(KEY_INT64, 1) : ARK_HS_FN(KEY_INT64, 0);
 #undef ARK_HS_FN
+#undef ARK_HS_R
   ARK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (48 * 1024 + 32)));
   int occ = 0;
   ARK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, HS_THREADS, smem));

@@ -105,8 +105,9 @@ __global__ void __launch_bounds__(HT_THREADS, 3) hash_agg_tile_kernel(const __gr
     if (P.key_kind == KEY_NONE && blockIdx.x == 0) {  // a global aggregate always yields one row
       Key16 mine; unsigned long long h;
       make_key(KEY_NONE, kc, 0, &mine, &h);
-      Key16 cur = cas128(reinterpret_cast<Key16*>(P.table + (h & P.mask) * (unsigned long long)P.slot_stride), Key16{KEY_EMPTY, KEY_EMPTY}, mine);
-      if (cur.hi == KEY_EMPTY && cur.lo == KEY_EMPTY) atomicAdd(P.group_count, 1u);
+      unsigned int c = 0;
+      table_find_or_claim(P.table, P.mask >> 2, P.bucket_stride, h, mine, kc, kc, &c);
+      if (c) atomicAdd(P.group_count, c);
     }
   }
   const int copies = tiny ? HT_THREADS / 32 : 1;
@@ -245,29 +246,17 @@ __global__ void __launch_bounds__(HT_THREADS, 3) hash_agg_tile_kernel(const __gr
   for (int s = tid; s < S; s += HT_THREADS) {
     const Key16 mine = K[s];
     if (mine.hi == KEY_EMPTY) continue;
-    unsigned long long g = (P.key_kind == KEY_NONE ? 0ull : stored_key_hash(mine, kc)) & P.mask;
-    int probes = 0;
-    bool placed = false;
-    while (true) {
-      Key16* sk = reinterpret_cast<Key16*>(P.table + g * (unsigned long long)P.slot_stride);
-      Key16 c = ld128(sk);
-      if (c.hi == KEY_EMPTY) {
-        c = cas128(sk, Key16{KEY_EMPTY, KEY_EMPTY}, mine);
-        if (c.hi == KEY_EMPTY && c.lo == KEY_EMPTY) {
-          const unsigned cnt = atomicAdd(P.group_count, 1u);
-          if (cnt >= P.max_groups) atomicExch(P.overflow, 1);
-          placed = true; break;
-        }
-      }
-      if (key_equal(mine, c, kc, kc)) { placed = true; break; }
-      g = (g + 1) & P.mask;
-      if (++probes > 4096) { atomicExch(P.overflow, 1); break; }
+    unsigned int c = 0;
+    const unsigned long long g = table_find_or_claim(P.table, P.mask >> 2, P.bucket_stride, P.key_kind == KEY_NONE ? 0ull : stored_key_hash(mine, kc),
+                                                     mine, kc, kc, &c, 1024);
+    if (g == ~0ull) { atomicExch(P.overflow, 1); continue; }
+    if (c) {
+      const unsigned cnt = atomicAdd(P.group_count, 1u);
+      if (cnt >= P.max_groups) atomicExch(P.overflow, 1);
     }
-    if (!placed) continue;
     for (int a = 0; a < P.n_acc; ++a) {
       const unsigned long long v = ACC[a * S + s];
-      if (v != acc_identity(P.accs[a].kind))
-        merge_acc(P.accs[a].kind, reinterpret_cast<unsigned long long*>(P.table + g * (unsigned long long)P.slot_stride + P.accs[a].acc_offset), v);
+      if (v != acc_identity(P.accs[a].kind)) merge_acc(P.accs[a].kind, tbl_acc(P.table, g, a, P.bucket_stride), v);
     }
   }
 }

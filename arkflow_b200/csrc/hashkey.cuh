@@ -165,4 +165,31 @@ static __device__ __forceinline__ void make_key_smem(const uint8_t* p, int len, 
 }
 
 
+// Finds the slot of `mine` in the bucketed table or claims the first free lane on its probe path (buckets home,
+// home + 1, …; lanes 0..3 in order, so a key is always met before any empty lane after it).  `mc` / `sc`: the
+// columns long keys of the prober / of stored keys point into.  Returns the slot, or ~0 when `max_buckets` buckets
+// were full of other keys (table too loaded: the host retries with more slots).
+static __device__ __forceinline__ unsigned long long table_find_or_claim(uint8_t* table, unsigned long long bucket_mask, int bstride,
+                                                                         unsigned long long home, Key16 mine, const ColView& mc, const ColView& sc,
+                                                                         unsigned int* claimed, int max_buckets = 128) {
+  unsigned long long b = home & bucket_mask;
+  for (int probes = 0; probes < max_buckets; ++probes) {
+    Key16* kb = reinterpret_cast<Key16*>(table + b * (unsigned long long)bstride);
+    Key16 k[TBL_B];
+#pragma unroll
+    for (int i = 0; i < TBL_B; ++i) k[i] = ld128(kb + i);
+#pragma unroll
+    for (int i = 0; i < TBL_B; ++i) {
+      Key16 c = k[i];
+      if (c.hi == KEY_EMPTY) {
+        c = cas128(kb + i, Key16{KEY_EMPTY, KEY_EMPTY}, mine);
+        if (c.hi == KEY_EMPTY && c.lo == KEY_EMPTY) { ++*claimed; return b * TBL_B + i; }
+      }
+      if (key_equal(mine, c, mc, sc)) return b * TBL_B + i;
+    }
+    b = (b + 1) & bucket_mask;
+  }
+  return ~0ull;
+}
+
 }  // namespace ark

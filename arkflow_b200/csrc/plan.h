@@ -102,6 +102,7 @@ struct Plan {
   std::vector<AggSpec> aggs;
   std::vector<PostItem> post;
   std::shared_ptr<AggHints> hints = std::make_shared<AggHints>();
+  std::shared_ptr<AggHints> final_hints = std::make_shared<AggHints>();  // table of the multi-GPU final merge
   // Join (two tables, inner equi-join)
   std::string left_table, right_table;
   std::vector<Field> right_fields;

@@ -72,6 +72,35 @@ class NativeEngine:
     def process(self, batch: DeviceBatch) -> Optional[DeviceBatch]:
         return self.proc.process_device(batch)
 
+    # ---- device-side exchange (csrc/group_exchange.cu) ----
+    def group_by_push(self, batch: DeviceBatch, ctx: "ExchangeContext") -> None:
+        from .arrow_ffi import release_array, release_schema
+        from .processor import _check
+
+        dev, sch = batch.export()
+        try:
+            status = L.lib().ark_sql_group_by_push_device(self.proc._h, ctx._h, C.byref(dev), C.byref(sch))
+        finally:
+            release_schema(sch)
+            release_array(dev.array)
+        _check(status)
+
+    def group_by_merge(self, ctx: "ExchangeContext") -> Optional[DeviceBatch]:
+        """This rank's share of the groups, or None when some rank held a key that cannot travel inline (every rank
+        gets None for that step and falls back to the descriptor exchange)."""
+        from .processor import _check
+
+        out_dev, out_sch = L.ArrowDeviceArray(), L.ArrowSchema()
+        status = L.lib().ark_sql_group_by_merge_device(self.proc._h, ctx._h, C.byref(out_dev), C.byref(out_sch))
+        if status == L.ARK_ERR_UNSUPPORTED:
+            return None
+        _check(status)
+        return DeviceBatch.adopt(out_dev, out_sch)
+
+    def group_by_exchange(self, batch: DeviceBatch, ctx: "ExchangeContext") -> Optional[DeviceBatch]:
+        self.group_by_push(batch, ctx)
+        return self.group_by_merge(ctx)
+
     def hash_partition(self, batch: DeviceBatch, key_column: str, n_parts: int):
         from .arrow_ffi import release_array, release_schema
         from .processor import _check
@@ -90,6 +119,60 @@ class NativeEngine:
 
     def join(self, tables: dict) -> DeviceBatch:
         return self.proc.process_tables_device(tables)
+
+
+class ExchangeContext:
+    """One rank's end of the device-side GROUP BY exchange (include/arkflow_b200.h: ark_dist_*).  `region_bytes` must
+    hold the partial states one source sends this rank in one step (32 bytes per group for up to two accumulators)."""
+
+    def __init__(self, rank: int, world: int, region_bytes: int):
+        from .processor import _check
+
+        self.rank, self.world, self.region_bytes = rank, world, region_bytes
+        self._h = C.c_void_p()
+        _check(L.lib().ark_dist_create(rank, world, region_bytes, C.byref(self._h)))
+
+    def handle(self) -> bytes:
+        from .processor import _check
+
+        n = int(L.lib().ark_dist_handle_bytes())
+        blob = (C.c_uint8 * n)()
+        size = C.c_int64(0)
+        _check(L.lib().ark_dist_export(self._h, blob, n, C.byref(size)))
+        return bytes(blob[: size.value])
+
+    def connect(self, handles: list) -> None:
+        from .processor import _check
+
+        assert len(handles) == self.world
+        stride = len(handles[0])
+        buf = (C.c_uint8 * (stride * self.world)).from_buffer_copy(b"".join(handles))
+        _check(L.lib().ark_dist_connect(self._h, buf, stride))
+
+    @classmethod
+    def from_process_group(cls, region_bytes: int, group=None) -> "ExchangeContext":
+        """One context per rank of a torch.distributed group; the handles travel in one all_gather."""
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ctx = cls(rank, world, region_bytes)
+        mine = torch.frombuffer(bytearray(ctx.handle()), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            mine = mine.cuda()
+        everyone = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(everyone, mine, group=group)
+        ctx.connect([bytes(t.cpu().numpy()) for t in everyone])
+        dist.barrier(group)
+        return ctx
+
+    def close(self) -> None:
+        if self._h:
+            L.lib().ark_dist_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---------------------------------------------------------------------------------------------
@@ -235,10 +318,18 @@ def _exchange(batch: DeviceBatch, part_rows: list[int], group, p2p: Optional[boo
     return exchange_partitions(batch, part_rows, group)
 
 
-def distributed_group_by(engine, local_batch: DeviceBatch, group=None, p2p: Optional[bool] = None) -> DeviceBatch:
+def distributed_group_by(engine, local_batch: DeviceBatch, group=None, p2p: Optional[bool] = None,
+                         ctx: Optional[ExchangeContext] = None) -> DeviceBatch:
     """GROUP BY over the union of every rank's `local_batch`; returns this rank's share of the groups
-    (group owners are disjoint, so the concatenation over ranks is the full result)."""
+    (group owners are disjoint, so the concatenation over ranks is the full result).  With an ExchangeContext the
+    partial states are pushed over NVLink by the kernel that scans the partial table and merged by the owner without
+    a host round trip (csrc/group_exchange.cu); keys that cannot travel inline make every rank fall back, for that
+    batch, to the descriptor exchange below."""
     world = dist.get_world_size(group)
+    if ctx is not None:
+        out = engine.group_by_exchange(local_batch, ctx)
+        if out is not None:
+            return out
     partial, part_rows = engine.partial_aggregate(local_batch, world)
     keyless = not partial.columns or partial.columns[0].name.startswith("__acc")
     received = _exchange(partial, part_rows, group, p2p)

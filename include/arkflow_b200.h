@@ -94,6 +94,7 @@ typedef enum ark_status {
 typedef struct ark_proc ark_proc_t; /* a built Processor (sql / json_to_arrow / arrow_to_json)       */
 typedef struct ark_buf ark_buf_t;   /* a built Buffer (memory / session_window / tumbling_window / sliding_window) */
 typedef struct ark_batcher ark_batcher_t; /* a built `batch` processor                                  */
+typedef struct ark_dist ark_dist_t; /* one rank's end of the device-side GROUP BY exchange              */
 
 /* ---- library ---- */
 /* Bind the calling process to CUDA device `device` (-1: keep current) and warm the pools.
@@ -235,6 +236,38 @@ int ark_ipc_export_device(struct ArrowDeviceArray* in, struct ArrowSchema* in_sc
 int ark_ipc_concat_slices_device(int n_src, const uint8_t* const* blobs, const int64_t* blob_sizes,
                                  const int64_t* row0, const int64_t* n_rows,
                                  struct ArrowDeviceArray* out, struct ArrowSchema* out_schema);
+
+/* ---- the GROUP BY exchange as device code (csrc/group_exchange.cu; one node, one process — or context — per GPU).
+ *      Replaces the host-orchestrated sequence partial_aggregate → export → all-gather → pull → final_aggregate
+ *      for keys that fit a table slot (Utf8/Binary up to 12 bytes, Int64, Boolean, NULL): the kernel that scans
+ *      the partial hash table PUSHES each group's {key, accumulators} slot over NVLink into the owner rank's receive
+ *      region, signals with a system-scope release store, and the owner's merge kernel consumes the records of
+ *      every source as soon as their flags arrive — no NCCL call, no host round trip and no staging copy on the
+ *      data path (DataFusion's AggregateExec(Partial) → RepartitionExec(Hash) → AggregateExec(FinalPartitioned),
+ *      reached in-process from crates/arkflow-plugin/src/processor/sql.rs:126-129).
+ *
+ *      Set-up, once per process: ark_dist_create allocates this rank's comm buffer (header + 2 × world receive
+ *      regions of region_bytes: a region must hold the partial states one source sends this rank in one step,
+ *      32 bytes per group for up to two accumulators); ark_dist_export describes it (CUDA IPC handle,
+ *      ark_dist_handle_bytes() bytes); the caller gathers every rank's handle by any means (the harness uses one
+ *      torch.distributed all_gather) and passes them, in rank order, to ark_dist_connect.
+ *      Per batch, on every rank in the same order: ark_sql_group_by_exchange_device(in) → this rank's share of the
+ *      groups (owners are disjoint: the concatenation over ranks is the full result).  The push and merge halves
+ *      are also exported separately (several ranks driven from one thread in the tests).
+ *      Returns ARK_ERR_UNSUPPORTED on EVERY rank alike when some rank met a key that cannot travel inline (longer
+ *      than 12 bytes); the step is consumed and the caller falls back to the descriptor exchange above. ---- */
+int ark_dist_create(int rank, int world, int64_t region_bytes, ark_dist_t** out);
+int64_t ark_dist_handle_bytes(void);
+int ark_dist_export(ark_dist_t* d, uint8_t* blob, int64_t blob_cap, int64_t* blob_size);
+int ark_dist_connect(ark_dist_t* d, const uint8_t* blobs, int64_t blob_stride);
+void ark_dist_destroy(ark_dist_t* d);
+int ark_sql_group_by_exchange_device(ark_proc_t* p, ark_dist_t* d, struct ArrowDeviceArray* in,
+                                     struct ArrowSchema* in_schema, struct ArrowDeviceArray* out,
+                                     struct ArrowSchema* out_schema);
+int ark_sql_group_by_push_device(ark_proc_t* p, ark_dist_t* d, struct ArrowDeviceArray* in,
+                                 struct ArrowSchema* in_schema);
+int ark_sql_group_by_merge_device(ark_proc_t* p, ark_dist_t* d, struct ArrowDeviceArray* out,
+                                  struct ArrowSchema* out_schema);
 
 /* ---- synthetic input of schema S, generated in HBM.  Bench/test support. ---- */
 /* value_kind: 0 = Int64 uniform [0,20), 1 = Float64 20*u.  key_space K: sensor = "temp_%07d" % k.

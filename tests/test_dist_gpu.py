@@ -63,6 +63,81 @@ def test_partial_exchange_final_on_one_gpu(gpu, ranks, query, keys, floats):
                 assert gv == wv, (k, name, gv, wv)
 
 
+def _exchange_contexts(ranks, region_bytes):
+    from arkflow_b200.dist import ExchangeContext
+
+    ctxs = [ExchangeContext(r, ranks, region_bytes) for r in range(ranks)]
+    handles = [c.handle() for c in ctxs]
+    for c in ctxs:
+        c.connect(handles)
+    return ctxs
+
+
+@pytest.mark.parametrize("ranks", [1, 2, 5, 8])
+@pytest.mark.parametrize("query,keys,floats", [
+    ("SELECT sensor, SUM(value), COUNT(*) FROM flow GROUP BY sensor", ["sensor"], []),
+    ("SELECT sensor, AVG(value), MIN(value), MAX(value), COUNT(value) FROM flow WHERE value >= 3 GROUP BY sensor", ["sensor"], ["avg(flow.value)"]),
+    ("SELECT value, COUNT(*), MAX(timestamp) FROM flow GROUP BY value", ["value"], []),
+    ("SELECT COUNT(*), SUM(value) FROM flow", [], []),
+])
+def test_device_side_exchange_on_one_gpu(gpu, ranks, query, keys, floats):
+    """csrc/group_exchange.cu with every rank's context in one process on one GPU (peers resolve to the owners'
+    own pointers; the push / flag / merge protocol is the one peers run over NVLink).  All ranks push, then all merge;
+    several steps reuse the double-buffered regions.  The union over ranks must equal the oracle on the whole table."""
+    ctxs = _exchange_contexts(ranks, 1 << 20)
+    engines = [NativeEngine(query) for _ in range(ranks)]
+    for step in range(4):  # ≥ 3 steps: both parities reused, acks exercised
+        n = 30_000 + 1000 * step
+        shards = [synth_batch(n, row0=(step * ranks + r) * n, seed=42 + step, key_space=1531) for r in range(ranks)]
+        for r in range(ranks):
+            engines[r].group_by_push(DeviceBatch.from_arrow(shards[r]), ctxs[r])
+        outs = [engines[r].group_by_merge(ctxs[r]) for r in range(ranks)]
+        assert all(o is not None for o in outs)
+        full = pa.Table.from_batches(shards).combine_chunks().to_batches()[0]
+        want = sql_process(full, query)
+        wd = {tuple(r[k] for k in keys): r for r in want.to_pylist()}
+        seen = {}
+        for o in outs:
+            rb = o.to_arrow()
+            assert rb.schema.names == want.schema.names
+            for row in rb.to_pylist():
+                k = tuple(row[c] for c in keys)
+                assert k not in seen, f"group {k} owned by two ranks"
+                seen[k] = row
+        assert seen.keys() == wd.keys()
+        for k, w in wd.items():
+            for name, wv in w.items():
+                gv = seen[k][name]
+                if name in floats:
+                    assert abs(gv - wv) <= 1e-9 * max(1.0, abs(wv))
+                else:
+                    assert gv == wv, (step, k, name, gv, wv)
+    for c in ctxs:
+        c.close()
+
+
+def test_device_side_exchange_long_keys_fall_back_on_every_rank(gpu):
+    """Keys longer than 12 bytes cannot travel inline: EVERY rank's merge reports it (None), also ranks whose own
+    keys were short, and the following step works again."""
+    ranks = 3
+    ctxs = _exchange_contexts(ranks, 1 << 18)
+    q = "SELECT sensor, COUNT(*) FROM flow GROUP BY sensor"
+    engines = [NativeEngine(q) for _ in range(ranks)]
+    short = synth_batch(5000, seed=5, key_space=50)
+    long_keys = pa.record_batch({"timestamp": short.column("timestamp"), "value": short.column("value"),
+                                 "sensor": pa.array([f"a_rather_long_sensor_name_{i % 7}" for i in range(5000)])})
+    for r in range(ranks):
+        engines[r].group_by_push(DeviceBatch.from_arrow(long_keys if r == 1 else short), ctxs[r])
+    assert [engines[r].group_by_merge(ctxs[r]) for r in range(ranks)] == [None] * ranks
+    for r in range(ranks):
+        engines[r].group_by_push(DeviceBatch.from_arrow(short), ctxs[r])
+    outs = [engines[r].group_by_merge(ctxs[r]) for r in range(ranks)]
+    total = sum(sum(o.to_arrow().column("count(*)").to_pylist()) for o in outs)
+    assert total == ranks * 5000
+    for c in ctxs:
+        c.close()
+
+
 def test_partial_states_of_one_key_land_in_one_partition(gpu):
     eng = NativeEngine("SELECT sensor, COUNT(*) FROM flow GROUP BY sensor")
     owner = {}
