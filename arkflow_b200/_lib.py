@@ -110,6 +110,7 @@ def _declare(lib):
         "ark_dist_handle_bytes": (C.c_int64, []),
         "ark_dist_export": (C.c_int, [vp, P(C.c_uint8), C.c_int64, P(C.c_int64)]),
         "ark_dist_connect": (C.c_int, [vp, P(C.c_uint8), C.c_int64]),
+        "ark_dist_stats": (C.c_int, [vp, P(C.c_int64)]),
         "ark_dist_destroy": (None, [vp]),
         "ark_sql_group_by_exchange_device": (C.c_int, [vp, vp, P(ArrowDeviceArray), P(ArrowSchema), P(ArrowDeviceArray), P(ArrowSchema)]),
         "ark_sql_group_by_push_device": (C.c_int, [vp, vp, P(ArrowDeviceArray), P(ArrowSchema)]),

@@ -1,7 +1,11 @@
 // batch.cu — pools, stream leases, Arrow C Data Interface import/export (see batch.h).
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <map>
+#include <thread>
 
 #include "batch.h"
 
@@ -144,9 +148,22 @@ void BlockPool::free_now(void* p) {
   }
 }
 
+void BlockPool::mark_exported(const void* base) {
+  std::lock_guard<std::mutex> l(mu_);
+  if (std::find(exported_.begin(), exported_.end(), base) == exported_.end()) exported_.push_back(base);
+}
+
 void BlockPool::trim() {
   std::vector<Block> drop;
-  { std::lock_guard<std::mutex> l(mu_); drop.swap(free_); for (auto& b : drop) reserved_ -= b.size; }
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    std::vector<Block> keep;
+    for (auto& b : free_) {
+      if (std::find(exported_.begin(), exported_.end(), (const void*)b.p) != exported_.end()) keep.push_back(b);  // peers may still have it mapped
+      else { drop.push_back(b); reserved_ -= b.size; }
+    }
+    free_.swap(keep);
+  }
   for (auto& b : drop) { if (kind_ == Device) cudaFree(b.p); else cudaFreeHost(b.p); }
 }
 
@@ -225,10 +242,118 @@ static bool format_supported(const std::string& f) {
 }
 
 // ---- import ---------------------------------------------------------------------------------------------
+// Host → device copy of one Arrow buffer.  A Rust shim hands over arrow-rs heap buffers, i.e. PAGEABLE memory: a plain
+// cudaMemcpyAsync from such a pointer is staged by the driver through one small pinned buffer, synchronously, at a
+// fraction of the link rate.  Large pageable sources are therefore staged here: a small pool of host threads copies
+// 2 MB chunks into pinned slots (two per thread, from the pinned pool) and queues each chunk's H2D as soon as it is
+// filled, so host memcpy, PCIe transfer and — across concurrent callers — the kernels of other calls overlap.
+// Pinned or registered sources (cudaPointerGetAttributes ≠ unregistered) take the direct copy.
+namespace {
+
+struct StagePool {
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<std::function<void()>> q;
+  bool stop = false;
+  explicit StagePool(int n) {
+    for (int i = 0; i < n; ++i)
+      threads.emplace_back([this] {
+        for (;;) {
+          std::function<void()> f;
+          {
+            std::unique_lock<std::mutex> l(mu);
+            cv.wait(l, [&] { return stop || !q.empty(); });
+            if (stop && q.empty()) return;
+            f = std::move(q.front());
+            q.pop_front();
+          }
+          f();
+        }
+      });
+  }
+  ~StagePool() {
+    { std::lock_guard<std::mutex> l(mu); stop = true; }
+    cv.notify_all();
+    for (auto& t : threads) t.detach();  // process teardown: do not wait on threads that may sit in the CUDA runtime
+  }
+  void submit(std::function<void()> f) {
+    { std::lock_guard<std::mutex> l(mu); q.push_back(std::move(f)); }
+    cv.notify_one();
+  }
+};
+
+int stage_threads() {
+  static const int n = [] {
+    const char* e = getenv("ARK_STAGE_THREADS");
+    int v = e ? atoi(e) : 8;
+    return std::max(0, std::min(v, 32));
+  }();
+  return n;
+}
+StagePool& stage_pool() {
+  static StagePool* p = new StagePool(stage_threads());  // leaked on purpose (see ~BlockPool)
+  return *p;
+}
+
+constexpr size_t STAGE_CHUNK = 2u << 20;
+constexpr size_t STAGE_MIN = 8u << 20;  // smaller sources are not worth the hand-off
+
+bool is_pageable(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+
+void staged_h2d(void* dst, const void* src, size_t n, cudaStream_t s) {
+  const int T = stage_threads();
+  const size_t n_chunks = (n + STAGE_CHUNK - 1) / STAGE_CHUNK;
+  BufferPtr ring = pinned_alloc((size_t)T * 2 * STAGE_CHUNK);
+  std::mutex mu;
+  std::condition_variable cv;
+  int done = 0;
+  cudaError_t first_err = cudaSuccess;
+  for (int w = 0; w < T; ++w) {
+    stage_pool().submit([&, w] {
+      ensure_device();
+      cudaEvent_t ev[2] = {nullptr, nullptr};
+      cudaError_t err = cudaSuccess;
+      bool used[2] = {false, false};
+      for (int k = 0; k < 2 && err == cudaSuccess; ++k) err = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+      int turn = 0;
+      for (size_t c = (size_t)w; c < n_chunks && err == cudaSuccess; c += (size_t)T, turn ^= 1) {
+        uint8_t* slot = (uint8_t*)ring.get() + ((size_t)w * 2 + turn) * STAGE_CHUNK;
+        const size_t off = c * STAGE_CHUNK, len = std::min(STAGE_CHUNK, n - off);
+        if (used[turn]) err = cudaEventSynchronize(ev[turn]);  // the slot's previous chunk has left for the device
+        if (err != cudaSuccess) break;
+        memcpy(slot, (const uint8_t*)src + off, len);
+        err = cudaMemcpyAsync((uint8_t*)dst + off, slot, len, cudaMemcpyHostToDevice, s);
+        if (err == cudaSuccess) err = cudaEventRecord(ev[turn], s);
+        used[turn] = true;
+      }
+      for (int k = 0; k < 2; ++k) if (ev[k]) cudaEventDestroy(ev[k]);
+      std::lock_guard<std::mutex> l(mu);
+      if (err != cudaSuccess && first_err == cudaSuccess) first_err = err;
+      ++done;
+      cv.notify_one();
+    });
+  }
+  {
+    std::unique_lock<std::mutex> l(mu);
+    cv.wait(l, [&] { return done == T; });
+  }
+  ARK_CUDA(first_err);
+  // `ring` returns to the pinned pool when this call's stream has been synchronised (blocks freed inside a call are
+  // parked until then), i.e. after the queued copies have read it
+}
+
+}  // namespace
+
 static void h2d(void* dst, const void* src, size_t n, cudaStream_t s, int64_t* acc) {
   if (n == 0) return;
-  ARK_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s));
   if (acc) *acc += (int64_t)n;
+  if (n >= STAGE_MIN && stage_threads() > 0 && is_pageable(src)) { staged_h2d(dst, src, n, s); return; }
+  ARK_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s));
 }
 
 Batch import_host(const ArrowArray* arr, const ArrowSchema* schema, const std::vector<bool>* needed,

@@ -30,6 +30,9 @@ class BlockPool {
   void free_now(void* p);
   size_t bytes_reserved() const { return reserved_; }
   void trim();
+  // A block whose CUDA IPC handle has been given to a peer stays mapped there for the life of the process
+  // (ipc_exchange.cu caches the mappings): it must never go back to the driver, so trim() keeps it.
+  void mark_exported(const void* base);
 
  private:
   struct Block { void* p; size_t size; };
@@ -37,6 +40,7 @@ class BlockPool {
   std::mutex mu_;
   std::vector<Block> free_;    // sorted by size
   std::vector<Block> live_;
+  std::vector<const void*> exported_;
   size_t reserved_ = 0;
 };
 

@@ -641,6 +641,205 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
   }
 }
 
+// ================================================================================================
+// filter_project_tile_kernel — warp-striped rows (as filter_project_pipe_kernel), ONE tile per CTA, tile claimed
+// from a ticket.  Measured on B200 (profiles/r2b_*): the persistent kernel needs a tile's aggregate to be published
+// while its CTA is still busy with the previous tile's look-back, so the CTAs end up waiting for each other in a
+// convoy (0.26 ms; 0.117 ms with the look-back stubbed out).  With one tile per CTA a tile's aggregate depends on
+// nothing but its own loads, many short-lived CTAs per SM hide each other's look-back, and the ticket — claimed by
+// the CTA when it STARTS — keeps the guarantee that a tile is only ever owned by a running CTA.
+// ================================================================================================
+template <int NF, bool VARLEN, int MINB>
+__global__ void __launch_bounds__(256, MINB) filter_project_tile_kernel(const __grid_constant__ TmaParams P) {
+  constexpr int T_THREADS = 256, TT = T_THREADS * 4, T_WARPS = T_THREADS / 32;
+  extern __shared__ __align__(16) uint8_t smem[];   // [in_bytes][out_bytes], each str_cap + 32
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int s_tile;
+  __shared__ int s_str_base, s_str_staged;
+  __shared__ int s_cnt[T_WARPS], s_bytes[T_WARPS];
+  __shared__ long long s_excl[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wrow0 = warp * 128;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  uint8_t* const in_bytes = smem;
+  uint8_t* const out_bytes = smem + P.str_cap + 32;
+  const int n_tiles = P.n_tiles;
+  if (tid == 0) {
+    if (VARLEN) { mbar_init(&s_bar, 1); mbar_fence_init(); }
+    const int t = (int)atomicAdd(P.ticket, 1u);   // tiles in START order: every smaller tile belongs to a CTA that is running
+    s_tile = t;
+    if (VARLEN && t < n_tiles) {
+      const int64_t r0 = (int64_t)t * TT;
+      const int64_t rr = P.n_rows - r0;
+      const int32_t o0 = P.offsets_in[r0], o1 = P.offsets_in[r0 + (rr < TT ? rr : TT)];
+      const uintptr_t a0 = reinterpret_cast<uintptr_t>(P.data_in + o0), a1 = reinterpret_cast<uintptr_t>(P.data_in + o1);
+      const uintptr_t lo = a0 & ~(uintptr_t)15, hi = (a1 + 15) & ~(uintptr_t)15;
+      int staged = 0;
+      if (o1 > o0 && hi - lo <= (uintptr_t)P.str_cap) {  // staged ⇒ selected bytes ≤ window ≤ str_cap
+        staged = 1;
+        mbar_expect_tx(&s_bar, (unsigned)(hi - lo));
+        tma_load_1d(in_bytes, reinterpret_cast<const void*>(lo), (unsigned)(hi - lo), &s_bar);
+      }
+      s_str_base = o0 - (int32_t)(a0 - lo); s_str_staged = staged;
+    }
+  }
+  __syncthreads();
+  const int tile = s_tile;
+  if (tile >= n_tiles) return;
+  const int64_t row0 = (int64_t)tile * TT;
+  const int rows = (int)((P.n_rows - row0) < TT ? (P.n_rows - row0) : TT);
+  unsigned long long pv[4];
+  int off[4] = {0, 0, 0, 0}, offx = 0;
+  load_rows_striped<VARLEN>(P, row0, rows, wrow0, lane, pv, off, &offx);
+  // ---- B: predicate; ranks from ballots; byte positions ----
+  unsigned flags = 0;
+  int len[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long key = P.sp_is_f64 ? f64_total_key(pv[j]) : (long long)pv[j];
+    bool f = (unsigned long long)(key - P.range_lo) <= P.range_span;
+    f = (f != (bool)P.negate) && (wrow0 + 32 * j + lane < rows);
+    flags |= (unsigned)f << j;
+  }
+  if (VARLEN) {
+    // end of row (j, lane) = start of row (j, lane + 1); lane 31: row (j + 1, 0), or the next warp's first row
+    const int rows_w = rows - wrow0;  // rows of this warp's slice that exist (may be ≤ 0 or < 128 in the last tile)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int e = __shfl_down_sync(0xffffffffu, off[j], 1);
+      const int nxt = j < 3 ? __shfl_sync(0xffffffffu, off[j < 3 ? j + 1 : 3], 0) : offx;
+      if (lane == 31) e = nxt;
+      len[j] = (32 * j + lane < rows_w) ? e - off[j] : 0;
+    }
+  }
+  int wpos[4];  // rank of row (j, lane) among the warp's selected rows
+  int warp_cnt = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned m = __ballot_sync(0xffffffffu, (flags >> j) & 1);
+    wpos[j] = warp_cnt + __popc(m & lt_mask);
+    warp_cnt += __popc(m);
+  }
+  int bpos[4] = {0, 0, 0, 0};  // byte position of row (j, lane) among the warp's selected bytes
+  int warp_bytes = 0;
+  if (VARLEN) {
+    const int len0 = __shfl_sync(0xffffffffu, len[0], 0);
+    const bool same = (len[0] == len0 || wrow0 + lane >= rows) && (len[1] == len0 || wrow0 + 32 + lane >= rows) &&
+                      (len[2] == len0 || wrow0 + 64 + lane >= rows) && (len[3] == len0 || wrow0 + 96 + lane >= rows);
+    if (__all_sync(0xffffffffu, same)) {  // fixed-width strings: positions follow from the ranks
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bpos[j] = wpos[j] * len0;
+      warp_bytes = warp_cnt * len0;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int sl = ((flags >> j) & 1) ? len[j] : 0;
+        const int incl = warp_incl_scan(sl, lane);
+        bpos[j] = warp_bytes + incl - sl;
+        warp_bytes += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+  }
+  if (lane == 0) { s_cnt[warp] = warp_cnt; if (VARLEN) s_bytes[warp] = warp_bytes; }
+  // other projected fixed-width columns: requested now, stored after the look-back
+  unsigned long long fx[NF > 0 ? NF : 1][4];
+#pragma unroll
+  for (int c = 0; c < NF; ++c) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      fx[c][j] = pv[j];
+      if (!((P.fixed_is_pred >> c) & 1) && ((flags >> j) & 1)) fx[c][j] = ld_stream_u64(P.fixed_in[c] + row0 + wrow0 + 32 * j + lane);
+    }
+  }
+  __syncthreads();
+
+  // ---- D: tile scan over the per-warp totals (every warp, redundantly); publish the tile aggregate at once ----
+  int w_cnt_excl, w_bytes_excl = 0, tile_cnt, tb = 0;
+  {
+    const int c = lane < T_WARPS ? s_cnt[lane] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < T_WARPS; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    w_cnt_excl = __shfl_sync(0xffffffffu, incl - c, warp);
+    tile_cnt = __shfl_sync(0xffffffffu, incl, T_WARPS - 1);
+    if (VARLEN) {
+      const int b = lane < T_WARPS ? s_bytes[lane] : 0;
+      int bi = b;
+#pragma unroll
+      for (int o = 1; o < T_WARPS; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, bi, o); if (lane >= o) bi += t; }
+      w_bytes_excl = __shfl_sync(0xffffffffu, bi - b, warp);
+      tb = __shfl_sync(0xffffffffu, bi, T_WARPS - 1);
+    }
+  }
+  if (warp == 0 && lane == 0) st_volatile_u64(P.desc + (size_t)tile * P.desc_stride, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
+  // ---- F: decoupled look-back (warp 0) runs while the other warps compact the strings ----
+  if (warp == 0) {
+    long long ex0, ex1;
+    if (P.debug & 1) { ex0 = (long long)tile * (TT / 2); ex1 = ex0 * 12; }
+    else lookback_resolve(P.desc, P.desc_stride, tile, tile_cnt, tb, lane, &ex0, &ex1);
+    if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
+  }
+  // ---- E: compact the strings in shared memory at tile-local positions ----
+  bool str_fast = false;
+  if (VARLEN) {
+    str_fast = s_str_staged;
+    if (str_fast) {
+      mbar_wait(&s_bar, 0);  // this tile's window
+      const int base = s_str_base;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((flags >> j) & 1) smem_copy(out_bytes + w_bytes_excl + bpos[j], in_bytes + (off[j] - base), len[j]);
+    }
+  }
+  __syncthreads();
+  const long long base_cnt = s_excl[0];
+  const long long bb = VARLEN ? s_excl[1] : 0;
+  if (tile == n_tiles - 1 && tid == 0) { P.totals[0] = base_cnt + tile_cnt; P.totals[1] = bb + tb; }
+
+  // ---- G: stores — for each j the surviving lanes of a warp write consecutive slots ----
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (!((flags >> j) & 1)) continue;
+    const long long pos = base_cnt + w_cnt_excl + wpos[j];
+#pragma unroll
+    for (int c = 0; c < NF; ++c) P.fixed_out[c][pos] = fx[c][j];
+    if (VARLEN) P.offsets_out[pos] = (int32_t)(bb + w_bytes_excl + bpos[j]);
+  }
+  if (VARLEN) {
+    if (tile == n_tiles - 1 && tid == 0) P.offsets_out[base_cnt + tile_cnt] = (int32_t)(bb + tb);
+    if (str_fast) {
+      // destination-aligned 16-byte stores; the shared-memory source is misaligned by d = (-bb) mod 16
+      uint8_t* gdst = P.data_out + bb;
+      const int head = (int)((16 - (bb & 15)) & 15) < tb ? (int)((16 - (bb & 15)) & 15) : tb;
+      if (tid < head) gdst[tid] = out_bytes[tid];
+      const int body = (tb - head) >> 4;
+      const unsigned* sw = reinterpret_cast<const unsigned*>(out_bytes + (head & ~3));
+      const unsigned sh = (head & 3) * 8;
+      for (int g = tid; g < body; g += T_THREADS) {
+        const unsigned* w = sw + g * 4;
+        uint4 v;
+        if (sh == 0) { v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3]; }
+        else {
+          const unsigned a = w[0], b = w[1], c = w[2], d = w[3], e = w[4];
+          v.x = __funnelshift_r(a, b, sh); v.y = __funnelshift_r(b, c, sh); v.z = __funnelshift_r(c, d, sh); v.w = __funnelshift_r(d, e, sh);
+        }
+        *reinterpret_cast<uint4*>(gdst + head + g * 16) = v;
+      }
+      const int done = head + body * 16;
+      if (tid < tb - done) gdst[done + tid] = out_bytes[done + tid];
+    } else {  // long strings: straight from global to global
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!((flags >> j) & 1)) continue;
+        const uint8_t* src = P.data_in + off[j];
+        uint8_t* dst = P.data_out + bb + w_bytes_excl + bpos[j];
+        for (int i = 0; i < len[j]; ++i) dst[i] = src[i];
+      }
+    }
+  }
+}
+
 }  // namespace
 
 static std::atomic<double> g_avg_len_hint{12.8};
@@ -701,8 +900,32 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
   P.str_cap = cap;
   P.desc_stride = g_desc_stride;
   const bool v = P.has_varlen;
-  // implementation: 0 = persistent pipelined kernel (default), 1 = one tile per CTA (the r1 kernel, kept for A/B runs)
-  static const int impl = [] { const char* e = getenv("ARK_FP_IMPL"); return e ? atoi(e) : 0; }();
+  // implementation: 2 = striped rows, one ticketed tile per CTA (default); 0 = persistent pipelined striped kernel;
+  // 1 = the r1 kernel (blocked rows, tile = blockIdx).  0 and 1 are kept for A/B runs.
+  static const int impl = [] { const char* e = getenv("ARK_FP_IMPL"); return e ? atoi(e) : 2; }();
+  if (impl == 2 && g_fp_threads == 256 && ticket != nullptr) {
+    const size_t smem = v ? 2 * (size_t)(cap + 32) : 0;
+    static const int minb = [] { const char* e = getenv("ARK_FP_MINB"); const int x = e ? atoi(e) : 5; return x >= 4 && x <= 6 ? x : 5; }();
+#define ARK_TILE_FN(NF, V) (minb == 4 ? (const void*)filter_project_tile_kernel<NF, V, 4> : minb == 6 ? (const void*)filter_project_tile_kernel<NF, V, 6> : (const void*)filter_project_tile_kernel<NF, V, 5>)
+    static bool configured = false;
+    if (!configured) {
+      for (const void* f : {ARK_TILE_FN(0, true), ARK_TILE_FN(1, true), ARK_TILE_FN(2, true)})
+        ARK_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (48 * 1024 + 32)));
+      configured = true;
+    }
+    const void* fn = nullptr;
+    if (n_fixed_out == 0 && v) fn = ARK_TILE_FN(0, true);
+    else if (n_fixed_out == 1 && v) fn = ARK_TILE_FN(1, true);
+    else if (n_fixed_out == 2 && v) fn = ARK_TILE_FN(2, true);
+    else if (n_fixed_out == 1) fn = ARK_TILE_FN(1, false);
+    else if (n_fixed_out == 2) fn = ARK_TILE_FN(2, false);
+    else return false;
+#undef ARK_TILE_FN
+    KernelTimer t("filter_project_tma_kernel", stream);
+    void* args[] = {(void*)&P};
+    ARK_CUDA(cudaLaunchKernel(fn, dim3(P.n_tiles), dim3(256), args, smem, stream));
+    return true;
+  }
   if (impl == 0 && g_fp_threads == 256 && ticket != nullptr) {
     const size_t smem = v ? 3 * (size_t)(cap + 32) : 0;
     static int occ[2][3] = {{0, 0, 0}, {0, 0, 0}};   // CTAs per SM by (varlen, n_fixed) at the largest staging size seen

@@ -345,6 +345,15 @@ int ark_dist_connect(ark_dist_t* d, const uint8_t* blobs, int64_t blob_stride) {
   });
 }
 
+int ark_dist_stats(ark_dist_t* d, int64_t* out4) {
+  return gx_guarded([&] {
+    if (!d || !out4) fail(ARK_ERR_PROCESS, "null argument");
+    std::lock_guard<std::mutex> l(d->ctx.mu);
+    out4[0] = (int64_t)d->ctx.step; out4[1] = (int64_t)d->ctx.last_recv_records; out4[2] = (int64_t)d->ctx.last_groups;
+    out4[3] = (int64_t)d->ctx.region_bytes;
+  });
+}
+
 void ark_dist_destroy(ark_dist_t* d) {
   if (!d) return;
   cudaDeviceSynchronize();

@@ -36,6 +36,8 @@ struct DistCtx {
   unsigned long long step = 0;    // exchanges issued so far (every rank counts the same calls)
   // state carried from the push phase to the merge phase of one step
   bool pushed = false;
+  // last completed step, for callers that report the exchange (bench.py): records received / groups owned here
+  unsigned long long last_recv_records = 0, last_groups = 0;
   std::mutex mu;
 };
 

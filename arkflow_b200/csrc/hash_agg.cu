@@ -760,6 +760,7 @@ bool run_group_by_merge(const Plan& plan, DistCtx& d, Batch& out, cudaStream_t s
     }
     dg.n_groups = groups;
     dg.capacity = capacity;
+    d.last_recv_records = total; d.last_groups = groups;
     unsigned long long want = 1ull << 10;
     while (want < 2ull * groups) want <<= 1;
     hints.capacity.store(want);

@@ -63,7 +63,7 @@ __device__ __forceinline__ void ld_vec_off(const int32_t* os, bool fast, int lr0
 
 // SIG 1: the accumulators are exactly {COUNT(*), SUM(<non-null Int64 column>)} (config 3): two REDs, no dispatch.
 template <int KEYK, int PRED, int R, int SIG>
-__global__ void __launch_bounds__(HS_THREADS) hash_agg_stream_kernel(const __grid_constant__ AggParams P, const int str_cap) {
+__global__ void __launch_bounds__(HS_THREADS) hash_agg_stream_kernel(const __grid_constant__ AggParams P, const int str_cap, const int dbg) {
   constexpr int TR = HS_THREADS * R;
   constexpr int PRODUCER = HS_THREADS - 32;
   extern __shared__ __align__(16) uint8_t smem[];  // KEY_BYTES: [key bytes stage 0][stage 1], each str_cap + 32
@@ -228,15 +228,17 @@ __global__ void __launch_bounds__(HS_THREADS) hash_agg_stream_kernel(const __gri
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       if (!((ok >> j) & 1)) continue;
+      if (dbg & 4) { kb[j][0].lo = home[j]; continue; }  // measurement: no table reads at all
       const Key16* b = reinterpret_cast<const Key16*>(P.table + (unsigned long long)home[j] * (unsigned long long)bstride);
-#pragma unroll
-      for (int i = 0; i < TBL_B; ++i) kb[j][i] = ld128(b + i);
+      ld256_keys(b, &kb[j][0], &kb[j][1]);
+      ld256_keys(b + 2, &kb[j][2], &kb[j][3]);
     }
     unsigned long long slot[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       slot[j] = ~0ull;
       if (!((ok >> j) & 1)) continue;
+      if (dbg & 2) { slot[j] = (unsigned long long)home[j] * TBL_B + (kb[j][0].lo & 3); continue; }  // measurement: no probing
       Key16* b = reinterpret_cast<Key16*>(P.table + (unsigned long long)home[j] * (unsigned long long)bstride);
       bool done = false;
 #pragma unroll
@@ -255,6 +257,7 @@ __global__ void __launch_bounds__(HS_THREADS) hash_agg_stream_kernel(const __gri
       }
     }
     // ---- accumulate (fire-and-forget REDs) ----
+    if (dbg & 1) continue;  // measurement: no accumulation
     if (SIG == 1) {
 #pragma unroll
       for (int j = 0; j < R; ++j) {
@@ -325,7 +328,8 @@ bool launch_hash_agg_stream(const AggParams& P, unsigned long long capacity, int
   const int n_tiles = (int)ceil_div(P.n_rows, TR);
   const int grid = std::max(1, std::min(n_tiles, sms * occ));
   KernelTimer t("hash_agg_kernel", stream);
-  void* args[] = {(void*)&P, (void*)&cap};
+  static const int dbg = [] { const char* e = getenv("ARK_AGG_DEBUG"); return e ? atoi(e) : 0; }();  // measurement knob, results void
+  void* args[] = {(void*)&P, (void*)&cap, (void*)&dbg};
   ARK_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(HS_THREADS), args, smem, stream));
   return true;
 }

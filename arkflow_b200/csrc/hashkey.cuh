@@ -24,6 +24,12 @@ static __device__ __forceinline__ Key16 ld128(const Key16* addr) {  // single 12
   return v;
 }
 
+// two adjacent keys (32 bytes, 32-byte aligned) with one 256-bit access (LDG.E.256.STRONG.GPU): one L2 request per sector
+static __device__ __forceinline__ void ld256_keys(const Key16* addr, Key16* k0, Key16* k1) {
+  asm volatile("ld.relaxed.gpu.global.v4.u64 {%0, %1, %2, %3}, [%4];"
+               : "=l"(k0->lo), "=l"(k0->hi), "=l"(k1->lo), "=l"(k1->hi) : "l"(addr) : "memory");
+}
+
 static __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
@@ -176,8 +182,8 @@ static __device__ __forceinline__ unsigned long long table_find_or_claim(uint8_t
   for (int probes = 0; probes < max_buckets; ++probes) {
     Key16* kb = reinterpret_cast<Key16*>(table + b * (unsigned long long)bstride);
     Key16 k[TBL_B];
-#pragma unroll
-    for (int i = 0; i < TBL_B; ++i) k[i] = ld128(kb + i);
+    ld256_keys(kb, &k[0], &k[1]);
+    ld256_keys(kb + 2, &k[2], &k[3]);
 #pragma unroll
     for (int i = 0; i < TBL_B; ++i) {
       Key16 c = k[i];

@@ -56,14 +56,15 @@ void export_buf(const void* p, IpcBuf* b) {
     cudaGetLastError();
     fail(ARK_ERR_UNSUPPORTED, std::string("ipc export: ") + cudaGetErrorString(e) + " (memory not created by cudaMalloc?)");
   }
+  device_pool().mark_exported((const void*)(uintptr_t)base);  // peers cache the mapping: the block must outlive trim()
   memcpy(b->handle, &h, 64);
   b->offset = (uint64_t)((unsigned long long)(uintptr_t)p - base);
   b->raw = (uint64_t)(uintptr_t)p;
   b->present = 1;
 }
 
-// opened peer allocations, by handle bytes.  Pool blocks are never returned to the driver while the
-// process lives (BlockPool::trim only runs on allocation failure), so a mapping stays valid.
+// opened peer allocations, by handle bytes.  An exported pool block is never returned to the driver while the
+// process lives (export_buf marks it; BlockPool::trim skips marked blocks), so a cached mapping stays valid.
 const uint8_t* open_buf(const IpcBuf& b, bool same_process) {
   if (!b.present) return nullptr;
   if (same_process) return (const uint8_t*)(uintptr_t)b.raw;

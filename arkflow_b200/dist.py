@@ -163,6 +163,11 @@ class ExchangeContext:
         dist.barrier(group)
         return ctx
 
+    def stats(self) -> dict:
+        out = (C.c_int64 * 4)()
+        L.lib().ark_dist_stats(self._h, out)
+        return {"steps": out[0], "records_received": out[1], "groups": out[2], "region_bytes": out[3]}
+
     def close(self) -> None:
         if self._h:
             L.lib().ark_dist_destroy(self._h)

@@ -1,19 +1,26 @@
 #!/usr/bin/env python
 """bench.py — rows/s through the `sql` processor on synthetic Arrow batches (BASELINE.json metric).
 
-Workload (BASELINE.json configs[1]): `SELECT sensor, value FROM flow WHERE value >= 10` over a
-2^30-row table of schema S (timestamp Int64, value Int64, sensor Utf8 "temp_%07d"), fed as 64
-RecordBatches of 2^24 rows (one Utf8 array cannot exceed 2 GiB).  A *step* is one process() call on
-one 2^24-row batch; the default 64 steps are the whole 2^30-row job.  N>1: every rank owns its own
-2^30-row shard (weak scaling, no collective on this path — SURVEY.md §8(e)).
+Contract workload (BASELINE.json configs[1]): `SELECT sensor, value FROM flow WHERE value >= 10` over batches of
+2^24 rows of schema S (timestamp Int64, value Int64, sensor Utf8 "temp_%07d"); a *step* is one process() call on one
+2^24-row batch (a 2^30-row table is 64 such steps; one Utf8 array cannot exceed 2 GiB).  N > 1: every rank filters
+its own shard — weak scaling, no collective on this path.
 
-  value   device-resident: ark_sql_process_device on batches already in HBM
-  e2e     reference-facing call with HOST buffers: ark_sql_process on pinned host Arrow buffers,
-          H2D + kernel + D2H inside the timed region
-  roofline  filter_project_kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
+  value     device-resident: ark_sql_process_device on batches already in HBM, one caller
+  e2e       the reference-facing call with HOST buffers: ark_sql_process on PAGEABLE host Arrow buffers (what a Rust
+            shim hands over), H2D + kernel + D2H inside the timed region; the same with pinned buffers is reported
+            beside it (e2e.pinned)
+  roofline  filter kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
+  verified  one timed output compared with a numpy restatement of the same synthetic batch (count, order-sensitive
+            checksums of the values and of the string bytes)
   cpu_baseline  the oracle port (numpy/pyarrow restatement; the Rust reference cannot be built here)
 
-`--impl reference` times that oracle port on the host cores with the same JSON contract.
+The line also carries the sharded workloads of BASELINE.json configs[2] and [3] (`groupby`, `join`): per rank one
+2^24-row batch per step, partial aggregate → device-side exchange over NVLink → final merge (arkflow_b200/dist.py),
+each with its own rows/s, roofline, exchange block and parity check; a compact copy sits in config.sharded so that
+it survives tools that keep only the contract keys.
+
+`--impl reference` times the oracle port on the host cores with the same JSON contract and the same step size.
 """
 from __future__ import annotations
 
@@ -33,11 +40,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 QUERY = "SELECT sensor, value FROM flow WHERE value >= 10"
+GROUP_QUERY = "SELECT sensor, SUM(value), COUNT(*) FROM flow GROUP BY sensor"
+JOIN_QUERY = "SELECT * FROM flow_input1 JOIN flow_input2 ON flow_input1.sensor = flow_input2.sensor"
 ROWS_PER_BATCH = 1 << 24
-N_BATCHES = 64  # × 2^24 = 2^30 rows per GPU
+N_BATCHES = 64  # x 2^24 = 2^30 rows per GPU
 SEED = 42
 KEY_SPACE = 1_000_000
 METRIC = "rows/sec through sql processor on synthetic Arrow batches"
+NVLINK_GBS = 770.0  # measured peer-copy bandwidth per direction on this pool (B200_PROFILING.md); nominal 900
 
 
 def env_int(name, default):
@@ -48,9 +58,48 @@ def env_int(name, default):
 
 
 # ------------------------------------------------------------------------------------------------
+# numpy restatement of the synthetic generator (csrc/synth.cu) — used to VERIFY timed outputs.
+# Written out here so that the verification does not route through oracle/ (test infrastructure).
+# ------------------------------------------------------------------------------------------------
+def np_splitmix(seed, idx):
+    import numpy as np
+
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + (idx.astype(np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def np_values_keys(n, row0, key_space, seed=SEED):
+    import numpy as np
+
+    idx = np.arange(row0, row0 + n, dtype=np.uint64)
+    value = (np_splitmix(seed, idx) % np.uint64(20)).astype(np.int64)
+    key = (np_splitmix(seed ^ 0x9E37, idx) % np.uint64(key_space)).astype(np.int64)
+    return value, key
+
+
+def order_checksum_np(a):
+    """sum_i (i + 1) * a[i] mod 2^64 — sensitive to order, position and content."""
+    import numpy as np
+
+    with np.errstate(over="ignore"):
+        w = np.arange(1, len(a) + 1, dtype=np.uint64)
+        return int((w * a.astype(np.uint64)).sum(dtype=np.uint64))
+
+
+def order_checksum_torch(t):
+    import torch
+
+    w = torch.arange(1, t.numel() + 1, dtype=torch.int64, device=t.device)
+    return int((w * t.to(torch.int64)).sum().item()) & 0xFFFFFFFFFFFFFFFF
+
+
+# ------------------------------------------------------------------------------------------------
 # CPU side: oracle port, all host cores (partition-parallel like DataFusion's target_partitions)
 # ------------------------------------------------------------------------------------------------
-def cpu_process_batch(rb, pool, n_threads, chunk_rows=1 << 20):
+def cpu_process_batch(rb, pool, chunk_rows=1 << 20):
     from oracle.sql_oracle import sql_process
 
     chunks = [rb.slice(o, min(chunk_rows, rb.num_rows - o)) for o in range(0, rb.num_rows, chunk_rows)]
@@ -64,13 +113,13 @@ def cpu_baseline_measure(sample_rows, budget_s=12.0):
     n_threads = os.cpu_count() or 1
     rb = synth_batch(sample_rows, seed=SEED, key_space=KEY_SPACE)
     with ThreadPoolExecutor(max_workers=n_threads) as pool:
-        cpu_process_batch(rb, pool, n_threads)  # warm-up
+        cpu_process_batch(rb, pool)  # warm-up
         t0 = time.perf_counter()
         passes = 0
         while True:
-            cpu_process_batch(rb, pool, n_threads)
+            cpu_process_batch(rb, pool)
             passes += 1
-            if time.perf_counter() - t0 >= budget_s or passes >= 50:
+            if time.perf_counter() - t0 >= budget_s or passes >= 30:
                 break
         dt = time.perf_counter() - t0
     return {"value": passes * sample_rows / dt, "unit": "rows/s", "cores": n_threads, "kind": "port",
@@ -79,52 +128,100 @@ def cpu_baseline_measure(sample_rows, budget_s=12.0):
 
 
 def run_reference(args):
-    """The reference's CPU implementation of the path = the oracle port (the Rust reference cannot be
-    compiled in this image).  Each step = one bounded 2^22-row batch of the workload."""
+    """The reference's CPU implementation of the path = the oracle port (the Rust reference cannot be compiled in this
+    image).  Same step as the GPU arm: one 2^24-row batch per step.  Also reports the reference's own concurrency
+    shape (crates/arkflow-plugin/src/processor/sql.rs:89,118-120: at most 4 batches in flight, each a single-partition
+    scan) beside the all-cores number."""
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
+    from oracle.sql_oracle import sql_process
     from oracle.synth import synth_batch
 
-    sample_rows = 1 << 22
     n_threads = os.cpu_count() or 1
-    batches = [synth_batch(sample_rows, row0=i * sample_rows, seed=SEED, key_space=KEY_SPACE) for i in range(4)]
+    batches = [synth_batch(ROWS_PER_BATCH, row0=i * ROWS_PER_BATCH, seed=SEED, key_space=KEY_SPACE) for i in range(2)]
     with ThreadPoolExecutor(max_workers=n_threads) as pool:
         for i in range(args.warmup):
-            cpu_process_batch(batches[i % 4], pool, n_threads)
+            cpu_process_batch(batches[i % 2], pool)
         t0 = time.perf_counter()
         for i in range(args.steps):
-            cpu_process_batch(batches[i % 4], pool, n_threads)
+            cpu_process_batch(batches[i % 2], pool)
         dt = time.perf_counter() - t0
-    value = args.steps * sample_rows / dt
+    value = args.steps * ROWS_PER_BATCH / dt
+    # the reference's shape: 4 workers, each running whole (here 2^22-row) batches on one thread
+    shape_rows = 1 << 22
+    small = [batches[0].slice(i * shape_rows, shape_rows) for i in range(4)]
+    with ThreadPoolExecutor(max_workers=4) as pool4:
+        list(pool4.map(lambda b: sql_process(b, QUERY), small))
+        t1 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            list(pool4.map(lambda b: sql_process(b, QUERY), small))
+        dt4 = time.perf_counter() - t1
+    shape_value = reps * 4 * shape_rows / dt4
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "filter+project SELECT sensor,value WHERE value>=10 (BASELINE configs[1])",
-                   "rows_per_step": sample_rows, "query": QUERY, "schema": "timestamp:Int64,value:Int64,sensor:Utf8(12B)"},
+        "config": workload_config(1, args.steps, None, None),
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": n_threads, "kind": "port",
-                         "sample": f"{args.steps} steps of a {sample_rows}-row batch; oracle port (numpy/pyarrow), {n_threads} threads"},
+                         "sample": f"{args.steps} steps of a {ROWS_PER_BATCH}-row batch; oracle port (numpy/pyarrow), {n_threads} threads"},
+        "reference_concurrency_shape": {"value": shape_value, "unit": "rows/s", "cores": 4,
+                                        "note": "4 concurrent batches x 1 thread each (sql.rs:89 pool of 4 contexts, single-partition register_batch)"},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
     return 0
 
 
+def workload_config(world, steps, selectivity, resident):
+    cfg = {"workload": f"filter+project SELECT sensor,value WHERE value>=10 on int64/Utf8 batches of schema S (BASELINE configs[1]); "
+                       f"{steps} steps of one 2^24-row batch per GPU were timed (a 2^30-row table is 64 such steps)",
+           "query": QUERY, "rows_per_step": ROWS_PER_BATCH, "schema": "timestamp:Int64,value:Int64,sensor:Utf8(12B)",
+           "l2": "inputs larger than L2 (537 MB per batch, a different resident batch each step)",
+           "parallelism": f"{world} rank(s), row shards, no collective"}
+    if selectivity is not None:
+        cfg["selectivity"] = selectivity
+    if resident is not None:
+        cfg["resident_batches"] = resident
+    return cfg
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------------
+def numa_bind(gpu_index):
+    """Run this process (and every thread it creates later: staging threads, callers) on the CPUs next to its GPU, so
+    that pinned staging buffers are first-touched on the GPU's NUMA node.  8 ranks pulling ~75 GB/s each through the
+    wrong socket is what cost the 8-GPU end-to-end number half its efficiency in round 1."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": len(cpus), "first": min(cpus), "last": max(cpus)}
+    except Exception as e:  # noqa: BLE001 — binding is an optimisation, never a failure
+        return {"error": str(e)[:80]}
+    return None
+
+
 class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu_index, self.proc, self.lines = gpu_index, None, []
 
     def start(self):
-        if os.environ.get("ARK_BENCH_NO_SAMPLER"):  # experiment knob: how much does polling nvidia-smi cost the timed region?
+        if os.environ.get("ARK_BENCH_NO_SAMPLER"):
             return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -170,11 +267,30 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic():
+    """dram__bytes_read + dram__bytes_write of one launch of the filter kernel, from the newest ncu --set full capture
+    committed under profiles/ (a constant of that capture, not measured in this run)."""
+    best = (None, None)
+    for name in ("r2_filter_project_traffic.json", "r1_filter_project_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp):
+            try:
+                best = (json.load(open(tp)).get("dram_bytes_per_launch"), f"profiles/{name} (ncu --set full capture; not measured in this run)")
+                break
+            except Exception:
+                pass
+    return best
+
+
 def run_b200(args):
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    numa = numa_bind(local_rank)  # before torch / the library create their threads
+
+    import numpy as np
+    import pyarrow as pa
     import torch
     import torch.distributed as dist
 
-    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -183,49 +299,57 @@ def run_b200(args):
     from arkflow_b200 import _lib as L
     from arkflow_b200 import arrow_ffi as F
     from arkflow_b200.processor import SqlProcessor, _check
-    import pyarrow as pa
 
     lib = L.lib()
     _check(lib.ark_b200_init(local_rank))
-    proc = SqlProcessor({"query": QUERY})
-    shard_row0 = rank * N_BATCHES * ROWS_PER_BATCH
+    peak, peak_src = load_peaks()
 
-    # ---- resident inputs: 64 batches of 2^24 rows generated in HBM ----
-    n_resident = min(N_BATCHES, max(args.steps, 8))
-    resident = []
-    for b in range(n_resident):
+    def synth_device(n, row0, key_space=KEY_SPACE, kind=0):
         dev, sch = L.ArrowDeviceArray(), L.ArrowSchema()
-        _check(lib.ark_synth_batch_device(ROWS_PER_BATCH, shard_row0 + b * ROWS_PER_BATCH, SEED, 0, KEY_SPACE, C.byref(dev), C.byref(sch)))
-        resident.append(F.DeviceBatch.adopt(dev, sch))
-    for b in resident:  # build each resident batch's Arrow C struct tree now: describing the inputs is set-up, not a step
-        d, s_ = b.export()
+        _check(lib.ark_synth_batch_device(n, row0, SEED, kind, key_space, C.byref(dev), C.byref(sch)))
+        b = F.DeviceBatch.adopt(dev, sch)
+        d, s_ = b.export()  # build the Arrow C struct tree now: describing a resident input is set-up, not a step
         F.release_schema(s_)
         F.release_array(d.array)
+        return b
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    max_over_ranks = lambda x: reduce_ranks(x, dist.ReduceOp.MAX) if world > 1 else x  # noqa: E731
+    sum_over_ranks = lambda x: reduce_ranks(x, dist.ReduceOp.SUM) if world > 1 else x  # noqa: E731
 
-    # ---- device-resident timed region (single caller: one process() after another) ----
-    def device_step(i):
+    def kernel_ms(name):
+        ms, n = C.c_double(), C.c_int64()
+        lib.ark_kernel_timing_get(name.encode(), C.byref(ms), C.byref(n))
+        return (ms.value / n.value if n.value else 0.0), int(n.value)
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # =====================================================================================================
+    # contract workload: filter + project
+    # =====================================================================================================
+    proc = SqlProcessor({"query": QUERY})
+    shard_row0 = rank * N_BATCHES * ROWS_PER_BATCH
+    n_resident = min(N_BATCHES, max(args.steps, 8))
+    resident = [synth_device(ROWS_PER_BATCH, shard_row0 + b * ROWS_PER_BATCH) for b in range(n_resident)]
+
+    def device_step(i, keep=None):
         out = proc.process_device(resident[i % n_resident])
         rows = out.num_rows
-        out.close()
+        if keep is not None and i == keep[0]:
+            keep.append(out)
+        else:
+            out.close()
         return rows
 
     for i in range(args.warmup):
@@ -236,11 +360,11 @@ def run_b200(args):
     barrier()
     sampler.start()
     launches0 = lib.ark_kernel_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    keep = [args.steps - 1]  # the LAST timed output is kept for verification
     ev0.record()
     out_rows = 0
     for i in range(args.steps):
-        out_rows += device_step(i)
+        out_rows += device_step(i, keep)
     torch.cuda.synchronize()
     ev1.record()
     ev1.synchronize()
@@ -248,16 +372,44 @@ def run_b200(args):
     launches = lib.ark_kernel_launch_count() - launches0
     barrier()
     lib.ark_kernel_timing_enable(0)
-    kms, kn = C.c_double(), C.c_int64()
-    lib.ark_kernel_timing_get(b"filter_project_tma_kernel", C.byref(kms), C.byref(kn))
+    k_avg_ms, k_n = kernel_ms("filter_project_tma_kernel")
     dev_ms = max_over_ranks(dev_ms_local)
+    rows_total = args.steps * ROWS_PER_BATCH * world
+    value = rows_total / (dev_ms / 1e3)
+
+    # ---- verify the last timed output against numpy on the same synthetic rows ----
+    verified = {"ok": False}
+    try:
+        out = keep[1]
+        bi = (args.steps - 1) % n_resident
+        val_np, key_np = np_values_keys(ROWS_PER_BATCH, shard_row0 + bi * ROWS_PER_BATCH, KEY_SPACE)
+        m = val_np >= 10
+        want_n = int(m.sum())
+        oc = {c.name: c for c in out.columns}
+        got_val = oc["value"].data[:out.num_rows]
+        sb = oc["sensor"].data.tensor() if hasattr(oc["sensor"].data, "tensor") else oc["sensor"].data
+        sbytes = sb[: out.num_rows * 12].view(-1, 12).to(torch.int64)
+        got_keys = torch.zeros(out.num_rows, dtype=torch.int64, device=sbytes.device)
+        for d in range(7):
+            got_keys = got_keys * 10 + (sbytes[:, 5 + d] - 48)
+        prefix_ok = bool((sbytes[:, :5] == torch.tensor(list(b"temp_"), device=sbytes.device)).all().item())
+        offs = oc["sensor"].offsets[: out.num_rows + 1]
+        offs_ok = bool((offs == torch.arange(0, (out.num_rows + 1) * 12, 12, dtype=torch.int32, device=offs.device)).all().item())
+        checks = {"rows": out.num_rows == want_n, "value_checksum": order_checksum_torch(got_val) == order_checksum_np(val_np[m]),
+                  "string_checksum": order_checksum_torch(got_keys) == order_checksum_np(key_np[m]), "string_prefix": prefix_ok, "offsets": offs_ok}
+        verified = {"ok": all(checks.values()), "checks": checks, "rows": want_n,
+                    "what": "last timed step's output vs numpy restatement of the same 2^24 synthetic rows: row count, order-sensitive "
+                            "checksums sum((i+1)*x_i) of value and of the key ids parsed from the string bytes, 'temp_' prefix, offsets"}
+        out.close()
+    except Exception as e:  # noqa: BLE001
+        verified = {"ok": False, "error": str(e)[:200]}
+
     # extra: the same K steps driven by several host threads, as the reference's `thread_num` workers do
-    # (crates/arkflow-core/src/stream/mod.rs:117-126; process() is re-entrant).  Not the contract `value`.
     dthreads = max(1, args.device_threads)
     conc = None
     if dthreads > 1:
         with ThreadPoolExecutor(max_workers=dthreads) as dpool:
-            work = lambda t, hi: sum(device_step(i) for i in range(t, hi, dthreads))
+            work = lambda t, hi: sum(device_step(i) for i in range(t, hi, dthreads))  # noqa: E731
             list(dpool.map(lambda t: work(t, max(args.warmup, dthreads)), range(dthreads)))
             barrier()
             ev0.record()
@@ -268,75 +420,98 @@ def run_b200(args):
         conc_ms = max_over_ranks(ev0.elapsed_time(ev1))
         conc = {"value": args.steps * ROWS_PER_BATCH * world / (conc_ms / 1e3), "unit": "rows/s", "host_threads": dthreads,
                 "ms_per_step": conc_ms / args.steps}
-    rows_total = args.steps * ROWS_PER_BATCH * world
-    value = rows_total / (dev_ms / 1e3)
 
-    # roofline of the dominant kernel: algorithmic bytes of one launch = n·(8 value + 4 offsets + 12 bytes)
-    # read + kept·(8 + 4 + 12) written (36 B/row at σ = 0.5; exact σ from the run)
     kept = out_rows / max(args.steps, 1)
     alg_bytes = ROWS_PER_BATCH * 24 + kept * 24 + 4
-    peak, peak_src = load_peaks()
-    k_avg_ms = kms.value / max(kn.value, 1)
     achieved = alg_bytes / (k_avg_ms / 1e3) / 1e9 if k_avg_ms > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_filter_project_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    traffic, traffic_src = load_traffic()
 
-    # ---- e2e: host (pinned) Arrow buffers in, host Arrow buffers out, copies inside the timed region ----
-    n_host = 4
-    host_batches, keep = [], []
-    for b in range(n_host):
-        db = resident[b]
-        arrays = []
-        for c in db.columns:
-            if c.dtype == "int64":
-                t = torch.empty(c.length, dtype=torch.int64, pin_memory=True)
-                t.copy_(c.data)
-                keep.append(t)
-                arrays.append(pa.Array.from_buffers(pa.int64(), c.length, [None, pa.foreign_buffer(t.data_ptr(), c.length * 8, base=t)]))
-            else:
-                to = torch.empty(c.length + 1, dtype=torch.int32, pin_memory=True)
-                to.copy_(c.offsets)
-                dsrc = c.data.tensor() if hasattr(c.data, "tensor") else c.data
-                td = torch.empty(dsrc.numel(), dtype=torch.uint8, pin_memory=True)
-                td.copy_(dsrc)
-                keep += [to, td]
-                arrays.append(pa.Array.from_buffers(pa.utf8(), c.length, [None, pa.foreign_buffer(to.data_ptr(), (c.length + 1) * 4, base=to),
-                                                                          pa.foreign_buffer(td.data_ptr(), td.numel(), base=td)]))
-        torch.cuda.synchronize()
-        host_batches.append(pa.RecordBatch.from_arrays(arrays, names=[c.name for c in db.columns]))
+    # ---- e2e: host Arrow buffers in, host Arrow buffers out, copies inside the timed region ----
+    n_host = 3
     h2d_per_step = ROWS_PER_BATCH * 8 + (ROWS_PER_BATCH + 1) * 4 + ROWS_PER_BATCH * 12
+
+    def host_batches(pinned):
+        batches, keepalive = [], []
+        for b in range(n_host):
+            db = resident[b]
+            arrays = []
+            for c in db.columns:
+                if c.dtype == "int64":
+                    if pinned:
+                        t = torch.empty(c.length, dtype=torch.int64, pin_memory=True)
+                        t.copy_(c.data)
+                        keepalive.append(t)
+                        buf = pa.foreign_buffer(t.data_ptr(), c.length * 8, base=t)
+                    else:
+                        a = c.data.cpu().numpy().copy()  # numpy-owned heap memory: pageable, like an arrow-rs buffer
+                        keepalive.append(a)
+                        buf = pa.py_buffer(a)
+                    arrays.append(pa.Array.from_buffers(pa.int64(), c.length, [None, buf]))
+                else:
+                    dsrc = c.data.tensor() if hasattr(c.data, "tensor") else c.data
+                    if pinned:
+                        to = torch.empty(c.length + 1, dtype=torch.int32, pin_memory=True)
+                        to.copy_(c.offsets)
+                        td = torch.empty(dsrc.numel(), dtype=torch.uint8, pin_memory=True)
+                        td.copy_(dsrc)
+                        keepalive += [to, td]
+                        bo, bd = pa.foreign_buffer(to.data_ptr(), (c.length + 1) * 4, base=to), pa.foreign_buffer(td.data_ptr(), td.numel(), base=td)
+                    else:
+                        ao, ad = c.offsets.cpu().numpy().copy(), dsrc.cpu().numpy().copy()
+                        keepalive += [ao, ad]
+                        bo, bd = pa.py_buffer(ao), pa.py_buffer(ad)
+                    arrays.append(pa.Array.from_buffers(pa.utf8(), c.length, [None, bo, bd]))
+            torch.cuda.synchronize()
+            batches.append(pa.RecordBatch.from_arrays(arrays, names=[c.name for c in db.columns]))
+        return batches, keepalive
+
     e2e_threads = args.e2e_threads
-    d2h_acc = [0] * e2e_threads
-
-    def e2e_worker(tid, steps):
-        for i in steps:
-            r = proc.process(host_batches[i % n_host])
-            rb = r.batches[0].record_batch
-            d2h_acc[tid] += rb.nbytes
-            del r, rb
-
     e2e_steps = max(args.e2e_steps, e2e_threads)
-    with ThreadPoolExecutor(max_workers=e2e_threads) as pool:
-        list(pool.map(lambda t: e2e_worker(t, range(t, max(args.warmup, e2e_threads), e2e_threads)), range(e2e_threads)))
-        d2h_acc[:] = [0] * e2e_threads
-        barrier()
-        t0 = time.perf_counter()
-        ev0.record()
-        list(pool.map(lambda t: e2e_worker(t, range(t, e2e_steps, e2e_threads)), range(e2e_threads)))
-        torch.cuda.synchronize()
-        ev1.record()
-        ev1.synchronize()
-        e2e_ms_local = ev0.elapsed_time(ev1)
-        e2e_wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop()  # sampled across both timed regions (device-resident and end-to-end)
-    e2e_ms = max_over_ranks(max(e2e_ms_local, e2e_wall_ms))
-    e2e_value = e2e_steps * ROWS_PER_BATCH * world / (e2e_ms / 1e3)
-    d2h_per_step = sum(d2h_acc) / e2e_steps
+
+    def e2e_run(pinned):
+        batches, keepalive = host_batches(pinned)
+        d2h_acc = [0] * e2e_threads
+
+        def worker(tid, steps):
+            for i in steps:
+                r = proc.process(batches[i % n_host])
+                rb = r.batches[0].record_batch
+                d2h_acc[tid] += rb.nbytes
+                del r, rb
+
+        with ThreadPoolExecutor(max_workers=e2e_threads) as pool:
+            list(pool.map(lambda t: worker(t, range(t, max(args.warmup, e2e_threads), e2e_threads)), range(e2e_threads)))
+            d2h_acc[:] = [0] * e2e_threads
+            barrier()
+            t0 = time.perf_counter()
+            ev0.record()
+            list(pool.map(lambda t: worker(t, range(t, e2e_steps, e2e_threads)), range(e2e_threads)))
+            torch.cuda.synchronize()
+            ev1.record()
+            ev1.synchronize()
+            ms_local = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
+        ms = max_over_ranks(ms_local)
+        del batches, keepalive
+        return e2e_steps * ROWS_PER_BATCH * world / (ms / 1e3), ms / e2e_steps, sum(d2h_acc) / e2e_steps
+
+    e2e_pageable, e2e_pageable_ms, d2h_per_step = e2e_run(False)
+    e2e_pinned, e2e_pinned_ms, _ = e2e_run(True)
+    clocks = sampler.stop()  # sampled across the device-resident and the end-to-end timed regions
+
+    # =====================================================================================================
+    # sharded workloads: GROUP BY (configs[2]) and JOIN (configs[3]) with the repartition exchange
+    # =====================================================================================================
+    del resident
+    sharded = {}
+    if not args.no_sharded:
+        try:
+            sharded["groupby"] = run_groupby(args, rank, world, lib, synth_device, barrier, max_over_ranks, sum_over_ranks, kernel_ms, peak)
+        except Exception as e:  # noqa: BLE001 — the contract line must survive a failure of the extra workloads
+            sharded["groupby"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        try:
+            sharded["join"] = run_join(args, rank, world, lib, synth_device, barrier, max_over_ranks, sum_over_ranks, kernel_ms, peak)
+        except Exception as e:  # noqa: BLE001
+            sharded["join"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -344,25 +519,32 @@ def run_b200(args):
     barrier()
 
     if rank == 0:
+        cfg = workload_config(world, args.steps, kept / ROWS_PER_BATCH, n_resident)
+        if numa:
+            cfg["numa_binding"] = numa
+        if sharded:
+            cfg["sharded"] = {k: ({kk: v[kk] for kk in ("value", "unit", "ms_per_step", "roofline_frac", "verified", "exchange_gbs_out_per_rank", "error") if kk in v})
+                              for k, v in sharded.items()}
         line = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int64", "data": "synthetic",
-            "config": {"workload": "filter+project SELECT sensor,value WHERE value>=10 on 2^30-row int64/Utf8 table, 64 batches of 2^24 rows per GPU (BASELINE configs[1])",
-                       "query": QUERY, "rows_per_step": ROWS_PER_BATCH, "resident_batches": n_resident,
-                       "schema": "timestamp:Int64,value:Int64,sensor:Utf8(12B)", "selectivity": kept / ROWS_PER_BATCH,
-                       "l2": "inputs larger than L2 (537 MB per batch, distinct batch each step)", "parallelism": f"{world} rank(s), row shards, no collective"},
-            "roofline": {"bound": "hbm", "kernel": "filter_project_tma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": kn.value},
-            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": d2h_per_step,
-                    "steps": e2e_steps, "host_threads": e2e_threads, "ms_per_step": e2e_ms / e2e_steps,
-                    "note": "pinned host Arrow buffers → ark_sql_process → host Arrow buffers; PCIe-bound"},
+            "dtype": "int64", "data": "synthetic", "config": cfg,
+            "roofline": {"bound": "hbm", "kernel": "filter_project_pipe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": k_n},
+            "e2e": {"value": e2e_pageable, "unit": "rows/s", "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": d2h_per_step,
+                    "steps": e2e_steps, "host_threads": e2e_threads, "ms_per_step": e2e_pageable_ms, "input_memory": "pageable",
+                    "pinned": {"value": e2e_pinned, "ms_per_step": e2e_pinned_ms},
+                    "pageable_over_pinned": e2e_pageable / e2e_pinned if e2e_pinned else None,
+                    "note": "pageable host Arrow buffers -> ark_sql_process (chunked staging through the pinned pool) -> host Arrow buffers; PCIe-bound"},
+            "verified": verified["ok"], "verification": verified,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if conc is not None:
             line["concurrent_callers"] = conc
+        for k, v in sharded.items():
+            line[k] = v
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -371,15 +553,210 @@ def run_b200(args):
     return 0
 
 
+def run_groupby(args, rank, world, lib, synth_device, barrier, max_over_ranks, sum_over_ranks, kernel_ms, peak):
+    """BASELINE configs[2]: SELECT sensor, SUM(value), COUNT(*) GROUP BY sensor, 10^6 keys; per step every rank
+    aggregates one 2^24-row batch, the partial states cross NVLink (device-side push exchange), owners merge."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from arkflow_b200.dist import ExchangeContext, NativeEngine, distributed_group_by
+
+    K = KEY_SPACE
+    steps, warm = args.groupby_steps, 3
+    eng = NativeEngine(GROUP_QUERY)
+    base = (1 << 40) + rank * (1 << 32)  # rows disjoint from the filter workload's and across ranks
+    batches = [synth_device(ROWS_PER_BATCH, base + b * ROWS_PER_BATCH, K) for b in range(3)]
+    ctx = ExchangeContext.from_process_group(64 << 20) if world > 1 else None
+
+    def step(i):
+        b = batches[i % 3]
+        if world > 1:
+            return distributed_group_by(eng, b, ctx=ctx)
+        return eng.process(b)
+
+    for i in range(warm):
+        step(i).close()
+    lib.ark_kernel_timing_reset()
+    lib.ark_kernel_timing_enable(1)
+    barrier()
+    import torch as _t
+
+    ev0, ev1 = _t.cuda.Event(enable_timing=True), _t.cuda.Event(enable_timing=True)
+    ev0.record()
+    last = None
+    for i in range(steps):
+        out = step(i)
+        if i == steps - 1:
+            last = out
+        else:
+            out.close()
+    _t.cuda.synchronize()
+    ev1.record()
+    ev1.synchronize()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    lib.ark_kernel_timing_enable(0)
+    k_ms, k_n = kernel_ms("hash_agg_kernel")
+    push_ms, _ = kernel_ms("exchange_push_kernel")
+    merge_ms, _ = kernel_ms("exchange_merge_kernel")
+    value = steps * ROWS_PER_BATCH * world / (ms / 1e3)
+    alg = ROWS_PER_BATCH * 24
+    achieved = alg / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
+    res = {"metric": "rows/sec through sql processor, GROUP BY sensor SUM(value),COUNT(*) (BASELINE configs[2] shape)", "value": value, "unit": "rows/s",
+           "ms_per_step": ms / steps, "steps": steps, "rows_per_step_per_gpu": ROWS_PER_BATCH, "keys": K, "n_gpus": world,
+           "query": GROUP_QUERY,
+           "roofline": {"bound": "hbm", "kernel": "hash_agg_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak if peak else None, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": k_ms, "launches_timed": k_n,
+                        "note": "24 B/row (SURVEY.md §8(d)); the table's random accesses are L2 traffic, not counted"},
+           "roofline_frac": achieved / peak if peak else None}
+    if world > 1:
+        st = ctx.stats()
+        rec_bytes = 32
+        sent = st["records_received"] * rec_bytes * (world - 1) / world  # by symmetry of the hash partition: out ≈ in
+        res["exchange"] = {"kind": "device-side push over peer memory (csrc/group_exchange.cu): no NCCL call, no host round trip on the data path",
+                           "records_received_per_rank": st["records_received"], "bytes_out_per_rank": sent,
+                           "push_kernel_ms": push_ms, "merge_kernel_ms": merge_ms,
+                           "gbs_out_per_rank_over_push_kernel": sent / (push_ms / 1e3) / 1e9 if push_ms > 0 else None,
+                           "nvlink_gbs_per_direction_measured_peer_copy": NVLINK_GBS,
+                           "frac_of_nvlink": (sent / (push_ms / 1e3) / 1e9 / NVLINK_GBS) if push_ms > 0 else None,
+                           "note": "the push kernel also scans the 64 MB partial table; config 3 moves partial states (<= K x 32 B per rank), so the exchange is latency-, not link-bound"}
+        res["exchange_gbs_out_per_rank"] = res["exchange"]["gbs_out_per_rank_over_push_kernel"]
+    # ---- parity: (a) invariants of the last timed result at full scale, (b) a down-sampled shard against numpy ----
+    oc = {c.name: c for c in last.columns}
+    cnt = int(oc["count(*)"].data[: last.num_rows].sum().item()) if last.num_rows else 0
+    sm = int(oc["sum(flow.value)"].data[: last.num_rows].sum().item()) if last.num_rows else 0
+    bi = (steps - 1) % 3
+    vcol = [c for c in batches[bi].columns if c.name == "value"][0]
+    local_sum = int(vcol.data.sum().item())
+    tot_cnt, tot_sum, want_sum = sum_over_ranks(float(cnt)), sum_over_ranks(float(sm)), sum_over_ranks(float(local_sum))
+    groups_total = sum_over_ranks(float(last.num_rows))
+    last.close()
+    inv_ok = int(tot_cnt) == ROWS_PER_BATCH * world and int(tot_sum) == int(want_sum) and int(groups_total) <= K
+    # (b) small shard, every group compared
+    n_small, k_small = 1 << 18, 5000
+    sb = synth_device(n_small, (1 << 44) + rank * n_small, k_small)
+    small = step_small = None
+    if world > 1:
+        small = distributed_group_by(eng, sb, ctx=ctx)
+    else:
+        small = eng.process(sb)
+    vals, keys = [], []
+    for r in range(world):
+        v, k = np_values_keys(n_small, (1 << 44) + r * n_small, k_small)
+        vals.append(v)
+        keys.append(k)
+    v, k = np.concatenate(vals), np.concatenate(keys)
+    want_cnt = np.bincount(k, minlength=k_small)
+    want_sum_k = np.bincount(k, weights=v.astype(np.float64), minlength=k_small).astype(np.int64)
+    so = {c.name: c for c in small.columns}
+    sbts = so["sensor"].data.tensor() if hasattr(so["sensor"].data, "tensor") else so["sensor"].data
+    kb = sbts[: small.num_rows * 12].view(-1, 12).to(torch.int64)
+    gk = torch.zeros(small.num_rows, dtype=torch.int64, device=kb.device)
+    for d in range(7):
+        gk = gk * 10 + (kb[:, 5 + d] - 48)
+    gk = gk.cpu().numpy()
+    gc = so["count(*)"].data[: small.num_rows].cpu().numpy()
+    gs = so["sum(flow.value)"].data[: small.num_rows].cpu().numpy()
+    small_ok = bool((want_cnt[gk] == gc).all() and (want_sum_k[gk] == gs).all() and len(np.unique(gk)) == len(gk))
+    n_groups_all = sum_over_ranks(float(small.num_rows))
+    small_ok = small_ok and int(n_groups_all) == int((want_cnt > 0).sum())
+    all_ok = sum_over_ranks(0.0 if small_ok else 1.0) == 0.0
+    small.close()
+    res["verified"] = bool(inv_ok and all_ok)
+    res["verification"] = {"full_scale_invariants": {"ok": bool(inv_ok), "sum_count": int(tot_cnt), "rows": ROWS_PER_BATCH * world, "sum_of_sums": int(tot_sum),
+                                                     "sum_of_value_column": int(want_sum), "groups": int(groups_total)},
+                           "downsampled_shard": {"ok": bool(all_ok), "rows_per_rank": n_small, "keys": k_small, "groups": int(n_groups_all),
+                                                 "what": "every group of every rank's share compared with numpy bincount over all ranks' rows; owners disjoint"}}
+    if ctx is not None:
+        barrier()
+        ctx.close()
+    return res
+
+
+def run_join(args, rank, world, lib, synth_device, barrier, max_over_ranks, sum_over_ranks, kernel_ms, peak):
+    """BASELINE configs[3] shape: hash join of two streams on sensor, probe 2^24 rows x build 2^20 rows per rank and
+    step (probe : build ≈ 10 : 1 as 1B : 100M), SELECT *.  N > 1: both sides are hash-partitioned on the key and
+    exchanged (descriptor pull over peer memory, csrc/ipc_exchange.cu), then joined locally."""
+    import torch
+
+    from arkflow_b200.dist import NativeEngine, distributed_join
+
+    steps, warm = args.join_steps, 2
+    n_probe, n_build, K = ROWS_PER_BATCH, 1 << 20, 1 << 20
+    eng = NativeEngine(JOIN_QUERY)
+    base = (1 << 42) + rank * (1 << 34)
+    probes = [synth_device(n_probe, base + b * n_probe, K) for b in range(2)]
+    build = synth_device(n_build, (1 << 43) + rank * n_build, K)
+
+    def step(i):
+        tables = {"flow_input1": probes[i % 2], "flow_input2": build}
+        if world > 1:
+            return distributed_join(eng, tables, {"flow_input1": "sensor", "flow_input2": "sensor"})
+        return eng.join(tables)
+
+    out_rows = 0
+    for i in range(warm):
+        o = step(i)
+        o.close()
+    lib.ark_kernel_timing_reset()
+    lib.ark_kernel_timing_enable(1)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+        o = step(i)
+        out_rows += o.num_rows
+        o.close()
+    torch.cuda.synchronize()
+    ev1.record()
+    ev1.synchronize()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    lib.ark_kernel_timing_enable(0)
+    value = steps * n_probe * world / (ms / 1e3)
+    out_total = sum_over_ranks(float(out_rows)) / steps
+    alg = (n_probe + n_build) * 32 + (out_total / world) * 64
+    res = {"metric": "probe rows/sec through the join (BASELINE configs[3] shape)", "value": value, "unit": "rows/s", "ms_per_step": ms / steps,
+           "steps": steps, "probe_rows_per_step_per_gpu": n_probe, "build_rows_per_step_per_gpu": n_build, "n_gpus": world, "query": JOIN_QUERY,
+           "output_rows_per_step": out_total,
+           "roofline": {"bound": "hbm", "achieved": alg / (ms / steps / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (ms / steps / 1e3) / 1e9 / peak if peak else None, "algorithmic_bytes_per_step_per_gpu": alg,
+                        "note": "whole call (partition + exchange + build + probe + gathers), inputs read once + output written once"},
+           "kernels_ms": {k: kernel_ms(k)[0] for k in ("join_build_kernel", "join_probe_count_kernel", "join_probe_fill_kernel", "take_bytes_tile_kernel",
+                                                       "take_fixed8_kernel", "concat_copy_kernel", "partition_ids_kernel", "partition_scatter_kernel")}}
+    res["roofline_frac"] = res["roofline"]["frac"]
+    if world > 1:
+        sent = (n_probe + n_build) * 32 * (world - 1) / world
+        res["exchange"] = {"kind": "hash partition -> descriptor pull over peer memory (csrc/ipc_exchange.cu)", "bytes_out_per_rank_per_step": sent,
+                           "nvlink_floor_ms": sent / (NVLINK_GBS * 1e9) * 1e3, "note": "NVLink-bound config (SURVEY.md §8(d)): 3/4.. (N-1)/N of the input rows cross the links"}
+    # parity: multiplicity identity — every probe row meets exactly mult(key) build rows; checked as a count against numpy
+    import numpy as np
+
+    want = 0
+    if rank == 0:
+        bk = np.concatenate([np_values_keys(n_build, (1 << 43) + r * n_build, K)[1] for r in range(world)])
+        mult = np.bincount(bk, minlength=K)
+        want = sum(int(mult[np_values_keys(n_probe, (1 << 42) + r * (1 << 34) + ((steps - 1) % 2) * n_probe, K)[1]].sum()) for r in range(world))
+    last_rows = step(steps - 1)
+    got = sum_over_ranks(float(last_rows.num_rows))
+    last_rows.close()
+    res["verified"] = bool(rank != 0 or int(got) == int(want))
+    res["verification"] = {"join_output_rows": int(got), "numpy_expected": int(want) if rank == 0 else None,
+                           "what": "output row count of one step = sum over probe rows of the build-side multiplicity of their key (numpy bincount over all ranks' rows)"}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=16)
+    ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--e2e-threads", type=int, default=3)
     ap.add_argument("--device-threads", type=int, default=4)
+    ap.add_argument("--groupby-steps", type=int, default=12)
+    ap.add_argument("--join-steps", type=int, default=4)
+    ap.add_argument("--no-sharded", action="store_true", help="skip the GROUP BY / JOIN workloads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -260,6 +260,8 @@ int ark_dist_create(int rank, int world, int64_t region_bytes, ark_dist_t** out)
 int64_t ark_dist_handle_bytes(void);
 int ark_dist_export(ark_dist_t* d, uint8_t* blob, int64_t blob_cap, int64_t* blob_size);
 int ark_dist_connect(ark_dist_t* d, const uint8_t* blobs, int64_t blob_stride);
+/* out4 = {steps issued, records received in the last step, groups owned after the last merge, region_bytes} */
+int ark_dist_stats(ark_dist_t* d, int64_t* out4);
 void ark_dist_destroy(ark_dist_t* d);
 int ark_sql_group_by_exchange_device(ark_proc_t* p, ark_dist_t* d, struct ArrowDeviceArray* in,
                                      struct ArrowSchema* in_schema, struct ArrowDeviceArray* out,
