@@ -1,4 +1,4 @@
-// hash_join.cu — inner equi-join (build + probe + gather) and hash repartition, device-resident.
+// hash_join.cu — equi-join (inner, LEFT / RIGHT outer: build + probe + gather) and hash repartition, device-resident.
 //
 // Stands in for DataFusion's HashJoinExec and RepartitionExec(Hash) reached from
 // JoinOperation::join_operation (crates/arkflow-plugin/src/buffer/join.rs:111-118).
@@ -8,6 +8,9 @@
 //           (probe_row, build_row) pairs — then one gather per output column.
 // NULL keys never match.  `SELECT *` = left columns then right columns (SQL order), whichever side
 // was used to build.  Output row order is unspecified (as in DataFusion).
+// LEFT / RIGHT [OUTER] JOIN (the shipped temporary_list example, examples/redis_temporary_example.yaml:29, is a
+// RIGHT JOIN): the preserved side is the probe side; a probe row without a match yields one output row whose
+// build-side index is NO_ROW, which the gathers turn into NULLs (validity bitmaps on every build-side column).
 #include <cub/device/device_scan.cuh>
 
 #include "engine.h"
@@ -59,7 +62,7 @@ __global__ void join_build_kernel(ColView kc, int key_kind, int64_t n, Key16* ke
 
 // Probe pass: counts[row] = number of matches, match_slot[row] = table slot of the probe key (NO_ROW if none).
 __global__ void join_probe_count_kernel(ColView pc, ColView bc, int key_kind, int64_t n, const Key16* keys, const unsigned int* head,
-                                        const unsigned int* next, unsigned long long mask, long long* counts, unsigned int* match_slot) {
+                                        const unsigned int* next, unsigned long long mask, long long* counts, unsigned int* match_slot, int outer) {
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
     long long c = 0;
     unsigned int found = NO_ROW;
@@ -78,7 +81,7 @@ __global__ void join_probe_count_kernel(ColView pc, ColView bc, int key_kind, in
         slot = (slot + 1) & mask;
       }
     }
-    counts[row] = c;
+    counts[row] = (outer && c == 0) ? 1 : c;  // outer join: an unmatched probe row survives once, with NULLs
     match_slot[row] = found;
   }
 }
@@ -86,11 +89,14 @@ __global__ void join_probe_count_kernel(ColView pc, ColView bc, int key_kind, in
 // Fill pass: the (probe row, build row) pairs at offsets[row]; the slot comes from the count pass (no second
 // hash + probe: 4 sequential bytes per row instead of a random table access).
 __global__ void join_probe_fill_kernel(int64_t n, const unsigned int* head, const unsigned int* next, const unsigned int* match_slot,
-                                       const long long* offsets, unsigned int* out_probe, unsigned int* out_build) {
+                                       const long long* offsets, unsigned int* out_probe, unsigned int* out_build, int outer) {
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
     const unsigned int slot = match_slot[row];
-    if (slot == NO_ROW) continue;
     long long o = offsets[row];
+    if (slot == NO_ROW) {
+      if (outer) { out_probe[o] = (unsigned int)row; out_build[o] = NO_ROW; }
+      continue;
+    }
     for (unsigned int b = head[slot]; b != NO_ROW; b = next[b]) { out_probe[o] = (unsigned int)row; out_build[o] = b; ++o; }
   }
 }
@@ -98,15 +104,24 @@ __global__ void join_probe_fill_kernel(int64_t n, const unsigned int* head, cons
 // ---- gathers -----------------------------------------------------------------------------------------
 __global__ void take_fixed8_kernel(const unsigned long long* src, const unsigned int* idx, long long n, unsigned long long* out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = src[idx[i]];
+  if (i < n) { const unsigned int r = idx[i]; out[i] = r == NO_ROW ? 0ull : src[r]; }
 }
 __global__ void take_bits_kernel(const uint8_t* bits, int bit0, const unsigned int* idx, long long n, uint8_t* out_bytes) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { const long long p = (long long)idx[i] + bit0; out_bytes[i] = (bits[p >> 3] >> (p & 7)) & 1; }
+  if (i < n) {
+    const unsigned int r = idx[i];
+    const long long p = (long long)r + bit0;
+    out_bytes[i] = r == NO_ROW ? 0 : ((bits[p >> 3] >> (p & 7)) & 1);  // NO_ROW (outer join, no match): NULL / false
+  }
+}
+// validity of a gathered column that had none: only the NO_ROW rows are NULL
+__global__ void take_matched_kernel(const unsigned int* idx, long long n, uint8_t* out_bytes) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out_bytes[i] = idx[i] != NO_ROW;
 }
 __global__ void take_lengths_kernel(const int32_t* offsets, const unsigned int* idx, long long n, int32_t* lens) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { const unsigned int r = idx[i]; lens[i] = offsets[r + 1] - offsets[r]; }
+  if (i < n) { const unsigned int r = idx[i]; lens[i] = r == NO_ROW ? 0 : offsets[r + 1] - offsets[r]; }
 }
 // global → shared copy of one string, word-granular on the (shared) destination: aligned source words are
 // funnel-shifted into place, so a 12-byte key costs 3–4 loads and 3 stores instead of 12 + 12.
@@ -153,6 +168,7 @@ __global__ void __launch_bounds__(256) take_bytes_tile_kernel(const uint8_t* dat
     const int lane = tid & 31;
     for (int i = tid >> 5; i < rows; i += 8) {
       const unsigned int r = idx[row0 + i];
+      if (r == NO_ROW) continue;
       const int32_t s0 = offsets[r], len = offsets[r + 1] - s0;
       uint8_t* d = out + out_offsets[row0 + i];
       for (int b = lane; b < len; b += 32) d[b] = data[s0 + b];
@@ -171,8 +187,10 @@ __global__ void __launch_bounds__(256) take_bytes_tile_kernel(const uint8_t* dat
     s0[k] = 0; len[k] = 0; dst[k] = 0;
     if (i < rows) {
       const unsigned int r = idx[row0 + i];
-      s0[k] = offsets[r];
-      len[k] = offsets[r + 1] - s0[k];
+      if (r != NO_ROW) {
+        s0[k] = offsets[r];
+        len[k] = offsets[r + 1] - s0[k];
+      }
       dst[k] = out_offsets[row0 + i] - bb;
     }
   }
@@ -238,8 +256,9 @@ unsigned grid_for(int64_t n, int threads = 256) { return (unsigned)std::max<int6
 
 }  // namespace
 
-// out[i] = column[idx[i]] for i < n  (idx on the device)
-Column take_column(const Column& src, const unsigned int* idx, int64_t n, const std::string& name, cudaStream_t stream) {
+// out[i] = column[idx[i]] for i < n  (idx on the device).  may_miss: idx may hold NO_ROW (outer join without a match):
+// such rows come out NULL, so the column always gets a validity bitmap.
+Column take_column(const Column& src, const unsigned int* idx, int64_t n, const std::string& name, cudaStream_t stream, bool may_miss) {
   Column c;
   c.field = src.field; c.field.name = name; c.length = n;
   const unsigned g = (unsigned)std::max<int64_t>(1, ceil_div(n, 256));
@@ -285,9 +304,11 @@ Column take_column(const Column& src, const unsigned int* idx, int64_t n, const 
       if (src.field.format != "n") fail(ARK_ERR_UNSUPPORTED, "gather of a column with Arrow type '" + src.field.format + "'");
       break;
   }
-  if (src.validity && n > 0) {
+  if (may_miss) c.field.nullable = true;
+  if ((src.validity || may_miss) && n > 0) {
     BufferPtr vb = device_alloc((size_t)n), bits = device_alloc((size_t)(n + 7) / 8 + 1);
-    { KernelTimer t("take_bits_kernel", stream); take_bits_kernel<<<g, 256, 0, stream>>>(src.validity, src.validity_bit0, idx, n, (uint8_t*)vb.get()); }
+    if (src.validity) { KernelTimer t("take_bits_kernel", stream); take_bits_kernel<<<g, 256, 0, stream>>>(src.validity, src.validity_bit0, idx, n, (uint8_t*)vb.get()); }
+    else { KernelTimer t("take_matched_kernel", stream); take_matched_kernel<<<g, 256, 0, stream>>>(idx, n, (uint8_t*)vb.get()); }
     launch_pack_bits((const uint8_t*)vb.get(), n, (uint8_t*)bits.get(), nullptr, stream);
     c.validity = (const uint8_t*)bits.get(); c.validity_bit0 = 0; c.null_count = -1;
     c.owners.push_back(bits); c.owners.push_back(vb);
@@ -300,7 +321,9 @@ Batch run_join(const Plan& plan, Batch& left, Batch& right, cudaStream_t stream)
   Column& lk = left.cols[plan.left_key];
   Column& rk = right.cols[plan.right_key];
   const int key_kind = key_kind_of(lk.field.type);
-  const bool build_left = left.num_rows <= right.num_rows;
+  // outer joins probe with the preserved side (LEFT: left, RIGHT: right); inner joins build on the smaller side
+  const int outer = plan.join_type != 0;
+  const bool build_left = plan.join_type == 1 ? false : plan.join_type == 2 ? true : left.num_rows <= right.num_rows;
   Batch& B = build_left ? left : right;
   Batch& Pb = build_left ? right : left;
   const ColView bc = (build_left ? lk : rk).view(), pc = (build_left ? rk : lk).view();
@@ -324,7 +347,7 @@ Batch run_join(const Plan& plan, Batch& left, Batch& right, cudaStream_t stream)
   if (np) {
     KernelTimer t("join_probe_count_kernel", stream);
     join_probe_count_kernel<<<grid_for(np), 256, 0, stream>>>(pc, bc, key_kind, np, (const Key16*)keys.get(), (const unsigned int*)head.get(),
-                                                              (const unsigned int*)next.get(), capacity - 1, (long long*)counts.get(), (unsigned int*)match_slot.get());
+                                                              (const unsigned int*)next.get(), capacity - 1, (long long*)counts.get(), (unsigned int*)match_slot.get(), outer);
   }
   size_t tb = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tb, (long long*)counts.get(), (long long*)offsets.get(), (int)(np + 1), stream);
@@ -340,7 +363,7 @@ Batch run_join(const Plan& plan, Batch& left, Batch& right, cudaStream_t stream)
   if (np && pairs) {
     KernelTimer t("join_probe_fill_kernel", stream);
     join_probe_fill_kernel<<<grid_for(np), 256, 0, stream>>>(np, (const unsigned int*)head.get(), (const unsigned int*)next.get(), (const unsigned int*)match_slot.get(),
-                                                             (const long long*)offsets.get(), (unsigned int*)probe_idx.get(), (unsigned int*)build_idx.get());
+                                                             (const long long*)offsets.get(), (unsigned int*)probe_idx.get(), (unsigned int*)build_idx.get(), outer);
   }
   ARK_CUDA(cudaGetLastError());
   const unsigned int* lidx = (const unsigned int*)(build_left ? build_idx.get() : probe_idx.get());
@@ -350,7 +373,8 @@ Batch run_join(const Plan& plan, Batch& left, Batch& right, cudaStream_t stream)
   for (const auto& jo : plan.join_out) {
     const Column& src = jo.side == 0 ? left.cols[jo.col] : right.cols[jo.col];
     if (!src.present) fail(ARK_ERR_UNSUPPORTED, "join output column '" + jo.name + "' has Arrow type '" + src.field.format + "'");
-    out.cols.push_back(take_column(src, jo.side == 0 ? lidx : ridx, pairs, jo.name, stream));
+    const bool build_side = (jo.side == 0) == build_left;
+    out.cols.push_back(take_column(src, jo.side == 0 ? lidx : ridx, pairs, jo.name, stream, outer && build_side));
   }
   ARK_CUDA(cudaStreamSynchronize(stream));
   return out;

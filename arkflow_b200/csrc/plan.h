@@ -107,6 +107,7 @@ struct Plan {
   std::string left_table, right_table;
   std::vector<Field> right_fields;
   int left_key = -1, right_key = -1;     // column indices in each table
+  int join_type = 0;                     // JoinClause::Type: 0 inner, 1 left outer, 2 right outer
   struct JoinOut { int side; int col; std::string name; };
   std::vector<JoinOut> join_out;
 };

@@ -567,6 +567,7 @@ Plan bind_join(const Query& q, const std::vector<std::string>& names, const std:
     return -1;
   };
   const JoinClause& jc = q.joins[0];
+  plan.join_type = (int)jc.type;
   if (!jc.using_cols.empty()) unsupported("JOIN … USING");
   const Expr* on = jc.on.get();
   if (!on || on->kind != Expr::Binary || on->op != "=" || on->args[0]->kind != Expr::Column || on->args[1]->kind != Expr::Column)

@@ -58,6 +58,7 @@ struct TableRef {
 };
 
 struct JoinClause {
+  enum Type { Inner = 0, Left = 1, Right = 2 } type = Inner;  // LEFT / RIGHT [OUTER]: the other side's columns turn NULL
   TableRef table;
   ExprPtr on;
   std::vector<std::string> using_cols;

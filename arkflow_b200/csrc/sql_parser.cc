@@ -213,11 +213,19 @@ struct Parser {
     while (true) {
       if (accept(Tok::Comma)) unsupported("comma (cross) join");
       bool inner = false;
+      JoinClause::Type jtype = JoinClause::Inner;
       if (is_kw("INNER")) { ++p; inner = true; }
-      if (is_kw("LEFT") || is_kw("RIGHT") || is_kw("FULL") || is_kw("CROSS") || is_kw("NATURAL"))
+      else if (is_kw("LEFT") || is_kw("RIGHT")) {  // LEFT [OUTER] JOIN / RIGHT [OUTER] JOIN
+        jtype = is_kw("LEFT") ? JoinClause::Left : JoinClause::Right;
+        ++p;
+        accept_kw("OUTER");
+        inner = true;  // JOIN must follow
+      }
+      if (is_kw("FULL") || is_kw("CROSS") || is_kw("NATURAL"))
         unsupported(cur().upper + " JOIN");
       if (accept_kw("JOIN")) {
         JoinClause j;
+        j.type = jtype;
         j.table = parse_table_ref();
         if (accept_kw("ON")) {
           j.on = parse_expr();
@@ -230,7 +238,7 @@ struct Parser {
         }
         q.joins.push_back(std::move(j));
       } else {
-        if (inner) syntax("Expected JOIN after INNER, found: " + describe());
+        if (inner) syntax("Expected JOIN, found: " + describe());
         break;
       }
     }

@@ -184,15 +184,22 @@ class _Parser:
         table, alias = self.table_ref()
         joins = []
         while True:
-            self.accept_kw("INNER")
-            for w in ("LEFT", "RIGHT", "FULL", "CROSS"):
+            jtype = "inner"
+            if not self.accept_kw("INNER"):
+                for w in ("LEFT", "RIGHT"):  # LEFT [OUTER] JOIN / RIGHT [OUTER] JOIN
+                    if self.accept_kw(w):
+                        jtype = w.lower()
+                        self.accept_kw("OUTER")
+            for w in ("FULL", "CROSS"):
                 if self.kw(w):
                     raise OracleError("Unsupported", w + " JOIN")
             if self.accept_kw("JOIN"):
                 jt, ja = self.table_ref()
                 if not self.accept_kw("ON"):
                     self.err("ON")
-                joins.append((jt, ja, self.expr()))
+                joins.append((jt, ja, self.expr(), jtype))
+            elif jtype != "inner":
+                self.err("JOIN")
             else:
                 break
         where = self.expr() if self.accept_kw("WHERE") else None
@@ -962,7 +969,10 @@ def sql_process(rb: pa.RecordBatch, query: str, table_name: str = "flow") -> Opt
 
 
 def sql_join(tables: dict[str, pa.RecordBatch], query: str) -> pa.RecordBatch:
-    """JoinOperation's `ctx.sql(query).collect()` (buffer/join.rs:111-131) for one inner equi-join."""
+    """JoinOperation's `ctx.sql(query).collect()` (buffer/join.rs:111-131) for one equi-join: inner, or LEFT / RIGHT
+    [OUTER] as in the shipped temporary_list example (examples/redis_temporary_example.yaml:29): rows of the preserved
+    side without a match appear once with NULLs for the other side's columns, whose fields become nullable (DataFusion
+    HashJoinExec / build_join_schema).  PARITY unpinned: the reference holds no join assertion."""
     q = parse(query)
     if not q.joins:
         if q.table not in tables:
@@ -971,7 +981,7 @@ def sql_join(tables: dict[str, pa.RecordBatch], query: str) -> pa.RecordBatch:
         return r if r is not None else _empty_schema_batch()
     if len(q.joins) != 1 or q.where is not None or q.group_by or q.limit >= 0:
         raise OracleError("Unsupported", "join shape")
-    jt, ja, on = q.joins[0]
+    jt, ja, on, jtype = q.joins[0]
     for t in (q.table, jt):
         if t not in tables:
             raise OracleError("Process", f"Execution query error: Error during planning: table '{t}' not found")
@@ -1006,19 +1016,30 @@ def sql_join(tables: dict[str, pa.RecordBatch], query: str) -> pa.RecordBatch:
         if kv is not None:
             build.setdefault(kv, []).append(j)
     li, ri = [], []
+    matched_r = set()
     for i, kv in enumerate(lkeys):
-        if kv is not None:
-            for j in build.get(kv, ()):
-                li.append(i)
+        hits = build.get(kv, ()) if kv is not None else ()
+        for j in hits:
+            li.append(i)
+            ri.append(j)
+            matched_r.add(j)
+        if not hits and jtype == "left":
+            li.append(i)
+            ri.append(None)
+    if jtype == "right":
+        for j in range(len(rkeys)):
+            if j not in matched_r:
+                li.append(None)
                 ri.append(j)
     li, ri = pa.array(li, type=pa.int64()), pa.array(ri, type=pa.int64())
     cols, fields = [], []
+    null_side = {"left": 1, "right": 0}.get(jtype)  # the side whose columns turn NULL for unmatched rows
 
     def add_all(s):
         T, idx = (L, li) if s == 0 else (R, ri)
         for i, f in enumerate(T.schema):
             cols.append(T.column(i).take(idx))
-            fields.append(pa.field(f.name, f.type, f.nullable))
+            fields.append(pa.field(f.name, f.type, f.nullable or s == null_side))
 
     for it in q.select:
         if it.star:
@@ -1036,7 +1057,7 @@ def sql_join(tables: dict[str, pa.RecordBatch], query: str) -> pa.RecordBatch:
             T, idx = (L, li) if s == 0 else (R, ri)
             f = T.schema.field(nm)
             cols.append(T.column(nm).take(idx))
-            fields.append(pa.field(it.alias or nm, f.type, f.nullable))
+            fields.append(pa.field(it.alias or nm, f.type, f.nullable or s == null_side))
         else:
             raise OracleError("Unsupported", "computed join projection")
     return pa.RecordBatch.from_arrays(cols, schema=pa.schema(fields))

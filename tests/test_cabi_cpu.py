@@ -44,7 +44,8 @@ def test_config_shape_errors(lib):
     "SELECT * FROM flow", "select Sensor, VALUE from FLOW where value>=10", "SELECT sum(value),avg(value) ,111 as x FROM flow  group by sensor",
     "SELECT *,cast( __value__  as string) as y FROM flow ", "SELECT count(*) FROM flow WHERE value >= 10 group by sensor",
     "SELECT * FROM flow_input1 join flow_input2 on (flow_input1.id = flow_input2.id)",
-    "SELECT a.x, b.y FROM t1 AS a INNER JOIN t2 b ON a.k = b.k", "SELECT \"Weird Name\", -value, value % 3 FROM flow WHERE NOT (value IS NULL) LIMIT 5;",
+    "SELECT a.x, b.y FROM t1 AS a INNER JOIN t2 b ON a.k = b.k", "SELECT * FROM a LEFT JOIN b ON a.k = b.k",
+    "SELECT * FROM flow right join redis_table on (flow.sensor = redis_table.x)", "SELECT * FROM a LEFT OUTER JOIN b ON a.k = b.k", "SELECT \"Weird Name\", -value, value % 3 FROM flow WHERE NOT (value IS NULL) LIMIT 5;",
 ])
 def test_accepted_sql(lib, q):
     SqlProcessor({"query": q})
@@ -55,7 +56,8 @@ def test_accepted_sql(lib, q):
     ("SELECT (1 FROM flow", "Process"), ("DROP TABLE flow", "Process"), ("INSERT INTO flow VALUES (1)", "Process"), ("", "Process"),
     ("SELECT * FROM flow ORDER BY value", "Unsupported"), ("SELECT DISTINCT sensor FROM flow", "Unsupported"),
     ("SELECT * FROM (SELECT * FROM flow) t", "Unsupported"), ("SELECT CASE WHEN value > 1 THEN 1 END FROM flow", "Unsupported"),
-    ("SELECT * FROM a LEFT JOIN b ON a.k = b.k", "Unsupported"),
+    ("SELECT * FROM a FULL JOIN b ON a.k = b.k", "Unsupported"), ("SELECT * FROM a CROSS JOIN b", "Unsupported"),
+    ("SELECT * FROM a LEFT b ON a.k = b.k", "Process"),
 ])
 def test_rejected_sql(lib, q, kind):
     with pytest.raises(ArkError) as e:

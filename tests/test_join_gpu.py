@@ -63,6 +63,40 @@ def test_join_int_key_duplicates_nulls_and_projection(gpu):
     check_join({"a": a, "b": b}, "SELECT x.*, y.bv FROM a AS x JOIN b y ON x.k = y.k")
 
 
+def test_outer_joins(gpu):
+    """LEFT / RIGHT [OUTER] JOIN: unmatched rows of the preserved side survive once with NULLs on the other side
+    (every type: Int64, Float64, Utf8, Boolean), duplicates and NULL keys included."""
+    rng = np.random.default_rng(14)
+    n1, n2 = 4000, 1500
+    a = pa.record_batch({"k": pa.array([None if rng.random() < 0.1 else int(x) for x in rng.integers(0, 300, n1)], pa.int64()),
+                         "av": pa.array(rng.random(n1), pa.float64()), "astr": pa.array(["a%d" % i for i in range(n1)]),
+                         "ab": pa.array([bool(i & 1) for i in range(n1)], pa.bool_())})
+    b = pa.record_batch({"k": pa.array([None if rng.random() < 0.1 else int(x) for x in rng.integers(200, 600, n2)], pa.int64()),
+                         "bv": pa.array(rng.integers(0, 9, n2), pa.int64(), mask=rng.random(n2) < 0.2),
+                         "bstr": pa.array(["b-%d" % (i % 37) for i in range(n2)]), "bb": pa.array([i % 3 == 0 for i in range(n2)], pa.bool_())})
+    for q in ("SELECT * FROM a LEFT JOIN b ON a.k = b.k", "SELECT * FROM a RIGHT JOIN b ON a.k = b.k",
+              "SELECT * FROM a LEFT OUTER JOIN b ON b.k = a.k", "SELECT a.astr, b.bstr, b.bb, a.k AS ak, b.k AS bk FROM a RIGHT OUTER JOIN b ON a.k = b.k",
+              "SELECT * FROM b LEFT JOIN a ON a.k = b.k"):
+        out = check_join({"a": a, "b": b}, q)
+        assert out.num_rows >= (n1 if "LEFT" in q and "FROM a" in q else 0)
+    # nothing matches: every preserved row once, the other side all NULL
+    c = pa.record_batch({"k": pa.array([10_000 + i for i in range(40)], pa.int64()), "y": pa.array(["y%d" % i for i in range(40)])})
+    out = check_join({"a": a, "c": c}, "SELECT * FROM a LEFT JOIN c ON a.k = c.k")
+    assert out.num_rows == n1 and out.column("y").null_count == n1
+    out = check_join({"a": a, "c": c}, "SELECT * FROM a RIGHT JOIN c ON a.k = c.k")
+    assert out.num_rows == 40 and out.column("astr").null_count == 40
+
+
+def test_shipped_temporary_right_join_shape(gpu):
+    """examples/redis_temporary_example.yaml:29: `SELECT * FROM flow right join redis_table on (flow.sensor = redis_table.x)` —
+    the batch joined against the rows a temporary store returned; store rows without a flow row survive with NULL flow columns."""
+    flow = synth_batch(20_000, seed=3, key_space=40)
+    redis_table = pa.record_batch({"x": pa.array(["temp_%07d" % i for i in range(30, 55)]), "meta": pa.array(range(25), pa.int64())})
+    out = check_join({"flow": flow, "redis_table": redis_table}, "SELECT * FROM flow right join redis_table on (flow.sensor = redis_table.x)")
+    assert out.schema.names == ["timestamp", "value", "sensor", "x", "meta"]
+    assert out.column("sensor").null_count == 15  # store keys 40..54 have no flow row
+
+
 def test_join_long_string_keys_and_no_matches(gpu):
     rng = np.random.default_rng(8)
     keys = ["k%d-%s" % (i, "z" * int(rng.integers(0, 40))) for i in range(400)]
