@@ -93,7 +93,15 @@ def _declare(lib):
         "ark_buffer_create": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, P(vp)]),
         "ark_buffer_write": (C.c_int, [vp, P(ArrowArray), P(ArrowSchema), C.c_char_p, C.c_uint64]),
         "ark_buffer_read": (C.c_int, [vp, P(ArrowArray), P(ArrowSchema), P(C.c_uint64), C.c_int64, P(C.c_int64)]),
+        "ark_buffer_write_device": (C.c_int, [vp, P(ArrowDeviceArray), P(ArrowSchema), C.c_char_p, C.c_uint64]),
+        "ark_buffer_read_device": (C.c_int, [vp, P(ArrowDeviceArray), P(ArrowSchema), P(C.c_uint64), C.c_int64, P(C.c_int64)]),
         "ark_buffer_flush": (C.c_int, [vp]),
+        "ark_input_create": (C.c_int, [C.c_char_p, C.c_char_p, P(vp)]),
+        "ark_input_connect": (C.c_int, [vp]),
+        "ark_input_read": (C.c_int, [vp, P(ArrowArray), P(ArrowSchema)]),
+        "ark_input_read_device": (C.c_int, [vp, P(ArrowDeviceArray), P(ArrowSchema)]),
+        "ark_input_close": (C.c_int, [vp]),
+        "ark_input_destroy": (None, [vp]),
         "ark_buffer_close": (C.c_int, [vp]),
         "ark_buffer_destroy": (None, [vp]),
         "ark_batch_create": (C.c_int, [C.c_char_p, P(vp)]),

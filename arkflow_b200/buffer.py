@@ -122,6 +122,30 @@ class Buffer:
         got = [self._acks.pop(int(acks[i])) for i in range(n.value)]
         return MessageBatch(rb), VecAck(got)
 
+    def write_device(self, batch: F.DeviceBatch, input_name: Optional[str] = None, ack: Optional[Ack] = None) -> None:
+        """The same write for a batch that is already in HBM (ark_buffer_write_device: nothing is copied)."""
+        token = next(self._next)
+        self._acks[token] = ack or NoopAck()
+        dev, sch = batch.export()
+        try:
+            status = L.lib().ark_buffer_write_device(self._h, C.byref(dev), C.byref(sch), None if input_name is None else input_name.encode(), token)
+        finally:
+            F.release_schema(sch)
+            F.release_array(dev.array)
+        _check(status)
+
+    def read_device(self):
+        """Like read(), the window stays in HBM: None or (DeviceBatch, VecAck)."""
+        out_dev, out_sch = L.ArrowDeviceArray(), L.ArrowSchema()
+        cap = max(len(self._acks), 1) + 16
+        acks = (C.c_uint64 * cap)()
+        n = C.c_int64(0)
+        _check(L.lib().ark_buffer_read_device(self._h, C.byref(out_dev), C.byref(out_sch), acks, cap, C.byref(n)))
+        if not out_dev.array.release:
+            return None
+        got = [self._acks.pop(int(acks[i]), NoopAck()) for i in range(n.value)]
+        return F.DeviceBatch.adopt(out_dev, out_sch), VecAck(got)
+
     def flush(self) -> None:
         _check(L.lib().ark_buffer_flush(self._h))
 

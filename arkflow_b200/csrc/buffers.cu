@@ -270,6 +270,25 @@ int ark_buffer_create(const char* kind, const char* config_json, const char* inp
   });
 }
 
+static void buffer_enqueue(ark_buf* b, Batch&& batch, const char* input_name, uint64_t ack_token) {
+  batch.input_name = input_name ? input_name : "";
+  std::lock_guard<std::mutex> l(b->mu);
+  if (b->kind == ark_buf::Memory) {
+    b->queued_rows += batch.num_rows;
+    b->queue.push_front({std::move(batch), ack_token});            // memory.rs:155
+    if (b->queued_rows >= (int64_t)b->capacity) b->cv.notify_all();  // memory.rs:164-167
+  } else if (b->kind == ark_buf::Sliding) {
+    b->queue.push_back({std::move(batch), ack_token});               // sliding_window.rs:170-174
+    if (b->queue.size() >= b->window_size) b->cv.notify_all();       // (the reference waits for the next timer tick)
+  } else {
+    size_t idx = 0;
+    for (; idx < b->input_order.size(); ++idx) if (b->input_order[idx] == batch.input_name) break;
+    if (idx == b->input_order.size()) { b->input_order.push_back(batch.input_name); b->input_queues.emplace_back(); }
+    b->input_queues[idx].push_front({std::move(batch), ack_token});  // window.rs:184-187
+    if (b->kind == ark_buf::Session) b->last_write = Clock::now();   // session_window.rs:109
+  }
+}
+
 int ark_buffer_write(ark_buf_t* b, ArrowArray* in, ArrowSchema* in_schema, const char* input_name, uint64_t ack_token) {
   BufferPtr in_owner = adopt_array(in);
   return guarded([&] {
@@ -279,33 +298,40 @@ int ark_buffer_write(ark_buf_t* b, ArrowArray* in, ArrowSchema* in_schema, const
     StreamLease lease;
     Batch batch = import_host(arr, in_schema, nullptr, lease.s);  // the window lives in HBM from here on
     ARK_CUDA(cudaStreamSynchronize(lease.s));
-    batch.input_name = input_name ? input_name : "";
-    std::lock_guard<std::mutex> l(b->mu);
-    if (b->kind == ark_buf::Memory) {
-      b->queued_rows += batch.num_rows;
-      b->queue.push_front({std::move(batch), ack_token});            // memory.rs:155
-      if (b->queued_rows >= (int64_t)b->capacity) b->cv.notify_all();  // memory.rs:164-167
-    } else if (b->kind == ark_buf::Sliding) {
-      b->queue.push_back({std::move(batch), ack_token});               // sliding_window.rs:170-174
-      if (b->queue.size() >= b->window_size) b->cv.notify_all();       // (the reference waits for the next timer tick)
-    } else {
-      size_t idx = 0;
-      for (; idx < b->input_order.size(); ++idx) if (b->input_order[idx] == batch.input_name) break;
-      if (idx == b->input_order.size()) { b->input_order.push_back(batch.input_name); b->input_queues.emplace_back(); }
-      b->input_queues[idx].push_front({std::move(batch), ack_token});  // window.rs:184-187
-      if (b->kind == ark_buf::Session) b->last_write = Clock::now();   // session_window.rs:109
-    }
+    buffer_enqueue(b, std::move(batch), input_name, ack_token);
   });
 }
 
-int ark_buffer_read(ark_buf_t* b, ArrowArray* out, ArrowSchema* out_schema, uint64_t* acks, int64_t acks_cap, int64_t* n_acks) {
+// The same write for a batch that is already in HBM (an input or processor of this library produced it): the
+// buffer keeps the caller's device buffers alive, nothing is copied.
+int ark_buffer_write_device(ark_buf_t* b, ArrowDeviceArray* in, ArrowSchema* in_schema, const char* input_name, uint64_t ack_token) {
+  BufferPtr in_owner = adopt_array(&in->array);
   return guarded([&] {
     if (!b) fail(ARK_ERR_PROCESS, "null buffer");
-    memset(out, 0, sizeof(*out));
+    if (!in_owner) fail(ARK_ERR_PROCESS, "input array already released");
+    ArrowDeviceArray view = *in;
+    view.array = *(const ArrowArray*)in_owner.get();
+    Batch batch = import_device(&view, in_schema, nullptr, in_owner);
+    buffer_enqueue(b, std::move(batch), input_name, ack_token);
+  });
+}
+
+// out_host XOR out_dev: where the window is exported to
+static int buffer_read_impl(ark_buf_t* b, ArrowArray* out_host, ArrowDeviceArray* out_dev, ArrowSchema* out_schema, uint64_t* acks, int64_t acks_cap,
+                            int64_t* n_acks) {
+  return guarded([&] {
+    if (!b) fail(ARK_ERR_PROCESS, "null buffer");
+    ArrowArray* out = out_host ? out_host : &out_dev->array;
+    if (out_host) memset(out_host, 0, sizeof(*out_host)); else memset(out_dev, 0, sizeof(*out_dev));
     if (out_schema) memset(out_schema, 0, sizeof(*out_schema));
     if (n_acks) *n_acks = 0;
     std::vector<uint64_t> got_acks;
     StreamLease lease;
+    auto export_host = [&](Batch& r, cudaStream_t s_, ArrowArray*, ArrowSchema* sch) {  // shadows ark::export_host below
+      if (out_host) ark::export_host(r, s_, out_host, sch);
+      else { ARK_CUDA(cudaStreamSynchronize(s_)); ark::export_device(r, out_dev, sch); }
+    };
+    (void)out;
     if (b->kind == ark_buf::Memory) {
       std::vector<Batch> bs;
       {
@@ -367,6 +393,14 @@ int ark_buffer_read(ark_buf_t* b, ArrowArray* out, ArrowSchema* out_schema, uint
     for (size_t i = 0; i < got_acks.size(); ++i) acks[i] = got_acks[i];
     if (n_acks) *n_acks = (int64_t)got_acks.size();
   });
+}
+
+int ark_buffer_read(ark_buf_t* b, ArrowArray* out, ArrowSchema* out_schema, uint64_t* acks, int64_t acks_cap, int64_t* n_acks) {
+  return buffer_read_impl(b, out, nullptr, out_schema, acks, acks_cap, n_acks);
+}
+// The window stays in HBM: out->array.release == NULL ⇒ Ok(None).
+int ark_buffer_read_device(ark_buf_t* b, ArrowDeviceArray* out, ArrowSchema* out_schema, uint64_t* acks, int64_t acks_cap, int64_t* n_acks) {
+  return buffer_read_impl(b, nullptr, out, out_schema, acks, acks_cap, n_acks);
 }
 
 int ark_buffer_flush(ark_buf_t* b) {

@@ -95,6 +95,7 @@ typedef struct ark_proc ark_proc_t; /* a built Processor (sql / json_to_arrow / 
 typedef struct ark_buf ark_buf_t;   /* a built Buffer (memory / session_window / tumbling_window / sliding_window) */
 typedef struct ark_batcher ark_batcher_t; /* a built `batch` processor                                  */
 typedef struct ark_dist ark_dist_t; /* one rank's end of the device-side GROUP BY exchange              */
+typedef struct ark_input ark_input_t; /* a built Input (`generate`, `file`) that produces batches in HBM   */
 
 /* ---- library ---- */
 /* Bind the calling process to CUDA device `device` (-1: keep current) and warm the pools.
@@ -187,6 +188,11 @@ int ark_buffer_write(ark_buf_t* b, struct ArrowArray* in, struct ArrowSchema* in
  * batches were merged into `out` (VecAck, window.rs:124-139 / ArrayAck, memory.rs:121-137). */
 int ark_buffer_read(ark_buf_t* b, struct ArrowArray* out, struct ArrowSchema* out_schema,
                     uint64_t* acks, int64_t acks_cap, int64_t* n_acks);
+/* The same write / read for batches that already are / shall stay in HBM (nothing is copied). */
+int ark_buffer_write_device(ark_buf_t* b, struct ArrowDeviceArray* in, struct ArrowSchema* in_schema,
+                            const char* input_name, uint64_t ack_token);
+int ark_buffer_read_device(ark_buf_t* b, struct ArrowDeviceArray* out, struct ArrowSchema* out_schema,
+                           uint64_t* acks, int64_t acks_cap, int64_t* n_acks);
 int ark_buffer_flush(ark_buf_t* b);
 int ark_buffer_close(ark_buf_t* b);
 void ark_buffer_destroy(ark_buf_t* b);
@@ -270,6 +276,25 @@ int ark_sql_group_by_push_device(ark_proc_t* p, ark_dist_t* d, struct ArrowDevic
                                  struct ArrowSchema* in_schema);
 int ark_sql_group_by_merge_device(ark_proc_t* p, ark_dist_t* d, struct ArrowDeviceArray* out,
                                   struct ArrowSchema* out_schema);
+
+/* ---- inputs that produce their batches on the device (csrc/inputs.cu).
+ *      type "generate" ← `impl Input for GenerateInput`, crates/arkflow-plugin/src/input/generate.rs:59-96: config
+ *        {context: string, interval: duration string, count?: usize, batch_size?: usize (default 1)}; read() yields
+ *        batch_size clones of `context` as a non-null Binary column `__value__`, sleeps `interval` before every read
+ *        but the first, and returns ARK_ERR_EOF once `count` is reached or the next batch would exceed it.
+ *        NULL config → ARK_ERR_CONFIG "Generate input configuration is missing" (generate.rs:107-111).
+ *      type "file" ← `impl Input for FileInput`, crates/arkflow-plugin/src/input/file.rs:395-455: config
+ *        {input_type: {type: "json" | "csv", path}, query?: {query, table?}, batch_size?}; connect() loads the file into
+ *        HBM and indexes its lines, read() decodes the next batch_size lines (NDJSON: json_to_arrow kernels; CSV:
+ *        header + type inference over the first 1000 rows on the host, csv_parse_kernel) and applies the optional
+ *        query; ARK_ERR_EOF at the end.  parquet / avro / arrow and remote stores → ARK_ERR_UNSUPPORTED.
+ *      ark_input_read_device leaves the batch in HBM (feed it to ark_buffer_write_device / *_process_device). ---- */
+int ark_input_create(const char* type, const char* config_json, ark_input_t** out);
+int ark_input_connect(ark_input_t* in);
+int ark_input_read(ark_input_t* in, struct ArrowArray* out, struct ArrowSchema* out_schema);
+int ark_input_read_device(ark_input_t* in, struct ArrowDeviceArray* out, struct ArrowSchema* out_schema);
+int ark_input_close(ark_input_t* in);
+void ark_input_destroy(ark_input_t* in);
 
 /* ---- synthetic input of schema S, generated in HBM.  Bench/test support. ---- */
 /* value_kind: 0 = Int64 uniform [0,20), 1 = Float64 20*u.  key_space K: sensor = "temp_%07d" % k.

@@ -3,7 +3,7 @@
 set -u
 OUT=gpurun_out/r2c
 mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -x -q -k "filter or aggregate or fuzz or golden or dist" > $OUT/pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest.log
+timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest.log
 tail -5 $OUT/pytest.log
 FQ="SELECT sensor, value FROM flow WHERE value >= 10"
 GQ="SELECT sensor, SUM(value), COUNT(*) FROM flow GROUP BY sensor"
