@@ -612,13 +612,27 @@ __global__ void realign_bits_kernel(const uint8_t* in, uint8_t* out, int64_t n, 
 
 }  // namespace
 
+static void fill_column_schema(ArrowSchema* s, const Column& c) {
+  fill_schema(s, dtype_arrow_format(c.field.type), c.field.name, c.field.nullable);
+  if (c.children.empty()) return;
+  auto* p = (SchemaPriv*)s->private_data;
+  p->child_storage.resize(c.children.size());
+  p->child_ptrs.resize(c.children.size());
+  for (size_t i = 0; i < c.children.size(); ++i) {
+    fill_column_schema(&p->child_storage[i], c.children[i]);
+    p->child_ptrs[i] = &p->child_storage[i];
+  }
+  s->n_children = (int64_t)c.children.size();
+  s->children = p->child_ptrs.data();
+}
+
 void export_schema(const Batch& b, ArrowSchema* out) {
   fill_schema(out, "+s", "", false);
   auto* p = (SchemaPriv*)out->private_data;
   p->child_storage.resize(b.cols.size());
   p->child_ptrs.resize(b.cols.size());
   for (size_t i = 0; i < b.cols.size(); ++i) {
-    fill_schema(&p->child_storage[i], dtype_arrow_format(b.cols[i].field.type), b.cols[i].field.name, b.cols[i].field.nullable);
+    fill_column_schema(&p->child_storage[i], b.cols[i]);
     p->child_ptrs[i] = &p->child_storage[i];
   }
   out->n_children = (int64_t)b.cols.size();
@@ -695,9 +709,58 @@ static ExportCol normalise_for_export(const Column& c_in, bool to_host, cudaStre
       e.buf2 = c.data ? c.data + c.first_offset : nullptr; e.buf2_bytes = c.data_bytes;
       break;
     }
+    case DType::List:  // offsets (library-produced: first offset 0) + one child
+      e.buf1 = c.offsets; e.buf1_bytes = (n + 1) * 4; e.n_buffers = 2; break;
+    case DType::Struct:
+      e.n_buffers = 1; break;
     default: e.n_buffers = 0; break;
   }
   return e;
+}
+
+// one column (and, for List / Struct, its children) as an ArrowArray
+static void build_column_array(const Column& c, ExportCol& e, bool to_host, cudaStream_t stream, ArrowArray* ca, int64_t* d2h_bytes) {
+  auto* cp = new ArrayPriv();
+  memset(ca, 0, sizeof(*ca));
+  ca->length = c.length; ca->offset = 0;
+  ca->null_count = e.validity ? (c.null_count < 0 ? -1 : c.null_count) : 0;
+  auto place = [&](const void* dptr, int64_t bytes) -> const void* {
+    if (!to_host) return dptr;
+    if (!dptr && bytes == 0) {
+      BufferPtr h = pinned_alloc(64);
+      cp->owners.push_back(h);
+      return h.get();
+    }
+    BufferPtr h = pinned_alloc((size_t)std::max<int64_t>(bytes, 1));
+    if (bytes > 0) {
+      ARK_CUDA(cudaMemcpyAsync(h.get(), dptr, (size_t)bytes, cudaMemcpyDeviceToHost, stream));
+      if (d2h_bytes) *d2h_bytes += bytes;
+    }
+    cp->owners.push_back(h);
+    return h.get();
+  };
+  if (c.field.type == DType::Null) {
+    ca->n_buffers = 0; ca->null_count = c.length;
+  } else {
+    cp->buffers.push_back(e.validity ? place(e.validity, e.validity_bytes) : nullptr);
+    if (e.n_buffers >= 2) cp->buffers.push_back(place(e.buf1, e.buf1_bytes));
+    if (e.n_buffers == 3) cp->buffers.push_back(place(e.buf2, e.buf2_bytes));
+    ca->n_buffers = (int64_t)cp->buffers.size();
+  }
+  ca->buffers = cp->buffers.data();
+  if (!to_host) cp->owners = e.owners;  // device export keeps the HBM blocks alive
+  if (!c.children.empty()) {
+    cp->child_storage.resize(c.children.size());
+    cp->child_ptrs.resize(c.children.size());
+    for (size_t k = 0; k < c.children.size(); ++k) {
+      ExportCol ce = normalise_for_export(c.children[k], to_host, stream);
+      build_column_array(c.children[k], ce, to_host, stream, &cp->child_storage[k], d2h_bytes);
+      cp->child_ptrs[k] = &cp->child_storage[k];
+    }
+    ca->n_children = (int64_t)c.children.size();
+    ca->children = cp->child_ptrs.data();
+  }
+  ca->release = release_array; ca->private_data = cp;
 }
 
 static void build_struct_array(const Batch& b, std::vector<ExportCol>& cols, bool to_host, cudaStream_t stream,
@@ -710,40 +773,8 @@ static void build_struct_array(const Batch& b, std::vector<ExportCol>& cols, boo
   top->child_storage.resize(cols.size());
   top->child_ptrs.resize(cols.size());
   for (size_t i = 0; i < cols.size(); ++i) {
-    ExportCol& e = cols[i];
-    const Column& c = b.cols[i];
-    auto* cp = new ArrayPriv();
-    ArrowArray* ca = &top->child_storage[i];
-    memset(ca, 0, sizeof(*ca));
-    ca->length = c.length; ca->offset = 0;
-    ca->null_count = e.validity ? (c.null_count < 0 ? -1 : c.null_count) : 0;
-    auto place = [&](const void* dptr, int64_t bytes) -> const void* {
-      if (!to_host) return dptr;
-      if (!dptr && bytes == 0) {
-        BufferPtr h = pinned_alloc(64);
-        cp->owners.push_back(h);
-        return h.get();
-      }
-      BufferPtr h = pinned_alloc((size_t)std::max<int64_t>(bytes, 1));
-      if (bytes > 0) {
-        ARK_CUDA(cudaMemcpyAsync(h.get(), dptr, (size_t)bytes, cudaMemcpyDeviceToHost, stream));
-        if (d2h_bytes) *d2h_bytes += bytes;
-      }
-      cp->owners.push_back(h);
-      return h.get();
-    };
-    if (c.field.type == DType::Null) {
-      ca->n_buffers = 0; ca->null_count = c.length;
-    } else {
-      cp->buffers.push_back(e.validity ? place(e.validity, e.validity_bytes) : nullptr);
-      cp->buffers.push_back(place(e.buf1, e.buf1_bytes));
-      if (e.n_buffers == 3) cp->buffers.push_back(place(e.buf2, e.buf2_bytes));
-      ca->n_buffers = (int64_t)cp->buffers.size();
-    }
-    ca->buffers = cp->buffers.data();
-    if (!to_host) cp->owners = e.owners;  // device export keeps the HBM blocks alive
-    ca->release = release_array; ca->private_data = cp;
-    top->child_ptrs[i] = ca;
+    build_column_array(b.cols[i], cols[i], to_host, stream, &top->child_storage[i], d2h_bytes);
+    top->child_ptrs[i] = &top->child_storage[i];
   }
   out->n_children = (int64_t)cols.size();
   out->children = top->child_ptrs.data();

@@ -84,6 +84,9 @@ struct Column {
   int64_t data_bound = -1;            // var-len, extent unknown: upper bound on offsets[n] (end of the allocation), or -1
   std::vector<BufferPtr> owners;      // keep-alive for everything referenced above
   bool present = true;                // false ⇒ column was not imported (projection push-down)
+  // List: children[0] = the elements (offsets index into it); Struct: one child per field, each of `length` rows.
+  // Only json_to_arrow produces these (one nesting level); they can be exported, not queried.
+  std::vector<Column> children;
 
   ColView view() const {
     ColView v;

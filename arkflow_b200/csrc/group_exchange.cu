@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(GX_THREADS) exchange_push_kernel(const __grid_
     if (s >= P.capacity) continue;
     key[j] = *tbl_key(P.table, s, bstride);
     if (key[j].hi == KEY_EMPTY) continue;
-    if (key_is_long(key[j])) { flags |= 1; continue; }
+    if (key_is_long(key[j]) || key_is_pair(key[j])) { flags |= 1; continue; }  // keys that reference the sender's rows cannot travel inline
     part[j] = P.world > 1 ? partition_of(P.key_kind == KEY_NONE ? 0 : hash_key16(key[j]), P.world) : 0;
     local[j] = atomicAdd(&s_cnt[part[j]], 1u);
   }
@@ -377,7 +377,6 @@ int ark_sql_group_by_push_device(ark_proc_t* p, ark_dist_t* d, ArrowDeviceArray*
     std::vector<Field> fields = schema_fields(in_schema);
     auto plan = sp->plan_for(fields);
     if (plan->kind != Plan::Aggregate) fail(ARK_ERR_PROCESS, "not an aggregate query");
-    if (plan->keys.size() > 1) fail(ARK_ERR_UNSUPPORTED, "device-side exchange: more than one GROUP BY key");
     std::vector<bool> mask(fields.size(), false);
     for (int col : plan->used_cols) mask[col] = true;
     StreamLease lease;

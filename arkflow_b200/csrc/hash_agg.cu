@@ -96,8 +96,14 @@ __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_cons
     unsigned long long slot = 0;
     if (ok) {
       Key16 mine;
-      const unsigned long long h = table_hash(P.key_kind, kc, row, &mine);
-      slot = table_find_or_claim(P.table, bmask, bstride, h, mine, kc, kc, &claimed);
+      if (P.key_kind == KEY_PAIR) {
+        const ColView& k2 = P.cols[P.key_slot2];
+        const unsigned long long h = make_pair_key(P.key_kind1, kc, P.key_kind2, k2, row, &mine);
+        slot = table_find_or_claim_pair(P.table, bmask, bstride, h, mine, P.key_kind1, kc, P.key_kind2, k2, &claimed);
+      } else {
+        const unsigned long long h = table_hash(P.key_kind, kc, row, &mine);
+        slot = table_find_or_claim(P.table, bmask, bstride, h, mine, kc, kc, &claimed);
+      }
       if (slot == ~0ull) { atomicExch(P.overflow, 1); ok = false; }  // the table is too loaded for this batch
     }
     // ---- accumulate; a warp whose lanes all hit one group reduces with shuffles first ----
@@ -256,6 +262,9 @@ struct AggExec {
   int key_kind = KEY_NONE;
   int key_slot = 0;
   DType key_type = DType::Null;
+  // two GROUP BY keys: key_kind == KEY_PAIR, the columns' own kinds / slots / types here
+  int key_kind1 = KEY_NONE, key_kind2 = KEY_NONE, key_slot2 = 0;
+  DType key_type2 = DType::Null;
   std::vector<AccPlan> accs;
   std::vector<VmProgram> progs;
   int find_or_add(const AccPlan& a) {
@@ -315,6 +324,7 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     if (P.pred_kind == 1) { P.sp_slot = plan.simple.slot; P.sp_cmp = plan.simple.cmp; P.sp_is_f64 = plan.simple.is_f64; P.sp_const = plan.simple.constant; }
     if (P.pred_kind == 2) P.pred = plan.pred;
     P.key_kind = ex.key_kind; P.key_slot = ex.key_slot;
+    P.key_slot2 = ex.key_slot2; P.key_kind1 = ex.key_kind1; P.key_kind2 = ex.key_kind2;
     for (size_t s = 0; s < plan.used_cols.size(); ++s) P.cols[s] = in.cols[plan.used_cols[s]].view();
     P.n_acc = (int)ex.accs.size();
     for (size_t a = 0; a < ex.accs.size(); ++a) {
@@ -332,7 +342,7 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     ARK_CUDA(cudaMemsetAsync(ctl.get(), 0, 512, stream));
     // large tables: partition rows by table region, build each region in shared memory (hash_agg_radix.cu)
     std::vector<BufferPtr> radix_keep;
-    const bool radix = allow_radix && n > 0 && launch_hash_agg_radix(P, capacity, (int32_t*)((char*)ctl.get() + 12), &radix_keep, stream);
+    const bool radix = allow_radix && n > 0 && ex.key_kind != KEY_PAIR && launch_hash_agg_radix(P, capacity, (int32_t*)((char*)ctl.get() + 12), &radix_keep, stream);
     if (!radix) {
       KernelTimer t("agg_init_kernel", stream);
       const int grid = (int)std::min<unsigned long long>((capacity + 255) / 256, 148ull * 8);
@@ -358,7 +368,7 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     // serialise on L2 atomics here (K = 2: 12.9 ms vs 0.24 ms).  Everything larger: this file's row kernel.
     static const unsigned long long tile_max = [] { const char* e = getenv("ARK_AGG_TILE_MAX"); return e ? (unsigned long long)atoll(e) : 1024ull; }();  // 2048 slots (≈ 1000 groups): 1.65 ms here vs 1.34 ms in hash_agg_kernel
     if (radix) {
-    } else if (n > 0 && capacity <= tile_max && launch_hash_agg_tile(P, capacity, hints.groups.load(), key_bytes, stream)) {
+    } else if (n > 0 && capacity <= tile_max && ex.key_kind != KEY_PAIR && launch_hash_agg_tile(P, capacity, hints.groups.load(), key_bytes, stream)) {
     } else if (n > 0 && launch_hash_agg_stream(P, capacity, key_bytes, stream)) {
     } else {
       if (P.pred_kind == 0) launch_agg<0>(P, n, stream);
@@ -498,6 +508,22 @@ static Column emit_key_column(const AggExec& ex, const DenseGroups& dg, const Co
   return emit_key_column(ex, dg, src.view(), src.validity != nullptr, name, nullable, stream);
 }
 
+// pair keys: the row each group was first seen at (Key16.lo) → gather index for take_column
+__global__ void agg_key_rows_kernel(const uint8_t* table, int stride, const unsigned int* slots, unsigned int n_groups, unsigned int* rows) {
+  unsigned int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_groups) rows[g] = (unsigned int)tbl_key(table, slots[g], stride)->lo;
+}
+static BufferPtr pair_key_rows(const DenseGroups& dg, cudaStream_t stream) {
+  const unsigned int G = dg.n_groups;
+  BufferPtr rows = device_alloc((size_t)std::max<unsigned int>(G, 1) * 4);
+  if (G) {
+    KernelTimer t("agg_key_rows_kernel", stream);
+    agg_key_rows_kernel<<<(unsigned)ceil_div(G, 256), 256, 0, stream>>>((const uint8_t*)dg.table.get(), dg.stride, (const unsigned int*)dg.slots.get(), G,
+                                                                        (unsigned int*)rows.get());
+  }
+  return rows;
+}
+
 static BufferPtr gather_acc(const DenseGroups& dg, int acc, cudaStream_t stream) {
   const unsigned int G = dg.n_groups;
   BufferPtr out = device_alloc((size_t)std::max<unsigned int>(G, 1) * 8);
@@ -534,11 +560,16 @@ static Column finalize_column(const std::string& name, DType type, int op, Buffe
 // over partial-state rows (column layout produced by partial_state_batch below).
 static void build_exec(const Plan& plan, const Batch* in, AggExec& ex, std::vector<AggOutput>& outs) {
   const bool schema_nullability = in == nullptr;
-  if (plan.keys.size() > 1) fail(ARK_ERR_UNSUPPORTED, "more than one GROUP BY key");
+  if (plan.keys.size() > 2) fail(ARK_ERR_UNSUPPORTED, "more than two GROUP BY keys");
+  auto kind_of = [](DType t) { return t == DType::Int64 ? KEY_INT64 : (t == DType::Bool ? KEY_BOOL : KEY_BYTES); };
   if (!plan.keys.empty()) {
     const ValueSource& k = plan.keys[0];
     ex.key_slot = k.slot; ex.key_type = k.type;
-    ex.key_kind = k.type == DType::Int64 ? KEY_INT64 : (k.type == DType::Bool ? KEY_BOOL : KEY_BYTES);
+    ex.key_kind = kind_of(k.type);
+    if (plan.keys.size() == 2) {
+      ex.key_kind1 = ex.key_kind; ex.key_kind = KEY_PAIR;
+      ex.key_slot2 = plan.keys[1].slot; ex.key_type2 = plan.keys[1].type; ex.key_kind2 = kind_of(plan.keys[1].type);
+    }
   }
   auto arg_of = [&](const ValueSource& v, AccPlan& a, bool* nullable) {
     if (v.kind == ValueSource::PassThrough) {
@@ -580,14 +611,19 @@ static void build_exec(const Plan& plan, const Batch* in, AggExec& ex, std::vect
 }
 
 static Batch project_groups(const Plan& plan, const AggExec& ex, const std::vector<AggOutput>& outs, const DenseGroups& dg,
-                            const Column* key_src, cudaStream_t stream) {
+                            const Column* key_src, cudaStream_t stream, const Column* key_src2 = nullptr) {
   const unsigned int G = dg.n_groups;
   Batch out;
   out.num_rows = G;
   std::vector<BufferPtr> dense(ex.accs.size());
   auto dense_acc = [&](int a) -> BufferPtr { if (!dense[a]) dense[a] = gather_acc(dg, a, stream); return dense[a]; };
+  BufferPtr pair_rows;  // KEY_PAIR: keys are gathered from the rows that first held each pair
   for (const PostItem& pi : plan.post) {
-    if (pi.kind == PostItem::Key) {
+    if (pi.kind == PostItem::Key && ex.key_kind == KEY_PAIR) {
+      if (!pair_rows) pair_rows = pair_key_rows(dg, stream);
+      const Column& src = pi.index == 0 ? *key_src : *key_src2;
+      out.cols.push_back(take_column(src, (const unsigned int*)pair_rows.get(), G, pi.name, stream));
+    } else if (pi.kind == PostItem::Key) {
       out.cols.push_back(emit_key_column(ex, dg, *key_src, pi.name, key_src->field.nullable, stream));
     } else if (pi.kind == PostItem::Agg) {
       const AggOutput& o = outs[pi.index];
@@ -617,7 +653,8 @@ Batch run_aggregate(const Plan& plan, Batch& in, cudaStream_t stream) {
   build_exec(plan, &in, ex, outs);
   DenseGroups dg = hash_pass(plan, ex, in, 1, stream);
   const Column* key_src = ex.key_kind == KEY_NONE ? nullptr : &in.cols[plan.used_cols[ex.key_slot]];
-  Batch out = project_groups(plan, ex, outs, dg, key_src, stream);
+  const Column* key_src2 = ex.key_kind == KEY_PAIR ? &in.cols[plan.used_cols[ex.key_slot2]] : nullptr;
+  Batch out = project_groups(plan, ex, outs, dg, key_src, stream, key_src2);
   ARK_CUDA(cudaStreamSynchronize(stream));
   return out;
 }
@@ -633,7 +670,11 @@ Batch run_partial_aggregate(const Plan& plan, Batch& in, int n_parts, std::vecto
   part_rows = dg.part_rows;
   Batch out;
   out.num_rows = dg.n_groups;
-  if (ex.key_kind != KEY_NONE) {
+  if (ex.key_kind == KEY_PAIR) {
+    BufferPtr rows = pair_key_rows(dg, stream);
+    out.cols.push_back(take_column(in.cols[plan.used_cols[ex.key_slot]], (const unsigned int*)rows.get(), dg.n_groups, plan.key_names[0], stream));
+    out.cols.push_back(take_column(in.cols[plan.used_cols[ex.key_slot2]], (const unsigned int*)rows.get(), dg.n_groups, plan.key_names[1], stream));
+  } else if (ex.key_kind != KEY_NONE) {
     const Column& src = in.cols[plan.used_cols[ex.key_slot]];
     out.cols.push_back(emit_key_column(ex, dg, src, plan.key_names[0], src.field.nullable, stream));
   }
@@ -654,12 +695,13 @@ Batch run_final_aggregate(const Plan& plan, Batch& partial, cudaStream_t stream)
   AggExec ex;
   std::vector<AggOutput> outs;
   build_exec(plan, nullptr, ex, outs);  // same accumulator layout as the partial side
-  const int key_cols = ex.key_kind == KEY_NONE ? 0 : 1;
+  const int key_cols = ex.key_kind == KEY_NONE ? 0 : (ex.key_kind == KEY_PAIR ? 2 : 1);
   if ((int)partial.cols.size() != key_cols + (int)ex.accs.size())
     fail(ARK_ERR_PROCESS, "final aggregate: partial-state batch has " + std::to_string(partial.cols.size()) + " columns, expected " +
                               std::to_string(key_cols + ex.accs.size()));
   AggExec mx;  // merge: aggregate the state columns
   mx.key_kind = ex.key_kind; mx.key_slot = 0; mx.key_type = ex.key_type;
+  mx.key_kind1 = ex.key_kind1; mx.key_kind2 = ex.key_kind2; mx.key_slot2 = 1; mx.key_type2 = ex.key_type2;
   for (size_t a = 0; a < ex.accs.size(); ++a) {
     AccPlan m;
     m.arg_slot = key_cols + (int)a;
@@ -677,7 +719,7 @@ Batch run_final_aggregate(const Plan& plan, Batch& partial, cudaStream_t stream)
   for (size_t i = 0; i < partial.cols.size(); ++i) mp.used_cols.push_back((int)i);
   if ((int)mp.used_cols.size() > MAX_COLS) fail(ARK_ERR_UNSUPPORTED, "too many accumulator columns");
   DenseGroups dg = hash_pass(mp, mx, partial, 1, stream);
-  Batch out = project_groups(plan, mx, outs, dg, key_cols ? &partial.cols[0] : nullptr, stream);
+  Batch out = project_groups(plan, mx, outs, dg, key_cols ? &partial.cols[0] : nullptr, stream, key_cols == 2 ? &partial.cols[1] : nullptr);
   ARK_CUDA(cudaStreamSynchronize(stream));
   return out;
 }

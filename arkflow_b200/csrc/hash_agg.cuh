@@ -15,6 +15,8 @@ constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;  // lo == hi == 
 constexpr unsigned KEYTAG_NULL = 0xFFFFFFFEu;                    // tag (top 32 bits of hi) of the NULL key
 constexpr unsigned KEYTAG_LONG = 0x80000000u;                    // | length for keys longer than 12 bytes
 constexpr unsigned KEYTAG_INT = 0x40000000u;                     // Int64 / Bool key: lo = value
+constexpr unsigned KEYTAG_PAIR = 0x20000000u;                    // two GROUP BY keys: lo = row that first held the pair, low 32 bits of hi = top
+                                                                 // 32 bits of the pair's hash (compared first; also decides the owner rank)
 
 // Table layout.  Slot s lives in bucket s / 4, lane s % 4.  A bucket is
 //   [Key16 key[4]]  (64 bytes = two 32-byte sectors)  followed by  [u64 acc_a[4]] (one sector) per accumulator a,
@@ -51,7 +53,7 @@ enum AccKind : int32_t {
   ACC_MIN_F64, ACC_MAX_F64,  // on the totalOrder key
 };
 
-enum KeyKind : int32_t { KEY_NONE = 0, KEY_INT64 = 1, KEY_BYTES = 2, KEY_BOOL = 3 };
+enum KeyKind : int32_t { KEY_NONE = 0, KEY_INT64 = 1, KEY_BYTES = 2, KEY_BOOL = 3, KEY_PAIR = 4 /* two key columns */ };
 
 constexpr int AGG_MAX_ACC = 8;
 constexpr int AGG_MAX_PROGS = 2;
@@ -73,7 +75,8 @@ struct AggParams {
   int32_t key_kind;
   int32_t key_slot;
   int32_t n_acc;
-  int32_t pad;
+  int32_t key_slot2;   // KEY_PAIR: the second key column; key_kind1 / key_kind2 = the kinds of the two columns
+  int32_t key_kind1, key_kind2;
   ColView cols[MAX_COLS];
   AccParam accs[AGG_MAX_ACC];
   VmProgram pred;

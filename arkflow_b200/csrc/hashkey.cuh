@@ -121,7 +121,25 @@ static __device__ inline bool key_equal(Key16 mine, Key16 stored, const ColView&
 }
 
 
+static __device__ __forceinline__ bool key_is_pair(Key16 k) { return (unsigned)(k.hi >> 32) == KEYTAG_PAIR; }
+
+// equality of the values two rows hold in one key column (NULL equals NULL: one group)
+static __device__ inline bool rows_equal(int kind, const ColView& c, int64_t a, int64_t b) {
+  const bool va = col_valid(c, a), vb = col_valid(c, b);
+  if (!va || !vb) return va == vb;
+  if (kind == KEY_INT64) return ((const unsigned long long*)c.data)[a] == ((const unsigned long long*)c.data)[b];
+  if (kind == KEY_BOOL) return bit_get((const uint8_t*)c.data, a + c.data_bit0) == bit_get((const uint8_t*)c.data, b + c.data_bit0);
+  const int32_t a0 = c.offsets[a], b0 = c.offsets[b];
+  const int la = c.offsets[a + 1] - a0, lb = c.offsets[b + 1] - b0;
+  if (la != lb) return false;
+  const uint8_t* pa = (const uint8_t*)c.data + a0;
+  const uint8_t* pb = (const uint8_t*)c.data + b0;
+  for (int i = 0; i < la; ++i) if (pa[i] != pb[i]) return false;
+  return true;
+}
+
 static __device__ __forceinline__ unsigned long long stored_key_hash(Key16 k, const ColView& kc) {
+  if (key_is_pair(k)) return (k.hi & 0xFFFFFFFFull) << 32;  // the stored top half of the pair's hash: enough for partition_of
   if (key_is_long(k)) {
     const int len = (int)((unsigned)(k.hi >> 32) & 0x7FFFFFFFu);
     return hash_bytes((const uint8_t*)kc.data + kc.offsets[(int64_t)k.lo], len);
@@ -170,6 +188,42 @@ static __device__ __forceinline__ void make_key_smem(const uint8_t* p, int len, 
   }
 }
 
+
+// The table key of a (k1, k2) pair at `row` and its 64-bit hash.
+static __device__ inline unsigned long long make_pair_key(int kind1, const ColView& c1, int kind2, const ColView& c2, int64_t row, Key16* key) {
+  Key16 t; unsigned long long h1, h2;
+  make_key(kind1, c1, row, &t, &h1);
+  make_key(kind2, c2, row, &t, &h2);
+  const unsigned long long h = mix64(h1 * 0x9E3779B97F4A7C15ull + (h2 ^ 0xD6E8FEB86659FD93ull));
+  key->lo = (unsigned long long)row;
+  key->hi = (h >> 32) | ((unsigned long long)KEYTAG_PAIR << 32);
+  return h;
+}
+
+// table_find_or_claim for pair keys: equal fingerprints, then the two columns of the two rows are compared
+static __device__ __forceinline__ unsigned long long table_find_or_claim_pair(uint8_t* table, unsigned long long bucket_mask, int bstride,
+                                                                              unsigned long long home, Key16 mine, int kind1, const ColView& c1,
+                                                                              int kind2, const ColView& c2, unsigned int* claimed, int max_buckets = 128) {
+  unsigned long long b = home & bucket_mask;
+  for (int probes = 0; probes < max_buckets; ++probes) {
+    Key16* kb = reinterpret_cast<Key16*>(table + b * (unsigned long long)bstride);
+    Key16 k[TBL_B];
+    ld256_keys(kb, &k[0], &k[1]);
+    ld256_keys(kb + 2, &k[2], &k[3]);
+#pragma unroll
+    for (int i = 0; i < TBL_B; ++i) {
+      Key16 c = k[i];
+      if (c.hi == KEY_EMPTY) {
+        c = cas128(kb + i, Key16{KEY_EMPTY, KEY_EMPTY}, mine);
+        if (c.hi == KEY_EMPTY && c.lo == KEY_EMPTY) { ++*claimed; return b * TBL_B + i; }
+      }
+      if (c.hi == mine.hi && (c.lo == mine.lo || (rows_equal(kind1, c1, (int64_t)mine.lo, (int64_t)c.lo) && rows_equal(kind2, c2, (int64_t)mine.lo, (int64_t)c.lo))))
+        return b * TBL_B + i;
+    }
+    b = (b + 1) & bucket_mask;
+  }
+  return ~0ull;
+}
 
 // Finds the slot of `mine` in the bucketed table or claims the first free lane on its probe path (buckets home,
 // home + 1, …; lanes 0..3 in order, so a key is always met before any empty lane after it).  `mc` / `sc`: the

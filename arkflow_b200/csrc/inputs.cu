@@ -189,9 +189,8 @@ __global__ void csv_parse_kernel(const __grid_constant__ CsvParams P) {
     bool bad = false;
     while (col < P.n_cols) {
       long long f0 = pos, f1;
-      bool quoted = false, escaped = false;
+      bool escaped = false;
       if (pos < end && P.data[pos] == '"') {
-        quoted = true;
         f0 = ++pos;
         while (pos < end) {
           if (P.data[pos] == '"') { if (pos + 1 < end && P.data[pos + 1] == '"') { escaped = true; pos += 2; continue; } break; }

@@ -27,8 +27,9 @@ namespace ark {
 
 namespace {
 
-constexpr int JS_MAX_FIELDS = 16;
-constexpr int JS_MAX_NAME = 48;
+constexpr int JS_MAX_FIELDS = 16;   // fields that travel in the kernel parameter block (constant bank); larger schemas use a table in HBM
+constexpr int JS_MAX_NAME = 48;     // name bytes held inline; longer names are read through long_name
+constexpr int JS_MAX_FIELDS_EXT = 64;  // the per-record `seen` mask is 64 bits wide
 
 enum JsonErr : int32_t { JE_NONE = 0, JE_SYNTAX = 1, JE_NOT_OBJECT = 2, JE_TYPE = 3, JE_NUMBER = 4 };
 
@@ -40,7 +41,9 @@ struct JsonField {
   uint8_t* valid_bytes;    // byte per row
   int32_t* str_len;        // Utf8: decoded length per row (pass A), later the offsets array
   long long* str_src;      // Utf8: absolute source position of the raw string body (after the quote)
-  int32_t* str_raw_len;    // Utf8: raw (escaped) byte length; negative ⇒ contains escapes
+  int32_t* str_raw_len;    // Utf8: raw (escaped) byte length; negative ⇒ contains escapes.  List / Struct: the value's raw span
+                           // (str_src / str_raw_len), decoded by a second stage (json_list_* kernels / a nested parse pass)
+  const char* long_name;   // name bytes in HBM when name_len > JS_MAX_NAME, else nullptr
 };
 
 struct JsonParams {
@@ -51,6 +54,11 @@ struct JsonParams {
   int64_t n_payloads;
   int32_t n_fields;
   JsonField fields[JS_MAX_FIELDS];
+  const JsonField* fields_ext; // the field table in HBM when n_fields > JS_MAX_FIELDS (else nullptr: `fields` is used)
+  // nested pass: payload i is the span data[span_src[i] .. + span_len[i]) (the raw value of a Struct field) instead of
+  // a row of the Binary column; a zero-length span (NULL / missing struct) yields a row of NULL children
+  const long long* span_src;
+  const int32_t* span_len;
   const long long* row_start;  // pass A: first output row of payload i
   int32_t* counts;             // count pass: records in payload i
   int32_t* error;              // [0] = JsonErr, [1] = payload index (first error wins), [2] = some payload does not hold exactly one record
@@ -336,9 +344,10 @@ __global__ void __launch_bounds__(JS_THREADS) json_parse_kernel(const __grid_con
     if (MODE == 2) P.error[2] = 1;
     return;
   }
+  const JsonField* const FT = P.fields_ext ? P.fields_ext : P.fields;
   // `origin` + column byte offset = address of that byte (in the staging window or in global memory)
   const uint8_t* origin = staged ? js_stage - stage_off : P.data;
-  Cursor c{origin + P.offsets[i], origin + P.offsets[i + 1]};
+  Cursor c = P.span_src ? Cursor{P.data + P.span_src[i], P.data + P.span_src[i] + P.span_len[i]} : Cursor{origin + P.offsets[i], origin + P.offsets[i + 1]};
   int records = 0;
   long long row = MODE == 1 ? P.row_start[i] : (MODE == 2 ? (long long)i : 0);
   while (true) {
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(JS_THREADS) json_parse_kernel(const __grid_con
     }
     // ---- MODE 1: one object → one row ----
     ++c.p;
-    unsigned seen = 0;
+    unsigned long long seen = 0;
     int next_field = 0;
     skip_ws(c);
     bool first = true;
@@ -374,21 +383,23 @@ __global__ void __launch_bounds__(JS_THREADS) json_parse_kernel(const __grid_con
       if (!kesc) {
         // records usually list their keys in the order of the first record: try that position first
         for (int t = 0, k = next_field; t < P.n_fields; ++t, k = (k + 1 == P.n_fields ? 0 : k + 1)) {
-          if (P.fields[k].name_len != kl) continue;
+          if (FT[k].name_len != kl) continue;
+          const char* nm = FT[k].long_name ? FT[k].long_name : FT[k].name;
           bool eq = true;
-          for (int b = 0; b < kl; ++b) if ((uint8_t)P.fields[k].name[b] != kb[b]) { eq = false; break; }
+          for (int b = 0; b < kl; ++b) if ((uint8_t)nm[b] != kb[b]) { eq = false; break; }
           if (eq) { f = k; break; }
         }
         if (f >= 0) next_field = f + 1 == P.n_fields ? 0 : f + 1;
       }
       if (f < 0) { if (!skip_value(c, 0)) { raise(P, JE_SYNTAX, i); return; } continue; }
-      const JsonField& F = P.fields[f];
+      const JsonField& F = FT[f];
       if (c.p >= c.end) { raise(P, JE_SYNTAX, i); return; }
       const uint8_t ch = *c.p;
       if (ch == 'n') {  // null
         if (!match_lit(c, "null", 4)) { raise(P, JE_SYNTAX, i); return; }
-        F.valid_bytes[row] = 0; seen |= 1u << f;
+        F.valid_bytes[row] = 0; seen |= 1ull << f;
         if (F.dtype == (int)DType::Utf8) { F.str_len[row] = 0; F.str_raw_len[row] = 0; }
+        if (F.dtype == (int)DType::List || F.dtype == (int)DType::Struct) F.str_raw_len[row] = 0;
         continue;
       }
       switch ((DType)F.dtype) {
@@ -424,21 +435,119 @@ __global__ void __launch_bounds__(JS_THREADS) json_parse_kernel(const __grid_con
           F.str_len[row] = dl; F.str_src[row] = (long long)(sb - origin); F.str_raw_len[row] = esc ? -sl : sl;
           break;
         }
+        case DType::List: case DType::Struct: {  // the raw span of the value; its elements / fields are decoded by a second stage
+          if (ch != ((DType)F.dtype == DType::List ? '[' : '{')) { raise(P, JE_TYPE, i); return; }
+          const uint8_t* v0 = c.p;
+          if (!skip_value(c, 0)) { raise(P, JE_SYNTAX, i); return; }
+          F.str_src[row] = (long long)(v0 - origin); F.str_raw_len[row] = (int)(c.p - v0);
+          break;
+        }
         default:  // Null-typed column: any non-null value is a type error in arrow-json's NullArrayDecoder
           raise(P, JE_TYPE, i); return;
       }
-      F.valid_bytes[row] = 1; seen |= 1u << f;
+      F.valid_bytes[row] = 1; seen |= 1ull << f;
     }
     for (int k = 0; k < P.n_fields; ++k) {
       if (!((seen >> k) & 1)) {  // missing key → NULL
-        P.fields[k].valid_bytes[row] = 0;
-        if (P.fields[k].dtype == (int)DType::Utf8) { P.fields[k].str_len[row] = 0; P.fields[k].str_raw_len[row] = 0; }
+        FT[k].valid_bytes[row] = 0;
+        if (FT[k].dtype == (int)DType::Utf8) { FT[k].str_len[row] = 0; FT[k].str_raw_len[row] = 0; }
+        if (FT[k].dtype == (int)DType::List || FT[k].dtype == (int)DType::Struct) FT[k].str_raw_len[row] = 0;
       }
     }
     ++row; ++records;
   }
   if (MODE == 0) P.counts[i] = records;
-  if (MODE == 2 && records != 1) P.error[2] = 1;  // blank payload: no row
+  if (MODE == 2 && records != 1) {
+    if (P.span_src && records == 0) {  // nested pass, NULL / missing struct: a row of NULL children
+      for (int k = 0; k < P.n_fields; ++k) {
+        FT[k].valid_bytes[i] = 0;
+        if (FT[k].dtype == (int)DType::Utf8) { FT[k].str_len[i] = 0; FT[k].str_raw_len[i] = 0; }
+      }
+    } else P.error[2] = 1;  // blank payload: no row
+  }
+}
+
+// ---- List<primitive> columns: second stage over the raw spans captured by the parse pass -------------------------
+// counts[row] = number of elements of the array at data[src[row] .. + raw[row]) (0 for NULL rows)
+__global__ void json_list_count_kernel(const uint8_t* data, const long long* src, const int32_t* raw, int64_t n, int32_t* counts, int32_t* error) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int cnt = 0;
+  if (raw[r] > 0) {
+    Cursor c{data + src[r] + 1, data + src[r] + raw[r]};  // past '['
+    skip_ws(c);
+    if (c.p < c.end && *c.p != ']') {
+      while (true) {
+        if (!skip_value(c, 0)) { if (atomicCAS(error, 0, JE_SYNTAX) == 0) error[1] = (int32_t)r; break; }
+        ++cnt;
+        skip_ws(c);
+        if (c.p < c.end && *c.p == ',') { ++c.p; continue; }
+        break;
+      }
+    }
+  }
+  counts[r] = cnt;
+}
+
+// elements of row r go to child positions offsets[r] ..; same scalar rules as the top-level decoder
+__global__ void json_list_fill_kernel(const uint8_t* data, const long long* src, const int32_t* raw, int64_t n, const int32_t* offsets, int elem_dtype,
+                                      void* values, uint8_t* valid, int32_t* str_len, long long* str_src, int32_t* str_raw, int32_t* error) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n || raw[r] <= 0) return;
+  Cursor c{data + src[r] + 1, data + src[r] + raw[r]};
+  long long e = offsets[r];
+  const long long e_end = offsets[r + 1];
+  auto bad = [&](int code) { if (atomicCAS(error, 0, code) == 0) error[1] = (int32_t)r; };
+  while (e < e_end) {
+    skip_ws(c);
+    if (c.p >= c.end) { bad(JE_SYNTAX); return; }
+    const uint8_t ch = *c.p;
+    if (ch == 'n') {
+      if (!match_lit(c, "null", 4)) { bad(JE_SYNTAX); return; }
+      valid[e] = 0;
+      if (elem_dtype == (int)DType::Utf8) { str_len[e] = 0; str_raw[e] = 0; }
+    } else {
+      switch ((DType)elem_dtype) {
+        case DType::Int64: case DType::Float64: {
+          const uint8_t* ns; int nl;
+          FastInt fi{false, 0};
+          if (ch == '"') { bool esc; if (!skip_string(c, &ns, &nl, &esc)) { bad(JE_SYNTAX); return; } }
+          else if (ch == '-' || (ch >= '0' && ch <= '9')) { if (!skip_number(c, &ns, &nl, &fi)) { bad(JE_SYNTAX); return; } }
+          else { bad(JE_TYPE); return; }
+          if ((DType)elem_dtype == DType::Int64) {
+            long long v = fi.value;
+            if (!fi.ok && !parse_i64(ns, nl, &v)) { bad(JE_NUMBER); return; }
+            ((long long*)values)[e] = v;
+          } else {
+            double v;
+            if (!parse_f64(ns, nl, &v)) { bad(JE_NUMBER); return; }
+            ((double*)values)[e] = v;
+          }
+          break;
+        }
+        case DType::Bool: {
+          if (ch == 't') { if (!match_lit(c, "true", 4)) { bad(JE_SYNTAX); return; } ((uint8_t*)values)[e] = 1; }
+          else if (ch == 'f') { if (!match_lit(c, "false", 5)) { bad(JE_SYNTAX); return; } ((uint8_t*)values)[e] = 0; }
+          else { bad(JE_TYPE); return; }
+          break;
+        }
+        case DType::Utf8: {
+          if (ch != '"') { bad(JE_TYPE); return; }
+          const uint8_t* sb; int sl; bool esc;
+          if (!skip_string(c, &sb, &sl, &esc)) { bad(JE_SYNTAX); return; }
+          int dl = sl;
+          if (esc) { dl = decoded_len(sb, sl); if (dl < 0) { bad(JE_SYNTAX); return; } }
+          str_len[e] = dl; str_src[e] = (long long)(sb - data); str_raw[e] = esc ? -sl : sl;
+          break;
+        }
+        default: bad(JE_TYPE); return;  // List<Null>: only nulls
+      }
+      valid[e] = 1;
+    }
+    ++e;
+    skip_ws(c);
+    if (c.p < c.end && *c.p == ',') ++c.p;
+  }
 }
 
 // string bytes of one Utf8 column: thread per row
@@ -459,7 +568,59 @@ __global__ void i32_to_i64_kernel(const int32_t* in, long long* out, int64_t n) 
   if (i < n) out[i] = in[i];
 }
 
-struct InferredField { std::string name; DType type; bool supported; std::string why; };
+// One column of the inferred schema.  List: `elem` is the element type; Struct: `kids` are its (scalar) fields.
+// Deeper nesting (arrays of arrays / of objects, objects inside objects) is outside the GPU subset → `supported` false.
+struct InferredField {
+  std::string name;
+  DType type = DType::Null;
+  DType elem = DType::Null;
+  std::vector<InferredField> kids;
+  bool supported = true;
+  std::string why;
+};
+
+// arrow-json's type of one JSON value (infer_json_schema): scalars as documented in SURVEY.md §8(c); an array's element
+// type is the coercion of its elements' types (Int64 + Float64 → Float64, X + Null → X, [] → List<Null>).
+InferredField infer_value(const std::string& name, const JsonValue& v, int depth) {
+  InferredField f;
+  f.name = name;
+  switch (v.kind) {
+    case JsonValue::Null: f.type = DType::Null; break;
+    case JsonValue::Bool: f.type = DType::Bool; break;
+    case JsonValue::Number: f.type = v.is_int ? DType::Int64 : DType::Float64; break;
+    case JsonValue::String: f.type = DType::Utf8; break;
+    case JsonValue::Array: {
+      f.type = DType::List;
+      if (depth > 0) { f.supported = false; f.why = "List inside a nested value"; break; }
+      DType t = DType::Null;
+      for (auto& e : v.arr) {
+        if (e.kind == JsonValue::Array || e.kind == JsonValue::Object) { f.supported = false; f.why = "List of nested values"; break; }
+        const DType et = e.kind == JsonValue::Null ? DType::Null : e.kind == JsonValue::Bool ? DType::Bool
+                         : e.kind == JsonValue::Number ? (e.is_int ? DType::Int64 : DType::Float64) : DType::Utf8;
+        if (t == DType::Null) t = et;
+        else if (et == DType::Null || et == t) {}
+        else if ((t == DType::Int64 && et == DType::Float64) || (t == DType::Float64 && et == DType::Int64)) t = DType::Float64;
+        else { f.supported = false; f.why = "List of mixed types"; break; }
+      }
+      f.elem = t;
+      break;
+    }
+    case JsonValue::Object: {
+      f.type = DType::Struct;
+      if (depth > 0) { f.supported = false; f.why = "Struct inside a nested value"; break; }
+      for (auto& kv : v.obj) {
+        bool dup = false;
+        for (auto& k : f.kids) if (k.name == kv.first) dup = true;
+        if (dup) continue;
+        InferredField k = infer_value(kv.first, kv.second, depth + 1);
+        if (!k.supported) { f.supported = false; f.why = k.why; }
+        f.kids.push_back(std::move(k));
+      }
+      break;
+    }
+  }
+  return f;
+}
 
 // arrow-json infer_json_schema over the first record (host side; the record is a few dozen bytes)
 std::vector<InferredField> infer_schema(const std::string& first_record) {
@@ -491,19 +652,138 @@ std::vector<InferredField> infer_schema(const std::string& first_record) {
     bool dup = false;
     for (auto& f : out) if (f.name == kv.first) dup = true;
     if (dup) continue;
-    InferredField f;
-    f.name = kv.first; f.supported = true;
-    switch (kv.second.kind) {
-      case JsonValue::Null: f.type = DType::Null; break;
-      case JsonValue::Bool: f.type = DType::Bool; break;
-      case JsonValue::Number: f.type = kv.second.is_int ? DType::Int64 : DType::Float64; break;
-      case JsonValue::String: f.type = DType::Utf8; break;
-      case JsonValue::Array: f.type = DType::Null; f.supported = false; f.why = "List"; break;
-      case JsonValue::Object: f.type = DType::Null; f.supported = false; f.why = "Struct"; break;
-    }
-    out.push_back(f);
+    out.push_back(infer_value(kv.first, kv.second, 0));
   }
   return out;
+}
+
+const char* json_err_text(int code) {
+  switch (code) {
+    case JE_NOT_OBJECT: return "Arrow JSON Reader Error: Json error: expected { got a non-object value";
+    case JE_TYPE: return "Arrow JSON Reader Error: Json error: whilst decoding field: value does not match the inferred column type";
+    case JE_NUMBER: return "Arrow JSON Reader Error: Json error: failed to parse number";
+    default: return "Arrow JSON Reader Error: Json error: Encountered unexpected token / truncated record";
+  }
+}
+
+// A scalar column (values / strings / validity) of `rows` rows being decoded.
+struct FieldBufs { BufferPtr values, valid_bytes, str_len, str_src, str_raw, str_offsets, vbits; };
+
+void alloc_field(DType type, int64_t rows, FieldBufs& fb, JsonField& F, cudaStream_t stream) {
+  fb.valid_bytes = device_alloc((size_t)std::max<int64_t>(rows, 1));
+  F.valid_bytes = (uint8_t*)fb.valid_bytes.get();
+  if (type == DType::Int64 || type == DType::Float64) { fb.values = device_alloc((size_t)std::max<int64_t>(rows, 1) * 8); F.values = fb.values.get(); }
+  else if (type == DType::Bool) { fb.values = device_alloc((size_t)std::max<int64_t>(rows, 1)); F.values = fb.values.get(); }
+  else if (type == DType::Utf8 || type == DType::List || type == DType::Struct) {
+    fb.str_len = device_alloc((size_t)(rows + 1) * 4); fb.str_src = device_alloc((size_t)std::max<int64_t>(rows, 1) * 8);
+    fb.str_raw = device_alloc((size_t)std::max<int64_t>(rows, 1) * 4);
+    ARK_CUDA(cudaMemsetAsync((int32_t*)fb.str_len.get() + rows, 0, 4, stream));  // the scan reads rows + 1 entries
+    F.str_len = (int32_t*)fb.str_len.get(); F.str_src = (long long*)fb.str_src.get(); F.str_raw_len = (int32_t*)fb.str_raw.get();
+  }
+}
+
+// exclusive scan of n + 1 int32 lengths; returns the offsets buffer, *total_dev points at the last entry
+BufferPtr scan_lengths(const int32_t* lens, int64_t n, cudaStream_t stream) {
+  BufferPtr offs = device_alloc((size_t)(n + 1) * 4);
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, lens, (int32_t*)offs.get(), (int)(n + 1), stream);
+  BufferPtr t2 = device_alloc(tb + 16);
+  note_launch("cub::DeviceScan::ExclusiveSum");
+  cub::DeviceScan::ExclusiveSum(t2.get(), tb, lens, (int32_t*)offs.get(), (int)(n + 1), stream);
+  return offs;
+}
+
+// Finishes a scalar column whose decode pass has run: validity bitmap, Boolean bit packing, string bytes.
+// `data` is the byte base str_src refers to.  Synchronises the stream (string totals / null counts).
+Column finish_scalar(const std::string& name, DType type, int64_t rows, FieldBufs& fb, const uint8_t* data, cudaStream_t stream) {
+  Column c;
+  c.field.name = name; c.field.type = type; c.field.nullable = true; c.length = rows;
+  if (type == DType::Null) { c.field.format = "n"; return c; }
+  BufferPtr nulls = device_alloc(16), h = pinned_alloc(32);
+  ARK_CUDA(cudaMemsetAsync(nulls.get(), 0, 16, stream));
+  if (rows > 0) {
+    fb.vbits = device_alloc((size_t)(rows + 7) / 8 + 1);
+    launch_pack_bits((const uint8_t*)fb.valid_bytes.get(), rows, (uint8_t*)fb.vbits.get(), (unsigned long long*)nulls.get(), stream);
+  }
+  ARK_CUDA(cudaMemcpyAsync(h.get(), nulls.get(), 8, cudaMemcpyDeviceToHost, stream));
+  if (type == DType::Utf8) {
+    fb.str_offsets = scan_lengths((const int32_t*)fb.str_len.get(), rows, stream);
+    ARK_CUDA(cudaMemcpyAsync((char*)h.get() + 8, (int32_t*)fb.str_offsets.get() + rows, 4, cudaMemcpyDeviceToHost, stream));
+  }
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  if (type == DType::Int64 || type == DType::Float64) {
+    c.data = (const uint8_t*)fb.values.get(); c.data_bytes = rows * 8; c.owners = {fb.values};
+  } else if (type == DType::Bool) {
+    BufferPtr bits = device_alloc((size_t)(rows + 7) / 8 + 1);
+    launch_pack_bits((const uint8_t*)fb.values.get(), rows, (uint8_t*)bits.get(), nullptr, stream);
+    c.data = (const uint8_t*)bits.get(); c.data_bytes = (rows + 7) / 8; c.owners = {bits, fb.values};
+  } else if (type == DType::Utf8) {
+    const int32_t total = *(const int32_t*)((char*)h.get() + 8);
+    BufferPtr bytes = device_alloc((size_t)total + 16);
+    if (rows) {
+      KernelTimer t("json_strings_kernel", stream);
+      json_strings_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(data, (const long long*)fb.str_src.get(), (const int32_t*)fb.str_raw.get(),
+                                                                            (const int32_t*)fb.str_offsets.get(), rows, (uint8_t*)bytes.get());
+    }
+    c.offsets = (const int32_t*)fb.str_offsets.get(); c.data = (const uint8_t*)bytes.get(); c.data_bytes = total; c.first_offset = 0;
+    c.owners = {fb.str_offsets, bytes};
+  }
+  const long long n_null = *(const long long*)h.get();
+  if (rows > 0 && n_null > 0) { c.validity = (const uint8_t*)fb.vbits.get(); c.null_count = n_null; c.owners.push_back(fb.vbits); }
+  return c;
+}
+
+[[noreturn]] void raise_json(int code, int where, const char* what) {
+  fail(ARK_ERR_PROCESS, std::string(json_err_text(code)) + " (" + what + " " + std::to_string(where) + ")");
+}
+
+// List<primitive> column from the raw spans of its rows (fb.str_src / fb.str_raw hold them, fb.valid_bytes the row validity)
+Column finish_list(const InferredField& f, int64_t rows, FieldBufs& fb, const uint8_t* data, cudaStream_t stream) {
+  BufferPtr err = device_alloc(16), h = pinned_alloc(32);
+  ARK_CUDA(cudaMemsetAsync(err.get(), 0, 16, stream));
+  BufferPtr counts = device_alloc((size_t)(rows + 1) * 4);
+  ARK_CUDA(cudaMemsetAsync((int32_t*)counts.get() + rows, 0, 4, stream));
+  const unsigned g = (unsigned)std::max<int64_t>(1, ceil_div(rows, 128));
+  if (rows) {
+    KernelTimer t("json_list_count_kernel", stream);
+    json_list_count_kernel<<<g, 128, 0, stream>>>(data, (const long long*)fb.str_src.get(), (const int32_t*)fb.str_raw.get(), rows, (int32_t*)counts.get(), (int32_t*)err.get());
+  }
+  BufferPtr offs = scan_lengths((const int32_t*)counts.get(), rows, stream);
+  ARK_CUDA(cudaMemcpyAsync(h.get(), (int32_t*)offs.get() + rows, 4, cudaMemcpyDeviceToHost, stream));
+  ARK_CUDA(cudaMemcpyAsync((char*)h.get() + 8, err.get(), 8, cudaMemcpyDeviceToHost, stream));
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  if (((int32_t*)((char*)h.get() + 8))[0]) raise_json(((int32_t*)((char*)h.get() + 8))[0], ((int32_t*)((char*)h.get() + 8))[1], "row");
+  const int64_t total = *(const int32_t*)h.get();
+  FieldBufs cb;
+  JsonField CF;
+  memset(&CF, 0, sizeof CF);
+  alloc_field(f.elem, total, cb, CF, stream);
+  if (rows && total) {
+    KernelTimer t("json_list_fill_kernel", stream);
+    json_list_fill_kernel<<<g, 128, 0, stream>>>(data, (const long long*)fb.str_src.get(), (const int32_t*)fb.str_raw.get(), rows, (const int32_t*)offs.get(), (int)f.elem,
+                                                 CF.values, CF.valid_bytes, CF.str_len, CF.str_src, CF.str_raw_len, (int32_t*)err.get());
+  }
+  ARK_CUDA(cudaMemcpyAsync((char*)h.get() + 8, err.get(), 8, cudaMemcpyDeviceToHost, stream));
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  if (((int32_t*)((char*)h.get() + 8))[0]) raise_json(((int32_t*)((char*)h.get() + 8))[0], ((int32_t*)((char*)h.get() + 8))[1], "row");
+  Column child = finish_scalar("item", f.elem, total, cb, data, stream);  // arrow-rs names a list's field "item"
+  Column c;
+  c.field.name = f.name; c.field.type = DType::List; c.field.format = "+l"; c.field.nullable = true; c.length = rows;
+  // row validity
+  BufferPtr nulls = device_alloc(16), hn = pinned_alloc(16);
+  ARK_CUDA(cudaMemsetAsync(nulls.get(), 0, 16, stream));
+  if (rows > 0) {
+    BufferPtr vb = device_alloc((size_t)(rows + 7) / 8 + 1);
+    launch_pack_bits((const uint8_t*)fb.valid_bytes.get(), rows, (uint8_t*)vb.get(), (unsigned long long*)nulls.get(), stream);
+    ARK_CUDA(cudaMemcpyAsync(hn.get(), nulls.get(), 8, cudaMemcpyDeviceToHost, stream));
+    ARK_CUDA(cudaStreamSynchronize(stream));
+    const long long n_null = *(const long long*)hn.get();
+    if (n_null > 0) { c.validity = (const uint8_t*)vb.get(); c.null_count = n_null; c.owners.push_back(vb); }
+  }
+  c.offsets = (const int32_t*)offs.get(); c.first_offset = 0;
+  c.owners.push_back(offs);
+  c.children.push_back(std::move(child));
+  return c;
 }
 
 }  // namespace
@@ -540,7 +820,107 @@ std::unique_ptr<Processor> make_json_to_arrow(const char* config_json) {
 
 const std::string& json_to_arrow_value_field(const Processor& p) { return static_cast<const JsonToArrowProcessor&>(p).value_field; }
 
-// `in` holds the payload column (device-resident).  first_record: the bytes of the first payload.
+namespace {
+
+// Uploads the field table of `specs` (names included) and returns the parameter block's view of it.
+struct FieldTable {
+  std::vector<FieldBufs> fb;
+  BufferPtr table_dev, names_dev;  // only for schemas that do not fit the parameter block
+};
+
+// Decodes `specs` into `rows` rows.  The payloads are rows of a Binary column (P.offsets) or raw spans (P.span_src).
+// optimistic: payload i → row i in ONE pass; returns false (nothing raised) when the batch is not of that shape or
+// holds an error — the caller then takes the two-pass route, which reports errors the canonical way.
+bool decode_fields(const std::vector<InferredField>& specs, JsonParams Q, unsigned grid, size_t smem, int64_t rows, bool optimistic,
+                   const long long* row_start, const uint8_t* data, std::vector<Column>& out_cols, cudaStream_t stream) {
+  const size_t nf = specs.size();
+  std::vector<FieldBufs> fb(nf);
+  std::vector<JsonField> table(nf);
+  // names longer than the inline slot live in one HBM pool
+  std::string pool;
+  std::vector<size_t> pool_off(nf, 0);
+  for (size_t k = 0; k < nf; ++k) if ((int)specs[k].name.size() > JS_MAX_NAME) { pool_off[k] = pool.size(); pool += specs[k].name; }
+  BufferPtr names_dev;
+  if (!pool.empty()) {
+    names_dev = device_alloc(pool.size());
+    ARK_CUDA(cudaMemcpyAsync(names_dev.get(), pool.data(), pool.size(), cudaMemcpyHostToDevice, stream));
+  }
+  for (size_t k = 0; k < nf; ++k) {
+    JsonField& F = table[k];
+    memset(&F, 0, sizeof F);
+    F.dtype = (int)specs[k].type; F.name_len = (int)specs[k].name.size();
+    if ((int)specs[k].name.size() > JS_MAX_NAME) F.long_name = (const char*)names_dev.get() + pool_off[k];
+    else memcpy(F.name, specs[k].name.data(), specs[k].name.size());
+    alloc_field(specs[k].type, rows, fb[k], F, stream);
+  }
+  Q.n_fields = (int)nf;
+  Q.row_start = row_start;
+  BufferPtr table_dev;
+  if (nf > (size_t)JS_MAX_FIELDS) {
+    table_dev = device_alloc(nf * sizeof(JsonField));
+    ARK_CUDA(cudaMemcpyAsync(table_dev.get(), table.data(), nf * sizeof(JsonField), cudaMemcpyHostToDevice, stream));
+    ARK_CUDA(cudaStreamSynchronize(stream));  // `table` / `pool` are host temporaries
+    Q.fields_ext = (const JsonField*)table_dev.get();
+  } else {
+    for (size_t k = 0; k < nf; ++k) Q.fields[k] = table[k];
+    Q.fields_ext = nullptr;
+    if (!pool.empty()) ARK_CUDA(cudaStreamSynchronize(stream));
+  }
+  BufferPtr err = device_alloc(16), h = pinned_alloc(32);
+  Q.error = (int32_t*)err.get();
+  ARK_CUDA(cudaMemsetAsync(err.get(), 0, 16, stream));
+  {
+    KernelTimer t("json_parse_kernel", stream);
+    if (optimistic) json_parse_kernel<2><<<grid, JS_THREADS, smem, stream>>>(Q);
+    else json_parse_kernel<1><<<grid, JS_THREADS, smem, stream>>>(Q);
+  }
+  ARK_CUDA(cudaGetLastError());
+  ARK_CUDA(cudaMemcpyAsync(h.get(), err.get(), 16, cudaMemcpyDeviceToHost, stream));
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  const int32_t* e = (const int32_t*)h.get();
+  if (optimistic && (e[0] != JE_NONE || e[2])) return false;
+  if (e[0] != JE_NONE) raise_json(e[0], e[1], Q.span_src ? "row" : "payload");
+  out_cols.clear();
+  for (size_t k = 0; k < nf; ++k) {
+    const InferredField& f = specs[k];
+    if (f.type == DType::List) out_cols.push_back(finish_list(f, rows, fb[k], data, stream));
+    else if (f.type == DType::Struct) {
+      // the struct's children: the same decoder over the captured spans, one row per span
+      JsonParams S;
+      memset(&S, 0, sizeof S);
+      S.data = data; S.n_payloads = rows; S.stage_bytes = 0;
+      S.span_src = (const long long*)fb[k].str_src.get(); S.span_len = (const int32_t*)fb[k].str_raw.get();
+      std::vector<Column> kids;
+      if (rows > 0 && !f.kids.empty()) {
+        if (!decode_fields(f.kids, S, (unsigned)ceil_div(rows, JS_THREADS), 32, rows, true, nullptr, data, kids, stream))
+          decode_fields(f.kids, S, (unsigned)ceil_div(rows, JS_THREADS), 32, rows, false, nullptr, data, kids, stream);  // raises the canonical error
+      } else {
+        for (auto& kf : f.kids) { Column kc; kc.field.name = kf.name; kc.field.type = kf.type; kc.field.nullable = true; kc.length = rows; if (kf.type == DType::Null) kc.field.format = "n"; kids.push_back(kc); }
+      }
+      Column c;
+      c.field.name = f.name; c.field.type = DType::Struct; c.field.format = "+s"; c.field.nullable = true; c.length = rows;
+      BufferPtr nulls = device_alloc(16), hn = pinned_alloc(16);
+      ARK_CUDA(cudaMemsetAsync(nulls.get(), 0, 16, stream));
+      if (rows > 0) {
+        BufferPtr vb = device_alloc((size_t)(rows + 7) / 8 + 1);
+        launch_pack_bits((const uint8_t*)fb[k].valid_bytes.get(), rows, (uint8_t*)vb.get(), (unsigned long long*)nulls.get(), stream);
+        ARK_CUDA(cudaMemcpyAsync(hn.get(), nulls.get(), 8, cudaMemcpyDeviceToHost, stream));
+        ARK_CUDA(cudaStreamSynchronize(stream));
+        const long long n_null = *(const long long*)hn.get();
+        if (n_null > 0) { c.validity = (const uint8_t*)vb.get(); c.null_count = n_null; c.owners.push_back(vb); }
+      }
+      c.children = std::move(kids);
+      out_cols.push_back(std::move(c));
+    } else out_cols.push_back(finish_scalar(f.name, f.type, rows, fb[k], data, stream));
+  }
+  ARK_CUDA(cudaGetLastError());
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  return true;
+}
+
+}  // namespace
+
+// `in` holds the payload column (device-resident).
 Batch json_to_arrow_device(const Processor& proc, Batch& in, cudaStream_t stream) {
   const auto& jp = static_cast<const JsonToArrowProcessor&>(proc);
   const int ci = in.find(jp.value_field);
@@ -591,139 +971,32 @@ Batch json_to_arrow_device(const Processor& proc, Batch& in, cudaStream_t stream
     for (auto& f : inferred) if (std::find(jp.include.begin(), jp.include.end(), f.name) != jp.include.end()) fields.push_back(f);
   } else fields = inferred;
   for (auto& f : fields)
-    if (!f.supported) fail(ARK_ERR_UNSUPPORTED, "json_to_arrow: field '" + f.name + "' is a nested value (" + f.why + " column)");
-  if ((int)fields.size() > JS_MAX_FIELDS) fail(ARK_ERR_UNSUPPORTED, "json_to_arrow: more than 16 fields");
-  for (auto& f : fields) if ((int)f.name.size() > JS_MAX_NAME) fail(ARK_ERR_UNSUPPORTED, "json_to_arrow: field name longer than 48 bytes");
+    if (!f.supported) fail(ARK_ERR_UNSUPPORTED, "json_to_arrow: field '" + f.name + "': " + f.why + " (one level of List<primitive> / Struct<primitives> is decoded)");
+  if ((int)fields.size() > JS_MAX_FIELDS_EXT) fail(ARK_ERR_UNSUPPORTED, "json_to_arrow: more than 64 fields in one record");
+  for (auto& f : fields) if ((int)f.kids.size() > JS_MAX_FIELDS_EXT) fail(ARK_ERR_UNSUPPORTED, "json_to_arrow: more than 64 fields in one nested object");
 
   JsonParams P;
   memset(&P, 0, sizeof P);
   P.data = col.data; P.offsets = col.offsets; P.validity = col.validity; P.validity_bit0 = col.validity_bit0;
-  P.n_payloads = n; P.n_fields = (int)fields.size();
+  P.n_payloads = n;
   // staging window: the CTA's payload bytes + alignment slack; payloads that average more than 256 bytes are parsed in place
   static const bool no_stage = getenv("ARK_JSON_NO_STAGE") != nullptr;
   const double avg = (double)col.data_bytes / (double)n;
   P.stage_bytes = (!no_stage && avg <= 256.0) ? (int)round_up((int64_t)(avg * JS_THREADS * 1.25) + 256, 1024) : 0;
   const size_t smem = (size_t)P.stage_bytes + 32;
-  for (size_t k = 0; k < fields.size(); ++k) {
-    JsonField& F = P.fields[k];
-    F.dtype = (int)fields[k].type; F.name_len = (int)fields[k].name.size();
-    memcpy(F.name, fields[k].name.data(), fields[k].name.size());
-  }
-  BufferPtr err = device_alloc(16);
-  P.error = (int32_t*)err.get();
-  BufferPtr h = pinned_alloc(256);  // [0,16) error words, [16,24) rows, [32,96) string totals, [96,224) null counts
   const unsigned grid = (unsigned)ceil_div(n, JS_THREADS);
-  auto raise_host = [&](const int32_t* e) {
-    const std::string where = " (payload " + std::to_string(e[1]) + ")";
-    switch (e[0]) {
-      case JE_NOT_OBJECT: fail(ARK_ERR_PROCESS, "Arrow JSON Reader Error: Json error: expected { got a non-object value" + where);
-      case JE_TYPE: fail(ARK_ERR_PROCESS, "Arrow JSON Reader Error: Json error: whilst decoding field: value does not match the inferred column type" + where);
-      case JE_NUMBER: fail(ARK_ERR_PROCESS, "Arrow JSON Reader Error: Json error: failed to parse number" + where);
-      default: fail(ARK_ERR_PROCESS, "Arrow JSON Reader Error: Json error: Encountered unexpected token / truncated record" + where);
-    }
-  };
-
-  // Parses into freshly allocated columns of `rows` rows.  optimistic: payload i → row i in ONE pass; returns
-  // false (nothing raised) when the batch is not of that shape or holds an error, and the caller takes the
-  // two-pass route, which reports errors the canonical way.
-  auto parse = [&](int64_t rows, bool optimistic, const long long* row_start) -> bool {
-    struct FieldBufs { BufferPtr values, valid_bytes, str_len, str_src, str_raw, str_offsets, vbits; };
-    std::vector<FieldBufs> fb(fields.size());
-    JsonParams Q = P;
-    Q.row_start = row_start;
-    for (size_t k = 0; k < fields.size(); ++k) {
-      JsonField& F = Q.fields[k];
-      fb[k].valid_bytes = device_alloc((size_t)std::max<int64_t>(rows, 1));
-      F.valid_bytes = (uint8_t*)fb[k].valid_bytes.get();
-      if (fields[k].type == DType::Int64 || fields[k].type == DType::Float64) { fb[k].values = device_alloc((size_t)std::max<int64_t>(rows, 1) * 8); F.values = fb[k].values.get(); }
-      else if (fields[k].type == DType::Bool) { fb[k].values = device_alloc((size_t)std::max<int64_t>(rows, 1)); F.values = fb[k].values.get(); }
-      else if (fields[k].type == DType::Utf8) {
-        fb[k].str_len = device_alloc((size_t)(rows + 1) * 4); fb[k].str_src = device_alloc((size_t)std::max<int64_t>(rows, 1) * 8);
-        fb[k].str_raw = device_alloc((size_t)std::max<int64_t>(rows, 1) * 4);
-        ARK_CUDA(cudaMemsetAsync((int32_t*)fb[k].str_len.get() + rows, 0, 4, stream));  // the scan reads rows + 1 entries
-        F.str_len = (int32_t*)fb[k].str_len.get(); F.str_src = (long long*)fb[k].str_src.get(); F.str_raw_len = (int32_t*)fb[k].str_raw.get();
-      }
-    }
-    ARK_CUDA(cudaMemsetAsync(err.get(), 0, 16, stream));
-    if (optimistic) {
-      KernelTimer t("json_parse_kernel", stream);
-      json_parse_kernel<2><<<grid, JS_THREADS, smem, stream>>>(Q);
-    } else {
-      KernelTimer t("json_parse_kernel", stream);
-      json_parse_kernel<1><<<grid, JS_THREADS, smem, stream>>>(Q);
-    }
-    ARK_CUDA(cudaGetLastError());
-    // string offsets (exclusive scan of the decoded lengths) and validity bitmaps + null counts, then ONE round trip
-    BufferPtr nulls = device_alloc(fields.size() * 8 + 8);
-    ARK_CUDA(cudaMemsetAsync(nulls.get(), 0, fields.size() * 8 + 8, stream));
-    int n_str = 0;
-    for (size_t k = 0; k < fields.size(); ++k) {
-      if (fields[k].type == DType::Utf8) {
-        fb[k].str_offsets = device_alloc((size_t)(rows + 1) * 4);
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, (int32_t*)fb[k].str_len.get(), (int32_t*)fb[k].str_offsets.get(), (int)(rows + 1), stream);
-        BufferPtr t2 = device_alloc(tb + 16);
-        note_launch("cub::DeviceScan::ExclusiveSum");
-        cub::DeviceScan::ExclusiveSum(t2.get(), tb, (int32_t*)fb[k].str_len.get(), (int32_t*)fb[k].str_offsets.get(), (int)(rows + 1), stream);
-        ARK_CUDA(cudaMemcpyAsync((char*)h.get() + 32 + 4 * n_str, (int32_t*)fb[k].str_offsets.get() + rows, 4, cudaMemcpyDeviceToHost, stream));
-        ++n_str;
-      }
-      if (fields[k].type != DType::Null && rows > 0) {
-        fb[k].vbits = device_alloc((size_t)(rows + 7) / 8 + 1);
-        launch_pack_bits((const uint8_t*)fb[k].valid_bytes.get(), rows, (uint8_t*)fb[k].vbits.get(), (unsigned long long*)nulls.get() + k, stream);
-      }
-    }
-    ARK_CUDA(cudaMemcpyAsync((char*)h.get() + 96, nulls.get(), fields.size() * 8, cudaMemcpyDeviceToHost, stream));
-    ARK_CUDA(cudaMemcpyAsync(h.get(), err.get(), 16, cudaMemcpyDeviceToHost, stream));
-    ARK_CUDA(cudaStreamSynchronize(stream));
-    const int32_t* e = (const int32_t*)h.get();
-    if (optimistic && (e[0] != JE_NONE || e[2])) return false;
-    if (e[0] != JE_NONE) raise_host(e);
-    out.num_rows = rows;
-    out.cols.clear();
-    n_str = 0;
-    for (size_t k = 0; k < fields.size(); ++k) {
-      Column c;
-      c.field.name = fields[k].name; c.field.type = fields[k].type; c.field.nullable = true; c.length = rows;
-      if (fields[k].type == DType::Null) c.field.format = "n";
-      if (fields[k].type == DType::Int64 || fields[k].type == DType::Float64) {
-        c.data = (const uint8_t*)fb[k].values.get(); c.data_bytes = rows * 8; c.owners = {fb[k].values};
-      } else if (fields[k].type == DType::Bool) {
-        BufferPtr bits = device_alloc((size_t)(rows + 7) / 8 + 1);
-        launch_pack_bits((const uint8_t*)fb[k].values.get(), rows, (uint8_t*)bits.get(), nullptr, stream);
-        c.data = (const uint8_t*)bits.get(); c.data_bytes = (rows + 7) / 8; c.owners = {bits, fb[k].values};
-      } else if (fields[k].type == DType::Utf8) {
-        const int32_t total = *(const int32_t*)((char*)h.get() + 32 + 4 * n_str);
-        ++n_str;
-        BufferPtr bytes = device_alloc((size_t)total + 16);
-        if (rows) {
-          KernelTimer t("json_strings_kernel", stream);
-          json_strings_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(col.data, (const long long*)fb[k].str_src.get(), (const int32_t*)fb[k].str_raw.get(),
-                                                                                (const int32_t*)fb[k].str_offsets.get(), rows, (uint8_t*)bytes.get());
-        }
-        c.offsets = (const int32_t*)fb[k].str_offsets.get(); c.data = (const uint8_t*)bytes.get(); c.data_bytes = total; c.first_offset = 0;
-        c.owners = {fb[k].str_offsets, bytes};
-      }
-      const long long n_null = ((const long long*)((char*)h.get() + 96))[k];
-      if (fields[k].type != DType::Null && rows > 0 && n_null > 0) {
-        c.validity = (const uint8_t*)fb[k].vbits.get(); c.null_count = n_null; c.owners.push_back(fb[k].vbits);
-      }
-      out.cols.push_back(std::move(c));
-    }
-    ARK_CUDA(cudaGetLastError());
-    ARK_CUDA(cudaStreamSynchronize(stream));
-    return true;
-  };
 
   // ---- one pass when every payload holds exactly one record (the shape of every shipped example) ----
   static const bool two_pass_only = getenv("ARK_JSON_TWO_PASS") != nullptr;
-  if (!two_pass_only && parse(n, true, nullptr)) return out;
+  if (!two_pass_only && decode_fields(fields, P, grid, smem, n, true, nullptr, col.data, out.cols, stream)) { out.num_rows = n; return out; }
 
   // ---- general route: records per payload → row offsets → parse ----
+  BufferPtr err = device_alloc(16), h = pinned_alloc(64);
   BufferPtr counts = device_alloc((size_t)(n + 1) * 4), counts64 = device_alloc((size_t)(n + 1) * 8), row_start = device_alloc((size_t)(n + 1) * 8);
   ARK_CUDA(cudaMemsetAsync(err.get(), 0, 16, stream));
   ARK_CUDA(cudaMemsetAsync(counts.get(), 0, (size_t)(n + 1) * 4, stream));
   P.counts = (int32_t*)counts.get();
+  P.error = (int32_t*)err.get();
   {
     KernelTimer t("json_count_kernel", stream);
     json_parse_kernel<0><<<grid, JS_THREADS, smem, stream>>>(P);
@@ -740,9 +1013,10 @@ Batch json_to_arrow_device(const Processor& proc, Batch& in, cudaStream_t stream
   ARK_CUDA(cudaMemcpyAsync((char*)h.get() + 16, (long long*)row_start.get() + n, 8, cudaMemcpyDeviceToHost, stream));
   ARK_CUDA(cudaMemcpyAsync(h.get(), err.get(), 16, cudaMemcpyDeviceToHost, stream));
   ARK_CUDA(cudaStreamSynchronize(stream));
-  if (((const int32_t*)h.get())[0] != JE_NONE) raise_host((const int32_t*)h.get());
+  if (((const int32_t*)h.get())[0] != JE_NONE) raise_json(((const int32_t*)h.get())[0], ((const int32_t*)h.get())[1], "payload");
   const int64_t rows = *(const long long*)((char*)h.get() + 16);
-  parse(rows, false, (const long long*)row_start.get());
+  decode_fields(fields, P, grid, smem, rows, false, (const long long*)row_start.get(), col.data, out.cols, stream);
+  out.num_rows = rows;
   return out;
 }
 

@@ -23,6 +23,8 @@ const char* dtype_name(DType t) {
     case DType::Float64: return "Float64";
     case DType::Utf8: return "Utf8";
     case DType::Binary: return "Binary";
+    case DType::List: return "List";
+    case DType::Struct: return "Struct";
   }
   return "?";
 }
@@ -34,6 +36,8 @@ const char* dtype_arrow_format(DType t) {
     case DType::Float64: return "g";
     case DType::Utf8: return "u";
     case DType::Binary: return "z";
+    case DType::List: return "+l";
+    case DType::Struct: return "+s";
   }
   return "n";
 }

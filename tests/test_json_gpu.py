@@ -48,7 +48,7 @@ def test_generate_example_payloads(gpu):
 
 
 def test_basic_types_scalar_fields(gpu):
-    # json.rs:170-207 (array/object fields are outside the subset: see test_nested_values_are_unsupported)
+    # json.rs:170-207, scalar fields (the full record: test_reference_basic_types_record_with_array_and_object)
     rec = {"null_field": None, "bool_field": True, "int_field": 42, "uint_field": 18446744073709551615, "float_field": 3.14, "string_field": "hello"}
     out = check([json.dumps(rec).encode()], approx=("uint_field",))
     assert out.num_rows == 1 and out.num_columns == 6
@@ -83,9 +83,89 @@ def test_missing_config_and_wrong_column(gpu):
     assert e.value.message == "not support data type"
 
 
-def test_nested_values_are_unsupported(gpu):
+def check_nested(payloads, cfg=None, monkeypatch=None):
+    """Host entry point only (the Python DeviceBatch mirror materialises flat columns); oracle in NESTED mode."""
+    import oracle.json_oracle as jo
+
+    monkeypatch.setattr(jo, "NESTED", True)
+    mb = MessageBatch.new_binary(payloads)
+    want = jo.json_to_arrow(mb.record_batch)
+    got = run(mb, cfg, False)
+    assert got.schema.names == want.schema.names
+    assert got.num_rows == want.num_rows
+    for name in want.schema.names:
+        g, w = got.column(name), want.column(name)
+        assert g.type == w.type, (name, g.type, w.type)
+        assert g.to_pylist() == w.to_pylist(), name
+    return got
+
+
+def test_reference_basic_types_record_with_array_and_object(gpu, monkeypatch):
+    # crates/arkflow-plugin/src/processor/json.rs:170-207, the record as the reference's own test builds it
+    rec = {"null_field": None, "bool_field": True, "int_field": 42, "uint_field": 18446744073709551615, "float_field": 3.14,
+           "string_field": "hello", "array_field": [1, 2, 3], "object_field": {"key": "value"}}
+    import oracle.json_oracle as jo
+
+    monkeypatch.setattr(jo, "NESTED", True)
+    mb = MessageBatch.new_binary([json.dumps(rec).encode()])
+    got = run(mb)
+    assert got.num_rows == 1  # what the reference asserts
+    assert got.column("array_field").to_pylist() == [[1, 2, 3]] and got.column("object_field").to_pylist() == [{"key": "value"}]
+    assert str(got.schema.field("array_field").type) == "list<item: int64>" and str(got.schema.field("object_field").type) == "struct<key: string>"
+
+
+def test_nested_lists_and_structs_vs_oracle(gpu, monkeypatch):
+    rng = np.random.default_rng(3)
+    payloads = []
+    for i in range(3000):
+        rec = {"id": i, "tags": ["t%d" % int(x) for x in rng.integers(0, 9, int(rng.integers(0, 5)))],
+               "nums": [int(x) for x in rng.integers(-5, 5, int(rng.integers(0, 4)))],
+               "ratios": [float(x) / 4 for x in rng.integers(0, 99, int(rng.integers(1, 3)))],
+               "pos": {"x": float(i) / 8, "y": int(rng.integers(0, 100)), "label": "p\"%d" % i, "ok": bool(i & 1)},
+               "flags": [bool(x) for x in rng.integers(0, 2, 2)]}
+        if i % 7 == 0:
+            rec["tags"] = None
+        if i % 11 == 0:
+            del rec["pos"]
+        if i % 13 == 0:
+            rec["pos"] = {"y": "17", "extra": [1, {"deep": 2}]}  # missing children → NULL, quoted number, ignored key
+        if i % 17 == 0:
+            rec["nums"] = [1, None, "3"]
+        if i == 0:
+            rec["ratios"] = [1, 2.5]  # Int64 + Float64 in the first record → List<Float64>
+        payloads.append(json.dumps(rec).encode())
+    got = check_nested(payloads, monkeypatch=monkeypatch)
+    assert str(got.schema.field("ratios").type) == "list<item: double>"
+
+
+def test_nested_edge_cases(gpu, monkeypatch):
+    got = check_nested([b'{"a": [], "s": {}, "n": 1}', b'{"a": [null, null], "s": {}, "n": 2}', b'{"n": 3}'], monkeypatch=monkeypatch)
+    assert str(got.schema.field("a").type) == "list<item: null>"
+    # a scalar where the first record had an array / object is a type error, as in arrow-json
+    for bad in (b'{"a": 5}', b'{"s": "x"}'):
+        with pytest.raises(ArkError) as e:
+            run(MessageBatch.new_binary([b'{"a": [1], "s": {"k": 1}}', bad]))
+        assert e.value.kind == "Process"
+    # two levels of nesting stay outside the subset
+    for deep in (b'{"a": [[1]]}', b'{"a": [{"k": 1}]}', b'{"s": {"t": {"u": 1}}}', b'{"s": {"t": [1]}}', b'{"a": [1, "x"]}'):
+        with pytest.raises(ArkError) as e:
+            run(MessageBatch.new_binary([deep]))
+        assert e.value.kind == "Unsupported"
+
+
+def test_wide_records_and_long_field_names(gpu):
+    """More than 16 top-level keys and names longer than 48 bytes (the r1 limits of the parameter-block field table)."""
+    long_name = "a_field_name_that_is_considerably_longer_than_forty_eight_bytes_in_total"
+    recs = []
+    for i in range(500):
+        r = {"k%02d" % c: i * c for c in range(40)}
+        r[long_name] = "v%d" % i
+        r["\u00e9t\u00e9"] = i  # a key that needs no escape once serialised as UTF-8
+        recs.append(r)
+    out = check([json.dumps(r, ensure_ascii=False).encode() for r in recs])
+    assert out.num_columns == 42 and out.column(long_name)[499].as_py() == "v499"
     with pytest.raises(ArkError) as e:
-        run(MessageBatch.new_binary([b'{"a": [1,2]}']))
+        run(MessageBatch.new_binary([json.dumps({"c%d" % c: c for c in range(65)}).encode()]))
     assert e.value.kind == "Unsupported"
 
 

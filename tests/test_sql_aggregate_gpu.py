@@ -51,8 +51,26 @@ def check_agg(rb, query, key_cols, float_cols=(), abs_sums=None, counts=None):
             w = sorted(map(tuple, zip(*[c.to_pylist() for c in want.columns])), key=repr)
             if not float_cols:
                 assert g == w
-            else:
+            else:  # float aggregates without a projected key: every row's floats within the §8(d) bound over the whole batch
                 assert len(g) == len(w)
+                n_rows = rb.num_rows
+                s_abs = abs_sums[()] if abs_sums and () in abs_sums else None
+                if s_abs is None and "value" in rb.schema.names:
+                    s_abs = float(sum(abs(v) for v in rb.column("value").to_pylist() if v is not None))
+                fidx = [i for i, nm in enumerate(want.schema.names) if nm in float_cols]
+                key_of = lambda row: tuple(v for i, v in enumerate(row) if i not in fidx)  # noqa: E731
+                g2, w2 = sorted(g, key=lambda r: repr(key_of(r))), sorted(w, key=lambda r: repr(key_of(r)))
+                for gr, wr in zip(g2, w2):
+                    assert key_of(gr) == key_of(wr)
+                    for i in fidx:
+                        gv, wv = gr[i], wr[i]
+                        assert (gv is None) == (wv is None)
+                        if wv is None:
+                            continue
+                        bound = 2 * max(n_rows - 1, 1) * 2.0 ** -53 * (s_abs if s_abs is not None else abs(wv) * n_rows) + 1e-300
+                        if want.schema.names[i].startswith("avg"):
+                            bound = bound + abs(wv) * 2.0 ** -52
+                        assert abs(gv - wv) <= bound, (want.schema.names[i], gv, wv, bound)
             continue
         gd, wd = rows_as_dict(got, key_cols), rows_as_dict(want, key_cols)
         assert gd.keys() == wd.keys()
@@ -300,3 +318,35 @@ def test_protobuf_example_query_cast_of_aggregate_and_order_by(gpu):
     with pytest.raises(ArkError) as e:
         run(rb, "SELECT cast(avg(value) as string) FROM flow")
     assert e.value.kind == "Unsupported"
+
+
+def test_two_group_by_keys(gpu):
+    """Composite keys (KEY_PAIR): every combination of key types, NULLs in either key, the keys projected in any order."""
+    rng = np.random.default_rng(21)
+    n = 60_000
+    rb = pa.record_batch({
+        "a": pa.array([None if rng.random() < 0.05 else int(x) for x in rng.integers(0, 40, n)], pa.int64()),
+        "s": pa.array([None if rng.random() < 0.05 else "k%d" % int(x) for x in rng.integers(0, 25, n)]),
+        "long": pa.array(["a_long_key_value_%02d" % int(x) for x in rng.integers(0, 30, n)]),
+        "b": pa.array([bool(x) for x in rng.integers(0, 2, n)], pa.bool_()),
+        "v": pa.array(rng.integers(-100, 100, n), pa.int64()),
+        "f": pa.array(rng.random(n), pa.float64()),
+    })
+    check_agg(rb, "SELECT a, s, SUM(v), COUNT(*) FROM flow GROUP BY a, s", ["a", "s"])
+    check_agg(rb, "SELECT s, a, MIN(v), MAX(v), COUNT(v) FROM flow WHERE v <> 0 GROUP BY a, s", ["a", "s"])
+    check_agg(rb, "SELECT long, b, COUNT(*), SUM(v) FROM flow GROUP BY long, b", ["long", "b"])
+    check_agg(rb, "SELECT s, long, COUNT(*) FROM flow GROUP BY s, long", ["s", "long"])
+    check_agg(rb, "SELECT b, a, COUNT(*) FROM flow GROUP BY b, a", ["b", "a"])
+    check_agg(rb, "SELECT a, COUNT(*) FROM flow GROUP BY a, b", [])  # second key not projected: duplicate `a` rows
+    sums = {}
+    for a, s_, f in zip(rb.column("a").to_pylist(), rb.column("s").to_pylist(), rb.column("f").to_pylist()):
+        sums[(a, s_)] = sums.get((a, s_), 0.0) + abs(f)
+    counts = {}
+    for a, s_ in zip(rb.column("a").to_pylist(), rb.column("s").to_pylist()):
+        counts[(a, s_)] = counts.get((a, s_), 0) + 1
+    check_agg(rb, "SELECT a, s, SUM(f), AVG(f) FROM flow GROUP BY a, s", ["a", "s"], float_cols=("sum(flow.f)", "avg(flow.f)"), abs_sums=sums, counts=counts)
+
+
+def test_two_keys_high_cardinality(gpu):
+    rb = synth_batch(400_000, key_space=50_000)
+    check_agg(rb, "SELECT sensor, value, COUNT(*), SUM(timestamp) FROM flow GROUP BY sensor, value", ["sensor", "value"])
