@@ -93,16 +93,18 @@ struct PendingOut {
   bool is_bool = false;
 };
 
+}  // namespace
+
 const char* vm_error_text(int e) {
   switch (e) {
     case VMERR_DIV_ZERO: return "Arrow error: Divide by zero error";
-    case VMERR_OVERFLOW: return "Arrow error: Arithmetic overflow: Overflow happened on: i64::MIN / -1";
+    case VMERR_OVERFLOW: return "Arrow error: Arithmetic overflow: Overflow happened on: -9223372036854775808 / -1";
+    case VMERR_OVERFLOW_MOD: return "Arrow error: Arithmetic overflow: Overflow happened on: -9223372036854775808 % -1";
     case VMERR_CAST: return "Arrow error: Cast error: Can't cast value to type Int64";
     default: return "unknown evaluation error";
   }
 }
 
-}  // namespace
 
 // ---- fast path: filter_project_tma.cu ------------------------------------------------------------------
 int filter_project_tma_tile_rows();

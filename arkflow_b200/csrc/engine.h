@@ -29,6 +29,7 @@ Column format_int64_column(const Column& src, const std::string& name, cudaStrea
 // kernels' host launchers
 void launch_filter_project(const FpParams& P, int pred_kind, cudaStream_t stream);
 void launch_utf8_validate(const int32_t* offsets, const uint8_t* data, const uint8_t* validity, int vbit0, int64_t n, int* bad, cudaStream_t stream);
+const char* vm_error_text(int vm_error);  // arrow-arith / arrow-cast message of a VmError
 void launch_pack_bits(const uint8_t* bytes, int64_t n, uint8_t* bitmap, unsigned long long* zeros, cudaStream_t stream);
 
 struct Processor {
@@ -71,6 +72,7 @@ void run_group_by_push(const Plan& plan, Batch& in, DistCtx& d, cudaStream_t str
 bool run_group_by_merge(const Plan& plan, DistCtx& d, Batch& out, cudaStream_t stream);
 std::unique_ptr<Processor> make_json_to_arrow(const char* config_json);
 const std::string& json_to_arrow_value_field(const Processor& p);
+std::unique_ptr<Processor> make_json_to_arrow_for_sample(const std::vector<std::string>& sample_records);  // schema fixed by the sample (file input)
 Batch json_to_arrow_device(const Processor& proc, Batch& in, cudaStream_t stream);
 Batch hash_partition(Batch& in, const std::string& key_column, int n_parts, std::vector<int64_t>& part_rows, cudaStream_t stream);
 Column take_column(const Column& src, const unsigned int* idx, int64_t n, const std::string& name, cudaStream_t stream, bool may_miss = false);

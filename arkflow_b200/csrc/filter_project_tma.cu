@@ -85,13 +85,43 @@ __device__ __forceinline__ unsigned long long desc_pack(unsigned long long statu
 constexpr unsigned long long DESC_FIELD = (1ull << 31) - 1;
 constexpr int LB_WINDOWS = 2;  // 2 × 32 predecessor tiles fetched per look-back round
 
+// Forward progress without relying on CTA dispatch order.  A tile's look-back may only wait for tiles whose CTAs are
+// running; with tile = blockIdx.x that holds when CTAs are dispatched in blockIdx order (what CUB's single-pass scans
+// assume), but nothing in the programming model promises it (MPS, time slicing, a debugger, compute-sanitizer).  So a
+// warp that has spun `spin_limit` times on an unpublished predecessor HELPS: it computes that tile's aggregate itself
+// — the predicate over the tile's 1024 rows, 32 per lane — and publishes it with a CAS if it is still missing.  The
+// aggregate is a pure function of the input, so helper and owner can only ever write the same value; the owner still
+// publishes its inclusive prefix when it gets to run.  The fast path never executes this (`ARK_FP_DEBUG=4` forces it:
+// tests/test_sql_filter_gpu.py).
+template <bool VARLEN>
+__device__ __forceinline__ void help_publish_aggregate(const TmaParams& P, int t, int lane) {
+  constexpr int TT = 1024;
+  const int64_t row0 = (int64_t)t * TT;
+  const int rows = (int)((P.n_rows - row0) < TT ? (P.n_rows - row0) : TT);
+  int cnt = 0, bytes = 0;
+  for (int r = lane; r < rows; r += 32) {
+    const unsigned long long v = P.pred_in[row0 + r];
+    const long long key = P.sp_is_f64 ? f64_total_key(v) : (long long)v;
+    bool f = (unsigned long long)(key - P.range_lo) <= P.range_span;
+    f = f != (bool)P.negate;
+    if (f) { ++cnt; if (VARLEN) bytes += P.offsets_in[row0 + r + 1] - P.offsets_in[row0 + r]; }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  bytes = __reduce_add_sync(0xffffffffu, bytes);
+  if (lane == 0) atomicCAS(P.desc + (size_t)t * P.desc_stride, 0ull, desc_pack(t == 0 ? DESC_PREFIX : DESC_AGG, cnt, bytes));
+}
+
 // Decoupled look-back, resolve half (warp 0).  The tile's aggregate is already published.
 // The sustainable tile rate of a single-pass scan is (tiles inspected per round) / (round latency):
 // at ~85 tiles/µs a 32-wide round with shuffle reductions (~0.4 µs) is exactly the limit, so the
 // round is kept short — one volatile load per window, REDUX (`__reduce_add_sync`) instead of shuffle
 // trees, the prefix tile's sums fetched with one shuffle — and two windows are in flight per round.
-__device__ void lookback_resolve(unsigned long long* desc, int stride, int tile, long long agg_cnt, long long agg_bytes, int lane,
+template <bool VARLEN>
+__device__ void lookback_resolve(const TmaParams& P, int tile, long long agg_cnt, long long agg_bytes, int lane,
                                  long long* ex_cnt, long long* ex_bytes) {
+  unsigned long long* const desc = P.desc;
+  const int stride = P.desc_stride;
+  const int spin_limit = (P.debug & 4) ? 2 : 4096;
   long long run_c = 0, run_b = 0;
   if (tile > 0) {
     int look = tile - 1;
@@ -105,7 +135,15 @@ __device__ void lookback_resolve(unsigned long long* desc, int stride, int tile,
         if (!done) {  // warp-uniform
           const int idx = w == 0 ? idx0 : idx1;
           unsigned long long dw = w == 0 ? d0 : d1;
-          while (__any_sync(0xffffffffu, (dw >> 62) == 0)) {  // a predecessor has not published yet
+          int spins = 0;
+          while (true) {  // a predecessor has not published yet
+            const unsigned pending = __ballot_sync(0xffffffffu, (dw >> 62) == 0);
+            if (!pending) break;
+            if (++spins > spin_limit) {  // not making progress: do the nearest missing tile's counting ourselves
+              const int helped = __shfl_sync(0xffffffffu, idx, __ffs(pending) - 1);
+              help_publish_aggregate<VARLEN>(P, helped, lane);
+              spins = 0;
+            }
             if ((dw >> 62) == 0) dw = ld_volatile_u64(desc + (size_t)idx * stride);
           }
           const unsigned pm = __ballot_sync(0xffffffffu, (dw >> 62) == 2);
@@ -307,7 +345,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? ARK_FP_MINBLOCKS : 3
   // ---- F: decoupled look-back (warp 0) ----
   if (warp == 0) {
     long long ex0, ex1;
-    lookback_resolve(P.desc, P.desc_stride, tile, tile_cnt, tb, lane, &ex0, &ex1);
+    lookback_resolve<VARLEN>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
     if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
   }
   __syncthreads();
@@ -573,7 +611,7 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
     if (warp == 0) {
       long long ex0, ex1;
       if (P.debug & 1) { ex0 = (long long)tile * (TT / 2); ex1 = ex0 * 12; }
-      else lookback_resolve(P.desc, P.desc_stride, tile, tile_cnt, tb, lane, &ex0, &ex1);
+      else lookback_resolve<VARLEN>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
       if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
     }
     // ---- E: compact the strings in shared memory at tile-local positions ----
@@ -650,8 +688,10 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
 // the CTA when it STARTS — keeps the guarantee that a tile is only ever owned by a running CTA.
 // ================================================================================================
 template <int NF, bool VARLEN, int MINB>
-__global__ void __launch_bounds__(256, MINB) filter_project_tile_kernel(const __grid_constant__ TmaParams P) {
-  constexpr int T_THREADS = 256, TT = T_THREADS * 4, T_WARPS = T_THREADS / 32;
+__global__ void __launch_bounds__(288, MINB) filter_project_tile_kernel(const __grid_constant__ TmaParams P) {
+  // warps 0..7: the tile's rows; warp 8: producer (tile id, bulk copy) and look-back — nothing but its own few values is
+  // live there, so the (rare) call into help_publish_aggregate costs the data warps no registers and no spills
+  constexpr int T_THREADS = 256, TT = T_THREADS * 4, T_WARPS = T_THREADS / 32, LB_WARP = T_WARPS;
   extern __shared__ __align__(16) uint8_t smem[];   // [in_bytes][out_bytes], each str_cap + 32
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_tile;
@@ -665,9 +705,12 @@ __global__ void __launch_bounds__(256, MINB) filter_project_tile_kernel(const __
   uint8_t* const in_bytes = smem;
   uint8_t* const out_bytes = smem + P.str_cap + 32;
   const int n_tiles = P.n_tiles;
-  if (tid == 0) {
+  if (tid == LB_WARP * 32) {
     if (VARLEN) { mbar_init(&s_bar, 1); mbar_fence_init(); }
-    const int t = (int)atomicAdd(P.ticket, 1u);   // tiles in START order: every smaller tile belongs to a CTA that is running
+    // tile = blockIdx.x: no atomic on the CTA's critical path (a ticket — tiles in START order — costs 12 % here: every CTA
+    // waits ~1 µs for its atomicAdd before it can issue a load; ARK_FP_TICKET=1 selects it).  Forward progress does not
+    // depend on the dispatch order either way: see help_publish_aggregate.
+    const int t = P.ticket ? (int)atomicAdd(P.ticket, 1u) : (int)blockIdx.x;
     s_tile = t;
     if (VARLEN && t < n_tiles) {
       const int64_t r0 = (int64_t)t * TT;
@@ -687,6 +730,20 @@ __global__ void __launch_bounds__(256, MINB) filter_project_tile_kernel(const __
   __syncthreads();
   const int tile = s_tile;
   if (tile >= n_tiles) return;
+  if (warp == LB_WARP) {
+    __syncthreads();   // (1): the data warps' totals are in shared memory
+    int tile_cnt = lane < T_WARPS ? s_cnt[lane] : 0, tb = (VARLEN && lane < T_WARPS) ? s_bytes[lane] : 0;
+    tile_cnt = __reduce_add_sync(0xffffffffu, tile_cnt);
+    tb = __reduce_add_sync(0xffffffffu, tb);
+    if ((P.debug & 4) && (tile % 37) == 5) __nanosleep(40000);  // test knob: a late tile, so that successors have to help
+    if (lane == 0) st_volatile_u64(P.desc + (size_t)tile * P.desc_stride, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
+    long long ex0, ex1;
+    if (P.debug & 1) { ex0 = (long long)tile * (TT / 2); ex1 = ex0 * 12; }
+    else lookback_resolve<VARLEN>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
+    if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
+    __syncthreads();   // (2)
+    return;
+  }
   const int64_t row0 = (int64_t)tile * TT;
   const int rows = (int)((P.n_rows - row0) < TT ? (P.n_rows - row0) : TT);
   unsigned long long pv[4];
@@ -771,14 +828,6 @@ __global__ void __launch_bounds__(256, MINB) filter_project_tile_kernel(const __
       w_bytes_excl = __shfl_sync(0xffffffffu, bi - b, warp);
       tb = __shfl_sync(0xffffffffu, bi, T_WARPS - 1);
     }
-  }
-  if (warp == 0 && lane == 0) st_volatile_u64(P.desc + (size_t)tile * P.desc_stride, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
-  // ---- F: decoupled look-back (warp 0) runs while the other warps compact the strings ----
-  if (warp == 0) {
-    long long ex0, ex1;
-    if (P.debug & 1) { ex0 = (long long)tile * (TT / 2); ex1 = ex0 * 12; }
-    else lookback_resolve(P.desc, P.desc_stride, tile, tile_cnt, tb, lane, &ex0, &ex1);
-    if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
   }
   // ---- E: compact the strings in shared memory at tile-local positions ----
   bool str_fast = false;
@@ -904,6 +953,8 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
   // 1 = the r1 kernel (blocked rows, tile = blockIdx).  0 and 1 are kept for A/B runs.
   static const int impl = [] { const char* e = getenv("ARK_FP_IMPL"); return e ? atoi(e) : 2; }();
   if (impl == 2 && g_fp_threads == 256 && ticket != nullptr) {
+    static const bool use_ticket = [] { const char* e = getenv("ARK_FP_TICKET"); return e && atoi(e) != 0; }();
+    if (!use_ticket) P.ticket = nullptr;
     const size_t smem = v ? 2 * (size_t)(cap + 32) : 0;
     static const int minb = [] { const char* e = getenv("ARK_FP_MINB"); const int x = e ? atoi(e) : 5; return x >= 4 && x <= 6 ? x : 5; }();
 #define ARK_TILE_FN(NF, V) (minb == 4 ? (const void*)filter_project_tile_kernel<NF, V, 4> : minb == 6 ? (const void*)filter_project_tile_kernel<NF, V, 6> : (const void*)filter_project_tile_kernel<NF, V, 5>)
@@ -923,7 +974,7 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
 #undef ARK_TILE_FN
     KernelTimer t("filter_project_tma_kernel", stream);
     void* args[] = {(void*)&P};
-    ARK_CUDA(cudaLaunchKernel(fn, dim3(P.n_tiles), dim3(256), args, smem, stream));
+    ARK_CUDA(cudaLaunchKernel(fn, dim3(P.n_tiles), dim3(288), args, smem, stream));
     return true;
   }
   if (impl == 0 && g_fp_threads == 256 && ticket != nullptr) {

@@ -392,8 +392,7 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
       hints.groups.store(0);  // the previous batch's group count undersized the shared-memory table: size it by capacity
       continue;
     }
-    if (err) fail(ARK_ERR_PROCESS, std::string("Collection query results error: ") +
-                                       (err == VMERR_DIV_ZERO ? "Arrow error: Divide by zero error" : "Arrow error: arithmetic/cast error"));
+    if (err) fail(ARK_ERR_PROCESS, std::string("Collection query results error: ") + vm_error_text(err));
     dg.n_groups = groups;
     dg.capacity = capacity;
     // next batch: the smallest power of two ≥ 2× the groups just seen (load ≤ 0.5), at least 2^12, so that

@@ -695,6 +695,20 @@ int ark_input_connect(ark_input_t* in) {
     StreamLease lease;
     file_connect(in, lease.s);
     if (in->kind == ark_input::FileCsv) csv_prepare(in, lease.s);
+    else if (in->n_lines > 0) {
+      // schema of the file = merge over its first ≤ 1000 records (DataFusion's schema_infer_max_records), fixed for every batch
+      const int64_t sample_lines = std::min<int64_t>(in->n_lines, 1000);
+      std::vector<long long> starts((size_t)sample_lines + 1);
+      ARK_CUDA(cudaMemcpyAsync(starts.data(), in->line_off.get(), (size_t)(sample_lines + 1) * 8, cudaMemcpyDeviceToHost, lease.s));
+      ARK_CUDA(cudaStreamSynchronize(lease.s));
+      std::string text((size_t)(starts[(size_t)sample_lines] - starts[0]), '\0');
+      ARK_CUDA(cudaMemcpyAsync(&text[0], (const uint8_t*)in->file_dev.get() + starts[0], text.size(), cudaMemcpyDeviceToHost, lease.s));
+      ARK_CUDA(cudaStreamSynchronize(lease.s));
+      std::vector<std::string> sample;
+      for (int64_t i = 0; i < sample_lines; ++i)
+        sample.push_back(text.substr((size_t)(starts[(size_t)i] - starts[0]), (size_t)(starts[(size_t)i + 1] - starts[(size_t)i])));
+      in->decoder = make_json_to_arrow_for_sample(sample);
+    }
     in->connected = true;
   });
 }

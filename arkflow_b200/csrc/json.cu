@@ -568,6 +568,8 @@ __global__ void i32_to_i64_kernel(const int32_t* in, long long* out, int64_t n) 
   if (i < n) out[i] = in[i];
 }
 
+}  // namespace
+
 // One column of the inferred schema.  List: `elem` is the element type; Struct: `kids` are its (scalar) fields.
 // Deeper nesting (arrays of arrays / of objects, objects inside objects) is outside the GPU subset → `supported` false.
 struct InferredField {
@@ -578,6 +580,8 @@ struct InferredField {
   bool supported = true;
   std::string why;
 };
+
+namespace {
 
 // arrow-json's type of one JSON value (infer_json_schema): scalars as documented in SURVEY.md §8(c); an array's element
 // type is the coercion of its elements' types (Int64 + Float64 → Float64, X + Null → X, [] → List<Null>).
@@ -655,6 +659,32 @@ std::vector<InferredField> infer_schema(const std::string& first_record) {
     out.push_back(infer_value(kv.first, kv.second, 0));
   }
   return out;
+}
+
+// coerce_data_type of arrow-json's schema inference over several records: X + Null → X, Int64 + Float64 → Float64,
+// equal types stay, anything else → Utf8; nested types must agree (their element / child types are merged the same way)
+void merge_field(InferredField& into, const InferredField& f) {
+  if (!f.supported) { into.supported = false; into.why = f.why; }
+  if (f.type == DType::Null) return;
+  if (into.type == DType::Null) { const std::string n = into.name; const bool sup = into.supported; const std::string why = into.why; into = f; into.name = n; if (!sup) { into.supported = false; into.why = why; } return; }
+  if (into.type == f.type) {
+    if (f.type == DType::List) {
+      if (into.elem == DType::Null) into.elem = f.elem;
+      else if (f.elem == DType::Null || f.elem == into.elem) {}
+      else if ((into.elem == DType::Int64 && f.elem == DType::Float64) || (into.elem == DType::Float64 && f.elem == DType::Int64)) into.elem = DType::Float64;
+      else into.elem = DType::Utf8;
+    } else if (f.type == DType::Struct) {
+      for (auto& k : f.kids) {
+        bool found = false;
+        for (auto& mine : into.kids) if (mine.name == k.name) { merge_field(mine, k); found = true; }
+        if (!found) into.kids.push_back(k);
+      }
+    }
+    return;
+  }
+  if ((into.type == DType::Int64 && f.type == DType::Float64) || (into.type == DType::Float64 && f.type == DType::Int64)) { into.type = DType::Float64; return; }
+  if (into.type == DType::List || into.type == DType::Struct || f.type == DType::List || f.type == DType::Struct) { into.supported = false; into.why = "nested and scalar values under one key"; return; }
+  into.type = DType::Utf8;
 }
 
 const char* json_err_text(int code) {
@@ -793,7 +823,29 @@ struct JsonToArrowProcessor : Processor {
   std::string value_field = "__value__";  // DEFAULT_BINARY_VALUE_FIELD, core/lib.rs:46
   bool has_include = false;
   std::vector<std::string> include;
+  // the `file` input fixes the schema once per file (DataFusion infers it from the first 1000 records at connect time)
+  bool has_fixed_schema = false;
+  std::vector<InferredField> fixed_schema;
 };
+
+// A decoder whose schema is the merge of `sample` (one JSON record per string): what DataFusion's NDJSON reader does
+// with schema_infer_max_records = 1000 (crates/arkflow-plugin/src/input/file.rs:218-228 → ctx.read_json).
+std::unique_ptr<Processor> make_json_to_arrow_for_sample(const std::vector<std::string>& sample) {
+  auto p = std::make_unique<JsonToArrowProcessor>();
+  p->has_fixed_schema = true;
+  for (auto& rec : sample) {
+    bool blank = true;
+    for (char ch : rec) if (!isspace((unsigned char)ch)) blank = false;
+    if (blank) continue;
+    std::vector<InferredField> one = infer_schema(rec);
+    for (auto& f : one) {
+      bool found = false;
+      for (auto& mine : p->fixed_schema) if (mine.name == f.name) { merge_field(mine, f); found = true; }
+      if (!found) p->fixed_schema.push_back(f);
+    }
+  }
+  return p;
+}
 
 std::unique_ptr<Processor> make_json_to_arrow(const char* config_json) {
   // reference: json.rs:124-128 (missing configuration)
@@ -965,7 +1017,7 @@ Batch json_to_arrow_device(const Processor& proc, Batch& in, cudaStream_t stream
     }
   }
   if (first.empty()) return out;
-  std::vector<InferredField> inferred = infer_schema(first);
+  std::vector<InferredField> inferred = jp.has_fixed_schema ? jp.fixed_schema : infer_schema(first);
   std::vector<InferredField> fields;
   if (jp.has_include) {
     for (auto& f : inferred) if (std::find(jp.include.begin(), jp.include.end(), f.name) != jp.include.end()) fields.push_back(f);

@@ -89,8 +89,8 @@ static __device__ __noinline__ VmVal vm_eval(const VmProgram& prog, const ColVie
           int64_t x = (int64_t)r[in.a].bits, y = (int64_t)r[in.b].bits;
           if (y == 0) { *err = VMERR_DIV_ZERO; out.valid = false; }
           else if (x == INT64_MIN && y == -1) {
-            if (in.op == VM_DIV_I64) { *err = VMERR_OVERFLOW; out.valid = false; }
-            else out.bits = 0;
+            *err = in.op == VM_DIV_I64 ? VMERR_OVERFLOW : VMERR_OVERFLOW_MOD;
+            out.valid = false;
           } else out.bits = (uint64_t)(in.op == VM_DIV_I64 ? x / y : x % y);
         }
         break;

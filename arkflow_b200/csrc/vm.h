@@ -8,7 +8,8 @@
 // Semantics restated from arrow-rs 55.2 / DataFusion 47 (third-party, not in /root/reference; call
 // sites crates/arkflow-plugin/src/processor/sql.rs:126-129,197-203):
 //   * Int64 + - * wrap (DataFusion BinaryExpr uses *_wrapping kernels unless fail_on_overflow);
-//   * Int64 / and % by zero raise "Divide by zero error"; i64::MIN / -1 raises an overflow error;
+//   * Int64 / and % by zero raise "Divide by zero error"; i64::MIN / -1 and i64::MIN % -1 raise arrow-arith's
+//     ArithmeticOverflow (div_checked / mod_checked: checked_div / checked_rem return None for both);
 //   * Float64 comparisons use IEEE-754 totalOrder (NaN above +Inf, -0.0 < +0.0, eq is bitwise);
 //   * AND / OR are Kleene three-valued; a NULL predicate drops the row (FilterExec);
 //   * CAST(Float64 AS BIGINT) truncates toward zero and errors on NaN / out-of-range.
@@ -39,7 +40,7 @@ enum VmOp : uint8_t {
 
 enum VmCmp : int32_t { CMP_EQ = 0, CMP_NE, CMP_LT, CMP_LE, CMP_GT, CMP_GE };
 
-enum VmError : int32_t { VMERR_NONE = 0, VMERR_DIV_ZERO = 1, VMERR_OVERFLOW = 2, VMERR_CAST = 3 };
+enum VmError : int32_t { VMERR_NONE = 0, VMERR_DIV_ZERO = 1, VMERR_OVERFLOW = 2 /* i64::MIN / -1 */, VMERR_CAST = 3, VMERR_OVERFLOW_MOD = 4 /* i64::MIN % -1 */ };
 
 struct VmInstr {
   uint8_t op;

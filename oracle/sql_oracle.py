@@ -671,8 +671,10 @@ class _Ctx:
                 else:
                     if np.any((y == 0) & valid):
                         raise OracleError("Process", "Collection query results error: Arrow error: Divide by zero error")
-                    if e.op == "/" and np.any((x == np.iinfo(np.int64).min) & (y == -1) & valid):
-                        raise OracleError("Process", "Collection query results error: Arrow error: Arithmetic overflow")
+                    # arrow-arith div_checked / mod_checked: i64::MIN / -1 and i64::MIN % -1 both overflow (checked_div / checked_rem → None)
+                    if np.any((x == np.iinfo(np.int64).min) & (y == -1) & valid):
+                        raise OracleError("Process", "Collection query results error: Arrow error: Arithmetic overflow: Overflow happened on: "
+                                                     f"-9223372036854775808 {e.op} -1")
                     ys = np.where(y == 0, 1, y)
                     q = np.abs(x.astype(object)) // np.abs(ys.astype(object))  # truncating division, exact
                     q = np.where((x < 0) != (ys < 0), -q, q)

@@ -57,6 +57,49 @@ def main():
         assert got == want, "distributed GROUP BY differs from the oracle"
         print(f"GROUPBY_OK world={world} groups={len(got)} per-rank={[len(p) for p in gathered]}")
 
+    # ---- the device-side exchange (csrc/group_exchange.cu): push over peer memory, flag, merge; several steps ----
+    from arkflow_b200.dist import ExchangeContext
+
+    ctx = ExchangeContext.from_process_group(8 << 20)
+    for step in range(5):
+        q2 = query if step % 2 == 0 else "SELECT sensor, AVG(value), MIN(value), MAX(timestamp), COUNT(*) FROM flow WHERE value >= 2 GROUP BY sensor"
+        e2 = NativeEngine(q2)
+        rb = synth_batch(n + 1000 * step, row0=(step * world + rank) * (n + 5000), seed=100 + step, key_space=10_007)
+        got_dev = distributed_group_by(e2, DeviceBatch.from_arrow(rb), ctx=ctx).to_arrow()
+        rows2 = got_dev.to_pylist()
+        g2 = [None] * world
+        dist.all_gather_object(g2, rows2)
+        if rank == 0:
+            full = pa.Table.from_batches([synth_batch(n + 1000 * step, row0=(step * world + r) * (n + 5000), seed=100 + step, key_space=10_007)
+                                          for r in range(world)]).combine_chunks().to_batches()[0]
+            want2 = {r["sensor"]: r for r in sql_process(full, q2).to_pylist()}
+            got2 = {}
+            for part in g2:
+                for r in part:
+                    assert r["sensor"] not in got2, "group owned by two ranks"
+                    got2[r["sensor"]] = r
+            assert got2.keys() == want2.keys()
+            for k, w in want2.items():
+                for name, wv in w.items():
+                    gv = got2[k][name]
+                    assert gv == wv or (isinstance(wv, float) and abs(gv - wv) <= 1e-9 * max(1.0, abs(wv))), (step, k, name, gv, wv)
+    st = ctx.stats()
+    assert st["steps"] == 5
+    # long keys: every rank falls back to the descriptor exchange for that batch, then the device path works again
+    long_rb = pa.record_batch({"timestamp": local_rb.column("timestamp"), "value": local_rb.column("value"),
+                               "sensor": pa.array(["a_sensor_name_longer_than_twelve_bytes_%d" % (i % 97) for i in range(n)])})
+    before = taken["p2p"]
+    out_long = distributed_group_by(eng, DeviceBatch.from_arrow(long_rb if rank == 0 else local_rb), ctx=ctx).to_arrow()
+    assert taken["p2p"] == before + 1, "the fallback exchange was not taken after a long key"
+    cnt = torch.tensor([sum(out_long.column("count(*)").to_pylist())], dtype=torch.int64, device="cuda")
+    dist.all_reduce(cnt)
+    assert int(cnt.item()) == n * world
+    out_again = distributed_group_by(eng, DeviceBatch.from_arrow(local_rb), ctx=ctx).to_arrow()
+    assert key(out_again) == key(out), "device-side exchange differs from the descriptor exchange"
+    ctx.close()
+    if rank == 0:
+        print(f"EXCHANGE_PUSH_OK world={world}")
+
     # ---- distributed join: probe rows sharded by rank, build side (unique keys) sharded by rank ----
     from arkflow_b200.dist import distributed_join
     from oracle.sql_oracle import sql_join
@@ -67,9 +110,10 @@ def main():
     probe = synth_batch(50_000, row0=rank * 50_000, seed=7, key_space=K)
     lo, hi = rank * K // world, (rank + 1) * K // world
     build = pa.record_batch({"sensor": pa.array(["temp_%07d" % i for i in range(lo, hi)]), "w": pa.array(range(lo, hi), pa.int64())})
+    before_join = taken["p2p"]
     jout_nccl = distributed_join(jeng, {"p": DeviceBatch.from_arrow(probe), "b": DeviceBatch.from_arrow(build)}, {"p": "sensor", "b": "sensor"}, p2p=False).to_arrow()
     jout = distributed_join(jeng, {"p": DeviceBatch.from_arrow(probe), "b": DeviceBatch.from_arrow(build)}, {"p": "sensor", "b": "sensor"}, p2p=True).to_arrow()
-    assert taken["p2p"] == 3, "the peer-memory exchange was not taken for the join"
+    assert taken["p2p"] == before_join + 2, "the peer-memory exchange was not taken for the join"
     assert key(jout) == key(jout_nccl), "peer-memory and NCCL join exchanges disagree"
     jrows = list(map(repr, zip(*[c.to_pylist() for c in jout.columns])))
     jg = [None] * world

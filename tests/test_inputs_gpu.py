@@ -98,7 +98,7 @@ def _write_ndjson(path, n, seed=0):
         for i in range(n):
             r = {"timestamp": 1625000000000 + i, "value": int(rng.integers(0, 20)), "sensor": "temp_%d" % int(rng.integers(0, 50)),
                  "ratio": float(rng.integers(0, 1000)) / 8.0, "ok": bool(i % 3)}
-            if i % 17 == 0:
+            if i % 17 == 5:
                 del r["ratio"]
             rows.append(r)
             f.write(json.dumps(r) + "\n")
@@ -127,6 +127,23 @@ def test_file_ndjson_scan_matches_the_json_decoder(gpu, tmp_path):
     assert table.schema.names == want.schema.names
     for name in want.schema.names:
         assert table.column(name).combine_chunks().equals(want.column(name)), name
+
+
+def test_file_ndjson_schema_is_merged_over_the_first_records(gpu, tmp_path):
+    """DataFusion infers a file's schema once, over its first 1000 records: a field missing from the first record still
+    becomes a column, Int64 then Float64 coerces to Float64 (checked against Arrow C++'s reader, which merges the same way)."""
+    import pyarrow.json as pajson
+
+    p = str(tmp_path / "merge.json")
+    with open(p, "w") as f:
+        f.write('{"a": 1, "n": 5}\n{"a": 2, "b": "x", "n": 2.5}\n{"b": "y", "c": true, "n": 7}\n')
+    inp = FileInput({"input_type": {"type": "json", "path": p}})
+    inp.connect()
+    got = inp.read()[0].record_batch
+    want = pajson.read_json(p)
+    assert got.schema.names == want.schema.names == ["a", "n", "b", "c"]
+    assert [str(t) for t in got.schema.types] == ["int64", "double", "string", "bool"]
+    assert got.to_pylist() == want.to_pylist()
 
 
 def test_file_ndjson_with_query(gpu, tmp_path):

@@ -10,7 +10,7 @@ import pytest
 
 from arkflow_b200.arrow_ffi import DeviceBatch
 from arkflow_b200.processor import ArkError, MessageBatch, SqlProcessor
-from oracle.sql_oracle import sql_process
+from oracle.sql_oracle import OracleError, sql_process
 from oracle.synth import synth_batch
 
 pytestmark = pytest.mark.gpu
@@ -158,6 +158,48 @@ def test_divide_by_zero_is_a_process_error(gpu):
     assert e.value.kind == "Process" and "Divide by zero" in e.value.message
     # rows removed by the filter are not evaluated (FilterExec runs before ProjectionExec)
     check(rb, "SELECT 10 / value FROM flow WHERE value > 0")
+
+
+def test_lookback_helping_path(gpu):
+    """Forward progress without in-order dispatch: with ARK_FP_DEBUG=4 some tiles publish their aggregate late and the
+    look-back of their successors gives up spinning after 2 polls and computes the missing aggregates itself
+    (help_publish_aggregate, csrc/filter_project_tma.cu).  Results must not change.  Run in a subprocess: the knob is
+    read once per process."""
+    import os
+    import subprocess
+    import sys
+
+    code = '''
+import sys
+sys.path.insert(0, %r)
+from arkflow_b200 import _lib as L
+from arkflow_b200.processor import SqlProcessor, MessageBatch, _check
+from oracle.sql_oracle import sql_process
+from oracle.synth import synth_batch
+_check(L.lib().ark_b200_init(0))
+for n, q in ((300_000, "SELECT sensor, value FROM flow WHERE value >= 10"), (257_123, "SELECT timestamp, value FROM flow WHERE value < 7"),
+             (99_999, "SELECT sensor FROM flow WHERE value <> 3")):
+    rb = synth_batch(n, key_space=1000)
+    got = SqlProcessor({"query": q}).process(MessageBatch.new_arrow(rb)).batches[0].record_batch
+    assert got.equals(sql_process(rb, q)), q
+print("HELP_OK")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, ARK_FP_DEBUG="4"))
+    assert r.returncode == 0 and "HELP_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_min_over_minus_one_overflows_for_div_and_mod(gpu):
+    """arrow-arith div_checked / mod_checked: i64::MIN / -1 and i64::MIN % -1 are ArithmeticOverflow errors, with arrow's text."""
+    rb = pa.record_batch({"a": pa.array([5, -(2 ** 63), 7], pa.int64()), "b": pa.array([1, -1, 2], pa.int64())})
+    for op in ("/", "%"):
+        q = f"SELECT a {op} b FROM flow"
+        with pytest.raises(ArkError) as e:
+            run(rb, q)
+        assert e.value.kind == "Process" and f"Overflow happened on: -9223372036854775808 {op} -1" in e.value.message
+        with pytest.raises(OracleError) as oe:
+            sql_process(rb, q)
+        assert f"-9223372036854775808 {op} -1" in str(oe.value)
+        check(rb, f"SELECT a {op} b FROM flow WHERE a > 0")
 
 
 def test_nulls(gpu):
