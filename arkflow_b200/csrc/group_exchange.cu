@@ -50,7 +50,8 @@ __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned l
 struct PushParams {
   const uint8_t* table;
   unsigned long long capacity;
-  int32_t n_acc, rec_bytes, key_kind, world, rank, pad;
+  int32_t n_acc, rec_bytes, key_kind, world, rank;
+  int32_t need_count;  // the table also holds keys of earlier batches: push only slots whose COUNT(*) accumulator is non-zero
   unsigned long long step;
   unsigned long long cap_records, region_bytes;
   uint8_t* peers[GX_MAX_WORLD];  // comm buffer of every rank as mapped here (peers[rank] = the local one)
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(GX_THREADS) exchange_push_kernel(const __grid_
     if (s >= P.capacity) continue;
     key[j] = *tbl_key(P.table, s, bstride);
     if (key[j].hi == KEY_EMPTY) continue;
+    if (P.need_count && *tbl_acc(P.table, s, 0, bstride) == 0) continue;
     if (key_is_long(key[j]) || key_is_pair(key[j])) { flags |= 1; continue; }  // keys that reference the sender's rows cannot travel inline
     part[j] = P.world > 1 ? partition_of(P.key_kind == KEY_NONE ? 0 : hash_key16(key[j]), P.world) : 0;
     local[j] = atomicAdd(&s_cnt[part[j]], 1u);
@@ -197,11 +199,11 @@ __global__ void exchange_ack_kernel(GxPeers peers, int world, int rank, unsigned
 int exchange_record_bytes(int n_acc) { return 16 * ((16 + 8 * n_acc + 15) / 16); }
 
 void launch_exchange_push(const uint8_t* table, unsigned long long capacity, int n_acc, int key_kind, const GxPeers& peers, int world, int rank,
-                          unsigned long long step, unsigned long long region_bytes, cudaStream_t stream) {
+                          unsigned long long step, unsigned long long region_bytes, int need_count, cudaStream_t stream) {
   PushParams P;
   memset(&P, 0, sizeof P);
   P.table = table; P.capacity = capacity; P.n_acc = n_acc; P.rec_bytes = exchange_record_bytes(n_acc); P.key_kind = key_kind;
-  P.world = world; P.rank = rank; P.step = step;
+  P.world = world; P.rank = rank; P.step = step; P.need_count = need_count;
   P.region_bytes = region_bytes; P.cap_records = region_bytes / (unsigned long long)P.rec_bytes;
   if (P.cap_records == 0) fail(ARK_ERR_PROCESS, "exchange region smaller than one record");
   for (int i = 0; i < world; ++i) P.peers[i] = peers.p[i];

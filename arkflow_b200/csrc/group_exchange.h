@@ -42,7 +42,7 @@ struct DistCtx {
 };
 
 void launch_exchange_push(const uint8_t* table, unsigned long long capacity, int n_acc, int key_kind, const GxPeers& peers, int world, int rank,
-                          unsigned long long step, unsigned long long region_bytes, cudaStream_t stream);
+                          unsigned long long step, unsigned long long region_bytes, int need_count, cudaStream_t stream);
 void launch_exchange_merge(uint8_t* table, unsigned long long capacity, int n_acc, const int32_t* acc_kind, const uint8_t* comm,
                            int world, int rank, unsigned long long step, unsigned long long region_bytes, unsigned int* group_count,
                            int32_t* overflow, int32_t* status, unsigned long long* total, cudaStream_t stream);

@@ -37,6 +37,21 @@ __global__ void agg_init_kernel(uint8_t* table, unsigned long long capacity, int
   }
 }
 
+// a cached table starts its next batch: the keys stay, every accumulator goes back to its identity
+__global__ void agg_reset_acc_kernel(uint8_t* table, unsigned long long capacity, int bstride, int n_acc, AccParam a0, AccParam a1, AccParam a2,
+                                     AccParam a3, AccParam a4, AccParam a5, AccParam a6, AccParam a7) {
+  const AccParam accs[AGG_MAX_ACC] = {a0, a1, a2, a3, a4, a5, a6, a7};
+  const unsigned long long lanes = capacity * (unsigned long long)n_acc;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < lanes; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long bucket = i / (4ull * n_acc), r = i % (4ull * n_acc);
+    const int a = (int)(r / 4), lane = (int)(r % 4);
+    unsigned long long init = 0;
+    if (accs[a].kind == ACC_MIN_I64 || accs[a].kind == ACC_MIN_F64) init = 0x7FFFFFFFFFFFFFFFull;
+    if (accs[a].kind == ACC_MAX_I64 || accs[a].kind == ACC_MAX_F64) init = 0x8000000000000000ull;
+    *tbl_acc(table, bucket * 4 + lane, a, bstride) = init;
+  }
+}
+
 constexpr int AGG_THREADS = 256;
 
 // home-slot hash of this kernel's table: the 32-bit key hash spread over 64 bits (a quarter of hash_key16's
@@ -98,10 +113,12 @@ __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_cons
       Key16 mine;
       if (P.key_kind == KEY_PAIR) {
         const ColView& k2 = P.cols[P.key_slot2];
+        *P.long_seen = 1;  // pair keys are stored by row reference
         const unsigned long long h = make_pair_key(P.key_kind1, kc, P.key_kind2, k2, row, &mine);
         slot = table_find_or_claim_pair(P.table, bmask, bstride, h, mine, P.key_kind1, kc, P.key_kind2, k2, &claimed);
       } else {
         const unsigned long long h = table_hash(P.key_kind, kc, row, &mine);
+        if (key_is_long(mine)) *P.long_seen = 1;
         slot = table_find_or_claim(P.table, bmask, bstride, h, mine, kc, kc, &claimed);
       }
       if (slot == ~0ull) { atomicExch(P.overflow, 1); ok = false; }  // the table is too loaded for this batch
@@ -160,12 +177,15 @@ __global__ void __launch_bounds__(AGG_THREADS) hash_agg_kernel(const __grid_cons
 }
 
 // ---- table → dense group list, ordered by partition = hash(key) mod n_parts -----------------------
+// need_count: the table carries keys of earlier batches too (AggHints::CachedTable): a slot belongs to THIS batch's
+// result iff its COUNT(*) accumulator (always accumulator 0) is non-zero
 __global__ void agg_count_parts_kernel(const uint8_t* table, int stride, unsigned long long capacity, ColView kc, int key_kind, int n_parts,
-                                       unsigned int* part_counts) {
+                                       unsigned int* part_counts, int need_count) {
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     Key16 k = *tbl_key(table, i, stride);
     if (k.hi == KEY_EMPTY) continue;
+    if (need_count && *tbl_acc(table, i, 0, stride) == 0) continue;
     const int p = n_parts > 1 ? partition_of(key_kind == KEY_NONE ? 0 : stored_key_hash(k, kc), n_parts) : 0;
     atomicAdd(part_counts + p, 1u);
   }
@@ -173,11 +193,12 @@ __global__ void agg_count_parts_kernel(const uint8_t* table, int stride, unsigne
 
 // part_cursor[p] starts at the exclusive prefix of part_counts; slots[] receives table slot ids
 __global__ void agg_compact_kernel(const uint8_t* table, int stride, unsigned long long capacity, ColView kc, int key_kind, int n_parts,
-                                   unsigned int* part_cursor, unsigned int* slots) {
+                                   unsigned int* part_cursor, unsigned int* slots, int need_count) {
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < capacity;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     Key16 k = *tbl_key(table, i, stride);
     if (k.hi == KEY_EMPTY) continue;
+    if (need_count && *tbl_acc(table, i, 0, stride) == 0) continue;
     const int p = n_parts > 1 ? partition_of(key_kind == KEY_NONE ? 0 : stored_key_hash(k, kc), n_parts) : 0;
     slots[atomicAdd(part_cursor + p, 1u)] = (unsigned int)i;
   }
@@ -290,6 +311,11 @@ struct DenseGroups {  // result of the hash pass: dense arrays of G groups, part
   std::vector<int64_t> part_rows;
   BufferPtr table, slots;                // table + dense slot list
   int stride = 128;   // bucket stride (hash_agg.cuh: table layout)
+  // table reuse across batches (AggHints::CachedTable)
+  bool count_filter = false;            // occupied slots may belong to earlier batches: a group of this batch has COUNT(*) > 0
+  bool cacheable = false;               // may go back to the plan's cache after this call
+  unsigned long long total_keys = 0;    // keys in the table (all batches)
+  int n_acc = 0;
   unsigned long long capacity = 0;
 };
 
@@ -303,7 +329,7 @@ void hash_agg_radix_note_skew();
 static void compact_groups(DenseGroups& dg, const ColView& kc, int key_kind, int n_parts, BufferPtr ctl, BufferPtr hctl, cudaStream_t stream);
 
 // compact == false: stop once the table is built (the device-side exchange pushes the slots themselves)
-static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int n_parts, cudaStream_t stream, bool compact = true) {
+static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int n_parts, cudaStream_t stream, bool compact = true, bool merge_mode = false) {
   const int64_t n = in.num_rows;
   AggHints& hints = *plan.hints;  // per plan: the table size this query needed last time
   unsigned long long capacity = std::max<unsigned long long>(hints.capacity.load(), 1ull << 10);
@@ -313,10 +339,29 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
   BufferPtr hctl = pinned_alloc(512);
   bool allow_radix = true;
   if (n_parts > 32) fail(ARK_ERR_UNSUPPORTED, "more than 32 partitions");
+  static const unsigned long long tile_max = [] { const char* e = getenv("ARK_AGG_TILE_MAX"); return e ? (unsigned long long)atoll(e) : 1024ull; }();  // 2048 slots (≈ 1000 groups): 1.65 ms in the tile kernel vs 1.34 ms in hash_agg_kernel
+  static const bool cache_enabled = [] { const char* e = getenv("ARK_AGG_TABLE_CACHE"); return !e || atoi(e) != 0; }();
+  // reuse needs self-contained keys (no row references) and a COUNT(*) accumulator that tells this batch's groups apart
+  const bool can_cache = cache_enabled && (ex.key_kind == KEY_INT64 || ex.key_kind == KEY_BYTES || ex.key_kind == KEY_BOOL) &&
+                         !ex.accs.empty() && (ex.accs[0].kind == ACC_COUNT_STAR || merge_mode);
+  bool fresh_only = false;
   while (true) {
     const int stride = table_bucket_stride((int)ex.accs.size());
     dg.stride = stride;
-    dg.table = device_alloc((size_t)table_bytes(capacity, (int)ex.accs.size()));
+    dg.n_acc = (int)ex.accs.size();
+    AggHints::CachedTable ct;
+    bool reused = false;
+    // tables of the low-cardinality path (≤ tile_max slots: per-CTA shared-memory tables) are cheap to rebuild and must
+    // not be probed row by row (hot keys would serialise on L2 atomics): they are never reused
+    const bool cache_now = can_cache && capacity > tile_max;
+    if (cache_now && !fresh_only) {
+      std::lock_guard<std::mutex> l(hints.cache_mu);
+      for (size_t i = 0; i < hints.cache.size(); ++i)
+        if (hints.cache[i].capacity == capacity && hints.cache[i].n_acc == dg.n_acc) { ct = hints.cache[i]; hints.cache.erase(hints.cache.begin() + i); reused = true; break; }
+      if (!reused) hints.cache.clear();  // other sizes are of no use any more
+    }
+    dg.table = reused ? ct.table : device_alloc((size_t)table_bytes(capacity, (int)ex.accs.size()));
+    dg.count_filter = reused;  // a fresh table holds only this batch's keys
     AggParams P;
     memset(&P, 0, sizeof P);
     P.n_rows = n;
@@ -338,12 +383,18 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     P.group_count = (unsigned int*)ctl.get();
     P.overflow = (int32_t*)((char*)ctl.get() + 4);
     P.error = (int32_t*)((char*)ctl.get() + 8);
+    P.long_seen = (int32_t*)((char*)ctl.get() + 280);
     P.max_groups = (unsigned int)std::min<unsigned long long>(capacity - capacity / 4, 0x7FFFFFFFull);  // retry above load 0.75
     ARK_CUDA(cudaMemsetAsync(ctl.get(), 0, 512, stream));
     // large tables: partition rows by table region, build each region in shared memory (hash_agg_radix.cu)
     std::vector<BufferPtr> radix_keep;
-    const bool radix = allow_radix && n > 0 && ex.key_kind != KEY_PAIR && launch_hash_agg_radix(P, capacity, (int32_t*)((char*)ctl.get() + 12), &radix_keep, stream);
-    if (!radix) {
+    const bool radix = !reused && allow_radix && n > 0 && ex.key_kind != KEY_PAIR && launch_hash_agg_radix(P, capacity, (int32_t*)((char*)ctl.get() + 12), &radix_keep, stream);
+    if (reused) {
+      KernelTimer t("agg_reset_acc_kernel", stream);
+      const int grid = (int)std::min<unsigned long long>((capacity * P.n_acc + 255) / 256, 148ull * 8);
+      agg_reset_acc_kernel<<<grid, 256, 0, stream>>>(P.table, capacity, stride, P.n_acc, P.accs[0], P.accs[1], P.accs[2], P.accs[3], P.accs[4],
+                                                     P.accs[5], P.accs[6], P.accs[7]);
+    } else if (!radix) {
       KernelTimer t("agg_init_kernel", stream);
       const int grid = (int)std::min<unsigned long long>((capacity + 255) / 256, 148ull * 8);
       agg_init_kernel<<<grid, 256, 0, stream>>>(P.table, capacity, stride, P.n_acc, P.accs[0], P.accs[1], P.accs[2], P.accs[3], P.accs[4],
@@ -366,9 +417,8 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     }
     // low cardinality (table ≤ 1024 slots): per-CTA hash table in shared memory (hash_agg_tile.cu) — hot keys would
     // serialise on L2 atomics here (K = 2: 12.9 ms vs 0.24 ms).  Everything larger: this file's row kernel.
-    static const unsigned long long tile_max = [] { const char* e = getenv("ARK_AGG_TILE_MAX"); return e ? (unsigned long long)atoll(e) : 1024ull; }();  // 2048 slots (≈ 1000 groups): 1.65 ms here vs 1.34 ms in hash_agg_kernel
     if (radix) {
-    } else if (n > 0 && capacity <= tile_max && ex.key_kind != KEY_PAIR && launch_hash_agg_tile(P, capacity, hints.groups.load(), key_bytes, stream)) {
+    } else if (n > 0 && !reused && capacity <= tile_max && ex.key_kind != KEY_PAIR && launch_hash_agg_tile(P, capacity, hints.groups.load(), key_bytes, stream)) {
     } else if (n > 0 && launch_hash_agg_stream(P, capacity, key_bytes, stream)) {
     } else {
       if (P.pred_kind == 0) launch_agg<0>(P, n, stream);
@@ -377,10 +427,18 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
     }
     ARK_CUDA(cudaGetLastError());
     ARK_CUDA(cudaMemcpyAsync(hctl.get(), ctl.get(), 16, cudaMemcpyDeviceToHost, stream));
+    ARK_CUDA(cudaMemcpyAsync((char*)hctl.get() + 280, (char*)ctl.get() + 280, 4, cudaMemcpyDeviceToHost, stream));
     ARK_CUDA(cudaStreamSynchronize(stream));
-    const unsigned int groups = *(unsigned int*)hctl.get();
+    const unsigned int claimed_now = *(unsigned int*)hctl.get();  // keys claimed by THIS launch
+    const unsigned long long keys_total = (reused ? ct.total_keys : 0) + claimed_now;
+    const unsigned int groups = (unsigned int)std::min<unsigned long long>(keys_total, 0xFFFFFFFFull);
     const int overflow = *(int32_t*)((char*)hctl.get() + 4);
     const int err = *(int32_t*)((char*)hctl.get() + 8);
+    const bool long_seen = *(int32_t*)((char*)hctl.get() + 280) != 0;
+    if (reused && (overflow || groups > P.max_groups)) {  // the dictionary filled up with keys of past batches: start over at this size
+      fresh_only = true;
+      continue;
+    }
     if (*(int32_t*)((char*)hctl.get() + 12)) {  // skewed keys overflowed a bucket's record array: same capacity, row kernel
       hash_agg_radix_note_skew();
       allow_radix = false;
@@ -393,14 +451,18 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
       continue;
     }
     if (err) fail(ARK_ERR_PROCESS, std::string("Collection query results error: ") + vm_error_text(err));
-    dg.n_groups = groups;
+    dg.n_groups = groups;  // upper bound when the table is reused (compact_groups counts this batch's groups)
     dg.capacity = capacity;
+    dg.total_keys = keys_total;
+    dg.cacheable = cache_now && !long_seen && keys_total * 10 <= capacity * 6;
     // next batch: the smallest power of two ≥ 2× the groups just seen (load ≤ 0.5), at least 2^12, so that
     // the table of config 3 (10^6 keys × 32-byte slots = 64 MB) stays inside the 126 MB L2
-    unsigned long long want = 1ull << 10;
-    while (want < 2ull * groups) want <<= 1;
-    hints.capacity.store(want);
-    hints.groups.store(groups);
+    if (!reused) {  // a reused dictionary keeps its size (keys_total counts keys of past batches too)
+      unsigned long long want = 1ull << 10;
+      while (want < 2ull * groups) want <<= 1;
+      hints.capacity.store(want);
+      hints.groups.store(groups);
+    }
     break;
   }
   if (!compact) return dg;
@@ -409,17 +471,29 @@ static DenseGroups hash_pass(const Plan& plan, const AggExec& ex, Batch& in, int
   return dg;
 }
 
+// After the call that used it: a table with self-contained keys goes back to its plan for the next batch.
+static void return_table(AggHints& hints, DenseGroups& dg) {
+  if (!dg.cacheable || !dg.table) return;
+  std::lock_guard<std::mutex> l(hints.cache_mu);
+  if (hints.cache.size() >= 4) return;
+  AggHints::CachedTable ct;
+  ct.table = dg.table; ct.capacity = dg.capacity; ct.total_keys = dg.total_keys; ct.n_acc = dg.n_acc;
+  hints.cache.push_back(std::move(ct));
+}
+static void return_table(const Plan& plan, DenseGroups& dg) { return_table(*plan.hints, dg); }
+
 static void compact_groups(DenseGroups& dg, const ColView& kc, int key_kind, int n_parts, BufferPtr ctl, BufferPtr hctl, cudaStream_t stream) {
   unsigned int* part_counts = (unsigned int*)((char*)ctl.get() + 16);
   unsigned int* part_cursor = (unsigned int*)((char*)ctl.get() + 16 + 128);
   ARK_CUDA(cudaMemsetAsync(part_counts, 0, 256, stream));
-  dg.slots = device_alloc((size_t)std::max<unsigned int>(dg.n_groups, 1) * 4);
+  const int need_count = dg.count_filter ? 1 : 0;
+  dg.slots = device_alloc((size_t)std::max<unsigned int>(dg.n_groups, 1) * 4);  // n_groups: exact, or an upper bound when the table is reused
   dg.part_rows.assign(n_parts, 0);
   const int sgrid = (int)std::min<unsigned long long>((dg.capacity + 255) / 256, 148ull * 8);
   if (n_parts > 1) {
     {
       KernelTimer t("agg_count_parts_kernel", stream);
-      agg_count_parts_kernel<<<sgrid, 256, 0, stream>>>((const uint8_t*)dg.table.get(), dg.stride, dg.capacity, kc, key_kind, n_parts, part_counts);
+      agg_count_parts_kernel<<<sgrid, 256, 0, stream>>>((const uint8_t*)dg.table.get(), dg.stride, dg.capacity, kc, key_kind, n_parts, part_counts, need_count);
     }
     ARK_CUDA(cudaMemcpyAsync((char*)hctl.get() + 16, part_counts, 128, cudaMemcpyDeviceToHost, stream));
     ARK_CUDA(cudaStreamSynchronize(stream));
@@ -427,14 +501,21 @@ static void compact_groups(DenseGroups& dg, const ColView& kc, int key_kind, int
     unsigned int* hcur = (unsigned int*)((char*)hctl.get() + 16 + 128);
     unsigned int run = 0;
     for (int p = 0; p < n_parts; ++p) { dg.part_rows[p] = hc[p]; hcur[p] = run; run += hc[p]; }
+    if (need_count) dg.n_groups = run;
     ARK_CUDA(cudaMemcpyAsync(part_cursor, hcur, 128, cudaMemcpyHostToDevice, stream));
-  } else {
-    dg.part_rows[0] = dg.n_groups;
   }
   if (dg.n_groups > 0) {
     KernelTimer t("agg_compact_kernel", stream);
     agg_compact_kernel<<<sgrid, 256, 0, stream>>>((const uint8_t*)dg.table.get(), dg.stride, dg.capacity, kc, key_kind, n_parts, part_cursor,
-                                                  (unsigned int*)dg.slots.get());
+                                                  (unsigned int*)dg.slots.get(), need_count);
+  }
+  if (n_parts == 1) {
+    if (need_count && dg.n_groups > 0) {  // this batch's group count = where the cursor stopped
+      ARK_CUDA(cudaMemcpyAsync((char*)hctl.get() + 16, part_cursor, 4, cudaMemcpyDeviceToHost, stream));
+      ARK_CUDA(cudaStreamSynchronize(stream));
+      dg.n_groups = *(unsigned int*)((char*)hctl.get() + 16);
+    }
+    dg.part_rows[0] = dg.n_groups;
   }
   ARK_CUDA(cudaGetLastError());
 }
@@ -655,6 +736,7 @@ Batch run_aggregate(const Plan& plan, Batch& in, cudaStream_t stream) {
   const Column* key_src2 = ex.key_kind == KEY_PAIR ? &in.cols[plan.used_cols[ex.key_slot2]] : nullptr;
   Batch out = project_groups(plan, ex, outs, dg, key_src, stream, key_src2);
   ARK_CUDA(cudaStreamSynchronize(stream));
+  return_table(plan, dg);
   return out;
 }
 
@@ -687,6 +769,7 @@ Batch run_partial_aggregate(const Plan& plan, Batch& in, int n_parts, std::vecto
     out.cols.push_back(c);
   }
   ARK_CUDA(cudaStreamSynchronize(stream));
+  return_table(plan, dg);
   return out;
 }
 
@@ -717,9 +800,10 @@ Batch run_final_aggregate(const Plan& plan, Batch& partial, cudaStream_t stream)
   mp.hints = plan.final_hints;  // the merge table's size carries over from batch to batch like the partial side's
   for (size_t i = 0; i < partial.cols.size(); ++i) mp.used_cols.push_back((int)i);
   if ((int)mp.used_cols.size() > MAX_COLS) fail(ARK_ERR_UNSUPPORTED, "too many accumulator columns");
-  DenseGroups dg = hash_pass(mp, mx, partial, 1, stream);
+  DenseGroups dg = hash_pass(mp, mx, partial, 1, stream, true, /*merge_mode=*/true);
   Batch out = project_groups(plan, mx, outs, dg, key_cols ? &partial.cols[0] : nullptr, stream, key_cols == 2 ? &partial.cols[1] : nullptr);
   ARK_CUDA(cudaStreamSynchronize(stream));
+  return_table(mp, dg);  // mp.hints is the plan's final_hints
   return out;
 }
 
@@ -730,9 +814,11 @@ void run_group_by_push(const Plan& plan, Batch& in, DistCtx& d, cudaStream_t str
   std::vector<AggOutput> outs;
   build_exec(plan, nullptr, ex, outs);  // accumulator layout from the schema alone: identical on every rank
   DenseGroups dg = hash_pass(plan, ex, in, 1, stream, /*compact=*/false);
-  launch_exchange_push((const uint8_t*)dg.table.get(), dg.capacity, (int)ex.accs.size(), ex.key_kind, d.peers, d.world, d.rank, d.step, d.region_bytes, stream);
+  launch_exchange_push((const uint8_t*)dg.table.get(), dg.capacity, (int)ex.accs.size(), ex.key_kind, d.peers, d.world, d.rank, d.step, d.region_bytes,
+                       dg.count_filter ? 1 : 0, stream);
   ARK_CUDA(cudaGetLastError());
-  ARK_CUDA(cudaStreamSynchronize(stream));  // the table is released when dg goes out of scope
+  ARK_CUDA(cudaStreamSynchronize(stream));
+  return_table(plan, dg);
 }
 
 // Merge phase: wait for every source's records, merge them into the final table, acknowledge, project the result.
@@ -760,19 +846,37 @@ bool run_group_by_merge(const Plan& plan, DistCtx& d, Batch& out, cudaStream_t s
   unsigned long long capacity = std::max<unsigned long long>(hints.capacity.load(), 1ull << 10);
   DenseGroups dg;
   dg.stride = table_bucket_stride((int)ex.accs.size());
+  dg.n_acc = (int)ex.accs.size();
   BufferPtr ctl = device_alloc(512), hctl = pinned_alloc(512);
-  bool poisoned = false;
+  bool poisoned = false, fresh_only = false;
+  static const bool cache_env = [] { const char* e = getenv("ARK_AGG_TABLE_CACHE"); return !e || atoi(e) != 0; }();
+  const bool cache_enabled = cache_env && mx.key_kind != KEY_NONE;  // a global aggregate's single group exists even with COUNT(*) = 0
   while (true) {
-    dg.table = device_alloc((size_t)table_bytes(capacity, (int)ex.accs.size()));
+    // the owner meets the same keys step after step: keep the merge table's keys, reset its accumulators (AggHints::CachedTable)
+    AggHints::CachedTable ct;
+    bool reused = false;
+    if (cache_enabled && !fresh_only) {
+      std::lock_guard<std::mutex> l(hints.cache_mu);
+      for (size_t i = 0; i < hints.cache.size(); ++i)
+        if (hints.cache[i].capacity == capacity && hints.cache[i].n_acc == dg.n_acc) { ct = hints.cache[i]; hints.cache.erase(hints.cache.begin() + i); reused = true; break; }
+      if (!reused) hints.cache.clear();
+    }
+    dg.table = reused ? ct.table : device_alloc((size_t)table_bytes(capacity, (int)ex.accs.size()));
     ARK_CUDA(cudaMemsetAsync(ctl.get(), 0, 512, stream));
     {
       AccParam ap[AGG_MAX_ACC];
       memset(ap, 0, sizeof ap);
       for (size_t a = 0; a < mx.accs.size(); ++a) { ap[a].kind = mx.accs[a].kind; ap[a].acc_index = (int)a; }
-      KernelTimer t("agg_init_kernel", stream);
-      const int grid = (int)std::min<unsigned long long>((capacity + 255) / 256, 148ull * 8);
-      agg_init_kernel<<<grid, 256, 0, stream>>>((uint8_t*)dg.table.get(), capacity, dg.stride, (int)mx.accs.size(), ap[0], ap[1], ap[2], ap[3], ap[4],
-                                                ap[5], ap[6], ap[7]);
+      KernelTimer t(reused ? "agg_reset_acc_kernel" : "agg_init_kernel", stream);
+      if (reused) {
+        const int grid = (int)std::min<unsigned long long>((capacity * mx.accs.size() + 255) / 256, 148ull * 8);
+        agg_reset_acc_kernel<<<grid, 256, 0, stream>>>((uint8_t*)dg.table.get(), capacity, dg.stride, (int)mx.accs.size(), ap[0], ap[1], ap[2], ap[3], ap[4],
+                                                       ap[5], ap[6], ap[7]);
+      } else {
+        const int grid = (int)std::min<unsigned long long>((capacity + 255) / 256, 148ull * 8);
+        agg_init_kernel<<<grid, 256, 0, stream>>>((uint8_t*)dg.table.get(), capacity, dg.stride, (int)mx.accs.size(), ap[0], ap[1], ap[2], ap[3], ap[4],
+                                                  ap[5], ap[6], ap[7]);
+      }
     }
     // ctl: [group_count u32 | overflow i32 | status i32 | pad | total u64 @ 272]
     launch_exchange_merge((uint8_t*)dg.table.get(), capacity, (int)mx.accs.size(), kinds, d.comm, d.world, d.rank, d.step, d.region_bytes,
@@ -782,7 +886,8 @@ bool run_group_by_merge(const Plan& plan, DistCtx& d, Batch& out, cudaStream_t s
     ARK_CUDA(cudaMemcpyAsync(hctl.get(), ctl.get(), 16, cudaMemcpyDeviceToHost, stream));
     ARK_CUDA(cudaMemcpyAsync((char*)hctl.get() + 16, (char*)ctl.get() + 272, 8, cudaMemcpyDeviceToHost, stream));
     ARK_CUDA(cudaStreamSynchronize(stream));
-    const unsigned int groups = *(unsigned int*)hctl.get();
+    const unsigned int claimed_now = *(unsigned int*)hctl.get();
+    const unsigned long long keys_total = (reused ? ct.total_keys : 0) + claimed_now;
     const int overflow = *(int32_t*)((char*)hctl.get() + 4);
     const int status = *(int32_t*)((char*)hctl.get() + 8);
     const unsigned long long total = *(unsigned long long*)((char*)hctl.get() + 16);
@@ -793,19 +898,25 @@ bool run_group_by_merge(const Plan& plan, DistCtx& d, Batch& out, cudaStream_t s
     }
     if (status & 1) { poisoned = true; break; }
     const unsigned long long max_groups = capacity - capacity / 4;
-    if (overflow || groups > max_groups) {  // the records stay in the receive region until the ack: merge again into a larger table
+    if (overflow || keys_total > max_groups) {  // the records stay in the receive region until the ack: merge again
+      if (reused) { fresh_only = true; continue; }  // the dictionary filled up with keys of past steps: same size, fresh table
       if (capacity >= (1ull << 31)) fail(ARK_ERR_PROCESS, "Collection query results error: group-by hash table exceeded 2^31 slots");
       capacity = std::max(capacity * 4, (unsigned long long)1 << 10);
       while (capacity < 2 * total) capacity <<= 1;
       continue;
     }
-    dg.n_groups = groups;
+    dg.n_groups = (unsigned int)keys_total;  // exact for a fresh table, an upper bound for a reused one (compact_groups counts)
     dg.capacity = capacity;
-    d.last_recv_records = total; d.last_groups = groups;
-    unsigned long long want = 1ull << 10;
-    while (want < 2ull * groups) want <<= 1;
-    hints.capacity.store(want);
-    hints.groups.store(groups);
+    dg.count_filter = reused;
+    dg.total_keys = keys_total;
+    dg.cacheable = cache_enabled && keys_total * 10 <= capacity * 6;
+    d.last_recv_records = total; d.last_groups = keys_total;
+    if (!reused) {
+      unsigned long long want = 1ull << 10;
+      while (want < 2ull * keys_total) want <<= 1;
+      hints.capacity.store(want);
+      hints.groups.store((unsigned int)keys_total);
+    }
     break;
   }
   launch_exchange_ack(d.peers, d.world, d.rank, d.step, stream);
@@ -839,6 +950,8 @@ bool run_group_by_merge(const Plan& plan, DistCtx& d, Batch& out, cudaStream_t s
     }
   }
   ARK_CUDA(cudaStreamSynchronize(stream));
+  d.last_groups = G;
+  return_table(hints, dg);
   return true;
 }
 

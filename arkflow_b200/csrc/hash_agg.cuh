@@ -89,6 +89,7 @@ struct AggParams {
   unsigned int max_groups;   // load-factor limit; beyond it the kernel raises `overflow`
   int32_t* overflow;
   int32_t* error;
+  int32_t* long_seen;        // set when a key longer than 12 bytes (stored by row reference) was met: the table cannot outlive the batch
 };
 
 }  // namespace ark

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(HS_THREADS) hash_agg_stream_kernel(const __gri
 
   unsigned int claimed = 0;
   unsigned ph = 0;
-  int32_t err_overflow = 0;
+  int32_t err_overflow = 0, long_flag = 0;
   const long long pred_c = P.sp_is_f64 ? f64_total_key(P.sp_const) : (long long)P.sp_const;
   for (int it = 0; tile < n_tiles; ++it, tile += (int)gridDim.x) {
     const int st = it & 1;
@@ -197,11 +197,11 @@ __global__ void __launch_bounds__(HS_THREADS) hash_agg_stream_kernel(const __gri
         const int64_t row = row0 + lr0 + j;
         unsigned h32;
         if (!col_valid(kc, row)) { mine[j].lo = 0; mine[j].hi = (unsigned long long)KEYTAG_NULL << 32; h32 = hash32_key16(mine[j]); }
-        else if (staged) make_key_smem(in_bytes + (off[j] - base), off[j + 1] - off[j], row, &mine[j], &h32);
+        else if (staged) { make_key_smem(in_bytes + (off[j] - base), off[j + 1] - off[j], row, &mine[j], &h32); if (off[j + 1] - off[j] > 12) long_flag = 1; }
         else {
           int llen = 0;
           const uint8_t* lp = make_key_raw(KEY_BYTES, kc, row, &mine[j], &llen);
-          if (lp) { const unsigned long long h = hash_bytes(lp, llen); h32 = (unsigned)(h >> 32) ^ (unsigned)h; }
+          if (lp) { const unsigned long long h = hash_bytes(lp, llen); h32 = (unsigned)(h >> 32) ^ (unsigned)h; long_flag = 1; }
           else h32 = hash32_key16(mine[j]);
         }
         home[j] = (unsigned)((h32 * 0x9E3779B1u) & bmask);
@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(HS_THREADS) hash_agg_stream_kernel(const __gri
     }
   }
   if (err_overflow) atomicExch(P.overflow, 1);
+  if (long_flag) *P.long_seen = 1;
   claimed = (unsigned int)__reduce_add_sync(0xffffffffu, claimed);
   if (lane == 0 && claimed) atomicAdd(P.group_count, claimed);
 }

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -81,6 +82,17 @@ struct AggHints {
   std::atomic<unsigned long long> capacity{1ull << 16};  // table slots to start with
   std::atomic<unsigned int> groups{0};                   // groups of the previous batch (0 = none yet)
   std::atomic<double> avg_key_len{-1.0};                 // bytes per var-len key of the previous batch (sizes the key staging)
+  // Key dictionaries kept from batch to batch.  A stream asks the same GROUP BY of batch after batch over largely the
+  // same keys (config 3: 10^10 rows, 10^6 sensors): the table's KEYS stay, only the accumulators are reset, so a batch
+  // finds its groups with a plain load instead of claiming 10^6 slots with 128-bit CAS again.  A group belongs to a
+  // batch's result iff its COUNT(*) accumulator is non-zero.  One table per concurrent caller (thread_num workers).
+  struct CachedTable {
+    BufferPtr table;
+    unsigned long long capacity = 0, total_keys = 0;
+    int n_acc = 0;
+  };
+  std::mutex cache_mu;
+  std::vector<CachedTable> cache;
 };
 
 struct Plan {

@@ -350,3 +350,34 @@ def test_two_group_by_keys(gpu):
 def test_two_keys_high_cardinality(gpu):
     rb = synth_batch(400_000, key_space=50_000)
     check_agg(rb, "SELECT sensor, value, COUNT(*), SUM(timestamp) FROM flow GROUP BY sensor, value", ["sensor", "value"])
+
+
+def test_key_dictionary_is_reused_across_batches(gpu):
+    """The processor keeps a plan's table (its KEYS) from batch to batch (AggHints::CachedTable) and resets only the
+    accumulators: keys of an earlier batch that are absent from the current one must not appear, new keys must, every
+    aggregate must be the batch's own — for string and integer keys, MIN/MAX identities included."""
+    for query, keys in (("SELECT sensor, SUM(value), COUNT(*), MIN(value), MAX(timestamp) FROM flow GROUP BY sensor", ["sensor"]),
+                        ("SELECT value, COUNT(*), AVG(timestamp) FROM flow WHERE timestamp > 0 GROUP BY value", ["value"])):
+        p = SqlProcessor({"query": query})
+        rng = np.random.default_rng(9)
+        for step in range(6):
+            n = 60_000
+            # key ranges drift: [0,3000) → [1500,4500) → … so that old keys disappear and new ones arrive
+            lo = 1500 * (step % 4)
+            k = rng.integers(lo, lo + 3000, n)
+            rb = pa.record_batch({"timestamp": pa.array(rng.integers(1, 10**9, n), pa.int64()),
+                                  "value": pa.array(k if "GROUP BY value" in query else rng.integers(-50, 50, n), pa.int64()),
+                                  "sensor": pa.array(["s%05d" % x for x in k])})
+            want = sql_process(rb, query)
+            for device in (False, True):
+                if device:
+                    got = p.process_device(DeviceBatch.from_arrow(rb)).to_arrow()
+                else:
+                    got = p.process(MessageBatch.new_arrow(rb)).batches[0].record_batch
+                assert got.num_rows == want.num_rows, (step, got.num_rows, want.num_rows)
+                gd, wd = rows_as_dict(got, keys), rows_as_dict(want, keys)
+                assert gd.keys() == wd.keys()
+                for kk in wd:
+                    for nm in want.schema.names:
+                        gv, wv = gd[kk][nm], wd[kk][nm]
+                        assert gv == wv or (isinstance(wv, float) and abs(gv - wv) <= 1e-9 * abs(wv)), (step, kk, nm, gv, wv)
