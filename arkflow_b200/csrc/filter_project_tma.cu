@@ -58,6 +58,7 @@ struct TmaParams {
   unsigned int* ticket;
   long long* totals;
   int32_t debug;                            // measurement knob (ARK_FP_DEBUG): bit 0 = skip the look-back (results are garbage)
+  int32_t lb_windows;                       // tile kernel: 32-tile windows requested per look-back round (≤ 8)
 };
 
 constexpr unsigned long long DESC_AGG = 1ull << 62;
@@ -93,9 +94,8 @@ constexpr int LB_WINDOWS = 2;  // 2 × 32 predecessor tiles fetched per look-bac
 // aggregate is a pure function of the input, so helper and owner can only ever write the same value; the owner still
 // publishes its inclusive prefix when it gets to run.  The fast path never executes this (`ARK_FP_DEBUG=4` forces it:
 // tests/test_sql_filter_gpu.py).
-template <bool VARLEN>
+template <bool VARLEN, int TT>
 __device__ __forceinline__ void help_publish_aggregate(const TmaParams& P, int t, int lane) {
-  constexpr int TT = 1024;
   const int64_t row0 = (int64_t)t * TT;
   const int rows = (int)((P.n_rows - row0) < TT ? (P.n_rows - row0) : TT);
   int cnt = 0, bytes = 0;
@@ -116,32 +116,40 @@ __device__ __forceinline__ void help_publish_aggregate(const TmaParams& P, int t
 // at ~85 tiles/µs a 32-wide round with shuffle reductions (~0.4 µs) is exactly the limit, so the
 // round is kept short — one volatile load per window, REDUX (`__reduce_add_sync`) instead of shuffle
 // trees, the prefix tile's sums fetched with one shuffle — and two windows are in flight per round.
-template <bool VARLEN>
+// HELP = false (the r1 / pipe kernels, kept for A/B runs): plain spinning, as in round 1.
+// WINDOWS: compile-time upper bound of the windows per round; the tile kernel picks P.lb_windows ≤ WINDOWS at run time.
+template <bool VARLEN, int TT = 1024, bool HELP = true, int WINDOWS = LB_WINDOWS>
 __device__ void lookback_resolve(const TmaParams& P, int tile, long long agg_cnt, long long agg_bytes, int lane,
                                  long long* ex_cnt, long long* ex_bytes) {
   unsigned long long* const desc = P.desc;
   const int stride = P.desc_stride;
   const int spin_limit = (P.debug & 4) ? 2 : 4096;
+  const int nw = HELP ? (P.lb_windows < WINDOWS ? P.lb_windows : WINDOWS) : WINDOWS;
   long long run_c = 0, run_b = 0;
   if (tile > 0) {
     int look = tile - 1;
     bool done = false;
     while (!done) {
-      const int idx0 = look - lane, idx1 = look - 32 - lane;
-      unsigned long long d0 = idx0 >= 0 ? ld_volatile_u64(desc + (size_t)idx0 * stride) : DESC_PREFIX;  // virtual tile -1: prefix 0
-      unsigned long long d1 = idx1 >= 0 ? ld_volatile_u64(desc + (size_t)idx1 * stride) : DESC_PREFIX;
+      // WINDOWS × 32 predecessor descriptors are requested before any is inspected: one L2 round trip per round
+      unsigned long long dwin[WINDOWS];
 #pragma unroll
-      for (int w = 0; w < LB_WINDOWS; ++w) {
-        if (!done) {  // warp-uniform
-          const int idx = w == 0 ? idx0 : idx1;
-          unsigned long long dw = w == 0 ? d0 : d1;
+      for (int w = 0; w < WINDOWS; ++w) {
+        const int idxw = look - 32 * w - lane;
+        dwin[w] = DESC_PREFIX;  // virtual tile -1: prefix 0
+        if (w < nw && idxw >= 0) dwin[w] = ld_volatile_u64(desc + (size_t)idxw * stride);
+      }
+#pragma unroll
+      for (int w = 0; w < WINDOWS; ++w) {
+        if (!done && w < nw) {  // warp-uniform
+          const int idx = look - 32 * w - lane;
+          unsigned long long dw = dwin[w];
           int spins = 0;
           while (true) {  // a predecessor has not published yet
             const unsigned pending = __ballot_sync(0xffffffffu, (dw >> 62) == 0);
             if (!pending) break;
-            if (++spins > spin_limit) {  // not making progress: do the nearest missing tile's counting ourselves
+            if (HELP && ++spins > spin_limit) {  // not making progress: do the nearest missing tile's counting ourselves
               const int helped = __shfl_sync(0xffffffffu, idx, __ffs(pending) - 1);
-              help_publish_aggregate<VARLEN>(P, helped, lane);
+              help_publish_aggregate<VARLEN, TT>(P, helped, lane);
               spins = 0;
             }
             if ((dw >> 62) == 0) dw = ld_volatile_u64(desc + (size_t)idx * stride);
@@ -160,7 +168,7 @@ __device__ void lookback_resolve(const TmaParams& P, int tile, long long agg_cnt
           }
         }
       }
-      look -= LB_WINDOWS * 32;
+      look -= nw * 32;
     }
     if (lane == 0) st_volatile_u64(desc + (size_t)tile * stride, desc_pack(DESC_PREFIX, run_c + agg_cnt, run_b + agg_bytes));
   }
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? ARK_FP_MINBLOCKS : 3
   // ---- F: decoupled look-back (warp 0) ----
   if (warp == 0) {
     long long ex0, ex1;
-    lookback_resolve<VARLEN>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
+    lookback_resolve<VARLEN, 1024, false>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
     if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
   }
   __syncthreads();
@@ -611,7 +619,7 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
     if (warp == 0) {
       long long ex0, ex1;
       if (P.debug & 1) { ex0 = (long long)tile * (TT / 2); ex1 = ex0 * 12; }
-      else lookback_resolve<VARLEN>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
+      else lookback_resolve<VARLEN, 1024, false>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
       if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
     }
     // ---- E: compact the strings in shared memory at tile-local positions ----
@@ -687,11 +695,12 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
 // nothing but its own loads, many short-lived CTAs per SM hide each other's look-back, and the ticket — claimed by
 // the CTA when it STARTS — keeps the guarantee that a tile is only ever owned by a running CTA.
 // ================================================================================================
-template <int NF, bool VARLEN, int MINB>
-__global__ void __launch_bounds__(288, MINB) filter_project_tile_kernel(const __grid_constant__ TmaParams P) {
+template <int NF, bool VARLEN, int MINB, int DT>
+__global__ void __launch_bounds__(DT + 32, MINB) filter_project_tile_kernel(const __grid_constant__ TmaParams P) {
   // warps 0..7: the tile's rows; warp 8: producer (tile id, bulk copy) and look-back — nothing but its own few values is
   // live there, so the (rare) call into help_publish_aggregate costs the data warps no registers and no spills
-  constexpr int T_THREADS = 256, TT = T_THREADS * 4, T_WARPS = T_THREADS / 32, LB_WARP = T_WARPS;
+  // DT data threads: 256 (1024-row tiles) or 512 (2048-row tiles: half the descriptors on the look-back chain)
+  constexpr int T_THREADS = DT, TT = T_THREADS * 4, T_WARPS = T_THREADS / 32, LB_WARP = T_WARPS;
   extern __shared__ __align__(16) uint8_t smem[];   // [in_bytes][out_bytes], each str_cap + 32
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_tile;
@@ -739,7 +748,7 @@ __global__ void __launch_bounds__(288, MINB) filter_project_tile_kernel(const __
     if (lane == 0) st_volatile_u64(P.desc + (size_t)tile * P.desc_stride, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
     long long ex0, ex1;
     if (P.debug & 1) { ex0 = (long long)tile * (TT / 2); ex1 = ex0 * 12; }
-    else lookback_resolve<VARLEN>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
+    else lookback_resolve<VARLEN, TT, true, 8>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
     if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
     __syncthreads();   // (2)
     return;
@@ -937,6 +946,8 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
   P.desc = desc; P.ticket = ticket; P.totals = totals;
   static const int debug = [] { const char* e = getenv("ARK_FP_DEBUG"); return e ? atoi(e) : 0; }();
   P.debug = debug;
+  static const int lbw = [] { const char* e = getenv("ARK_FP_LB_WINDOWS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 8 ? v : 4; }();
+  P.lb_windows = lbw;
   // string staging sized from the batch's average string length (+25 %), 2 KB granules, 4..24 KB
   int cap = 0;
   if (P.has_varlen) {
@@ -956,12 +967,17 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
     static const bool use_ticket = [] { const char* e = getenv("ARK_FP_TICKET"); return e && atoi(e) != 0; }();
     if (!use_ticket) P.ticket = nullptr;
     const size_t smem = v ? 2 * (size_t)(cap + 32) : 0;
-    static const int minb = [] { const char* e = getenv("ARK_FP_MINB"); const int x = e ? atoi(e) : 5; return x >= 4 && x <= 6 ? x : 5; }();
-#define ARK_TILE_FN(NF, V) (minb == 4 ? (const void*)filter_project_tile_kernel<NF, V, 4> : minb == 6 ? (const void*)filter_project_tile_kernel<NF, V, 6> : (const void*)filter_project_tile_kernel<NF, V, 5>)
+    // data threads per CTA: g_fp_threads (ARK_FP_THREADS = 256 | 512); CTAs per SM the kernel is compiled for: ARK_FP_MINB
+    static const int minb = [] { const char* e = getenv("ARK_FP_MINB"); const int x = e ? atoi(e) : 0; return x; }();
+    const int dt = g_fp_threads;
+    const int mb = dt == 512 ? (minb == 2 ? 2 : 3) : (minb >= 4 && minb <= 6 ? minb : 5);
+#define ARK_TILE_FN(NF, V) (dt == 512 ? (mb == 2 ? (const void*)filter_project_tile_kernel<NF, V, 2, 512> : (const void*)filter_project_tile_kernel<NF, V, 3, 512>) \
+                            : (mb == 4 ? (const void*)filter_project_tile_kernel<NF, V, 4, 256> : mb == 6 ? (const void*)filter_project_tile_kernel<NF, V, 6, 256> \
+                                                                                                    : (const void*)filter_project_tile_kernel<NF, V, 5, 256>))
     static bool configured = false;
     if (!configured) {
       for (const void* f : {ARK_TILE_FN(0, true), ARK_TILE_FN(1, true), ARK_TILE_FN(2, true)})
-        ARK_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (48 * 1024 + 32)));
+        ARK_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * 24 * 1024 + 32)));
       configured = true;
     }
     const void* fn = nullptr;
@@ -974,7 +990,7 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
 #undef ARK_TILE_FN
     KernelTimer t("filter_project_tma_kernel", stream);
     void* args[] = {(void*)&P};
-    ARK_CUDA(cudaLaunchKernel(fn, dim3(P.n_tiles), dim3(288), args, smem, stream));
+    ARK_CUDA(cudaLaunchKernel(fn, dim3(P.n_tiles), dim3(dt + 32), args, smem, stream));
     return true;
   }
   if (impl == 0 && g_fp_threads == 256 && ticket != nullptr) {

@@ -119,6 +119,12 @@ __global__ void take_matched_kernel(const unsigned int* idx, long long n, uint8_
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out_bytes[i] = idx[i] != NO_ROW;
 }
+__global__ void sum_lengths_kernel(const int32_t* lens, long long n, unsigned long long* total) {
+  unsigned long long acc = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc += (unsigned long long)lens[i];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
+}
 __global__ void take_lengths_kernel(const int32_t* offsets, const unsigned int* idx, long long n, int32_t* lens) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { const unsigned int r = idx[i]; lens[i] = r == NO_ROW ? 0 : offsets[r + 1] - offsets[r]; }
@@ -259,6 +265,7 @@ unsigned grid_for(int64_t n, int threads = 256) { return (unsigned)std::max<int6
 // out[i] = column[idx[i]] for i < n  (idx on the device).  may_miss: idx may hold NO_ROW (outer join without a match):
 // such rows come out NULL, so the column always gets a validity bitmap.
 Column take_column(const Column& src, const unsigned int* idx, int64_t n, const std::string& name, cudaStream_t stream, bool may_miss) {
+  if (n >= (1ll << 31) - 1) fail(ARK_ERR_UNSUPPORTED, "gather of 2^31 or more rows in one batch");
   Column c;
   c.field = src.field; c.field.name = name; c.length = n;
   const unsigned g = (unsigned)std::max<int64_t>(1, ceil_div(n, 256));
@@ -280,6 +287,18 @@ Column take_column(const Column& src, const unsigned int* idx, int64_t n, const 
       BufferPtr lens = device_alloc((size_t)(n + 1) * 4), offs = device_alloc((size_t)(n + 1) * 4);
       ARK_CUDA(cudaMemsetAsync(lens.get(), 0, (size_t)(n + 1) * 4, stream));
       if (n) { KernelTimer t("take_lengths_kernel", stream); take_lengths_kernel<<<g, 256, 0, stream>>>(src.offsets, idx, n, (int32_t*)lens.get()); }
+      {
+        // the int32 scan below wraps silently past 2 GiB: when the gathered bytes could get near that, add them up in 64 bits first
+        const double avg_len = src.length > 0 && src.data_bytes >= 0 ? (double)src.data_bytes / (double)src.length : 64.0;
+        if (avg_len * (double)n > 1.0e9) {
+          BufferPtr sum = device_alloc(16), hs = pinned_alloc(16);
+          ARK_CUDA(cudaMemsetAsync(sum.get(), 0, 16, stream));
+          { KernelTimer t("sum_lengths_kernel", stream); sum_lengths_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 148 * 16), 256, 0, stream>>>((const int32_t*)lens.get(), n, (unsigned long long*)sum.get()); }
+          ARK_CUDA(cudaMemcpyAsync(hs.get(), sum.get(), 8, cudaMemcpyDeviceToHost, stream));
+          ARK_CUDA(cudaStreamSynchronize(stream));
+          if (*(unsigned long long*)hs.get() > 2147483647ull) fail(ARK_ERR_PROCESS, "Collection query results error: Arrow error: offset overflow, result column exceeds 2 GiB");
+        }
+      }
       size_t tb = 0;
       cub::DeviceScan::ExclusiveSum(nullptr, tb, (int32_t*)lens.get(), (int32_t*)offs.get(), (int)(n + 1), stream);
       BufferPtr tmp = device_alloc(tb + 16);
@@ -317,7 +336,8 @@ Column take_column(const Column& src, const unsigned int* idx, int64_t n, const 
 }
 
 Batch run_join(const Plan& plan, Batch& left, Batch& right, cudaStream_t stream) {
-  if (left.num_rows >= (1ll << 32) - 1 || right.num_rows >= (1ll << 32) - 1) fail(ARK_ERR_UNSUPPORTED, "join input with 2^32 or more rows");
+  // row counts travel through cub scans with 32-bit item counts and through 32-bit row indices
+  if (left.num_rows >= (1ll << 31) - 1 || right.num_rows >= (1ll << 31) - 1) fail(ARK_ERR_UNSUPPORTED, "join input with 2^31 or more rows in one batch");
   Column& lk = left.cols[plan.left_key];
   Column& rk = right.cols[plan.right_key];
   const int key_kind = key_kind_of(lk.field.type);
@@ -386,7 +406,7 @@ Batch hash_partition(Batch& in, const std::string& key_column, int n_parts, std:
   const int ki = in.find(key_column);
   if (ki < 0) fail(ARK_ERR_PROCESS, "Schema error: No field named " + key_column + ".");
   const int64_t n = in.num_rows;
-  if (n >= (1ll << 32) - 1) fail(ARK_ERR_UNSUPPORTED, "partition input with 2^32 or more rows");
+  if (n >= (1ll << 31) - 1) fail(ARK_ERR_UNSUPPORTED, "partition input with 2^31 or more rows in one batch");
   const int key_kind = key_kind_of(in.cols[ki].field.type);
   BufferPtr part = device_alloc((size_t)std::max<int64_t>(n, 1)), idx = device_alloc((size_t)std::max<int64_t>(n, 1) * 4);
   BufferPtr ctl = device_alloc(256), hctl = pinned_alloc(256);

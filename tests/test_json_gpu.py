@@ -123,13 +123,13 @@ def test_nested_lists_and_structs_vs_oracle(gpu, monkeypatch):
                "ratios": [float(x) / 4 for x in rng.integers(0, 99, int(rng.integers(1, 3)))],
                "pos": {"x": float(i) / 8, "y": int(rng.integers(0, 100)), "label": "p\"%d" % i, "ok": bool(i & 1)},
                "flags": [bool(x) for x in rng.integers(0, 2, 2)]}
-        if i % 7 == 0:
+        if i % 7 == 3:
             rec["tags"] = None
-        if i % 11 == 0:
+        if i % 11 == 5:
             del rec["pos"]
-        if i % 13 == 0:
+        if i % 13 == 6:
             rec["pos"] = {"y": "17", "extra": [1, {"deep": 2}]}  # missing children → NULL, quoted number, ignored key
-        if i % 17 == 0:
+        if i % 17 == 8:
             rec["nums"] = [1, None, "3"]
         if i == 0:
             rec["ratios"] = [1, 2.5]  # Int64 + Float64 in the first record → List<Float64>
