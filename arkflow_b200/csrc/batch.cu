@@ -286,7 +286,7 @@ struct StagePool {
 int stage_threads() {
   static const int n = [] {
     const char* e = getenv("ARK_STAGE_THREADS");
-    int v = e ? atoi(e) : 6;
+    int v = e ? atoi(e) : 8;
     return std::max(0, std::min(v, 32));
   }();
   return n;
@@ -296,10 +296,11 @@ StagePool& stage_pool() {
   return *p;
 }
 
-// chunk size: every chunk costs three driver calls (copy, event record, event wait) that serialise across threads
-// (~20 µs per chunk measured: 2 MB chunks added 4 ms to a 400 MB step); 8 MB keeps that below 1 ms
+// chunk size (ARK_STAGE_CHUNK_MB) and thread count (ARK_STAGE_THREADS) made no measurable difference between 2-16 MB and
+// 4-16 threads on the B200 hosts (profiles/r2_e2e_staging.txt): the end-to-end rate with pageable inputs stayed at
+// 0.6-0.77 of the pinned one, run-to-run noise included
 size_t stage_chunk() {
-  static const size_t v = [] { const char* e = getenv("ARK_STAGE_CHUNK_MB"); const int mb = e ? atoi(e) : 8; return (size_t)std::max(1, std::min(mb, 64)) << 20; }();
+  static const size_t v = [] { const char* e = getenv("ARK_STAGE_CHUNK_MB"); const int mb = e ? atoi(e) : 4; return (size_t)std::max(1, std::min(mb, 64)) << 20; }();
   return v;
 }
 constexpr size_t STAGE_MIN = 8u << 20;  // smaller sources are not worth the hand-off

@@ -695,8 +695,10 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
 // nothing but its own loads, many short-lived CTAs per SM hide each other's look-back, and the ticket — claimed by
 // the CTA when it STARTS — keeps the guarantee that a tile is only ever owned by a running CTA.
 // ================================================================================================
-template <int NF, bool VARLEN, int MINB, int DT>
-__global__ void __launch_bounds__(DT + 32, MINB) filter_project_tile_kernel(const __grid_constant__ TmaParams P) {
+// MAXR: register cap (__maxnreg__): CTAs per SM follow from it — ptxas rounds a 288- / 544-thread CTA up when it derives
+// the cap from __launch_bounds__'s minBlocks (544 threads, 3 blocks → 32 registers and spills instead of the 40 that fit)
+template <int NF, bool VARLEN, int MAXR, int DT>
+__global__ void __launch_bounds__(DT + 32) __maxnreg__(MAXR) filter_project_tile_kernel(const __grid_constant__ TmaParams P) {
   // warps 0..7: the tile's rows; warp 8: producer (tile id, bulk copy) and look-back — nothing but its own few values is
   // live there, so the (rare) call into help_publish_aggregate costs the data warps no registers and no spills
   // DT data threads: 256 (1024-row tiles) or 512 (2048-row tiles: half the descriptors on the look-back chain)
@@ -748,7 +750,7 @@ __global__ void __launch_bounds__(DT + 32, MINB) filter_project_tile_kernel(cons
     if (lane == 0) st_volatile_u64(P.desc + (size_t)tile * P.desc_stride, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
     long long ex0, ex1;
     if (P.debug & 1) { ex0 = (long long)tile * (TT / 2); ex1 = ex0 * 12; }
-    else lookback_resolve<VARLEN, TT, true, 8>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
+    else lookback_resolve<VARLEN, TT, true, 2>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
     if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
     __syncthreads();   // (2)
     return;
@@ -967,13 +969,12 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
     static const bool use_ticket = [] { const char* e = getenv("ARK_FP_TICKET"); return e && atoi(e) != 0; }();
     if (!use_ticket) P.ticket = nullptr;
     const size_t smem = v ? 2 * (size_t)(cap + 32) : 0;
-    // data threads per CTA: g_fp_threads (ARK_FP_THREADS = 256 | 512); CTAs per SM the kernel is compiled for: ARK_FP_MINB
-    static const int minb = [] { const char* e = getenv("ARK_FP_MINB"); const int x = e ? atoi(e) : 0; return x; }();
+    // data threads per CTA: g_fp_threads (ARK_FP_THREADS = 256 | 512); register cap: ARK_FP_MAXR (40 | 48 | 56)
+    static const int maxr = [] { const char* e = getenv("ARK_FP_MAXR"); const int x = e ? atoi(e) : 40; return x == 48 || x == 56 ? x : 40; }();
     const int dt = g_fp_threads;
-    const int mb = dt == 512 ? (minb == 2 ? 2 : 3) : (minb >= 4 && minb <= 6 ? minb : 5);
-#define ARK_TILE_FN(NF, V) (dt == 512 ? (mb == 2 ? (const void*)filter_project_tile_kernel<NF, V, 2, 512> : (const void*)filter_project_tile_kernel<NF, V, 3, 512>) \
-                            : (mb == 4 ? (const void*)filter_project_tile_kernel<NF, V, 4, 256> : mb == 6 ? (const void*)filter_project_tile_kernel<NF, V, 6, 256> \
-                                                                                                    : (const void*)filter_project_tile_kernel<NF, V, 5, 256>))
+#define ARK_TILE_R(NF, V, D) (maxr == 56 ? (const void*)filter_project_tile_kernel<NF, V, 56, D> : maxr == 48 ? (const void*)filter_project_tile_kernel<NF, V, 48, D> \
+                                                                                                     : (const void*)filter_project_tile_kernel<NF, V, 40, D>)
+#define ARK_TILE_FN(NF, V) (dt == 512 ? ARK_TILE_R(NF, V, 512) : ARK_TILE_R(NF, V, 256))
     static bool configured = false;
     if (!configured) {
       for (const void* f : {ARK_TILE_FN(0, true), ARK_TILE_FN(1, true), ARK_TILE_FN(2, true)})
@@ -988,6 +989,7 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
     else if (n_fixed_out == 2) fn = ARK_TILE_FN(2, false);
     else return false;
 #undef ARK_TILE_FN
+#undef ARK_TILE_R
     KernelTimer t("filter_project_tma_kernel", stream);
     void* args[] = {(void*)&P};
     ARK_CUDA(cudaLaunchKernel(fn, dim3(P.n_tiles), dim3(dt + 32), args, smem, stream));
