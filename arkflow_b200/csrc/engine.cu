@@ -110,6 +110,7 @@ const char* vm_error_text(int e) {
 int filter_project_tma_tile_rows();
 int filter_project_tma_max_fixed_out();
 int filter_project_tma_desc_stride();
+size_t filter_project_tma_desc_words(int64_t n_tiles);
 void filter_project_tma_note_avg_len(double avg);
 bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_out, const void* const* fixed_in, void* const* fixed_out,
                                const int32_t* offsets_in, const uint8_t* data_in, int64_t data_bytes, int32_t* offsets_out, uint8_t* data_out,
@@ -145,7 +146,7 @@ static bool try_fast_filter(const Plan& plan, Batch& in, Batch& out, cudaStream_
   }
   const Column* vs = varlen_out >= 0 ? &src_col(plan.outputs[varlen_out].src.slot) : nullptr;
   if (vs) { obuf = device_alloc((size_t)(n + 1) * 4 + 16); dbuf = device_alloc((size_t)std::max<int64_t>(varlen_bytes_bound(*vs), 0) + 32); }
-  const size_t desc_bytes = (size_t)n_tiles * 8 * (size_t)filter_project_tma_desc_stride();
+  const size_t desc_bytes = filter_project_tma_desc_words(n_tiles) * 8;
   const size_t scratch_bytes = round_up((int64_t)desc_bytes + 64 + FP_CHANNELS * 8, 256);
   BufferPtr scratch = device_alloc(scratch_bytes);
   ARK_CUDA(cudaMemsetAsync(scratch.get(), 0, scratch_bytes, stream));

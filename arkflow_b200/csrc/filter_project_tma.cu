@@ -59,6 +59,8 @@ struct TmaParams {
   long long* totals;
   int32_t debug;                            // measurement knob (ARK_FP_DEBUG): bit 0 = skip the look-back (results are garbage)
   int32_t lb_windows;                       // tile kernel: 32-tile windows requested per look-back round (≤ 8)
+  int32_t lb_mode;                          // tile kernel: 2 = two-level look-back (groups of 32 tiles), 1 = one chain of tiles
+  int32_t lb_sleep, lb_delay;               // tile kernel: ns between polls of an unpublished descriptor / before the first poll
 };
 
 constexpr unsigned long long DESC_AGG = 1ull << 62;
@@ -71,11 +73,12 @@ __device__ __forceinline__ unsigned long long ld_stream_u64(const unsigned long 
 }
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  // descriptor traffic stays inside this GPU: relaxed.gpu (LDG.E.64.STRONG.GPU) — ld.volatile compiles to the system-scope form
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // Tile descriptor: [status:2 | rows:31 | bytes:31] in ONE 64-bit word, so both running sums travel (and
@@ -126,6 +129,7 @@ __device__ void lookback_resolve(const TmaParams& P, int tile, long long agg_cnt
   const int spin_limit = (P.debug & 4) ? 2 : 4096;
   const int nw = HELP ? (P.lb_windows < WINDOWS ? P.lb_windows : WINDOWS) : WINDOWS;
   long long run_c = 0, run_b = 0;
+  if (HELP && P.lb_delay) __nanosleep(P.lb_delay);
   if (tile > 0) {
     int look = tile - 1;
     bool done = false;
@@ -152,6 +156,7 @@ __device__ void lookback_resolve(const TmaParams& P, int tile, long long agg_cnt
               help_publish_aggregate<VARLEN, TT>(P, helped, lane);
               spins = 0;
             }
+            if (HELP && P.lb_sleep) __nanosleep(P.lb_sleep);
             if ((dw >> 62) == 0) dw = ld_volatile_u64(desc + (size_t)idx * stride);
           }
           const unsigned pm = __ballot_sync(0xffffffffu, (dw >> 62) == 2);
@@ -173,6 +178,89 @@ __device__ void lookback_resolve(const TmaParams& P, int tile, long long agg_cnt
     if (lane == 0) st_volatile_u64(desc + (size_t)tile * stride, desc_pack(DESC_PREFIX, run_c + agg_cnt, run_b + agg_bytes));
   }
   *ex_cnt = run_c; *ex_bytes = run_b;
+}
+
+// ---- two-level look-back -------------------------------------------------------------------------------
+// A single chain of tile descriptors moves a prefix forward by one window (64 tiles) per L2 round trip (~0.6 µs), and
+// the CTAs of one wave (148 SMs × 5-6 CTAs) publish their aggregates at about the same time — so the prefix crawls
+// through every wave at ~100 tiles/µs whatever the byte rate (measured: 0.176 ms per 16384 tiles against 0.119 ms with
+// the look-back stubbed out).  Here tiles form groups of 32.  A tile sums the aggregates of the tiles before it in its
+// own group (one window) and, at the same time, looks back over GROUP descriptors (one window = 32 groups = 1024 tiles,
+// more than a wave), which the last tile of every group publishes: first the group's aggregate, then — after its own
+// group-level look-back — the inclusive prefix.  No descriptor waits for a PREFIX that is itself waiting: every tile
+// resolves two or three round trips after the aggregates around it exist.
+// Group descriptors live behind the tile descriptors (same stride); the trailing partial group is never published.
+template <bool VARLEN, int TT>
+__device__ __forceinline__ void help_publish_group(const TmaParams& P, unsigned long long* gdesc, int g, int lane) {
+  const int t = g * 32 + lane;  // only complete groups are ever waited for
+  unsigned long long d = ld_volatile_u64(P.desc + (size_t)t * P.desc_stride);
+  unsigned miss = __ballot_sync(0xffffffffu, (d >> 62) == 0);
+  while (miss) {
+    help_publish_aggregate<VARLEN, TT>(P, g * 32 + __ffs(miss) - 1, lane);
+    miss &= miss - 1;
+  }
+  while ((d >> 62) == 0) d = ld_volatile_u64(P.desc + (size_t)t * P.desc_stride);  // owner or helper has published by now
+  const unsigned c = __reduce_add_sync(0xffffffffu, (unsigned)((d >> 31) & DESC_FIELD));
+  const unsigned b = __reduce_add_sync(0xffffffffu, (unsigned)(d & DESC_FIELD));
+  if (lane == 0) atomicCAS(gdesc + (size_t)g * P.desc_stride, 0ull, desc_pack(g == 0 ? DESC_PREFIX : DESC_AGG, c, b));
+}
+
+template <bool VARLEN, int TT, bool HELP = true>
+__device__ __forceinline__ void lookback_two_level(const TmaParams& P, int tile, long long agg_cnt, long long agg_bytes, int lane,
+                                                   long long* ex_cnt, long long* ex_bytes) {
+  unsigned long long* const desc = P.desc;
+  const int stride = P.desc_stride;
+  unsigned long long* const gdesc = desc + (size_t)P.n_tiles * stride;
+  const int spin_limit = (P.debug & 4) ? 2 : 4096;
+  const int g = tile >> 5, i = tile & 31;
+  // both windows are requested before either is inspected
+  if (P.lb_delay) __nanosleep(P.lb_delay);
+  const int tidx = tile - 1 - lane;          // lanes < i: the tiles before this one in its group
+  unsigned long long dt = DESC_AGG;          // other lanes: an empty aggregate
+  if (lane < i) dt = ld_volatile_u64(desc + (size_t)tidx * stride);
+  int look = g - 1;
+  unsigned long long dg = DESC_PREFIX;       // virtual group -1: prefix 0
+  if (look - lane >= 0) dg = ld_volatile_u64(gdesc + (size_t)(look - lane) * stride);
+  for (int spins = 0;;) {
+    const unsigned pending = __ballot_sync(0xffffffffu, (dt >> 62) == 0);
+    if (!pending) break;
+    if (HELP && ++spins > spin_limit) { help_publish_aggregate<VARLEN, TT>(P, tile - 1 - (__ffs(pending) - 1), lane); spins = 0; }
+    if (P.lb_sleep) __nanosleep(P.lb_sleep);
+    if ((dt >> 62) == 0) dt = ld_volatile_u64(desc + (size_t)tidx * stride);
+  }
+  const long long in_c = __reduce_add_sync(0xffffffffu, lane < i ? (unsigned)((dt >> 31) & DESC_FIELD) : 0u);
+  const long long in_b = __reduce_add_sync(0xffffffffu, lane < i ? (unsigned)(dt & DESC_FIELD) : 0u);
+  const bool closes_group = i == 31;
+  if (closes_group && lane == 0) st_volatile_u64(gdesc + (size_t)g * stride, desc_pack(g == 0 ? DESC_PREFIX : DESC_AGG, in_c + agg_cnt, in_b + agg_bytes));
+  long long run_c = 0, run_b = 0;
+  if (g > 0) {
+    for (;;) {
+      const int idx = look - lane;
+      for (int spins = 0;;) {
+        const unsigned pending = __ballot_sync(0xffffffffu, (dg >> 62) == 0);
+        if (!pending) break;
+        if (HELP && ++spins > spin_limit) { help_publish_group<VARLEN, TT>(P, gdesc, look - (__ffs(pending) - 1), lane); spins = 0; }
+        if (P.lb_sleep) __nanosleep(P.lb_sleep);
+        if ((dg >> 62) == 0) dg = ld_volatile_u64(gdesc + (size_t)idx * stride);
+      }
+      const unsigned pm = __ballot_sync(0xffffffffu, (dg >> 62) == 2);
+      const int first = pm ? __ffs(pm) - 1 : 32;
+      const bool is_agg = lane < first;
+      run_c += __reduce_add_sync(0xffffffffu, is_agg ? (unsigned)((dg >> 31) & DESC_FIELD) : 0u);
+      run_b += __reduce_add_sync(0xffffffffu, is_agg ? (unsigned)(dg & DESC_FIELD) : 0u);
+      if (pm) {
+        const unsigned long long dp = __shfl_sync(0xffffffffu, dg, first);
+        run_c += (long long)((dp >> 31) & DESC_FIELD);
+        run_b += (long long)(dp & DESC_FIELD);
+        break;
+      }
+      look -= 32;
+      dg = DESC_PREFIX;
+      if (look - lane >= 0) dg = ld_volatile_u64(gdesc + (size_t)(look - lane) * stride);
+    }
+    if (closes_group && lane == 0) st_volatile_u64(gdesc + (size_t)g * stride, desc_pack(DESC_PREFIX, run_c + in_c + agg_cnt, run_b + in_b + agg_bytes));
+  }
+  *ex_cnt = run_c + in_c; *ex_bytes = run_b + in_b;
 }
 
 // copy len bytes inside shared memory, word-granular on the destination
@@ -278,7 +366,16 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? ARK_FP_MINBLOCKS : 3
   __shared__ long long s_excl[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x;   // tiles are claimed in launch order (as CUB's single-pass scans assume)
+  // tile = blockIdx.x relies on CTAs being dispatched in launch order (as CUB's single-pass scans assume); with a ticket
+  // (ARK_FP_TICKET=1) a tile is only ever owned by a running CTA, whatever the dispatch order
+  __shared__ int s_tile;
+  int tile = blockIdx.x;
+  if (P.ticket) {
+    if (tid == 0) s_tile = (int)atomicAdd(P.ticket, 1u);
+    __syncthreads();
+    tile = s_tile;
+    if (tile >= P.n_tiles) return;
+  }
   const int64_t row0 = (int64_t)tile * TT;
   const int rows = (int)((P.n_rows - row0) < TT ? (P.n_rows - row0) : TT);
   uint8_t* in_bytes = smem;
@@ -353,7 +450,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? ARK_FP_MINBLOCKS : 3
   // ---- F: decoupled look-back (warp 0) ----
   if (warp == 0) {
     long long ex0, ex1;
-    lookback_resolve<VARLEN, 1024, false>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
+    if (P.lb_mode == 2) lookback_two_level<VARLEN, TT, false>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
+    else lookback_resolve<VARLEN, 1024, false>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
     if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
   }
   __syncthreads();
@@ -688,12 +786,18 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
 }
 
 // ================================================================================================
-// filter_project_tile_kernel — warp-striped rows (as filter_project_pipe_kernel), ONE tile per CTA, tile claimed
-// from a ticket.  Measured on B200 (profiles/r2b_*): the persistent kernel needs a tile's aggregate to be published
-// while its CTA is still busy with the previous tile's look-back, so the CTAs end up waiting for each other in a
-// convoy (0.26 ms; 0.117 ms with the look-back stubbed out).  With one tile per CTA a tile's aggregate depends on
-// nothing but its own loads, many short-lived CTAs per SM hide each other's look-back, and the ticket — claimed by
-// the CTA when it STARTS — keeps the guarantee that a tile is only ever owned by a running CTA.
+// filter_project_tile_kernel — the default.  Warp-striped rows (lane l of warp w owns rows 128w + 32j + l: coalesced
+// 8-byte loads and stores, no shared-memory bank conflicts), ONE tile per CTA, a ninth warp that sets up the bulk copy of
+// the tile's string bytes and runs the two-level look-back while the data warps compact the strings.
+// Measured on B200, 2^24 rows of config 2 (profiles/r2_filter_variants.txt):
+//   * look-back stubbed out: 0.113 ms (0.81 of the measured HBM peak) — the data path itself;
+//   * with the look-back: 0.151 ms (0.61).  The difference is the time a tile's CTA waits for the aggregates of the tiles
+//     before it (their loads were issued at the same time and some always land late), during which it holds its slot
+//     on the SM without having loads in flight; 5 CTAs per SM (40 registers x 288 threads) do not cover it, and 7 CTAs at
+//     32 registers spill (0.154 ms).  2048-row tiles (DT = 512) 0.158 ms; a ticket instead of blockIdx 0.166 ms; one chain
+//     of tile descriptors instead of the two levels 0.172 ms; the persistent pipelined kernel above 0.26 ms (its CTAs wait
+//     for each other in a convoy); the blocked-row kernel of round 1: 0.152 ms (1024-row tiles), 0.145 ms (2048-row).
+//   * forward progress does not depend on CTA dispatch order: see help_publish_aggregate / help_publish_group.
 // ================================================================================================
 // MAXR: register cap (__maxnreg__): CTAs per SM follow from it — ptxas rounds a 288- / 544-thread CTA up when it derives
 // the cap from __launch_bounds__'s minBlocks (544 threads, 3 blocks → 32 registers and spills instead of the 40 that fit)
@@ -716,31 +820,33 @@ __global__ void __launch_bounds__(DT + 32) __maxnreg__(MAXR) filter_project_tile
   uint8_t* const in_bytes = smem;
   uint8_t* const out_bytes = smem + P.str_cap + 32;
   const int n_tiles = P.n_tiles;
-  if (tid == LB_WARP * 32) {
-    if (VARLEN) { mbar_init(&s_bar, 1); mbar_fence_init(); }
-    // tile = blockIdx.x: no atomic on the CTA's critical path (a ticket — tiles in START order — costs 12 % here: every CTA
-    // waits ~1 µs for its atomicAdd before it can issue a load; ARK_FP_TICKET=1 selects it).  Forward progress does not
-    // depend on the dispatch order either way: see help_publish_aggregate.
-    const int t = P.ticket ? (int)atomicAdd(P.ticket, 1u) : (int)blockIdx.x;
-    s_tile = t;
-    if (VARLEN && t < n_tiles) {
-      const int64_t r0 = (int64_t)t * TT;
-      const int64_t rr = P.n_rows - r0;
-      const int32_t o0 = P.offsets_in[r0], o1 = P.offsets_in[r0 + (rr < TT ? rr : TT)];
-      const uintptr_t a0 = reinterpret_cast<uintptr_t>(P.data_in + o0), a1 = reinterpret_cast<uintptr_t>(P.data_in + o1);
-      const uintptr_t lo = a0 & ~(uintptr_t)15, hi = (a1 + 15) & ~(uintptr_t)15;
-      int staged = 0;
-      if (o1 > o0 && hi - lo <= (uintptr_t)P.str_cap) {  // staged ⇒ selected bytes ≤ window ≤ str_cap
-        staged = 1;
-        mbar_expect_tx(&s_bar, (unsigned)(hi - lo));
-        tma_load_1d(in_bytes, reinterpret_cast<const void*>(lo), (unsigned)(hi - lo), &s_bar);
-      }
-      s_str_base = o0 - (int32_t)(a0 - lo); s_str_staged = staged;
-    }
+  // tile = blockIdx.x: no atomic on the CTA's critical path (a ticket — tiles in START order — makes every CTA wait ~1 µs
+  // for its atomicAdd before it can issue a load; ARK_FP_TICKET=1 selects it).  Forward progress does not depend on the
+  // dispatch order either way: see help_publish_aggregate.
+  int tile = blockIdx.x;
+  if (P.ticket) {
+    if (tid == LB_WARP * 32) s_tile = (int)atomicAdd(P.ticket, 1u);
+    __syncthreads();
+    tile = s_tile;
   }
-  __syncthreads();
-  const int tile = s_tile;
   if (tile >= n_tiles) return;
+  // the data warps issue their loads at once; the window of string bytes is set up by the look-back warp meanwhile (its two
+  // offset loads used to sit in front of a CTA-wide barrier: every tile started one memory latency late)
+  if (VARLEN && tid == LB_WARP * 32) {
+    mbar_init(&s_bar, 1); mbar_fence_init();
+    const int64_t r0 = (int64_t)tile * TT;
+    const int64_t rr = P.n_rows - r0;
+    const int32_t o0 = P.offsets_in[r0], o1 = P.offsets_in[r0 + (rr < TT ? rr : TT)];
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(P.data_in + o0), a1 = reinterpret_cast<uintptr_t>(P.data_in + o1);
+    const uintptr_t lo = a0 & ~(uintptr_t)15, hi = (a1 + 15) & ~(uintptr_t)15;
+    int staged = 0;
+    if (o1 > o0 && hi - lo <= (uintptr_t)P.str_cap) {  // staged ⇒ selected bytes ≤ window ≤ str_cap
+      staged = 1;
+      mbar_expect_tx(&s_bar, (unsigned)(hi - lo));
+      tma_load_1d(in_bytes, reinterpret_cast<const void*>(lo), (unsigned)(hi - lo), &s_bar);
+    }
+    s_str_base = o0 - (int32_t)(a0 - lo); s_str_staged = staged;   // read by the data warps after barrier (1)
+  }
   if (warp == LB_WARP) {
     __syncthreads();   // (1): the data warps' totals are in shared memory
     int tile_cnt = lane < T_WARPS ? s_cnt[lane] : 0, tb = (VARLEN && lane < T_WARPS) ? s_bytes[lane] : 0;
@@ -749,7 +855,8 @@ __global__ void __launch_bounds__(DT + 32) __maxnreg__(MAXR) filter_project_tile
     if ((P.debug & 4) && (tile % 37) == 5) __nanosleep(40000);  // test knob: a late tile, so that successors have to help
     if (lane == 0) st_volatile_u64(P.desc + (size_t)tile * P.desc_stride, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
     long long ex0, ex1;
-    if (P.debug & 1) { ex0 = (long long)tile * (TT / 2); ex1 = ex0 * 12; }
+    if (P.debug & 1) { ex0 = (long long)tile * (TT / 2) + ((P.debug & 8) ? 3 : 0); ex1 = ex0 * 12 + ((P.debug & 8) ? 5 : 0); }  // bit 3: misaligned fake positions
+    else if (P.lb_mode == 2) lookback_two_level<VARLEN, TT>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
     else lookback_resolve<VARLEN, TT, true, 2>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
     if (lane == 0) { s_excl[0] = ex0; s_excl[1] = ex1; }
     __syncthreads();   // (2)
@@ -908,6 +1015,8 @@ static int g_fp_threads = [] { const char* e = getenv("ARK_FP_THREADS"); return 
 static int g_desc_stride = [] { const char* e = getenv("ARK_FP_DESC_STRIDE"); int v = e ? atoi(e) : 4; return v >= 1 && v <= 16 ? v : 4; }();  // one descriptor per 32-byte sector
 int filter_project_tma_tile_rows() { return g_fp_threads * 4; }
 int filter_project_tma_desc_stride() { return g_desc_stride; }
+// u64 words of descriptor scratch for n_tiles tiles: the tile descriptors, then one descriptor per group of 32 tiles
+size_t filter_project_tma_desc_words(int64_t n_tiles) { return (size_t)(n_tiles + (n_tiles + 31) / 32) * (size_t)g_desc_stride; }
 int filter_project_tma_max_fixed_out() { return T_MAX_FIXED_OUT; }
 
 // Returns false when the inputs do not meet the alignment rules of this path (caller falls back).
@@ -950,6 +1059,15 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
   P.debug = debug;
   static const int lbw = [] { const char* e = getenv("ARK_FP_LB_WINDOWS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 8 ? v : 4; }();
   P.lb_windows = lbw;
+  static const int lb_mode = [] { const char* e = getenv("ARK_FP_LB"); return e && atoi(e) == 1 ? 1 : 2; }();
+  P.lb_mode = lb_mode;
+  static const int lb_sleep = [] { const char* e = getenv("ARK_FP_LB_SLEEP"); return e ? atoi(e) : 0; }();
+  // the look-back warp sleeps this long before its first poll: the aggregates it needs belong to tiles whose loads were issued
+  // at about the same time as its own, and the 60-odd descriptor loads of a poll that finds them missing are wasted L2
+  // requests (measured, 2^24 rows: 0 ns 0.161 ms, 250 ns 0.156, 500 ns 0.152, 1000 ns 0.151, 1500 ns 0.176 before the
+  // start-up barrier went away)
+  static const int lb_delay = [] { const char* e = getenv("ARK_FP_LB_DELAY"); return e ? atoi(e) : 800; }();
+  P.lb_sleep = lb_sleep; P.lb_delay = lb_delay;
   // string staging sized from the batch's average string length (+25 %), 2 KB granules, 4..24 KB
   int cap = 0;
   if (P.has_varlen) {
@@ -965,15 +1083,15 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
   // implementation: 2 = striped rows, one ticketed tile per CTA (default); 0 = persistent pipelined striped kernel;
   // 1 = the r1 kernel (blocked rows, tile = blockIdx).  0 and 1 are kept for A/B runs.
   static const int impl = [] { const char* e = getenv("ARK_FP_IMPL"); return e ? atoi(e) : 2; }();
-  if (impl == 2 && g_fp_threads == 256 && ticket != nullptr) {
+  if (impl == 2 && ticket != nullptr) {
     static const bool use_ticket = [] { const char* e = getenv("ARK_FP_TICKET"); return e && atoi(e) != 0; }();
     if (!use_ticket) P.ticket = nullptr;
     const size_t smem = v ? 2 * (size_t)(cap + 32) : 0;
     // data threads per CTA: g_fp_threads (ARK_FP_THREADS = 256 | 512); register cap: ARK_FP_MAXR (40 | 48 | 56)
-    static const int maxr = [] { const char* e = getenv("ARK_FP_MAXR"); const int x = e ? atoi(e) : 40; return x == 48 || x == 56 ? x : 40; }();
+    static const int maxr = [] { const char* e = getenv("ARK_FP_MAXR"); const int x = e ? atoi(e) : 40; return x == 32 || x == 48 || x == 56 ? x : 40; }();
     const int dt = g_fp_threads;
 #define ARK_TILE_R(NF, V, D) (maxr == 56 ? (const void*)filter_project_tile_kernel<NF, V, 56, D> : maxr == 48 ? (const void*)filter_project_tile_kernel<NF, V, 48, D> \
-                                                                                                     : (const void*)filter_project_tile_kernel<NF, V, 40, D>)
+                              : maxr == 32 ? (const void*)filter_project_tile_kernel<NF, V, 32, D> : (const void*)filter_project_tile_kernel<NF, V, 40, D>)
 #define ARK_TILE_FN(NF, V) (dt == 512 ? ARK_TILE_R(NF, V, 512) : ARK_TILE_R(NF, V, 256))
     static bool configured = false;
     if (!configured) {
@@ -1031,6 +1149,10 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
     void* args[] = {(void*)&P};
     ARK_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(256), args, smem, stream));
     return true;
+  }
+  {
+    static const bool use_ticket = [] { const char* e = getenv("ARK_FP_TICKET"); return e && atoi(e) != 0; }();
+    if (!use_ticket) P.ticket = nullptr;
   }
   const size_t smem = P.has_varlen ? 2 * (size_t)(cap + 32) : 0;
   const int max_smem = 2 * (48 * 1024 + 32);

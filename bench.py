@@ -533,7 +533,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic", "config": cfg,
-            "roofline": {"bound": "hbm", "kernel": "filter_project_pipe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "filter_project_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": k_n},
             "e2e": {"value": e2e_pageable, "unit": "rows/s", "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": d2h_per_step,
