@@ -5,7 +5,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v --expt-relaxed-constexpr $(EXTRA)
 CSRC      := arkflow_b200/csrc
 OBJDIR    := build/obj
-SRCS      := $(wildcard $(CSRC)/*.cu) $(wildcard $(CSRC)/*.cc)
+SRCS      := $(wildcard $(CSRC)/*.cu) $(wildcard $(CSRC)/*.cc) $(wildcard $(CSRC)/*.cpp)
 OBJS      := $(patsubst $(CSRC)/%,$(OBJDIR)/%.o,$(SRCS))
 LIB       := arkflow_b200/libarkflow_b200.so
 HDRS      := $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/arkflow_b200.h
@@ -21,6 +21,11 @@ $(OBJDIR)/%.cc.o: $(CSRC)/%.cc $(HDRS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -x cu -c $< -o $@ 2> $@.log || (cat $@.log; exit 1)
 	@grep -E "error|warning" $@.log || true
+
+# pure host code (AVX intrinsics): g++ directly
+$(OBJDIR)/%.cpp.o: $(CSRC)/%.cpp $(HDRS)
+	@mkdir -p $(OBJDIR)
+	g++ -O3 -std=c++17 -fPIC -Wall -c $< -o $@
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -Xlinker -soname=libarkflow_b200.so

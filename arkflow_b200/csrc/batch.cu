@@ -1,4 +1,5 @@
 // batch.cu — pools, stream leases, Arrow C Data Interface import/export (see batch.h).
+#include <chrono>
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -248,6 +249,8 @@ static bool format_supported(const std::string& f) {
 // 2 MB chunks into pinned slots (two per thread, from the pinned pool) and queues each chunk's H2D as soon as it is
 // filled, so host memcpy, PCIe transfer and — across concurrent callers — the kernels of other calls overlap.
 // Pinned or registered sources (cudaPointerGetAttributes ≠ unregistered) take the direct copy.
+void host_copy_stream(void* dst, const void* src, size_t n, int kind);  // host_copy.cpp
+
 namespace {
 
 struct StagePool {
@@ -286,7 +289,7 @@ struct StagePool {
 int stage_threads() {
   static const int n = [] {
     const char* e = getenv("ARK_STAGE_THREADS");
-    int v = e ? atoi(e) : 8;
+    int v = e ? atoi(e) : 12;
     return std::max(0, std::min(v, 32));
   }();
   return n;
@@ -296,9 +299,10 @@ StagePool& stage_pool() {
   return *p;
 }
 
-// chunk size (ARK_STAGE_CHUNK_MB) and thread count (ARK_STAGE_THREADS) made no measurable difference between 2-16 MB and
-// 4-16 threads on the B200 hosts (profiles/r2_e2e_staging.txt): the end-to-end rate with pageable inputs stayed at
-// 0.6-0.77 of the pinned one, run-to-run noise included
+// Measured on the B200 hosts (profiles/r2_e2e_staging.txt): with glibc's memcpy the staging threads moved 3-4 GB/s each and
+// the end-to-end rate with pageable inputs sat at 0.5-0.75 of the pinned one whatever the chunk size (2-16 MB) or thread
+// count (4-24); with non-temporal copies (host_copy.cpp) 7.5-9 GB/s per thread and 0.80-0.82 with 8-12 threads — the
+// threads then wait for the PCIe copies, not the other way round.
 size_t stage_chunk() {
   static const size_t v = [] { const char* e = getenv("ARK_STAGE_CHUNK_MB"); const int mb = e ? atoi(e) : 4; return (size_t)std::max(1, std::min(mb, 64)) << 20; }();
   return v;
@@ -312,6 +316,10 @@ bool is_pageable(const void* p) {
 }
 
 void staged_h2d(void* dst, const void* src, size_t n, cudaStream_t s) {
+  using clk = std::chrono::steady_clock;
+  static const bool trace = getenv("ARK_STAGE_TRACE") != nullptr;
+  static const int copy_kind = [] { const char* e = getenv("ARK_STAGE_COPY"); return e ? atoi(e) : -1; }();  // 0 memcpy, 1 AVX2 NT, 2 AVX-512 NT
+  const auto t_begin = clk::now();
   const size_t STAGE_CHUNK = stage_chunk();
   const size_t n_chunks = (n + STAGE_CHUNK - 1) / STAGE_CHUNK;
   const int T = (int)std::min<size_t>((size_t)stage_threads(), n_chunks);
@@ -320,9 +328,12 @@ void staged_h2d(void* dst, const void* src, size_t n, cudaStream_t s) {
   std::condition_variable cv;
   int done = 0;
   cudaError_t first_err = cudaSuccess;
+  double us_copy = 0, us_wait = 0, us_issue = 0, us_start = 0;
   for (int w = 0; w < T; ++w) {
     stage_pool().submit([&, w] {
       ensure_device();
+      const auto t_start = clk::now();
+      double my_copy = 0, my_wait = 0, my_issue = 0;
       cudaEvent_t ev[2] = {nullptr, nullptr};
       cudaError_t err = cudaSuccess;
       bool used[2] = {false, false};
@@ -331,16 +342,27 @@ void staged_h2d(void* dst, const void* src, size_t n, cudaStream_t s) {
       for (size_t c = (size_t)w; c < n_chunks && err == cudaSuccess; c += (size_t)T, turn ^= 1) {
         uint8_t* slot = (uint8_t*)ring.get() + ((size_t)w * 2 + turn) * STAGE_CHUNK;
         const size_t off = c * STAGE_CHUNK, len = std::min(STAGE_CHUNK, n - off);
+        const auto t0 = clk::now();
         if (used[turn]) err = cudaEventSynchronize(ev[turn]);  // the slot's previous chunk has left for the device
         if (err != cudaSuccess) break;
-        memcpy(slot, (const uint8_t*)src + off, len);
+        const auto t1 = clk::now();
+        host_copy_stream(slot, (const uint8_t*)src + off, len, copy_kind);
+        const auto t2 = clk::now();
         err = cudaMemcpyAsync((uint8_t*)dst + off, slot, len, cudaMemcpyHostToDevice, s);
         if (err == cudaSuccess) err = cudaEventRecord(ev[turn], s);
         used[turn] = true;
+        if (trace) {
+          const auto t3 = clk::now();
+          my_wait += std::chrono::duration<double, std::micro>(t1 - t0).count();
+          my_copy += std::chrono::duration<double, std::micro>(t2 - t1).count();
+          my_issue += std::chrono::duration<double, std::micro>(t3 - t2).count();
+        }
       }
       for (int k = 0; k < 2; ++k) if (ev[k]) cudaEventDestroy(ev[k]);
       std::lock_guard<std::mutex> l(mu);
       if (err != cudaSuccess && first_err == cudaSuccess) first_err = err;
+      us_copy += my_copy; us_wait += my_wait; us_issue += my_issue;
+      us_start += std::chrono::duration<double, std::micro>(t_start - t_begin).count();
       ++done;
       cv.notify_one();
     });
@@ -350,6 +372,11 @@ void staged_h2d(void* dst, const void* src, size_t n, cudaStream_t s) {
     cv.wait(l, [&] { return done == T; });
   }
   ARK_CUDA(first_err);
+  if (trace) {
+    const double wall = std::chrono::duration<double, std::micro>(clk::now() - t_begin).count();
+    fprintf(stderr, "[stage] %.1f MB in %.0f us (%.1f GB/s) by %d threads: per thread copy %.0f us (%.1f GB/s each) wait %.0f us issue %.0f us start-lag %.0f us\n",
+            n / 1e6, wall, n / 1e3 / wall, T, us_copy / T, n / 1e3 / std::max(us_copy, 1.0), us_wait / T, us_issue / T, us_start / T);
+  }
   // `ring` returns to the pinned pool when this call's stream has been synchronised (blocks freed inside a call are
   // parked until then), i.e. after the queued copies have read it
 }
