@@ -18,6 +18,9 @@ engine to exercise this host logic under gloo with world_size 2.
 """
 from __future__ import annotations
 
+import os
+import sys
+import time
 import ctypes as C
 from typing import Optional
 
@@ -274,7 +277,16 @@ def exchange_partitions_p2p(batch: DeviceBatch, part_rows: list[int], group=None
     from .processor import _check
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    trace = os.environ.get("ARK_DIST_TRACE") and rank == 0
+    t_ = [time.perf_counter()]
+
+    def lap():
+        if trace:
+            torch.cuda.synchronize()
+            t_.append(time.perf_counter())
+
     blob = _ipc_export(batch)
+    lap()
     # ONE fixed-size all-gather carries every rank's descriptor and partition row counts:
     # [ok:int64 | blob_len:int64 | part_rows: world × int64 | blob bytes, zero-padded]
     slot = 16 + 8 * world + _IPC_SLOT_BYTES
@@ -289,6 +301,7 @@ def exchange_partitions_p2p(batch: DeviceBatch, part_rows: list[int], group=None
     everyone = torch.empty(slot * world, dtype=torch.uint8, device=device)
     dist.all_gather_into_tensor(everyone, mine.to(device), group=group)
     everyone = everyone.cpu()
+    lap()
     gathered = []
     for s_ in range(world):
         rec = everyone[s_ * slot: (s_ + 1) * slot]
@@ -303,8 +316,14 @@ def exchange_partitions_p2p(batch: DeviceBatch, part_rows: list[int], group=None
     ptrs = (C.POINTER(C.c_uint8) * world)(*[C.cast(k, C.POINTER(C.c_uint8)) for k in keep])
     sizes = (C.c_int64 * world)(*[len(b) for b in blobs])
     out_dev, out_sch = L.ArrowDeviceArray(), L.ArrowSchema()
+    lap()
     status = L.lib().ark_ipc_concat_slices_device(world, ptrs, sizes, row0, nrows, C.byref(out_dev), C.byref(out_sch))
+    lap()
     dist.barrier(group)  # every reader is done with this rank's buffers before they are released
+    lap()
+    if trace:
+        d = [(b - a) * 1e3 for a, b in zip(t_, t_[1:])]
+        print("[exchange p2p] rows %d: export %.2f ms, all-gather %.2f, decode %.2f, pull+concat %.2f, barrier %.2f" % (batch.num_rows, *d), file=sys.stderr)
     _check(status)
     return DeviceBatch.adopt(out_dev, out_sch)
 

@@ -685,8 +685,9 @@ def run_join(args, rank, world, lib, synth_device, barrier, max_over_ranks, sum_
 
     from arkflow_b200.dist import NativeEngine, distributed_join
 
-    steps, warm = args.join_steps, 2
-    n_probe, n_build, K = ROWS_PER_BATCH, 1 << 20, 1 << 20
+    steps, warm = args.join_steps, 3
+    n_probe, n_build = ROWS_PER_BATCH, 1 << 20
+    K = n_build * world  # the key space grows with the build side: every probe row meets ~one build row at any N
     eng = NativeEngine(JOIN_QUERY)
     base = (1 << 42) + rank * (1 << 34)
     probes = [synth_device(n_probe, base + b * n_probe, K) for b in range(2)]
@@ -780,7 +781,8 @@ def run_window(args, rank, world, lib, barrier, max_over_ranks, sum_over_ranks, 
         out.close()
         return rows_in, cnt
 
-    one_window()
+    for _ in range(3):  # pool blocks of the window's sizes exist after the first windows
+        one_window()
     lib.ark_kernel_timing_reset()
     lib.ark_kernel_timing_enable(1)
     barrier()
@@ -825,7 +827,7 @@ def main():
     ap.add_argument("--device-threads", type=int, default=4)
     ap.add_argument("--groupby-steps", type=int, default=12)
     ap.add_argument("--join-steps", type=int, default=4)
-    ap.add_argument("--window-steps", type=int, default=3)
+    ap.add_argument("--window-steps", type=int, default=6)
     ap.add_argument("--no-sharded", action="store_true", help="skip the GROUP BY / JOIN workloads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
