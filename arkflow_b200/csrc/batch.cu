@@ -111,7 +111,11 @@ void* BlockPool::alloc(size_t bytes) {
     std::lock_guard<std::mutex> l(mu_);
     auto it = std::lower_bound(free_.begin(), free_.end(), want, [](const Block& b, size_t w) { return b.size < w; });
     if (it != free_.end() && it->size <= std::max(want + (want >> 2), want + (1u << 20))) {
-      Block b = *it; free_.erase(it); live_.push_back(b); return b.p;
+      // among the free blocks of that size, the lowest address: the same buffer of consecutive batches tends to land in
+      // the same block whatever order the previous batch's buffers were released in (peers cache their IPC mappings)
+      auto best = it;
+      for (auto j = it; j != free_.end() && j->size == it->size; ++j) if (j->p < best->p) best = j;
+      Block b = *best; free_.erase(best); live_.push_back(b); return b.p;
     }
   }
   void* p = nullptr;
@@ -119,6 +123,7 @@ void* BlockPool::alloc(size_t bytes) {
   if (e != cudaSuccess) {
     cudaGetLastError();
     trim();
+    if (kind_ == Device) { device_pool().trim(); export_pool().trim(); }  // either device pool may hold the idle blocks
     e = kind_ == Device ? cudaMalloc(&p, want) : cudaHostAlloc(&p, want, cudaHostAllocDefault);
     if (e != cudaSuccess) {
       cudaGetLastError();
@@ -180,7 +185,17 @@ void BlockPool::trim() {
 BlockPool& device_pool() { static BlockPool* p = new BlockPool(BlockPool::Device); return *p; }
 BlockPool& pinned_pool() { static BlockPool* p = new BlockPool(BlockPool::Pinned); return *p; }
 
+BlockPool& export_pool() { static BlockPool* p = new BlockPool(BlockPool::Device); return *p; }
+
+static thread_local int tl_export_alloc = 0;
+ExportAllocScope::ExportAllocScope() { ++tl_export_alloc; }
+ExportAllocScope::~ExportAllocScope() { --tl_export_alloc; }
+
 BufferPtr device_alloc(size_t bytes) {
+  if (tl_export_alloc > 0) {
+    void* p = export_pool().alloc(bytes);
+    return BufferPtr(p, [](void* q) { export_pool().free(q); });
+  }
   void* p = device_pool().alloc(bytes);
   return BufferPtr(p, [](void* q) { device_pool().free(q); });
 }

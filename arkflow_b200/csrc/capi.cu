@@ -151,6 +151,7 @@ int ark_sql_partial_aggregate_device(ark_proc_t* p, ArrowDeviceArray* in, ArrowS
     StreamLease lease;
     Batch b = import_device(&view, in_schema, &mask, in_owner);
     std::vector<int64_t> rows;
+    ExportAllocScope exported;  // the partial states are published to the other ranks over CUDA IPC
     Batch r = run_partial_aggregate(*plan, b, n_parts, rows, lease.s);
     for (int i = 0; i < n_parts; ++i) part_rows[i] = rows[i];
     export_device(r, out, out_schema);

@@ -432,6 +432,7 @@ Batch hash_partition(Batch& in, const std::string& key_column, int n_parts, std:
   ARK_CUDA(cudaGetLastError());
   Batch out;
   out.num_rows = n; out.input_name = in.input_name;
+  ExportAllocScope exported;  // the partition-ordered columns are what the peers map (ipc_exchange.cu)
   for (auto& c : in.cols) {
     if (!c.present) fail(ARK_ERR_UNSUPPORTED, "partition of a column with Arrow type '" + c.field.format + "'");
     out.cols.push_back(take_column(c, (const unsigned int*)idx.get(), n, c.field.name, stream));

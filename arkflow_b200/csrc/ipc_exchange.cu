@@ -57,6 +57,7 @@ void export_buf(const void* p, IpcBuf* b) {
     fail(ARK_ERR_UNSUPPORTED, std::string("ipc export: ") + cudaGetErrorString(e) + " (memory not created by cudaMalloc?)");
   }
   device_pool().mark_exported((const void*)(uintptr_t)base);  // peers cache the mapping: the block must outlive trim()
+  export_pool().mark_exported((const void*)(uintptr_t)base);
   memcpy(b->handle, &h, 64);
   b->offset = (uint64_t)((unsigned long long)(uintptr_t)p - base);
   b->raw = (uint64_t)(uintptr_t)p;

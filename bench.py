@@ -685,7 +685,9 @@ def run_join(args, rank, world, lib, synth_device, barrier, max_over_ranks, sum_
 
     from arkflow_b200.dist import NativeEngine, distributed_join
 
-    steps, warm = args.join_steps, 3
+    # N > 1: every block a rank publishes is mapped once by every peer (cudaIpcOpenMemHandle, ~1.5 ms each); the first steps of
+    # a stream pay for that, the timed steps are the steady state
+    steps, warm = args.join_steps, (3 if world == 1 else 10)
     n_probe, n_build = ROWS_PER_BATCH, 1 << 20
     K = n_build * world  # the key space grows with the build side: every probe row meets ~one build row at any N
     eng = NativeEngine(JOIN_QUERY)
@@ -826,7 +828,7 @@ def main():
     ap.add_argument("--e2e-threads", type=int, default=3)
     ap.add_argument("--device-threads", type=int, default=4)
     ap.add_argument("--groupby-steps", type=int, default=12)
-    ap.add_argument("--join-steps", type=int, default=4)
+    ap.add_argument("--join-steps", type=int, default=6)
     ap.add_argument("--window-steps", type=int, default=6)
     ap.add_argument("--no-sharded", action="store_true", help="skip the GROUP BY / JOIN workloads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
