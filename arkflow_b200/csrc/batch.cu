@@ -187,12 +187,59 @@ BlockPool& pinned_pool() { static BlockPool* p = new BlockPool(BlockPool::Pinned
 
 BlockPool& export_pool() { static BlockPool* p = new BlockPool(BlockPool::Device); return *p; }
 
+// ---- arenas for exported outputs (see ExportAllocScope) ----
+namespace {
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t size = 0, used = 0;
+  std::atomic<int> live{0};   // buffers cut from the arena that are still referenced (+1 while a scope holds it)
+};
+std::mutex g_arena_mu;
+std::vector<Arena*> g_arenas;  // never freed: peers keep them mapped
+
+Arena* arena_acquire(size_t bytes) {
+  std::lock_guard<std::mutex> l(g_arena_mu);
+  for (Arena* a : g_arenas)
+    if (a->live.load() == 0 && a->size >= bytes) { a->used = 0; a->live.store(1); return a; }
+  ensure_device();
+  size_t want = bytes + (bytes >> 2);
+  size_t step = (size_t)1 << 20;
+  while ((step << 3) <= want) step <<= 1;
+  want = (size_t)round_up((int64_t)want, (int64_t)step);
+  void* p = nullptr;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    cudaGetLastError();
+    device_pool().trim(); export_pool().trim();
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }  // the scope falls back to the pool
+  }
+  Arena* a = new Arena;
+  a->base = (uint8_t*)p; a->size = want; a->live.store(1);
+  g_arenas.push_back(a);
+  return a;
+}
+}  // namespace
+
 static thread_local int tl_export_alloc = 0;
-ExportAllocScope::ExportAllocScope() { ++tl_export_alloc; }
-ExportAllocScope::~ExportAllocScope() { --tl_export_alloc; }
+static thread_local Arena* tl_arena = nullptr;
+ExportAllocScope::ExportAllocScope(size_t expected_bytes) {
+  ++tl_export_alloc;
+  if (expected_bytes > 0 && tl_arena == nullptr) tl_arena = arena_acquire(expected_bytes);
+}
+ExportAllocScope::~ExportAllocScope() {
+  if (--tl_export_alloc == 0 && tl_arena) { tl_arena->live.fetch_sub(1); tl_arena = nullptr; }
+}
 
 BufferPtr device_alloc(size_t bytes) {
   if (tl_export_alloc > 0) {
+    if (Arena* a = tl_arena) {
+      const size_t need = (size_t)round_up((int64_t)std::max<size_t>(bytes, 1), 512);
+      if (a->used + need <= a->size) {
+        void* p = a->base + a->used;
+        a->used += need;
+        a->live.fetch_add(1);
+        return BufferPtr(p, [a](void*) { a->live.fetch_sub(1); });
+      }
+    }
     void* p = export_pool().alloc(bytes);
     return BufferPtr(p, [](void* q) { export_pool().free(q); });
   }

@@ -52,14 +52,19 @@ using BufferPtr = std::shared_ptr<void>;  // owner of one allocation; get() = ba
 BufferPtr device_alloc(size_t bytes);
 BufferPtr pinned_alloc(size_t bytes);
 
-// While one of these is alive on a thread, device_alloc() on that thread draws from export_pool().  The outputs of a hash
-// partition / partial aggregate are published to the other ranks as CUDA IPC handles and every peer caches its mapping of a
-// block; taken from the general pool, a different block served the same buffer from step to step and each new block cost
-// every peer a cudaIpcOpenMemHandle (measured on 8 GPUs: 86 ms per join step, 56 opens of ~1.5 ms).  A pool that only these
-// outputs use sees the same request sequence every step and hands out the same few blocks.
+// While one of these is alive on a thread, device_alloc() on that thread serves buffers that are going to be published to
+// the other ranks as CUDA IPC handles (the outputs of a hash partition / partial aggregate).  Every peer caches its mapping of
+// a block, and a new block costs every peer a cudaIpcOpenMemHandle (~1.5 ms): taken from the general pool, a different block
+// served the same buffer from step to step (measured on 8 GPUs: 86 ms per join step, 56 opens).  So:
+//  * with `expected_bytes` > 0 the scope bump-allocates from ONE arena block that holds the whole output (and the few
+//    temporaries allocated next to it); an arena is reused as soon as every buffer cut from it has been released, the
+//    lowest-numbered free arena first — consecutive batches of a stream land in the same one or two blocks;
+//  * otherwise (or when the arena is full) from export_pool(), a pool that only such outputs use.
 struct ExportAllocScope {
-  ExportAllocScope();
+  explicit ExportAllocScope(size_t expected_bytes = 0);
   ~ExportAllocScope();
+  ExportAllocScope(const ExportAllocScope&) = delete;
+  ExportAllocScope& operator=(const ExportAllocScope&) = delete;
 };
 
 // ---- streams ------------------------------------------------------------------------------------

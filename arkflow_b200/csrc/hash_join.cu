@@ -432,7 +432,15 @@ Batch hash_partition(Batch& in, const std::string& key_column, int n_parts, std:
   ARK_CUDA(cudaGetLastError());
   Batch out;
   out.num_rows = n; out.input_name = in.input_name;
-  ExportAllocScope exported;  // the partition-ordered columns are what the peers map (ipc_exchange.cu)
+  // the partition-ordered columns are what the peers map (ipc_exchange.cu): one arena for all of them.  The output is a
+  // permutation of the input, so its size is the input's (+ the gather's temporaries: lengths, offsets, scan scratch)
+  size_t out_bytes = 1 << 20;
+  for (auto& c : in.cols) {
+    const bool vl = c.field.type == DType::Utf8 || c.field.type == DType::Binary;
+    out_bytes += vl ? (size_t)(n + 1) * 12 + (size_t)std::max<int64_t>(varlen_bytes_bound(c), 0) + 4096 : (size_t)n * 8 + 1024;
+    out_bytes += c.validity ? (size_t)n + (size_t)n / 8 + 2048 : 0;
+  }
+  ExportAllocScope exported(out_bytes);
   for (auto& c : in.cols) {
     if (!c.present) fail(ARK_ERR_UNSUPPORTED, "partition of a column with Arrow type '" + c.field.format + "'");
     out.cols.push_back(take_column(c, (const unsigned int*)idx.get(), n, c.field.name, stream));
