@@ -76,6 +76,8 @@ std::unique_ptr<Processor> make_json_to_arrow_for_sample(const std::vector<std::
 Batch json_to_arrow_device(const Processor& proc, Batch& in, cudaStream_t stream);
 Batch hash_partition(Batch& in, const std::string& key_column, int n_parts, std::vector<int64_t>& part_rows, cudaStream_t stream);
 Column take_column(const Column& src, const unsigned int* idx, int64_t n, const std::string& name, cudaStream_t stream, bool may_miss = false);
+struct TakeSpec { const Column* src; int side; std::string name; bool may_miss; };  // side: which index array (0 | 1)
+std::vector<Column> take_columns(const std::vector<TakeSpec>& specs, const unsigned int* idx0, const unsigned int* idx1, int64_t n, cudaStream_t stream);
 std::unique_ptr<Processor> make_arrow_to_json(const char* config_json);
 Batch arrow_to_json_device(const Processor& proc, Batch& in, cudaStream_t stream);
 Batch concat_device(std::vector<Batch>& ins, cudaStream_t stream);

@@ -129,6 +129,40 @@ __global__ void take_lengths_kernel(const int32_t* offsets, const unsigned int* 
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { const unsigned int r = idx[i]; lens[i] = r == NO_ROW ? 0 : offsets[r + 1] - offsets[r]; }
 }
+// All plain gathers of one output batch in ONE launch: every output row reads its (up to two) source row indices once,
+// then copies the 8-byte value of every fixed-width column and records the length of every string column.  One launch per
+// column read the index array again for each of them and cost 0.10 / 0.09 ms apiece on 2^24 rows (join of two schema-S
+// tables: four fixed-width + two string columns).
+constexpr int TAKE_MAX_FIXED = 8, TAKE_MAX_STR = 4;
+struct TakeMultiParams {
+  const unsigned int* idx[2];
+  int32_t n_fixed, n_str;
+  const unsigned long long* fsrc[TAKE_MAX_FIXED];
+  unsigned long long* fdst[TAKE_MAX_FIXED];
+  uint8_t fside[TAKE_MAX_FIXED];
+  const int32_t* soff[TAKE_MAX_STR];
+  int32_t* slen[TAKE_MAX_STR];
+  uint8_t sside[TAKE_MAX_STR];
+};
+__global__ void __launch_bounds__(256) take_multi_kernel(const __grid_constant__ TakeMultiParams P, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned int r[2];
+    r[0] = P.idx[0] ? P.idx[0][i] : NO_ROW;
+    r[1] = P.idx[1] ? P.idx[1][i] : NO_ROW;
+    unsigned long long v[TAKE_MAX_FIXED];
+    int32_t l[TAKE_MAX_STR];
+#pragma unroll
+    for (int c = 0; c < TAKE_MAX_FIXED; ++c)
+      if (c < P.n_fixed) { const unsigned int rr = r[P.fside[c]]; v[c] = rr == NO_ROW ? 0ull : P.fsrc[c][rr]; }
+#pragma unroll
+    for (int c = 0; c < TAKE_MAX_STR; ++c)
+      if (c < P.n_str) { const unsigned int rr = r[P.sside[c]]; l[c] = rr == NO_ROW ? 0 : P.soff[c][rr + 1] - P.soff[c][rr]; }
+#pragma unroll
+    for (int c = 0; c < TAKE_MAX_FIXED; ++c) if (c < P.n_fixed) P.fdst[c][i] = v[c];
+#pragma unroll
+    for (int c = 0; c < TAKE_MAX_STR; ++c) if (c < P.n_str) P.slen[c][i] = l[c];
+  }
+}
 // global → shared copy of one string, word-granular on the (shared) destination: aligned source words are
 // funnel-shifted into place, so a 12-byte key costs 3–4 loads and 3 stores instead of 12 + 12.
 __device__ __forceinline__ void gather_string(uint8_t* dst, const uint8_t* src, int len) {
@@ -335,6 +369,93 @@ Column take_column(const Column& src, const unsigned int* idx, int64_t n, const 
   return c;
 }
 
+// Gathers several columns at once: specs[k] = (source column, which of the two index arrays, output name, may_miss).
+// Fixed-width and string columns without a validity bitmap go through take_multi_kernel — one launch for all values and
+// lengths, one host round trip for all string totals; anything else (Boolean, nullable, outer-join misses) takes take_column.
+std::vector<Column> take_columns(const std::vector<TakeSpec>& specs, const unsigned int* idx0, const unsigned int* idx1, int64_t n, cudaStream_t stream) {
+  if (n >= (1ll << 31) - 1) fail(ARK_ERR_UNSUPPORTED, "gather of 2^31 or more rows in one batch");
+  std::vector<Column> out(specs.size());
+  std::vector<int> fixed, strs;
+  for (size_t k = 0; k < specs.size(); ++k) {
+    const Column& src = *specs[k].src;
+    const bool plain = !src.validity && !specs[k].may_miss && n > 0;
+    const bool is_fixed = src.field.type == DType::Int64 || src.field.type == DType::Float64;
+    const bool is_str = src.field.type == DType::Utf8 || src.field.type == DType::Binary;
+    if (plain && is_fixed && (int)fixed.size() < TAKE_MAX_FIXED) fixed.push_back((int)k);
+    else if (plain && is_str && (int)strs.size() < TAKE_MAX_STR) strs.push_back((int)k);
+    else out[k] = take_column(src, specs[k].side == 0 ? idx0 : idx1, n, specs[k].name, stream, specs[k].may_miss);
+  }
+  if (fixed.empty() && strs.empty()) return out;
+  TakeMultiParams P;
+  memset(&P, 0, sizeof P);
+  P.idx[0] = idx0; P.idx[1] = idx1;
+  std::vector<BufferPtr> fbuf, lens, offs;
+  for (int k : fixed) {
+    BufferPtr d = device_alloc((size_t)n * 8);
+    P.fsrc[P.n_fixed] = (const unsigned long long*)specs[k].src->data; P.fdst[P.n_fixed] = (unsigned long long*)d.get(); P.fside[P.n_fixed] = (uint8_t)specs[k].side;
+    ++P.n_fixed; fbuf.push_back(d);
+  }
+  for (int k : strs) {
+    BufferPtr l = device_alloc((size_t)(n + 1) * 4), o = device_alloc((size_t)(n + 1) * 4);
+    ARK_CUDA(cudaMemsetAsync((int32_t*)l.get() + n, 0, 4, stream));
+    P.soff[P.n_str] = specs[k].src->offsets; P.slen[P.n_str] = (int32_t*)l.get(); P.sside[P.n_str] = (uint8_t)specs[k].side;
+    ++P.n_str; lens.push_back(l); offs.push_back(o);
+  }
+  {
+    KernelTimer t("take_multi_kernel", stream);
+    take_multi_kernel<<<grid_for(n), 256, 0, stream>>>(P, n);
+  }
+  // string columns: offsets by scan; every column's total (and, near 2 GiB, its 64-bit sum) comes back in one round trip
+  BufferPtr sums = device_alloc(8 * (size_t)std::max<size_t>(strs.size(), 1)), h = pinned_alloc(16 * (size_t)std::max<size_t>(strs.size(), 1));
+  bool check64 = false;
+  for (size_t j = 0; j < strs.size(); ++j) {
+    const Column& src = *specs[strs[j]].src;
+    const double avg_len = src.length > 0 && src.data_bytes >= 0 ? (double)src.data_bytes / (double)src.length : 64.0;
+    if (avg_len * (double)n > 1.0e9) check64 = true;
+  }
+  if (check64) {
+    ARK_CUDA(cudaMemsetAsync(sums.get(), 0, 8 * strs.size(), stream));
+    for (size_t j = 0; j < strs.size(); ++j) {
+      KernelTimer t("sum_lengths_kernel", stream);
+      sum_lengths_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), 148 * 16), 256, 0, stream>>>((const int32_t*)lens[j].get(), n, (unsigned long long*)sums.get() + j);
+    }
+    ARK_CUDA(cudaMemcpyAsync((uint8_t*)h.get() + 8 * strs.size(), sums.get(), 8 * strs.size(), cudaMemcpyDeviceToHost, stream));
+  }
+  for (size_t j = 0; j < strs.size(); ++j) {
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, (int32_t*)lens[j].get(), (int32_t*)offs[j].get(), (int)(n + 1), stream);
+    BufferPtr tmp = device_alloc(tb + 16);
+    note_launch("cub::DeviceScan::ExclusiveSum");
+    cub::DeviceScan::ExclusiveSum(tmp.get(), tb, (int32_t*)lens[j].get(), (int32_t*)offs[j].get(), (int)(n + 1), stream);
+    ARK_CUDA(cudaMemcpyAsync((int32_t*)h.get() + j, (int32_t*)offs[j].get() + n, 4, cudaMemcpyDeviceToHost, stream));
+  }
+  if (!strs.empty()) ARK_CUDA(cudaStreamSynchronize(stream));
+  for (size_t j = 0; j < strs.size(); ++j) {
+    const int32_t total = ((const int32_t*)h.get())[j];
+    const unsigned long long s64 = check64 ? ((const unsigned long long*)((const uint8_t*)h.get() + 8 * strs.size()))[j] : 0;
+    if (total < 0 || s64 > 2147483647ull) fail(ARK_ERR_PROCESS, "Collection query results error: Arrow error: offset overflow, result column exceeds 2 GiB");
+    const TakeSpec& sp = specs[strs[j]];
+    BufferPtr bytes = device_alloc((size_t)total + 16);
+    {
+      KernelTimer t("take_bytes_tile_kernel", stream);
+      const int stage = (int)std::min<int64_t>(TAKE_STAGE_MAX, round_up((int64_t)((double)total / (double)n * TAKE_TILE * 1.5) + 256, 1024));
+      take_bytes_tile_kernel<<<(unsigned)ceil_div(n, TAKE_TILE), 256, stage, stream>>>(sp.src->data, sp.src->offsets, sp.side == 0 ? idx0 : idx1, n, (const int32_t*)offs[j].get(),
+                                                                                      (uint8_t*)bytes.get(), stage);
+    }
+    Column& c = out[strs[j]];
+    c.field = sp.src->field; c.field.name = sp.name; c.length = n;
+    c.offsets = (const int32_t*)offs[j].get(); c.data = (const uint8_t*)bytes.get(); c.data_bytes = total; c.first_offset = 0;
+    c.owners = {offs[j], bytes}; c.validity = nullptr; c.null_count = 0;
+  }
+  for (size_t j = 0; j < fixed.size(); ++j) {
+    const TakeSpec& sp = specs[fixed[j]];
+    Column& c = out[fixed[j]];
+    c.field = sp.src->field; c.field.name = sp.name; c.length = n;
+    c.data = (const uint8_t*)fbuf[j].get(); c.data_bytes = n * 8; c.owners = {fbuf[j]}; c.validity = nullptr; c.null_count = 0;
+  }
+  return out;
+}
+
 Batch run_join(const Plan& plan, Batch& left, Batch& right, cudaStream_t stream) {
   // row counts travel through cub scans with 32-bit item counts and through 32-bit row indices
   if (left.num_rows >= (1ll << 31) - 1 || right.num_rows >= (1ll << 31) - 1) fail(ARK_ERR_UNSUPPORTED, "join input with 2^31 or more rows in one batch");
@@ -390,12 +511,14 @@ Batch run_join(const Plan& plan, Batch& left, Batch& right, cudaStream_t stream)
   const unsigned int* ridx = (const unsigned int*)(build_left ? probe_idx.get() : build_idx.get());
   Batch out;
   out.num_rows = pairs;
+  std::vector<TakeSpec> specs;
   for (const auto& jo : plan.join_out) {
     const Column& src = jo.side == 0 ? left.cols[jo.col] : right.cols[jo.col];
     if (!src.present) fail(ARK_ERR_UNSUPPORTED, "join output column '" + jo.name + "' has Arrow type '" + src.field.format + "'");
     const bool build_side = (jo.side == 0) == build_left;
-    out.cols.push_back(take_column(src, jo.side == 0 ? lidx : ridx, pairs, jo.name, stream, outer && build_side));
+    specs.push_back({&src, jo.side, jo.name, (bool)(outer && build_side)});
   }
+  out.cols = take_columns(specs, lidx, ridx, pairs, stream);
   ARK_CUDA(cudaStreamSynchronize(stream));
   return out;
 }
@@ -441,10 +564,12 @@ Batch hash_partition(Batch& in, const std::string& key_column, int n_parts, std:
     out_bytes += c.validity ? (size_t)n + (size_t)n / 8 + 2048 : 0;
   }
   ExportAllocScope exported(out_bytes);
+  std::vector<TakeSpec> specs;
   for (auto& c : in.cols) {
     if (!c.present) fail(ARK_ERR_UNSUPPORTED, "partition of a column with Arrow type '" + c.field.format + "'");
-    out.cols.push_back(take_column(c, (const unsigned int*)idx.get(), n, c.field.name, stream));
+    specs.push_back({&c, 0, c.field.name, false});
   }
+  out.cols = take_columns(specs, (const unsigned int*)idx.get(), nullptr, n, stream);
   ARK_CUDA(cudaStreamSynchronize(stream));
   return out;
 }
