@@ -1007,11 +1007,295 @@ __global__ void __launch_bounds__(DT + 32) __maxnreg__(MAXR) filter_project_tile
   }
 }
 
+
+// ================================================================================================
+// filter_project_ring_kernel — persistent CTAs, every input of a tile by TMA, the store of tile k AFTER the count of tile k+1.
+//
+// One tile per CTA (above) leaves a CTA idle on its SM while the tiles before it publish their aggregates.  Here a CTA
+// keeps two input stages and two output stages in shared memory:
+//   * the producer (thread 0) issues the bulk copies of tile it+2 — predicate column, key offsets, string bytes — as soon
+//     as every warp has consumed the stage of tile it: two tiles per CTA are always in flight, no registers involved;
+//   * the data warps evaluate tile it from shared memory and compact the surviving values, tile-local offsets and
+//     string bytes into OUTPUT stage it&1; warp 0 publishes the tile's aggregate at once;
+//   * a ninth warp runs the two-level look-back of the tiles one after the other;
+//   * the data warps store output stage (it-1)&1 — whose prefix the ninth warp has resolved meanwhile — with coalesced
+//     stores, then go on to tile it+1.  The look-back latency of a tile overlaps the count phase of the next one.
+// Measured on B200, 2^24 rows of config 2 (profiles/r2_filter_variants.txt, ARK_FP_IMPL=3): 0.147-0.148 ms against 0.1505 ms for
+// the one-tile-per-CTA kernel; 0.138 ms with the look-back stubbed out — the wait is hidden (0.010 ms left of 0.038), but
+// with two CTAs of nine warps per SM the serial chain of a tile (wait for the stage, LDS, ballots, barrier, STS, barrier,
+// stores, barrier) is exposed and the data path itself is slower than the other kernel's (0.113 ms).  512-row tiles and four
+// CTAs per SM: same data path (0.136), more descriptors (0.168-0.182).  Kept selectable, not the default: 2 % is within what
+// the input's shape (two fixed-width outputs: 0.189 ms) takes back.
+// ================================================================================================
+constexpr int ring_pred_bytes(int tt) { return tt * 8 + 32; }
+constexpr int ring_offs_bytes(int tt) { return ((tt + 1) * 4 + 32 + 15) / 16 * 16; }   // (tt + 1) offsets + alignment hull
+// DT data threads, DT * 4 rows per tile: 256 (two CTAs per SM) or 128 (four: more independent tile chains per SM)
+template <int NF, int NFX, int DT>
+__global__ void __launch_bounds__(DT + 32) filter_project_ring_kernel(const __grid_constant__ TmaParams P) {
+  constexpr int TT = DT * 4, T_THREADS = DT, T_WARPS = DT / 32, LB_WARP = T_WARPS;
+  constexpr int RING_PRED_BYTES = ring_pred_bytes(TT), RING_OFFS_BYTES = ring_offs_bytes(TT);
+  extern __shared__ __align__(16) uint8_t smem[];
+  // Two input and two output stages.  Measured alternative: three input stages and ONE output stage (the store of tile k-1
+  // between the count and the compaction of tile k): 0.156 ms instead of 0.148 — the longer serial chain per tile costs more
+  // than the third tile in flight brings.
+  constexpr int IN_STAGES = 2;
+  __shared__ __align__(8) unsigned long long s_full[IN_STAGES], s_agg[2], s_res[2];
+  __shared__ int s_shift[IN_STAGES][2 + (NFX > 0 ? NFX : 1)];
+  __shared__ int s_str_base[IN_STAGES], s_str_staged[IN_STAGES];
+  __shared__ int s_cnt[2][T_WARPS], s_bytes[2][T_WARPS];
+  __shared__ int s_tot[2][2];
+  __shared__ long long s_excl[2][2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_tiles = P.n_tiles;
+  const int str_stage = P.str_cap + 32;
+  const int in_bytes_per = RING_PRED_BYTES + RING_OFFS_BYTES + NFX * RING_PRED_BYTES + str_stage;
+  const int out_bytes_per = NF * TT * 8 + (TT * 4 + 16) + str_stage;
+  uint8_t* const in_base = smem;
+  uint8_t* const out_base = smem + IN_STAGES * in_bytes_per;
+  auto tile_of = [&](int it) { return (int)blockIdx.x + it * (int)gridDim.x; };
+  auto tile_rows = [&](int t) { const int64_t r = P.n_rows - (int64_t)t * TT; return (int)(r < TT ? r : TT); };
+  // fixed-width inputs that are not the predicate column, in the order of the outputs that use them
+  const unsigned long long* fx_src[NFX > 0 ? NFX : 1];
+  {
+    int k = 0;
+#pragma unroll
+    for (int c = 0; c < NF; ++c) if (!((P.fixed_is_pred >> c) & 1) && k < NFX) fx_src[k++] = P.fixed_in[c];
+    if (NFX == 0) fx_src[0] = nullptr;
+  }
+  // producer: every bulk copy of tile t into input stage st; (o0, o1) = the tile's bounding string offsets
+  auto issue_tile = [&](int st, int t, int32_t o0, int32_t o1) {
+    const int rows = tile_rows(t);
+    uint8_t* stage = in_base + (size_t)st * in_bytes_per;
+    const int64_t r0 = (int64_t)t * TT;
+    uintptr_t lo[4 + NFX], hi[4 + NFX];
+    unsigned total = 0;
+    {
+      const uintptr_t a0 = reinterpret_cast<uintptr_t>(P.pred_in + r0), a1 = a0 + (uintptr_t)rows * 8;
+      lo[0] = a0 & ~(uintptr_t)15; hi[0] = (a1 + 15) & ~(uintptr_t)15; s_shift[st][0] = (int)(a0 - lo[0]);
+    }
+    {
+      const uintptr_t a0 = reinterpret_cast<uintptr_t>(P.offsets_in + r0), a1 = a0 + (uintptr_t)(rows + 1) * 4;
+      lo[1] = a0 & ~(uintptr_t)15; hi[1] = (a1 + 15) & ~(uintptr_t)15; s_shift[st][1] = (int)(a0 - lo[1]);
+    }
+#pragma unroll
+    for (int k = 0; k < NFX; ++k) {
+      const uintptr_t a0 = reinterpret_cast<uintptr_t>(fx_src[k] + r0), a1 = a0 + (uintptr_t)rows * 8;
+      lo[2 + k] = a0 & ~(uintptr_t)15; hi[2 + k] = (a1 + 15) & ~(uintptr_t)15; s_shift[st][2 + k] = (int)(a0 - lo[2 + k]);
+    }
+    const uintptr_t s0 = reinterpret_cast<uintptr_t>(P.data_in + o0), s1 = reinterpret_cast<uintptr_t>(P.data_in + o1);
+    const uintptr_t slo = s0 & ~(uintptr_t)15, shi = (s1 + 15) & ~(uintptr_t)15;
+    const int staged = (o1 > o0 && shi - slo <= (uintptr_t)P.str_cap) ? 1 : 0;
+    s_str_base[st] = o0 - (int32_t)(s0 - slo); s_str_staged[st] = staged;
+    for (int k = 0; k < 2 + NFX; ++k) total += (unsigned)(hi[k] - lo[k]);
+    if (staged) total += (unsigned)(shi - slo);
+    mbar_expect_tx(&s_full[st], total);
+    tma_load_1d(stage, reinterpret_cast<const void*>(lo[0]), (unsigned)(hi[0] - lo[0]), &s_full[st]);
+    tma_load_1d(stage + RING_PRED_BYTES, reinterpret_cast<const void*>(lo[1]), (unsigned)(hi[1] - lo[1]), &s_full[st]);
+#pragma unroll
+    for (int k = 0; k < NFX; ++k)
+      tma_load_1d(stage + RING_PRED_BYTES + RING_OFFS_BYTES + k * RING_PRED_BYTES, reinterpret_cast<const void*>(lo[2 + k]), (unsigned)(hi[2 + k] - lo[2 + k]), &s_full[st]);
+    if (staged) tma_load_1d(stage + RING_PRED_BYTES + RING_OFFS_BYTES + NFX * RING_PRED_BYTES, reinterpret_cast<const void*>(slo), (unsigned)(shi - slo), &s_full[st]);
+  };
+  auto bounds_of = [&](int t, int32_t* o0, int32_t* o1) {
+    const int64_t r0 = (int64_t)t * TT;
+    *o0 = P.offsets_in[r0]; *o1 = P.offsets_in[r0 + tile_rows(t)];
+  };
+
+  int32_t no0 = 0, no1 = 0;  // producer: bounds of the tile it will issue next
+  if (tid == 0) {
+    for (int k = 0; k < IN_STAGES; ++k) mbar_init(&s_full[k], 1);
+    for (int k = 0; k < 2; ++k) { mbar_init(&s_agg[k], 1); mbar_init(&s_res[k], 1); }
+    mbar_fence_init();
+    for (int k = 0; k < IN_STAGES; ++k)
+      if (tile_of(k) < n_tiles) { int32_t o0, o1; bounds_of(tile_of(k), &o0, &o1); issue_tile(k, tile_of(k), o0, o1); }
+    if (tile_of(IN_STAGES) < n_tiles) bounds_of(tile_of(IN_STAGES), &no0, &no1);
+  }
+  __syncthreads();
+
+  if (warp == LB_WARP) {  // ---- look-back of this CTA's tiles, one after the other ----
+    for (int it = 0; tile_of(it) < n_tiles; ++it) {
+      const int st = it & 1, tile = tile_of(it);
+      mbar_wait(&s_agg[st], (it >> 1) & 1);
+      const long long tile_cnt = s_tot[st][0], tb = s_tot[st][1];
+      long long ex0, ex1;
+      if (P.debug & 1) { ex0 = (long long)tile * (TT / 2); ex1 = ex0 * 12; }
+      else lookback_two_level<true, TT>(P, tile, tile_cnt, tb, lane, &ex0, &ex1);
+      if (lane == 0) { s_excl[st][0] = ex0; s_excl[st][1] = ex1; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_res[st]);
+    }
+    return;
+  }
+
+  const int wrow0 = warp * 128;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  // store of the tile whose outputs sit in output stage pst
+  auto store_tile = [&](int pit) {
+    const int pst = pit & 1, tile = tile_of(pit);
+    uint8_t* ostage = out_base + (size_t)pst * out_bytes_per;
+    mbar_wait(&s_res[pst], (pit >> 1) & 1);
+    const long long base_cnt = s_excl[pst][0], bb = s_excl[pst][1];
+    const int cnt = s_tot[pst][0], tb = s_tot[pst][1];
+    const int32_t* ooff = reinterpret_cast<const int32_t*>(ostage + NF * TT * 8);
+    const uint8_t* ostr = ostage + NF * TT * 8 + TT * 4 + 16;
+#pragma unroll
+    for (int c = 0; c < NF; ++c) {
+      const unsigned long long* of = reinterpret_cast<const unsigned long long*>(ostage + c * TT * 8);
+      unsigned long long* g = P.fixed_out[c] + base_cnt;
+      for (int i = tid; i < cnt; i += T_THREADS) g[i] = of[i];
+    }
+    for (int i = tid; i < cnt; i += T_THREADS) P.offsets_out[base_cnt + i] = (int32_t)(bb + ooff[i]);
+    if (tile == n_tiles - 1 && tid == 0) { P.totals[0] = base_cnt + cnt; P.totals[1] = bb + tb; P.offsets_out[base_cnt + cnt] = (int32_t)(bb + tb); }
+    if (ooff[TT]) {  // staged flag, kept behind the offsets
+      uint8_t* gdst = P.data_out + bb;
+      const int head = (int)((16 - (bb & 15)) & 15) < tb ? (int)((16 - (bb & 15)) & 15) : tb;
+      if (tid < head) gdst[tid] = ostr[tid];
+      const int body = (tb - head) >> 4;
+      const unsigned* sw = reinterpret_cast<const unsigned*>(ostr + (head & ~3));
+      const unsigned sh = (head & 3) * 8;
+      for (int g = tid; g < body; g += T_THREADS) {
+        const unsigned* w = sw + g * 4;
+        uint4 v;
+        if (sh == 0) { v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3]; }
+        else {
+          const unsigned a = w[0], b = w[1], c = w[2], d = w[3], e = w[4];
+          v.x = __funnelshift_r(a, b, sh); v.y = __funnelshift_r(b, c, sh); v.z = __funnelshift_r(c, d, sh); v.w = __funnelshift_r(d, e, sh);
+        }
+        *reinterpret_cast<uint4*>(gdst + head + g * 16) = v;
+      }
+      const int done = head + body * 16;
+      if (tid < tb - done) gdst[done + tid] = ostr[done + tid];
+    } else {  // strings too long for the stage: the string region holds the source offset of every surviving row
+      const int32_t* osrc = reinterpret_cast<const int32_t*>(ostr);
+      for (int i = tid; i < cnt; i += T_THREADS) {
+        const int len = (i + 1 < cnt ? ooff[i + 1] : tb) - ooff[i];
+        const uint8_t* src = P.data_in + osrc[i];
+        uint8_t* dst = P.data_out + bb + ooff[i];
+        for (int b = 0; b < len; ++b) dst[b] = src[b];
+      }
+    }
+  };
+
+  int it = 0;
+  for (; tile_of(it) < n_tiles; ++it) {
+    const int st = it & 1, ist = it % IN_STAGES, tile = tile_of(it);
+    const int rows = tile_rows(tile);
+    const uint8_t* istage = in_base + (size_t)ist * in_bytes_per;
+    uint8_t* ostage = out_base + (size_t)st * out_bytes_per;
+    mbar_wait(&s_full[ist], (it / IN_STAGES) & 1);
+    const unsigned long long* spred = reinterpret_cast<const unsigned long long*>(istage + s_shift[ist][0]);
+    const int32_t* soff = reinterpret_cast<const int32_t*>(istage + RING_PRED_BYTES + s_shift[ist][1]);
+    const bool staged = s_str_staged[ist];
+    const uint8_t* sstr = istage + RING_PRED_BYTES + RING_OFFS_BYTES + NFX * RING_PRED_BYTES;
+    const int str_base = s_str_base[ist];
+    // ---- predicate, ranks, byte positions (rows striped over the warp) ----
+    unsigned long long pv[4];
+    int off[4], len[4];
+    unsigned flags = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = wrow0 + 32 * j + lane;
+      const bool in = r < rows;
+      pv[j] = in ? spred[r] : 0ull;
+      off[j] = in ? soff[r] : 0;
+      len[j] = in ? soff[r + 1] - off[j] : 0;
+      const long long key = P.sp_is_f64 ? f64_total_key(pv[j]) : (long long)pv[j];
+      bool f = (unsigned long long)(key - P.range_lo) <= P.range_span;
+      f = (f != (bool)P.negate) && in;
+      flags |= (unsigned)f << j;
+    }
+    int wpos[4], warp_cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned m = __ballot_sync(0xffffffffu, (flags >> j) & 1);
+      wpos[j] = warp_cnt + __popc(m & lt_mask);
+      warp_cnt += __popc(m);
+    }
+    int bpos[4] = {0, 0, 0, 0}, warp_bytes = 0;
+    {
+      const int len0 = __shfl_sync(0xffffffffu, len[0], 0);
+      const bool same = (len[0] == len0 || wrow0 + lane >= rows) && (len[1] == len0 || wrow0 + 32 + lane >= rows) &&
+                        (len[2] == len0 || wrow0 + 64 + lane >= rows) && (len[3] == len0 || wrow0 + 96 + lane >= rows);
+      if (__all_sync(0xffffffffu, same)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bpos[j] = wpos[j] * len0;
+        warp_bytes = warp_cnt * len0;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int sl = ((flags >> j) & 1) ? len[j] : 0;
+          const int incl = warp_incl_scan(sl, lane);
+          bpos[j] = warp_bytes + incl - sl;
+          warp_bytes += __shfl_sync(0xffffffffu, incl, 31);
+        }
+      }
+    }
+    if (lane == 0) { s_cnt[st][warp] = warp_cnt; s_bytes[st][warp] = warp_bytes; }
+    bar_sync(1, T_THREADS);  // (A')
+    int w_cnt_excl, w_bytes_excl, tile_cnt, tb;
+    {
+      const int c = lane < T_WARPS ? s_cnt[st][lane] : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < T_WARPS; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      w_cnt_excl = __shfl_sync(0xffffffffu, incl - c, warp);
+      tile_cnt = __shfl_sync(0xffffffffu, incl, T_WARPS - 1);
+      const int b = lane < T_WARPS ? s_bytes[st][lane] : 0;
+      int bi = b;
+#pragma unroll
+      for (int o = 1; o < T_WARPS; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, bi, o); if (lane >= o) bi += t; }
+      w_bytes_excl = __shfl_sync(0xffffffffu, bi - b, warp);
+      tb = __shfl_sync(0xffffffffu, bi, T_WARPS - 1);
+    }
+    if (tid == 0) {  // the aggregate is public before anything else happens to this tile
+      st_volatile_u64(P.desc + (size_t)tile * P.desc_stride, desc_pack(tile == 0 ? DESC_PREFIX : DESC_AGG, tile_cnt, tb));
+      s_tot[st][0] = tile_cnt; s_tot[st][1] = tb;
+      mbar_arrive(&s_agg[st]);
+    }
+    // ---- compaction into output stage st at tile-local positions ----
+    int32_t* ooff = reinterpret_cast<int32_t*>(ostage + NF * TT * 8);
+    uint8_t* ostr = ostage + NF * TT * 8 + TT * 4 + 16;
+    if (tid == 0) ooff[TT] = staged ? 1 : 0;
+    {
+      int kx = 0;
+#pragma unroll
+      for (int c = 0; c < NF; ++c) {
+        unsigned long long* of = reinterpret_cast<unsigned long long*>(ostage + c * TT * 8);
+        const bool is_pred = (P.fixed_is_pred >> c) & 1;
+        const unsigned long long* sfx = nullptr;
+        if (!is_pred && NFX > 0) { sfx = reinterpret_cast<const unsigned long long*>(istage + RING_PRED_BYTES + RING_OFFS_BYTES + kx * RING_PRED_BYTES + s_shift[ist][2 + (kx < NFX ? kx : 0)]); ++kx; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if ((flags >> j) & 1) of[w_cnt_excl + wpos[j]] = is_pred ? pv[j] : sfx[wrow0 + 32 * j + lane];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!((flags >> j) & 1)) continue;
+      ooff[w_cnt_excl + wpos[j]] = w_bytes_excl + bpos[j];
+      if (staged) smem_copy(ostr + w_bytes_excl + bpos[j], sstr + (off[j] - str_base), len[j]);
+      else reinterpret_cast<int32_t*>(ostr)[w_cnt_excl + wpos[j]] = off[j];
+    }
+    bar_sync(1, T_THREADS);  // (A): input stage ist is consumed, the output stage is complete
+    if (tid == 0) {
+      const int t2 = tile_of(it + IN_STAGES);
+      if (t2 < n_tiles) issue_tile(ist, t2, no0, no1);
+      const int t3 = tile_of(it + IN_STAGES + 1);
+      if (t3 < n_tiles) bounds_of(t3, &no0, &no1);
+    }
+    // ---- the previous tile's outputs leave now: its prefix was resolved while this tile was counted ----
+    if (it > 0) store_tile(it - 1);
+    bar_sync(2, T_THREADS);  // (B): output stage (it-1)&1 may be overwritten by tile it+1
+  }
+  if (it > 0) store_tile(it - 1);
+}
+
 }  // namespace
 
 static std::atomic<double> g_avg_len_hint{12.8};
 void filter_project_tma_note_avg_len(double avg) { if (avg > 0) g_avg_len_hint.store(avg); }
-static int g_fp_threads = [] { const char* e = getenv("ARK_FP_THREADS"); return e && atoi(e) == 512 ? 512 : 256; }();
+static int g_fp_threads = [] { const char* e = getenv("ARK_FP_THREADS"); const int v = e ? atoi(e) : 256; return v == 512 || v == 128 ? v : 256; }();
 static int g_desc_stride = [] { const char* e = getenv("ARK_FP_DESC_STRIDE"); int v = e ? atoi(e) : 4; return v >= 1 && v <= 16 ? v : 4; }();  // one descriptor per 32-byte sector
 int filter_project_tma_tile_rows() { return g_fp_threads * 4; }
 int filter_project_tma_desc_stride() { return g_desc_stride; }
@@ -1075,7 +1359,7 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
     double avg = n_rows > 0 && data_bytes >= 0 ? (double)data_bytes / (double)n_rows : g_avg_len_hint.load();
     static const double slack = [] { const char* e = getenv("ARK_FP_CAP_SLACK"); return e ? atof(e) : 1.0625; }();
     cap = (int)round_up((int64_t)(avg * TT * slack) + 64, 1024);
-    cap = std::max(4096, std::min(cap, (TT / 1024) * 24 * 1024));
+    cap = std::max(TT >= 1024 ? 4096 : 2048, std::min(cap, std::max(TT / 1024, 1) * 24 * 1024));
   }
   P.str_cap = cap;
   P.desc_stride = g_desc_stride;
@@ -1083,7 +1367,44 @@ bool launch_filter_project_tma(int64_t n_rows, const void* pred_in, int n_fixed_
   // implementation: 2 = striped rows, one ticketed tile per CTA (default); 0 = persistent pipelined striped kernel;
   // 1 = the r1 kernel (blocked rows, tile = blockIdx).  0 and 1 are kept for A/B runs.
   static const int impl = [] { const char* e = getenv("ARK_FP_IMPL"); return e ? atoi(e) : 2; }();
-  if (impl == 2 && ticket != nullptr) {
+  if (g_fp_threads == 128 && (impl != 3 || !v)) return false;  // 512-row tiles: the ring kernel only
+  if (impl == 3 && v && ticket != nullptr && g_fp_threads <= 256) {
+    int nfx = 0;
+    for (int c = 0; c < n_fixed_out; ++c) if (!((P.fixed_is_pred >> c) & 1)) ++nfx;
+    const int dt = g_fp_threads, tt = dt * 4;
+    const size_t in_per = (size_t)ring_pred_bytes(tt) + ring_offs_bytes(tt) + (size_t)nfx * ring_pred_bytes(tt) + (size_t)cap + 32;
+    const size_t out_per = (size_t)n_fixed_out * tt * 8 + tt * 4 + 16 + (size_t)cap + 32;
+    const size_t smem = 2 * in_per + 2 * out_per;
+    const void* fn = nullptr;
+#define ARK_RING_FN(NF, NFX) (dt == 128 ? (const void*)filter_project_ring_kernel<NF, NFX, 128> : (const void*)filter_project_ring_kernel<NF, NFX, 256>)
+    if (n_fixed_out == 0) fn = ARK_RING_FN(0, 0);
+    else if (n_fixed_out == 1 && nfx == 0) fn = ARK_RING_FN(1, 0);
+    else if (n_fixed_out == 1 && nfx == 1) fn = ARK_RING_FN(1, 1);
+    else if (n_fixed_out == 2 && nfx == 1) fn = ARK_RING_FN(2, 1);
+    if (fn && smem <= 112 * 1024) {   // at least two CTAs per SM; otherwise the one-tile-per-CTA kernel below
+      static bool configured = false;
+      if (!configured) {
+        for (const void* f : {ARK_RING_FN(0, 0), ARK_RING_FN(1, 0), ARK_RING_FN(1, 1), ARK_RING_FN(2, 1)})
+          ARK_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        configured = true;
+      }
+#undef ARK_RING_FN
+      int occ = 0;
+      ARK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, dt + 32, smem));
+      if (occ >= 1) {
+        static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+        static const int cap_per_sm = [] { const char* e = getenv("ARK_FP_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+        if (cap_per_sm > 0) occ = std::min(occ, cap_per_sm);
+        const int grid = std::max(1, std::min(P.n_tiles, sms * occ));
+        KernelTimer t("filter_project_tma_kernel", stream);
+        void* args[] = {(void*)&P};
+        ARK_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(dt + 32), args, smem, stream));
+        return true;
+      }
+    }
+    if (dt == 128) return false;  // 512-row tiles exist for this kernel only
+  }
+  if ((impl == 2 || impl == 3) && ticket != nullptr) {
     static const bool use_ticket = [] { const char* e = getenv("ARK_FP_TICKET"); return e && atoi(e) != 0; }();
     if (!use_ticket) P.ticket = nullptr;
     const size_t smem = v ? 2 * (size_t)(cap + 32) : 0;

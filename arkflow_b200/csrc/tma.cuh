@@ -14,6 +14,11 @@ static __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.m
 static __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
+static __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+// named barrier over `count` threads of the CTA (a multiple of 32): the warps that do not take part keep running
+static __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 static __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"

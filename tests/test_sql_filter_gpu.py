@@ -188,6 +188,44 @@ print("HELP_OK")
     assert r.returncode == 0 and "HELP_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
 
+@pytest.mark.parametrize("env", [{"ARK_FP_IMPL": "3"}, {"ARK_FP_IMPL": "3", "ARK_FP_THREADS": "128"}, {"ARK_FP_IMPL": "3", "ARK_FP_DEBUG": "4"},
+                                 {"ARK_FP_IMPL": "1"}, {"ARK_FP_IMPL": "1", "ARK_FP_TICKET": "1", "ARK_FP_THREADS": "512"}, {"ARK_FP_THREADS": "512"}])
+def test_alternative_filter_kernels(gpu, env):
+    """The kernels kept next to the default for A/B runs — the persistent ring kernel (ARK_FP_IMPL=3: every input by TMA, store of
+    tile k after the count of tile k+1; also with 512-row tiles and with forced helping), the blocked-row kernel of round 1
+    (ARK_FP_IMPL=1, with and without a ticket) and 2048-row tiles — give the oracle's results too, ragged last tiles, long
+    strings (the unstaged path) and an empty result included.  Subprocess: the knobs are read once per process."""
+    import os
+    import subprocess
+    import sys
+
+    code = '''
+import sys
+sys.path.insert(0, %r)
+import pyarrow as pa
+from arkflow_b200 import _lib as L
+from arkflow_b200.processor import SqlProcessor, MessageBatch, _check
+from oracle.sql_oracle import sql_process
+from oracle.synth import synth_batch
+_check(L.lib().ark_b200_init(0))
+cases = [(300_000, "SELECT sensor, value FROM flow WHERE value >= 10"), (257_123, "SELECT timestamp, value, sensor FROM flow WHERE value < 7"),
+         (99_999, "SELECT sensor FROM flow WHERE value <> 3"), (1, "SELECT sensor, value FROM flow WHERE value >= 0"),
+         (5_000, "SELECT sensor, value FROM flow WHERE value > 1000"), (1_000_003, "SELECT sensor, timestamp FROM flow WHERE value >= 19")]
+for n, q in cases:
+    rb = synth_batch(n, key_space=1000)
+    got = SqlProcessor({"query": q}).process(MessageBatch.new_arrow(rb)).batches[0].record_batch
+    assert got.equals(sql_process(rb, q)), q
+long_rb = pa.record_batch({"value": pa.array([i %% 20 for i in range(40_000)], pa.int64()),
+                           "sensor": pa.array([("x" * (300 if 20_000 <= i < 21_500 else i %% 9)) + str(i) for i in range(40_000)])})  # a few tiles exceed the staging window
+q = "SELECT sensor, value FROM flow WHERE value >= 10"
+got = SqlProcessor({"query": q}).process(MessageBatch.new_arrow(long_rb)).batches[0].record_batch
+assert got.equals(sql_process(long_rb, q)), "long strings"
+print("ALT_OK")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, **env))
+    assert r.returncode == 0 and "ALT_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
 def test_min_over_minus_one_overflows_for_div_and_mod(gpu):
     """arrow-arith div_checked / mod_checked: i64::MIN / -1 and i64::MIN % -1 are ArithmeticOverflow errors, with arrow's text."""
     rb = pa.record_batch({"a": pa.array([5, -(2 ** 63), 7], pa.int64()), "b": pa.array([1, -1, 2], pa.int64())})
