@@ -797,6 +797,11 @@ __global__ void __launch_bounds__(256, MINB) filter_project_pipe_kernel(const __
 //     32 registers spill (0.154 ms).  2048-row tiles (DT = 512) 0.158 ms; a ticket instead of blockIdx 0.166 ms; one chain
 //     of tile descriptors instead of the two levels 0.172 ms; the persistent pipelined kernel above 0.26 ms (its CTAs wait
 //     for each other in a convoy); the blocked-row kernel of round 1: 0.152 ms (1024-row tiles), 0.145 ms (2048-row).
+//   * tried against that wait and dropped (profiles/r2_filter_variants.txt, r3a-r3e): "scout" CTAs that compute the aggregates
+//     of a whole group of 32 tiles ahead of the tiles' own CTAs (0.19-0.21 ms: one CTA cannot stream 393 KB fast enough to
+//     stay ahead); the look-back warp of every CTA computing the aggregate of the tile 64-2048 tiles ahead from a bulk
+//     copy of its predicate column and offsets, before barrier (1) (0.183 ms: it makes the CTA late) or after barrier (2)
+//     (0.165-0.18 ms; DRAM traffic unchanged — the second read hits L2 — but +55 % L2 read sectors and a lingering warp).
 //   * forward progress does not depend on CTA dispatch order: see help_publish_aggregate / help_publish_group.
 // ================================================================================================
 // MAXR: register cap (__maxnreg__): CTAs per SM follow from it — ptxas rounds a 288- / 544-thread CTA up when it derives
