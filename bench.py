@@ -213,7 +213,7 @@ def numa_bind(gpu_index):
 
 class ClockSampler:
     def __init__(self, gpu_index):
-        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+        self.gpu_index, self.proc, self.lines, self.first = gpu_index, None, [], 0
 
     def start(self):
         if os.environ.get("ARK_BENCH_NO_SAMPLER"):
@@ -232,6 +232,16 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def wait_ready(self, timeout=8.0):
+        """nvidia-smi's start-up (NVML initialisation over every GPU of the box, by every rank at once) disturbs running work for
+        a moment: it is started before the warm-up and the timed region begins only once it delivers samples."""
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark(self):
+        self.first = len(self.lines)  # samples from here on were taken under load
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -242,7 +252,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -352,13 +362,16 @@ def run_b200(args):
             out.close()
         return rows
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()  # the communicator is created here, not at the edge of the timed region
     for i in range(args.warmup):
         device_step(i)
-    sampler = ClockSampler(local_rank)
+    sampler.wait_ready()
     lib.ark_kernel_timing_reset()
     lib.ark_kernel_timing_enable(1)
     barrier()
-    sampler.start()
+    sampler.mark()
     launches0 = lib.ark_kernel_launch_count()
     keep = [args.steps - 1]  # the LAST timed output is kept for verification
     ev0.record()
