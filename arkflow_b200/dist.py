@@ -357,7 +357,9 @@ def distributed_group_by(engine, local_batch: DeviceBatch, group=None, p2p: Opti
     partial, part_rows = engine.partial_aggregate(local_batch, world)
     keyless = not partial.columns or partial.columns[0].name.startswith("__acc")
     received = _exchange(partial, part_rows, group, p2p)
+    partial.close()
     result = engine.final_aggregate(received)
+    received.close()
     if keyless and dist.get_rank(group) != 0:
         # a global aggregate has one group, owned by rank 0; other ranks merged nothing
         result = DeviceBatch([DeviceColumn(c.name, c.dtype, 0, c.data[:0], None if c.offsets is None else c.offsets[:1], None, 0, c.nullable)
@@ -374,4 +376,11 @@ def distributed_join(engine, tables: dict, keys: dict, group=None, p2p: Optional
     for name, batch in tables.items():
         parted, rows = engine.hash_partition(batch, keys[name], world)
         local[name] = _exchange(parted, rows, group, p2p)
-    return engine.join(local)
+        # released here, not whenever the garbage collector gets to it: the arena the partition was published from is
+        # reusable as soon as its buffers are gone, and a rank that publishes from a NEW arena costs every peer a
+        # cudaIpcOpenMemHandle (the exchange has ended with a barrier: no peer reads it any more)
+        parted.close()
+    out = engine.join(local)
+    for b in local.values():
+        b.close()
+    return out
