@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2: full GPU test suite, bench (both arms), ncu launch list and full captures of the two headline kernels
 set -u
-OUT=gpurun_out/r2o
+OUT=gpurun_out/r3f
 mkdir -p $OUT
 timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest.log
 tail -4 $OUT/pytest.log
@@ -10,6 +10,6 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_r
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
 FQ="SELECT sensor, value FROM flow WHERE value >= 10"
 GQ="SELECT sensor, SUM(value), COUNT(*) FROM flow GROUP BY sensor"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:filter_project_tile -s 6 -c 2 -o $OUT/fp_tile python scripts/prof_query.py "$FQ" 16777216 1000000 4 0 3 > $OUT/ncu_fp.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:hash_agg_staged -s 6 -c 2 -o $OUT/agg_staged python scripts/prof_query.py "$GQ" 16777216 1000000 4 0 3 > $OUT/ncu_agg.log 2>&1
+
+
 ls -la $OUT
