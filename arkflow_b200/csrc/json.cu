@@ -276,6 +276,45 @@ __device__ int decoded_len(const uint8_t* b, int raw) {
   return n;
 }
 
+// does the JSON string body b[0..raw) (which contains escapes) decode to exactly nm[0..nlen)?  Malformed escapes: no.
+__device__ bool decoded_equals(const uint8_t* b, int raw, const char* nm, int nlen) {
+  int n = 0;
+  for (int i = 0; i < raw;) {
+    uint8_t out[4];
+    int k = 0;
+    if (b[i] != '\\') { out[k++] = b[i++]; }
+    else {
+      if (i + 1 >= raw) return false;
+      const uint8_t e = b[i + 1];
+      if (e == 'u') {
+        if (i + 6 > raw) return false;
+        auto hex4 = [&](int at, unsigned* cp) { unsigned v = 0; for (int q = 0; q < 4; ++q) { const uint8_t h = b[at + q];
+          const unsigned d = h >= '0' && h <= '9' ? h - '0' : h >= 'a' && h <= 'f' ? h - 'a' + 10 : h >= 'A' && h <= 'F' ? h - 'A' + 10 : 99; if (d == 99) return false; v = v * 16 + d; } *cp = v; return true; };
+        unsigned cp;
+        if (!hex4(i + 2, &cp)) return false;
+        i += 6;
+        if (cp >= 0xD800 && cp < 0xDC00) {
+          unsigned lo;
+          if (i + 6 > raw || b[i] != '\\' || b[i + 1] != 'u' || !hex4(i + 2, &lo)) return false;
+          i += 6;
+          cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+        }
+        if (cp < 0x80) out[k++] = (uint8_t)cp;
+        else if (cp < 0x800) { out[k++] = 0xC0 | (cp >> 6); out[k++] = 0x80 | (cp & 0x3F); }
+        else if (cp < 0x10000) { out[k++] = 0xE0 | (cp >> 12); out[k++] = 0x80 | ((cp >> 6) & 0x3F); out[k++] = 0x80 | (cp & 0x3F); }
+        else { out[k++] = 0xF0 | (cp >> 18); out[k++] = 0x80 | ((cp >> 12) & 0x3F); out[k++] = 0x80 | ((cp >> 6) & 0x3F); out[k++] = 0x80 | (cp & 0x3F); }
+      } else {
+        uint8_t ch = e;
+        if (e == 'b') ch = '\b'; else if (e == 'f') ch = '\f'; else if (e == 'n') ch = '\n'; else if (e == 'r') ch = '\r'; else if (e == 't') ch = '\t';
+        else if (e != '"' && e != '\\' && e != '/') return false;
+        out[k++] = ch; i += 2;
+      }
+    }
+    for (int q = 0; q < k; ++q) { if (n >= nlen || (uint8_t)nm[n] != out[q]) return false; ++n; }
+  }
+  return n == nlen;
+}
+
 __device__ void decode_string(const uint8_t* b, int raw, uint8_t* out) {
   for (int i = 0; i < raw;) {
     if (b[i] != '\\') { *out++ = b[i++]; continue; }
@@ -390,6 +429,11 @@ __global__ void __launch_bounds__(JS_THREADS) json_parse_kernel(const __grid_con
           if (eq) { f = k; break; }
         }
         if (f >= 0) next_field = f + 1 == P.n_fields ? 0 : f + 1;
+      } else {  // a key written with escapes ("val\u0075e"): compared after decoding, as arrow-json's tape decoder does
+        for (int k = 0; k < P.n_fields; ++k) {
+          const char* nm = FT[k].long_name ? FT[k].long_name : FT[k].name;
+          if (decoded_equals(kb, kl, nm, FT[k].name_len)) { f = k; break; }
+        }
       }
       if (f < 0) { if (!skip_value(c, 0)) { raise(P, JE_SYNTAX, i); return; } continue; }
       const JsonField& F = FT[f];

@@ -169,6 +169,22 @@ def test_wide_records_and_long_field_names(gpu):
     assert e.value.kind == "Unsupported"
 
 
+def test_keys_written_with_escapes(gpu):
+    """A record may spell a key with escapes ("val\\u0075e", "sens\\/or" …): arrow-json's tape decoder compares decoded names, so
+    such a key fills its column like any other (they used to be treated as unknown keys and dropped)."""
+    payloads = [
+        b'{"value": 1, "sensor": "a", "t/s": 5, "\\u00e9t\\u00e9": 7}',
+        b'{"val\\u0075e": 2, "sens\\u006fr": "b", "t\\/s": 6, "\\u00e9t\\u00E9": 8}',
+        b'{"\\u0076alue": 3, "sensor": "c", "val\\u0075": 99, "\\ud83d\\ude00": 1}',   # unknown escaped keys are skipped
+        b'{"valu\\u0065": "4", "t\\u002fs": null}',
+    ]
+    out = check(payloads)
+    assert out.column("value").to_pylist() == [1, 2, 3, 4]
+    assert out.column("sensor").to_pylist() == ["a", "b", "c", None]
+    assert out.column("t/s").to_pylist() == [5, 6, None, None]
+    assert out.column("\u00e9t\u00e9").to_pylist() == [7, 8, None, None]
+
+
 def test_non_strict_decoding(gpu):
     payloads = [
         b'{"timestamp": 1, "value": 10, "sensor": "a", "flag": true}',

@@ -192,6 +192,21 @@ def test_long_and_ragged_string_keys(gpu):
     check_agg(rbb, "SELECT sensor, SUM(value), COUNT(*) FROM flow GROUP BY sensor", ["sensor"])
 
 
+def test_low_cardinality_key_lengths_change_by_region(gpu):
+    """the per-CTA-table kernel stages a tile's key bytes only when they fit its window, and its mbarrier
+    phase must advance only for staged tiles.  > 1M rows so that every CTA takes several tiles; short keys, then a region of
+    ~48-byte keys that exceed the window sized from the batch average, then short keys again; also an all-empty-key region."""
+    n = 1_400_000
+    idx = np.arange(n)
+    region = (idx // 100_000) % 7
+    keys = np.where(region == 2, np.char.add("k" * 47, (idx % 5).astype(str)),
+           np.where(region == 4, "", np.where(region == 5, np.char.add("a_key_of_25_bytes_exactly_", (idx % 3).astype(str)), np.char.add("s", (idx % 6).astype(str)))))
+    rng = np.random.default_rng(5)
+    rb = pa.record_batch({"sensor": pa.array(keys.tolist()), "value": pa.array(rng.integers(-50, 50, n), pa.int64())})
+    for _ in range(2):  # the second call reuses the hints of the first (table size, window)
+        check_agg(rb, "SELECT sensor, SUM(value), COUNT(*), MIN(value) FROM flow GROUP BY sensor", ["sensor"])
+
+
 def test_computed_aggregate_arguments(gpu):
     rb = synth_batch(100_000, key_space=50)
     check_agg(rb, "SELECT sensor, SUM(value * 2 + 1), AVG(value + 0.5), COUNT(*) FROM flow WHERE value >= 3 GROUP BY sensor", ["sensor"],
