@@ -74,6 +74,48 @@ def test_inner_join_matches_acero():
     assert key(got) == key(want)  # NULL keys never match, on either side
 
 
+@pytest.mark.parametrize("kind,acero", [("LEFT", "left outer"), ("RIGHT", "right outer"), ("LEFT OUTER", "left outer")])
+def test_outer_joins_match_acero(kind, acero):
+    """LEFT / RIGHT [OUTER] JOIN of the oracle against Acero: unmatched rows of the preserved side come out once with NULLs
+    on the other side, NULL keys never match (but are preserved), duplicate build keys multiply rows."""
+    left = batch(41, n=2000, keys=40)
+    rng = np.random.default_rng(42)
+    rk = [f"key_{i:03d}" for i in range(10, 70, 3)] + [None, "key_013", "key_013"]
+    right = pa.record_batch({"k": pa.array(rk), "z": pa.array(rng.integers(0, 9, len(rk)), pa.int64())})
+    got = sql_join({"a": left, "b": right}, f"SELECT a.k, v, z FROM a {kind} JOIN b ON a.k = b.k")
+    lt, rt = pa.Table.from_batches([left]), pa.Table.from_batches([right])
+    want = lt.join(rt, keys="k", join_type=acero, coalesce_keys=False, right_suffix="_r").select(["k", "v", "z"])  # a.k as it is on the left side
+    key = lambda tbl: sorted(map(repr, zip(*[tbl.column(i).to_pylist() for i in range(3)])))
+    assert key(got) == key(want)
+
+
+def test_nested_json_matches_arrow_json_reader():
+    """List<scalar> and Struct columns of the oracle's optional nested decoding against Arrow C++'s JSON reader on records whose
+    every row has the first record's shape (where first-record inference and whole-file inference agree)."""
+    import io
+    import json
+
+    import pyarrow.json as pj
+
+    import oracle.json_oracle as jo
+    from arkflow_b200.processor import MessageBatch
+
+    rng = np.random.default_rng(9)
+    recs = [{"id": i, "tags": ["t%d" % int(x) for x in rng.integers(0, 5, int(rng.integers(1, 4)))], "nums": [int(x) for x in rng.integers(-9, 9, 3)],
+             "pos": {"x": float(i) / 4, "y": int(i % 7), "label": "p%d" % i}} for i in range(300)]
+    payloads = [json.dumps(r).encode() for r in recs]
+    prev = jo.NESTED
+    jo.NESTED = True
+    try:
+        got = jo.json_to_arrow(MessageBatch.new_binary(payloads).record_batch)
+    finally:
+        jo.NESTED = prev
+    want = pj.read_json(io.BytesIO(b"\n".join(payloads)))
+    assert got.schema.names == want.schema.names
+    for name in want.schema.names:
+        assert got.column(name).to_pylist() == want[name].to_pylist(), name
+
+
 def test_json_decode_matches_arrow_json_reader():
     # uniform scalar records: arrow-json (first-record inference) and Arrow C++'s reader must decode the same values
     import io
