@@ -128,6 +128,7 @@ def _declare(lib):
         "ark_kernel_timing_enable": (None, [C.c_int]),
         "ark_kernel_timing_reset": (None, []),
         "ark_kernel_timing_get": (C.c_int, [C.c_char_p, P(C.c_double), P(C.c_int64)]),
+        "ark_host_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     }
     missing = []
     for name, (res, args) in sig.items():

@@ -320,7 +320,7 @@ static bool format_supported(const std::string& f) {
 // 2 MB chunks into pinned slots (two per thread, from the pinned pool) and queues each chunk's H2D as soon as it is
 // filled, so host memcpy, PCIe transfer and — across concurrent callers — the kernels of other calls overlap.
 // Pinned or registered sources (cudaPointerGetAttributes ≠ unregistered) take the direct copy.
-void host_copy_stream(void* dst, const void* src, size_t n, int kind);  // host_copy.cpp
+int host_copy_stream(void* dst, const void* src, size_t n, int kind);  // host_copy.cpp
 
 namespace {
 

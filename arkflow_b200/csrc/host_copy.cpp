@@ -49,16 +49,22 @@ int detect() {
 }  // namespace
 
 // kind: 0 memcpy, 1 AVX2 non-temporal, 2 AVX-512 non-temporal, -1 best available (ARK_STAGE_COPY overrides in batch.cu)
-void host_copy_stream(void* dst, const void* src, size_t n, int kind) {
+int host_copy_stream(void* dst, const void* src, size_t n, int kind) {
   static const int best = detect();
   if (kind < 0 || kind > best) kind = best;
   char* dp = static_cast<char*>(dst);
   const char* sp = static_cast<const char*>(src);
-  if (kind == 0 || n < 4096) { memcpy(dp, sp, n); return; }
+  if (kind == 0 || n < 4096) { memcpy(dp, sp, n); return kind; }
   const size_t head = (64 - (reinterpret_cast<uintptr_t>(dp) & 63)) & 63;  // streaming stores want an aligned destination
   if (head) { memcpy(dp, sp, head); dp += head; sp += head; n -= head; }
   if (kind == 2) copy_nt512(dp, sp, n); else copy_nt256(dp, sp, n);
   _mm_sfence();  // the chunk is handed to the DMA engine next: the streaming stores must be globally visible
+  return kind;
 }
 
 }  // namespace ark
+
+extern "C" int ark_host_copy(void* dst, const void* src, int64_t n, int kind) {
+  if (!dst || !src || n < 0) return -1;
+  return ark::host_copy_stream(dst, src, (size_t)n, kind);
+}

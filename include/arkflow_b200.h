@@ -311,6 +311,11 @@ void ark_kernel_timing_enable(int on);
 void ark_kernel_timing_reset(void);
 int ark_kernel_timing_get(const char* name, double* total_ms, int64_t* launches);
 
+/* The host copy used to stage pageable input buffers into pinned memory (csrc/host_copy.cpp; no reference counterpart — arrow-rs
+ * buffers are handed to DataFusion in place).  kind: 0 memcpy, 1 AVX2 non-temporal, 2 AVX-512 non-temporal, -1 best the CPU has.
+ * Exposed so that the copy can be tested without a GPU.  Returns the kind that was used. */
+int ark_host_copy(void* dst, const void* src, int64_t n, int kind);
+
 #ifdef __cplusplus
 }
 #endif

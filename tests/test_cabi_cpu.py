@@ -141,3 +141,29 @@ def test_expr_config_and_evaluate_result_host_logic():
     assert s.get(0) == "test" and s.get(1) == "test"
     vec = EvaluateResult("Vec", ["a", "b"])
     assert vec.get(0) == "a" and vec.get(1) == "b" and vec.get(2) is None
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, -1])
+def test_host_copy_kinds_copy_exactly(lib, kind):
+    """The staging copy of pageable inputs (csrc/host_copy.cpp): every kind the CPU supports must copy byte-exactly for any
+    size, source misalignment (a sliced Arrow buffer) and destination misalignment, and must not touch bytes outside the
+    destination range.  Pure host code: runs without a GPU."""
+    import ctypes as C
+
+    import numpy as np
+
+    rng = np.random.default_rng(7)
+    src = rng.integers(0, 256, (6 << 20) + 512, dtype=np.uint8)
+    sizes = [0, 1, 63, 64, 65, 255, 4095, 4096, 4097, 4096 + 255, 65536 + 3, (4 << 20) - 64, (4 << 20) + 129]
+    used = set()
+    for n in sizes:
+        for s_off, d_off in ((0, 0), (8, 0), (3, 0), (0, 16), (5, 37), (64, 63)):
+            dst = np.full(n + 256, 0xA5, dtype=np.uint8)
+            got = lib.ark_host_copy(C.c_void_p(dst.ctypes.data + d_off), C.c_void_p(src.ctypes.data + s_off), n, kind)
+            assert got >= 0
+            used.add(got)
+            assert np.array_equal(dst[d_off:d_off + n], src[s_off:s_off + n]), (kind, n, s_off, d_off)
+            assert (dst[:d_off] == 0xA5).all() and (dst[d_off + n:] == 0xA5).all(), ("bytes outside the range were written", kind, n, s_off, d_off)
+    if kind == 0:
+        assert used == {0}
+    assert lib.ark_host_copy(None, None, 8, kind) == -1
