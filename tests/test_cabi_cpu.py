@@ -167,3 +167,27 @@ def test_host_copy_kinds_copy_exactly(lib, kind):
     if kind == 0:
         assert used == {0}
     assert lib.ark_host_copy(None, None, 8, kind) == -1
+
+
+def test_input_config_errors(lib):
+    """`generate` / `file` input builders (csrc/inputs.cu): config shape errors are serde-style `Error::Serialization`s as in the
+    reference (`input/generate.rs:30-43`, `input/file.rs:395-455`), formats this library does not decode are Unsupported — all
+    decided at construction, without a GPU."""
+    from arkflow_b200.input import FileInput, GenerateInput, build_input
+
+    GenerateInput({"context": "x", "interval": "1s", "batch_size": 3}).close()
+    GenerateInput({"context": "{}", "interval": "10ms"}).close()  # batch_size and count are optional
+    for cfg, frag in (({"interval": "1s"}, "missing field `context`"), ({"context": "x", "interval": "abc"}, "duration"),
+                      ({"context": "x", "interval": "1ms", "count": -1}, "count"), ({"context": "x"}, "interval")):
+        with pytest.raises(ArkError) as e:
+            GenerateInput(cfg)
+        assert e.value.kind == "Serialization" and frag in e.value.message, (cfg, e.value.message)
+    for cfg, kind, frag in (({"path": "/tmp/x.csv"}, "Serialization", "input_type"), ({"input_type": {"type": "csv"}}, "Serialization", "path"),
+                            ({"input_type": {"type": "xml", "path": "/tmp/x"}}, "Serialization", "unknown variant `xml`"),
+                            ({"input_type": {"type": "parquet", "path": "/tmp/x.parquet"}}, "Unsupported", "parquet")):
+        with pytest.raises(ArkError) as e:
+            FileInput(cfg)
+        assert e.value.kind == kind and frag in e.value.message, (cfg, e.value.message)
+    FileInput({"input_type": {"type": "csv", "path": "/nonexistent.csv"}}).close()  # the file is opened by connect(), as in the reference
+    with pytest.raises(ArkError):
+        build_input({"type": "kafka"})
